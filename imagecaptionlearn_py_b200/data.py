@@ -1,0 +1,221 @@
+"""Host-side batch marshalling: the py3 mirror of `nn_utils/data.py` for the hot path.
+
+`load_batch` returns the *same dict* (`batch_tensors`) the reference's `nn_utils/data.py:349-528` returns --
+same keys, shapes and integer contents (verified bit-for-bit against a loop restatement in the tests) -- but
+is built with vectorised NumPy gathers from a flat token table instead of per-word Python row copies, and in
+float32/int32 (what TensorFlow converts the feed to anyway, `nn_utils/core.py:288,294,348`).
+
+Also here: `build_model_filename` (`nn_utils/data.py:274-327`), the predict-time edge padding
+(`nn_utils/core.py:656-659`), and the relation / affinity enumeration helpers
+(`icl_relation_lstm.py:213-245`, `icl_affinity_lstm.py:24-74`).
+"""
+import numpy as np
+
+INDEX_NAMES = ("first_i_bw", "first_i_fw", "last_i_fw", "last_i_bw", "sent_last_i_fw", "sent_first_i_bw",
+               "first_j_bw", "last_j_fw", "first_j_fw", "last_j_bw", "sent_last_j_fw", "sent_first_j_bw")
+
+
+def _flat_table(data_dict):
+    """Cache: all caption matrices concatenated into one [N,E] float32 array + id -> (offset,len)."""
+    ft = data_dict.get("_flat")
+    if ft is None or ft[2] != len(data_dict["sentences"]):
+        offs, parts, pos = {}, [], 0
+        for sid, mat in data_dict["sentences"].items():
+            offs[sid] = (pos, len(mat))
+            parts.append(np.asarray(mat, dtype=np.float32))
+            pos += len(mat)
+        E = data_dict["word_embedding_width"]
+        flat = np.concatenate(parts, 0) if parts else np.zeros((0, E), np.float32)
+        ft = (flat, offs, len(data_dict["sentences"]))
+        data_dict["_flat"] = ft
+    return ft
+
+
+def load_batch(ids, data_dict, task, n_classes, packed=False):
+    """Vectorised equivalent of nn_utils/data.py:349-528.
+
+    packed=True additionally returns 'sentences_packed' [sum(len),E] (caption-major valid tokens) and skips
+    materialising the zero-padded 'sentences' tensor -- the fast path `core.run_op` understands."""
+    B = len(ids)
+    cross = task == "rel_cross"
+    n_seq = 2 * B if cross else B
+    T, E = data_dict["max_seq_len"], data_dict["word_embedding_width"]
+    flat, offs, _ = _flat_table(data_dict)
+    cap_of = data_dict["caption_ids"]
+
+    m_ids, b_ids = list(ids), None
+    if task == "affinity":
+        split = [s.split("|") for s in ids]
+        m_ids = [s[0] for s in split]
+        b_ids = [s[1] for s in split]
+    if cross:
+        sids = [c for m in m_ids for c in cap_of[m]]
+    elif task == "rel_intra":
+        sids = [cap_of[m][0] for m in m_ids]
+    else:
+        sids = [cap_of[m] for m in m_ids]
+    ol = np.array([offs[s] for s in sids], dtype=np.int64).reshape(n_seq, 2)
+    lens = ol[:, 1]
+    rows = np.repeat(np.arange(n_seq), lens)
+    starts = np.cumsum(lens) - lens
+    cols = np.arange(int(lens.sum())) - np.repeat(starts, lens)
+    src = np.repeat(ol[:, 0], lens) + cols
+
+    out = {}
+    if packed:
+        out["sentences_packed"] = flat[src]
+    else:
+        sent = np.zeros([n_seq, T, E], np.float32)
+        sent[rows, cols] = flat[src]
+        out["sentences"] = sent
+    out["seq_lengths"] = lens.astype(np.int32)
+
+    out["labels"] = np.stack([data_dict["labels"][i] for i in ids]).astype(np.float32).reshape(B, n_classes)
+    mi = np.array([data_dict["mention_indices"][m] for m in m_ids], dtype=np.int32)
+    ar = np.arange(B, dtype=np.int32)
+    si, sj = (2 * ar, 2 * ar + 1) if cross else (ar, ar)
+    zeros, ones = np.zeros(B, np.int32), np.ones(B, np.int32)
+
+    def rows3(d, s, w):
+        return np.stack([d, s, w.astype(np.int32)], 1)
+
+    for name in INDEX_NAMES:
+        out[name] = np.zeros([B, 3], np.int32)
+    out["first_i_fw"] = rows3(zeros, si, mi[:, 0])
+    out["first_i_bw"] = rows3(ones, si, mi[:, 0])
+    out["last_i_fw"] = rows3(zeros, si, mi[:, 1])
+    out["last_i_bw"] = rows3(ones, si, mi[:, 1])
+    if "rel" in task:
+        out["first_j_fw"] = rows3(zeros, sj, mi[:, 2])
+        out["first_j_bw"] = rows3(ones, sj, mi[:, 2])
+        out["last_j_fw"] = rows3(zeros, sj, mi[:, 3])
+        out["last_j_bw"] = rows3(ones, sj, mi[:, 3])
+    out["sent_last_i_fw"] = rows3(zeros, si, lens[si] - 1)
+    out["sent_first_i_bw"] = rows3(ones, si, zeros)
+    out["sent_last_j_fw"] = rows3(zeros, sj, lens[sj] - 1)
+    out["sent_first_j_bw"] = rows3(ones, sj, zeros)
+
+    feats = np.stack([data_dict["mention_features"][m] for m in m_ids]).astype(np.float32)
+    out["ij_feats" if "rel" in task else "m_feats"] = feats
+    if task == "affinity":
+        out["box_embeddings"] = _box_rows(b_ids, data_dict)
+        if data_dict.get("box_categories"):
+            bf = np.zeros([B, data_dict["n_box_feats"]], np.float32)
+            for i, b in enumerate(b_ids):
+                if b in data_dict["box_categories"]:
+                    bf[i] = data_dict["box_categories"][b]
+            out["b_feats"] = bf
+    return out
+
+
+def _box_rows(b_ids, data_dict):
+    """Box feature rows: from the in-memory table when present, else the per-image liblinear `.feats` files
+    the reference streams (nn_utils/data.py:506-524, utils/data.py:163-217; 1-based indices shifted by -1)."""
+    W = data_dict["box_embedding_width"]
+    table = data_dict.get("box_table")
+    out = np.zeros([len(b_ids), W], np.float32)
+    cache = data_dict.setdefault("_box_cache", {})
+    for i, b in enumerate(b_ids):
+        if table is not None and b in table:
+            out[i] = table[b]
+            continue
+        if b not in cache:
+            cache.clear()
+            img = b.split(";")[0]
+            cache.update(read_box_feats(data_dict["box_dir"] + "/" + img.replace(".jpg", ".feats"), W))
+        out[i] = cache[b]
+    return out
+
+
+def read_box_feats(path, width):
+    """liblinear line: '<label> <idx>:<val> ... # <id>' with 1-based indices (utils/data.py:163-217)."""
+    rows = {}
+    with open(path, "r") as f:
+        for line in f:
+            body, _, cid = line.partition("#")
+            vec = np.zeros(width, np.float32)
+            for tok in body.split()[1:]:
+                k, _, v = tok.partition(":")
+                vec[int(k) - 1] = float(v)
+            rows[cid.strip()] = vec
+    return rows
+
+
+def pad_ids_for_predict(ids, batch_size):
+    """nn_utils/core.py:656-659: pad = B*(n//B + 1) - n (>=1, a whole batch when n % B == 0), mode 'edge'."""
+    n = len(ids)
+    pad = batch_size * (n // batch_size + 1) - n
+    arr = np.pad(np.asarray(list(ids), dtype=object), (0, pad), "edge")
+    return arr.reshape([-1, batch_size]), pad
+
+
+def kv_str_to_dict(s):
+    """utils/string.py:132-145: 'k:v;k:v' -> dict."""
+    return dict(kv.split(":", 1) for kv in s.split(";"))
+
+
+def get_ij_pairs(mention_pairs):
+    """icl_relation_lstm.py:213-222."""
+    out = []
+    for p in mention_pairs:
+        d = kv_str_to_dict(p)
+        if d["caption_1"] == d["caption_2"] and int(d["mention_1"]) < int(d["mention_2"]):
+            out.append(p)
+    return out
+
+
+def induce_ji_predictions(pred_scores):
+    """icl_relation_lstm.py:225-245: add the mirrored pair with classes 2<->3 swapped (in place)."""
+    for ij in list(pred_scores.keys()):
+        d = kv_str_to_dict(ij)
+        ji = "doc:%s;caption_1:%s;mention_1:%s;caption_2:%s;mention_2:%s" % (
+            d["doc"], d["caption_2"], d["mention_2"], d["caption_1"], d["mention_1"])
+        s = np.array(pred_scores[ij], dtype=np.float64)
+        s[[2, 3]] = s[[3, 2]]
+        pred_scores[ji] = s
+    return pred_scores
+
+
+def get_valid_mention_box_pairs(data_dict):
+    """icl_affinity_lstm.py:59-74."""
+    loaded = set(data_dict["mention_indices"].keys())
+    return [mb for mb in data_dict["labels"].keys() if mb.split("|")[0] in loaded]
+
+
+def shuffle_mention_box_pairs(mention_box_pairs, rng=np.random):
+    """icl_affinity_lstm.py:24-56: images in random order, pairs shuffled within an image, grouped by image."""
+    by_img = {}
+    for mb in mention_box_pairs:
+        by_img.setdefault(mb.split("#")[0], []).append(mb)
+    imgs = list(by_img.keys())
+    rng.shuffle(imgs)
+    out = []
+    for im in imgs:
+        rng.shuffle(by_img[im])
+        out.extend(by_img[im])
+    return out
+
+
+def build_model_filename(arg_dict, task):
+    """nn_utils/data.py:274-327 -- hyper-parameters encoded in the model file name."""
+    name = arg_dict["data_root"] if "data_root" in arg_dict else arg_dict["data"] + "_" + arg_dict["split"]
+    if arg_dict.get("rel_type") is not None:
+        name += "_" + task.replace("_", "_" + arg_dict["rel_type"] + "_")
+    else:
+        name += "_" + task
+    enc = arg_dict.get("encoding_scheme")
+    name += {"first_last_sentence": "_fls", "first_last_mention": "_flm"}.get(enc, "")
+    name += "_%s_epch%d_lrn%s_btch%d_drp%d%d_lstm%d_hdn%d-%d_admEps%s" % (
+        arg_dict["activation"], int(arg_dict["epochs"]), str(arg_dict["learn_rate"]),
+        int(arg_dict["batch_size"]), int(arg_dict["lstm_input_dropout"] * 100), int(arg_dict["dropout"] * 100),
+        int(arg_dict["lstm_hidden_width"]), int(arg_dict["start_hidden_width"]), int(arg_dict["hidden_depth"]),
+        str(arg_dict["adam_epsilon"]))
+    if arg_dict.get("clip_norm") is not None:
+        name += "_clip" + str(arg_dict["clip_norm"])
+    if arg_dict.get("data_norm"):
+        name += "_dataNorm"
+    if arg_dict.get("weighted_classes"):
+        name += "_weighted"
+    if arg_dict.get("early_stopping"):
+        name += "_early"
+    return name + ".model"

@@ -1,0 +1,107 @@
+"""Host batch builder vs the loop oracle (bit-exact integers), enumeration helpers, predict padding."""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from imagecaptionlearn_py_b200 import data as D
+from imagecaptionlearn_py_b200 import synth
+from oracle import load_batch_oracle as LO
+
+
+@pytest.fixture(scope="module")
+def corpus():
+    return synth.make_corpus(6, seed=123, E=8, with_boxes=True, box_width=16, n_boxes=3)
+
+
+@pytest.mark.parametrize("task", ["nonvis", "card", "rel_intra", "rel_cross", "affinity"])
+def test_load_batch_bit_exact(corpus, task):
+    dd = synth.make_data_dict(corpus, task, F=12)
+    ids = synth.example_ids(dd, task)
+    rng = np.random.default_rng(0)
+    rng.shuffle(ids)
+    ids = ids[:17]
+    C = synth.N_CLASSES[task]
+    got = D.load_batch(ids, dd, task, C)
+    ref = LO.load_batch(ids, dd, task, C, box_lookup=lambda b: dd["box_table"][b] if task == "affinity" else None)
+    assert set(ref) <= set(got)
+    for k in ref:
+        assert got[k].shape == ref[k].shape, k
+        if k in LO.INDEX_NAMES or k in ("seq_lengths", "labels"):
+            assert np.array_equal(got[k].astype(np.int64), ref[k].astype(np.int64)), k
+        else:
+            assert np.array_equal(got[k].astype(np.float32), ref[k].astype(np.float32)), k
+    # packed form carries the same valid tokens
+    pk = D.load_batch(ids, dd, task, C, packed=True)
+    lens = got["seq_lengths"]
+    rows = np.concatenate([got["sentences"][s, :lens[s]] for s in range(len(lens))])
+    assert np.array_equal(pk["sentences_packed"], rows)
+
+
+def test_index_rows_in_range(corpus):
+    for task in ("nonvis", "rel_intra", "rel_cross"):
+        dd = synth.make_data_dict(corpus, task, F=4)
+        ids = synth.example_ids(dd, task)[:23]
+        b = D.load_batch(ids, dd, task, synth.N_CLASSES[task])
+        S = len(b["seq_lengths"])
+        for n in D.INDEX_NAMES:
+            m = b[n]
+            used = ("_j_" not in n) or task.startswith("rel")
+            if not used:
+                continue
+            assert m[:, 0].min() >= 0 and m[:, 0].max() <= 1
+            assert m[:, 1].max() < S
+            assert np.all(m[:, 2] < b["seq_lengths"][m[:, 1]]) and m[:, 2].min() >= 0
+        if task == "rel_cross":
+            assert np.array_equal(b["first_i_fw"][:, 1], 2 * np.arange(len(ids)))
+            assert np.array_equal(b["first_j_fw"][:, 1], 2 * np.arange(len(ids)) + 1)
+
+
+@settings(max_examples=50, deadline=None)
+@given(n=st.integers(1, 70), B=st.integers(1, 16))
+def test_predict_padding(n, B):
+    ids = ["id%d" % i for i in range(n)]
+    mat, pad = D.pad_ids_for_predict(ids, B)
+    ref, rpad = LO.pad_ids_for_predict(ids, B)
+    assert pad == rpad and 1 <= pad <= B and mat.shape == ref.shape
+    assert list(mat.ravel()) == list(ref.ravel())
+    flat = list(mat.ravel())
+    assert flat[:n] == ids and all(x == ids[-1] for x in flat[n:])
+    assert (mat.shape[0] - 1) * B + (B - pad) == n         # rows kept by core.py:673-677 == n
+
+
+def test_ij_ji_induction_is_involution(corpus):
+    dd = synth.make_data_dict(corpus, "rel_intra", F=4)
+    ids = synth.example_ids(dd, "rel_intra")
+    ij = D.get_ij_pairs(ids)
+    assert ij == LO.get_ij_pairs(ids) and 0 < len(ij) < len(ids)
+    rng = np.random.default_rng(0)
+    scores = {p: rng.random(4) for p in ij}
+    full = D.induce_ji_predictions(dict(scores))
+    ref = LO.induce_ji(scores)
+    assert len(full) == 2 * len(ij)
+    for k, v in ref.items():
+        assert np.array_equal(full[k], v)
+    again = D.induce_ji_predictions({k: full[k] for k in ref})
+    for p in ij:
+        assert np.array_equal(again[p], scores[p])
+
+
+def test_affinity_pairs_grouped_by_image(corpus):
+    dd = synth.make_data_dict(corpus, "affinity", F=4)
+    pairs = D.get_valid_mention_box_pairs(dd)
+    assert len(pairs) == len(dd["mention_indices"]) * 3
+    sh = D.shuffle_mention_box_pairs(pairs, np.random.default_rng(0))
+    assert sorted(sh) == sorted(pairs)
+    imgs = [p.split("#")[0] for p in sh]
+    changes = sum(1 for a, b in zip(imgs, imgs[1:]) if a != b)
+    assert changes == len(set(imgs)) - 1
+
+
+def test_model_filename():
+    a = dict(data_root="flickr30k_train", encoding_scheme="first_last_mention", activation="relu", epochs=100,
+             learn_rate=0.001, batch_size=512, lstm_input_dropout=0.5, dropout=0.5, lstm_hidden_width=200,
+             start_hidden_width=1024, hidden_depth=3, adam_epsilon=1e-08, clip_norm=5.0, data_norm=True,
+             weighted_classes=False, early_stopping=True, rel_type="intra")
+    assert D.build_model_filename(a, "rel_lstm") == (
+        "flickr30k_train_rel_intra_lstm_flm_relu_epch100_lrn0.001_btch512_drp5050_lstm200_hdn1024-3_"
+        "admEps1e-08_clip5.0_dataNorm_early.model")
