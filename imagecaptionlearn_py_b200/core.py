@@ -1,0 +1,460 @@
+"""Drop-in for the graph layer of the reference: `nn_utils/core.py`.
+
+Same function names, argument meaning and results as the reference, with the TensorFlow graph + `sess.run`
+(`nn_utils/core.py:625`) replaced by libicl_b200.so (hand-written sm_100a kernels, C-ABI in include/icl_b200.h):
+
+    setup_bidirectional_lstm(n_hidden, data_norm, n_embedding_width, n_parallel)          core.py:271-332
+    setup_core_architecture(task, encoding_scheme, batch_size, ...)                       core.py:443-514
+    add_train_op(loss, lrn_rate, adam_epsilon, clip_norm)                                 core.py:74-106
+    run_op(sess, op, batch_tensor_list, lstm_input_dropout, dropout, encoding_scheme,
+           tasks, scope_names, include_labels)                                            core.py:517-626
+    get_pred_scores_mcc(task, encoding_scheme, sess, batch_size, ids, data_dict, ...)     core.py:629-681
+    get_collection(name)[0], variable_scope(name), Session(), Saver()                     (the TF symbols the scripts touch)
+
+TF "collections" become entries of a module-level `Graph`; ops are `Op` handles ('train_op', 'loss', 'accuracy',
+'predicted_proba', 'pred', optionally '<scope>/...').  `run_op` takes the unchanged `batch_tensors` dicts of
+`nn_utils/data.py:load_batch` (float64 or float32, indices as float or int) and returns NumPy values of the
+shape/dtype the TF op would: train_op -> None, loss/accuracy -> float32 scalar, predicted_proba -> float32 [B,C],
+pred -> int64 [B].
+
+Multi-task (`icl_multitask_lstm.py`): the reference's joint path feeds only the last task's sentences to the shared
+LSTM (core.py:558-561 inside the loop at :544), which is a defect; here every task's sentences go through ONE
+shared-weight encoder pass (concatenated) and each head indexes its own slice -- the intended semantics.
+"""
+import contextlib
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _cabi
+from . import data as nn_data
+
+__all__ = ["set_random_seeds", "get_widths", "setup_bidirectional_lstm", "setup_core_architecture", "add_train_op",
+           "run_op", "get_pred_scores_mcc", "get_collection", "variable_scope", "reset_default_graph", "Session",
+           "Saver", "Op"]
+
+
+class Op(object):
+    def __init__(self, kind, scope=""):
+        self.kind, self.scope = kind, scope
+
+    def __repr__(self):
+        return "<icl op %s%s>" % (self.scope + "/" if self.scope else "", self.kind)
+
+
+class Graph(object):
+    def __init__(self):
+        self.lstm = None            # dict(n_hidden, data_norm, E)
+        self.heads = []             # list of dicts, in creation order
+        self.train = {}             # scope -> dict(lr, eps, clip)
+        self.scope_stack = []
+        self.seed = 20171201
+
+
+_graph = Graph()
+
+
+def reset_default_graph():
+    global _graph
+    _graph = Graph()
+
+
+def set_random_seeds(seed=20171201):
+    """core.py:10-18."""
+    import random
+    _graph.seed = seed
+    np.random.seed(seed)
+    random.seed(seed)
+
+
+@contextlib.contextmanager
+def variable_scope(name):
+    _graph.scope_stack.append(name)
+    try:
+        yield
+    finally:
+        _graph.scope_stack.pop()
+
+
+def _scope():
+    # only the task scope matters to the scripts ('bidirectional_lstm' is handled by name)
+    s = [x for x in _graph.scope_stack if x != "bidirectional_lstm"]
+    return "/".join(s)
+
+
+def get_collection(name):
+    """tf.get_collection(name) for the names the scripts use: '[<scope>/]loss|accuracy|train_op|predicted_proba|pred'."""
+    scope, _, kind = name.rpartition("/")
+    if kind in ("loss", "accuracy", "train_op", "predicted_proba", "pred"):
+        return [Op(kind, scope)]
+    return []
+
+
+def get_widths(start_width, depth, end_width=None):
+    """core.py:121-143 (depth d -> d+1 widths when end_width is None)."""
+    w = [int(start_width)]
+    if end_width is None:
+        for d in range(1, depth + 1):
+            w.append(int(w[d - 1] / 2))
+    else:
+        for d in range(1, depth):
+            w.append(int(max(w[d - 1] - end_width, 0) / 2 + end_width))
+        w.append(int(end_width))
+    return w
+
+
+def setup_bidirectional_lstm(n_hidden, data_norm=False, n_embedding_width=300, n_parallel=64):
+    """core.py:271-332.  n_parallel (TF while-loop parallel_iterations) has no meaning here and is ignored."""
+    _graph.lstm = dict(n_hidden=int(n_hidden), data_norm=bool(data_norm), E=int(n_embedding_width))
+
+
+def setup_core_architecture(task, encoding_scheme, batch_size, start_hidden_width, hidden_depth, weighted_classes,
+                            activation, n_classes, n_mention_feats, box_embedding_width=None, n_box_feats=None):
+    """core.py:443-514.  The head is registered under the current variable_scope (task name in multitask)."""
+    if task not in _cabi.TASKS or encoding_scheme not in _cabi.ENCODINGS:
+        raise ValueError("unknown task/encoding_scheme: %r %r" % (task, encoding_scheme))
+    _graph.heads.append(dict(task=task, encoding_scheme=encoding_scheme, batch_size=int(batch_size),
+                             widths=get_widths(start_hidden_width, hidden_depth), weighted=bool(weighted_classes),
+                             activation=activation, n_classes=int(n_classes), F=int(n_mention_feats),
+                             box_width=int(box_embedding_width or 0) if task == "affinity" else 0,
+                             n_box_feats=int(n_box_feats or 0) if task == "affinity" else 0, scope=_scope()))
+
+
+def add_train_op(loss, lrn_rate, adam_epsilon, clip_norm):
+    """core.py:74-106: Adam(lr, eps) with optional clip_by_global_norm.  One optimizer over all variables."""
+    _graph.train[_scope()] = dict(lr=float(lrn_rate), eps=float(adam_epsilon),
+                                  clip=-1.0 if clip_norm is None else float(clip_norm))
+
+
+class Session(object):
+    """Stands in for tf.Session: owns the device model (parameters, Adam state, workspaces)."""
+
+    def __init__(self, graph=None, max_seq_len=64, device=None, gemm_mode=_cabi.GEMM_TCGEN05_TF32, dist=None, seed=None):
+        self.graph = graph or _graph
+        self.max_seq_len = int(max_seq_len)
+        self.gemm_mode = gemm_mode
+        self.dist = dist                 # None or a torch.distributed process group marker (True = default group)
+        self.device = device
+        self.handle = None
+        self.run_counter = 0
+        self.base_seed = self.graph.seed if seed is None else seed
+        self._grad_view = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def close(self):
+        if self.handle is not None:
+            _cabi.lib().icl_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- model construction ------------------------------------------------------------------------------------------
+    def _config(self):
+        g = self.graph
+        if g.lstm is None or not g.heads:
+            raise RuntimeError("setup_bidirectional_lstm / setup_core_architecture must be called first")
+        cfg = _cabi.Config()
+        cfg.embed_width, cfg.lstm_hidden, cfg.data_norm = g.lstm["E"], g.lstm["n_hidden"], int(g.lstm["data_norm"])
+        cfg.max_seqs = sum(h["batch_size"] * (2 if h["task"] == "rel_cross" else 1) for h in g.heads)
+        cfg.max_seq_len = self.max_seq_len
+        cfg.n_heads = len(g.heads)
+        for i, h in enumerate(g.heads):
+            hc = cfg.heads[i]
+            hc.task, hc.encoding = _cabi.TASKS[h["task"]], _cabi.ENCODINGS[h["encoding_scheme"]]
+            hc.batch_size, hc.n_classes, hc.n_feats = h["batch_size"], h["n_classes"], h["F"]
+            hc.box_width, hc.n_box_feats = h["box_width"], h["n_box_feats"]
+            hc.n_hidden = len(h["widths"])
+            for k, w in enumerate(h["widths"]):
+                hc.widths[k] = w
+            hc.activation = _cabi.ACTIVATIONS[h["activation"]]
+            hc.weighted_classes = int(h["weighted"])
+            hc.scope = h["scope"].encode()
+        tr = next(iter(g.train.values())) if g.train else dict(lr=1e-3, eps=1e-8, clip=-1.0)
+        cfg.learn_rate, cfg.adam_epsilon, cfg.clip_norm = tr["lr"], tr["eps"], tr["clip"]
+        cfg.beta1, cfg.beta2 = 0.9, 0.999
+        if self.device is None:
+            import os
+            self.device = int(os.environ.get("LOCAL_RANK", "0"))
+        cfg.device, cfg.gemm_mode = self.device, self.gemm_mode
+        return cfg
+
+    def _create(self, state=None):
+        cfg = self._config()
+        h = C.c_void_p()
+        _cabi.check(_cabi.lib().icl_create(C.byref(cfg), C.byref(h)))
+        self.handle = h
+        self._grad_view = None
+        if state is None:
+            self.initialize()
+        else:
+            self.load_state(state)
+
+    def ensure(self, T=None):
+        if T is not None and T > self.max_seq_len:
+            state = self.state_dict() if self.handle is not None else None
+            self.close()
+            self.max_seq_len = int(T)
+            self._create(state)
+        elif self.handle is None:
+            self._create()
+
+    def param_info(self):
+        L = _cabi.lib()
+        out = []
+        for i in range(L.icl_param_count(self.handle)):
+            name, r, c, off = C.c_char_p(), C.c_int32(), C.c_int32(), C.c_int64()
+            _cabi.check(L.icl_param_info(self.handle, i, C.byref(name), C.byref(r), C.byref(c), C.byref(off)))
+            out.append((name.value.decode(), r.value, c.value, off.value))
+        return out
+
+    def initialize(self):
+        """global_variables_initializer: glorot-uniform LSTM kernels + zero bias (TF default), the reference's Xavier
+        rule for the heads (core.py:32-36,59-63).  TF's Philox stream cannot be reproduced; parity tests inject weights."""
+        rng = np.random.RandomState(self.graph.seed % (2 ** 32))
+        for name, r, c, _ in self.param_info():
+            if name.endswith("basic_lstm_cell/bias"):
+                v = np.zeros((r, c), np.float32)
+            else:
+                lim = math.sqrt(6.0 / (r + c))
+                v = rng.uniform(-lim, lim, (r, c)).astype(np.float32)
+            self.set_tensor(name, v)
+
+    def get_tensor(self, name, kind=0):
+        for n, r, c, _ in self.param_info():
+            if n == name:
+                out = np.empty((r, c), np.float32)
+                _cabi.check(_cabi.lib().icl_get_tensor(self.handle, kind, name.encode(), _cabi.np_ptr(out)))
+                return out
+        raise KeyError(name)
+
+    def set_tensor(self, name, value, kind=0):
+        v = np.ascontiguousarray(np.asarray(value, dtype=np.float32))
+        _cabi.check(_cabi.lib().icl_set_tensor(self.handle, kind, name.encode(), _cabi.np_ptr(v)))
+
+    def state_dict(self):
+        st = {}
+        for n, _, _, _ in self.param_info():
+            st[n] = self.get_tensor(n, 0)
+            st["adam_m/" + n] = self.get_tensor(n, 2)
+            st["adam_v/" + n] = self.get_tensor(n, 3)
+        t = C.c_int64()
+        _cabi.check(_cabi.lib().icl_get_step(self.handle, C.byref(t)))
+        st["adam_step"] = np.int64(t.value)
+        return st
+
+    def load_state(self, st):
+        for n, r, c, _ in self.param_info():
+            if n in st:
+                self.set_tensor(n, np.asarray(st[n]).reshape(r, c), 0)
+            if "adam_m/" + n in st:
+                self.set_tensor(n, np.asarray(st["adam_m/" + n]).reshape(r, c), 2)
+                self.set_tensor(n, np.asarray(st["adam_v/" + n]).reshape(r, c), 3)
+        if "adam_step" in st:
+            _cabi.check(_cabi.lib().icl_set_step(self.handle, int(st["adam_step"])))
+
+    # -- execution ---------------------------------------------------------------------------------------------------
+    def _bind_stream(self):
+        try:
+            import torch
+            if torch.cuda.is_available():
+                torch.cuda.set_device(self.device)
+                _cabi.lib().icl_set_stream(self.handle, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        except ImportError:
+            pass
+
+    def grad_tensor(self):
+        """torch view of the flat device gradient buffer (for the NCCL all-reduce)."""
+        if self._grad_view is None:
+            import torch
+            p, n = C.c_void_p(), C.c_int64()
+            _cabi.check(_cabi.lib().icl_grad_buffer(self.handle, C.byref(p), C.byref(n)))
+
+            class _Arr(object):
+                __cuda_array_interface__ = dict(shape=(n.value,), typestr="<f4", data=(p.value, False), version=2)
+            self._grad_view = torch.as_tensor(_Arr(), device="cuda:%d" % self.device)
+        return self._grad_view
+
+    def build_batch(self, batch_tensor_list, include_labels, keepalive):
+        g = self.graph
+        b = _cabi.Batch()
+        first = batch_tensor_list[0]
+        packed = "sentences_packed" in first
+        sents, lens = [], []
+        off = 0
+        b.n_heads = len(batch_tensor_list)
+        T = 0
+        for i, bt in enumerate(batch_tensor_list):
+            hb = b.heads[i]
+            hb.sent_offset = off
+            ln = np.asarray(bt["seq_lengths"])
+            lens.append(ln)
+            s = bt["sentences_packed"] if packed else bt["sentences"]
+            sents.append(s)
+            if not packed:
+                T = max(T, s.shape[1])
+            off += len(ln)
+            task = g.heads[i]["task"]
+            idxs = []
+            for k, name in enumerate(_cabi.INDEX_ORDER):
+                if name in bt:
+                    a = _cabi.as_supported(bt[name])
+                    idxs.append(a)
+                else:
+                    idxs.append(None)
+            dts = set(a.dtype for a in idxs if a is not None)
+            if len(dts) > 1:
+                idxs = [None if a is None else a.astype(np.float64) for a in idxs]
+            for k, a in enumerate(idxs):
+                if a is not None:
+                    keepalive.append(a)
+                    hb.idx[k] = a.ctypes.data
+                    hb.idx_dtype = _cabi.dtype_code(a)
+
+            def put(field, key):
+                if key in bt and bt[key] is not None:
+                    a = _cabi.as_supported(bt[key])
+                    keepalive.append(a)
+                    setattr(hb, field, a.ctypes.data)
+                    setattr(hb, field + "_dtype", _cabi.dtype_code(a))
+            put("feats", "ij_feats" if "rel" in task else "m_feats")
+            if task == "affinity":
+                put("box", "box_embeddings")
+                put("bfeats", "b_feats")
+            if include_labels:
+                put("labels", "labels")
+        if len(sents) == 1:
+            x = _cabi.as_supported(sents[0])
+            ln = _cabi.as_supported(lens[0])
+        else:
+            if not packed:
+                Tm = max(s.shape[1] for s in sents)
+                sents = [np.pad(s, ((0, 0), (0, Tm - s.shape[1]), (0, 0))) for s in sents]
+            x = _cabi.as_supported(np.concatenate(sents, 0))
+            ln = _cabi.as_supported(np.concatenate(lens, 0))
+        if x.dtype.kind != "f":
+            x = x.astype(np.float32)
+        keepalive += [x, ln]
+        b.sentences, b.sent_dtype, b.sent_packed = x.ctypes.data, _cabi.dtype_code(x), int(packed)
+        b.seq_lengths, b.len_dtype = ln.ctypes.data, _cabi.dtype_code(ln)
+        b.n_seqs = len(ln)
+        b.padded_T = T if not packed else int(ln.max()) if len(ln) else 0
+        rank = 0
+        if self.dist:
+            import torch.distributed as td
+            rank = td.get_rank()
+        b.seq_gid_offset = rank * b.n_seqs
+        b.ex_gid_offset = rank * max(h["batch_size"] for h in g.heads)
+        return b
+
+    def run(self, op_kind, batch_tensor_list, keep_in, keep, include_labels, want=("proba", "pred")):
+        L = _cabi.lib()
+        g = self.graph
+        if len(batch_tensor_list) != len(g.heads):
+            raise ValueError("got %d batches for %d heads" % (len(batch_tensor_list), len(g.heads)))
+        keepalive = []
+        need_T = max((bt["sentences"].shape[1] if "sentences" in bt else int(np.max(bt["seq_lengths"])))
+                     for bt in batch_tensor_list)
+        self.ensure(need_T)
+        b = self.build_batch(batch_tensor_list, include_labels, keepalive)
+        self._bind_stream()
+        outs = (_cabi.HeadOut * _cabi.MAX_HEADS)()
+        res = []
+        for i, h in enumerate(g.heads):
+            pr = np.empty((h["batch_size"], h["n_classes"]), np.float32)
+            pd = np.empty((h["batch_size"],), np.int64)
+            outs[i].proba = pr.ctypes.data_as(C.POINTER(C.c_float))
+            outs[i].pred = pd.ctypes.data_as(C.POINTER(C.c_int64))
+            res.append([pr, pd])
+        self.run_counter += 1
+        seed = (self.base_seed * 1000003 + self.run_counter) & 0xFFFFFFFFFFFFFFFF
+        self.last_seed = seed
+        if op_kind == _cabi.OP_TRAIN and self.dist:
+            import torch.distributed as td
+            _cabi.check(L.icl_upload(self.handle, C.byref(b)))
+            _cabi.check(L.icl_run_resident(self.handle, _cabi.OP_GRADS, keep_in, keep, seed))
+            td.all_reduce(self.grad_tensor(), op=td.ReduceOp.SUM)       # loss is a SUM over examples (core.py:267)
+            _cabi.check(L.icl_apply_update(self.handle))
+            _cabi.check(L.icl_fetch(self.handle, outs))
+        else:
+            _cabi.check(L.icl_run(self.handle, op_kind, C.byref(b), keep_in, keep, seed, outs))
+        return [dict(proba=r[0], pred=r[1], loss=np.float32(outs[i].loss), accuracy=np.float32(outs[i].accuracy))
+                for i, r in enumerate(res)]
+
+
+def run_op(sess, op, batch_tensor_list, lstm_input_dropout, dropout, encoding_scheme, tasks, scope_names,
+           include_labels=False):
+    """core.py:517-626.  `tasks`/`scope_names` must list the heads in the order they were set up (as the
+    reference's scripts do); `encoding_scheme` was fixed at setup time and is checked, not re-applied."""
+    g = sess.graph
+    if [h["task"] for h in g.heads] != list(tasks):
+        raise ValueError("run_op tasks %r do not match the graph's heads %r" % (tasks, [h["task"] for h in g.heads]))
+    for h in g.heads:
+        if h["encoding_scheme"] != encoding_scheme:
+            raise ValueError("encoding_scheme differs from the one the graph was built with")
+    kind = {"train_op": _cabi.OP_TRAIN}.get(op.kind, _cabi.OP_PREDICT)
+    if kind == _cabi.OP_TRAIN and not include_labels:
+        raise ValueError("train_op needs include_labels=True")
+    res = sess.run(kind, batch_tensor_list, float(lstm_input_dropout), float(dropout), include_labels)
+    if op.kind == "train_op":
+        return None
+    scopes = [h["scope"] for h in g.heads]
+    if op.kind == "loss" and op.scope == "" and len(g.heads) > 1:
+        return np.float32(sum(r["loss"] for r in res))       # simple_joint: sum of the task losses
+    i = scopes.index(op.scope) if op.scope in scopes else 0
+    return res[i][{"predicted_proba": "proba"}.get(op.kind, op.kind)]
+
+
+def get_pred_scores_mcc(task, encoding_scheme, sess, batch_size, ids, data_dict, n_classes, log=None):
+    """core.py:629-681: edge-pad ids to a multiple of B (always >= 1 pad), predict with keep-probs 1.0, keep the
+    first B-pad rows of the last batch."""
+    pred_scores = dict()
+    id_matrix, pad = nn_data.pad_ids_for_predict(list(ids), batch_size)
+    scope = _scope()
+    for i in range(id_matrix.shape[0]):
+        if log is not None:
+            log.log_status('info', None, 'Predicting; %d batches complete (%.2f%%)', i, 100.0 * i / id_matrix.shape[0])
+        bt = nn_data.load_batch(list(id_matrix[i]), data_dict, task, n_classes)
+        scores = run_op(sess, Op("predicted_proba", scope), [bt], 1.0, 1.0, encoding_scheme, [task], [scope], False)
+        n_rows = len(scores) if i < id_matrix.shape[0] - 1 else batch_size - pad
+        for j in range(n_rows):
+            pred_scores[id_matrix[i][j]] = scores[j].copy()
+    return pred_scores, data_dict['labels']
+
+
+class Saver(object):
+    """tf.train.Saver stand-in (icl_core_lstm.py:107,155,393-394): one .npz keyed by the TF variable names,
+    plus the Adam moments and step so training can resume."""
+
+    def __init__(self, max_to_keep=100):
+        pass
+
+    def save(self, sess, path):
+        sess.ensure()
+        np.savez(path + ".npz", **sess.state_dict())
+        return path
+
+    def restore(self, sess, path):
+        sess.ensure()
+        with np.load(path + ".npz") as z:
+            sess.load_state({k: z[k] for k in z.files})
+
+
+def _debug_mask(sess, stream, n, keep, seed=None):
+    """Test hook: the 0/1 dropout mask the kernels derive for elements [0,n) of `stream` (see csrc/icl_kernels.cuh)."""
+    out = np.empty(int(n), np.float32)
+    _cabi.check(_cabi.lib().icl_debug_mask(sess.handle, C.c_uint64(sess.last_seed if seed is None else seed),
+                                           C.c_uint32(stream), 0, int(n), float(keep), _cabi.np_ptr(out)))
+    return out
+
+
+Session.debug_mask = _debug_mask

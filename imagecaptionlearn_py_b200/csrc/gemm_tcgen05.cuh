@@ -1,0 +1,275 @@
+// TF32 GEMM on the 5th-gen tensor cores (sm_100a): TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory
+// -> tcgen05.mma.kind::tf32 with the fp32 accumulator in TMEM -> tcgen05.ld epilogue.
+//
+//   C[M,N] = epilogue( A * B ),  fp32 in HBM on both sides (kind::tf32 reads the fp32 containers directly).
+//   A: K-major ([M,K], k contiguous) or MN-major ([K,M], m contiguous); B likewise ([N,K] or [K,N]).
+// Both majors are needed without transposes: forward layers are (K, MN), input-gradient GEMMs are (K, K) and the
+// time-batched weight-gradient GEMMs (contraction over tokens) are (MN, MN).
+//
+// One 128x128 output tile per CTA, BK = 32 fp32 (one 128-byte swizzle row), 3-stage mbarrier pipeline.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2-5 = epilogue.
+// ~97 KB of shared memory -> two CTAs per SM, so one CTA's epilogue overlaps the other's main loop.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <tuple>
+
+#include "icl_kernels.cuh"
+
+namespace icl {
+
+constexpr int TG_BM = 128, TG_BN = 128, TG_BK = 32, TG_STAGES = 3;
+constexpr int TG_TILE_BYTES = TG_BM * TG_BK * 4;                       // 16 KB per operand per stage
+constexpr int TG_SMEM = TG_STAGES * 2 * TG_TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TG_THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < (1u << 24); it++) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives TMEM lane (base+i), columns [c, c+32)
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t r[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (tcgen05 "SmemDescriptor"): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+//  K-major tile  [rows][32 fp32]: 8-row groups are 1024 B apart (SBO); LBO unused for swizzled K-major (1).
+//  MN-major tile [mn/32][k][32 fp32]: 128-byte MN blocks are LBO apart, 8-k groups 1024 B apart (SBO).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor: c_format F32 (1) [4,6); a/b format [7,10)/[10,13) (F16=0, BF16=1, TF32=2);
+// a_major [15], b_major [16] (1 = MN-major); N>>3 [17,23); M>>4 [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, bool a_mn, bool b_mn, int M, int N) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA,
+                                                             const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t sA = base, sB = base + TG_STAGES * TG_TILE_BYTES;
+  const uint32_t bars = sB + TG_STAGES * TG_TILE_BYTES;
+  const uint32_t full0 = bars, empty0 = bars + 8 * TG_STAGES, tmem_full = bars + 16 * TG_STAGES, tmem_slot = tmem_full + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TG_BM, n0 = blockIdx.x * TG_BN;
+  const int num_kb = (g.K + TG_BK - 1) / TG_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TG_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TG_BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_acc;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {                                                   // ---- TMA producer
+      for (int kb = 0; kb < num_kb; kb++) {
+        const int s = kb % TG_STAGES;
+        mbar_wait(empty0 + 8 * s, ((kb / TG_STAGES) & 1) ^ 1);
+        const uint32_t fb = full0 + 8 * s;
+        mbar_expect_tx(fb, 2 * TG_TILE_BYTES);                         // OOB parts of a box are zero-filled and still counted
+        const uint32_t a = sA + s * TG_TILE_BYTES, b = sB + s * TG_TILE_BYTES;
+        if (A_MN) {
+#pragma unroll
+          for (int j = 0; j < TG_BM / 32; j++) tma_load_2d(a + j * (32 * TG_BK * 4), &tmA, m0 + 32 * j, kb * TG_BK, fb);
+        } else {
+          tma_load_2d(a, &tmA, kb * TG_BK, m0, fb);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int j = 0; j < TG_BN / 32; j++) tma_load_2d(b + j * (32 * TG_BK * 4), &tmB, n0 + 32 * j, kb * TG_BK, fb);
+        } else {
+          tma_load_2d(b, &tmB, kb * TG_BK, n0, fb);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                                                   // ---- MMA issuer (one thread)
+      constexpr uint32_t idesc = make_idesc(2, A_MN, B_MN, TG_BM, TG_BN);
+      for (int kb = 0; kb < num_kb; kb++) {
+        const int s = kb % TG_STAGES;
+        mbar_wait(full0 + 8 * s, (kb / TG_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a = sA + s * TG_TILE_BYTES, b = sB + s * TG_TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < TG_BK / 8; kk++) {                       // UMMA_K = 8 for tf32
+          const uint64_t ad = A_MN ? make_smem_desc(a + kk * 1024, 32 * TG_BK * 4, 1024) : make_smem_desc(a + kk * 32, 16, 1024);
+          const uint64_t bd = B_MN ? make_smem_desc(b + kk * 1024, 32 * TG_BK * 4, 1024) : make_smem_desc(b + kk * 32, 16, 1024);
+          tc_mma_tf32(tmem_acc, ad, bd, idesc, (kb | kk) != 0);
+        }
+        tc_commit(empty0 + 8 * s);                                     // frees the smem stage when these MMAs retire
+      }
+      tc_commit(tmem_full);
+    }
+  } else {                                                             // ---- epilogue: TMEM -> registers -> HBM
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;                                            // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int m = m0 + q * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < TG_BN; c += 32) {
+      uint32_t r[32];
+      tc_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + c, r);
+      if (m < g.M) {
+        float* crow = g.C + (long)m * g.ldc;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          const int n = n0 + c + j;
+          if (n < g.N) {
+            float cold = g.epi.beta != 0.0f ? crow[n] : 0.0f;
+            crow[n] = epilogue_apply(g.epi, __uint_as_float(r[j]), m, n, g.N, cold);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(TG_BN) : "memory");
+  }
+}
+
+// ----------------------------------------------------------------------------- host side: tensor maps + launch
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+static int tcgen05_gemm_init() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return -1;
+  g_encode = (PFN_encodeTiled)fn;
+  cudaFuncSetAttribute(k_gemm_tcgen05<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM);
+  cudaFuncSetAttribute(k_gemm_tcgen05<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM);
+  cudaFuncSetAttribute(k_gemm_tcgen05<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM);
+  cudaFuncSetAttribute(k_gemm_tcgen05<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+struct TmaCache {
+  std::map<std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t, uint32_t>, CUtensorMap> maps;
+  // 2-D fp32 tensor: dim0 (contiguous) x dim1 with row pitch ld (floats); box = box0 x box1, 128B swizzle, zero OOB fill
+  int get(const float* ptr, uint64_t dim0, uint64_t dim1, uint64_t ld, uint32_t box0, uint32_t box1, CUtensorMap* out) {
+    auto key = std::make_tuple((const void*)ptr, dim0, dim1, ld, box0, box1);
+    auto it = maps.find(key);
+    if (it != maps.end()) { *out = it->second; return 0; }
+    cuuint64_t dims[2] = {dim0, dim1};
+    cuuint64_t strides[1] = {ld * 4};
+    cuuint32_t box[2] = {box0, box1};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMap tm;
+    CUresult r = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return (int)r;
+    if (maps.size() > 4096) maps.clear();
+    maps[key] = tm;
+    *out = tm;
+    return 0;
+  }
+};
+
+static bool tcgen05_gemm_supported(const GemmArgs& g, bool a_mn, bool b_mn) {
+  // TMA: 16-byte aligned base and row pitch; tiny problems stay on the SIMT kernel
+  if (((uintptr_t)g.A & 15) || ((uintptr_t)g.B & 15) || (g.lda & 3) || (g.ldb & 3)) return false;
+  if (g.N < 16 || g.M < 16 || g.K < 8) return false;
+  (void)a_mn; (void)b_mn;
+  return true;
+}
+
+static int tcgen05_gemm_launch(TmaCache& cache, cudaStream_t st, bool a_mn, bool b_mn, const GemmArgs& g) {
+  CUtensorMap ta, tb;
+  int r;
+  if (a_mn) r = cache.get(g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda, 32, TG_BK, &ta);
+  else r = cache.get(g.A, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)g.lda, TG_BK, TG_BM, &ta);
+  if (r) return 1000 + r;
+  if (b_mn) r = cache.get(g.B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb, 32, TG_BK, &tb);
+  else r = cache.get(g.B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb, TG_BK, TG_BN, &tb);
+  if (r) return 2000 + r;
+  dim3 grid((g.N + TG_BN - 1) / TG_BN, (g.M + TG_BM - 1) / TG_BM);
+  if (!a_mn && !b_mn) k_gemm_tcgen05<false, false><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, g);
+  else if (!a_mn && b_mn) k_gemm_tcgen05<false, true><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, g);
+  else if (a_mn && b_mn) k_gemm_tcgen05<true, true><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, g);
+  else k_gemm_tcgen05<true, false><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, g);
+  return cudaGetLastError() == cudaSuccess ? 0 : 3000;
+}
+
+}  // namespace icl

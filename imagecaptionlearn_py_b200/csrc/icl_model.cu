@@ -1,0 +1,676 @@
+// libicl_b200.so -- host orchestration + C-ABI (include/icl_b200.h) for the BiLSTM + mention-span-head path.
+// Replaces the TF graph built by nn_utils/core.py:271-514,74-106 and executed by sess.run (core.py:625).
+#include "../../include/icl_b200.h"
+#include "icl_kernels.cuh"
+#include "gemm_tcgen05.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace icl;
+
+static thread_local char g_err[1024] = "";
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return -1;
+}
+#define CK(x)                                                                                         \
+  do {                                                                                                \
+    cudaError_t e_ = (x);                                                                             \
+    if (e_ != cudaSuccess) return fail("%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
+  } while (0)
+#define CKI(x)                  \
+  do {                          \
+    int r_ = (x);               \
+    if (r_ != 0) return r_;     \
+  } while (0)
+
+struct Param { std::string name; int rows, cols; int64_t off; };
+
+struct Head {
+  icl_head_config c;
+  int D0 = 0, D0g = 0;               // input width; width of the prefix that carries gathered LSTM columns
+  std::vector<int> dims;             // D0, w1..wL, C
+  std::vector<int> pW, pB;           // param indices per layer (L hidden + softmax)
+  SlotTable slots;                   // device pointers filled at create
+  std::vector<int> slot_index_id;    // per slot: index-matrix id or -1
+  float *bi = nullptr, *dbi = nullptr, *dA = nullptr, *dBuf = nullptr;
+  std::vector<float*> act;           // y_k [B,w_k]
+  float *proba = nullptr, *dlogits = nullptr, *row_loss = nullptr, *row_correct = nullptr, *scalars = nullptr;
+  long long* pred = nullptr;
+  int* idx[ICL_N_INDEX] = {};
+  float *feats = nullptr, *box = nullptr, *bfeats = nullptr, *labels = nullptr;
+  bool has_labels = false;
+  // pinned staging
+  int* h_idx = nullptr; float* h_dense = nullptr; float* h_out = nullptr; long long* h_pred = nullptr;
+  size_t h_dense_floats = 0;
+};
+
+struct icl_model {
+  icl_config cfg;
+  int E, H, S_cap, T_cap;
+  long Np_cap, Ntok_cap;
+  std::vector<Param> params;
+  std::map<std::string, int> pindex;
+  int64_t n_params = 0;
+  float *P = nullptr, *G = nullptr, *M = nullptr, *V = nullptr;
+  int pK[2], pBias[2];
+  int64_t step = 0;
+  // workspaces
+  float *xraw = nullptr, *xd[2] = {}, *Z[2] = {}, *HP[2] = {}, *CP[2] = {}, *dHout[2] = {}, *dhrec[2] = {}, *dcc[2] = {};
+  int *d_order = nullptr, *d_start = nullptr, *d_lens = nullptr, *d_tokseq = nullptr, *d_tokstart = nullptr;
+  float* h_x = nullptr; int* h_ints = nullptr;         // pinned
+  double* d_partial = nullptr; float* d_gnorm = nullptr;
+  std::vector<Head> heads;
+  // resident batch
+  int S = 0, Tmax = 0; long Ntok = 0, Np = 0;
+  int64_t seq_gid0 = 0, ex_gid0 = 0;
+  std::vector<int> n_active;
+  bool resident = false;
+  cudaStream_t stream = nullptr, aux = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  int64_t launches = 0;
+  float last_ms = 0.f;
+  TmaCache tma;
+};
+
+// ----------------------------------------------------------------------------- small helpers
+static double read_num(const void* p, int dtype, size_t i) {
+  switch (dtype) {
+    case ICL_F32: return ((const float*)p)[i];
+    case ICL_F64: return ((const double*)p)[i];
+    case ICL_I32: return ((const int32_t*)p)[i];
+    default: return (double)((const int64_t*)p)[i];
+  }
+}
+static void to_f32(float* dst, const void* src, int dtype, size_t n) {
+  if (dtype == ICL_F32) { memcpy(dst, src, n * sizeof(float)); return; }
+  if (dtype == ICL_F64) { const double* s = (const double*)src; for (size_t i = 0; i < n; i++) dst[i] = (float)s[i]; return; }
+  for (size_t i = 0; i < n; i++) dst[i] = (float)read_num(src, dtype, i);
+}
+
+static void slot_plan(const icl_head_config& c, std::vector<int>& kinds /*index id or -1..-3*/) {
+  // nn_utils/core.py:377-433.  -1 feats, -2 box, -3 bfeats
+  kinds = {ICL_FIRST_I_BW, ICL_LAST_I_FW};
+  if (c.encoding == ICL_ENC_FIRST_LAST_SENTENCE) { kinds.push_back(ICL_SENT_LAST_I_FW); kinds.push_back(ICL_SENT_FIRST_I_BW); }
+  else { kinds.push_back(ICL_FIRST_I_FW); kinds.push_back(ICL_LAST_I_BW); }
+  bool rel = c.task == ICL_TASK_REL_INTRA || c.task == ICL_TASK_REL_CROSS;
+  if (rel) {
+    kinds.push_back(ICL_FIRST_J_BW); kinds.push_back(ICL_LAST_J_FW); kinds.push_back(-1);
+    if (c.encoding == ICL_ENC_FIRST_LAST_SENTENCE && c.task == ICL_TASK_REL_CROSS) { kinds.push_back(ICL_SENT_LAST_J_FW); kinds.push_back(ICL_SENT_FIRST_J_BW); }
+    else if (c.encoding == ICL_ENC_FIRST_LAST_MENTION) { kinds.push_back(ICL_FIRST_J_FW); kinds.push_back(ICL_LAST_J_BW); }
+  } else {
+    kinds.push_back(-1);
+    if (c.task == ICL_TASK_AFFINITY) { kinds.push_back(-2); if (c.n_box_feats > 0) kinds.push_back(-3); }
+  }
+}
+
+static int add_param(icl_model* m, const std::string& name, int rows, int cols) {
+  Param p{name, rows, cols, m->n_params};
+  m->n_params += ((int64_t)rows * cols + 3) / 4 * 4;        // keep every tensor 16-byte aligned
+  m->pindex[name] = (int)m->params.size();
+  m->params.push_back(p);
+  return (int)m->params.size() - 1;
+}
+
+template <typename T> static cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
+
+// ----------------------------------------------------------------------------- GEMM dispatch
+static int gemm(icl_model* m, cudaStream_t st, bool a_mn, bool b_mn, const GemmArgs& g, int force_mode = -1) {
+  int mode = force_mode >= 0 ? force_mode : m->cfg.gemm_mode;
+  bool gathers = g.amap.mode != 0 || g.cmap.mode != 0;
+  if (mode == ICL_GEMM_TCGEN05_TF32 && !gathers && tcgen05_gemm_supported(g, a_mn, b_mn)) {
+    int r = tcgen05_gemm_launch(m->tma, st, a_mn, b_mn, g);
+    if (r != 0) return fail("tcgen05 gemm launch failed (%d): %s", r, cudaGetErrorString(cudaGetLastError()));
+    m->launches++;
+    return 0;
+  }
+  dim3 grid((g.N + 63) / 64, (g.M + 63) / 64);
+  if (!a_mn && !b_mn) k_gemm_simt<true, true><<<grid, 256, 0, st>>>(g);
+  else if (!a_mn && b_mn) k_gemm_simt<true, false><<<grid, 256, 0, st>>>(g);
+  else if (a_mn && b_mn) k_gemm_simt<false, false><<<grid, 256, 0, st>>>(g);
+  else k_gemm_simt<false, true><<<grid, 256, 0, st>>>(g);
+  m->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static GemmArgs mk_gemm(const float* A, long lda, const float* B, long ldb, float* C, long ldc, int M, int N, int K) {
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
+  g.epi.drop.keep = 1.0f;
+  return g;
+}
+
+// ----------------------------------------------------------------------------- API
+extern "C" const char* icl_last_error(void) { return g_err; }
+extern "C" int icl_version(void) { return 1; }
+
+extern "C" void icl_destroy(icl_model* m) {
+  if (!m) return;
+  cudaDeviceSynchronize();
+  auto F = [](void* p) { if (p) cudaFree(p); };
+  F(m->P); F(m->G); F(m->M); F(m->V); F(m->xraw);
+  for (int d = 0; d < 2; d++) { F(m->xd[d]); F(m->Z[d]); F(m->HP[d]); F(m->CP[d]); F(m->dHout[d]); F(m->dhrec[d]); F(m->dcc[d]); }
+  F(m->d_order); F(m->d_start); F(m->d_lens); F(m->d_tokseq); F(m->d_tokstart); F(m->d_partial); F(m->d_gnorm);
+  if (m->h_x) cudaFreeHost(m->h_x);
+  if (m->h_ints) cudaFreeHost(m->h_ints);
+  for (auto& h : m->heads) {
+    F(h.bi); F(h.dbi); F(h.dA); F(h.dBuf); for (auto a : h.act) F(a);
+    F(h.proba); F(h.dlogits); F(h.row_loss); F(h.row_correct); F(h.scalars); F(h.pred);
+    for (int i = 0; i < ICL_N_INDEX; i++) F(h.idx[i]);
+    F(h.feats); F(h.box); F(h.bfeats); F(h.labels);
+    if (h.h_idx) cudaFreeHost(h.h_idx);
+    if (h.h_dense) cudaFreeHost(h.h_dense);
+    if (h.h_out) cudaFreeHost(h.h_out);
+    if (h.h_pred) cudaFreeHost(h.h_pred);
+  }
+  if (m->aux) cudaStreamDestroy(m->aux);
+  for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_t0, m->ev_t1}) if (e) cudaEventDestroy(e);
+  delete m;
+}
+
+extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
+  if (!cfg || !out) return fail("icl_create: null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("icl_create: no CUDA device -- this library has no CPU fallback");
+  CK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) return fail("icl_create: device sm_%d%d is not Blackwell sm_100 (kernels are sm_100a-only)", prop.major, prop.minor);
+  if (cfg->embed_width % 4 || cfg->lstm_hidden % 4) return fail("icl_create: embed_width and lstm_hidden must be multiples of 4");
+  if (cfg->n_heads < 1 || cfg->n_heads > ICL_MAX_HEADS) return fail("icl_create: n_heads out of range");
+  icl_model* m = new icl_model();
+  m->cfg = *cfg;
+  if (m->cfg.beta1 <= 0) m->cfg.beta1 = 0.9f;
+  if (m->cfg.beta2 <= 0) m->cfg.beta2 = 0.999f;
+  int E = m->E = cfg->embed_width, H = m->H = cfg->lstm_hidden;
+  m->S_cap = cfg->max_seqs; m->T_cap = cfg->max_seq_len;
+  m->Ntok_cap = (long)m->S_cap * m->T_cap;
+  m->Np_cap = m->Ntok_cap + m->S_cap;
+  // parameters, named like the TF variables
+  const char* dn[2] = {"fw", "bw"};
+  for (int d = 0; d < 2; d++) {
+    std::string base = std::string("bidirectional_lstm/bidirectional_rnn/") + dn[d] + "/basic_lstm_cell/";
+    m->pK[d] = add_param(m, base + "kernel", E + H, 4 * H);
+    m->pBias[d] = add_param(m, base + "bias", 1, 4 * H);
+  }
+  m->heads.resize(cfg->n_heads);
+  for (int hi = 0; hi < cfg->n_heads; hi++) {
+    Head& h = m->heads[hi];
+    h.c = cfg->heads[hi];
+    if (h.c.n_hidden < 1 || h.c.n_hidden > ICL_MAX_LAYERS) { icl_destroy(m); return fail("head %d: n_hidden out of range", hi); }
+    if (h.c.n_classes < 2 || h.c.n_classes > 32) { icl_destroy(m); return fail("head %d: n_classes must be in [2,32]", hi); }
+    std::vector<int> plan;
+    slot_plan(h.c, plan);
+    memset(&h.slots, 0, sizeof(h.slots));
+    int col = 0;
+    for (size_t i = 0; i < plan.size(); i++) {
+      int w = plan[i] >= 0 ? H : plan[i] == -1 ? h.c.n_feats : plan[i] == -2 ? h.c.box_width : h.c.n_box_feats;
+      h.slots.kind[i] = plan[i] >= 0 ? 0 : 1;
+      h.slots.col[i] = col;
+      h.slots.width[i] = w;
+      col += w;
+      if (plan[i] >= 0) h.D0g = col;
+    }
+    h.slots.n_slots = (int)plan.size();
+    h.slot_index_id = plan;
+    h.D0 = col;
+    h.dims.push_back(h.D0);
+    for (int k = 0; k < h.c.n_hidden; k++) h.dims.push_back(h.c.widths[k]);
+    h.dims.push_back(h.c.n_classes);
+    std::string pre = h.c.scope[0] ? std::string(h.c.scope) + "/" : "";
+    for (int k = 0; k <= h.c.n_hidden; k++) {
+      std::string sc = k < h.c.n_hidden ? pre + "hdn_" + std::to_string(k + 1) : pre + "softmax";
+      h.pW.push_back(add_param(m, sc + "/Variable", h.dims[k], h.dims[k + 1]));
+      h.pB.push_back(add_param(m, sc + "/Variable_1", 1, h.dims[k + 1]));
+    }
+  }
+  *out = m;   // from here on failures leave a destroyable handle
+#define CKD(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fail("icl_create: %s -> %s", #x, cudaGetErrorString(e_)); icl_destroy(m); *out = nullptr; return -1; } } while (0)
+  size_t np = (size_t)m->n_params;
+  CKD(dmalloc(&m->P, np)); CKD(dmalloc(&m->G, np)); CKD(dmalloc(&m->M, np)); CKD(dmalloc(&m->V, np));
+  CKD(cudaMemset(m->P, 0, np * 4)); CKD(cudaMemset(m->G, 0, np * 4)); CKD(cudaMemset(m->M, 0, np * 4)); CKD(cudaMemset(m->V, 0, np * 4));
+  CKD(dmalloc(&m->xraw, (size_t)m->Ntok_cap * E));
+  for (int d = 0; d < 2; d++) {
+    CKD(dmalloc(&m->xd[d], (size_t)m->Np_cap * E));
+    CKD(dmalloc(&m->Z[d], (size_t)m->Np_cap * 4 * H));
+    CKD(dmalloc(&m->HP[d], (size_t)m->Np_cap * H));
+    CKD(dmalloc(&m->CP[d], (size_t)m->Np_cap * H));
+    CKD(dmalloc(&m->dHout[d], (size_t)m->Np_cap * H));
+    CKD(dmalloc(&m->dhrec[d], (size_t)m->S_cap * H));
+    CKD(dmalloc(&m->dcc[d], (size_t)m->S_cap * H));
+  }
+  CKD(dmalloc(&m->d_order, m->S_cap)); CKD(dmalloc(&m->d_start, m->S_cap)); CKD(dmalloc(&m->d_lens, m->S_cap));
+  CKD(dmalloc(&m->d_tokstart, m->S_cap)); CKD(dmalloc(&m->d_tokseq, m->Ntok_cap));
+  CKD(dmalloc(&m->d_partial, 1024)); CKD(dmalloc(&m->d_gnorm, 4));
+  CKD(cudaMallocHost((void**)&m->h_x, (size_t)m->Ntok_cap * E * 4));
+  CKD(cudaMallocHost((void**)&m->h_ints, ((size_t)m->S_cap * 4 + m->Ntok_cap) * 4));
+  for (auto& h : m->heads) {
+    int B = h.c.batch_size, C = h.c.n_classes;
+    int maxw = 0;
+    for (int k = 1; k <= h.c.n_hidden; k++) maxw = std::max(maxw, h.dims[k]);
+    CKD(dmalloc(&h.bi, (size_t)B * h.D0)); CKD(dmalloc(&h.dbi, (size_t)B * std::max(h.D0g, 1)));
+    CKD(dmalloc(&h.dA, (size_t)B * maxw)); CKD(dmalloc(&h.dBuf, (size_t)B * maxw));
+    for (int k = 1; k <= h.c.n_hidden; k++) { float* a; CKD(dmalloc(&a, (size_t)B * h.dims[k])); h.act.push_back(a); }
+    CKD(dmalloc(&h.proba, (size_t)B * C)); CKD(dmalloc(&h.dlogits, (size_t)B * C));
+    CKD(dmalloc(&h.row_loss, B)); CKD(dmalloc(&h.row_correct, B)); CKD(dmalloc(&h.scalars, 4)); CKD(dmalloc(&h.pred, B));
+    for (int i = 0; i < ICL_N_INDEX; i++) CKD(dmalloc(&h.idx[i], (size_t)B * 3));
+    CKD(dmalloc(&h.feats, (size_t)B * std::max(h.c.n_feats, 1)));
+    CKD(dmalloc(&h.box, (size_t)B * std::max(h.c.box_width, 1)));
+    CKD(dmalloc(&h.bfeats, (size_t)B * std::max(h.c.n_box_feats, 1)));
+    CKD(dmalloc(&h.labels, (size_t)B * C));
+    h.h_dense_floats = (size_t)B * (h.c.n_feats + h.c.box_width + h.c.n_box_feats + C);
+    CKD(cudaMallocHost((void**)&h.h_idx, (size_t)B * 3 * ICL_N_INDEX * 4));
+    CKD(cudaMallocHost((void**)&h.h_dense, std::max<size_t>(h.h_dense_floats, 1) * 4));
+    CKD(cudaMallocHost((void**)&h.h_out, ((size_t)B * C + 4) * 4));
+    CKD(cudaMallocHost((void**)&h.h_pred, (size_t)B * 8));
+    for (int i = 0; i < h.slots.n_slots; i++) {
+      int id = h.slot_index_id[i];
+      if (id >= 0) h.slots.idx[i] = h.idx[id];
+      else h.slots.dense[i] = id == -1 ? h.feats : id == -2 ? h.box : h.bfeats;
+    }
+  }
+  CKD(cudaStreamCreateWithFlags(&m->aux, cudaStreamNonBlocking));
+  CKD(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+  CKD(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+  CKD(cudaEventCreate(&m->ev_t0)); CKD(cudaEventCreate(&m->ev_t1));
+  if (tcgen05_gemm_init() != 0) { fail("icl_create: cannot resolve cuTensorMapEncodeTiled"); icl_destroy(m); *out = nullptr; return -1; }
+#undef CKD
+  return 0;
+}
+
+extern "C" int icl_set_stream(icl_model* m, void* s) { m->stream = (cudaStream_t)s; return 0; }
+extern "C" int icl_sync(icl_model* m) { CK(cudaStreamSynchronize(m->stream)); CK(cudaStreamSynchronize(m->aux)); return 0; }
+extern "C" int icl_param_count(icl_model* m) { return (int)m->params.size(); }
+extern "C" int icl_param_info(icl_model* m, int i, const char** name, int32_t* rows, int32_t* cols, int64_t* off) {
+  if (i < 0 || i >= (int)m->params.size()) return fail("param index out of range");
+  const Param& p = m->params[i];
+  if (name) *name = p.name.c_str();
+  if (rows) *rows = p.rows;
+  if (cols) *cols = p.cols;
+  if (off) *off = p.off;
+  return 0;
+}
+static float* kind_buf(icl_model* m, int kind) { return kind == 0 ? m->P : kind == 1 ? m->G : kind == 2 ? m->M : kind == 3 ? m->V : nullptr; }
+extern "C" int icl_get_tensor(icl_model* m, int kind, const char* name, float* host) {
+  auto it = m->pindex.find(name);
+  if (it == m->pindex.end() || !kind_buf(m, kind)) return fail("unknown tensor '%s' (kind %d)", name, kind);
+  const Param& p = m->params[it->second];
+  CK(cudaStreamSynchronize(m->stream));
+  CK(cudaMemcpy(host, kind_buf(m, kind) + p.off, (size_t)p.rows * p.cols * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+extern "C" int icl_set_tensor(icl_model* m, int kind, const char* name, const float* host) {
+  auto it = m->pindex.find(name);
+  if (it == m->pindex.end() || !kind_buf(m, kind)) return fail("unknown tensor '%s' (kind %d)", name, kind);
+  const Param& p = m->params[it->second];
+  CK(cudaStreamSynchronize(m->stream));
+  CK(cudaMemcpy(kind_buf(m, kind) + p.off, host, (size_t)p.rows * p.cols * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+extern "C" int icl_get_step(icl_model* m, int64_t* t) { *t = m->step; return 0; }
+extern "C" int icl_set_step(icl_model* m, int64_t t) { m->step = t; return 0; }
+extern "C" int icl_grad_buffer(icl_model* m, void** p, int64_t* n) { *p = m->G; *n = m->n_params; return 0; }
+extern "C" int icl_param_buffer(icl_model* m, void** p, int64_t* n) { *p = m->P; *n = m->n_params; return 0; }
+extern "C" int icl_kernel_launches(icl_model* m, int64_t* n) { *n = m->launches; return 0; }
+extern "C" int icl_last_step_ms(icl_model* m, float* ms) { *ms = m->last_ms; return 0; }
+
+// ----------------------------------------------------------------------------- upload (H2D of one batch_tensors dict)
+extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
+  if (!m || !b) return fail("icl_upload: null argument");
+  int S = b->n_seqs, E = m->E;
+  if (S < 1 || S > m->S_cap) return fail("icl_upload: n_seqs=%d exceeds capacity %d", S, m->S_cap);
+  if (b->n_heads != m->cfg.n_heads) return fail("icl_upload: batch has %d heads, model has %d", b->n_heads, m->cfg.n_heads);
+  if (!b->sent_packed && (b->padded_T < 1 || b->padded_T > m->T_cap)) return fail("icl_upload: padded_T=%d exceeds capacity %d", b->padded_T, m->T_cap);
+  int T = b->sent_packed ? m->T_cap : b->padded_T;
+  CK(cudaStreamSynchronize(m->stream));          // pinned staging is reused
+  int* lens = m->h_ints; int* start = lens + m->S_cap; int* order = start + m->S_cap; int* tokstart = order + m->S_cap; int* tokseq = tokstart + m->S_cap;
+  long ntok = 0, np = 0; int tmax = 0;
+  for (int s = 0; s < S; s++) {
+    double l = read_num(b->seq_lengths, b->len_dtype, s);
+    int li = (int)l;
+    if (li != l || li < 0 || li > T) return fail("icl_upload: seq_lengths[%d]=%g outside [0,%d]", s, l, T);
+    lens[s] = li; start[s] = (int)np; tokstart[s] = (int)ntok;
+    ntok += li; np += li + 1; tmax = std::max(tmax, li);
+  }
+  std::iota(order, order + S, 0);
+  std::stable_sort(order, order + S, [&](int a, int c) { return lens[a] > lens[c]; });
+  m->n_active.assign(tmax, 0);
+  for (int s = 0; s < S; s++) for (int k = 0; k < lens[s]; k++) m->n_active[k]++;
+  // pack valid tokens (caption-major) into pinned memory as fp32
+  size_t esz = b->sent_dtype == ICL_F64 ? 8 : 4;
+  if (b->sent_dtype != ICL_F32 && b->sent_dtype != ICL_F64) return fail("icl_upload: sentences must be float32/float64");
+  for (int s = 0; s < S; s++) {
+    const char* src = (const char*)b->sentences + (b->sent_packed ? (size_t)tokstart[s] * E : (size_t)s * T * E) * esz;
+    to_f32(m->h_x + (size_t)tokstart[s] * E, src, b->sent_dtype, (size_t)lens[s] * E);
+    for (int t = 0; t < lens[s]; t++) tokseq[tokstart[s] + t] = s;
+  }
+  cudaStream_t st = m->stream;
+  CK(cudaMemcpyAsync(m->xraw, m->h_x, (size_t)ntok * E * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(m->d_lens, lens, S * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(m->d_start, start, S * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(m->d_order, order, S * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(m->d_tokstart, tokstart, S * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(m->d_tokseq, tokseq, (size_t)ntok * 4, cudaMemcpyHostToDevice, st));
+  for (int hi = 0; hi < b->n_heads; hi++) {
+    Head& h = m->heads[hi];
+    const icl_head_batch& hb = b->heads[hi];
+    int B = h.c.batch_size, C = h.c.n_classes;
+    for (int sl = 0; sl < h.slots.n_slots; sl++) {
+      int id = h.slot_index_id[sl];
+      if (id < 0) continue;
+      if (!hb.idx[id]) return fail("icl_upload: head %d is missing index matrix %d", hi, id);
+      int* dst = h.h_idx + (size_t)id * B * 3;
+      for (int r = 0; r < B; r++) {
+        double d = read_num(hb.idx[id], hb.idx_dtype, r * 3), sq = read_num(hb.idx[id], hb.idx_dtype, r * 3 + 1) + hb.sent_offset,
+               w = read_num(hb.idx[id], hb.idx_dtype, r * 3 + 2);
+        // TF-CPU gather_nd raises on an out-of-range index (core.py:350); so do we
+        if (!(d == 0 || d == 1) || sq < 0 || sq >= S || w < 0 || w >= T || sq != (int)sq || w != (int)w)
+          return fail("icl_upload: head %d index matrix %d row %d = [%g,%g,%g] out of range (S=%d,T=%d)", hi, id, r, d, sq, w, S, T);
+        dst[r * 3] = (int)d; dst[r * 3 + 1] = (int)sq; dst[r * 3 + 2] = (int)w;
+      }
+      CK(cudaMemcpyAsync(h.idx[id], dst, (size_t)B * 3 * 4, cudaMemcpyHostToDevice, st));
+    }
+    float* hd = h.h_dense;
+    auto up = [&](const void* src, int dt, float* dev, size_t n, const char* what) -> int {
+      if (n == 0) return 0;
+      if (!src) return fail("icl_upload: head %d is missing %s", hi, what);
+      to_f32(hd, src, dt, n);
+      cudaError_t e = cudaMemcpyAsync(dev, hd, n * 4, cudaMemcpyHostToDevice, st);
+      hd += n;
+      return e == cudaSuccess ? 0 : fail("icl_upload: copy of %s failed: %s", what, cudaGetErrorString(e));
+    };
+    CKI(up(hb.feats, hb.feats_dtype, h.feats, (size_t)B * h.c.n_feats, "m_feats/ij_feats"));
+    CKI(up(hb.box, hb.box_dtype, h.box, (size_t)B * h.c.box_width, "box_embeddings"));
+    CKI(up(hb.bfeats, hb.bfeats_dtype, h.bfeats, (size_t)B * h.c.n_box_feats, "b_feats"));
+    h.has_labels = hb.labels != nullptr;
+    if (h.has_labels) CKI(up(hb.labels, hb.labels_dtype, h.labels, (size_t)B * C, "labels"));
+  }
+  m->S = S; m->Tmax = tmax; m->Ntok = ntok; m->Np = np;
+  m->seq_gid0 = b->seq_gid_offset; m->ex_gid0 = b->ex_gid_offset;
+  m->resident = true;
+  return 0;
+}
+
+// ----------------------------------------------------------------------------- forward / backward on resident data
+static SeqMap mk_map(icl_model* m, int mode, int k, int dir) {
+  SeqMap s; s.order = m->d_order; s.start = m->d_start; s.lens = m->d_lens; s.k = k; s.dir = dir; s.mode = mode;
+  return s;
+}
+#define LAUNCHED(m) do { (m)->launches++; CK(cudaGetLastError()); } while (0)
+
+static int lstm_forward(icl_model* m, float keep_in, uint64_t seed) {
+  int E = m->E, H = m->H, S = m->S;
+  long Np = m->Np;
+  cudaStream_t st = m->stream;
+  if (m->Ntok > 0) {
+    k_prep_x<<<(unsigned)((m->Ntok * 32 + 255) / 256), 256, 0, st>>>(m->xraw, m->d_tokseq, m->d_tokstart, m->d_start, (int)m->Ntok, E,
+                                                                   m->T_cap, m->cfg.data_norm, keep_in, seed, m->seq_gid0, m->xd[0], m->xd[1]);
+    LAUNCHED(m);
+  }
+  k_zero_rows<<<S, 128, 0, st>>>(m->xd[0], m->d_start, m->d_lens, S, E, 1); LAUNCHED(m);
+  k_zero_rows<<<S, 128, 0, st>>>(m->xd[1], m->d_start, m->d_lens, S, E, 0); LAUNCHED(m);
+  CK(cudaEventRecord(m->ev_fork, st));
+  CK(cudaStreamWaitEvent(m->aux, m->ev_fork, 0));
+  for (int d = 0; d < 2; d++) {
+    cudaStream_t sd = d ? m->aux : st;
+    const Param& pk = m->params[m->pK[d]];
+    const float* K = m->P + pk.off;
+    const float* bias = m->P + m->params[m->pBias[d]].off;
+    // K1: time-batched input projection  Z = Xd * W_ih + b   (W_ih = kernel rows [0,E))
+    GemmArgs g = mk_gemm(m->xd[d], E, K, 4 * H, m->Z[d], 4 * H, (int)Np, 4 * H, E);
+    g.epi.bias = bias;
+    CKI(gemm(m, sd, false, true, g));
+    k_zero_rows<<<S, 128, 0, sd>>>(m->HP[d], m->d_start, m->d_lens, S, H, d); LAUNCHED(m);
+    k_zero_rows<<<S, 128, 0, sd>>>(m->CP[d], m->d_start, m->d_lens, S, H, d); LAUNCHED(m);
+    const float* Whh = K + (size_t)E * 4 * H;
+    for (int k = 0; k < m->Tmax; k++) {
+      int n = m->n_active[k];
+      if (k > 0) {   // h_prev is zero at the first step
+        GemmArgs r = mk_gemm(m->HP[d], H, Whh, 4 * H, m->Z[d], 4 * H, n, 4 * H, H);
+        r.amap = mk_map(m, 1, k, d); r.cmap = mk_map(m, 1, k, d); r.epi.beta = 1.0f;
+        CKI(gemm(m, sd, false, true, r));
+      }
+      k_lstm_cell_fwd<<<n, 128, 0, sd>>>(m->Z[d], m->HP[d], m->CP[d], mk_map(m, 1, k, d), n, H); LAUNCHED(m);
+    }
+  }
+  CK(cudaEventRecord(m->ev_join, m->aux));
+  CK(cudaStreamWaitEvent(st, m->ev_join, 0));
+  return 0;
+}
+
+static Drop mk_drop(uint64_t seed, uint32_t stream, float keep, int64_t gid0) { Drop d; d.seed = seed; d.stream = stream; d.keep = keep; d.row_gid0 = gid0; return d; }
+
+static int heads_forward(icl_model* m, float keep, uint64_t seed) {
+  cudaStream_t st = m->stream;
+  int H = m->H;
+  for (size_t hi = 0; hi < m->heads.size(); hi++) {
+    Head& h = m->heads[hi];
+    int B = h.c.batch_size, C = h.c.n_classes, L = h.c.n_hidden;
+    k_gather_concat<<<B, 128, 0, st>>>(h.slots, m->HP[0], m->HP[1], m->d_start, m->d_lens, H, m->T_cap, h.D0,
+                                      mk_drop(seed, 0, keep, m->seq_gid0), h.bi);
+    LAUNCHED(m);
+    const float* in = h.bi;
+    for (int k = 0; k < L; k++) {
+      const Param& pw = m->params[h.pW[k]];
+      GemmArgs g = mk_gemm(in, h.dims[k], m->P + pw.off, h.dims[k + 1], h.act[k], h.dims[k + 1], B, h.dims[k + 1], h.dims[k]);
+      g.epi.mode = EPI_BIAS_ACT_DROP; g.epi.bias = m->P + m->params[h.pB[k]].off; g.epi.act = h.c.activation;
+      g.epi.drop = mk_drop(seed, STREAM_HEAD + (uint32_t)hi * 8 + k, keep, m->ex_gid0);
+      CKI(gemm(m, st, false, true, g));
+      in = h.act[k];
+    }
+    float scale = h.c.weighted_classes ? 1.0f / B : 1.0f;   // "weighted" as executed == mean CE (core.py:244-267)
+    k_softmax_ce<<<(B * 32 + 127) / 128, 128, 0, st>>>(in, h.dims[L], m->P + m->params[h.pW[L]].off, m->P + m->params[h.pB[L]].off, C,
+                                                      h.has_labels ? h.labels : nullptr, B, scale, h.proba, h.pred, h.row_loss,
+                                                      h.row_correct, h.dlogits);
+    LAUNCHED(m);
+    if (h.has_labels) {
+      k_reduce_sum<<<1, 256, 0, st>>>(h.row_loss, B, h.scalars, 0.f); LAUNCHED(m);
+      k_reduce_sum<<<1, 256, 0, st>>>(h.row_correct, B, h.scalars + 1, (float)B); LAUNCHED(m);
+    }
+  }
+  return 0;
+}
+
+static int colsum(icl_model* m, cudaStream_t st, const float* X, long rows, int N, long ld, float* out) {
+  k_colsum<<<(N + 31) / 32, 256, 0, st>>>(X, rows, N, ld, out);
+  LAUNCHED(m);
+  return 0;
+}
+
+static int heads_backward(icl_model* m, float keep, uint64_t seed) {
+  cudaStream_t st = m->stream;
+  int H = m->H;
+  for (int d = 0; d < 2; d++) CK(cudaMemsetAsync(m->dHout[d], 0, (size_t)m->Np * H * 4, st));
+  for (size_t hi = 0; hi < m->heads.size(); hi++) {
+    Head& h = m->heads[hi];
+    if (!h.has_labels) return fail("backward needs labels for head %zu", hi);
+    int B = h.c.batch_size, L = h.c.n_hidden;
+    const float* dz = h.dlogits;       // gradient w.r.t. the pre-activation of layer k+1 (softmax layer first)
+    float* bufs[2] = {h.dA, h.dBuf};
+    int cur = 0;
+    for (int k = L; k >= 0; k--) {
+      const float* in = k == 0 ? h.bi : h.act[k - 1];
+      int din = h.dims[k], dout = h.dims[k + 1];
+      const Param& pw = m->params[h.pW[k]];
+      // dW = in^T * dz   (contraction over the batch: both operands MN-major)
+      GemmArgs gw = mk_gemm(in, din, dz, dout, m->G + pw.off, dout, din, dout, B);
+      CKI(gemm(m, st, true, true, gw));
+      CKI(colsum(m, st, dz, B, dout, dout, m->G + m->params[h.pB[k]].off));
+      // d(in) = dz * W^T  (W [din,dout] row-major is K-major as the B operand)
+      if (k > 0) {
+        GemmArgs gx = mk_gemm(dz, dout, m->P + pw.off, dout, bufs[cur], din, B, din, dout);
+        gx.epi.mode = EPI_DACT; gx.epi.act = h.c.activation; gx.epi.aux = h.act[k - 1]; gx.epi.ldaux = din;
+        gx.epi.drop = mk_drop(seed, STREAM_HEAD + (uint32_t)hi * 8 + (k - 1), keep, m->ex_gid0);
+        CKI(gemm(m, st, false, false, gx));
+        dz = bufs[cur];
+        cur ^= 1;
+      } else if (h.D0g > 0) {
+        GemmArgs gx = mk_gemm(dz, dout, m->P + pw.off, dout, h.dbi, h.D0g, B, h.D0g, dout);
+        CKI(gemm(m, st, false, false, gx));
+        k_scatter_spans<<<B, 128, 0, st>>>(h.slots, h.dbi, m->d_start, m->d_lens, H, m->T_cap, h.D0g,
+                                          mk_drop(seed, 0, keep, m->seq_gid0), m->dHout[0], m->dHout[1]);
+        LAUNCHED(m);
+      }
+    }
+  }
+  return 0;
+}
+
+static int lstm_backward(icl_model* m) {
+  int E = m->E, H = m->H, S = m->S;
+  long Np = m->Np;
+  cudaStream_t st = m->stream;
+  CK(cudaEventRecord(m->ev_fork, st));
+  CK(cudaStreamWaitEvent(m->aux, m->ev_fork, 0));
+  for (int d = 0; d < 2; d++) {
+    cudaStream_t sd = d ? m->aux : st;
+    const Param& pk = m->params[m->pK[d]];
+    const float* Whh = m->P + pk.off + (size_t)E * 4 * H;
+    CK(cudaMemsetAsync(m->dhrec[d], 0, (size_t)S * H * 4, sd));
+    CK(cudaMemsetAsync(m->dcc[d], 0, (size_t)S * H * 4, sd));
+    for (int k = m->Tmax - 1; k >= 0; k--) {
+      int n = m->n_active[k];
+      k_lstm_cell_bwd<<<n, 128, 0, sd>>>(m->Z[d], m->CP[d], m->dHout[d], m->Z[d], m->dhrec[d], m->dcc[d], mk_map(m, 1, k, d), n, H);
+      LAUNCHED(m);
+      if (k > 0) {   // dh_{prev} = dz * W_hh^T
+        GemmArgs r = mk_gemm(m->Z[d], 4 * H, Whh, 4 * H, m->dhrec[d], H, n, H, 4 * H);
+        r.amap = mk_map(m, 1, k, d); r.cmap = mk_map(m, 2, k, d);
+        CKI(gemm(m, sd, false, false, r));
+      }
+    }
+    // pad rows of dZ must be exactly zero for the time-batched weight-gradient GEMMs
+    k_zero_rows<<<S, 128, 0, sd>>>(m->Z[d], m->d_start, m->d_lens, S, 4 * H, d == 0 ? 1 : 0); LAUNCHED(m);
+    float* dK = m->G + pk.off;
+    GemmArgs gi = mk_gemm(m->xd[d], E, m->Z[d], 4 * H, dK, 4 * H, E, 4 * H, (int)Np);          // dW_ih = Xd^T dZ
+    CKI(gemm(m, sd, true, true, gi));
+    GemmArgs gh = mk_gemm(m->HP[d], H, m->Z[d], 4 * H, dK + (size_t)E * 4 * H, 4 * H, H, 4 * H, (int)Np);   // dW_hh = Hprev^T dZ
+    CKI(gemm(m, sd, true, true, gh));
+    float* db = m->G + m->params[m->pBias[d]].off;
+    CK(cudaMemsetAsync(db, 0, (size_t)4 * H * 4, sd));
+    int rpb = 256;
+    dim3 grid((4 * H + 127) / 128, (unsigned)((Np + rpb - 1) / rpb));
+    k_colsum_atomic<<<grid, 128, 0, sd>>>(m->Z[d], Np, 4 * H, 4 * H, db, rpb); LAUNCHED(m);
+  }
+  CK(cudaEventRecord(m->ev_join, m->aux));
+  CK(cudaStreamWaitEvent(st, m->ev_join, 0));
+  return 0;
+}
+
+extern "C" int icl_apply_update(icl_model* m) {
+  cudaStream_t st = m->stream;
+  long n = (long)m->n_params;
+  if (m->cfg.clip_norm > 0) {
+    k_sumsq_partial<<<592, 256, 0, st>>>(m->G, n, m->d_partial); LAUNCHED(m);
+    k_sumsq_final<<<1, 256, 0, st>>>(m->d_partial, 592, m->d_gnorm); LAUNCHED(m);
+  }
+  m->step++;
+  double b1 = m->cfg.beta1, b2 = m->cfg.beta2;
+  float lr_t = (float)(m->cfg.learn_rate * std::sqrt(1.0 - std::pow(b2, (double)m->step)) / (1.0 - std::pow(b1, (double)m->step)));
+  k_adam<<<592, 256, 0, st>>>(m->P, m->G, m->M, m->V, n, m->d_gnorm, m->cfg.clip_norm, lr_t, (float)b1, (float)b2, m->cfg.adam_epsilon);
+  LAUNCHED(m);
+  return 0;
+}
+
+extern "C" int icl_run_resident(icl_model* m, int op, float keep_in, float keep, uint64_t seed) {
+  if (!m->resident) return fail("icl_run_resident: no batch uploaded");
+  if (!(keep_in > 0 && keep_in <= 1 && keep > 0 && keep <= 1)) return fail("keep probabilities must be in (0,1]");
+  CK(cudaEventRecord(m->ev_t0, m->stream));
+  CKI(lstm_forward(m, keep_in, seed));
+  CKI(heads_forward(m, keep, seed));
+  if (op >= ICL_OP_GRADS) {
+    CKI(heads_backward(m, keep, seed));
+    CKI(lstm_backward(m));
+  }
+  if (op == ICL_OP_TRAIN) CKI(icl_apply_update(m));
+  CK(cudaEventRecord(m->ev_t1, m->stream));
+  return 0;
+}
+
+extern "C" int icl_fetch(icl_model* m, icl_head_out* out) {
+  cudaStream_t st = m->stream;
+  for (size_t hi = 0; hi < m->heads.size(); hi++) {
+    Head& h = m->heads[hi];
+    int B = h.c.batch_size, C = h.c.n_classes;
+    CK(cudaMemcpyAsync(h.h_out, h.proba, (size_t)B * C * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h.h_out + (size_t)B * C, h.scalars, 2 * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h.h_pred, h.pred, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  cudaEventElapsedTime(&m->last_ms, m->ev_t0, m->ev_t1);
+  for (size_t hi = 0; hi < m->heads.size() && out; hi++) {
+    Head& h = m->heads[hi];
+    int B = h.c.batch_size, C = h.c.n_classes;
+    if (out[hi].proba) memcpy(out[hi].proba, h.h_out, (size_t)B * C * 4);
+    if (out[hi].pred) memcpy(out[hi].pred, h.h_pred, (size_t)B * 8);
+    out[hi].loss = h.has_labels ? h.h_out[(size_t)B * C] : NAN;
+    out[hi].accuracy = h.has_labels ? h.h_out[(size_t)B * C + 1] : NAN;
+  }
+  return 0;
+}
+
+extern "C" int icl_run(icl_model* m, int op, const icl_batch* b, float keep_in, float keep, uint64_t seed, icl_head_out* out) {
+  CKI(icl_upload(m, b));
+  CKI(icl_run_resident(m, op, keep_in, keep, seed));
+  return icl_fetch(m, out);
+}
+
+// ----------------------------------------------------------------------------- hooks
+extern "C" int icl_get_lstm_outputs(icl_model* m, int dir, float* host) {
+  if (!m->resident) return fail("no batch resident");
+  int T = m->T_cap;
+  float* tmp;
+  size_t n = (size_t)m->S * T * m->H;
+  CK(dmalloc(&tmp, n));
+  k_unpack_outputs<<<m->S * T, 128, 0, m->stream>>>(m->HP[dir], m->d_start, m->d_lens, m->S, T, m->H, dir, tmp);
+  cudaError_t e = cudaMemcpyAsync(host, tmp, n * 4, cudaMemcpyDeviceToHost, m->stream);
+  cudaStreamSynchronize(m->stream);
+  cudaFree(tmp);
+  CK(e);
+  return 0;
+}
+extern "C" int icl_get_batch_input(icl_model* m, int head, float* host) {
+  Head& h = m->heads[head];
+  CK(cudaStreamSynchronize(m->stream));
+  CK(cudaMemcpy(host, h.bi, (size_t)h.c.batch_size * h.D0 * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+extern "C" int icl_debug_mask(icl_model* m, uint64_t seed, uint32_t stream, int64_t first, int64_t n, float keep, float* host) {
+  float* tmp;
+  CK(dmalloc(&tmp, (size_t)n));
+  k_debug_mask<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(seed, stream, first, n, keep, tmp);
+  cudaError_t e = cudaMemcpyAsync(host, tmp, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream);
+  cudaStreamSynchronize(m->stream);
+  cudaFree(tmp);
+  CK(e);
+  return 0;
+}
+extern "C" int icl_gemm(icl_model* m, int mode, int a_mn, int b_mn, int M, int N, int K, const float* A, const float* B, float* C) {
+  float *dA, *dB, *dC;
+  CK(dmalloc(&dA, (size_t)M * K)); CK(dmalloc(&dB, (size_t)K * N)); CK(dmalloc(&dC, (size_t)M * N));
+  CK(cudaMemcpy(dA, A, (size_t)M * K * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, B, (size_t)K * N * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dC, 0xff, (size_t)M * N * 4));
+  GemmArgs g = mk_gemm(dA, a_mn ? M : K, dB, b_mn ? N : K, dC, N, M, N, K);
+  int r = gemm(m, m->stream, a_mn, b_mn, g, mode);
+  cudaError_t e = cudaStreamSynchronize(m->stream);
+  if (r == 0 && e == cudaSuccess) e = cudaMemcpy(C, dC, (size_t)M * N * 4, cudaMemcpyDeviceToHost);
+  cudaFree(dA); cudaFree(dB); cudaFree(dC);
+  if (r != 0) return r;
+  CK(e);
+  return 0;
+}

@@ -1,0 +1,132 @@
+/* icl_b200.h -- C-ABI of libicl_b200.so: the B200 (sm_100a) implementation of the neural hot path of
+ * cmcervantes/ImageCaptionLearn_py.
+ *
+ * The reference has no FFI: its seam is the Python function layer of nn_utils/core.py in front of
+ * `sess.run(op, feed_dict)` (nn_utils/core.py:625).  Each entry point below replaces one piece of that seam;
+ * the Python shim `imagecaptionlearn_py_b200/core.py` binds them with ctypes and re-exposes the reference's
+ * own function names (setup_bidirectional_lstm, setup_core_architecture, add_train_op, run_op,
+ * get_pred_scores_mcc).  Plain pointers and sizes only -- no torch types.
+ *
+ * Conventions: every function returns 0 on success, non-zero on error (text via icl_last_error()); nothing
+ * throws across the boundary.  The caller owns every input/output buffer; the library owns parameters,
+ * optimizer state and workspaces inside the handle.  One handle per device per process; calls on a handle are
+ * not re-entrant.  There is NO CPU fallback: icl_create fails if no sm_100 device is present.
+ */
+#ifndef ICL_B200_H
+#define ICL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICL_MAX_HEADS 8
+#define ICL_MAX_LAYERS 8
+#define ICL_N_INDEX 12
+
+/* task / encoding / activation enums follow the strings of nn_utils/core.py:452-453,178-185 */
+enum { ICL_TASK_NONVIS = 0, ICL_TASK_CARD = 1, ICL_TASK_REL_INTRA = 2, ICL_TASK_REL_CROSS = 3, ICL_TASK_AFFINITY = 4 };
+enum { ICL_ENC_FIRST_LAST_MENTION = 0, ICL_ENC_FIRST_LAST_SENTENCE = 1 };
+enum { ICL_ACT_NONE = 0, ICL_ACT_SIGMOID = 1, ICL_ACT_TANH = 2, ICL_ACT_RELU = 3, ICL_ACT_LEAKY_RELU = 4 };
+enum { ICL_F32 = 0, ICL_F64 = 1, ICL_I32 = 2, ICL_I64 = 3 };
+/* index matrices, in the order of nn_utils/data.py:409-413 */
+enum { ICL_FIRST_I_BW = 0, ICL_FIRST_I_FW, ICL_LAST_I_FW, ICL_LAST_I_BW, ICL_SENT_LAST_I_FW, ICL_SENT_FIRST_I_BW,
+       ICL_FIRST_J_BW, ICL_LAST_J_FW, ICL_FIRST_J_FW, ICL_LAST_J_BW, ICL_SENT_LAST_J_FW, ICL_SENT_FIRST_J_BW };
+/* what icl_run computes -- the `op` argument of run_op (nn_utils/core.py:517) */
+enum { ICL_OP_PREDICT = 0,     /* predicted_proba / pred (+ loss, accuracy when labels are given) */
+       ICL_OP_GRADS = 1,       /* forward + backward; gradients left in the flat gradient buffer (DP: all-reduce it) */
+       ICL_OP_TRAIN = 2 };     /* train_op: forward + backward + clip_by_global_norm + Adam */
+enum { ICL_GEMM_TCGEN05_TF32 = 0, ICL_GEMM_SIMT_FP32 = 1 };
+
+/* one classification head = one setup_core_architecture() call (nn_utils/core.py:443-514) */
+typedef struct icl_head_config {
+  int32_t task, encoding, batch_size, n_classes;
+  int32_t n_feats;          /* n_mention_feats */
+  int32_t box_width;        /* box_embedding_width (affinity) or 0 */
+  int32_t n_box_feats;      /* n_box_feats or 0 */
+  int32_t n_hidden;         /* number of hidden layers = len(get_widths(start, depth)) */
+  int32_t widths[ICL_MAX_LAYERS];
+  int32_t activation, weighted_classes;
+  char scope[32];           /* variable-scope prefix ("" single-task; task name in icl_multitask_lstm.py:50-82) */
+} icl_head_config;
+
+/* setup_bidirectional_lstm (core.py:271) + heads + add_train_op (core.py:74) */
+typedef struct icl_config {
+  int32_t embed_width, lstm_hidden, data_norm;
+  int32_t max_seqs, max_seq_len;         /* capacity: sequences per call, padded length T */
+  int32_t n_heads;
+  icl_head_config heads[ICL_MAX_HEADS];
+  float learn_rate, adam_epsilon, clip_norm;   /* clip_norm <= 0: no clipping (clip_norm=None) */
+  float beta1, beta2;
+  int32_t device, gemm_mode;
+} icl_config;
+
+/* the per-head part of the batch_tensors dict (nn_utils/data.py:349-528) */
+typedef struct icl_head_batch {
+  const void* idx[ICL_N_INDEX];          /* [B,3] rows [dir,sent,word]; NULL when unused by the head */
+  int32_t idx_dtype;
+  const void* feats;  int32_t feats_dtype;      /* m_feats / ij_feats [B,F] */
+  const void* box;    int32_t box_dtype;        /* box_embeddings [B,box_width] or NULL */
+  const void* bfeats; int32_t bfeats_dtype;     /* b_feats or NULL */
+  const void* labels; int32_t labels_dtype;     /* one-hot [B,C] or NULL (include_labels=False) */
+  int32_t sent_offset;                           /* added to the `sent` column (multi-head shared encoder pass) */
+} icl_head_batch;
+
+typedef struct icl_batch {
+  const void* sentences;  int32_t sent_dtype;   /* padded [S,T,E] (sent_packed=0) or packed [sum(len),E] (=1) */
+  int32_t sent_packed;
+  const void* seq_lengths; int32_t len_dtype;   /* [S] */
+  int32_t n_seqs, padded_T;
+  int64_t seq_gid_offset, ex_gid_offset;        /* global ids of row 0 (dropout RNG is keyed on global ids) */
+  int32_t n_heads;
+  icl_head_batch heads[ICL_MAX_HEADS];
+} icl_batch;
+
+typedef struct icl_head_out {
+  float* proba;      /* [B,C] or NULL */
+  int64_t* pred;     /* [B]   or NULL */
+  float loss, accuracy;
+} icl_head_out;
+
+typedef struct icl_model icl_model;
+
+const char* icl_last_error(void);
+int icl_version(void);
+int icl_create(const icl_config* cfg, icl_model** out);          /* replaces graph construction, core.py:271-514,74-106 */
+void icl_destroy(icl_model* m);
+int icl_set_stream(icl_model* m, void* cuda_stream);             /* cudaStream_t of the caller (e.g. torch's current) */
+
+/* parameters are named like the TF variables so checkpoints map 1:1 (tf.train.Saver, icl_core_lstm.py:107,155) */
+int icl_param_count(icl_model* m);
+int icl_param_info(icl_model* m, int i, const char** name, int32_t* rows, int32_t* cols, int64_t* offset);
+int icl_get_tensor(icl_model* m, int kind, const char* name, float* host);  /* kind: 0 param, 1 grad, 2 adam m, 3 adam v */
+int icl_set_tensor(icl_model* m, int kind, const char* name, const float* host);
+int icl_get_step(icl_model* m, int64_t* t);
+int icl_set_step(icl_model* m, int64_t t);
+
+/* sess.run(op, feed_dict) (core.py:625): host buffers in, host results out, copies inside */
+int icl_run(icl_model* m, int op, const icl_batch* b, float keep_in, float keep, uint64_t seed, icl_head_out* out);
+/* split form: stage the batch in HBM once, then run on resident data (bench `value`, DP overlap) */
+int icl_upload(icl_model* m, const icl_batch* b);
+int icl_run_resident(icl_model* m, int op, float keep_in, float keep, uint64_t seed);
+int icl_fetch(icl_model* m, icl_head_out* out);
+/* data-parallel: flat fp32 gradient buffer on the device (all-reduce SUM it), then apply clip + Adam */
+int icl_grad_buffer(icl_model* m, void** dev_ptr, int64_t* n_floats);
+int icl_param_buffer(icl_model* m, void** dev_ptr, int64_t* n_floats);
+int icl_apply_update(icl_model* m);
+int icl_sync(icl_model* m);
+
+/* test / profiling hooks */
+int icl_get_lstm_outputs(icl_model* m, int dir, float* host_STH);        /* pre-dropout outputs, padded [S,T,H] */
+int icl_get_batch_input(icl_model* m, int head, float* host_BD);         /* concat input of head [B,D0] */
+int icl_debug_mask(icl_model* m, uint64_t seed, uint32_t stream, int64_t first_idx, int64_t n, float keep, float* host);
+int icl_gemm(icl_model* m, int mode, int a_mn_major, int b_mn_major, int M, int N, int K,
+             const float* A, const float* B, float* C);                 /* C[M,N] = A*B on the device (validation) */
+int icl_kernel_launches(icl_model* m, int64_t* n);                       /* launches since create */
+int icl_last_step_ms(icl_model* m, float* ms);                           /* device time of last run_resident */
+
+#ifdef __cplusplus
+}
+#endif
+#endif
