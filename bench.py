@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Benchmark of the BiLSTM + mention-span-head hot path (BASELINE.json metric: BiLSTM train captions/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload card2048|nonvis512|...]
+
+One "step" = one `train_op` pass (forward + BPTT + clip + TF-Adam, dropout 0.5/0.5) of the hot path over one synthetic
+F30kE-shaped batch.  At N=1 the workload is BASELINE.json configs[1] (icl_core_lstm cardinality head, H=300,
+batch 2048 captions on one B200).  N>1: one process per GPU (torchrun), each rank trains on its own batch of the same
+size (weak scaling) and the flat gradient buffer is all-reduced (SUM: the loss is a sum over examples,
+nn_utils/core.py:267) over NCCL before the fused clip+Adam update.
+
+JSON line keys: see the contract in the task description.  `value` = captions/s with the batch resident in HBM
+(icl_run_resident), `e2e` = the same step through the reference-facing call `run_op(sess, train_op, [batch_tensors], ...)`
+with host NumPy buffers (H2D of the batch + D2H of loss/proba inside the timed region), `roofline` = the dominant
+kernel group's algorithmic FLOPs / its CUDA-event time, `cpu_baseline` = the NumPy oracle (a port of the reference's
+TF graph; TensorFlow 1.x cannot run here) timed on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (task, B, H, start_width, depth, n_classes, F, data_norm, BASELINE.json config it instantiates)
+    "nonvis512": dict(task="nonvis", B=512, H=300, start=512, depth=2, C=2, F=256, data_norm=False, cfg="configs[0]"),
+    "card2048": dict(task="card", B=2048, H=300, start=512, depth=2, C=12, F=256, data_norm=False, cfg="configs[1]"),
+    "rel_intra512": dict(task="rel_intra", B=512, H=200, start=1024, depth=3, C=4, F=512, data_norm=True, cfg="configs[2]"),
+    "rel_cross512": dict(task="rel_cross", B=512, H=200, start=1024, depth=3, C=4, F=512, data_norm=True, cfg="configs[2]"),
+    "affinity512": dict(task="affinity", B=512, H=300, start=512, depth=2, C=2, F=256, data_norm=False, cfg="configs[3]"),
+}
+E, T_PAD, KEEP_IN, KEEP = 300, 50, 0.5, 0.5
+LR, ADAM_EPS, CLIP = 1e-3, 1e-8, 5.0
+
+
+def make_batch(wl, seed):
+    """One reference-shaped batch_tensors dict (nn_utils/data.py:349-528) from the synthetic corpus."""
+    from imagecaptionlearn_py_b200 import data as nn_data
+    from imagecaptionlearn_py_b200 import synth
+    task, B = wl["task"], wl["B"]
+    n_img = {"affinity": max(4, B // 200), "rel_cross": max(4, B // 300)}.get(task, max(8, B // 10))
+    corpus = synth.make_corpus(n_img, seed=seed, with_boxes=(task == "affinity"))
+    dd = synth.make_data_dict(corpus, task, F=wl["F"])
+    dd["max_seq_len"] = T_PAD                      # the reference pads to the dataset-global maximum (data.py:375)
+    ids = synth.example_ids(dd, task)
+    rng = np.random.Generator(np.random.PCG64(seed + 1))
+    if task == "affinity":
+        ids = nn_data.shuffle_mention_box_pairs(ids, rng)
+    else:
+        ids = list(np.asarray(ids, dtype=object)[rng.permutation(len(ids))])
+    if len(ids) < B:
+        raise RuntimeError("synthetic corpus too small: %d ids for batch %d" % (len(ids), B))
+    return nn_data.load_batch(ids[:B], dd, task, wl["C"])
+
+
+def flops_per_token(H, train=True):
+    """valid-token FLOPs of the BiLSTM, both directions."""
+    fwd = 4 * (E + H) * 4 * H
+    return fwd * 2 + 4 * H * 4 * H if train else fwd
+
+
+def sample_clocks(stop, out):
+    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    dev = os.environ.get("LOCAL_RANK", "0")
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", "-i", dev, "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=5)
+            f = [x.strip() for x in r.stdout.strip().split(",")]
+            if len(f) >= 6:
+                out.append(f)
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def clocks_summary(samples):
+    if not samples:
+        return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unsampled"])
+    sm = sorted(float(s[0]) for s in samples)
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in samples)]
+    return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=float(samples[0][1]), reasons=reasons, samples=len(samples))
+
+
+# ----------------------------------------------------------------------------------------------- reference arm (CPU)
+def oracle_train_step(params, cfg, bt, state, keep_in, keep, rng):
+    from oracle import icl_oracle as O
+    S, T = bt["sentences"].shape[:2]
+    H = cfg["H"]
+    B = len(bt["labels"])
+    bern = lambda shape, k: (rng.random(shape) < k).astype(np.float32)
+    masks = dict(in_fw=bern((S, T, E), keep_in), in_bw=bern((S, T, E), keep_in), out_fw=bern((S, T, H), keep),
+                 out_bw=bern((S, T, H), keep), heads=[[bern((B, w), keep) for w in cfg["heads"][0]["widths"]]])
+    f = O.model_forward(params, cfg, bt["sentences"], bt["seq_lengths"], [bt], keep_in, keep, masks)
+    g = O.model_backward(params, cfg, f, [bt])
+    O.clip_and_adam(params, g, state, LR, ADAM_EPS, CLIP)
+    return float(f["loss"])
+
+
+def cpu_sample(wl, sample_B, steps, warmup):
+    """Time the NumPy oracle (port of the reference TF graph) on the first `sample_B` examples of the workload."""
+    from oracle import icl_oracle as O
+    from imagecaptionlearn_py_b200 import core
+    small = dict(wl, B=sample_B)
+    bt = make_batch(small, 20171201)
+    tl = int(bt["seq_lengths"].max())
+    bt["sentences"] = bt["sentences"][:, :tl]              # dynamic_rnn stops at the batch maximum (sequence_length)
+    widths = core.get_widths(wl["start"], wl["depth"])
+    H = wl["H"]
+    box_w = bt["box_embeddings"].shape[1] if "box_embeddings" in bt else 0
+    cfg = dict(H=H, data_norm=wl["data_norm"],
+               heads=[dict(task=wl["task"], scope="", encoding_scheme="first_last_mention", n_layers=len(widths),
+                           widths=widths, activation="relu", weighted_classes=False,
+                           in_width=O.head_in_width(wl["task"], "first_last_mention", H, wl["F"], box_w), n_classes=wl["C"])])
+    rng = np.random.default_rng(7)
+    params = O.init_params(rng, cfg, E, np.float32)
+    state = {}
+    for _ in range(warmup):
+        oracle_train_step(params, cfg, bt, state, KEEP_IN, KEEP, rng)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle_train_step(params, cfg, bt, state, KEEP_IN, KEEP, rng)
+    dt = time.perf_counter() - t0
+    try:
+        from threadpoolctl import threadpool_info
+        cores = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        cores = os.cpu_count() or 1
+    return dict(value=sample_B * steps / dt, unit="captions/s", cores=int(cores), kind="port",
+                sample="%d train steps of the NumPy oracle (fp32, BLAS threads=%d) on %d captions of the same workload"
+                       % (steps, cores, sample_B), ms_per_step=1e3 * dt / steps, steps=steps)
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_B = min(wl["B"], 256)
+    r = cpu_sample(wl, sample_B, args.steps, args.warmup)
+    line = dict(metric="bilstm_train_captions_per_sec", value=r["value"], unit="captions/s", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload=args.workload, baseline_config=wl["cfg"], task=wl["task"], batch_per_step=sample_B,
+                            lstm_hidden=wl["H"], embed=E, padded_T=T_PAD,
+                            note="TensorFlow 1.x / Python 2 are not installable here: the reference's TF CPU graph is "
+                                 "restated in NumPy (oracle/icl_oracle.py) and timed on the host cores"),
+                cpu_baseline=dict(value=r["value"], unit="captions/s", cores=r["cores"], kind="port", sample=r["sample"]),
+                e2e=dict(value=r["value"], unit="captions/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- our arm (B200)
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="card2048", choices=sorted(WORKLOADS))
+    ap.add_argument("--gemm", default="tf32", choices=["tf32", "simt"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wl)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    from imagecaptionlearn_py_b200 import _cabi, core
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    bt = make_batch(wl, 20171201 + 1000 * rank)
+    core.reset_default_graph()
+    core.set_random_seeds()
+    with core.variable_scope("bidirectional_lstm"):
+        core.setup_bidirectional_lstm(wl["H"], wl["data_norm"], n_embedding_width=E)
+    box_w = bt["box_embeddings"].shape[1] if "box_embeddings" in bt else None
+    core.setup_core_architecture(wl["task"], "first_last_mention", wl["B"], wl["start"], wl["depth"], False, "relu", wl["C"],
+                                 wl["F"], box_embedding_width=box_w)
+    core.add_train_op(core.get_collection("loss")[0], LR, ADAM_EPS, CLIP)
+    sess = core.Session(max_seq_len=T_PAD, device=local, dist=bool(dist),
+                        gemm_mode=_cabi.GEMM_TCGEN05_TF32 if args.gemm == "tf32" else _cabi.GEMM_SIMT_FP32)
+    sess.ensure()
+    L = _cabi.lib()
+    train_op = core.get_collection("train_op")[0]
+    if dist:                                   # identical initial weights on every rank
+        flat = sess.param_tensor()
+        dist.broadcast(flat, 0)
+
+    # ---- resident-data throughput (`value`)
+    keepalive = []
+    b = sess.build_batch([bt], True, keepalive)
+    sess._bind_stream()
+    _cabi.check(L.icl_upload(sess.handle, C.byref(b)))
+    ns, nt, tm = C.c_int64(), C.c_int64(), C.c_int32()
+    _cabi.check(L.icl_batch_stats(sess.handle, C.byref(ns), C.byref(nt), C.byref(tm)))
+    n_seqs, n_tok, t_max = ns.value, nt.value, tm.value
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+
+    def resident_step(i):
+        seed = 1000 + i
+        if dist:
+            _cabi.check(L.icl_run_resident(sess.handle, _cabi.OP_GRADS, KEEP_IN, KEEP, seed))
+            dist.all_reduce(sess.grad_tensor(), op=dist.ReduceOp.SUM)
+            _cabi.check(L.icl_apply_update(sess.handle))
+        else:
+            _cabi.check(L.icl_run_resident(sess.handle, _cabi.OP_TRAIN, KEEP_IN, KEEP, seed))
+
+    for i in range(args.warmup):
+        resident_step(i)
+    torch.cuda.synchronize()
+    n0 = C.c_int64()
+    L.icl_kernel_launches(sess.handle, C.byref(n0))
+    clk, stop = [], threading.Event()
+    th = threading.Thread(target=sample_clocks, args=(stop, clk), daemon=True)
+    if rank == 0:
+        th.start()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    phases = np.zeros(_cabi.N_PHASES)
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()                           # L2 flush between timed iterations (untimed)
+        ev[i][0].record()
+        resident_step(args.warmup + i)
+        ev[i][1].record()
+        ph = (C.c_float * _cabi.N_PHASES)()
+        _cabi.check(L.icl_phase_ms(sess.handle, ph))     # synchronises; CUDA-event time of each kernel group of this step
+        phases += np.array(list(ph))
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    wall = time.perf_counter() - wall0
+    total_ms = sum(a.elapsed_time(b_) for a, b_ in ev)
+    n1 = C.c_int64()
+    L.icl_kernel_launches(sess.handle, C.byref(n1))
+    launches = n1.value - n0.value
+    if dist:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n_seqs / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through the reference-facing API with host buffers (`e2e`)
+    e2e_steps = max(5, args.steps // 3)
+    for i in range(2):
+        core.run_op(sess, train_op, [bt], KEEP_IN, KEEP, "first_last_mention", [wl["task"]], [""], True)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        core.run_op(sess, train_op, [bt], KEEP_IN, KEEP, "first_last_mention", [wl["task"]], [""], True)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    h2d, d2h = C.c_int64(), C.c_int64()
+    L.icl_copy_bytes(sess.handle, C.byref(h2d), C.byref(d2h))
+    stop.set()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)           # fallback: the profiling guide's sustained figure
+        tf32_peak = bf16_peak / 2.0                                       # kind::tf32 issues at half the kind::f16 rate
+        ph_ms = phases / args.steps
+        dom = int(np.argmax(ph_ms))
+        H = wl["H"]
+        phase_flops = {                                                  # algorithmic FLOPs per step, per kernel group
+            "proj_gemm": 2.0 * n_tok * E * 4 * H * 2, "rec_fwd": 2.0 * n_tok * H * 4 * H * 2,
+            "rec_bwd": 2.0 * n_tok * H * 4 * H * 2, "wgrad": 2.0 * n_tok * (E + H) * 4 * H * 2}
+        name = _cabi.PHASES[dom]
+        roof = dict(kernel=name, bound="tensor", unit="TFLOP/s", peak=tf32_peak,
+                    peak_source=("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32 issues at half the bf16 rate)"
+                                 if peaks else "fallback 1400/2"), traffic=None,
+                    ms_per_launch_group=float(ph_ms[dom]))
+        if name in phase_flops:
+            roof["achieved"] = phase_flops[name] / (ph_ms[dom] * 1e-3) / 1e12
+            roof["frac"] = roof["achieved"] / tf32_peak
+        else:
+            roof["achieved"], roof["frac"] = None, None
+        step_flops = flops_per_token(H) * n_tok
+        line = dict(metric="bilstm_train_captions_per_sec", value=value, unit="captions/s", n_gpus=world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="tf32" if args.gemm == "tf32" else "f32", data="synthetic",
+                    config=dict(workload=args.workload, baseline_config=wl["cfg"], task=wl["task"], batch_per_gpu=wl["B"],
+                                global_batch=wl["B"] * world, lstm_hidden=H, embed=E, padded_T=T_PAD, t_max=t_max,
+                                tokens_per_step_per_gpu=n_tok, keep_prob=[KEEP_IN, KEEP], clip_norm=CLIP,
+                                parallelism="dp%d" % world, l2="flushed between timed steps (256 MiB memset, untimed)",
+                                tokens_per_sec=world * n_tok / (ms_per_step * 1e-3),
+                                bilstm_tflops=step_flops / (ms_per_step * 1e-3) / 1e12,
+                                wall_ms_per_step_incl_flush=1e3 * wall / args.steps),
+                    phases_ms={n: float(v) for n, v in zip(_cabi.PHASES, ph_ms)}, roofline=roof,
+                    e2e=dict(value=world * n_seqs * e2e_steps / e2e_s, unit="captions/s", h2d_bytes_per_step=h2d.value,
+                             d2h_bytes_per_step=d2h.value, ms_per_step=1e3 * e2e_s / e2e_steps, steps=e2e_steps,
+                             api="core.run_op(sess, train_op, [batch_tensors], ...) with host float32 NumPy buffers"),
+                    gpu_launches=launches, clocks=clocks_summary(clk))
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = {k: v for k, v in cpu_sample(wl, min(wl["B"], 256), 3, 1).items()
+                                    if k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    sess.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

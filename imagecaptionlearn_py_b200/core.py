@@ -284,6 +284,16 @@ class Session(object):
             self._grad_view = torch.as_tensor(_Arr(), device="cuda:%d" % self.device)
         return self._grad_view
 
+    def param_tensor(self):
+        """torch view of the flat device parameter buffer (rank-0 broadcast of the initial weights)."""
+        import torch
+        p, n = C.c_void_p(), C.c_int64()
+        _cabi.check(_cabi.lib().icl_param_buffer(self.handle, C.byref(p), C.byref(n)))
+
+        class _Arr(object):
+            __cuda_array_interface__ = dict(shape=(n.value,), typestr="<f4", data=(p.value, False), version=2)
+        return torch.as_tensor(_Arr(), device="cuda:%d" % self.device)
+
     def build_batch(self, batch_tensor_list, include_labels, keepalive):
         g = self.graph
         b = _cabi.Batch()

@@ -9,10 +9,13 @@
 // One 128x128 output tile per CTA, BK = 32 fp32 (one 128-byte swizzle row), 3-stage mbarrier pipeline.
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2-5 = epilogue.
 // ~97 KB of shared memory -> two CTAs per SM, so one CTA's epilogue overlaps the other's main loop.
+// Epilogue: TMEM -> registers (one accumulator row per thread) -> a per-warp 32x33 staging tile in the (by then idle)
+// pipeline buffers -> row-wise, so every global access of the fused epilogue (bias, aux, C) is a coalesced 128-byte line.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <map>
 #include <tuple>
@@ -91,15 +94,19 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t r[32]) {
 // version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
 //  K-major tile  [rows][32 fp32]: 8-row groups are 1024 B apart (SBO); LBO unused for swizzled K-major (1).
 //  MN-major tile [mn/32][k][32 fp32]: 128-byte MN blocks are LBO apart, 8-k groups 1024 B apart (SBO).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//  32-bit MN-major operands have ONE legal swizzled layout: SWIZZLE_128B_BASE32B (=1), i.e. 32-byte chunks XOR-ed with
+//  (k-row % 4); its TMA twin is CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  Atom = 4 k-rows x 128 B, so an 8-deep MMA spans two
+//  atoms SBO = 512 B apart; 128-byte MN blocks are LBO apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((addr & 0x3FFFF) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(layout & 7) << 61;
   return d;
 }
+struct MnDescCfg { uint32_t layout, sbo, lbo, kstep; };   // MN-major descriptor parameters (env-overridable for bring-up)
 // Instruction descriptor: c_format F32 (1) [4,6); a/b format [7,10)/[10,13) (F16=0, BF16=1, TF32=2);
 // a_major [15], b_major [16] (1 = MN-major); N>>3 [17,23); M>>4 [24,29).
 __host__ __device__ constexpr uint32_t make_idesc(int fmt, bool a_mn, bool b_mn, int M, int N) {
@@ -109,7 +116,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, bool a_mn, bool b_mn,
 
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA,
-                                                             const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+                                                             const __grid_constant__ CUtensorMap tmB, const GemmArgs g, const MnDescCfg mn) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t sA = base, sB = base + TG_STAGES * TG_TILE_BYTES;
@@ -117,7 +124,12 @@ __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_consta
   const uint32_t full0 = bars, empty0 = bars + 8 * TG_STAGES, tmem_full = bars + 16 * TG_STAGES, tmem_slot = tmem_full + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TG_BM, n0 = blockIdx.x * TG_BN;
-  const int num_kb = (g.K + TG_BK - 1) / TG_BK;
+  // split-K (gridDim.z > 1): this CTA contracts k-blocks [kb0, kb0+num_kb) and adds its partial tile to C with red.global
+  const int total_kb = (g.K + TG_BK - 1) / TG_BK;
+  const int kb_per = (total_kb + gridDim.z - 1) / gridDim.z;
+  const int kb0 = blockIdx.z * kb_per;
+  const int num_kb = max(0, min(kb_per, total_kb - kb0));
+  if (num_kb == 0) return;                                             // uniform per CTA, before any barrier / TMEM allocation
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TG_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -146,15 +158,15 @@ __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_consta
         const uint32_t a = sA + s * TG_TILE_BYTES, b = sB + s * TG_TILE_BYTES;
         if (A_MN) {
 #pragma unroll
-          for (int j = 0; j < TG_BM / 32; j++) tma_load_2d(a + j * (32 * TG_BK * 4), &tmA, m0 + 32 * j, kb * TG_BK, fb);
+          for (int j = 0; j < TG_BM / 32; j++) tma_load_2d(a + j * (32 * TG_BK * 4), &tmA, m0 + 32 * j, (kb0 + kb) * TG_BK, fb);
         } else {
-          tma_load_2d(a, &tmA, kb * TG_BK, m0, fb);
+          tma_load_2d(a, &tmA, (kb0 + kb) * TG_BK, m0, fb);
         }
         if (B_MN) {
 #pragma unroll
-          for (int j = 0; j < TG_BN / 32; j++) tma_load_2d(b + j * (32 * TG_BK * 4), &tmB, n0 + 32 * j, kb * TG_BK, fb);
+          for (int j = 0; j < TG_BN / 32; j++) tma_load_2d(b + j * (32 * TG_BK * 4), &tmB, n0 + 32 * j, (kb0 + kb) * TG_BK, fb);
         } else {
-          tma_load_2d(b, &tmB, kb * TG_BK, n0, fb);
+          tma_load_2d(b, &tmB, (kb0 + kb) * TG_BK, n0, fb);
         }
       }
     }
@@ -168,34 +180,38 @@ __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_consta
         const uint32_t a = sA + s * TG_TILE_BYTES, b = sB + s * TG_TILE_BYTES;
 #pragma unroll
         for (int kk = 0; kk < TG_BK / 8; kk++) {                       // UMMA_K = 8 for tf32
-          const uint64_t ad = A_MN ? make_smem_desc(a + kk * 1024, 32 * TG_BK * 4, 1024) : make_smem_desc(a + kk * 32, 16, 1024);
-          const uint64_t bd = B_MN ? make_smem_desc(b + kk * 1024, 32 * TG_BK * 4, 1024) : make_smem_desc(b + kk * 32, 16, 1024);
+          const uint64_t ad = A_MN ? make_smem_desc(a + kk * mn.kstep, mn.lbo, mn.sbo, mn.layout) : make_smem_desc(a + kk * 32, 16, 1024);
+          const uint64_t bd = B_MN ? make_smem_desc(b + kk * mn.kstep, mn.lbo, mn.sbo, mn.layout) : make_smem_desc(b + kk * 32, 16, 1024);
           tc_mma_tf32(tmem_acc, ad, bd, idesc, (kb | kk) != 0);
         }
         tc_commit(empty0 + 8 * s);                                     // frees the smem stage when these MMAs retire
       }
       tc_commit(tmem_full);
     }
-  } else {                                                             // ---- epilogue: TMEM -> registers -> HBM
-    mbar_wait(tmem_full, 0);
+  } else {                                                             // ---- epilogue: TMEM -> registers -> smem -> HBM
+    mbar_wait(tmem_full, 0);                                           // every MMA has retired: the stage buffers are idle
     tc_fence_after();
     const int q = warp & 3;                                            // a warp may only touch TMEM lanes [32*(warp%4), +32)
-    const int m = m0 + q * 32 + lane;
+    float* stg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))) + q * (32 * 33);
+    const int mrow0 = m0 + q * 32;
 #pragma unroll 1
     for (int c = 0; c < TG_BN; c += 32) {
+      if (n0 + c >= g.N) break;
       uint32_t r[32];
       tc_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + c, r);
-      if (m < g.M) {
-        float* crow = g.C + (long)m * g.ldc;
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-          const int n = n0 + c + j;
-          if (n < g.N) {
-            float cold = g.epi.beta != 0.0f ? crow[n] : 0.0f;
-            crow[n] = epilogue_apply(g.epi, __uint_as_float(r[j]), m, n, g.N, cold);
-          }
+      for (int j = 0; j < 32; j++) stg[lane * 33 + j] = __uint_as_float(r[j]);
+      __syncwarp();
+      const int n = n0 + c + lane;
+      if (n < g.N) {
+        const int rows = min(32, g.M - mrow0);
+        for (int rr = 0; rr < rows; rr++) {
+          const long m = mrow0 + rr;
+          if (gridDim.z > 1) atomicAdd(g.C + m * g.ldc + n, stg[rr * 33 + lane]);       // C pre-zeroed by the host
+          else g.C[m * g.ldc + n] = epilogue_apply(g.epi, stg[rr * 33 + lane], m, n, g.N);
         }
       }
+      __syncwarp();
     }
   }
   tc_fence_before();
@@ -212,8 +228,19 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static PFN_encodeTiled g_encode = nullptr;
 
+static MnDescCfg g_mn = {1u, 512u, 32u * TG_BK * 4u, 1024u};
+static int g_mn_tma_swizzle = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+static void tcgen05_read_env() {
+  if (const char* e = getenv("ICL_MN_LAYOUT")) g_mn.layout = (uint32_t)atoi(e);
+  if (const char* e = getenv("ICL_MN_SBO")) g_mn.sbo = (uint32_t)atoi(e);
+  if (const char* e = getenv("ICL_MN_LBO")) g_mn.lbo = (uint32_t)atoi(e);
+  if (const char* e = getenv("ICL_MN_KSTEP")) g_mn.kstep = (uint32_t)atoi(e);
+  if (const char* e = getenv("ICL_MN_TMASW")) g_mn_tma_swizzle = atoi(e);
+}
+
 static int tcgen05_gemm_init() {
   if (g_encode) return 0;
+  tcgen05_read_env();
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return -1;
@@ -226,10 +253,10 @@ static int tcgen05_gemm_init() {
 }
 
 struct TmaCache {
-  std::map<std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t, uint32_t>, CUtensorMap> maps;
+  std::map<std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t, uint32_t, int>, CUtensorMap> maps;
   // 2-D fp32 tensor: dim0 (contiguous) x dim1 with row pitch ld (floats); box = box0 x box1, 128B swizzle, zero OOB fill
-  int get(const float* ptr, uint64_t dim0, uint64_t dim1, uint64_t ld, uint32_t box0, uint32_t box1, CUtensorMap* out) {
-    auto key = std::make_tuple((const void*)ptr, dim0, dim1, ld, box0, box1);
+  int get(const float* ptr, uint64_t dim0, uint64_t dim1, uint64_t ld, uint32_t box0, uint32_t box1, int swizzle, CUtensorMap* out) {
+    auto key = std::make_tuple((const void*)ptr, dim0, dim1, ld, box0, box1, swizzle);
     auto it = maps.find(key);
     if (it != maps.end()) { *out = it->second; return 0; }
     cuuint64_t dims[2] = {dim0, dim1};
@@ -238,7 +265,7 @@ struct TmaCache {
     cuuint32_t estr[2] = {1, 1};
     CUtensorMap tm;
     CUresult r = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          (CUtensorMapSwizzle)swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return (int)r;
     if (maps.size() > 4096) maps.clear();
     maps[key] = tm;
@@ -250,25 +277,26 @@ struct TmaCache {
 static bool tcgen05_gemm_supported(const GemmArgs& g, bool a_mn, bool b_mn) {
   // TMA: 16-byte aligned base and row pitch; tiny problems stay on the SIMT kernel
   if (((uintptr_t)g.A & 15) || ((uintptr_t)g.B & 15) || (g.lda & 3) || (g.ldb & 3)) return false;
-  if (g.N < 16 || g.M < 16 || g.K < 8) return false;
+  if (g.N < 1 || g.M < 1 || g.K < 1) return false;
   (void)a_mn; (void)b_mn;
   return true;
 }
 
-static int tcgen05_gemm_launch(TmaCache& cache, cudaStream_t st, bool a_mn, bool b_mn, const GemmArgs& g) {
+static int tcgen05_gemm_launch(TmaCache& cache, cudaStream_t st, bool a_mn, bool b_mn, const GemmArgs& g, int splits = 1) {
   CUtensorMap ta, tb;
   int r;
-  if (a_mn) r = cache.get(g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda, 32, TG_BK, &ta);
-  else r = cache.get(g.A, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)g.lda, TG_BK, TG_BM, &ta);
+  const int swk = (int)CU_TENSOR_MAP_SWIZZLE_128B;
+  if (a_mn) r = cache.get(g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda, 32, TG_BK, g_mn_tma_swizzle, &ta);
+  else r = cache.get(g.A, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)g.lda, TG_BK, TG_BM, swk, &ta);
   if (r) return 1000 + r;
-  if (b_mn) r = cache.get(g.B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb, 32, TG_BK, &tb);
-  else r = cache.get(g.B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb, TG_BK, TG_BN, &tb);
+  if (b_mn) r = cache.get(g.B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb, 32, TG_BK, g_mn_tma_swizzle, &tb);
+  else r = cache.get(g.B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb, TG_BK, TG_BN, swk, &tb);
   if (r) return 2000 + r;
-  dim3 grid((g.N + TG_BN - 1) / TG_BN, (g.M + TG_BM - 1) / TG_BM);
-  if (!a_mn && !b_mn) k_gemm_tcgen05<false, false><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, g);
-  else if (!a_mn && b_mn) k_gemm_tcgen05<false, true><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, g);
-  else if (a_mn && b_mn) k_gemm_tcgen05<true, true><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, g);
-  else k_gemm_tcgen05<true, false><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, g);
+  dim3 grid((g.N + TG_BN - 1) / TG_BN, (g.M + TG_BM - 1) / TG_BM, splits);
+  if (!a_mn && !b_mn) k_gemm_tcgen05<false, false><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, g, g_mn);
+  else if (!a_mn && b_mn) k_gemm_tcgen05<false, true><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, g, g_mn);
+  else if (a_mn && b_mn) k_gemm_tcgen05<true, true><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, g, g_mn);
+  else k_gemm_tcgen05<true, false><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, g, g_mn);
   return cudaGetLastError() == cudaSuccess ? 0 : 3000;
 }
 

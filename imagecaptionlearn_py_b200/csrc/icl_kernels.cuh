@@ -1,6 +1,13 @@
-// Device kernels for the BiLSTM + mention-span-head path (everything except the tcgen05 GEMM).
-// All arithmetic is fp32; dropout masks are a pure function of (seed, stream, element index) so forward and
-// backward regenerate identical masks and nothing is stored.
+// Device kernels for the BiLSTM + mention-span-head path (everything except the tcgen05 GEMMs and the persistent
+// recurrent kernels).  All arithmetic is fp32; dropout masks are a pure function of (seed, stream, element index)
+// so forward and backward regenerate identical masks and nothing is stored.
+//
+// HBM layout of the recurrent tensors ("step-major"): sequences are ranked by length (descending, stable); step k
+// of a direction touches the first nact[k] ranks, and all per-token tensors of that direction (input rows, gates,
+// h, c, dH) keep step k's rows contiguously at [off[k], off[k]+nact[k]).  Forward step k consumes token k, backward
+// step k consumes token len-1-k (reverse_sequence, nn_utils/core.py:324-329), so token (s,t) of direction d lives
+// at row off[d ? len[s]-1-t : t] + rank[s].  Every per-step operand is therefore one dense row block that a single
+// TMA box can fetch -- no gathers inside the recurrence.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -54,7 +61,17 @@ struct Drop {          // dropout descriptor for an epilogue / elementwise kerne
   int64_t row_gid0;    // global id of row 0
 };
 
-// ----------------------------------------------------------------------------- activations
+// ----------------------------------------------------------------------------- numerics helpers
+// The tensor cores read fp32 containers as TF32 by TRUNCATING the low 13 mantissa bits (a systematic ~ -1e-3
+// relative bias per product).  Every tensor that is only ever an MMA operand is therefore stored pre-rounded
+// with round-to-nearest (cvt.rna), which makes the truncation a no-op and the error unbiased and ~4x smaller.
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float maybe_round(float x, int on) { return on ? tf32_rna(x) : x; }
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ float act_fwd(float z, int act) {
@@ -86,10 +103,10 @@ struct Epilogue {
   Drop drop;           // mode 1: applied to output; mode 2: mask of the layer whose output is `aux`
   const float* aux;    // mode 2: post-dropout output y of the producing layer, [M, ldaux]
   long ldaux;
-  float beta;          // 0: overwrite, 1: accumulate into C
+  int round_out;       // store the result RNA-rounded to TF32 (it is only an MMA operand downstream)
 };
 
-__device__ __forceinline__ float epilogue_apply(const Epilogue& e, float v, long m, long n, int N, float cold) {
+__device__ __forceinline__ float epilogue_apply(const Epilogue& e, float v, long m, long n, int N) {
   if (e.bias) v += e.bias[n];
   if (e.mode == EPI_BIAS_ACT_DROP) {
     v = act_fwd(v, e.act);
@@ -107,37 +124,16 @@ __device__ __forceinline__ float epilogue_apply(const Epilogue& e, float v, long
     }
     v *= act_bwd_from_out(a, e.act);
   }
-  if (e.beta != 0.0f) v += e.beta * cold;
-  return v;
+  return e.round_out ? tf32_rna(v) : v;
 }
 
-// ----------------------------------------------------------------------------- row maps for the recurrent steps
-// Packed, padded layout: sequence s owns rows start[s] .. start[s]+len[s] (len+1 rows).  For direction d and
-// token q: data row = start+q+d (x-projection, gates, dZ, h_prev, c_prev); state-out row = start+q+1-d.
-struct SeqMap {
-  const int* order;   // sequences sorted by length, descending
-  const int* start;   // [S]
-  const int* lens;    // [S]
-  int k;              // recurrence step
-  int dir;            // 0 fw, 1 bw
-  int mode;           // 0: identity rows; 1: data row of sorted position m at step k; 2: seq id (per-seq buffers)
-};
-__device__ __forceinline__ long seqmap_row(const SeqMap& s, int m) {
-  if (s.mode == 0) return m;
-  int sq = s.order[m];
-  if (s.mode == 2) return sq;
-  int q = s.dir ? (s.lens[sq] - 1 - s.k) : s.k;
-  return (long)s.start[sq] + q + s.dir;
-}
-
-// ----------------------------------------------------------------------------- SIMT fp32 GEMM (validation path and tiny-N layers)
-// C[M,N] = epi(A*B).  A(m,k) = A_KMAJOR ? A[row(m)*lda+k] : A[k*lda+m];  B(k,n) = B_KMAJOR ? B[n*ldb+k] : B[k*ldb+n].
+// ----------------------------------------------------------------------------- SIMT fp32 GEMM (validation mode and tiny / unaligned shapes)
+// C[M,N] = epi(A*B).  A(m,k) = A_KMAJOR ? A[m*lda+k] : A[k*lda+m];  B(k,n) = B_KMAJOR ? B[n*ldb+k] : B[k*ldb+n].
 struct GemmArgs {
   const float* A; long lda;
   const float* B; long ldb;
   float* C; long ldc;
   int M, N, K;
-  SeqMap amap, cmap;     // optional row gathers (A must be K-major when amap.mode != 0)
   Epilogue epi;
 };
 
@@ -158,7 +154,7 @@ __global__ void __launch_bounds__(256) k_gemm_simt(const GemmArgs g) {
       if (A_KMAJOR) { kk = e % BK; mm = e / BK; } else { mm = e % BM; kk = e / BM; }
       float v = 0.0f;
       if (m0 + mm < g.M && k0 + kk < g.K) {
-        if (A_KMAJOR) v = g.A[seqmap_row(g.amap, m0 + mm) * g.lda + k0 + kk];
+        if (A_KMAJOR) v = g.A[(long)(m0 + mm) * g.lda + k0 + kk];
         else v = g.A[(long)(k0 + kk) * g.lda + m0 + mm];
       }
       As[kk][mm] = v;
@@ -190,24 +186,33 @@ __global__ void __launch_bounds__(256) k_gemm_simt(const GemmArgs g) {
   for (int i = 0; i < 4; i++) {
     int m = m0 + ty * 4 + i;
     if (m >= g.M) continue;
-    long crow = seqmap_row(g.cmap, m);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       int n = n0 + tx + 16 * j;
       if (n >= g.N) continue;
-      float* p = g.C + crow * g.ldc + n;
-      float cold = g.epi.beta != 0.0f ? *p : 0.0f;
-      *p = epilogue_apply(g.epi, acc[i][j], m, n, g.N, cold);
+      g.C[(long)m * g.ldc + n] = epilogue_apply(g.epi, acc[i][j], m, n, g.N);
     }
   }
 }
 
+// ----------------------------------------------------------------------------- step-major layout
+struct StepLayout {
+  const int* off;    // [Tmax+1] first row of step k
+  const int* nact;   // [Tmax]   sequences still running at step k
+  const int* rank;   // [S]      rank of sequence s in the length-sorted order
+  const int* lens;   // [S]
+};
+__device__ __forceinline__ long token_row(const StepLayout& L, int dir, int s, int t) {
+  int k = dir ? (L.lens[s] - 1 - t) : t;
+  return (long)L.off[k] + L.rank[s];
+}
+
 // ----------------------------------------------------------------------------- input preparation
 // One warp per valid token: optional l2-normalise (core.py:289-290), then the two directions' input dropout
-// (core.py:309-312) written to the padded layouts Xd_fw[start+t], Xd_bw[start+t+1].
+// (core.py:309-312), written to each direction's step-major row; TF32-rounded when the rows feed the tensor cores.
 __global__ void k_prep_x(const float* __restrict__ xraw, const int* __restrict__ tok_seq, const int* __restrict__ tokstart,
-                         const int* __restrict__ start, int ntok, int E, int Tcap, int data_norm, float keep_in,
-                         uint64_t seed, int64_t seq_gid0, float* __restrict__ xfw, float* __restrict__ xbw) {
+                         StepLayout L, int ntok, int E, int Tcap, int data_norm, float keep_in, uint64_t seed,
+                         int64_t seq_gid0, int round_ops, float* __restrict__ xfw, float* __restrict__ xbw) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= ntok) return;
   int s = tok_seq[warp];
@@ -221,76 +226,119 @@ __global__ void k_prep_x(const float* __restrict__ xraw, const int* __restrict__
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     scale = rsqrtf(fmaxf(ss, 1e-12f));
   }
-  long rfw = (long)start[s] + t, rbw = rfw + 1;
+  long rfw = token_row(L, 0, s, t), rbw = token_row(L, 1, s, t);
   uint64_t base = (uint64_t)((seq_gid0 + s) * Tcap + t) * (uint64_t)E;
-  for (int e4 = lane * 4; e4 < E; e4 += 128) {
+  for (int e4 = lane * 4; e4 < E; e4 += 128) {       // E % 4 == 0 is enforced at create
     float mf[4] = {1, 1, 1, 1}, mb[4] = {1, 1, 1, 1};
-    if (keep_in < 1.0f) {      // E % 4 == 0 is enforced at create
+    if (keep_in < 1.0f) {
       drop4(seed, STREAM_IN_FW, (base + e4) >> 2, keep_in, mf);
       drop4(seed, STREAM_IN_BW, (base + e4) >> 2, keep_in, mb);
     }
+    float4 x = *reinterpret_cast<const float4*>(src + e4);
+    float xv[4] = {x.x * scale, x.y * scale, x.z * scale, x.w * scale}, vf[4], vb[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      float v = src[e4 + j] * scale;
-      float vf = v, vb = v;
-      if (keep_in < 1.0f) { vf = v / keep_in * mf[j]; vb = v / keep_in * mb[j]; }
-      xfw[rfw * E + e4 + j] = vf;
-      xbw[rbw * E + e4 + j] = vb;
+      vf[j] = xv[j]; vb[j] = xv[j];
+      if (keep_in < 1.0f) { vf[j] = xv[j] / keep_in * mf[j]; vb[j] = xv[j] / keep_in * mb[j]; }
+      vf[j] = maybe_round(vf[j], round_ops); vb[j] = maybe_round(vb[j], round_ops);
+    }
+    *reinterpret_cast<float4*>(xfw + rfw * E + e4) = make_float4(vf[0], vf[1], vf[2], vf[3]);
+    *reinterpret_cast<float4*>(xbw + rbw * E + e4) = make_float4(vb[0], vb[1], vb[2], vb[3]);
+  }
+}
+
+// ----------------------------------------------------------------------------- LSTM cell (BasicLSTMCell: i,j,f,o, forget_bias 1.0)
+// shared by the per-step kernels here and the fused epilogues of the persistent kernels
+struct CellOut { float si, tj, sf, so, c, h; };
+__device__ __forceinline__ CellOut lstm_cell(float zi, float zj, float zf, float zo, float cprev) {
+  CellOut o;
+  o.si = sigmoidf_(zi); o.tj = tanhf(zj); o.sf = sigmoidf_(zf + 1.0f); o.so = sigmoidf_(zo);
+  o.c = cprev * o.sf + o.si * o.tj;
+  o.h = tanhf(o.c) * o.so;
+  return o;
+}
+struct CellGrad { float di, dj, df, dg_o, dc_prev; };
+__device__ __forceinline__ CellGrad lstm_cell_bwd(float si, float tj, float sf, float so, float c, float cprev, float dh,
+                                                  float dc_in) {
+  CellGrad g;
+  float tc = tanhf(c);
+  float dc = dc_in + dh * so * (1.0f - tc * tc);
+  g.di = dc * tj * si * (1.0f - si);
+  g.dj = dc * si * (1.0f - tj * tj);
+  g.df = dc * cprev * sf * (1.0f - sf);
+  g.dg_o = dh * tc * so * (1.0f - so);
+  g.dc_prev = dc * sf;
+  return g;
+}
+
+// Per-step forward cell (the non-persistent path): z = Zx (+ R, the recurrent product of this step) for rows
+// [0,n) of step k.  Z rows are overwritten with the activated gates for the backward pass.  Each thread = 4 units.
+__global__ void k_lstm_cell_fwd(float* __restrict__ Zk, const float* __restrict__ R, const float* __restrict__ Cprev,
+                                float* __restrict__ Ck, float* __restrict__ Hk, float* __restrict__ Hp_next, int n, int n_next,
+                                int H, int round_ops) {
+  int q = H >> 2;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)n * q) return;
+  int m = (int)(i / q), u = (int)(i % q) * 4;
+  float* z = Zk + (long)m * 4 * H + u;
+  float4 g[4];
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    g[a] = *reinterpret_cast<float4*>(z + a * H);
+    if (R) {
+      float4 r = *reinterpret_cast<const float4*>(R + (long)m * 4 * H + a * H + u);
+      g[a].x += r.x; g[a].y += r.y; g[a].z += r.z; g[a].w += r.w;
     }
   }
-}
-
-// zero the per-sequence pad rows: which=0: fw-style (row start+len), which=1: bw-style (row start)
-__global__ void k_zero_rows(float* buf, const int* __restrict__ start, const int* __restrict__ lens, int S, int W, int at_end) {
-  int s = blockIdx.x;
-  if (s >= S) return;
-  long r = (long)start[s] + (at_end ? lens[s] : 0);
-  for (int e = threadIdx.x; e < W; e += blockDim.x) buf[r * W + e] = 0.0f;
-}
-
-// ----------------------------------------------------------------------------- LSTM cell, forward (BasicLSTMCell, i,j,f,o, forget_bias 1)
-// z (full pre-activation, x-projection + bias + recurrent term) is in Z[data row]; overwritten with the
-// activated gates (sig i, tanh j, sig f, sig o) for the backward pass.
-__global__ void k_lstm_cell_fwd(float* __restrict__ Z, float* __restrict__ HP, float* __restrict__ CP, SeqMap sm, int n_active, int H) {
-  int pos = blockIdx.x;
-  if (pos >= n_active) return;
-  int sq = sm.order[pos];
-  int q = sm.dir ? (sm.lens[sq] - 1 - sm.k) : sm.k;
-  long row = (long)sm.start[sq] + q + sm.dir, hrow = (long)sm.start[sq] + q + 1 - sm.dir;
-  float* z = Z + row * 4 * H;
-  for (int u = threadIdx.x; u < H; u += blockDim.x) {
-    float si = sigmoidf_(z[u]), tj = tanhf(z[H + u]), sf = sigmoidf_(z[2 * H + u] + 1.0f), so = sigmoidf_(z[3 * H + u]);
-    float c = CP[row * H + u] * sf + si * tj;
-    float h = tanhf(c) * so;
-    z[u] = si; z[H + u] = tj; z[2 * H + u] = sf; z[3 * H + u] = so;
-    CP[hrow * H + u] = c;
-    HP[hrow * H + u] = h;
+  float4 cp = Cprev ? *reinterpret_cast<const float4*>(Cprev + (long)m * H + u) : make_float4(0, 0, 0, 0);
+  const float* gi = &g[0].x; const float* gj = &g[1].x; const float* gf = &g[2].x; const float* go = &g[3].x;
+  const float* cpv = &cp.x;
+  float si[4], tj[4], sf[4], so[4], c[4], h[4], hr[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    CellOut o = lstm_cell(gi[j], gj[j], gf[j], go[j], cpv[j]);
+    si[j] = o.si; tj[j] = o.tj; sf[j] = o.sf; so[j] = o.so; c[j] = o.c; h[j] = o.h; hr[j] = maybe_round(o.h, round_ops);
   }
+  *reinterpret_cast<float4*>(z) = make_float4(si[0], si[1], si[2], si[3]);
+  *reinterpret_cast<float4*>(z + H) = make_float4(tj[0], tj[1], tj[2], tj[3]);
+  *reinterpret_cast<float4*>(z + 2 * H) = make_float4(sf[0], sf[1], sf[2], sf[3]);
+  *reinterpret_cast<float4*>(z + 3 * H) = make_float4(so[0], so[1], so[2], so[3]);
+  *reinterpret_cast<float4*>(Ck + (long)m * H + u) = make_float4(c[0], c[1], c[2], c[3]);
+  *reinterpret_cast<float4*>(Hk + (long)m * H + u) = make_float4(h[0], h[1], h[2], h[3]);
+  if (m < n_next) *reinterpret_cast<float4*>(Hp_next + (long)m * H + u) = make_float4(hr[0], hr[1], hr[2], hr[3]);
 }
 
-// backward of the cell at one step: gates in G[data row], writes dZ[data row]; carries dh (recurrent) and dc per sequence
-__global__ void k_lstm_cell_bwd(const float* G, const float* __restrict__ CP, const float* __restrict__ dHout,
-                                float* dZ /* may alias G: in-place gates -> dZ */, float* __restrict__ dhrec, float* __restrict__ dccarry,
-                                SeqMap sm, int n_active, int H) {
-  int pos = blockIdx.x;
-  if (pos >= n_active) return;
-  int sq = sm.order[pos];
-  int q = sm.dir ? (sm.lens[sq] - 1 - sm.k) : sm.k;
-  long row = (long)sm.start[sq] + q + sm.dir, hrow = (long)sm.start[sq] + q + 1 - sm.dir;
-  const float* g = G + row * 4 * H;
-  float* dz = dZ + row * 4 * H;
-  for (int u = threadIdx.x; u < H; u += blockDim.x) {
-    float si = g[u], tj = g[H + u], sf = g[2 * H + u], so = g[3 * H + u];
-    float c = CP[hrow * H + u], cprev = CP[row * H + u];
-    float tc = tanhf(c);
-    float dh = dHout[hrow * H + u] + dhrec[(long)sq * H + u];
-    float dc = dccarry[(long)sq * H + u] + dh * so * (1.0f - tc * tc);
-    dz[u] = dc * tj * si * (1.0f - si);
-    dz[H + u] = dc * si * (1.0f - tj * tj);
-    dz[2 * H + u] = dc * cprev * sf * (1.0f - sf);
-    dz[3 * H + u] = dh * tc * so * (1.0f - so);
-    dccarry[(long)sq * H + u] = dc * sf;
+// Per-step backward cell: gates in Zk rows -> dZ (in place); dh = dHout + dhrec (rank-indexed carry), dc carry.
+__global__ void k_lstm_cell_bwd(float* __restrict__ Zk, const float* __restrict__ Ck, const float* __restrict__ Cprev,
+                                const float* __restrict__ dHk, const float* __restrict__ dhrec, float* __restrict__ dcc, int n, int H,
+                                int round_ops) {
+  int q = H >> 2;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)n * q) return;
+  int m = (int)(i / q), u = (int)(i % q) * 4;
+  float* z = Zk + (long)m * 4 * H + u;
+  float4 g4[4];
+#pragma unroll
+  for (int a = 0; a < 4; a++) g4[a] = *reinterpret_cast<float4*>(z + a * H);
+  float4 c4 = *reinterpret_cast<const float4*>(Ck + (long)m * H + u);
+  float4 cp4 = Cprev ? *reinterpret_cast<const float4*>(Cprev + (long)m * H + u) : make_float4(0, 0, 0, 0);
+  float4 dh4 = *reinterpret_cast<const float4*>(dHk + (long)m * H + u);
+  float4 dr4 = *reinterpret_cast<const float4*>(dhrec + (long)m * H + u);
+  float4 dc4 = *reinterpret_cast<const float4*>(dcc + (long)m * H + u);
+  const float *si = &g4[0].x, *tj = &g4[1].x, *sf = &g4[2].x, *so = &g4[3].x, *c = &c4.x, *cp = &cp4.x, *dh = &dh4.x, *dr = &dr4.x,
+              *dc = &dc4.x;
+  float di[4], dj[4], df[4], dgo[4], dcp[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    CellGrad g = lstm_cell_bwd(si[j], tj[j], sf[j], so[j], c[j], cp[j], dh[j] + dr[j], dc[j]);
+    di[j] = maybe_round(g.di, round_ops); dj[j] = maybe_round(g.dj, round_ops); df[j] = maybe_round(g.df, round_ops);
+    dgo[j] = maybe_round(g.dg_o, round_ops); dcp[j] = g.dc_prev;
   }
+  *reinterpret_cast<float4*>(z) = make_float4(di[0], di[1], di[2], di[3]);
+  *reinterpret_cast<float4*>(z + H) = make_float4(dj[0], dj[1], dj[2], dj[3]);
+  *reinterpret_cast<float4*>(z + 2 * H) = make_float4(df[0], df[1], df[2], df[3]);
+  *reinterpret_cast<float4*>(z + 3 * H) = make_float4(dgo[0], dgo[1], dgo[2], dgo[3]);
+  *reinterpret_cast<float4*>(dcc + (long)m * H + u) = make_float4(dcp[0], dcp[1], dcp[2], dcp[3]);
 }
 
 // ----------------------------------------------------------------------------- span gather + concat (core.py:335-440)
@@ -303,35 +351,33 @@ struct SlotTable {
   const float* dense[16];  // kind 1: [B,width]
 };
 
-// one block per example; output dropout of the LSTM (core.py:312) is applied here, on the gathered rows
-__global__ void k_gather_concat(SlotTable st, const float* __restrict__ hp_fw, const float* __restrict__ hp_bw,
-                                const int* __restrict__ start, const int* __restrict__ lens, int H, int Tcap, int D0,
-                                Drop drop, float* __restrict__ out) {
+// one block per example; the LSTM's output dropout (core.py:312) is applied here, on the gathered rows.
+// batch_input is only ever a GEMM operand (layer-1 forward, layer-1 weight gradient): stored TF32-rounded.
+__global__ void k_gather_concat(SlotTable st, const float* __restrict__ h_fw, const float* __restrict__ h_bw, StepLayout L,
+                                int H, int Tcap, int D0, Drop drop, int round_ops, float* __restrict__ out) {
   int b = blockIdx.x;
   float* o = out + (long)b * D0;
   for (int sl = 0; sl < st.n_slots; sl++) {
     if (st.kind[sl] == 1) {
       const float* src = st.dense[sl] + (long)b * st.width[sl];
-      for (int e = threadIdx.x; e < st.width[sl]; e += blockDim.x) o[st.col[sl] + e] = src[e];
+      for (int e = threadIdx.x; e < st.width[sl]; e += blockDim.x) o[st.col[sl] + e] = maybe_round(src[e], round_ops);
     } else {
       const int* ix = st.idx[sl] + b * 3;
       int d = ix[0], s = ix[1], w = ix[2];
-      bool valid = w < lens[s];            // dynamic_rnn emits zeros past the sequence length
-      long row = (long)start[s] + w + 1 - d;
-      const float* src = (d ? hp_bw : hp_fw) + row * H;
+      bool valid = w < L.lens[s];            // dynamic_rnn emits zeros past the sequence length
+      const float* src = (d ? h_bw : h_fw) + (valid ? token_row(L, d, s, w) : 0) * H;
       uint64_t base = (uint64_t)((drop.row_gid0 + s) * Tcap + w) * (uint64_t)H;
       for (int u = threadIdx.x; u < H; u += blockDim.x) {
         float v = valid ? src[u] : 0.0f;
         if (drop.keep < 1.0f) v = v / drop.keep * drop1(drop.seed, STREAM_OUT_FW + d, base + u, drop.keep);
-        o[st.col[sl] + u] = v;
+        o[st.col[sl] + u] = maybe_round(v, round_ops);
       }
     }
   }
 }
 
-// backward: scatter-add d(batch_input) into dHout_fw/bw (pre-dropout gradient, dropout scaling applied here)
-__global__ void k_scatter_spans(SlotTable st, const float* __restrict__ dbi, const int* __restrict__ start,
-                                const int* __restrict__ lens, int H, int Tcap, int D0, Drop drop,
+// backward: scatter-add d(batch_input) into dH_fw/bw (pre-dropout gradient, dropout scaling applied here)
+__global__ void k_scatter_spans(SlotTable st, const float* __restrict__ dbi, StepLayout L, int H, int Tcap, int D0, Drop drop,
                                 float* __restrict__ dh_fw, float* __restrict__ dh_bw) {
   int b = blockIdx.x;
   const float* g = dbi + (long)b * D0;
@@ -339,9 +385,8 @@ __global__ void k_scatter_spans(SlotTable st, const float* __restrict__ dbi, con
     if (st.kind[sl] == 1) continue;
     const int* ix = st.idx[sl] + b * 3;
     int d = ix[0], s = ix[1], w = ix[2];
-    if (w >= lens[s]) continue;
-    long row = (long)start[s] + w + 1 - d;
-    float* dst = (d ? dh_bw : dh_fw) + row * H;
+    if (w >= L.lens[s]) continue;
+    float* dst = (d ? dh_bw : dh_fw) + token_row(L, d, s, w) * H;
     uint64_t base = (uint64_t)((drop.row_gid0 + s) * Tcap + w) * (uint64_t)H;
     for (int u = threadIdx.x; u < H; u += blockDim.x) {
       float v = g[st.col[sl] + u];
@@ -390,7 +435,7 @@ __global__ void k_softmax_ce(const float* __restrict__ a, int K, const float* __
   if (y) { row_loss[b] = loss * scale; row_correct[b] = (am == ay) ? 1.0f : 0.0f; }
 }
 
-// deterministic single-block sum of n floats into out[0] (and mean into out[1])
+// deterministic single-block sum of n floats into out[0] (divided by mean_div when > 0)
 __global__ void k_reduce_sum(const float* __restrict__ v, int n, float* out, float mean_div) {
   __shared__ double sh[256];
   double s = 0.0;
@@ -420,7 +465,7 @@ __global__ void k_colsum(const float* __restrict__ X, long rows, int N, long ld,
     out[c] = t;
   }
 }
-// wide variant: many row-blocks accumulate with atomics (for the [Np,4H] LSTM dZ)
+// wide variant: many row-blocks accumulate with atomics (for the [Ntok,4H] LSTM dZ)
 __global__ void k_colsum_atomic(const float* __restrict__ X, long rows, int N, long ld, float* __restrict__ out, int rows_per_block) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= N) return;
@@ -435,10 +480,14 @@ __global__ void k_colsum_atomic(const float* __restrict__ X, long rows, int N, l
 __global__ void k_sumsq_partial(const float* __restrict__ g, long n, double* __restrict__ partial) {
   __shared__ double sh[256];
   double s = 0.0;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    double v = g[i];
-    s += v * v;
+  long n4 = n >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 v = g4[i];
+    s += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long i = n4 << 2; i < n; i++) s += (double)g[i] * g[i];
   sh[threadIdx.x] = s;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
@@ -459,28 +508,42 @@ __global__ void k_sumsq_final(const double* __restrict__ partial, int n, float* 
   }
   if (threadIdx.x == 0) gnorm[0] = (float)sqrt(sh[0]);
 }
-// TF-1.x Adam: theta -= lr_t * m / (sqrt(v) + eps), lr_t computed on the host from the step count
-__global__ void k_adam(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
-                       const float* __restrict__ gnorm, float clip, float lr_t, float b1, float b2, float eps) {
+// TF-1.x Adam: theta -= lr_t * m / (sqrt(v) + eps), lr_t computed on the host from the step count.  Also writes the
+// TF32-rounded copy of the new parameters that the next step's GEMMs read (pr; may be null).
+__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                       float* __restrict__ pr, long n, const float* __restrict__ gnorm, float clip, float lr_t, float b1, float b2,
+                       float eps) {
   float scale = 1.0f;
   if (clip > 0.0f) scale = clip / fmaxf(gnorm[0], clip);
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    float gi = g[i] * scale;
-    float mi = b1 * m[i] + (1.0f - b1) * gi;
-    float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  long n4 = n >> 2;     // the flat buffers are padded to a multiple of 4 floats
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 g4 = reinterpret_cast<const float4*>(g)[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i],
+           p4 = reinterpret_cast<float4*>(p)[i];
+    float *gp = &g4.x, *mp = &m4.x, *vp = &v4.x, *pp = &p4.x, r[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float gi = gp[j] * scale;
+      mp[j] = b1 * mp[j] + (1.0f - b1) * gi;
+      vp[j] = b2 * vp[j] + (1.0f - b2) * gi * gi;
+      pp[j] -= lr_t * mp[j] / (sqrtf(vp[j]) + eps);
+      r[j] = tf32_rna(pp[j]);
+    }
+    reinterpret_cast<float4*>(m)[i] = m4;
+    reinterpret_cast<float4*>(v)[i] = v4;
+    reinterpret_cast<float4*>(p)[i] = p4;
+    if (pr) reinterpret_cast<float4*>(pr)[i] = make_float4(r[0], r[1], r[2], r[3]);
   }
+}
+__global__ void k_round_copy(const float* __restrict__ src, float* __restrict__ dst, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) dst[i] = tf32_rna(src[i]);
 }
 
 // ----------------------------------------------------------------------------- test hooks
-__global__ void k_unpack_outputs(const float* __restrict__ hp, const int* __restrict__ start, const int* __restrict__ lens,
-                                 int S, int T, int H, int dir, float* __restrict__ out) {
+__global__ void k_unpack_outputs(const float* __restrict__ h, StepLayout L, int S, int T, int H, int dir, float* __restrict__ out) {
   int s = blockIdx.x / T, t = blockIdx.x % T;
   float* o = out + ((long)s * T + t) * H;
-  bool valid = t < lens[s];
-  const float* src = hp + ((long)start[s] + t + 1 - dir) * H;
+  bool valid = t < L.lens[s];
+  const float* src = h + (valid ? token_row(L, dir, s, t) : 0) * H;
   for (int u = threadIdx.x; u < H; u += blockDim.x) o[u] = valid ? src[u] : 0.0f;
 }
 __global__ void k_debug_mask(uint64_t seed, uint32_t stream, int64_t first, int64_t n, float keep, float* out) {

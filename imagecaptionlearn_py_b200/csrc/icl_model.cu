@@ -56,30 +56,37 @@ struct Head {
   size_t h_dense_floats = 0;
 };
 
+enum { PH_PREP = 0, PH_PROJ, PH_REC_FWD, PH_HEADS_FWD, PH_HEADS_BWD, PH_REC_BWD, PH_WGRAD, PH_UPDATE, PH_N };
+
 struct icl_model {
   icl_config cfg;
   int E, H, S_cap, T_cap;
-  long Np_cap, Ntok_cap;
+  long Ntok_cap;
   std::vector<Param> params;
   std::map<std::string, int> pindex;
   int64_t n_params = 0;
-  float *P = nullptr, *G = nullptr, *M = nullptr, *V = nullptr;
+  float *P = nullptr, *G = nullptr, *M = nullptr, *V = nullptr, *Pr = nullptr;   // Pr: TF32-rounded copy of P (GEMM operands)
+  bool pr_dirty = true;
+  int round_ops = 1;
   int pK[2], pBias[2];
   int64_t step = 0;
-  // workspaces
-  float *xraw = nullptr, *xd[2] = {}, *Z[2] = {}, *HP[2] = {}, *CP[2] = {}, *dHout[2] = {}, *dhrec[2] = {}, *dcc[2] = {};
-  int *d_order = nullptr, *d_start = nullptr, *d_lens = nullptr, *d_tokseq = nullptr, *d_tokstart = nullptr;
+  // workspaces (step-major, see icl_kernels.cuh)
+  float *xraw = nullptr, *xd[2] = {}, *Z[2] = {}, *Hx[2] = {}, *Hp[2] = {}, *Cc[2] = {}, *dHout[2] = {}, *dhrec[2] = {}, *dcc[2] = {},
+        *R[2] = {};
+  int *d_off = nullptr, *d_nact = nullptr, *d_rank = nullptr, *d_lens = nullptr, *d_tokseq = nullptr, *d_tokstart = nullptr;
   float* h_x = nullptr; int* h_ints = nullptr;         // pinned
   double* d_partial = nullptr; float* d_gnorm = nullptr;
   std::vector<Head> heads;
   // resident batch
-  int S = 0, Tmax = 0; long Ntok = 0, Np = 0;
+  int S = 0, Tmax = 0; long Ntok = 0;
   int64_t seq_gid0 = 0, ex_gid0 = 0;
-  std::vector<int> n_active;
+  std::vector<int> n_active, off;
   bool resident = false;
   cudaStream_t stream = nullptr, aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
-  int64_t launches = 0;
+  cudaEvent_t ev_ph[PH_N][2] = {};
+  bool ph_used[PH_N] = {};
+  int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
   float last_ms = 0.f;
   TmaCache tma;
 };
@@ -126,11 +133,16 @@ static int add_param(icl_model* m, const std::string& name, int rows, int cols) 
 template <typename T> static cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
 
 // ----------------------------------------------------------------------------- GEMM dispatch
-static int gemm(icl_model* m, cudaStream_t st, bool a_mn, bool b_mn, const GemmArgs& g, int force_mode = -1) {
+// splits > 1: split-K over gridDim.z with a red.global epilogue (plain epilogue only; C is zeroed here)
+static int gemm(icl_model* m, cudaStream_t st, bool a_mn, bool b_mn, const GemmArgs& g, int force_mode = -1, int splits = 1) {
   int mode = force_mode >= 0 ? force_mode : m->cfg.gemm_mode;
-  bool gathers = g.amap.mode != 0 || g.cmap.mode != 0;
-  if (mode == ICL_GEMM_TCGEN05_TF32 && !gathers && tcgen05_gemm_supported(g, a_mn, b_mn)) {
-    int r = tcgen05_gemm_launch(m->tma, st, a_mn, b_mn, g);
+  if (g.M <= 0 || g.N <= 0) return 0;
+  if (mode == ICL_GEMM_TCGEN05_TF32 && tcgen05_gemm_supported(g, a_mn, b_mn)) {
+    if (splits > 1) {
+      if (g.ldc != g.N) return fail("split-K gemm needs a dense C");
+      CK(cudaMemsetAsync(g.C, 0, (size_t)g.M * g.N * 4, st));
+    }
+    int r = tcgen05_gemm_launch(m->tma, st, a_mn, b_mn, g, splits);
     if (r != 0) return fail("tcgen05 gemm launch failed (%d): %s", r, cudaGetErrorString(cudaGetLastError()));
     m->launches++;
     return 0;
@@ -155,15 +167,17 @@ static GemmArgs mk_gemm(const float* A, long lda, const float* B, long ldb, floa
 
 // ----------------------------------------------------------------------------- API
 extern "C" const char* icl_last_error(void) { return g_err; }
-extern "C" int icl_version(void) { return 1; }
+extern "C" int icl_version(void) { return 2; }
 
 extern "C" void icl_destroy(icl_model* m) {
   if (!m) return;
   cudaDeviceSynchronize();
   auto F = [](void* p) { if (p) cudaFree(p); };
-  F(m->P); F(m->G); F(m->M); F(m->V); F(m->xraw);
-  for (int d = 0; d < 2; d++) { F(m->xd[d]); F(m->Z[d]); F(m->HP[d]); F(m->CP[d]); F(m->dHout[d]); F(m->dhrec[d]); F(m->dcc[d]); }
-  F(m->d_order); F(m->d_start); F(m->d_lens); F(m->d_tokseq); F(m->d_tokstart); F(m->d_partial); F(m->d_gnorm);
+  F(m->P); F(m->G); F(m->M); F(m->V); F(m->Pr); F(m->xraw);
+  for (int d = 0; d < 2; d++) {
+    F(m->xd[d]); F(m->Z[d]); F(m->Hx[d]); F(m->Hp[d]); F(m->Cc[d]); F(m->dHout[d]); F(m->dhrec[d]); F(m->dcc[d]); F(m->R[d]);
+  }
+  F(m->d_off); F(m->d_nact); F(m->d_rank); F(m->d_lens); F(m->d_tokseq); F(m->d_tokstart); F(m->d_partial); F(m->d_gnorm);
   if (m->h_x) cudaFreeHost(m->h_x);
   if (m->h_ints) cudaFreeHost(m->h_ints);
   for (auto& h : m->heads) {
@@ -178,6 +192,7 @@ extern "C" void icl_destroy(icl_model* m) {
   }
   if (m->aux) cudaStreamDestroy(m->aux);
   for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_t0, m->ev_t1}) if (e) cudaEventDestroy(e);
+  for (int i = 0; i < PH_N; i++) for (int j = 0; j < 2; j++) if (m->ev_ph[i][j]) cudaEventDestroy(m->ev_ph[i][j]);
   delete m;
 }
 
@@ -193,14 +208,15 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   if (prop.major != 10) return fail("icl_create: device sm_%d%d is not Blackwell sm_100 (kernels are sm_100a-only)", prop.major, prop.minor);
   if (cfg->embed_width % 4 || cfg->lstm_hidden % 4) return fail("icl_create: embed_width and lstm_hidden must be multiples of 4");
   if (cfg->n_heads < 1 || cfg->n_heads > ICL_MAX_HEADS) return fail("icl_create: n_heads out of range");
+  if (cfg->max_seqs < 1 || cfg->max_seq_len < 1) return fail("icl_create: max_seqs / max_seq_len must be positive");
   icl_model* m = new icl_model();
   m->cfg = *cfg;
   if (m->cfg.beta1 <= 0) m->cfg.beta1 = 0.9f;
   if (m->cfg.beta2 <= 0) m->cfg.beta2 = 0.999f;
+  m->round_ops = cfg->gemm_mode == ICL_GEMM_TCGEN05_TF32;
   int E = m->E = cfg->embed_width, H = m->H = cfg->lstm_hidden;
   m->S_cap = cfg->max_seqs; m->T_cap = cfg->max_seq_len;
   m->Ntok_cap = (long)m->S_cap * m->T_cap;
-  m->Np_cap = m->Ntok_cap + m->S_cap;
   // parameters, named like the TF variables
   const char* dn[2] = {"fw", "bw"};
   for (int d = 0; d < 2; d++) {
@@ -242,23 +258,26 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   *out = m;   // from here on failures leave a destroyable handle
 #define CKD(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fail("icl_create: %s -> %s", #x, cudaGetErrorString(e_)); icl_destroy(m); *out = nullptr; return -1; } } while (0)
   size_t np = (size_t)m->n_params;
-  CKD(dmalloc(&m->P, np)); CKD(dmalloc(&m->G, np)); CKD(dmalloc(&m->M, np)); CKD(dmalloc(&m->V, np));
+  CKD(dmalloc(&m->P, np)); CKD(dmalloc(&m->G, np)); CKD(dmalloc(&m->M, np)); CKD(dmalloc(&m->V, np)); CKD(dmalloc(&m->Pr, np));
   CKD(cudaMemset(m->P, 0, np * 4)); CKD(cudaMemset(m->G, 0, np * 4)); CKD(cudaMemset(m->M, 0, np * 4)); CKD(cudaMemset(m->V, 0, np * 4));
+  CKD(cudaMemset(m->Pr, 0, np * 4));
   CKD(dmalloc(&m->xraw, (size_t)m->Ntok_cap * E));
   for (int d = 0; d < 2; d++) {
-    CKD(dmalloc(&m->xd[d], (size_t)m->Np_cap * E));
-    CKD(dmalloc(&m->Z[d], (size_t)m->Np_cap * 4 * H));
-    CKD(dmalloc(&m->HP[d], (size_t)m->Np_cap * H));
-    CKD(dmalloc(&m->CP[d], (size_t)m->Np_cap * H));
-    CKD(dmalloc(&m->dHout[d], (size_t)m->Np_cap * H));
+    CKD(dmalloc(&m->xd[d], (size_t)m->Ntok_cap * E));
+    CKD(dmalloc(&m->Z[d], (size_t)m->Ntok_cap * 4 * H));
+    CKD(dmalloc(&m->Hx[d], (size_t)m->Ntok_cap * H));
+    CKD(dmalloc(&m->Hp[d], (size_t)m->Ntok_cap * H));
+    CKD(dmalloc(&m->Cc[d], (size_t)m->Ntok_cap * H));
+    CKD(dmalloc(&m->dHout[d], (size_t)m->Ntok_cap * H));
     CKD(dmalloc(&m->dhrec[d], (size_t)m->S_cap * H));
     CKD(dmalloc(&m->dcc[d], (size_t)m->S_cap * H));
+    CKD(dmalloc(&m->R[d], (size_t)m->S_cap * 4 * H));
   }
-  CKD(dmalloc(&m->d_order, m->S_cap)); CKD(dmalloc(&m->d_start, m->S_cap)); CKD(dmalloc(&m->d_lens, m->S_cap));
-  CKD(dmalloc(&m->d_tokstart, m->S_cap)); CKD(dmalloc(&m->d_tokseq, m->Ntok_cap));
+  CKD(dmalloc(&m->d_off, m->T_cap + 1)); CKD(dmalloc(&m->d_nact, m->T_cap + 1)); CKD(dmalloc(&m->d_rank, m->S_cap));
+  CKD(dmalloc(&m->d_lens, m->S_cap)); CKD(dmalloc(&m->d_tokstart, m->S_cap)); CKD(dmalloc(&m->d_tokseq, m->Ntok_cap));
   CKD(dmalloc(&m->d_partial, 1024)); CKD(dmalloc(&m->d_gnorm, 4));
   CKD(cudaMallocHost((void**)&m->h_x, (size_t)m->Ntok_cap * E * 4));
-  CKD(cudaMallocHost((void**)&m->h_ints, ((size_t)m->S_cap * 4 + m->Ntok_cap) * 4));
+  CKD(cudaMallocHost((void**)&m->h_ints, ((size_t)m->S_cap * 3 + m->Ntok_cap + 2 * (m->T_cap + 1)) * 4));
   for (auto& h : m->heads) {
     int B = h.c.batch_size, C = h.c.n_classes;
     int maxw = 0;
@@ -288,6 +307,7 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   CKD(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
   CKD(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
   CKD(cudaEventCreate(&m->ev_t0)); CKD(cudaEventCreate(&m->ev_t1));
+  for (int i = 0; i < PH_N; i++) for (int j = 0; j < 2; j++) CKD(cudaEventCreate(&m->ev_ph[i][j]));
   if (tcgen05_gemm_init() != 0) { fail("icl_create: cannot resolve cuTensorMapEncodeTiled"); icl_destroy(m); *out = nullptr; return -1; }
 #undef CKD
   return 0;
@@ -320,16 +340,31 @@ extern "C" int icl_set_tensor(icl_model* m, int kind, const char* name, const fl
   const Param& p = m->params[it->second];
   CK(cudaStreamSynchronize(m->stream));
   CK(cudaMemcpy(kind_buf(m, kind) + p.off, host, (size_t)p.rows * p.cols * 4, cudaMemcpyHostToDevice));
+  if (kind == 0) m->pr_dirty = true;
   return 0;
 }
 extern "C" int icl_get_step(icl_model* m, int64_t* t) { *t = m->step; return 0; }
 extern "C" int icl_set_step(icl_model* m, int64_t t) { m->step = t; return 0; }
 extern "C" int icl_grad_buffer(icl_model* m, void** p, int64_t* n) { *p = m->G; *n = m->n_params; return 0; }
-extern "C" int icl_param_buffer(icl_model* m, void** p, int64_t* n) { *p = m->P; *n = m->n_params; return 0; }
+extern "C" int icl_param_buffer(icl_model* m, void** p, int64_t* n) { *p = m->P; *n = m->n_params; m->pr_dirty = true; return 0; }
 extern "C" int icl_kernel_launches(icl_model* m, int64_t* n) { *n = m->launches; return 0; }
 extern "C" int icl_last_step_ms(icl_model* m, float* ms) { *ms = m->last_ms; return 0; }
+extern "C" int icl_copy_bytes(icl_model* m, int64_t* h2d, int64_t* d2h) { *h2d = m->h2d_bytes; *d2h = m->d2h_bytes; return 0; }
+extern "C" int icl_batch_stats(icl_model* m, int64_t* n_seqs, int64_t* n_tokens, int32_t* t_max) {
+  *n_seqs = m->S; *n_tokens = m->Ntok; *t_max = m->Tmax; return 0;
+}
+// device time of each phase of the last icl_run_resident (ms; 0 where the phase did not run).  Synchronises the stream.
+extern "C" int icl_phase_ms(icl_model* m, float* ms) {
+  CK(cudaStreamSynchronize(m->stream));
+  for (int i = 0; i < PH_N; i++) {
+    ms[i] = 0.f;
+    if (m->ph_used[i]) CK(cudaEventElapsedTime(&ms[i], m->ev_ph[i][0], m->ev_ph[i][1]));
+  }
+  return 0;
+}
 
 // ----------------------------------------------------------------------------- upload (H2D of one batch_tensors dict)
+#define H2D(dst, src, bytes, st) do { CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st)); m->h2d_bytes += (int64_t)(bytes); } while (0)
 extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
   if (!m || !b) return fail("icl_upload: null argument");
   int S = b->n_seqs, E = m->E;
@@ -338,19 +373,27 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
   if (!b->sent_packed && (b->padded_T < 1 || b->padded_T > m->T_cap)) return fail("icl_upload: padded_T=%d exceeds capacity %d", b->padded_T, m->T_cap);
   int T = b->sent_packed ? m->T_cap : b->padded_T;
   CK(cudaStreamSynchronize(m->stream));          // pinned staging is reused
-  int* lens = m->h_ints; int* start = lens + m->S_cap; int* order = start + m->S_cap; int* tokstart = order + m->S_cap; int* tokseq = tokstart + m->S_cap;
-  long ntok = 0, np = 0; int tmax = 0;
+  m->h2d_bytes = 0;
+  int* lens = m->h_ints; int* rank = lens + m->S_cap; int* tokstart = rank + m->S_cap; int* tokseq = tokstart + m->S_cap;
+  int* offs = tokseq + m->Ntok_cap; int* nact = offs + m->T_cap + 1;
+  long ntok = 0; int tmax = 0;
   for (int s = 0; s < S; s++) {
     double l = read_num(b->seq_lengths, b->len_dtype, s);
     int li = (int)l;
     if (li != l || li < 0 || li > T) return fail("icl_upload: seq_lengths[%d]=%g outside [0,%d]", s, l, T);
-    lens[s] = li; start[s] = (int)np; tokstart[s] = (int)ntok;
-    ntok += li; np += li + 1; tmax = std::max(tmax, li);
+    lens[s] = li; tokstart[s] = (int)ntok;
+    ntok += li; tmax = std::max(tmax, li);
   }
-  std::iota(order, order + S, 0);
-  std::stable_sort(order, order + S, [&](int a, int c) { return lens[a] > lens[c]; });
-  m->n_active.assign(tmax, 0);
+  // rank by length (descending, stable): step k runs ranks [0, nact[k])
+  std::vector<int> order(S);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return lens[a] > lens[c]; });
+  for (int i = 0; i < S; i++) rank[order[i]] = i;
+  m->n_active.assign(tmax + 1, 0);
   for (int s = 0; s < S; s++) for (int k = 0; k < lens[s]; k++) m->n_active[k]++;
+  m->off.assign(tmax + 2, 0);
+  for (int k = 0; k <= tmax; k++) m->off[k + 1] = m->off[k] + m->n_active[k];
+  for (int k = 0; k <= tmax; k++) { offs[k] = m->off[k]; nact[k] = m->n_active[k]; }
   // pack valid tokens (caption-major) into pinned memory as fp32
   size_t esz = b->sent_dtype == ICL_F64 ? 8 : 4;
   if (b->sent_dtype != ICL_F32 && b->sent_dtype != ICL_F64) return fail("icl_upload: sentences must be float32/float64");
@@ -360,12 +403,13 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
     for (int t = 0; t < lens[s]; t++) tokseq[tokstart[s] + t] = s;
   }
   cudaStream_t st = m->stream;
-  CK(cudaMemcpyAsync(m->xraw, m->h_x, (size_t)ntok * E * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(m->d_lens, lens, S * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(m->d_start, start, S * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(m->d_order, order, S * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(m->d_tokstart, tokstart, S * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(m->d_tokseq, tokseq, (size_t)ntok * 4, cudaMemcpyHostToDevice, st));
+  H2D(m->xraw, m->h_x, (size_t)ntok * E * 4, st);
+  H2D(m->d_lens, lens, (size_t)S * 4, st);
+  H2D(m->d_rank, rank, (size_t)S * 4, st);
+  H2D(m->d_tokstart, tokstart, (size_t)S * 4, st);
+  H2D(m->d_tokseq, tokseq, (size_t)ntok * 4, st);
+  H2D(m->d_off, offs, (size_t)(tmax + 1) * 4, st);
+  H2D(m->d_nact, nact, (size_t)(tmax + 1) * 4, st);
   for (int hi = 0; hi < b->n_heads; hi++) {
     Head& h = m->heads[hi];
     const icl_head_batch& hb = b->heads[hi];
@@ -383,7 +427,7 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
           return fail("icl_upload: head %d index matrix %d row %d = [%g,%g,%g] out of range (S=%d,T=%d)", hi, id, r, d, sq, w, S, T);
         dst[r * 3] = (int)d; dst[r * 3 + 1] = (int)sq; dst[r * 3 + 2] = (int)w;
       }
-      CK(cudaMemcpyAsync(h.idx[id], dst, (size_t)B * 3 * 4, cudaMemcpyHostToDevice, st));
+      H2D(h.idx[id], dst, (size_t)B * 3 * 4, st);
     }
     float* hd = h.h_dense;
     auto up = [&](const void* src, int dt, float* dev, size_t n, const char* what) -> int {
@@ -391,6 +435,7 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
       if (!src) return fail("icl_upload: head %d is missing %s", hi, what);
       to_f32(hd, src, dt, n);
       cudaError_t e = cudaMemcpyAsync(dev, hd, n * 4, cudaMemcpyHostToDevice, st);
+      m->h2d_bytes += (int64_t)n * 4;
       hd += n;
       return e == cudaSuccess ? 0 : fail("icl_upload: copy of %s failed: %s", what, cudaGetErrorString(e));
     };
@@ -400,56 +445,73 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
     h.has_labels = hb.labels != nullptr;
     if (h.has_labels) CKI(up(hb.labels, hb.labels_dtype, h.labels, (size_t)B * C, "labels"));
   }
-  m->S = S; m->Tmax = tmax; m->Ntok = ntok; m->Np = np;
+  m->S = S; m->Tmax = tmax; m->Ntok = ntok;
   m->seq_gid0 = b->seq_gid_offset; m->ex_gid0 = b->ex_gid_offset;
   m->resident = true;
   return 0;
 }
 
 // ----------------------------------------------------------------------------- forward / backward on resident data
-static SeqMap mk_map(icl_model* m, int mode, int k, int dir) {
-  SeqMap s; s.order = m->d_order; s.start = m->d_start; s.lens = m->d_lens; s.k = k; s.dir = dir; s.mode = mode;
-  return s;
-}
 #define LAUNCHED(m) do { (m)->launches++; CK(cudaGetLastError()); } while (0)
+#define PH_BEGIN(m, ph) do { CK(cudaEventRecord((m)->ev_ph[ph][0], (m)->stream)); } while (0)
+#define PH_END(m, ph) do { CK(cudaEventRecord((m)->ev_ph[ph][1], (m)->stream)); (m)->ph_used[ph] = true; } while (0)
+
+static StepLayout mk_layout(icl_model* m) { StepLayout L; L.off = m->d_off; L.nact = m->d_nact; L.rank = m->d_rank; L.lens = m->d_lens; return L; }
+static const float* wbase(icl_model* m) { return m->round_ops ? m->Pr : m->P; }   // GEMM-operand view of the parameters
+
+static int refresh_rounded_params(icl_model* m) {
+  if (m->round_ops && m->pr_dirty) {
+    k_round_copy<<<296, 256, 0, m->stream>>>(m->P, m->Pr, (long)m->n_params); LAUNCHED(m);
+  }
+  m->pr_dirty = false;
+  return 0;
+}
 
 static int lstm_forward(icl_model* m, float keep_in, uint64_t seed) {
-  int E = m->E, H = m->H, S = m->S;
-  long Np = m->Np;
+  int E = m->E, H = m->H;
+  long Ntok = m->Ntok;
   cudaStream_t st = m->stream;
-  if (m->Ntok > 0) {
-    k_prep_x<<<(unsigned)((m->Ntok * 32 + 255) / 256), 256, 0, st>>>(m->xraw, m->d_tokseq, m->d_tokstart, m->d_start, (int)m->Ntok, E,
-                                                                   m->T_cap, m->cfg.data_norm, keep_in, seed, m->seq_gid0, m->xd[0], m->xd[1]);
-    LAUNCHED(m);
+  if (Ntok == 0) return 0;
+  PH_BEGIN(m, PH_PREP);
+  k_prep_x<<<(unsigned)((Ntok * 32 + 255) / 256), 256, 0, st>>>(m->xraw, m->d_tokseq, m->d_tokstart, mk_layout(m), (int)Ntok, E, m->T_cap,
+                                                               m->cfg.data_norm, keep_in, seed, m->seq_gid0, m->round_ops, m->xd[0], m->xd[1]);
+  LAUNCHED(m);
+  // h_prev of step 0 is the zero state: the first nact[0] rows of Hp stay zero (they are the A rows of dW_hh)
+  for (int d = 0; d < 2; d++) CK(cudaMemsetAsync(m->Hp[d], 0, (size_t)m->n_active[0] * H * 4, st));
+  PH_END(m, PH_PREP);
+  // K1: time-batched input projection  Z = Xd * W_ih + b   (W_ih = kernel rows [0,E)), both directions
+  PH_BEGIN(m, PH_PROJ);
+  for (int d = 0; d < 2; d++) {
+    const float* K = wbase(m) + m->params[m->pK[d]].off;
+    GemmArgs g = mk_gemm(m->xd[d], E, K, 4 * H, m->Z[d], 4 * H, (int)Ntok, 4 * H, E);
+    g.epi.bias = m->P + m->params[m->pBias[d]].off;
+    CKI(gemm(m, st, false, true, g));
   }
-  k_zero_rows<<<S, 128, 0, st>>>(m->xd[0], m->d_start, m->d_lens, S, E, 1); LAUNCHED(m);
-  k_zero_rows<<<S, 128, 0, st>>>(m->xd[1], m->d_start, m->d_lens, S, E, 0); LAUNCHED(m);
+  PH_END(m, PH_PROJ);
+  // K2: the recurrence
+  PH_BEGIN(m, PH_REC_FWD);
   CK(cudaEventRecord(m->ev_fork, st));
   CK(cudaStreamWaitEvent(m->aux, m->ev_fork, 0));
   for (int d = 0; d < 2; d++) {
     cudaStream_t sd = d ? m->aux : st;
-    const Param& pk = m->params[m->pK[d]];
-    const float* K = m->P + pk.off;
-    const float* bias = m->P + m->params[m->pBias[d]].off;
-    // K1: time-batched input projection  Z = Xd * W_ih + b   (W_ih = kernel rows [0,E))
-    GemmArgs g = mk_gemm(m->xd[d], E, K, 4 * H, m->Z[d], 4 * H, (int)Np, 4 * H, E);
-    g.epi.bias = bias;
-    CKI(gemm(m, sd, false, true, g));
-    k_zero_rows<<<S, 128, 0, sd>>>(m->HP[d], m->d_start, m->d_lens, S, H, d); LAUNCHED(m);
-    k_zero_rows<<<S, 128, 0, sd>>>(m->CP[d], m->d_start, m->d_lens, S, H, d); LAUNCHED(m);
-    const float* Whh = K + (size_t)E * 4 * H;
+    const float* Whh = wbase(m) + m->params[m->pK[d]].off + (size_t)E * 4 * H;
     for (int k = 0; k < m->Tmax; k++) {
-      int n = m->n_active[k];
-      if (k > 0) {   // h_prev is zero at the first step
-        GemmArgs r = mk_gemm(m->HP[d], H, Whh, 4 * H, m->Z[d], 4 * H, n, 4 * H, H);
-        r.amap = mk_map(m, 1, k, d); r.cmap = mk_map(m, 1, k, d); r.epi.beta = 1.0f;
+      int n = m->n_active[k], n_next = m->n_active[k + 1];
+      long o = m->off[k];
+      if (k > 0) {   // R = h_{k-1} * W_hh for the running rows
+        GemmArgs r = mk_gemm(m->Hp[d] + o * H, H, Whh, 4 * H, m->R[d], 4 * H, n, 4 * H, H);
         CKI(gemm(m, sd, false, true, r));
       }
-      k_lstm_cell_fwd<<<n, 128, 0, sd>>>(m->Z[d], m->HP[d], m->CP[d], mk_map(m, 1, k, d), n, H); LAUNCHED(m);
+      long nthr = (long)n * (H / 4);
+      k_lstm_cell_fwd<<<(unsigned)((nthr + 127) / 128), 128, 0, sd>>>(
+          m->Z[d] + o * 4 * H, k > 0 ? m->R[d] : nullptr, k > 0 ? m->Cc[d] + (long)m->off[k - 1] * H : nullptr, m->Cc[d] + o * H,
+          m->Hx[d] + o * H, m->Hp[d] + (long)m->off[k + 1] * H, n, n_next, H, m->round_ops);
+      LAUNCHED(m);
     }
   }
   CK(cudaEventRecord(m->ev_join, m->aux));
   CK(cudaStreamWaitEvent(st, m->ev_join, 0));
+  PH_END(m, PH_REC_FWD);
   return 0;
 }
 
@@ -458,16 +520,17 @@ static Drop mk_drop(uint64_t seed, uint32_t stream, float keep, int64_t gid0) { 
 static int heads_forward(icl_model* m, float keep, uint64_t seed) {
   cudaStream_t st = m->stream;
   int H = m->H;
+  PH_BEGIN(m, PH_HEADS_FWD);
   for (size_t hi = 0; hi < m->heads.size(); hi++) {
     Head& h = m->heads[hi];
     int B = h.c.batch_size, C = h.c.n_classes, L = h.c.n_hidden;
-    k_gather_concat<<<B, 128, 0, st>>>(h.slots, m->HP[0], m->HP[1], m->d_start, m->d_lens, H, m->T_cap, h.D0,
-                                      mk_drop(seed, 0, keep, m->seq_gid0), h.bi);
+    k_gather_concat<<<B, 128, 0, st>>>(h.slots, m->Hx[0], m->Hx[1], mk_layout(m), H, m->T_cap, h.D0, mk_drop(seed, 0, keep, m->seq_gid0),
+                                      m->round_ops, h.bi);
     LAUNCHED(m);
     const float* in = h.bi;
     for (int k = 0; k < L; k++) {
       const Param& pw = m->params[h.pW[k]];
-      GemmArgs g = mk_gemm(in, h.dims[k], m->P + pw.off, h.dims[k + 1], h.act[k], h.dims[k + 1], B, h.dims[k + 1], h.dims[k]);
+      GemmArgs g = mk_gemm(in, h.dims[k], wbase(m) + pw.off, h.dims[k + 1], h.act[k], h.dims[k + 1], B, h.dims[k + 1], h.dims[k]);
       g.epi.mode = EPI_BIAS_ACT_DROP; g.epi.bias = m->P + m->params[h.pB[k]].off; g.epi.act = h.c.activation;
       g.epi.drop = mk_drop(seed, STREAM_HEAD + (uint32_t)hi * 8 + k, keep, m->ex_gid0);
       CKI(gemm(m, st, false, true, g));
@@ -483,6 +546,7 @@ static int heads_forward(icl_model* m, float keep, uint64_t seed) {
       k_reduce_sum<<<1, 256, 0, st>>>(h.row_correct, B, h.scalars + 1, (float)B); LAUNCHED(m);
     }
   }
+  PH_END(m, PH_HEADS_FWD);
   return 0;
 }
 
@@ -495,7 +559,8 @@ static int colsum(icl_model* m, cudaStream_t st, const float* X, long rows, int 
 static int heads_backward(icl_model* m, float keep, uint64_t seed) {
   cudaStream_t st = m->stream;
   int H = m->H;
-  for (int d = 0; d < 2; d++) CK(cudaMemsetAsync(m->dHout[d], 0, (size_t)m->Np * H * 4, st));
+  PH_BEGIN(m, PH_HEADS_BWD);
+  for (int d = 0; d < 2; d++) CK(cudaMemsetAsync(m->dHout[d], 0, (size_t)m->Ntok * H * 4, st));
   for (size_t hi = 0; hi < m->heads.size(); hi++) {
     Head& h = m->heads[hi];
     if (!h.has_labels) return fail("backward needs labels for head %zu", hi);
@@ -513,67 +578,80 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
       CKI(colsum(m, st, dz, B, dout, dout, m->G + m->params[h.pB[k]].off));
       // d(in) = dz * W^T  (W [din,dout] row-major is K-major as the B operand)
       if (k > 0) {
-        GemmArgs gx = mk_gemm(dz, dout, m->P + pw.off, dout, bufs[cur], din, B, din, dout);
+        GemmArgs gx = mk_gemm(dz, dout, wbase(m) + pw.off, dout, bufs[cur], din, B, din, dout);
         gx.epi.mode = EPI_DACT; gx.epi.act = h.c.activation; gx.epi.aux = h.act[k - 1]; gx.epi.ldaux = din;
         gx.epi.drop = mk_drop(seed, STREAM_HEAD + (uint32_t)hi * 8 + (k - 1), keep, m->ex_gid0);
+        gx.epi.round_out = m->round_ops;
         CKI(gemm(m, st, false, false, gx));
         dz = bufs[cur];
         cur ^= 1;
       } else if (h.D0g > 0) {
-        GemmArgs gx = mk_gemm(dz, dout, m->P + pw.off, dout, h.dbi, h.D0g, B, h.D0g, dout);
+        GemmArgs gx = mk_gemm(dz, dout, wbase(m) + pw.off, dout, h.dbi, h.D0g, B, h.D0g, dout);
         CKI(gemm(m, st, false, false, gx));
-        k_scatter_spans<<<B, 128, 0, st>>>(h.slots, h.dbi, m->d_start, m->d_lens, H, m->T_cap, h.D0g,
-                                          mk_drop(seed, 0, keep, m->seq_gid0), m->dHout[0], m->dHout[1]);
+        k_scatter_spans<<<B, 128, 0, st>>>(h.slots, h.dbi, mk_layout(m), H, m->T_cap, h.D0g, mk_drop(seed, 0, keep, m->seq_gid0),
+                                          m->dHout[0], m->dHout[1]);
         LAUNCHED(m);
       }
     }
   }
+  PH_END(m, PH_HEADS_BWD);
   return 0;
 }
 
 static int lstm_backward(icl_model* m) {
   int E = m->E, H = m->H, S = m->S;
-  long Np = m->Np;
+  long Ntok = m->Ntok;
   cudaStream_t st = m->stream;
+  if (Ntok == 0) return 0;
+  // K3: BPTT
+  PH_BEGIN(m, PH_REC_BWD);
   CK(cudaEventRecord(m->ev_fork, st));
   CK(cudaStreamWaitEvent(m->aux, m->ev_fork, 0));
   for (int d = 0; d < 2; d++) {
     cudaStream_t sd = d ? m->aux : st;
-    const Param& pk = m->params[m->pK[d]];
-    const float* Whh = m->P + pk.off + (size_t)E * 4 * H;
+    const float* Whh = wbase(m) + m->params[m->pK[d]].off + (size_t)E * 4 * H;
     CK(cudaMemsetAsync(m->dhrec[d], 0, (size_t)S * H * 4, sd));
     CK(cudaMemsetAsync(m->dcc[d], 0, (size_t)S * H * 4, sd));
     for (int k = m->Tmax - 1; k >= 0; k--) {
       int n = m->n_active[k];
-      k_lstm_cell_bwd<<<n, 128, 0, sd>>>(m->Z[d], m->CP[d], m->dHout[d], m->Z[d], m->dhrec[d], m->dcc[d], mk_map(m, 1, k, d), n, H);
+      long o = m->off[k];
+      long nthr = (long)n * (H / 4);
+      k_lstm_cell_bwd<<<(unsigned)((nthr + 127) / 128), 128, 0, sd>>>(m->Z[d] + o * 4 * H, m->Cc[d] + o * H,
+                                                                     k > 0 ? m->Cc[d] + (long)m->off[k - 1] * H : nullptr,
+                                                                     m->dHout[d] + o * H, m->dhrec[d], m->dcc[d], n, H, m->round_ops);
       LAUNCHED(m);
-      if (k > 0) {   // dh_{prev} = dz * W_hh^T
-        GemmArgs r = mk_gemm(m->Z[d], 4 * H, Whh, 4 * H, m->dhrec[d], H, n, H, 4 * H);
-        r.amap = mk_map(m, 1, k, d); r.cmap = mk_map(m, 2, k, d);
+      if (k > 0) {   // dh_{k-1} = dZ_k * W_hh^T for the running rows
+        GemmArgs r = mk_gemm(m->Z[d] + o * 4 * H, 4 * H, Whh, 4 * H, m->dhrec[d], H, n, H, 4 * H);
         CKI(gemm(m, sd, false, false, r));
       }
     }
-    // pad rows of dZ must be exactly zero for the time-batched weight-gradient GEMMs
-    k_zero_rows<<<S, 128, 0, sd>>>(m->Z[d], m->d_start, m->d_lens, S, 4 * H, d == 0 ? 1 : 0); LAUNCHED(m);
-    float* dK = m->G + pk.off;
-    GemmArgs gi = mk_gemm(m->xd[d], E, m->Z[d], 4 * H, dK, 4 * H, E, 4 * H, (int)Np);          // dW_ih = Xd^T dZ
-    CKI(gemm(m, sd, true, true, gi));
-    GemmArgs gh = mk_gemm(m->HP[d], H, m->Z[d], 4 * H, dK + (size_t)E * 4 * H, 4 * H, H, 4 * H, (int)Np);   // dW_hh = Hprev^T dZ
-    CKI(gemm(m, sd, true, true, gh));
-    float* db = m->G + m->params[m->pBias[d]].off;
-    CK(cudaMemsetAsync(db, 0, (size_t)4 * H * 4, sd));
-    int rpb = 256;
-    dim3 grid((4 * H + 127) / 128, (unsigned)((Np + rpb - 1) / rpb));
-    k_colsum_atomic<<<grid, 128, 0, sd>>>(m->Z[d], Np, 4 * H, 4 * H, db, rpb); LAUNCHED(m);
   }
   CK(cudaEventRecord(m->ev_join, m->aux));
   CK(cudaStreamWaitEvent(st, m->ev_join, 0));
+  PH_END(m, PH_REC_BWD);
+  // time-batched weight gradients: dW_ih = Xd^T dZ, dW_hh = Hprev^T dZ (contraction over all tokens, split-K), db = colsum(dZ)
+  PH_BEGIN(m, PH_WGRAD);
+  int splits = (int)std::min<long>(16, std::max<long>(1, Ntok / 2048));
+  for (int d = 0; d < 2; d++) {
+    float* dK = m->G + m->params[m->pK[d]].off;
+    GemmArgs gi = mk_gemm(m->xd[d], E, m->Z[d], 4 * H, dK, 4 * H, E, 4 * H, (int)Ntok);
+    CKI(gemm(m, st, true, true, gi, -1, splits));
+    GemmArgs gh = mk_gemm(m->Hp[d], H, m->Z[d], 4 * H, dK + (size_t)E * 4 * H, 4 * H, H, 4 * H, (int)Ntok);
+    CKI(gemm(m, st, true, true, gh, -1, splits));
+    float* db = m->G + m->params[m->pBias[d]].off;
+    CK(cudaMemsetAsync(db, 0, (size_t)4 * H * 4, st));
+    int rpb = 256;
+    dim3 grid((4 * H + 127) / 128, (unsigned)((Ntok + rpb - 1) / rpb));
+    k_colsum_atomic<<<grid, 128, 0, st>>>(m->Z[d], Ntok, 4 * H, 4 * H, db, rpb); LAUNCHED(m);
+  }
+  PH_END(m, PH_WGRAD);
   return 0;
 }
 
 extern "C" int icl_apply_update(icl_model* m) {
   cudaStream_t st = m->stream;
   long n = (long)m->n_params;
+  PH_BEGIN(m, PH_UPDATE);
   if (m->cfg.clip_norm > 0) {
     k_sumsq_partial<<<592, 256, 0, st>>>(m->G, n, m->d_partial); LAUNCHED(m);
     k_sumsq_final<<<1, 256, 0, st>>>(m->d_partial, 592, m->d_gnorm); LAUNCHED(m);
@@ -581,15 +659,19 @@ extern "C" int icl_apply_update(icl_model* m) {
   m->step++;
   double b1 = m->cfg.beta1, b2 = m->cfg.beta2;
   float lr_t = (float)(m->cfg.learn_rate * std::sqrt(1.0 - std::pow(b2, (double)m->step)) / (1.0 - std::pow(b1, (double)m->step)));
-  k_adam<<<592, 256, 0, st>>>(m->P, m->G, m->M, m->V, n, m->d_gnorm, m->cfg.clip_norm, lr_t, (float)b1, (float)b2, m->cfg.adam_epsilon);
+  k_adam<<<592, 256, 0, st>>>(m->P, m->G, m->M, m->V, m->round_ops ? m->Pr : nullptr, n, m->d_gnorm, m->cfg.clip_norm, lr_t, (float)b1,
+                             (float)b2, m->cfg.adam_epsilon);
   LAUNCHED(m);
+  PH_END(m, PH_UPDATE);
   return 0;
 }
 
 extern "C" int icl_run_resident(icl_model* m, int op, float keep_in, float keep, uint64_t seed) {
   if (!m->resident) return fail("icl_run_resident: no batch uploaded");
   if (!(keep_in > 0 && keep_in <= 1 && keep > 0 && keep <= 1)) return fail("keep probabilities must be in (0,1]");
+  for (int i = 0; i < PH_N; i++) m->ph_used[i] = false;
   CK(cudaEventRecord(m->ev_t0, m->stream));
+  CKI(refresh_rounded_params(m));
   CKI(lstm_forward(m, keep_in, seed));
   CKI(heads_forward(m, keep, seed));
   if (op >= ICL_OP_GRADS) {
@@ -603,12 +685,14 @@ extern "C" int icl_run_resident(icl_model* m, int op, float keep_in, float keep,
 
 extern "C" int icl_fetch(icl_model* m, icl_head_out* out) {
   cudaStream_t st = m->stream;
+  m->d2h_bytes = 0;
   for (size_t hi = 0; hi < m->heads.size(); hi++) {
     Head& h = m->heads[hi];
     int B = h.c.batch_size, C = h.c.n_classes;
     CK(cudaMemcpyAsync(h.h_out, h.proba, (size_t)B * C * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h.h_out + (size_t)B * C, h.scalars, 2 * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h.h_pred, h.pred, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+    m->d2h_bytes += (int64_t)B * C * 4 + 8 + (int64_t)B * 8;
   }
   CK(cudaStreamSynchronize(st));
   cudaEventElapsedTime(&m->last_ms, m->ev_t0, m->ev_t1);
@@ -636,7 +720,7 @@ extern "C" int icl_get_lstm_outputs(icl_model* m, int dir, float* host) {
   float* tmp;
   size_t n = (size_t)m->S * T * m->H;
   CK(dmalloc(&tmp, n));
-  k_unpack_outputs<<<m->S * T, 128, 0, m->stream>>>(m->HP[dir], m->d_start, m->d_lens, m->S, T, m->H, dir, tmp);
+  k_unpack_outputs<<<m->S * T, 128, 0, m->stream>>>(m->Hx[dir], mk_layout(m), m->S, T, m->H, dir, tmp);
   cudaError_t e = cudaMemcpyAsync(host, tmp, n * 4, cudaMemcpyDeviceToHost, m->stream);
   cudaStreamSynchronize(m->stream);
   cudaFree(tmp);
@@ -649,6 +733,14 @@ extern "C" int icl_get_batch_input(icl_model* m, int head, float* host) {
   CK(cudaMemcpy(host, h.bi, (size_t)h.c.batch_size * h.D0 * 4, cudaMemcpyDeviceToHost));
   return 0;
 }
+extern "C" int icl_get_activation(icl_model* m, int head, int layer, float* host) {
+  if (head < 0 || head >= (int)m->heads.size()) return fail("head out of range");
+  Head& h = m->heads[head];
+  if (layer < 0 || layer >= h.c.n_hidden) return fail("layer out of range");
+  CK(cudaStreamSynchronize(m->stream));
+  CK(cudaMemcpy(host, h.act[layer], (size_t)h.c.batch_size * h.dims[layer + 1] * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
 extern "C" int icl_debug_mask(icl_model* m, uint64_t seed, uint32_t stream, int64_t first, int64_t n, float keep, float* host) {
   float* tmp;
   CK(dmalloc(&tmp, (size_t)n));
@@ -659,14 +751,15 @@ extern "C" int icl_debug_mask(icl_model* m, uint64_t seed, uint32_t stream, int6
   CK(e);
   return 0;
 }
-extern "C" int icl_gemm(icl_model* m, int mode, int a_mn, int b_mn, int M, int N, int K, const float* A, const float* B, float* C) {
+extern "C" int icl_gemm(icl_model* m, int mode, int a_mn, int b_mn, int M, int N, int K, const float* A, const float* B, float* C,
+                        int splits) {
   float *dA, *dB, *dC;
   CK(dmalloc(&dA, (size_t)M * K)); CK(dmalloc(&dB, (size_t)K * N)); CK(dmalloc(&dC, (size_t)M * N));
   CK(cudaMemcpy(dA, A, (size_t)M * K * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dB, B, (size_t)K * N * 4, cudaMemcpyHostToDevice));
   CK(cudaMemset(dC, 0xff, (size_t)M * N * 4));
   GemmArgs g = mk_gemm(dA, a_mn ? M : K, dB, b_mn ? N : K, dC, N, M, N, K);
-  int r = gemm(m, m->stream, a_mn, b_mn, g, mode);
+  int r = gemm(m, m->stream, a_mn, b_mn, g, mode, splits < 1 ? 1 : splits);
   cudaError_t e = cudaStreamSynchronize(m->stream);
   if (r == 0 && e == cudaSuccess) e = cudaMemcpy(C, dC, (size_t)M * N * 4, cudaMemcpyDeviceToHost);
   cudaFree(dA); cudaFree(dB); cudaFree(dC);

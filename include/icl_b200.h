@@ -120,11 +120,16 @@ int icl_sync(icl_model* m);
 /* test / profiling hooks */
 int icl_get_lstm_outputs(icl_model* m, int dir, float* host_STH);        /* pre-dropout outputs, padded [S,T,H] */
 int icl_get_batch_input(icl_model* m, int head, float* host_BD);         /* concat input of head [B,D0] */
+int icl_get_activation(icl_model* m, int head, int layer, float* host_BW);  /* hidden layer output (post-dropout) [B,w] */
 int icl_debug_mask(icl_model* m, uint64_t seed, uint32_t stream, int64_t first_idx, int64_t n, float keep, float* host);
 int icl_gemm(icl_model* m, int mode, int a_mn_major, int b_mn_major, int M, int N, int K,
-             const float* A, const float* B, float* C);                 /* C[M,N] = A*B on the device (validation) */
+             const float* A, const float* B, float* C, int splits);     /* C[M,N] = A*B on the device (validation) */
 int icl_kernel_launches(icl_model* m, int64_t* n);                       /* launches since create */
 int icl_last_step_ms(icl_model* m, float* ms);                           /* device time of last run_resident */
+#define ICL_N_PHASES 8   /* prep, input-projection GEMM, recurrence fwd, heads fwd, heads bwd, BPTT, weight grads, clip+Adam */
+int icl_phase_ms(icl_model* m, float* ms /*[ICL_N_PHASES]*/);            /* per-phase device time of the last run_resident */
+int icl_copy_bytes(icl_model* m, int64_t* h2d, int64_t* d2h);            /* bytes copied by the last upload / fetch */
+int icl_batch_stats(icl_model* m, int64_t* n_seqs, int64_t* n_tokens, int32_t* t_max);   /* of the resident batch */
 
 #ifdef __cplusplus
 }

@@ -277,7 +277,9 @@ def head_forward(params, scope, batch_input, y, n_layers, act, keep=1.0, masks=N
     return res
 
 
-def head_backward(params, res):
+def head_backward(params, res, act_grad_override=None):
+    """act_grad_override: optional list (per hidden layer) of arrays replacing activate_grad -- used by the parity
+    tests to evaluate a piecewise-linear activation on the same side of its kink as the device did."""
     layers, a_last, proba, y, scale, names, act, keep, masks = res["_bwd"]
     grads = {}
     dlog = (proba * y.sum(1, keepdims=True) - y) * scale
@@ -289,7 +291,7 @@ def head_backward(params, res):
         a_in, z, h = layers[k]
         if masks is not None:
             da = da / keep * masks[k]
-        dz = da * activate_grad(z, h, act)
+        dz = da * (activate_grad(z, h, act) if act_grad_override is None else act_grad_override[k])
         grads[names[k][0]] = a_in.T @ dz
         grads[names[k][1]] = dz.sum(0, keepdims=True)
         da = dz @ params[names[k][0]].T
@@ -335,13 +337,13 @@ def model_forward(params, cfg, sentences, seq_lengths, head_batches, keep_in=1.0
     return dict(heads=results, loss=total, out_fw=out_fw, out_bw=out_bw, _lstm=lcache)
 
 
-def model_backward(params, cfg, fwd, head_batches):
+def model_backward(params, cfg, fwd, head_batches, act_grad_override=None):
     grads = {}
     H = cfg["H"]
     d_fw = np.zeros_like(fwd["out_fw"])
     d_bw = np.zeros_like(fwd["out_bw"])
-    for hc, hb, r in zip(cfg["heads"], head_batches, fwd["heads"]):
-        g, d_bi = head_backward(params, r)
+    for hi, (hc, hb, r) in enumerate(zip(cfg["heads"], head_batches, fwd["heads"])):
+        g, d_bi = head_backward(params, r, None if act_grad_override is None else act_grad_override[hi])
         grads.update(g)
         a, b = scatter_spans(d_bi, r["plan"], hb, d_fw.shape, H)
         d_fw += a
