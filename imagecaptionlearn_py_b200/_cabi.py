@@ -62,7 +62,7 @@ class HeadOut(C.Structure):
 SYMBOLS = ["icl_last_error", "icl_version", "icl_create", "icl_destroy", "icl_set_stream", "icl_param_count",
            "icl_param_info", "icl_get_tensor", "icl_set_tensor", "icl_get_step", "icl_set_step", "icl_run",
            "icl_upload", "icl_run_resident", "icl_fetch", "icl_grad_buffer", "icl_param_buffer", "icl_apply_update",
-           "icl_sync", "icl_get_lstm_outputs", "icl_get_batch_input", "icl_get_activation", "icl_debug_mask", "icl_gemm",
+           "icl_sync", "icl_get_lstm_outputs", "icl_get_batch_input", "icl_get_activation", "icl_rec_trace", "icl_debug_mask", "icl_gemm",
            "icl_kernel_launches", "icl_last_step_ms", "icl_phase_ms", "icl_copy_bytes", "icl_batch_stats"]
 N_PHASES = 8
 PHASES = ("prep", "proj_gemm", "rec_fwd", "heads_fwd", "heads_bwd", "rec_bwd", "wgrad", "update")
@@ -100,6 +100,7 @@ def lib():
         L.icl_get_lstm_outputs.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.icl_get_batch_input.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.icl_get_activation.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.icl_rec_trace.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.icl_debug_mask.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int64, C.c_int64, C.c_float, C.c_void_p]
         L.icl_gemm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_int]

@@ -3,6 +3,7 @@
 #include "../../include/icl_b200.h"
 #include "icl_kernels.cuh"
 #include "gemm_tcgen05.cuh"
+#include "lstm_persistent.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -86,6 +87,14 @@ struct icl_model {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   cudaEvent_t ev_ph[PH_N][2] = {};
   bool ph_used[PH_N] = {};
+  // persistent recurrent kernels
+  int rp_U = 0, rp_nsl = 0, rp_nkb = 0, rp_max_tiles = 0;   // rp_U == 0: not available for this H (per-step path)
+  bool rp_on = true, wp_dirty = true;
+  long rows_cap = 0, NtokP = 0;
+  float* Wp[2] = {};
+  unsigned* rp_flags = nullptr;
+  long long* rp_trace = nullptr; int rp_trace_cta = 0;
+  RecFwdMaps rp_fmaps;
   int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
   float last_ms = 0.f;
   TmaCache tma;
@@ -165,6 +174,34 @@ static GemmArgs mk_gemm(const float* A, long lda, const float* B, long ldb, floa
   return g;
 }
 
+// ----------------------------------------------------------------------------- persistent recurrent kernels: host side
+static int box_map(icl_model* m, const float* ptr, uint64_t cols, uint64_t rows, uint32_t box_c, uint32_t box_r, int swizzle,
+                   CUtensorMap* out) {
+  int r = m->tma.get(ptr, cols, rows, cols, box_c, box_r, swizzle, out);
+  return r ? fail("cuTensorMapEncodeTiled failed (%d) for a {%u,%u} box over [%llu,%llu]", r, box_c, box_r,
+                  (unsigned long long)rows, (unsigned long long)cols) : 0;
+}
+template <int U> static int rec_set_attr() {
+  cudaError_t e = cudaFuncSetAttribute(k_rec_fwd<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, rec_fwd_smem<U>(10));
+  return e == cudaSuccess ? 0 : fail("cudaFuncSetAttribute(k_rec_fwd): %s", cudaGetErrorString(e));
+}
+static int rec_init(icl_model* m) {
+  const int H = m->H, U = m->rp_U;
+  const int U0 = U == 20 ? RecSplit<20>::U0 : RecSplit<16>::U0, U1 = U - U0;
+  const uint64_t RC = (uint64_t)m->rows_cap;
+  const int NONE = (int)CU_TENSOR_MAP_SWIZZLE_NONE, SW128 = (int)CU_TENSOR_MAP_SWIZZLE_128B;
+  RecFwdMaps& f = m->rp_fmaps;
+  for (int d = 0; d < 2; d++) {
+    CKI(box_map(m, m->Hp[d], H, RC, 32, 128, SW128, &f.a[d]));
+    CKI(box_map(m, m->Wp[d], (uint64_t)m->rp_nkb * 32, (uint64_t)m->rp_nsl * 4 * U, 32, 4 * U, SW128, &f.w[d]));
+    CKI(box_map(m, m->Z[d], 4 * H, RC, U0, 32, NONE, &f.z0[d]));   CKI(box_map(m, m->Z[d], 4 * H, RC, U1, 32, NONE, &f.z1[d]));
+    CKI(box_map(m, m->Cc[d], H, RC, U0, 32, NONE, &f.cc0[d]));     CKI(box_map(m, m->Cc[d], H, RC, U1, 32, NONE, &f.cc1[d]));
+    CKI(box_map(m, m->Hx[d], H, RC, U0, 32, NONE, &f.hx0[d]));     CKI(box_map(m, m->Hx[d], H, RC, U1, 32, NONE, &f.hx1[d]));
+    CKI(box_map(m, m->Hp[d], H, RC, U0, 32, NONE, &f.hp0[d]));     CKI(box_map(m, m->Hp[d], H, RC, U1, 32, NONE, &f.hp1[d]));
+  }
+  return U == 20 ? rec_set_attr<20>() : rec_set_attr<16>();
+}
+
 // ----------------------------------------------------------------------------- API
 extern "C" const char* icl_last_error(void) { return g_err; }
 extern "C" int icl_version(void) { return 2; }
@@ -177,6 +214,7 @@ extern "C" void icl_destroy(icl_model* m) {
   for (int d = 0; d < 2; d++) {
     F(m->xd[d]); F(m->Z[d]); F(m->Hx[d]); F(m->Hp[d]); F(m->Cc[d]); F(m->dHout[d]); F(m->dhrec[d]); F(m->dcc[d]); F(m->R[d]);
   }
+  F(m->Wp[0]); F(m->Wp[1]); F(m->rp_flags); F(m->rp_trace);
   F(m->d_off); F(m->d_nact); F(m->d_rank); F(m->d_lens); F(m->d_tokseq); F(m->d_tokstart); F(m->d_partial); F(m->d_gnorm);
   if (m->h_x) cudaFreeHost(m->h_x);
   if (m->h_ints) cudaFreeHost(m->h_ints);
@@ -217,6 +255,7 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   int E = m->E = cfg->embed_width, H = m->H = cfg->lstm_hidden;
   m->S_cap = cfg->max_seqs; m->T_cap = cfg->max_seq_len;
   m->Ntok_cap = (long)m->S_cap * m->T_cap;
+  m->rows_cap = (long)m->T_cap * ((m->S_cap + 127) / 128 * 128);      // every step block is padded to 128 rows
   // parameters, named like the TF variables
   const char* dn[2] = {"fw", "bw"};
   for (int d = 0; d < 2; d++) {
@@ -262,17 +301,26 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   CKD(cudaMemset(m->P, 0, np * 4)); CKD(cudaMemset(m->G, 0, np * 4)); CKD(cudaMemset(m->M, 0, np * 4)); CKD(cudaMemset(m->V, 0, np * 4));
   CKD(cudaMemset(m->Pr, 0, np * 4));
   CKD(dmalloc(&m->xraw, (size_t)m->Ntok_cap * E));
+  const size_t RC = (size_t)m->rows_cap, SP = (size_t)(m->S_cap + 127) / 128 * 128;
+  // zero-filled once: rows past nact[k] of a step block only ever hold finite don't-care values
+#define ZALLOC(p, n) do { CKD(dmalloc(&(p), (n))); CKD(cudaMemset((p), 0, (n) * 4)); } while (0)
   for (int d = 0; d < 2; d++) {
-    CKD(dmalloc(&m->xd[d], (size_t)m->Ntok_cap * E));
-    CKD(dmalloc(&m->Z[d], (size_t)m->Ntok_cap * 4 * H));
-    CKD(dmalloc(&m->Hx[d], (size_t)m->Ntok_cap * H));
-    CKD(dmalloc(&m->Hp[d], (size_t)m->Ntok_cap * H));
-    CKD(dmalloc(&m->Cc[d], (size_t)m->Ntok_cap * H));
-    CKD(dmalloc(&m->dHout[d], (size_t)m->Ntok_cap * H));
-    CKD(dmalloc(&m->dhrec[d], (size_t)m->S_cap * H));
-    CKD(dmalloc(&m->dcc[d], (size_t)m->S_cap * H));
-    CKD(dmalloc(&m->R[d], (size_t)m->S_cap * 4 * H));
+    ZALLOC(m->xd[d], RC * E); ZALLOC(m->Z[d], RC * 4 * H); ZALLOC(m->Hx[d], RC * H); ZALLOC(m->Hp[d], RC * H);
+    ZALLOC(m->Cc[d], RC * H); ZALLOC(m->dHout[d], RC * H); ZALLOC(m->dhrec[d], SP * H); ZALLOC(m->dcc[d], SP * H);
+    ZALLOC(m->R[d], SP * 4 * H);
   }
+  m->rp_U = (H % 20 == 0) ? 20 : (H % 16 == 0) ? 16 : 0;
+  m->rp_nkb = (H + 31) / 32;
+  if (m->rp_U && (m->rp_nkb > 10 || m->T_cap > RP_MAXT)) m->rp_U = 0;
+  if (const char* e = getenv("ICL_PERSISTENT")) m->rp_on = atoi(e) != 0;
+  if (m->cfg.gemm_mode != ICL_GEMM_TCGEN05_TF32) m->rp_U = 0;      // the fp32 validation mode keeps the per-step SIMT path
+  if (m->rp_U) {
+    m->rp_nsl = H / m->rp_U;
+    m->rp_max_tiles = (int)(SP / 128);
+    for (int d = 0; d < 2; d++) ZALLOC(m->Wp[d], (size_t)m->rp_nsl * 4 * m->rp_U * m->rp_nkb * 32);
+    CKD(dmalloc(&m->rp_flags, (size_t)2 * m->rp_max_tiles));
+  }
+#undef ZALLOC
   CKD(dmalloc(&m->d_off, m->T_cap + 1)); CKD(dmalloc(&m->d_nact, m->T_cap + 1)); CKD(dmalloc(&m->d_rank, m->S_cap));
   CKD(dmalloc(&m->d_lens, m->S_cap)); CKD(dmalloc(&m->d_tokstart, m->S_cap)); CKD(dmalloc(&m->d_tokseq, m->Ntok_cap));
   CKD(dmalloc(&m->d_partial, 1024)); CKD(dmalloc(&m->d_gnorm, 4));
@@ -309,6 +357,7 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   CKD(cudaEventCreate(&m->ev_t0)); CKD(cudaEventCreate(&m->ev_t1));
   for (int i = 0; i < PH_N; i++) for (int j = 0; j < 2; j++) CKD(cudaEventCreate(&m->ev_ph[i][j]));
   if (tcgen05_gemm_init() != 0) { fail("icl_create: cannot resolve cuTensorMapEncodeTiled"); icl_destroy(m); *out = nullptr; return -1; }
+  if (m->rp_U && rec_init(m) != 0) { icl_destroy(m); *out = nullptr; return -1; }
 #undef CKD
   return 0;
 }
@@ -340,13 +389,13 @@ extern "C" int icl_set_tensor(icl_model* m, int kind, const char* name, const fl
   const Param& p = m->params[it->second];
   CK(cudaStreamSynchronize(m->stream));
   CK(cudaMemcpy(kind_buf(m, kind) + p.off, host, (size_t)p.rows * p.cols * 4, cudaMemcpyHostToDevice));
-  if (kind == 0) m->pr_dirty = true;
+  if (kind == 0) m->pr_dirty = m->wp_dirty = true;
   return 0;
 }
 extern "C" int icl_get_step(icl_model* m, int64_t* t) { *t = m->step; return 0; }
 extern "C" int icl_set_step(icl_model* m, int64_t t) { m->step = t; return 0; }
 extern "C" int icl_grad_buffer(icl_model* m, void** p, int64_t* n) { *p = m->G; *n = m->n_params; return 0; }
-extern "C" int icl_param_buffer(icl_model* m, void** p, int64_t* n) { *p = m->P; *n = m->n_params; m->pr_dirty = true; return 0; }
+extern "C" int icl_param_buffer(icl_model* m, void** p, int64_t* n) { *p = m->P; *n = m->n_params; m->pr_dirty = m->wp_dirty = true; return 0; }
 extern "C" int icl_kernel_launches(icl_model* m, int64_t* n) { *n = m->launches; return 0; }
 extern "C" int icl_last_step_ms(icl_model* m, float* ms) { *ms = m->last_ms; return 0; }
 extern "C" int icl_copy_bytes(icl_model* m, int64_t* h2d, int64_t* d2h) { *h2d = m->h2d_bytes; *d2h = m->d2h_bytes; return 0; }
@@ -392,7 +441,7 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
   m->n_active.assign(tmax + 1, 0);
   for (int s = 0; s < S; s++) for (int k = 0; k < lens[s]; k++) m->n_active[k]++;
   m->off.assign(tmax + 2, 0);
-  for (int k = 0; k <= tmax; k++) m->off[k + 1] = m->off[k] + m->n_active[k];
+  for (int k = 0; k <= tmax; k++) m->off[k + 1] = m->off[k] + (m->n_active[k] + 127) / 128 * 128;   // blocks padded to 128 rows
   for (int k = 0; k <= tmax; k++) { offs[k] = m->off[k]; nact[k] = m->n_active[k]; }
   // pack valid tokens (caption-major) into pinned memory as fp32
   size_t esz = b->sent_dtype == ICL_F64 ? 8 : 4;
@@ -445,7 +494,7 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
     h.has_labels = hb.labels != nullptr;
     if (h.has_labels) CKI(up(hb.labels, hb.labels_dtype, h.labels, (size_t)B * C, "labels"));
   }
-  m->S = S; m->Tmax = tmax; m->Ntok = ntok;
+  m->S = S; m->Tmax = tmax; m->Ntok = ntok; m->NtokP = m->off[tmax];
   m->seq_gid0 = b->seq_gid_offset; m->ex_gid0 = b->ex_gid_offset;
   m->resident = true;
   return 0;
@@ -467,35 +516,90 @@ static int refresh_rounded_params(icl_model* m) {
   return 0;
 }
 
-static int lstm_forward(icl_model* m, float keep_in, uint64_t seed) {
+// rows [nact[k], padded end) of every step block -> 0 (operands of the time-batched weight-gradient GEMMs)
+__global__ void k_zero_pad_rows(float* __restrict__ buf, StepLayout L, int W) {
+  const int k = blockIdx.x;
+  const long r0 = (long)L.off[k] + L.nact[k], r1 = L.off[k + 1];
+  float4* p = reinterpret_cast<float4*>(buf + r0 * W);
+  const long n4 = (r1 - r0) * W / 4;
+  for (long i = threadIdx.x; i < n4; i += blockDim.x) p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+static bool rec_usable(icl_model* m) {
+  if (m->rp_U == 0 || !m->rp_on || m->Tmax > RP_MAXT) return false;
+  int tiles = (m->n_active[0] + 127) / 128, P = std::max(1, std::min(148 / (2 * m->rp_nsl), tiles));
+  return (tiles + P - 1) / P <= RP_MAXTPC;          // the kernel carries the cell state of <= RP_MAXTPC tiles per CTA in registers
+}
+
+static RecArgs rec_args(icl_model* m, int training) {
+  RecArgs a;
+  a.off = m->d_off; a.nact = m->d_nact; a.Tmax = m->Tmax; a.H = m->H; a.nsl = m->rp_nsl;
+  int tiles = (m->n_active[0] + 127) / 128;
+  a.P = std::max(1, std::min(148 / (2 * m->rp_nsl), tiles));
+  a.nkb = m->rp_nkb; a.nk8 = (m->H + 7) / 8; a.max_tiles = m->rp_max_tiles; a.training = training; a.flags = m->rp_flags;
+  a.trace = m->rp_trace; a.trace_cta = m->rp_trace_cta;
+  return a;
+}
+
+static int rec_forward_persistent(icl_model* m, int training) {
+  cudaStream_t st = m->stream;
+  const int E = m->E, H = m->H, U = m->rp_U;
+  if (m->wp_dirty) {
+    for (int d = 0; d < 2; d++) {
+      const float* Whh = m->P + m->params[m->pK[d]].off + (size_t)E * 4 * H;
+      k_pack_whh_fwd<<<148, 256, 0, st>>>(Whh, m->Wp[d], H, U, m->rp_nsl, m->rp_nkb * 32); LAUNCHED(m);
+    }
+    m->wp_dirty = false;
+  }
+  CK(cudaMemsetAsync(m->rp_flags, 0, (size_t)2 * m->rp_max_tiles * 4, st));
+  RecArgs a = rec_args(m, training);
+  void* args[] = {(void*)&m->rp_fmaps, (void*)&a};
+  dim3 grid(2 * a.P * a.nsl), block(RP_FWD_THREADS);
+  cudaError_t e;
+  if (U == 20) e = cudaLaunchCooperativeKernel((void*)k_rec_fwd<20>, grid, block, args, rec_fwd_smem<20>(a.nkb), st);
+  else e = cudaLaunchCooperativeKernel((void*)k_rec_fwd<16>, grid, block, args, rec_fwd_smem<16>(a.nkb), st);
+  if (e != cudaSuccess) return fail("k_rec_fwd launch failed: %s", cudaGetErrorString(e));
+  m->launches++;
+  return 0;
+}
+
+static int lstm_forward(icl_model* m, float keep_in, uint64_t seed, int training) {
   int E = m->E, H = m->H;
-  long Ntok = m->Ntok;
+  long Ntok = m->Ntok, NP = m->NtokP;
   cudaStream_t st = m->stream;
   if (Ntok == 0) return 0;
   PH_BEGIN(m, PH_PREP);
   k_prep_x<<<(unsigned)((Ntok * 32 + 255) / 256), 256, 0, st>>>(m->xraw, m->d_tokseq, m->d_tokstart, mk_layout(m), (int)Ntok, E, m->T_cap,
                                                                m->cfg.data_norm, keep_in, seed, m->seq_gid0, m->round_ops, m->xd[0], m->xd[1]);
   LAUNCHED(m);
-  // h_prev of step 0 is the zero state: the first nact[0] rows of Hp stay zero (they are the A rows of dW_hh)
-  for (int d = 0; d < 2; d++) CK(cudaMemsetAsync(m->Hp[d], 0, (size_t)m->n_active[0] * H * 4, st));
+  for (int d = 0; d < 2; d++) {
+    k_zero_pad_rows<<<m->Tmax, 256, 0, st>>>(m->xd[d], mk_layout(m), E); LAUNCHED(m);
+    // h_prev of step 0 is the zero state: step 0's block of Hp stays zero (these are A rows of dW_hh)
+    CK(cudaMemsetAsync(m->Hp[d], 0, (size_t)m->off[1] * H * 4, st));
+  }
   PH_END(m, PH_PREP);
   // K1: time-batched input projection  Z = Xd * W_ih + b   (W_ih = kernel rows [0,E)), both directions
   PH_BEGIN(m, PH_PROJ);
   for (int d = 0; d < 2; d++) {
     const float* K = wbase(m) + m->params[m->pK[d]].off;
-    GemmArgs g = mk_gemm(m->xd[d], E, K, 4 * H, m->Z[d], 4 * H, (int)Ntok, 4 * H, E);
+    GemmArgs g = mk_gemm(m->xd[d], E, K, 4 * H, m->Z[d], 4 * H, (int)NP, 4 * H, E);
     g.epi.bias = m->P + m->params[m->pBias[d]].off;
     CKI(gemm(m, st, false, true, g));
   }
   PH_END(m, PH_PROJ);
   // K2: the recurrence
   PH_BEGIN(m, PH_REC_FWD);
+  if (rec_usable(m)) {
+    CKI(rec_forward_persistent(m, training));
+    PH_END(m, PH_REC_FWD);
+    return 0;
+  }
   CK(cudaEventRecord(m->ev_fork, st));
   CK(cudaStreamWaitEvent(m->aux, m->ev_fork, 0));
-  for (int d = 0; d < 2; d++) {
-    cudaStream_t sd = d ? m->aux : st;
-    const float* Whh = wbase(m) + m->params[m->pK[d]].off + (size_t)E * 4 * H;
-    for (int k = 0; k < m->Tmax; k++) {
+  for (int k = 0; k < m->Tmax; k++) {
+    for (int d = 0; d < 2; d++) {        // directions interleaved on two streams so the host feeds both concurrently
+      cudaStream_t sd = d ? m->aux : st;
+      const float* Whh = wbase(m) + m->params[m->pK[d]].off + (size_t)E * 4 * H;
       int n = m->n_active[k], n_next = m->n_active[k + 1];
       long o = m->off[k];
       if (k > 0) {   // R = h_{k-1} * W_hh for the running rows
@@ -560,7 +664,7 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
   cudaStream_t st = m->stream;
   int H = m->H;
   PH_BEGIN(m, PH_HEADS_BWD);
-  for (int d = 0; d < 2; d++) CK(cudaMemsetAsync(m->dHout[d], 0, (size_t)m->Ntok * H * 4, st));
+  for (int d = 0; d < 2; d++) CK(cudaMemsetAsync(m->dHout[d], 0, (size_t)m->NtokP * H * 4, st));
   for (size_t hi = 0; hi < m->heads.size(); hi++) {
     Head& h = m->heads[hi];
     if (!h.has_labels) return fail("backward needs labels for head %zu", hi);
@@ -600,19 +704,22 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
 
 static int lstm_backward(icl_model* m) {
   int E = m->E, H = m->H, S = m->S;
-  long Ntok = m->Ntok;
+  long Ntok = m->NtokP;            // time-batched GEMMs run over the padded row space (pad rows are zero)
   cudaStream_t st = m->stream;
-  if (Ntok == 0) return 0;
+  if (m->Ntok == 0) return 0;
   // K3: BPTT
   PH_BEGIN(m, PH_REC_BWD);
   CK(cudaEventRecord(m->ev_fork, st));
   CK(cudaStreamWaitEvent(m->aux, m->ev_fork, 0));
   for (int d = 0; d < 2; d++) {
     cudaStream_t sd = d ? m->aux : st;
-    const float* Whh = wbase(m) + m->params[m->pK[d]].off + (size_t)E * 4 * H;
     CK(cudaMemsetAsync(m->dhrec[d], 0, (size_t)S * H * 4, sd));
     CK(cudaMemsetAsync(m->dcc[d], 0, (size_t)S * H * 4, sd));
-    for (int k = m->Tmax - 1; k >= 0; k--) {
+  }
+  for (int k = m->Tmax - 1; k >= 0; k--) {
+    for (int d = 0; d < 2; d++) {        // directions interleaved on two streams so the host feeds both concurrently
+      cudaStream_t sd = d ? m->aux : st;
+      const float* Whh = wbase(m) + m->params[m->pK[d]].off + (size_t)E * 4 * H;
       int n = m->n_active[k];
       long o = m->off[k];
       long nthr = (long)n * (H / 4);
@@ -628,6 +735,8 @@ static int lstm_backward(icl_model* m) {
   }
   CK(cudaEventRecord(m->ev_join, m->aux));
   CK(cudaStreamWaitEvent(st, m->ev_join, 0));
+  // pad rows of dZ must be exactly zero for the time-batched weight-gradient GEMMs (they still hold gates / Zx)
+  for (int d = 0; d < 2; d++) { k_zero_pad_rows<<<m->Tmax, 256, 0, st>>>(m->Z[d], mk_layout(m), 4 * H); LAUNCHED(m); }
   PH_END(m, PH_REC_BWD);
   // time-batched weight gradients: dW_ih = Xd^T dZ, dW_hh = Hprev^T dZ (contraction over all tokens, split-K), db = colsum(dZ)
   PH_BEGIN(m, PH_WGRAD);
@@ -672,7 +781,7 @@ extern "C" int icl_run_resident(icl_model* m, int op, float keep_in, float keep,
   for (int i = 0; i < PH_N; i++) m->ph_used[i] = false;
   CK(cudaEventRecord(m->ev_t0, m->stream));
   CKI(refresh_rounded_params(m));
-  CKI(lstm_forward(m, keep_in, seed));
+  CKI(lstm_forward(m, keep_in, seed, op >= ICL_OP_GRADS));
   CKI(heads_forward(m, keep, seed));
   if (op >= ICL_OP_GRADS) {
     CKI(heads_backward(m, keep, seed));
@@ -739,6 +848,17 @@ extern "C" int icl_get_activation(icl_model* m, int head, int layer, float* host
   if (layer < 0 || layer >= h.c.n_hidden) return fail("layer out of range");
   CK(cudaStreamSynchronize(m->stream));
   CK(cudaMemcpy(host, h.act[layer], (size_t)h.c.batch_size * h.dims[layer + 1] * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+// bring-up: trace the roles of one CTA of the persistent kernels during the next runs; host gets [4][RP_TRACE_EV][4] int64
+extern "C" int icl_rec_trace(icl_model* m, int cta, long long* host) {
+  if (!m->rp_trace) { CK(cudaMalloc((void**)&m->rp_trace, (size_t)4 * RP_TRACE_EV * 4 * 8)); }
+  if (host) {
+    CK(cudaStreamSynchronize(m->stream));
+    CK(cudaMemcpy(host, m->rp_trace, (size_t)4 * RP_TRACE_EV * 4 * 8, cudaMemcpyDeviceToHost));
+  }
+  CK(cudaMemset(m->rp_trace, 0xff, (size_t)4 * RP_TRACE_EV * 4 * 8));
+  m->rp_trace_cta = cta;
   return 0;
 }
 extern "C" int icl_debug_mask(icl_model* m, uint64_t seed, uint32_t stream, int64_t first, int64_t n, float keep, float* host) {

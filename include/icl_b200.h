@@ -121,6 +121,7 @@ int icl_sync(icl_model* m);
 int icl_get_lstm_outputs(icl_model* m, int dir, float* host_STH);        /* pre-dropout outputs, padded [S,T,H] */
 int icl_get_batch_input(icl_model* m, int head, float* host_BD);         /* concat input of head [B,D0] */
 int icl_get_activation(icl_model* m, int head, int layer, float* host_BW);  /* hidden layer output (post-dropout) [B,w] */
+int icl_rec_trace(icl_model* m, int cta, long long* host);               /* bring-up trace of one persistent-kernel CTA */
 int icl_debug_mask(icl_model* m, uint64_t seed, uint32_t stream, int64_t first_idx, int64_t n, float keep, float* host);
 int icl_gemm(icl_model* m, int mode, int a_mn_major, int b_mn_major, int M, int N, int K,
              const float* A, const float* B, float* C, int splits);     /* C[M,N] = A*B on the device (validation) */
