@@ -6,9 +6,13 @@
 // Both majors are needed without transposes: forward layers are (K, MN), input-gradient GEMMs are (K, K) and the
 // time-batched weight-gradient GEMMs (contraction over tokens) are (MN, MN).
 //
-// One 128x128 output tile per CTA, BK = 32 fp32 (one 128-byte swizzle row), 3-stage mbarrier pipeline.
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2-5 = epilogue.
-// ~97 KB of shared memory -> two CTAs per SM, so one CTA's epilogue overlaps the other's main loop.
+// One 128 x BN output tile per CTA (BN = 128 or 256), BK = 32 fp32 (one 128-byte swizzle row), STAGES-deep mbarrier
+// pipeline.  Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2-5 = epilogue.
+// Configurations (picked per call by tcgen05_gemm_launch):
+//   <128,3>  97 KB smem, two CTAs per SM: many-tile GEMMs, one CTA's epilogue overlaps the other's main loop
+//   <128,6> 193 KB smem, one CTA per SM: few tiles with a long K loop -- latency-bound, so a deeper ring
+//   <256,2>  97 KB / <256,4> 193 KB: wide tiles halve the L2->SM bytes per MMA cycle (TF32 tiles of 128x128 need ~128 B/clk
+//            per SM, more than one SM can ingest); used when N >= 512.
 // Epilogue: TMEM -> registers (one accumulator row per thread) -> a per-warp 32x33 staging tile in the (by then idle)
 // pipeline buffers -> row-wise, so every global access of the fused epilogue (bias, aux, C) is a coalesced 128-byte line.
 #pragma once
@@ -24,10 +28,10 @@
 
 namespace icl {
 
-constexpr int TG_BM = 128, TG_BN = 128, TG_BK = 32, TG_STAGES = 3;
-constexpr int TG_TILE_BYTES = TG_BM * TG_BK * 4;                       // 16 KB per operand per stage
-constexpr int TG_SMEM = TG_STAGES * 2 * TG_TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TG_BM = 128, TG_BK = 32;
+constexpr int TG_A_BYTES = TG_BM * TG_BK * 4;                          // 16 KB per A stage
 constexpr int TG_THREADS = 192;
+constexpr int tg_smem(int BN, int STAGES) { return STAGES * (TG_A_BYTES + BN * TG_BK * 4) + 1024 /*align*/ + 256 /*barriers*/; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -106,7 +110,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_b
   d |= (uint64_t)(layout & 7) << 61;
   return d;
 }
-struct MnDescCfg { uint32_t layout, sbo, lbo, kstep; };   // MN-major descriptor parameters (env-overridable for bring-up)
+// MN-major 32-bit operands: SWIZZLE_128B_BASE32B descriptors (layout 1), SBO = 512 B between 4-deep k atoms, LBO = 4 KB
+// between 128-byte MN blocks ([mn/32][k][32 fp32] tiles), 1 KB per 8-deep MMA step; TMA twin: SWIZZLE_128B_ATOM_32B.
+constexpr uint32_t MN_LAYOUT = 1, MN_SBO = 512, MN_LBO = 32 * TG_BK * 4, MN_KSTEP = 1024;
 // Instruction descriptor: c_format F32 (1) [4,6); a/b format [7,10)/[10,13) (F16=0, BF16=1, TF32=2);
 // a_major [15], b_major [16] (1 = MN-major); N>>3 [17,23); M>>4 [24,29).
 __host__ __device__ constexpr uint32_t make_idesc(int fmt, bool a_mn, bool b_mn, int M, int N) {
@@ -114,16 +120,17 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, bool a_mn, bool b_mn,
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int BN, int STAGES>
 __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA,
-                                                             const __grid_constant__ CUtensorMap tmB, const GemmArgs g, const MnDescCfg mn) {
+                                                             const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+  constexpr int B_BYTES = BN * TG_BK * 4;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-byte alignment
-  const uint32_t sA = base, sB = base + TG_STAGES * TG_TILE_BYTES;
-  const uint32_t bars = sB + TG_STAGES * TG_TILE_BYTES;
-  const uint32_t full0 = bars, empty0 = bars + 8 * TG_STAGES, tmem_full = bars + 16 * TG_STAGES, tmem_slot = tmem_full + 8;
+  const uint32_t sA = base, sB = base + STAGES * TG_A_BYTES;
+  const uint32_t bars = sB + STAGES * B_BYTES;
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tmem_full = bars + 16 * STAGES, tmem_slot = tmem_full + 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TG_BM, n0 = blockIdx.x * TG_BN;
+  const int m0 = blockIdx.y * TG_BM, n0 = blockIdx.x * BN;
   // split-K (gridDim.z > 1): this CTA contracts k-blocks [kb0, kb0+num_kb) and adds its partial tile to C with red.global
   const int total_kb = (g.K + TG_BK - 1) / TG_BK;
   const int kb_per = (total_kb + gridDim.z - 1) / gridDim.z;
@@ -132,14 +139,14 @@ __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_consta
   if (num_kb == 0) return;                                             // uniform per CTA, before any barrier / TMEM allocation
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TG_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TG_BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -151,11 +158,11 @@ __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_consta
   if (warp == 0) {
     if (lane == 0) {                                                   // ---- TMA producer
       for (int kb = 0; kb < num_kb; kb++) {
-        const int s = kb % TG_STAGES;
-        mbar_wait(empty0 + 8 * s, ((kb / TG_STAGES) & 1) ^ 1);
+        const int s = kb % STAGES;
+        mbar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
         const uint32_t fb = full0 + 8 * s;
-        mbar_expect_tx(fb, 2 * TG_TILE_BYTES);                         // OOB parts of a box are zero-filled and still counted
-        const uint32_t a = sA + s * TG_TILE_BYTES, b = sB + s * TG_TILE_BYTES;
+        mbar_expect_tx(fb, TG_A_BYTES + B_BYTES);                      // OOB parts of a box are zero-filled and still counted
+        const uint32_t a = sA + s * TG_A_BYTES, b = sB + s * B_BYTES;
         if (A_MN) {
 #pragma unroll
           for (int j = 0; j < TG_BM / 32; j++) tma_load_2d(a + j * (32 * TG_BK * 4), &tmA, m0 + 32 * j, (kb0 + kb) * TG_BK, fb);
@@ -164,7 +171,7 @@ __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_consta
         }
         if (B_MN) {
 #pragma unroll
-          for (int j = 0; j < TG_BN / 32; j++) tma_load_2d(b + j * (32 * TG_BK * 4), &tmB, n0 + 32 * j, (kb0 + kb) * TG_BK, fb);
+          for (int j = 0; j < BN / 32; j++) tma_load_2d(b + j * (32 * TG_BK * 4), &tmB, n0 + 32 * j, (kb0 + kb) * TG_BK, fb);
         } else {
           tma_load_2d(b, &tmB, (kb0 + kb) * TG_BK, n0, fb);
         }
@@ -172,16 +179,16 @@ __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_consta
     }
   } else if (warp == 1) {
     if (lane == 0) {                                                   // ---- MMA issuer (one thread)
-      constexpr uint32_t idesc = make_idesc(2, A_MN, B_MN, TG_BM, TG_BN);
+      constexpr uint32_t idesc = make_idesc(2, A_MN, B_MN, TG_BM, BN);
       for (int kb = 0; kb < num_kb; kb++) {
-        const int s = kb % TG_STAGES;
-        mbar_wait(full0 + 8 * s, (kb / TG_STAGES) & 1);
+        const int s = kb % STAGES;
+        mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
         tc_fence_after();
-        const uint32_t a = sA + s * TG_TILE_BYTES, b = sB + s * TG_TILE_BYTES;
+        const uint32_t a = sA + s * TG_A_BYTES, b = sB + s * B_BYTES;
 #pragma unroll
         for (int kk = 0; kk < TG_BK / 8; kk++) {                       // UMMA_K = 8 for tf32
-          const uint64_t ad = A_MN ? make_smem_desc(a + kk * mn.kstep, mn.lbo, mn.sbo, mn.layout) : make_smem_desc(a + kk * 32, 16, 1024);
-          const uint64_t bd = B_MN ? make_smem_desc(b + kk * mn.kstep, mn.lbo, mn.sbo, mn.layout) : make_smem_desc(b + kk * 32, 16, 1024);
+          const uint64_t ad = A_MN ? make_smem_desc(a + kk * MN_KSTEP, MN_LBO, MN_SBO, MN_LAYOUT) : make_smem_desc(a + kk * 32, 16, 1024);
+          const uint64_t bd = B_MN ? make_smem_desc(b + kk * MN_KSTEP, MN_LBO, MN_SBO, MN_LAYOUT) : make_smem_desc(b + kk * 32, 16, 1024);
           tc_mma_tf32(tmem_acc, ad, bd, idesc, (kb | kk) != 0);
         }
         tc_commit(empty0 + 8 * s);                                     // frees the smem stage when these MMAs retire
@@ -195,7 +202,7 @@ __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_consta
     float* stg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))) + q * (32 * 33);
     const int mrow0 = m0 + q * 32;
 #pragma unroll 1
-    for (int c = 0; c < TG_BN; c += 32) {
+    for (int c = 0; c < BN; c += 32) {
       if (n0 + c >= g.N) break;
       uint32_t r[32];
       tc_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + c, r);
@@ -218,7 +225,7 @@ __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_consta
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(TG_BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(BN) : "memory");
   }
 }
 
@@ -228,33 +235,29 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static PFN_encodeTiled g_encode = nullptr;
 
-static MnDescCfg g_mn = {1u, 512u, 32u * TG_BK * 4u, 1024u};
-static int g_mn_tma_swizzle = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-static void tcgen05_read_env() {
-  if (const char* e = getenv("ICL_MN_LAYOUT")) g_mn.layout = (uint32_t)atoi(e);
-  if (const char* e = getenv("ICL_MN_SBO")) g_mn.sbo = (uint32_t)atoi(e);
-  if (const char* e = getenv("ICL_MN_LBO")) g_mn.lbo = (uint32_t)atoi(e);
-  if (const char* e = getenv("ICL_MN_KSTEP")) g_mn.kstep = (uint32_t)atoi(e);
-  if (const char* e = getenv("ICL_MN_TMASW")) g_mn_tma_swizzle = atoi(e);
+template <bool A_MN, bool B_MN> static cudaError_t tg_set_attrs() {
+  cudaError_t e = cudaFuncSetAttribute(k_gemm_tcgen05<A_MN, B_MN, 128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg_smem(128, 3));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tcgen05<A_MN, B_MN, 128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg_smem(128, 6));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tcgen05<A_MN, B_MN, 256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg_smem(256, 2));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tcgen05<A_MN, B_MN, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg_smem(256, 4));
+  return e;
 }
-
 static int tcgen05_gemm_init() {
   if (g_encode) return 0;
-  tcgen05_read_env();
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return -1;
   g_encode = (PFN_encodeTiled)fn;
-  cudaFuncSetAttribute(k_gemm_tcgen05<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM);
-  cudaFuncSetAttribute(k_gemm_tcgen05<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM);
-  cudaFuncSetAttribute(k_gemm_tcgen05<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM);
-  cudaFuncSetAttribute(k_gemm_tcgen05<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM);
-  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+  cudaError_t e = tg_set_attrs<false, false>();
+  if (e == cudaSuccess) e = tg_set_attrs<false, true>();
+  if (e == cudaSuccess) e = tg_set_attrs<true, false>();
+  if (e == cudaSuccess) e = tg_set_attrs<true, true>();
+  return e == cudaSuccess ? 0 : -2;
 }
 
 struct TmaCache {
   std::map<std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t, uint32_t, int>, CUtensorMap> maps;
-  // 2-D fp32 tensor: dim0 (contiguous) x dim1 with row pitch ld (floats); box = box0 x box1, 128B swizzle, zero OOB fill
+  // 2-D fp32 tensor: dim0 (contiguous) x dim1 with row pitch ld (floats); box = box0 x box1, zero OOB fill
   int get(const float* ptr, uint64_t dim0, uint64_t dim1, uint64_t ld, uint32_t box0, uint32_t box1, int swizzle, CUtensorMap* out) {
     auto key = std::make_tuple((const void*)ptr, dim0, dim1, ld, box0, box1, swizzle);
     auto it = maps.find(key);
@@ -275,28 +278,41 @@ struct TmaCache {
 };
 
 static bool tcgen05_gemm_supported(const GemmArgs& g, bool a_mn, bool b_mn) {
-  // TMA: 16-byte aligned base and row pitch; tiny problems stay on the SIMT kernel
+  // TMA: 16-byte aligned base and row pitch
   if (((uintptr_t)g.A & 15) || ((uintptr_t)g.B & 15) || (g.lda & 3) || (g.ldb & 3)) return false;
   if (g.N < 1 || g.M < 1 || g.K < 1) return false;
   (void)a_mn; (void)b_mn;
   return true;
 }
 
+template <bool A_MN, bool B_MN, int BN, int STAGES>
+static void tg_launch(dim3 grid, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g) {
+  k_gemm_tcgen05<A_MN, B_MN, BN, STAGES><<<grid, TG_THREADS, tg_smem(BN, STAGES), st>>>(ta, tb, g);
+}
+template <bool A_MN, bool B_MN>
+static void tg_dispatch(int BN, bool deep, dim3 grid, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g) {
+  if (BN == 256) { if (deep) tg_launch<A_MN, B_MN, 256, 4>(grid, st, ta, tb, g); else tg_launch<A_MN, B_MN, 256, 2>(grid, st, ta, tb, g); }
+  else { if (deep) tg_launch<A_MN, B_MN, 128, 6>(grid, st, ta, tb, g); else tg_launch<A_MN, B_MN, 128, 3>(grid, st, ta, tb, g); }
+}
+
+// splits == 0: choose a split-K factor for few-tile / long-K problems (the caller must then accept a red.global epilogue)
 static int tcgen05_gemm_launch(TmaCache& cache, cudaStream_t st, bool a_mn, bool b_mn, const GemmArgs& g, int splits = 1) {
+  const int BN = g.N >= 512 ? 256 : 128;
   CUtensorMap ta, tb;
   int r;
-  const int swk = (int)CU_TENSOR_MAP_SWIZZLE_128B;
-  if (a_mn) r = cache.get(g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda, 32, TG_BK, g_mn_tma_swizzle, &ta);
+  const int swk = (int)CU_TENSOR_MAP_SWIZZLE_128B, swmn = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  if (a_mn) r = cache.get(g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda, 32, TG_BK, swmn, &ta);
   else r = cache.get(g.A, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)g.lda, TG_BK, TG_BM, swk, &ta);
   if (r) return 1000 + r;
-  if (b_mn) r = cache.get(g.B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb, 32, TG_BK, g_mn_tma_swizzle, &tb);
-  else r = cache.get(g.B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb, TG_BK, TG_BN, swk, &tb);
+  if (b_mn) r = cache.get(g.B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb, 32, TG_BK, swmn, &tb);
+  else r = cache.get(g.B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb, TG_BK, BN, swk, &tb);
   if (r) return 2000 + r;
-  dim3 grid((g.N + TG_BN - 1) / TG_BN, (g.M + TG_BM - 1) / TG_BM, splits);
-  if (!a_mn && !b_mn) k_gemm_tcgen05<false, false><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, g, g_mn);
-  else if (!a_mn && b_mn) k_gemm_tcgen05<false, true><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, g, g_mn);
-  else if (a_mn && b_mn) k_gemm_tcgen05<true, true><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, g, g_mn);
-  else k_gemm_tcgen05<true, false><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, g, g_mn);
+  dim3 grid((g.N + BN - 1) / BN, (g.M + TG_BM - 1) / TG_BM, splits);
+  const bool deep = (long)grid.x * grid.y * grid.z <= 148;             // one CTA per SM anyway: spend the smem on pipeline depth
+  if (!a_mn && !b_mn) tg_dispatch<false, false>(BN, deep, grid, st, ta, tb, g);
+  else if (!a_mn && b_mn) tg_dispatch<false, true>(BN, deep, grid, st, ta, tb, g);
+  else if (a_mn && b_mn) tg_dispatch<true, true>(BN, deep, grid, st, ta, tb, g);
+  else tg_dispatch<true, false>(BN, deep, grid, st, ta, tb, g);
   return cudaGetLastError() == cudaSuccess ? 0 : 3000;
 }
 

@@ -212,7 +212,7 @@ __device__ __forceinline__ long token_row(const StepLayout& L, int dir, int s, i
 // (core.py:309-312), written to each direction's step-major row; TF32-rounded when the rows feed the tensor cores.
 __global__ void k_prep_x(const float* __restrict__ xraw, const int* __restrict__ tok_seq, const int* __restrict__ tokstart,
                          StepLayout L, int ntok, int E, int Tcap, int data_norm, float keep_in, uint64_t seed,
-                         int64_t seq_gid0, int round_ops, float* __restrict__ xfw, float* __restrict__ xbw) {
+                         int64_t seq_gid0, int round_ops, float* __restrict__ xfw, float* __restrict__ xbw, int ldx) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= ntok) return;
   int s = tok_seq[warp];
@@ -242,8 +242,8 @@ __global__ void k_prep_x(const float* __restrict__ xraw, const int* __restrict__
       if (keep_in < 1.0f) { vf[j] = xv[j] / keep_in * mf[j]; vb[j] = xv[j] / keep_in * mb[j]; }
       vf[j] = maybe_round(vf[j], round_ops); vb[j] = maybe_round(vb[j], round_ops);
     }
-    *reinterpret_cast<float4*>(xfw + rfw * E + e4) = make_float4(vf[0], vf[1], vf[2], vf[3]);
-    *reinterpret_cast<float4*>(xbw + rbw * E + e4) = make_float4(vb[0], vb[1], vb[2], vb[3]);
+    *reinterpret_cast<float4*>(xfw + rfw * ldx + e4) = make_float4(vf[0], vf[1], vf[2], vf[3]);
+    *reinterpret_cast<float4*>(xbw + rbw * ldx + e4) = make_float4(vb[0], vb[1], vb[2], vb[3]);
   }
 }
 
@@ -274,8 +274,8 @@ __device__ __forceinline__ CellGrad lstm_cell_bwd(float si, float tj, float sf, 
 // Per-step forward cell (the non-persistent path): z = Zx (+ R, the recurrent product of this step) for rows
 // [0,n) of step k.  Z rows are overwritten with the activated gates for the backward pass.  Each thread = 4 units.
 __global__ void k_lstm_cell_fwd(float* __restrict__ Zk, const float* __restrict__ R, const float* __restrict__ Cprev,
-                                float* __restrict__ Ck, float* __restrict__ Hk, float* __restrict__ Hp_next, int n, int n_next,
-                                int H, int round_ops) {
+                                float* __restrict__ Ck, float* __restrict__ Hk, float* __restrict__ Hp_next, int ldhp, int n,
+                                int n_next, int H, int round_ops) {
   int q = H >> 2;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long)n * q) return;
@@ -305,7 +305,7 @@ __global__ void k_lstm_cell_fwd(float* __restrict__ Zk, const float* __restrict_
   *reinterpret_cast<float4*>(z + 3 * H) = make_float4(so[0], so[1], so[2], so[3]);
   *reinterpret_cast<float4*>(Ck + (long)m * H + u) = make_float4(c[0], c[1], c[2], c[3]);
   *reinterpret_cast<float4*>(Hk + (long)m * H + u) = make_float4(h[0], h[1], h[2], h[3]);
-  if (m < n_next) *reinterpret_cast<float4*>(Hp_next + (long)m * H + u) = make_float4(hr[0], hr[1], hr[2], hr[3]);
+  if (m < n_next) *reinterpret_cast<float4*>(Hp_next + (long)m * ldhp + u) = make_float4(hr[0], hr[1], hr[2], hr[3]);
 }
 
 // Per-step backward cell: gates in Zk rows -> dZ (in place); dh = dHout + dhrec (rank-indexed carry), dc carry.

@@ -12,7 +12,12 @@
 #include <cstring>
 #include <map>
 #include <numeric>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace icl;
@@ -72,6 +77,10 @@ struct icl_model {
   int pK[2], pBias[2];
   int64_t step = 0;
   // workspaces (step-major, see icl_kernels.cuh)
+  // XH[d] = [rows, E+H]: columns [0,E) the prepared inputs (xd), columns [E,E+H) the TF32 h_{k-1} operand rows (Hp) -- one
+  // matrix so that dKernel = XH^T dZ is a single GEMM; xd / Hp are views with row pitch ldx = E+H
+  float *XH[2] = {};
+  int ldx = 0;
   float *xraw = nullptr, *xd[2] = {}, *Z[2] = {}, *Hx[2] = {}, *Hp[2] = {}, *Cc[2] = {}, *dHout[2] = {}, *dhrec[2] = {}, *dcc[2] = {},
         *R[2] = {};
   int *d_off = nullptr, *d_nact = nullptr, *d_rank = nullptr, *d_lens = nullptr, *d_tokseq = nullptr, *d_tokstart = nullptr;
@@ -115,6 +124,58 @@ static void to_f32(float* dst, const void* src, int dtype, size_t n) {
   for (size_t i = 0; i < n; i++) dst[i] = (float)read_num(src, dtype, i);
 }
 
+// Host worker pool for the batch marshalling (pack / convert sentences into pinned memory).  Threads are created once
+// per process: spawning them per call costs more than the 30 MB copy they parallelise.
+struct HostPool {
+  std::vector<std::thread> th;
+  std::mutex mu;
+  std::condition_variable cv, cv_done;
+  std::function<void(int)> job;
+  int n_items = 0, busy = 0;
+  std::atomic<int> next{0};
+  uint64_t gen = 0;
+  bool stop = false;
+  HostPool() {
+    int n = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency())) - 1;
+    for (int i = 0; i < n; i++) th.emplace_back([this] { worker(); });
+  }
+  ~HostPool() {
+    { std::lock_guard<std::mutex> l(mu); stop = true; }
+    cv.notify_all();
+    for (auto& t : th) t.join();
+  }
+  void drain() { for (int i; (i = next.fetch_add(1)) < n_items;) job(i); }
+  void worker() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> l(mu);
+        cv.wait(l, [&] { return stop || gen != seen; });
+        if (stop) return;
+        seen = gen;
+        busy++;
+      }
+      drain();
+      { std::lock_guard<std::mutex> l(mu); busy--; }
+      cv_done.notify_one();
+    }
+  }
+  // run job(i) for i in [0, n) on the pool + the calling thread; returns when all items are done
+  void run(int n, std::function<void(int)> f) {
+    if (n <= 0) return;
+    {
+      std::unique_lock<std::mutex> l(mu);
+      cv_done.wait(l, [&] { return busy == 0; });          // a late waker of the previous run may still be draining
+      job = std::move(f); n_items = n; next = 0; gen++;
+    }
+    cv.notify_all();
+    drain();
+    std::unique_lock<std::mutex> l(mu);
+    cv_done.wait(l, [&] { return busy == 0 && next.load() >= n_items; });
+  }
+};
+static HostPool& host_pool() { static HostPool* p = new HostPool(); return *p; }   // leaked on purpose (no exit-time join)
+
 static void slot_plan(const icl_head_config& c, std::vector<int>& kinds /*index id or -1..-3*/) {
   // nn_utils/core.py:377-433.  -1 feats, -2 box, -3 bfeats
   kinds = {ICL_FIRST_I_BW, ICL_LAST_I_FW};
@@ -146,6 +207,11 @@ template <typename T> static cudaError_t dmalloc(T** p, size_t n) { return cudaM
 static int gemm(icl_model* m, cudaStream_t st, bool a_mn, bool b_mn, const GemmArgs& g, int force_mode = -1, int splits = 1) {
   int mode = force_mode >= 0 ? force_mode : m->cfg.gemm_mode;
   if (g.M <= 0 || g.N <= 0) return 0;
+  if (splits == 0) {     // auto: few output tiles + a long contraction -> split K so that about one wave of CTAs shares it
+    const int BN = g.N >= 512 ? 256 : 128, tiles = ((g.M + 127) / 128) * ((g.N + BN - 1) / BN), kb = (g.K + 31) / 32;
+    splits = (tiles >= 100 || kb < 16 || g.epi.mode != EPI_PLAIN || g.epi.bias || g.ldc != g.N) ? 1
+             : std::max(1, std::min(std::min(16, 148 / tiles), kb / 8));
+  }
   if (mode == ICL_GEMM_TCGEN05_TF32 && tcgen05_gemm_supported(g, a_mn, b_mn)) {
     if (splits > 1) {
       if (g.ldc != g.N) return fail("split-K gemm needs a dense C");
@@ -176,8 +242,8 @@ static GemmArgs mk_gemm(const float* A, long lda, const float* B, long ldb, floa
 
 // ----------------------------------------------------------------------------- persistent recurrent kernels: host side
 static int box_map(icl_model* m, const float* ptr, uint64_t cols, uint64_t rows, uint32_t box_c, uint32_t box_r, int swizzle,
-                   CUtensorMap* out) {
-  int r = m->tma.get(ptr, cols, rows, cols, box_c, box_r, swizzle, out);
+                   CUtensorMap* out, uint64_t ld = 0) {
+  int r = m->tma.get(ptr, cols, rows, ld ? ld : cols, box_c, box_r, swizzle, out);
   return r ? fail("cuTensorMapEncodeTiled failed (%d) for a {%u,%u} box over [%llu,%llu]", r, box_c, box_r,
                   (unsigned long long)rows, (unsigned long long)cols) : 0;
 }
@@ -192,12 +258,12 @@ static int rec_init(icl_model* m) {
   const int NONE = (int)CU_TENSOR_MAP_SWIZZLE_NONE, SW128 = (int)CU_TENSOR_MAP_SWIZZLE_128B;
   RecFwdMaps& f = m->rp_fmaps;
   for (int d = 0; d < 2; d++) {
-    CKI(box_map(m, m->Hp[d], H, RC, 32, 128, SW128, &f.a[d]));
+    CKI(box_map(m, m->Hp[d], H, RC, 32, 128, SW128, &f.a[d], m->ldx));
     CKI(box_map(m, m->Wp[d], (uint64_t)m->rp_nkb * 32, (uint64_t)m->rp_nsl * 4 * U, 32, 4 * U, SW128, &f.w[d]));
     CKI(box_map(m, m->Z[d], 4 * H, RC, U0, 32, NONE, &f.z0[d]));   CKI(box_map(m, m->Z[d], 4 * H, RC, U1, 32, NONE, &f.z1[d]));
     CKI(box_map(m, m->Cc[d], H, RC, U0, 32, NONE, &f.cc0[d]));     CKI(box_map(m, m->Cc[d], H, RC, U1, 32, NONE, &f.cc1[d]));
     CKI(box_map(m, m->Hx[d], H, RC, U0, 32, NONE, &f.hx0[d]));     CKI(box_map(m, m->Hx[d], H, RC, U1, 32, NONE, &f.hx1[d]));
-    CKI(box_map(m, m->Hp[d], H, RC, U0, 32, NONE, &f.hp0[d]));     CKI(box_map(m, m->Hp[d], H, RC, U1, 32, NONE, &f.hp1[d]));
+    CKI(box_map(m, m->Hp[d], H, RC, U0, 32, NONE, &f.hp0[d], m->ldx)); CKI(box_map(m, m->Hp[d], H, RC, U1, 32, NONE, &f.hp1[d], m->ldx));
   }
   return U == 20 ? rec_set_attr<20>() : rec_set_attr<16>();
 }
@@ -212,7 +278,7 @@ extern "C" void icl_destroy(icl_model* m) {
   auto F = [](void* p) { if (p) cudaFree(p); };
   F(m->P); F(m->G); F(m->M); F(m->V); F(m->Pr); F(m->xraw);
   for (int d = 0; d < 2; d++) {
-    F(m->xd[d]); F(m->Z[d]); F(m->Hx[d]); F(m->Hp[d]); F(m->Cc[d]); F(m->dHout[d]); F(m->dhrec[d]); F(m->dcc[d]); F(m->R[d]);
+    F(m->XH[d]); F(m->Z[d]); F(m->Hx[d]); F(m->Cc[d]); F(m->dHout[d]); F(m->dhrec[d]); F(m->dcc[d]); F(m->R[d]);
   }
   F(m->Wp[0]); F(m->Wp[1]); F(m->rp_flags); F(m->rp_trace);
   F(m->d_off); F(m->d_nact); F(m->d_rank); F(m->d_lens); F(m->d_tokseq); F(m->d_tokstart); F(m->d_partial); F(m->d_gnorm);
@@ -305,7 +371,8 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   // zero-filled once: rows past nact[k] of a step block only ever hold finite don't-care values
 #define ZALLOC(p, n) do { CKD(dmalloc(&(p), (n))); CKD(cudaMemset((p), 0, (n) * 4)); } while (0)
   for (int d = 0; d < 2; d++) {
-    ZALLOC(m->xd[d], RC * E); ZALLOC(m->Z[d], RC * 4 * H); ZALLOC(m->Hx[d], RC * H); ZALLOC(m->Hp[d], RC * H);
+    ZALLOC(m->XH[d], RC * (E + H)); m->xd[d] = m->XH[d]; m->Hp[d] = m->XH[d] + E; m->ldx = E + H;
+    ZALLOC(m->Z[d], RC * 4 * H); ZALLOC(m->Hx[d], RC * H);
     ZALLOC(m->Cc[d], RC * H); ZALLOC(m->dHout[d], RC * H); ZALLOC(m->dhrec[d], SP * H); ZALLOC(m->dcc[d], SP * H);
     ZALLOC(m->R[d], SP * 4 * H);
   }
@@ -446,13 +513,29 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
   // pack valid tokens (caption-major) into pinned memory as fp32
   size_t esz = b->sent_dtype == ICL_F64 ? 8 : 4;
   if (b->sent_dtype != ICL_F32 && b->sent_dtype != ICL_F64) return fail("icl_upload: sentences must be float32/float64");
-  for (int s = 0; s < S; s++) {
-    const char* src = (const char*)b->sentences + (b->sent_packed ? (size_t)tokstart[s] * E : (size_t)s * T * E) * esz;
-    to_f32(m->h_x + (size_t)tokstart[s] * E, src, b->sent_dtype, (size_t)lens[s] * E);
-    for (int t = 0; t < lens[s]; t++) tokseq[tokstart[s] + t] = s;
-  }
+  // pack + convert on several host threads, in chunks, so the H2D copy of chunk i overlaps the packing of chunk i+1
   cudaStream_t st = m->stream;
-  H2D(m->xraw, m->h_x, (size_t)ntok * E * 4, st);
+  {
+    const int n_chunks = ntok * (long)E * 4 > (4 << 20) ? 8 : 1;
+    int s0 = 0;
+    for (int c = 0; c < n_chunks; c++) {
+      const long tok_end = ntok * (c + 1) / n_chunks;
+      int s1 = s0;
+      while (s1 < S && (c == n_chunks - 1 || tokstart[s1] + lens[s1] <= tok_end)) s1++;
+      if (s1 == s0) continue;
+      const int per = 16, items = (s1 - s0 + per - 1) / per;           // 16 sequences per work item
+      host_pool().run(items, [&, s0, s1](int it) {
+        for (int s = s0 + it * per; s < std::min(s1, s0 + (it + 1) * per); s++) {
+          const char* src = (const char*)b->sentences + (b->sent_packed ? (size_t)tokstart[s] * E : (size_t)s * T * E) * esz;
+          to_f32(m->h_x + (size_t)tokstart[s] * E, src, b->sent_dtype, (size_t)lens[s] * E);
+          for (int t = 0; t < lens[s]; t++) tokseq[tokstart[s] + t] = s;
+        }
+      });
+      const long t0 = tokstart[s0], t1 = (long)tokstart[s1 - 1] + lens[s1 - 1];
+      if (t1 > t0) H2D(m->xraw + t0 * E, m->h_x + t0 * E, (size_t)(t1 - t0) * E * 4, st);
+      s0 = s1;
+    }
+  }
   H2D(m->d_lens, lens, (size_t)S * 4, st);
   H2D(m->d_rank, rank, (size_t)S * 4, st);
   H2D(m->d_tokstart, tokstart, (size_t)S * 4, st);
@@ -570,19 +653,19 @@ static int lstm_forward(icl_model* m, float keep_in, uint64_t seed, int training
   if (Ntok == 0) return 0;
   PH_BEGIN(m, PH_PREP);
   k_prep_x<<<(unsigned)((Ntok * 32 + 255) / 256), 256, 0, st>>>(m->xraw, m->d_tokseq, m->d_tokstart, mk_layout(m), (int)Ntok, E, m->T_cap,
-                                                               m->cfg.data_norm, keep_in, seed, m->seq_gid0, m->round_ops, m->xd[0], m->xd[1]);
+                                                               m->cfg.data_norm, keep_in, seed, m->seq_gid0, m->round_ops, m->xd[0], m->xd[1], m->ldx);
   LAUNCHED(m);
   for (int d = 0; d < 2; d++) {
-    k_zero_pad_rows<<<m->Tmax, 256, 0, st>>>(m->xd[d], mk_layout(m), E); LAUNCHED(m);
+    k_zero_pad_rows<<<m->Tmax, 256, 0, st>>>(m->XH[d], mk_layout(m), m->ldx); LAUNCHED(m);
     // h_prev of step 0 is the zero state: step 0's block of Hp stays zero (these are A rows of dW_hh)
-    CK(cudaMemsetAsync(m->Hp[d], 0, (size_t)m->off[1] * H * 4, st));
+    CK(cudaMemset2DAsync(m->Hp[d], (size_t)m->ldx * 4, 0, (size_t)H * 4, (size_t)m->off[1], st));
   }
   PH_END(m, PH_PREP);
   // K1: time-batched input projection  Z = Xd * W_ih + b   (W_ih = kernel rows [0,E)), both directions
   PH_BEGIN(m, PH_PROJ);
   for (int d = 0; d < 2; d++) {
     const float* K = wbase(m) + m->params[m->pK[d]].off;
-    GemmArgs g = mk_gemm(m->xd[d], E, K, 4 * H, m->Z[d], 4 * H, (int)NP, 4 * H, E);
+    GemmArgs g = mk_gemm(m->xd[d], m->ldx, K, 4 * H, m->Z[d], 4 * H, (int)NP, 4 * H, E);
     g.epi.bias = m->P + m->params[m->pBias[d]].off;
     CKI(gemm(m, st, false, true, g));
   }
@@ -603,13 +686,13 @@ static int lstm_forward(icl_model* m, float keep_in, uint64_t seed, int training
       int n = m->n_active[k], n_next = m->n_active[k + 1];
       long o = m->off[k];
       if (k > 0) {   // R = h_{k-1} * W_hh for the running rows
-        GemmArgs r = mk_gemm(m->Hp[d] + o * H, H, Whh, 4 * H, m->R[d], 4 * H, n, 4 * H, H);
+        GemmArgs r = mk_gemm(m->Hp[d] + o * m->ldx, m->ldx, Whh, 4 * H, m->R[d], 4 * H, n, 4 * H, H);
         CKI(gemm(m, sd, false, true, r));
       }
       long nthr = (long)n * (H / 4);
       k_lstm_cell_fwd<<<(unsigned)((nthr + 127) / 128), 128, 0, sd>>>(
           m->Z[d] + o * 4 * H, k > 0 ? m->R[d] : nullptr, k > 0 ? m->Cc[d] + (long)m->off[k - 1] * H : nullptr, m->Cc[d] + o * H,
-          m->Hx[d] + o * H, m->Hp[d] + (long)m->off[k + 1] * H, n, n_next, H, m->round_ops);
+          m->Hx[d] + o * H, m->Hp[d] + (long)m->off[k + 1] * m->ldx, m->ldx, n, n_next, H, m->round_ops);
       LAUNCHED(m);
     }
   }
@@ -678,7 +761,7 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
       const Param& pw = m->params[h.pW[k]];
       // dW = in^T * dz   (contraction over the batch: both operands MN-major)
       GemmArgs gw = mk_gemm(in, din, dz, dout, m->G + pw.off, dout, din, dout, B);
-      CKI(gemm(m, st, true, true, gw));
+      CKI(gemm(m, st, true, true, gw, -1, 0));
       CKI(colsum(m, st, dz, B, dout, dout, m->G + m->params[h.pB[k]].off));
       // d(in) = dz * W^T  (W [din,dout] row-major is K-major as the B operand)
       if (k > 0) {
@@ -729,7 +812,8 @@ static int lstm_backward(icl_model* m) {
       LAUNCHED(m);
       if (k > 0) {   // dh_{k-1} = dZ_k * W_hh^T for the running rows
         GemmArgs r = mk_gemm(m->Z[d] + o * 4 * H, 4 * H, Whh, 4 * H, m->dhrec[d], H, n, H, 4 * H);
-        CKI(gemm(m, sd, false, false, r));
+        int tiles = ((n + 127) / 128) * ((H + 127) / 128);
+        CKI(gemm(m, sd, false, false, r, -1, std::max(1, std::min(4, 74 / tiles))));   // split-K: both directions share the SMs
       }
     }
   }
@@ -740,13 +824,13 @@ static int lstm_backward(icl_model* m) {
   PH_END(m, PH_REC_BWD);
   // time-batched weight gradients: dW_ih = Xd^T dZ, dW_hh = Hprev^T dZ (contraction over all tokens, split-K), db = colsum(dZ)
   PH_BEGIN(m, PH_WGRAD);
-  int splits = (int)std::min<long>(16, std::max<long>(1, Ntok / 2048));
+  // 128x256 tiles: ceil((E+H)/128) x ceil(4H/256) of them; split-K so that ~one wave of 148 CTAs covers the contraction
+  int tiles = ((E + H + 127) / 128) * ((4 * H + 255) / 256);
+  int splits = (int)std::max<long>(1, std::min<long>(std::min<long>(16, 148 / std::max(1, tiles)), Ntok / 1024));
   for (int d = 0; d < 2; d++) {
     float* dK = m->G + m->params[m->pK[d]].off;
-    GemmArgs gi = mk_gemm(m->xd[d], E, m->Z[d], 4 * H, dK, 4 * H, E, 4 * H, (int)Ntok);
-    CKI(gemm(m, st, true, true, gi, -1, splits));
-    GemmArgs gh = mk_gemm(m->Hp[d], H, m->Z[d], 4 * H, dK + (size_t)E * 4 * H, 4 * H, H, 4 * H, (int)Ntok);
-    CKI(gemm(m, st, true, true, gh, -1, splits));
+    GemmArgs gk = mk_gemm(m->XH[d], m->ldx, m->Z[d], 4 * H, dK, 4 * H, E + H, 4 * H, (int)Ntok);   // dKernel = [Xd | Hprev]^T dZ
+    CKI(gemm(m, st, true, true, gk, -1, splits));
     float* db = m->G + m->params[m->pBias[d]].off;
     CK(cudaMemsetAsync(db, 0, (size_t)4 * H * 4, st));
     int rpb = 256;
