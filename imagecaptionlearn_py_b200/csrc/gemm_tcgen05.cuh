@@ -201,21 +201,40 @@ __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_consta
     const int q = warp & 3;                                            // a warp may only touch TMEM lanes [32*(warp%4), +32)
     float* stg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))) + q * (32 * 33);
     const int mrow0 = m0 + q * 32;
+    // everything the row loop needs lives in registers: kernel parameters sit in the constant bank and a dependent
+    // LDCU per use (once per element) made this loop ~10x slower than the MMA main loop
+    const Epilogue e = g.epi;
+    float* const Cp = g.C;
+    const long ldc = g.ldc;
+    const int M = g.M, N = g.N;
+    const bool splitk = gridDim.z > 1;
+    const int rows = min(32, M - mrow0);
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
-      if (n0 + c >= g.N) break;
+      if (n0 + c >= N) break;
       uint32_t r[32];
       tc_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + c, r);
 #pragma unroll
       for (int j = 0; j < 32; j++) stg[lane * 33 + j] = __uint_as_float(r[j]);
       __syncwarp();
       const int n = n0 + c + lane;
-      if (n < g.N) {
-        const int rows = min(32, g.M - mrow0);
-        for (int rr = 0; rr < rows; rr++) {
-          const long m = mrow0 + rr;
-          if (gridDim.z > 1) atomicAdd(g.C + m * g.ldc + n, stg[rr * 33 + lane]);       // C pre-zeroed by the host
-          else g.C[m * g.ldc + n] = epilogue_apply(g.epi, stg[rr * 33 + lane], m, n, g.N);
+      if (n < N && rows > 0) {
+        float* cp = Cp + (long)mrow0 * ldc + n;
+        if (splitk) {                                                  // C pre-zeroed by the host
+#pragma unroll 8
+          for (int rr = 0; rr < rows; rr++) atomicAdd(cp + (long)rr * ldc, stg[rr * 33 + lane]);
+        } else if (e.mode == EPI_PLAIN) {
+          const float bv = e.bias ? e.bias[n] : 0.0f;
+          if (e.round_out) {
+#pragma unroll 8
+            for (int rr = 0; rr < rows; rr++) cp[(long)rr * ldc] = tf32_rna(stg[rr * 33 + lane] + bv);
+          } else {
+#pragma unroll 8
+            for (int rr = 0; rr < rows; rr++) cp[(long)rr * ldc] = stg[rr * 33 + lane] + bv;
+          }
+        } else {
+#pragma unroll 4
+          for (int rr = 0; rr < rows; rr++) cp[(long)rr * ldc] = epilogue_apply(e, stg[rr * 33 + lane], mrow0 + rr, n, N);
         }
       }
       __syncwarp();
