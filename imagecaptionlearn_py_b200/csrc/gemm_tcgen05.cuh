@@ -209,6 +209,9 @@ __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_consta
     const int M = g.M, N = g.N;
     const bool splitk = gridDim.z > 1;
     const int rows = min(32, M - mrow0);
+    // float4 path: N, ldc (and the aux pitch) multiples of 4 and 16-byte aligned bases
+    const bool vec4 = (N & 3) == 0 && (ldc & 3) == 0 && ((uintptr_t)Cp & 15) == 0 && (!e.bias || ((uintptr_t)e.bias & 15) == 0) &&
+                      (e.mode != EPI_DACT || ((e.ldaux & 3) == 0 && ((uintptr_t)e.aux & 15) == 0));
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       if (n0 + c >= N) break;
@@ -232,9 +235,24 @@ __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_consta
 #pragma unroll 8
             for (int rr = 0; rr < rows; rr++) cp[(long)rr * ldc] = stg[rr * 33 + lane] + bv;
           }
-        } else {
+        } else if (!vec4) {
 #pragma unroll 4
           for (int rr = 0; rr < rows; rr++) cp[(long)rr * ldc] = epilogue_apply(e, stg[rr * 33 + lane], mrow0 + rr, n, N);
+        }
+      }
+      if (vec4 && !splitk && e.mode != EPI_PLAIN) {
+        // fused activation / dropout epilogues: lane = (row % 4, 4-column group) so one Philox call serves four outputs
+        const int cg = lane & 7, rsub = lane >> 3, n4 = n0 + c + cg * 4;
+        if (n4 < N) {
+#pragma unroll 2
+          for (int rb = 0; rb < 32; rb += 4) {
+            const int rr = rb + rsub;
+            if (rr < rows) {
+              const float* sp = stg + rr * 33 + cg * 4;
+              const float4 v = epilogue_apply4(e, make_float4(sp[0], sp[1], sp[2], sp[3]), mrow0 + rr, n4, N);
+              *reinterpret_cast<float4*>(Cp + (long)(mrow0 + rr) * ldc + n4) = v;
+            }
+          }
         }
       }
       __syncwarp();

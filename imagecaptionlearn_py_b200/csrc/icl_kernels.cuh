@@ -127,6 +127,38 @@ __device__ __forceinline__ float epilogue_apply(const Epilogue& e, float v, long
   return e.round_out ? tf32_rna(v) : v;
 }
 
+// four consecutive columns n..n+3 of row m at once: one Philox call yields the four dropout bits (N % 4 == 0, n % 4 == 0)
+__device__ __forceinline__ float4 epilogue_apply4(const Epilogue& e, float4 v, long m, int n, int N) {
+  float x[4] = {v.x, v.y, v.z, v.w};
+  if (e.bias) {
+    const float4 b = *reinterpret_cast<const float4*>(e.bias + n);
+    x[0] += b.x; x[1] += b.y; x[2] += b.z; x[3] += b.w;
+  }
+  float mk[4] = {1.f, 1.f, 1.f, 1.f};
+  const bool drop = e.mode != EPI_PLAIN && e.drop.keep < 1.0f;
+  if (drop) drop4(e.drop.seed, e.drop.stream, (uint64_t)((e.drop.row_gid0 + m) * N + n) >> 2, e.drop.keep, mk);
+  if (e.mode == EPI_BIAS_ACT_DROP) {
+    const float inv = drop ? 1.0f / e.drop.keep : 1.0f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { x[j] = act_fwd(x[j], e.act); if (drop) x[j] = x[j] / e.drop.keep * mk[j]; }
+    (void)inv;
+  } else if (e.mode == EPI_DACT) {
+    const float4 y4 = *reinterpret_cast<const float4*>(e.aux + m * e.ldaux + n);
+    const float y[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float a = y[j];
+      if (drop) { a = y[j] * e.drop.keep; x[j] = x[j] / e.drop.keep * mk[j]; }
+      x[j] *= act_bwd_from_out(a, e.act);
+    }
+  }
+  if (e.round_out) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) x[j] = tf32_rna(x[j]);
+  }
+  return make_float4(x[0], x[1], x[2], x[3]);
+}
+
 // ----------------------------------------------------------------------------- SIMT fp32 GEMM (validation mode and tiny / unaligned shapes)
 // C[M,N] = epi(A*B).  A(m,k) = A_KMAJOR ? A[m*lda+k] : A[k*lda+m];  B(k,n) = B_KMAJOR ? B[n*ldb+k] : B[k*ldb+n].
 struct GemmArgs {
@@ -367,10 +399,17 @@ __global__ void k_gather_concat(SlotTable st, const float* __restrict__ h_fw, co
       bool valid = w < L.lens[s];            // dynamic_rnn emits zeros past the sequence length
       const float* src = (d ? h_bw : h_fw) + (valid ? token_row(L, d, s, w) : 0) * H;
       uint64_t base = (uint64_t)((drop.row_gid0 + s) * Tcap + w) * (uint64_t)H;
-      for (int u = threadIdx.x; u < H; u += blockDim.x) {
-        float v = valid ? src[u] : 0.0f;
-        if (drop.keep < 1.0f) v = v / drop.keep * drop1(drop.seed, STREAM_OUT_FW + d, base + u, drop.keep);
-        o[st.col[sl] + u] = maybe_round(v, round_ops);
+      for (int u = threadIdx.x * 4; u < H; u += blockDim.x * 4) {        // H % 4 == 0; one Philox call per 4 units
+        float4 v4 = valid ? *reinterpret_cast<const float4*>(src + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float x[4] = {v4.x, v4.y, v4.z, v4.w};
+        if (drop.keep < 1.0f) {
+          float mk[4];
+          drop4(drop.seed, STREAM_OUT_FW + d, (base + u) >> 2, drop.keep, mk);
+#pragma unroll
+          for (int j = 0; j < 4; j++) x[j] = x[j] / drop.keep * mk[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) o[st.col[sl] + u + j] = maybe_round(x[j], round_ops);
       }
     }
   }
@@ -388,10 +427,15 @@ __global__ void k_scatter_spans(SlotTable st, const float* __restrict__ dbi, Ste
     if (w >= L.lens[s]) continue;
     float* dst = (d ? dh_bw : dh_fw) + token_row(L, d, s, w) * H;
     uint64_t base = (uint64_t)((drop.row_gid0 + s) * Tcap + w) * (uint64_t)H;
-    for (int u = threadIdx.x; u < H; u += blockDim.x) {
-      float v = g[st.col[sl] + u];
-      if (drop.keep < 1.0f) v = v / drop.keep * drop1(drop.seed, STREAM_OUT_FW + d, base + u, drop.keep);
-      atomicAdd(dst + u, v);
+    for (int u = threadIdx.x * 4; u < H; u += blockDim.x * 4) {
+      float mk[4] = {1.f, 1.f, 1.f, 1.f};
+      if (drop.keep < 1.0f) drop4(drop.seed, STREAM_OUT_FW + d, (base + u) >> 2, drop.keep, mk);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        float v = g[st.col[sl] + u + j];
+        if (drop.keep < 1.0f) v = v / drop.keep * mk[j];
+        if (v != 0.0f) atomicAdd(dst + u + j, v);
+      }
     }
   }
 }
@@ -449,22 +493,6 @@ __global__ void k_reduce_sum(const float* __restrict__ v, int n, float* out, flo
   if (threadIdx.x == 0) out[0] = (float)(mean_div > 0 ? sh[0] / mean_div : sh[0]);
 }
 
-// column sums of X[rows, N] -> out[N]  (bias gradients); grid.x covers N in 32-column strips, 256 threads = 8 row lanes
-__global__ void k_colsum(const float* __restrict__ X, long rows, int N, long ld, float* __restrict__ out) {
-  __shared__ float sh[8][33];
-  int c = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
-  float s = 0.0f;
-  if (c < N)
-    for (long r = rl; r < rows; r += 8) s += X[r * ld + c];
-  sh[rl][threadIdx.x & 31] = s;
-  __syncthreads();
-  if (rl == 0 && c < N) {
-    float t = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 8; i++) t += sh[i][threadIdx.x & 31];
-    out[c] = t;
-  }
-}
 // wide variant: many row-blocks accumulate with atomics (for the [Ntok,4H] LSTM dZ)
 __global__ void k_colsum_atomic(const float* __restrict__ X, long rows, int N, long ld, float* __restrict__ out, int rows_per_block) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;

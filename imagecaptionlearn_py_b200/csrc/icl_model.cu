@@ -738,7 +738,10 @@ static int heads_forward(icl_model* m, float keep, uint64_t seed) {
 }
 
 static int colsum(icl_model* m, cudaStream_t st, const float* X, long rows, int N, long ld, float* out) {
-  k_colsum<<<(N + 31) / 32, 256, 0, st>>>(X, rows, N, ld, out);
+  CK(cudaMemsetAsync(out, 0, (size_t)N * 4, st));
+  int rpb = 64;
+  dim3 grid((N + 127) / 128, (unsigned)((rows + rpb - 1) / rpb));
+  k_colsum_atomic<<<grid, 128, 0, st>>>(X, rows, N, ld, out, rpb);
   LAUNCHED(m);
   return 0;
 }
