@@ -150,8 +150,12 @@ def pad_ids_for_predict(ids, batch_size):
 
 
 def kv_str_to_dict(s):
-    """utils/string.py:132-145: 'k:v;k:v' -> dict."""
-    return dict(kv.split(":", 1) for kv in s.split(";"))
+    """utils/string.py:132-145: 'k:v;k:v' -> dict (the value is the SECOND ':'-field, anything after it is dropped)."""
+    out = {}
+    for kv in s.split(";"):
+        f = kv.split(":")
+        out[f[0]] = f[1]
+    return out
 
 
 def get_ij_pairs(mention_pairs):
