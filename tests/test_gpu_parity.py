@@ -255,3 +255,62 @@ def test_reference_style_predict_loop():
     assert set(scores) == set(ids)
     for v in scores.values():
         assert v.shape == (12,) and abs(v.sum() - 1) < 1e-5
+
+
+@pytest.mark.parametrize("mode,H", [("simt", 8), ("tf32", 20), ("tf32", 40)])
+def test_multitask_shared_encoder_matches_oracle(mode, H):
+    """icl_multitask_lstm.py:50-82,248-254 (intended semantics): one shared-weight encoder pass over the concatenation of
+    every task's sentences, one head per task under its own variable scope, joint loss = sum of the task losses.
+    H=20/40 also exercise the persistent forward kernel with one / two resident W_hh slices."""
+    from imagecaptionlearn_py_b200 import _cabi, core
+    E, T = 12, 9
+    specs = [dict(task="nonvis", S=11, F=4, widths=(8, 4)), dict(task="rel_cross", S=14, F=8, widths=(16,)),
+             dict(task="card", S=9, F=4, widths=(8,))]
+    probs = [tiny_problem(seed=40 + i, T=T, E=E, H=H, act="tanh", **s) for i, s in enumerate(specs)]
+    core.reset_default_graph()
+    with core.variable_scope("bidirectional_lstm"):
+        core.setup_bidirectional_lstm(H, False, n_embedding_width=E)
+    for p, s in zip(probs, specs):
+        with core.variable_scope(s["task"]):
+            core.setup_core_architecture(s["task"], "first_last_mention", p["B"], s["widths"][0], 0, False, "tanh", p["C"], p["F"])
+            core._graph.heads[-1]["widths"] = list(s["widths"])
+    core.add_train_op(core.get_collection("loss")[0], 1e-3, 1e-8, 5.0)
+    sess = core.Session(max_seq_len=T, gemm_mode=_mode(mode))
+    sess.ensure()
+    # oracle-side model: shared LSTM weights of problem 0, each head's weights under its scope, sentence indices offset
+    cfg = dict(H=H, data_norm=False, heads=[dict(p["cfg"]["heads"][0], scope=s["task"]) for p, s in zip(probs, specs)])
+    params = {k: v for k, v in probs[0]["params"].items() if "lstm" in k}
+    for p, s in zip(probs, specs):
+        for k, v in p["params"].items():
+            if "lstm" not in k:
+                params[s["task"] + "/" + k] = v
+    for k, v in params.items():
+        sess.set_tensor(k, v.reshape(1, -1) if v.ndim == 1 else v)
+    x = np.concatenate([p["x"] for p in probs], 0)
+    lens = np.concatenate([p["lens"] for p in probs], 0)
+    off, hbs = 0, []
+    for p in probs:
+        hb = {}
+        for k, v in p["batch"].items():
+            v = np.array(v)
+            if v.ndim == 2 and v.shape[1] == 3 and k.split("_")[0] in ("first", "last", "sent"):
+                v = v.copy()
+                v[:, 1] += off
+            hb[k] = v
+        hbs.append(hb)
+        off += p["S"]
+    res = sess.run(_cabi.OP_GRADS, [dict(p["batch"]) for p in probs], 1.0, 1.0, True)
+    f = O.model_forward(params, cfg, x, lens, hbs)
+    g = O.model_backward(params, cfg, f, hbs)
+    tol = TOL[mode]
+    assert abs(sum(r["loss"] for r in res) - f["loss"]) < tol["fwd"] * max(1.0, abs(f["loss"]))
+    for i, r in enumerate(res):
+        assert relerr(r["proba"], f["heads"][i]["proba"]) < tol["fwd"]
+    bad = {k: relerr(sess.get_tensor(k, 1).reshape(v.shape), v) for k, v in g.items()}
+    bad = {k: v for k, v in bad.items() if v > tol["grad"]}
+    assert not bad, bad
+    op = core.Op("loss", "")
+    joint = core.run_op(sess, op, [dict(p["batch"]) for p in probs], 1.0, 1.0, "first_last_mention",
+                        [s["task"] for s in specs], [s["task"] for s in specs], True)
+    assert abs(joint - f["loss"]) < tol["fwd"] * max(1.0, abs(f["loss"]))
+    sess.close()
