@@ -47,7 +47,7 @@ def make_batch(wl, seed):
     from imagecaptionlearn_py_b200 import data as nn_data
     from imagecaptionlearn_py_b200 import synth
     task, B = wl["task"], wl["B"]
-    n_img = {"affinity": max(4, B // 200), "rel_cross": max(4, B // 300)}.get(task, max(8, B // 10))
+    n_img = {"affinity": max(4, B // 200), "rel_cross": max(6, B // 60)}.get(task, max(8, B // 10))
     corpus = synth.make_corpus(n_img, seed=seed, with_boxes=(task == "affinity"))
     dd = synth.make_data_dict(corpus, task, F=wl["F"])
     dd["max_seq_len"] = T_PAD                      # the reference pads to the dataset-global maximum (data.py:375)
