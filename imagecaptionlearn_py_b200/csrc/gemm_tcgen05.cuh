@@ -154,6 +154,10 @@ __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_consta
   tc_fence_after();
   uint32_t tmem_acc;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot));
+  // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) overlaps the tail of the previous
+  // kernel in the stream; its results are visible after the wait.  No-ops when launched without the PDL attribute.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     if (lane == 0) {                                                   // ---- TMA producer
@@ -322,18 +326,27 @@ static bool tcgen05_gemm_supported(const GemmArgs& g, bool a_mn, bool b_mn) {
   return true;
 }
 
+// pdl: launch with programmatic stream serialization so the kernel's prologue overlaps its predecessor's tail
 template <bool A_MN, bool B_MN, int BN, int STAGES>
-static void tg_launch(dim3 grid, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g) {
-  k_gemm_tcgen05<A_MN, B_MN, BN, STAGES><<<grid, TG_THREADS, tg_smem(BN, STAGES), st>>>(ta, tb, g);
+static void tg_launch(dim3 grid, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, bool pdl) {
+  if (!pdl) { k_gemm_tcgen05<A_MN, B_MN, BN, STAGES><<<grid, TG_THREADS, tg_smem(BN, STAGES), st>>>(ta, tb, g); return; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(TG_THREADS); cfg.dynamicSmemBytes = tg_smem(BN, STAGES); cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, k_gemm_tcgen05<A_MN, B_MN, BN, STAGES>, ta, tb, g);
 }
 template <bool A_MN, bool B_MN>
-static void tg_dispatch(int BN, bool deep, dim3 grid, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g) {
-  if (BN == 256) { if (deep) tg_launch<A_MN, B_MN, 256, 4>(grid, st, ta, tb, g); else tg_launch<A_MN, B_MN, 256, 2>(grid, st, ta, tb, g); }
-  else { if (deep) tg_launch<A_MN, B_MN, 128, 6>(grid, st, ta, tb, g); else tg_launch<A_MN, B_MN, 128, 3>(grid, st, ta, tb, g); }
+static void tg_dispatch(int BN, bool deep, dim3 grid, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g,
+                        bool pdl) {
+  if (BN == 256) { if (deep) tg_launch<A_MN, B_MN, 256, 4>(grid, st, ta, tb, g, pdl); else tg_launch<A_MN, B_MN, 256, 2>(grid, st, ta, tb, g, pdl); }
+  else { if (deep) tg_launch<A_MN, B_MN, 128, 6>(grid, st, ta, tb, g, pdl); else tg_launch<A_MN, B_MN, 128, 3>(grid, st, ta, tb, g, pdl); }
 }
 
 // splits == 0: choose a split-K factor for few-tile / long-K problems (the caller must then accept a red.global epilogue)
-static int tcgen05_gemm_launch(TmaCache& cache, cudaStream_t st, bool a_mn, bool b_mn, const GemmArgs& g, int splits = 1) {
+static int tcgen05_gemm_launch(TmaCache& cache, cudaStream_t st, bool a_mn, bool b_mn, const GemmArgs& g, int splits = 1,
+                               bool pdl = false) {
   const int BN = g.N >= 512 ? 256 : 128;
   CUtensorMap ta, tb;
   int r;
@@ -346,10 +359,10 @@ static int tcgen05_gemm_launch(TmaCache& cache, cudaStream_t st, bool a_mn, bool
   if (r) return 2000 + r;
   dim3 grid((g.N + BN - 1) / BN, (g.M + TG_BM - 1) / TG_BM, splits);
   const bool deep = (long)grid.x * grid.y * grid.z <= 148;             // one CTA per SM anyway: spend the smem on pipeline depth
-  if (!a_mn && !b_mn) tg_dispatch<false, false>(BN, deep, grid, st, ta, tb, g);
-  else if (!a_mn && b_mn) tg_dispatch<false, true>(BN, deep, grid, st, ta, tb, g);
-  else if (a_mn && b_mn) tg_dispatch<true, true>(BN, deep, grid, st, ta, tb, g);
-  else tg_dispatch<true, false>(BN, deep, grid, st, ta, tb, g);
+  if (!a_mn && !b_mn) tg_dispatch<false, false>(BN, deep, grid, st, ta, tb, g, pdl);
+  else if (!a_mn && b_mn) tg_dispatch<false, true>(BN, deep, grid, st, ta, tb, g, pdl);
+  else if (a_mn && b_mn) tg_dispatch<true, true>(BN, deep, grid, st, ta, tb, g, pdl);
+  else tg_dispatch<true, false>(BN, deep, grid, st, ta, tb, g, pdl);
   return cudaGetLastError() == cudaSuccess ? 0 : 3000;
 }
 

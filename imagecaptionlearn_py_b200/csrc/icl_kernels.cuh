@@ -342,8 +342,10 @@ __global__ void k_lstm_cell_fwd(float* __restrict__ Zk, const float* __restrict_
 
 // Per-step backward cell: gates in Zk rows -> dZ (in place); dh = dHout + dhrec (rank-indexed carry), dc carry.
 __global__ void k_lstm_cell_bwd(float* __restrict__ Zk, const float* __restrict__ Ck, const float* __restrict__ Cprev,
-                                const float* __restrict__ dHk, const float* __restrict__ dhrec, float* __restrict__ dcc, int n, int H,
+                                const float* __restrict__ dHk, float* __restrict__ dhrec, float* __restrict__ dcc, int n, int H,
                                 int round_ops) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");               // PDL: the recurrent GEMM before us has fully completed
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   int q = H >> 2;
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long)n * q) return;
@@ -356,6 +358,7 @@ __global__ void k_lstm_cell_bwd(float* __restrict__ Zk, const float* __restrict_
   float4 cp4 = Cprev ? *reinterpret_cast<const float4*>(Cprev + (long)m * H + u) : make_float4(0, 0, 0, 0);
   float4 dh4 = *reinterpret_cast<const float4*>(dHk + (long)m * H + u);
   float4 dr4 = *reinterpret_cast<const float4*>(dhrec + (long)m * H + u);
+  *reinterpret_cast<float4*>(dhrec + (long)m * H + u) = make_float4(0.f, 0.f, 0.f, 0.f);   // ready for the next split-K accumulation
   float4 dc4 = *reinterpret_cast<const float4*>(dcc + (long)m * H + u);
   const float *si = &g4[0].x, *tj = &g4[1].x, *sf = &g4[2].x, *so = &g4[3].x, *c = &c4.x, *cp = &cp4.x, *dh = &dh4.x, *dr = &dr4.x,
               *dc = &dc4.x;

@@ -104,6 +104,10 @@ struct icl_model {
   unsigned* rp_flags = nullptr;
   long long* rp_trace = nullptr; int rp_trace_cta = 0;
   RecFwdMaps rp_fmaps;
+  RecBwdMaps rp_bmaps;
+  unsigned* rp_bar = nullptr;
+  bool rp_bwd_on = false;       // k_rec_bwd is correct but measured slower (0.84 ms) than the per-step path (0.56 ms): opt-in
+  int n_sms = 148;
   int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
   float last_ms = 0.f;
   TmaCache tma;
@@ -204,7 +208,9 @@ template <typename T> static cudaError_t dmalloc(T** p, size_t n) { return cudaM
 
 // ----------------------------------------------------------------------------- GEMM dispatch
 // splits > 1: split-K over gridDim.z with a red.global epilogue (plain epilogue only; C is zeroed here)
-static int gemm(icl_model* m, cudaStream_t st, bool a_mn, bool b_mn, const GemmArgs& g, int force_mode = -1, int splits = 1) {
+// prezeroed: C already holds zeros (split-K accumulates into it); pdl: programmatic dependent launch
+static int gemm(icl_model* m, cudaStream_t st, bool a_mn, bool b_mn, const GemmArgs& g, int force_mode = -1, int splits = 1,
+                bool prezeroed = false, bool pdl = false) {
   int mode = force_mode >= 0 ? force_mode : m->cfg.gemm_mode;
   if (g.M <= 0 || g.N <= 0) return 0;
   if (splits == 0) {     // auto: few output tiles + a long contraction -> split K so that about one wave of CTAs shares it
@@ -215,9 +221,9 @@ static int gemm(icl_model* m, cudaStream_t st, bool a_mn, bool b_mn, const GemmA
   if (mode == ICL_GEMM_TCGEN05_TF32 && tcgen05_gemm_supported(g, a_mn, b_mn)) {
     if (splits > 1) {
       if (g.ldc != g.N) return fail("split-K gemm needs a dense C");
-      CK(cudaMemsetAsync(g.C, 0, (size_t)g.M * g.N * 4, st));
+      if (!prezeroed) CK(cudaMemsetAsync(g.C, 0, (size_t)g.M * g.N * 4, st));
     }
-    int r = tcgen05_gemm_launch(m->tma, st, a_mn, b_mn, g, splits);
+    int r = tcgen05_gemm_launch(m->tma, st, a_mn, b_mn, g, splits, pdl);
     if (r != 0) return fail("tcgen05 gemm launch failed (%d): %s", r, cudaGetErrorString(cudaGetLastError()));
     m->launches++;
     return 0;
@@ -265,6 +271,13 @@ static int rec_init(icl_model* m) {
     CKI(box_map(m, m->Hx[d], H, RC, U0, 32, NONE, &f.hx0[d]));     CKI(box_map(m, m->Hx[d], H, RC, U1, 32, NONE, &f.hx1[d]));
     CKI(box_map(m, m->Hp[d], H, RC, U0, 32, NONE, &f.hp0[d], m->ldx)); CKI(box_map(m, m->Hp[d], H, RC, U1, 32, NONE, &f.hp1[d], m->ldx));
   }
+  for (int d = 0; d < 2; d++) {
+    CKI(box_map(m, m->Z[d], 4 * H, RC, 32, 128, SW128, &m->rp_bmaps.za[d]));
+    const float* Whh = m->Pr + m->params[m->pK[d]].off + (size_t)m->E * 4 * H;
+    CKI(box_map(m, Whh, 4 * H, H, 32, 128, SW128, &m->rp_bmaps.wb[d]));
+  }
+  if (cudaFuncSetAttribute(k_rec_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM) != cudaSuccess)
+    return fail("cudaFuncSetAttribute(k_rec_bwd) failed");
   return U == 20 ? rec_set_attr<20>() : rec_set_attr<16>();
 }
 
@@ -280,7 +293,7 @@ extern "C" void icl_destroy(icl_model* m) {
   for (int d = 0; d < 2; d++) {
     F(m->XH[d]); F(m->Z[d]); F(m->Hx[d]); F(m->Cc[d]); F(m->dHout[d]); F(m->dhrec[d]); F(m->dcc[d]); F(m->R[d]);
   }
-  F(m->Wp[0]); F(m->Wp[1]); F(m->rp_flags); F(m->rp_trace);
+  F(m->Wp[0]); F(m->Wp[1]); F(m->rp_flags); F(m->rp_trace); F(m->rp_bar);
   F(m->d_off); F(m->d_nact); F(m->d_rank); F(m->d_lens); F(m->d_tokseq); F(m->d_tokstart); F(m->d_partial); F(m->d_gnorm);
   if (m->h_x) cudaFreeHost(m->h_x);
   if (m->h_ints) cudaFreeHost(m->h_ints);
@@ -380,12 +393,15 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   m->rp_nkb = (H + 31) / 32;
   if (m->rp_U && (m->rp_nkb > 10 || m->T_cap > RP_MAXT)) m->rp_U = 0;
   if (const char* e = getenv("ICL_PERSISTENT")) m->rp_on = atoi(e) != 0;
+  if (const char* e = getenv("ICL_PERSISTENT_BWD")) m->rp_bwd_on = atoi(e) != 0;
+  m->n_sms = prop.multiProcessorCount;
   if (m->cfg.gemm_mode != ICL_GEMM_TCGEN05_TF32) m->rp_U = 0;      // the fp32 validation mode keeps the per-step SIMT path
   if (m->rp_U) {
     m->rp_nsl = H / m->rp_U;
     m->rp_max_tiles = (int)(SP / 128);
     for (int d = 0; d < 2; d++) ZALLOC(m->Wp[d], (size_t)m->rp_nsl * 4 * m->rp_U * m->rp_nkb * 32);
     CKD(dmalloc(&m->rp_flags, (size_t)2 * m->rp_max_tiles));
+    CKD(dmalloc(&m->rp_bar, 4));
   }
 #undef ZALLOC
   CKD(dmalloc(&m->d_off, m->T_cap + 1)); CKD(dmalloc(&m->d_nact, m->T_cap + 1)); CKD(dmalloc(&m->d_rank, m->S_cap));
@@ -797,6 +813,24 @@ static int lstm_backward(icl_model* m) {
   PH_BEGIN(m, PH_REC_BWD);
   CK(cudaEventRecord(m->ev_fork, st));
   CK(cudaStreamWaitEvent(m->aux, m->ev_fork, 0));
+  if (m->rp_U != 0 && m->rp_on && m->rp_bwd_on && m->Tmax <= RP_MAXT) {
+    // K3: every BPTT step of both directions in one cooperative launch (lstm_persistent.cuh)
+    for (int d = 0; d < 2; d++) {
+      CK(cudaMemsetAsync(m->dhrec[d], 0, (size_t)S * H * 4, st));
+      CK(cudaMemsetAsync(m->dcc[d], 0, (size_t)S * H * 4, st));
+    }
+    CK(cudaMemsetAsync(m->rp_bar, 0, 4, st));
+    RecBwdArgs a;
+    a.off = m->d_off; a.nact = m->d_nact; a.Tmax = m->Tmax; a.H = H; a.round_ops = m->round_ops; a.bar = m->rp_bar;
+    for (int d = 0; d < 2; d++) { a.Z[d] = m->Z[d]; a.Cc[d] = m->Cc[d]; a.dHout[d] = m->dHout[d]; a.dhrec[d] = m->dhrec[d]; a.dcc[d] = m->dcc[d]; }
+    void* args[] = {(void*)&m->rp_bmaps, (void*)&a};
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_rec_bwd, dim3(m->n_sms), dim3(RB_THREADS), args, RB_SMEM, st);
+    if (e != cudaSuccess) return fail("k_rec_bwd launch failed: %s", cudaGetErrorString(e));
+    m->launches++;
+    for (int d = 0; d < 2; d++) { k_zero_pad_rows<<<m->Tmax, 256, 0, st>>>(m->Z[d], mk_layout(m), 4 * H); LAUNCHED(m); }
+    PH_END(m, PH_REC_BWD);
+    goto wgrad;
+  }
   for (int d = 0; d < 2; d++) {
     cudaStream_t sd = d ? m->aux : st;
     CK(cudaMemsetAsync(m->dhrec[d], 0, (size_t)S * H * 4, sd));
@@ -809,14 +843,23 @@ static int lstm_backward(icl_model* m) {
       int n = m->n_active[k];
       long o = m->off[k];
       long nthr = (long)n * (H / 4);
-      k_lstm_cell_bwd<<<(unsigned)((nthr + 127) / 128), 128, 0, sd>>>(m->Z[d] + o * 4 * H, m->Cc[d] + o * H,
-                                                                     k > 0 ? m->Cc[d] + (long)m->off[k - 1] * H : nullptr,
-                                                                     m->dHout[d] + o * H, m->dhrec[d], m->dcc[d], n, H, m->round_ops);
-      LAUNCHED(m);
+      {   // cell backward of step k; launched with PDL so it is resident before the GEMM of step k+1 drains
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((nthr + 127) / 128)); cfg.blockDim = dim3(128); cfg.stream = sd;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        float* zk = m->Z[d] + o * 4 * H; const float* ck = m->Cc[d] + o * H;
+        const float* cprev = k > 0 ? m->Cc[d] + (long)m->off[k - 1] * H : nullptr;
+        const float* dhk = m->dHout[d] + o * H;
+        CK(cudaLaunchKernelEx(&cfg, k_lstm_cell_bwd, zk, ck, cprev, dhk, m->dhrec[d], m->dcc[d], n, H, m->round_ops));
+        LAUNCHED(m);
+      }
       if (k > 0) {   // dh_{k-1} = dZ_k * W_hh^T for the running rows
         GemmArgs r = mk_gemm(m->Z[d] + o * 4 * H, 4 * H, Whh, 4 * H, m->dhrec[d], H, n, H, 4 * H);
         int tiles = ((n + 127) / 128) * ((H + 127) / 128);
-        CKI(gemm(m, sd, false, false, r, -1, std::max(1, std::min(4, 74 / tiles))));   // split-K: both directions share the SMs
+        // split-K (about one wave per direction) accumulating into dhrec, which the cell kernel left zeroed
+        CKI(gemm(m, sd, false, false, r, -1, std::max(1, std::min(4, 148 / tiles)), true, m->cfg.gemm_mode == ICL_GEMM_TCGEN05_TF32));
       }
     }
   }
@@ -825,6 +868,7 @@ static int lstm_backward(icl_model* m) {
   // pad rows of dZ must be exactly zero for the time-batched weight-gradient GEMMs (they still hold gates / Zx)
   for (int d = 0; d < 2; d++) { k_zero_pad_rows<<<m->Tmax, 256, 0, st>>>(m->Z[d], mk_layout(m), 4 * H); LAUNCHED(m); }
   PH_END(m, PH_REC_BWD);
+wgrad:
   // time-batched weight gradients: dW_ih = Xd^T dZ, dW_hh = Hprev^T dZ (contraction over all tokens, split-K), db = colsum(dZ)
   PH_BEGIN(m, PH_WGRAD);
   // 128x256 tiles: ceil((E+H)/128) x ceil(4H/256) of them; split-K so that ~one wave of 148 CTAs covers the contraction

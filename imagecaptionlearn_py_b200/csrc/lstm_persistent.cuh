@@ -68,7 +68,10 @@ template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
-__device__ __forceinline__ void flag_release_add(unsigned* p) { asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory"); }
+// Publication of a tile.  The data was written by TMA bulk stores whose completion the caller has already waited for
+// (cp.async.bulk.wait_group), i.e. it is performed at L2 before the counter moves; a .release here would additionally drain
+// every bulk store of the thread that is still in flight (measured 1.3 us per tile), so the counter uses a relaxed red.
+__device__ __forceinline__ void flag_release_add(unsigned* p) { asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory"); }
 // bounded spin on a publication counter: a protocol bug traps instead of hanging the GPU
 __device__ __forceinline__ void flag_wait(const unsigned* p, unsigned target) {
   const long long t0 = clock64();
@@ -339,6 +342,204 @@ __global__ void __launch_bounds__(RP_FWD_THREADS, 1) k_rec_fwd(const __grid_cons
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+// =====================================================================================================================
+// Backward recurrence (k_rec_bwd, "K3"): ONE cooperative launch runs every BPTT step of both directions.
+//
+// Per step k (descending) the whole grid alternates two phases separated by a software grid barrier:
+//   E  all threads: backward of the LSTM cell for every running row of both directions (float4, coalesced along the hidden
+//      units): dh = dHout_k + dh_rec, gates -> dZ_k in place (TF32-rounded), dc carry; dh_rec is left zeroed;
+//   G  dh_rec[0:n_k) = dZ_k W_hh^T as 128x128 tcgen05 tiles (TMA -> 6-stage ring -> UMMA kind::tf32 -> TMEM -> red.global),
+//      tasks (direction, row tile, unit tile, K split) dealt round-robin to the CTAs; W_hh^T streams from L2 (a [128 x 4H]
+//      slice is 614 KB, it cannot stay resident next to the operand ring).
+// dZ_k is written by generic stores and read by TMA in the next phase: writers fence.proxy.async before the barrier.
+// =====================================================================================================================
+constexpr int RB_THREADS = 256, RB_STAGES = 6;
+constexpr int RB_SMEM = RB_STAGES * 2 * 16384 + 4 * 32 * 33 * 4 + 256 + 1024;
+
+struct RecBwdMaps { CUtensorMap za[2], wb[2]; };   // A: Z[d] {4H, rows}; B: W_hh {4H, H} (rows = hidden units, K-major); boxes {32, 128}
+struct RecBwdArgs {
+  const int* off; const int* nact;
+  int Tmax, H, round_ops;
+  float* Z[2]; const float* Cc[2]; const float* dHout[2]; float* dhrec[2]; float* dcc[2];
+  unsigned* bar;                                    // grid-barrier counter, zeroed before the launch
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    const long long t0 = clock64();
+    for (;;) {                                        // tight poll: the barrier is on the critical path of every step
+      unsigned v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      if (v >= target) break;
+      if (clock64() - t0 > 4000000000LL) __trap();
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(RB_THREADS, 1) k_rec_bwd(const __grid_constant__ RecBwdMaps maps, const RecBwdArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ int s_off[RP_MAXT + 2], s_n[RP_MAXT + 2];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sA = base, sB = base + RB_STAGES * 16384, sStg = sB + RB_STAGES * 16384;
+  const uint32_t bars = sStg + 4 * 32 * 33 * 4;
+  const uint32_t full0 = bars, empty0 = bars + 8 * RB_STAGES, tfull = bars + 16 * RB_STAGES, tempty = tfull + 8, tmem_slot = tempty + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = g.H, Tmax = g.Tmax, q4 = H >> 2;
+  const int total_kb = (4 * H + 31) / 32, Nt = (H + 127) / 128;
+
+  for (int i = threadIdx.x; i <= Tmax; i += blockDim.x) { s_off[i] = g.off[i]; s_n[i] = g.nact[i]; }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < RB_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(tfull, 1); mbar_init(tempty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(tmem_slot) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
+
+  uint32_t it = 0, acc = 0;                            // running k-block / accumulator counters (barrier parities)
+  unsigned bar_target = 0;
+  const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (long)gridDim.x * blockDim.x;
+  for (int k = Tmax - 1; k >= 0; k--) {
+    const int n = s_n[k];
+    const long o = s_off[k], op = k > 0 ? s_off[k - 1] : 0;
+    // ---------------------------------------------------------------- E: cell backward, both directions
+    const long per_dir = (long)n * q4;
+    for (long idx = gtid; idx < 2 * per_dir; idx += gthreads) {
+      const int d = idx >= per_dir;
+      const long r = idx - (d ? per_dir : 0);
+      const int m = (int)(r / q4), u = (int)(r % q4) * 4;
+      float* z = g.Z[d] + (o + m) * 4 * H + u;
+      float4 g4[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) g4[a] = *reinterpret_cast<float4*>(z + a * H);
+      const float4 c4 = *reinterpret_cast<const float4*>(g.Cc[d] + (o + m) * H + u);
+      const float4 cp4 = k > 0 ? *reinterpret_cast<const float4*>(g.Cc[d] + (op + m) * H + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 dh4 = *reinterpret_cast<const float4*>(g.dHout[d] + (o + m) * H + u);
+      float* drp = g.dhrec[d] + (long)m * H + u;
+      const float4 dr4 = *reinterpret_cast<float4*>(drp);
+      *reinterpret_cast<float4*>(drp) = make_float4(0.f, 0.f, 0.f, 0.f);
+      float* dcp = g.dcc[d] + (long)m * H + u;
+      const float4 dc4 = *reinterpret_cast<float4*>(dcp);
+      const float *si = &g4[0].x, *tj = &g4[1].x, *sf = &g4[2].x, *so = &g4[3].x, *c = &c4.x, *cp = &cp4.x, *dh = &dh4.x, *dr = &dr4.x,
+                  *dc = &dc4.x;
+      float di[4], dj[4], df[4], dgo[4], dcn[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const CellGrad cg = lstm_cell_bwd(si[j], tj[j], sf[j], so[j], c[j], cp[j], dh[j] + dr[j], dc[j]);
+        di[j] = maybe_round(cg.di, g.round_ops); dj[j] = maybe_round(cg.dj, g.round_ops); df[j] = maybe_round(cg.df, g.round_ops);
+        dgo[j] = maybe_round(cg.dg_o, g.round_ops); dcn[j] = cg.dc_prev;
+      }
+      *reinterpret_cast<float4*>(z) = make_float4(di[0], di[1], di[2], di[3]);
+      *reinterpret_cast<float4*>(z + H) = make_float4(dj[0], dj[1], dj[2], dj[3]);
+      *reinterpret_cast<float4*>(z + 2 * H) = make_float4(df[0], df[1], df[2], df[3]);
+      *reinterpret_cast<float4*>(z + 3 * H) = make_float4(dgo[0], dgo[1], dgo[2], dgo[3]);
+      *reinterpret_cast<float4*>(dcp) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
+    }
+    if (k == 0) break;
+    fence_async_all();                                  // dZ_k (generic stores) -> visible to the TMA reads of phase G
+    bar_target += gridDim.x;
+    grid_barrier(g.bar, bar_target);
+    // ---------------------------------------------------------------- G: dh_rec = dZ_k W_hh^T
+    const int Mt = (n + 127) / 128;
+    int sp = (int)gridDim.x / max(1, 2 * Mt * Nt);
+    sp = max(1, min(min(sp, 4), total_kb / 4));
+    const int kb_per = (total_kb + sp - 1) / sp;
+    const int tasks = 2 * Mt * Nt * sp;
+    if (warp == 0) {
+      if (lane == 0) {
+        fence_async_all();
+        for (int t = blockIdx.x; t < tasks; t += gridDim.x) {
+          const int s = t % sp, nt = (t / sp) % Nt, mt = (t / (sp * Nt)) % Mt, d = t / (sp * Nt * Mt);
+          const int kb0 = s * kb_per, nkb = min(kb_per, total_kb - kb0);
+          for (int kb = 0; kb < nkb; kb++, it++) {
+            const uint32_t st = it % RB_STAGES;
+            mbar_wait(empty0 + 8 * st, ((it / RB_STAGES) & 1) ^ 1);
+            mbar_expect_tx(full0 + 8 * st, 32768);
+            tma_load_2d(sA + st * 16384, &maps.za[d], (kb0 + kb) * 32, (int)o + mt * 128, full0 + 8 * st);
+            tma_load_2d(sB + st * 16384, &maps.wb[d], (kb0 + kb) * 32, nt * 128, full0 + 8 * st);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc(2, false, false, 128, 128);
+        for (int t = blockIdx.x; t < tasks; t += gridDim.x, acc++) {
+          const int s = t % sp;
+          const int kb0 = s * kb_per, nkb = min(kb_per, total_kb - kb0);
+          mbar_wait(tempty, (acc & 1) ^ 1);
+          tc_fence_after();
+          for (int kb = 0; kb < nkb; kb++, it++) {
+            const uint32_t st = it % RB_STAGES;
+            mbar_wait(full0 + 8 * st, (it / RB_STAGES) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++)
+              tc_mma_tf32(tmem, make_smem_desc(sA + st * 16384 + kk * 32, 16, 1024), make_smem_desc(sB + st * 16384 + kk * 32, 16, 1024),
+                          idesc, (kb | kk) != 0);
+            tc_commit(empty0 + 8 * st);
+          }
+          tc_commit(tfull);
+        }
+      }
+    } else if (warp < 6) {
+      const int q = warp & 3;
+      float* stg = reinterpret_cast<float*>(gbase + (sStg - base)) + q * (32 * 33);
+      for (int t = blockIdx.x; t < tasks; t += gridDim.x, acc++) {
+        const int nt = (t / sp) % Nt, mt = (t / (sp * Nt)) % Mt, d = t / (sp * Nt * Mt);
+        mbar_wait(tfull, acc & 1);
+        tc_fence_after();
+        const int mrow0 = mt * 128 + q * 32, rows = min(32, n - mrow0);
+        float* out = g.dhrec[d];
+#pragma unroll 1
+        for (int c = 0; c < 128; c += 32) {
+          const int ncol = nt * 128 + c + lane;
+          if (nt * 128 + c >= H) break;
+          uint32_t r[32];
+          tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + c, r);
+#pragma unroll
+          for (int j = 0; j < 32; j++) stg[lane * 33 + j] = __uint_as_float(r[j]);
+          __syncwarp();
+          if (ncol < H) {
+            float* cp = out + (long)mrow0 * H + ncol;
+            if (sp > 1) {
+#pragma unroll 8
+              for (int rr = 0; rr < rows; rr++) atomicAdd(cp + (long)rr * H, stg[rr * 33 + lane]);
+            } else {
+#pragma unroll 8
+              for (int rr = 0; rr < rows; rr++) cp[(long)rr * H] = stg[rr * 33 + lane];
+            }
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty);
+      }
+    }
+    bar_target += gridDim.x;
+    grid_barrier(g.bar, bar_target);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
   }
 }
 

@@ -314,3 +314,20 @@ def test_multitask_shared_encoder_matches_oracle(mode, H):
                         [s["task"] for s in specs], [s["task"] for s in specs], True)
     assert abs(joint - f["loss"]) < tol["fwd"] * max(1.0, abs(f["loss"]))
     sess.close()
+
+
+def test_persistent_backward_kernel_matches_per_step_path(monkeypatch):
+    """k_rec_bwd (opt-in: ICL_PERSISTENT_BWD=1; one cooperative launch for the whole BPTT recurrence) against the default
+    per-step path on the same batch: same gradients up to split-K summation order."""
+    from imagecaptionlearn_py_b200 import _cabi
+    p = tiny_problem(seed=27, dropout=True, **CASES[5])
+    grads = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("ICL_PERSISTENT_BWD", flag)
+        core, sess = make_session(p, "tf32")
+        sess.base_seed, sess.run_counter = 77, 0
+        sess.run(_cabi.OP_GRADS, [dict(p["batch"])], p["keep_in"], p["keep"], True)
+        grads[flag] = {k: sess.get_tensor(k, 1) for k in p["params"]}
+        sess.close()
+    for k in grads["0"]:
+        assert relerr(grads["1"][k], grads["0"][k]) < 1e-5, k
