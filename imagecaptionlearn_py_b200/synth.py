@@ -129,3 +129,61 @@ def example_ids(dd, task):
         loaded = set(dd["mention_indices"].keys())
         return [k for k in dd["labels"].keys() if k.split("|")[0] in loaded]     # icl_affinity_lstm.py:59-74
     return list(dd["mention_indices"].keys())
+
+
+def write_dataset(corpus, data_dir, data_root, task, F=None, seed=7):
+    """Emit the synthetic corpus in the reference's file formats and directory scheme (icl_core_lstm.py:333-345,
+    icl_relation_lstm.py:403-430, icl_affinity_lstm.py:412-433) so the drop-in CLIs run on it unmodified:
+    raw/<root>_captions.txt, raw/<root>_mentions_<task>.txt, feats/<root>_<task>_neural.feats + _meta.json
+    (relations: raw/<root>_mentionPairs_<rel>.txt, feats/<root>_relation_neural_<rel>.feats, raw/<root>_mentionPair_labels.txt),
+    raw/<root>_embeddings.npz (stand-in for the word2vec binary), and for affinity raw/<root>_affinity_labels.txt +
+    feats/<data>_boxes/<split>/<img>.feats."""
+    import json
+    import os
+    dd = make_data_dict(corpus, task, F=F)
+    F = dd["n_mention_feats"]
+    for sub in ("raw", "feats", "scores"):
+        os.makedirs(os.path.join(data_dir, sub), exist_ok=True)
+    vocab = ["w%d" % i for i in range(len(corpus["table"]) - 1)] + ["UNK"]
+    np.savez(os.path.join(data_dir, "raw", data_root + "_embeddings.npz"), vocab=np.array(vocab), matrix=corpus["table"])
+    with open(os.path.join(data_dir, "raw", data_root + "_captions.txt"), "w") as f:
+        for cap_id, wid in corpus["word_ids"].items():
+            f.write("%s\t%s\n" % (cap_id, " ".join("w%d" % w for w in wid)))
+    tag = task if not task.startswith("rel") else task.replace("rel_", "")
+    ment_name = {"nonvis": "_mentions_nonvis.txt", "card": "_mentions_card.txt", "affinity": "_mentions_affinity.txt"}.get(
+        task, "_mentionPairs_%s.txt" % tag)
+    with open(os.path.join(data_dir, "raw", data_root + ment_name), "w") as f:
+        for mid, idx in dd["mention_indices"].items():
+            lab = int(np.argmax(dd["labels"][mid])) if mid in dd["labels"] else 0
+            f.write("%s\t%s\t%d\n" % (mid, ",".join(str(i) for i in idx), lab))
+    froot = "%s_%s_neural" % (data_root, task) if not task.startswith("rel") else "%s_relation_neural_%s" % (data_root, tag)
+    with open(os.path.join(data_dir, "feats", froot + ".feats"), "w") as f:
+        for mid, v in dd["mention_features"].items():
+            nz = np.nonzero(v)[0]
+            f.write("0 %s # %s\n" % (" ".join("%d:%g" % (k, v[k]) for k in nz), mid))
+    json.dump({"max_idx": F - 1}, open(os.path.join(data_dir, "feats", froot + "_meta.json"), "w"))
+    if task == "affinity":
+        with open(os.path.join(data_dir, "raw", data_root + "_affinity_labels.txt"), "w") as f:
+            for k, v in dd["labels"].items():
+                f.write("%s\t%d\n" % (k, int(np.argmax(v))))
+        data, split = data_root.rsplit("_", 1)
+        bdir = os.path.join(data_dir, "feats", data + "_boxes", split)
+        os.makedirs(bdir, exist_ok=True)
+        by_img = {}
+        for bid, v in corpus["boxes"].items():
+            by_img.setdefault(bid.split(";")[0], []).append((bid, v))
+        for img, rows in by_img.items():
+            with open(os.path.join(bdir, img.replace(".jpg", ".feats")), "w") as f:
+                for bid, v in rows:
+                    nz = np.nonzero(v)[0]
+                    f.write("0 %s # %s\n" % (" ".join("%d:%g" % (k + 1, v[k]) for k in nz), bid))
+    if task.startswith("rel"):
+        names = ["null", "coref", "subset_ij", "subset_ji"]
+        with open(os.path.join(data_dir, "raw", data_root + "_mentionPair_labels.txt"), "a") as f:
+            for pid in dd["mention_indices"]:
+                d = dict(kv.split(":")[:2] for kv in pid.split(";"))
+                if (d["caption_1"], int(d["mention_1"])) < (d["caption_2"], int(d["mention_2"])):
+                    ji = "doc:%s;caption_1:%s;mention_1:%s;caption_2:%s;mention_2:%s" % (
+                        d["doc"], d["caption_2"], d["mention_2"], d["caption_1"], d["mention_1"])
+                    f.write("%s %s %s\n" % (pid, ji, names[int(np.argmax(dd["labels"][pid]))]))
+    return dd

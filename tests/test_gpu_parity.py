@@ -318,7 +318,8 @@ def test_multitask_shared_encoder_matches_oracle(mode, H):
 
 def test_persistent_backward_kernel_matches_per_step_path(monkeypatch):
     """k_rec_bwd (opt-in: ICL_PERSISTENT_BWD=1; one cooperative launch for the whole BPTT recurrence) against the default
-    per-step path on the same batch: same gradients up to split-K summation order."""
+    per-step path on the same batch: same gradients up to split-K summation order (a different fp32 summation order can
+    move a dZ element across a TF32 rounding boundary, 2^-11 relative, before it enters the next step: 5e-4)."""
     from imagecaptionlearn_py_b200 import _cabi
     p = tiny_problem(seed=27, dropout=True, **CASES[5])
     grads = {}
@@ -330,4 +331,4 @@ def test_persistent_backward_kernel_matches_per_step_path(monkeypatch):
         grads[flag] = {k: sess.get_tensor(k, 1) for k in p["params"]}
         sess.close()
     for k in grads["0"]:
-        assert relerr(grads["1"][k], grads["0"][k]) < 1e-5, k
+        assert relerr(grads["1"][k], grads["0"][k]) < 5e-4, k
