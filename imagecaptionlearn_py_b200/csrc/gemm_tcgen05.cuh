@@ -7,7 +7,7 @@
 // time-batched weight-gradient GEMMs (contraction over tokens) are (MN, MN).
 //
 // One 128 x BN output tile per CTA (BN = 128 or 256), BK = 32 fp32 (one 128-byte swizzle row), STAGES-deep mbarrier
-// pipeline.  Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2-5 = epilogue.
+// pipeline.  Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2-9 = epilogue.
 // Configurations (picked per call by tcgen05_gemm_launch):
 //   <128,3>  97 KB smem, two CTAs per SM: many-tile GEMMs, one CTA's epilogue overlaps the other's main loop
 //   <128,6> 193 KB smem, one CTA per SM: few tiles with a long K loop -- latency-bound, so a deeper ring
@@ -30,7 +30,7 @@ namespace icl {
 
 constexpr int TG_BM = 128, TG_BK = 32;
 constexpr int TG_A_BYTES = TG_BM * TG_BK * 4;                          // 16 KB per A stage
-constexpr int TG_THREADS = 192;
+constexpr int TG_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter, alternating 32-column chunks)
 constexpr int tg_smem(int BN, int STAGES) { return STAGES * (TG_A_BYTES + BN * TG_BK * 4) + 1024 /*align*/ + 256 /*barriers*/; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -203,7 +203,8 @@ __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_consta
     mbar_wait(tmem_full, 0);                                           // every MMA has retired: the stage buffers are idle
     tc_fence_after();
     const int q = warp & 3;                                            // a warp may only touch TMEM lanes [32*(warp%4), +32)
-    float* stg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))) + q * (32 * 33);
+    const int ehalf = (warp - 2) >> 2;                                 // which of the quarter's two warps
+    float* stg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))) + (warp - 2) * (32 * 33);
     const int mrow0 = m0 + q * 32;
     // everything the row loop needs lives in registers: kernel parameters sit in the constant bank and a dependent
     // LDCU per use (once per element) made this loop ~10x slower than the MMA main loop
@@ -213,11 +214,22 @@ __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_consta
     const int M = g.M, N = g.N;
     const bool splitk = gridDim.z > 1;
     const int rows = min(32, M - mrow0);
+    // scalar copies pinned in registers (an empty asm makes them opaque, so they are not re-read from the constant bank)
+    int p_mode = e.mode, p_act = e.act, p_round = e.round_out;
+    float p_keep = e.drop.keep;
+    uint64_t p_seed = e.drop.seed;
+    uint32_t p_stream = e.drop.stream;
+    long p_gid0 = e.drop.row_gid0, p_ldaux = e.ldaux;
+    const float *p_bias = e.bias, *p_aux = e.aux;
+    asm volatile("" : "+r"(p_mode), "+r"(p_act), "+r"(p_round), "+f"(p_keep), "+l"(p_seed), "+r"(p_stream), "+l"(p_gid0), "+l"(p_ldaux),
+                 "+l"(p_bias), "+l"(p_aux));
+    const bool p_drop = p_mode != EPI_PLAIN && p_keep < 1.0f;
+    const float p_inv_keep = 1.0f / p_keep;                            // x * (1/keep) instead of an IEEE division per element
     // float4 path: N, ldc (and the aux pitch) multiples of 4 and 16-byte aligned bases
     const bool vec4 = (N & 3) == 0 && (ldc & 3) == 0 && ((uintptr_t)Cp & 15) == 0 && (!e.bias || ((uintptr_t)e.bias & 15) == 0) &&
                       (e.mode != EPI_DACT || ((e.ldaux & 3) == 0 && ((uintptr_t)e.aux & 15) == 0));
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
+    for (int c = ehalf * 32; c < BN; c += 64) {
       if (n0 + c >= N) break;
       uint32_t r[32];
       tc_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + c, r);
@@ -248,13 +260,36 @@ __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_consta
         // fused activation / dropout epilogues: lane = (row % 4, 4-column group) so one Philox call serves four outputs
         const int cg = lane & 7, rsub = lane >> 3, n4 = n0 + c + cg * 4;
         if (n4 < N) {
-#pragma unroll 2
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p_bias) b4 = *reinterpret_cast<const float4*>(p_bias + n4);
+          // fully unrolled: eight independent Philox chains per thread hide each other's latency (one warp per scheduler)
+#pragma unroll
           for (int rb = 0; rb < 32; rb += 4) {
             const int rr = rb + rsub;
             if (rr < rows) {
+              const long m = mrow0 + rr;
               const float* sp = stg + rr * 33 + cg * 4;
-              const float4 v = epilogue_apply4(e, make_float4(sp[0], sp[1], sp[2], sp[3]), mrow0 + rr, n4, N);
-              *reinterpret_cast<float4*>(Cp + (long)(mrow0 + rr) * ldc + n4) = v;
+              float x[4] = {sp[0] + b4.x, sp[1] + b4.y, sp[2] + b4.z, sp[3] + b4.w};
+              float mk[4] = {1.f, 1.f, 1.f, 1.f};
+              if (p_drop) drop4(p_seed, p_stream, (uint64_t)((p_gid0 + m) * N + n4) >> 2, p_keep, mk);
+              if (p_mode == EPI_BIAS_ACT_DROP) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) { x[j] = act_fwd(x[j], p_act); if (p_drop) x[j] = x[j] * p_inv_keep * mk[j]; }
+              } else {                                                 // EPI_DACT
+                const float4 y4 = *reinterpret_cast<const float4*>(p_aux + m * p_ldaux + n4);
+                const float y[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                  float a = y[j];
+                  if (p_drop) { a = y[j] * p_keep; x[j] = x[j] * p_inv_keep * mk[j]; }
+                  x[j] *= act_bwd_from_out(a, p_act);
+                }
+              }
+              if (p_round) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) x[j] = tf32_rna(x[j]);
+              }
+              *reinterpret_cast<float4*>(Cp + m * ldc + n4) = make_float4(x[0], x[1], x[2], x[3]);
             }
           }
         }
