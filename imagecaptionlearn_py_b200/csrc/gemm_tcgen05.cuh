@@ -30,7 +30,8 @@ namespace icl {
 
 constexpr int TG_BM = 128, TG_BK = 32;
 constexpr int TG_A_BYTES = TG_BM * TG_BK * 4;                          // 16 KB per A stage
-constexpr int TG_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter, alternating 32-column chunks)
+constexpr int TG_EPW = 2;             // epilogue warps per TMEM lane quarter (they take alternating 32-column chunks)
+constexpr int TG_THREADS = 64 + 128 * TG_EPW;   // warp 0 TMA, warp 1 MMA, then the epilogue warps
 constexpr int tg_smem(int BN, int STAGES) { return STAGES * (TG_A_BYTES + BN * TG_BK * 4) + 1024 /*align*/ + 256 /*barriers*/; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_consta
     const bool vec4 = (N & 3) == 0 && (ldc & 3) == 0 && ((uintptr_t)Cp & 15) == 0 && (!e.bias || ((uintptr_t)e.bias & 15) == 0) &&
                       (e.mode != EPI_DACT || ((e.ldaux & 3) == 0 && ((uintptr_t)e.aux & 15) == 0));
 #pragma unroll 1
-    for (int c = ehalf * 32; c < BN; c += 64) {
+    for (int c = ehalf * 32; c < BN; c += 32 * TG_EPW) {
       if (n0 + c >= N) break;
       uint32_t r[32];
       tc_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + c, r);
