@@ -259,17 +259,16 @@ template <int U> static int rec_set_attr() {
 }
 static int rec_init(icl_model* m) {
   const int H = m->H, U = m->rp_U;
-  const int U0 = U == 20 ? RecSplit<20>::U0 : RecSplit<16>::U0, U1 = U - U0;
   const uint64_t RC = (uint64_t)m->rows_cap;
   const int NONE = (int)CU_TENSOR_MAP_SWIZZLE_NONE, SW128 = (int)CU_TENSOR_MAP_SWIZZLE_128B;
   RecFwdMaps& f = m->rp_fmaps;
   for (int d = 0; d < 2; d++) {
     CKI(box_map(m, m->Hp[d], H, RC, 32, 128, SW128, &f.a[d], m->ldx));
     CKI(box_map(m, m->Wp[d], (uint64_t)m->rp_nkb * 32, (uint64_t)m->rp_nsl * 4 * U, 32, 4 * U, SW128, &f.w[d]));
-    CKI(box_map(m, m->Z[d], 4 * H, RC, U0, 32, NONE, &f.z0[d]));   CKI(box_map(m, m->Z[d], 4 * H, RC, U1, 32, NONE, &f.z1[d]));
-    CKI(box_map(m, m->Cc[d], H, RC, U0, 32, NONE, &f.cc0[d]));     CKI(box_map(m, m->Cc[d], H, RC, U1, 32, NONE, &f.cc1[d]));
-    CKI(box_map(m, m->Hx[d], H, RC, U0, 32, NONE, &f.hx0[d]));     CKI(box_map(m, m->Hx[d], H, RC, U1, 32, NONE, &f.hx1[d]));
-    CKI(box_map(m, m->Hp[d], H, RC, U0, 32, NONE, &f.hp0[d], m->ldx)); CKI(box_map(m, m->Hp[d], H, RC, U1, 32, NONE, &f.hp1[d], m->ldx));
+    CKI(box_map(m, m->Z[d], 4 * H, RC, U, 32, NONE, &f.z[d]));
+    CKI(box_map(m, m->Cc[d], H, RC, U, 32, NONE, &f.cc[d]));
+    CKI(box_map(m, m->Hx[d], H, RC, U, 32, NONE, &f.hx[d]));
+    CKI(box_map(m, m->Hp[d], H, RC, U, 32, NONE, &f.hp[d], m->ldx));
   }
   for (int d = 0; d < 2; d++) {
     CKI(box_map(m, m->Z[d], 4 * H, RC, 32, 128, SW128, &m->rp_bmaps.za[d]));
@@ -822,6 +821,7 @@ static int lstm_backward(icl_model* m) {
     CK(cudaMemsetAsync(m->rp_bar, 0, 4, st));
     RecBwdArgs a;
     a.off = m->d_off; a.nact = m->d_nact; a.Tmax = m->Tmax; a.H = H; a.round_ops = m->round_ops; a.bar = m->rp_bar;
+    a.trace = m->rp_trace; a.trace_cta = m->rp_trace_cta;
     for (int d = 0; d < 2; d++) { a.Z[d] = m->Z[d]; a.Cc[d] = m->Cc[d]; a.dHout[d] = m->dHout[d]; a.dhrec[d] = m->dhrec[d]; a.dcc[d] = m->dcc[d]; }
     void* args[] = {(void*)&m->rp_bmaps, (void*)&a};
     cudaError_t e = cudaLaunchCooperativeKernel((void*)k_rec_bwd, dim3(m->n_sms), dim3(RB_THREADS), args, RB_SMEM, st);

@@ -47,7 +47,8 @@ struct RecArgs {
 constexpr int RP_TRACE_EV = 2048;
 struct Tracer {
   long long* p; int n;
-  __device__ __forceinline__ void init(const RecArgs& g, int role) { p = (g.trace && (int)blockIdx.x == g.trace_cta) ? g.trace + (long)role * RP_TRACE_EV * 4 : nullptr; n = 0; }
+  __device__ __forceinline__ void init(long long* trace, int cta, int role) { p = (trace && (int)blockIdx.x == cta) ? trace + (long)role * RP_TRACE_EV * 4 : nullptr; n = 0; }
+  __device__ __forceinline__ void init(const RecArgs& g, int role) { init(g.trace, g.trace_cta, role); }
   __device__ __forceinline__ void ev(int e, int k, int t) {
     if (p && n < RP_TRACE_EV) { p[n * 4] = e; p[n * 4 + 1] = k; p[n * 4 + 2] = t; p[n * 4 + 3] = clock64(); n++; }
   }
@@ -117,9 +118,9 @@ constexpr int RP_FWD_THREADS = 64 + 32 * RP_EW;
 template <int U> struct RecSplit {           // units of a slice handled by epilogue half 0 / half 1 (multiples of 4)
   static constexpr int U0 = (U / 4 + 1) / 2 * 4, U1 = U - U0;
 };
-struct RecFwdMaps {       // [direction]; *0 / *1: boxes {U0, 32 rows} / {U1, 32 rows} of the two epilogue halves
+struct RecFwdMaps {       // [direction]; z/cc/hx/hp: boxes {U units, 32 rows} of one TMEM lane quarter
   CUtensorMap a[2], w[2];
-  CUtensorMap z0[2], z1[2], cc0[2], cc1[2], hx0[2], hx1[2], hp0[2], hp1[2];
+  CUtensorMap z[2], cc[2], hx[2], hp[2];
 };
 
 template <int U>
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(RP_FWD_THREADS, 1) k_rec_fwd(const __grid_cons
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t sW = base;
   const uint32_t sA = sW + (uint32_t)g.nkb * N * 128;
-  const uint32_t sE = sA + RP_ASTAGES * 16384;                           // 4 quarters x {half 0: 7 boxes [32 x U0], half 1: 7 boxes [32 x U1]}
+  const uint32_t sE = sA + RP_ASTAGES * 16384;                           // 4 quarters x 7 boxes [32 rows x U]
   const uint32_t bars = sE + 7 * RP_ROWS * U * 4;
   const uint32_t full0 = bars, empty0 = bars + 24, wfull = bars + 48, efull0 = bars + 56, tfull0 = bars + 56 + 8 * RP_EW,
                  tempty0 = tfull0 + 8 * RP_MAXACC, tmem_slot = tempty0 + 8 * RP_MAXACC;
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(RP_FWD_THREADS, 1) k_rec_fwd(const __grid_cons
   if (threadIdx.x == 0) {
     for (int s = 0; s < RP_ASTAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     mbar_init(wfull, 1);
-    for (int w = 0; w < RP_EW; w++) mbar_init(efull0 + 8 * w, 1);
+    for (int w = 0; w < 4; w++) mbar_init(efull0 + 8 * w, 1);
     for (int a = 0; a < NACC; a++) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, RP_EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(RP_FWD_THREADS, 1) k_rec_fwd(const __grid_cons
   tc_fence_after();
   uint32_t tmem;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
-  const unsigned per_step = (unsigned)(g.nsl * RP_EW);                  // counter increments per (step, tile)
+  const unsigned per_step = (unsigned)(g.nsl * 4);                      // counter increments per (step, tile): slices x quarters
 
   if (warp == 0) {
     if (lane == 0) {                                                   // ---- A producer (h_{k-1} tiles) + resident W slice
@@ -217,23 +218,22 @@ __global__ void __launch_bounds__(RP_FWD_THREADS, 1) k_rec_fwd(const __grid_cons
       }
     }
   } else {
-    // ---- 8 self-contained epilogue warps.  Warp (q = TMEM lane quarter, hs = unit half) owns rows [32q, 32q+32) x its units of
-    // EVERY tile of this CTA: it TMA-loads its own Zx boxes, keeps its cell state c in registers across the steps,
-    // TMA-stores its own outputs and publishes them on the tile's counter.  No CTA-wide barrier in the step loop.
+    // ---- 8 epilogue warps = 4 TMEM lane quarters x 2 unit halves.  A quarter owns rows [32q, 32q+32) x the slice's U units
+    // of EVERY tile of this CTA: it TMA-loads its own Zx boxes {U x 32}, its two warps split the units (hs = 0/1), keep
+    // their cell state c in registers across the steps, and the quarter TMA-stores its outputs and publishes them on the
+    // tile's counter.  Only a 64-thread named barrier couples the two warps; no CTA-wide barrier in the step loop.
     const int ew = warp - 2, q = warp & 3, hs = ew >> 2;
     const int UH = hs ? U1 : U0, ubase = hs ? U0 : 0;                      // my units of the slice: [ubase, ubase + UH)
-    const int BOXB = 32 * UH * 4;
-    const uint32_t sMine = sE + (uint32_t)q * (7 * 32 * U * 4) + (hs ? 7 * 32 * U0 * 4 : 0);
-    float* zb = reinterpret_cast<float*>(gbase + (sMine - base));        // [4 gates][32][UH], then c, h, hr [32][UH]
-    float* cb = zb + 4 * 32 * UH;
-    float* hb = cb + 32 * UH;
-    float* hrb = hb + 32 * UH;
-    const CUtensorMap* mz = hs ? &maps.z1[d] : &maps.z0[d];
-    const CUtensorMap* mc = hs ? &maps.cc1[d] : &maps.cc0[d];
-    const CUtensorMap* mh = hs ? &maps.hx1[d] : &maps.hx0[d];
-    const CUtensorMap* mp = hs ? &maps.hp1[d] : &maps.hp0[d];
-    const uint32_t efull = efull0 + 8 * ew;
-    const int ucol = j * U + ubase;                                      // first hidden unit of this warp
+    constexpr int BOXB = 32 * U * 4;
+    const uint32_t sMine = sE + (uint32_t)q * (7 * BOXB);
+    float* zb = reinterpret_cast<float*>(gbase + (sMine - base)) + ubase;   // [4 gates][32][U], then c, h, hr [32][U]
+    float* cb = zb + 4 * 32 * U;
+    float* hb = cb + 32 * U;
+    float* hrb = hb + 32 * U;
+    const CUtensorMap *mz = &maps.z[d], *mc = &maps.cc[d], *mh = &maps.hx[d], *mp = &maps.hp[d];
+    const uint32_t efull = efull0 + 8 * q;
+    const int ucol = j * U;                                              // first hidden unit of the slice
+    const bool issuer = hs == 0 && lane == 0;                            // the quarter's TMA thread
     float cst[RP_MAXTPC][U0];                                            // carried cell state (U0 >= U1)
 #pragma unroll
     for (int i = 0; i < RP_MAXTPC; i++)
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(RP_FWD_THREADS, 1) k_rec_fwd(const __grid_cons
     Tracer tr; tr.init(g, 3);
     if (ew != 0 || lane != 0) tr.p = nullptr;
     uint32_t e = 0, acc = 0;
-    if (lane == 0 && p * RP_ROWS < s_n[0]) {                             // prefetch the first tile's Zx boxes
+    if (issuer && p * RP_ROWS < s_n[0]) {                                // prefetch the first tile's Zx boxes
       mbar_expect_tx(efull, 4 * BOXB);
       for (int gate = 0; gate < 4; gate++) tma_load_2d(sMine + gate * BOXB, mz, gate * H + ucol, s_off[0] + p * RP_ROWS + 32 * q, efull);
     }
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(RP_FWD_THREADS, 1) k_rec_fwd(const __grid_cons
             }
             float4 z4[4];
 #pragma unroll
-            for (int gate = 0; gate < 4; gate++) z4[gate] = *reinterpret_cast<float4*>(zb + gate * 32 * UH + lane * UH + c * 4);
+            for (int gate = 0; gate < 4; gate++) z4[gate] = *reinterpret_cast<float4*>(zb + gate * 32 * U + lane * U + c * 4);
             const float *zi = &z4[0].x, *zj = &z4[1].x, *zf = &z4[2].x, *zo = &z4[3].x;
             float si[4], tj[4], sf[4], so[4], hn[4], hr[4];
 #pragma unroll
@@ -288,15 +288,15 @@ __global__ void __launch_bounds__(RP_FWD_THREADS, 1) k_rec_fwd(const __grid_cons
               hr[x] = tf32_rna(hn[x]);
             }
             if (g.training) {
-              *reinterpret_cast<float4*>(zb + 0 * 32 * UH + lane * UH + c * 4) = make_float4(si[0], si[1], si[2], si[3]);
-              *reinterpret_cast<float4*>(zb + 1 * 32 * UH + lane * UH + c * 4) = make_float4(tj[0], tj[1], tj[2], tj[3]);
-              *reinterpret_cast<float4*>(zb + 2 * 32 * UH + lane * UH + c * 4) = make_float4(sf[0], sf[1], sf[2], sf[3]);
-              *reinterpret_cast<float4*>(zb + 3 * 32 * UH + lane * UH + c * 4) = make_float4(so[0], so[1], so[2], so[3]);
-              *reinterpret_cast<float4*>(cb + lane * UH + c * 4) =
+              *reinterpret_cast<float4*>(zb + 0 * 32 * U + lane * U + c * 4) = make_float4(si[0], si[1], si[2], si[3]);
+              *reinterpret_cast<float4*>(zb + 1 * 32 * U + lane * U + c * 4) = make_float4(tj[0], tj[1], tj[2], tj[3]);
+              *reinterpret_cast<float4*>(zb + 2 * 32 * U + lane * U + c * 4) = make_float4(sf[0], sf[1], sf[2], sf[3]);
+              *reinterpret_cast<float4*>(zb + 3 * 32 * U + lane * U + c * 4) = make_float4(so[0], so[1], so[2], so[3]);
+              *reinterpret_cast<float4*>(cb + lane * U + c * 4) =
                   make_float4(cst[i][c * 4], cst[i][c * 4 + 1], cst[i][c * 4 + 2], cst[i][c * 4 + 3]);
             }
-            *reinterpret_cast<float4*>(hb + lane * UH + c * 4) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-            *reinterpret_cast<float4*>(hrb + lane * UH + c * 4) = make_float4(hr[0], hr[1], hr[2], hr[3]);
+            *reinterpret_cast<float4*>(hb + lane * U + c * 4) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            *reinterpret_cast<float4*>(hrb + lane * U + c * 4) = make_float4(hr[0], hr[1], hr[2], hr[3]);
           }
         }
         if (k > 0) {
@@ -306,9 +306,9 @@ __global__ void __launch_bounds__(RP_FWD_THREADS, 1) k_rec_fwd(const __grid_cons
           acc++;
         }
         fence_async_smem();                                             // generic-proxy smem writes -> visible to the TMA engine
-        __syncwarp();
+        asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");       // both unit halves of the quarter are in smem
         tr.ev(3, k, t);
-        if (lane == 0) {
+        if (issuer) {
           const int row = s_off[k] + t * RP_ROWS + 32 * q;
           if (t * RP_ROWS < s_n[k + 1]) tma_store_2d(mp, sMine + 6 * BOXB, ucol, s_off[k + 1] + t * RP_ROWS + 32 * q);
           bulk_commit();                                               // group A: what step k+1 of the other slices waits for
@@ -329,10 +329,12 @@ __global__ void __launch_bounds__(RP_FWD_THREADS, 1) k_rec_fwd(const __grid_cons
           }
           bulk_wait<1>();                                               // group A is complete in global memory
           tr.ev(5, k, t);
-          flag_release_add(flags + t);
-          tr.ev(6, k, t);
         }
-        __syncwarp();
+        if (hs == 0) {
+          __syncwarp();
+          if (lane == 1) flag_release_add(flags + t);                   // a lane with no bulk copies in flight publishes the tile
+          if (lane == 0) tr.ev(6, k, t);
+        }
       }
     }
     if (lane == 0) bulk_wait<0>();
@@ -365,6 +367,7 @@ struct RecBwdArgs {
   int Tmax, H, round_ops;
   float* Z[2]; const float* Cc[2]; const float* dHout[2]; float* dhrec[2]; float* dcc[2];
   unsigned* bar;                                    // grid-barrier counter, zeroed before the launch
+  long long* trace; int trace_cta;                  // optional bring-up trace (see Tracer)
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
@@ -414,12 +417,15 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rec_bwd(const __grid_constant
 
   uint32_t it = 0, acc = 0;                            // running k-block / accumulator counters (barrier parities)
   unsigned bar_target = 0;
+  Tracer tr; tr.init(g.trace, g.trace_cta, warp == 0 ? 0 : warp == 1 ? 1 : warp == 2 ? 2 : 3);
+  if (lane != 0 || warp > 2) tr.p = nullptr;
   const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (long)gridDim.x * blockDim.x;
   for (int k = Tmax - 1; k >= 0; k--) {
     const int n = s_n[k];
     const long o = s_off[k], op = k > 0 ? s_off[k - 1] : 0;
     // ---------------------------------------------------------------- E: cell backward, both directions
     const long per_dir = (long)n * q4;
+    tr.ev(0, k, 0);
     for (long idx = gtid; idx < 2 * per_dir; idx += gthreads) {
       const int d = idx >= per_dir;
       const long r = idx - (d ? per_dir : 0);
@@ -452,9 +458,12 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rec_bwd(const __grid_constant
       *reinterpret_cast<float4*>(dcp) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
     }
     if (k == 0) break;
+    tr.ev(1, k, 0);
     fence_async_all();                                  // dZ_k (generic stores) -> visible to the TMA reads of phase G
+    tr.ev(2, k, 0);
     bar_target += gridDim.x;
     grid_barrier(g.bar, bar_target);
+    tr.ev(3, k, 0);
     // ---------------------------------------------------------------- G: dh_rec = dZ_k W_hh^T
     const int Mt = (n + 127) / 128;
     int sp = (int)gridDim.x / max(1, 2 * Mt * Nt);
@@ -532,8 +541,10 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rec_bwd(const __grid_constant
         if (lane == 0) mbar_arrive(tempty);
       }
     }
+    tr.ev(4, k, 0);
     bar_target += gridDim.x;
     grid_barrier(g.bar, bar_target);
+    tr.ev(5, k, 0);
   }
   tc_fence_before();
   __syncthreads();
