@@ -244,7 +244,7 @@ __device__ __forceinline__ long token_row(const StepLayout& L, int dir, int s, i
 // (core.py:309-312), written to each direction's step-major row; TF32-rounded when the rows feed the tensor cores.
 __global__ void k_prep_x(const float* __restrict__ xraw, const int* __restrict__ tok_seq, const int* __restrict__ tokstart,
                          StepLayout L, int ntok, int E, int Tcap, int data_norm, float keep_in, uint64_t seed,
-                         int64_t seq_gid0, int round_ops, float* __restrict__ xfw, float* __restrict__ xbw, int ldx) {
+                         int64_t seq_gid0, int round_ops, float* __restrict__ xfw, float* __restrict__ xbw, int ldx, int ones_col) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= ntok) return;
   int s = tok_seq[warp];
@@ -259,6 +259,7 @@ __global__ void k_prep_x(const float* __restrict__ xraw, const int* __restrict__
     scale = rsqrtf(fmaxf(ss, 1e-12f));
   }
   long rfw = token_row(L, 0, s, t), rbw = token_row(L, 1, s, t);
+  if (lane == 0) { xfw[rfw * ldx + ones_col] = 1.0f; xbw[rbw * ldx + ones_col] = 1.0f; }   // sums dZ into the bias gradient
   uint64_t base = (uint64_t)((seq_gid0 + s) * Tcap + t) * (uint64_t)E;
   for (int e4 = lane * 4; e4 < E; e4 += 128) {       // E % 4 == 0 is enforced at create
     float mf[4] = {1, 1, 1, 1}, mb[4] = {1, 1, 1, 1};

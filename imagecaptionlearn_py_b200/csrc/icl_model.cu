@@ -77,8 +77,9 @@ struct icl_model {
   int pK[2], pBias[2];
   int64_t step = 0;
   // workspaces (step-major, see icl_kernels.cuh)
-  // XH[d] = [rows, E+H]: columns [0,E) the prepared inputs (xd), columns [E,E+H) the TF32 h_{k-1} operand rows (Hp) -- one
-  // matrix so that dKernel = XH^T dZ is a single GEMM; xd / Hp are views with row pitch ldx = E+H
+  // XH[d] = [rows, E+H+4]: columns [0,E) the prepared inputs (xd), [E,E+H) the TF32 h_{k-1} operand rows (Hp), column E+H = 1
+  // on valid rows -- one matrix so that [dKernel; dbias] = XH^T dZ is a single GEMM (the ones column sums dZ into the bias
+  // gradient, which follows the kernel in the flat gradient buffer); xd / Hp are views with row pitch ldx
   float *XH[2] = {};
   int ldx = 0;
   float *xraw = nullptr, *xd[2] = {}, *Z[2] = {}, *Hx[2] = {}, *Hp[2] = {}, *Cc[2] = {}, *dHout[2] = {}, *dhrec[2] = {}, *dcc[2] = {},
@@ -383,7 +384,8 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   // zero-filled once: rows past nact[k] of a step block only ever hold finite don't-care values
 #define ZALLOC(p, n) do { CKD(dmalloc(&(p), (n))); CKD(cudaMemset((p), 0, (n) * 4)); } while (0)
   for (int d = 0; d < 2; d++) {
-    ZALLOC(m->XH[d], RC * (E + H)); m->xd[d] = m->XH[d]; m->Hp[d] = m->XH[d] + E; m->ldx = E + H;
+    m->ldx = E + H + 4;
+    ZALLOC(m->XH[d], RC * m->ldx); m->xd[d] = m->XH[d]; m->Hp[d] = m->XH[d] + E;
     ZALLOC(m->Z[d], RC * 4 * H); ZALLOC(m->Hx[d], RC * H);
     ZALLOC(m->Cc[d], RC * H); ZALLOC(m->dHout[d], RC * H); ZALLOC(m->dhrec[d], SP * H); ZALLOC(m->dcc[d], SP * H);
     ZALLOC(m->R[d], SP * 4 * H);
@@ -668,7 +670,7 @@ static int lstm_forward(icl_model* m, float keep_in, uint64_t seed, int training
   if (Ntok == 0) return 0;
   PH_BEGIN(m, PH_PREP);
   k_prep_x<<<(unsigned)((Ntok * 32 + 255) / 256), 256, 0, st>>>(m->xraw, m->d_tokseq, m->d_tokstart, mk_layout(m), (int)Ntok, E, m->T_cap,
-                                                               m->cfg.data_norm, keep_in, seed, m->seq_gid0, m->round_ops, m->xd[0], m->xd[1], m->ldx);
+                                                               m->cfg.data_norm, keep_in, seed, m->seq_gid0, m->round_ops, m->xd[0], m->xd[1], m->ldx, E + H);
   LAUNCHED(m);
   for (int d = 0; d < 2; d++) {
     k_zero_pad_rows<<<m->Tmax, 256, 0, st>>>(m->XH[d], mk_layout(m), m->ldx); LAUNCHED(m);
@@ -803,34 +805,32 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
   return 0;
 }
 
-static int lstm_backward(icl_model* m) {
-  int E = m->E, H = m->H, S = m->S;
-  long Ntok = m->NtokP;            // time-batched GEMMs run over the padded row space (pad rows are zero)
+// K3 (opt-in): every BPTT step of both directions in one cooperative launch (lstm_persistent.cuh)
+static int rec_backward_persistent(icl_model* m) {
+  const int H = m->H, S = m->S;
   cudaStream_t st = m->stream;
-  if (m->Ntok == 0) return 0;
-  // K3: BPTT
-  PH_BEGIN(m, PH_REC_BWD);
+  for (int d = 0; d < 2; d++) {
+    CK(cudaMemsetAsync(m->dhrec[d], 0, (size_t)S * H * 4, st));
+    CK(cudaMemsetAsync(m->dcc[d], 0, (size_t)S * H * 4, st));
+  }
+  CK(cudaMemsetAsync(m->rp_bar, 0, 4, st));
+  RecBwdArgs a;
+  a.off = m->d_off; a.nact = m->d_nact; a.Tmax = m->Tmax; a.H = H; a.round_ops = m->round_ops; a.bar = m->rp_bar;
+  a.trace = m->rp_trace; a.trace_cta = m->rp_trace_cta;
+  for (int d = 0; d < 2; d++) { a.Z[d] = m->Z[d]; a.Cc[d] = m->Cc[d]; a.dHout[d] = m->dHout[d]; a.dhrec[d] = m->dhrec[d]; a.dcc[d] = m->dcc[d]; }
+  void* args[] = {(void*)&m->rp_bmaps, (void*)&a};
+  cudaError_t e = cudaLaunchCooperativeKernel((void*)k_rec_bwd, dim3(m->n_sms), dim3(RB_THREADS), args, RB_SMEM, st);
+  if (e != cudaSuccess) return fail("k_rec_bwd launch failed: %s", cudaGetErrorString(e));
+  m->launches++;
+  return 0;
+}
+
+// K3 (default): one cell kernel + one split-K GEMM per step and direction, directions interleaved on two streams
+static int rec_backward_steps(icl_model* m) {
+  const int E = m->E, H = m->H, S = m->S;
+  cudaStream_t st = m->stream;
   CK(cudaEventRecord(m->ev_fork, st));
   CK(cudaStreamWaitEvent(m->aux, m->ev_fork, 0));
-  if (m->rp_U != 0 && m->rp_on && m->rp_bwd_on && m->Tmax <= RP_MAXT) {
-    // K3: every BPTT step of both directions in one cooperative launch (lstm_persistent.cuh)
-    for (int d = 0; d < 2; d++) {
-      CK(cudaMemsetAsync(m->dhrec[d], 0, (size_t)S * H * 4, st));
-      CK(cudaMemsetAsync(m->dcc[d], 0, (size_t)S * H * 4, st));
-    }
-    CK(cudaMemsetAsync(m->rp_bar, 0, 4, st));
-    RecBwdArgs a;
-    a.off = m->d_off; a.nact = m->d_nact; a.Tmax = m->Tmax; a.H = H; a.round_ops = m->round_ops; a.bar = m->rp_bar;
-    a.trace = m->rp_trace; a.trace_cta = m->rp_trace_cta;
-    for (int d = 0; d < 2; d++) { a.Z[d] = m->Z[d]; a.Cc[d] = m->Cc[d]; a.dHout[d] = m->dHout[d]; a.dhrec[d] = m->dhrec[d]; a.dcc[d] = m->dcc[d]; }
-    void* args[] = {(void*)&m->rp_bmaps, (void*)&a};
-    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_rec_bwd, dim3(m->n_sms), dim3(RB_THREADS), args, RB_SMEM, st);
-    if (e != cudaSuccess) return fail("k_rec_bwd launch failed: %s", cudaGetErrorString(e));
-    m->launches++;
-    for (int d = 0; d < 2; d++) { k_zero_pad_rows<<<m->Tmax, 256, 0, st>>>(m->Z[d], mk_layout(m), 4 * H); LAUNCHED(m); }
-    PH_END(m, PH_REC_BWD);
-    goto wgrad;
-  }
   for (int d = 0; d < 2; d++) {
     cudaStream_t sd = d ? m->aux : st;
     CK(cudaMemsetAsync(m->dhrec[d], 0, (size_t)S * H * 4, sd));
@@ -865,24 +865,31 @@ static int lstm_backward(icl_model* m) {
   }
   CK(cudaEventRecord(m->ev_join, m->aux));
   CK(cudaStreamWaitEvent(st, m->ev_join, 0));
-  // pad rows of dZ must be exactly zero for the time-batched weight-gradient GEMMs (they still hold gates / Zx)
+  return 0;
+}
+
+static int lstm_backward(icl_model* m) {
+  const int E = m->E, H = m->H;
+  const long Ntok = m->NtokP;            // time-batched GEMMs run over the padded row space (pad rows are zero)
+  cudaStream_t st = m->stream;
+  if (m->Ntok == 0) return 0;
+  PH_BEGIN(m, PH_REC_BWD);
+  if (m->rp_U != 0 && m->rp_on && m->rp_bwd_on && m->Tmax <= RP_MAXT) CKI(rec_backward_persistent(m));
+  else CKI(rec_backward_steps(m));
+  // pad rows of dZ must be exactly zero for the time-batched weight-gradient GEMM (they still hold gates / Zx)
   for (int d = 0; d < 2; d++) { k_zero_pad_rows<<<m->Tmax, 256, 0, st>>>(m->Z[d], mk_layout(m), 4 * H); LAUNCHED(m); }
   PH_END(m, PH_REC_BWD);
-wgrad:
-  // time-batched weight gradients: dW_ih = Xd^T dZ, dW_hh = Hprev^T dZ (contraction over all tokens, split-K), db = colsum(dZ)
+  // time-batched weight gradients: ONE split-K GEMM per direction (contraction over all tokens)
   PH_BEGIN(m, PH_WGRAD);
-  // 128x256 tiles: ceil((E+H)/128) x ceil(4H/256) of them; split-K so that ~one wave of 148 CTAs covers the contraction
-  int tiles = ((E + H + 127) / 128) * ((4 * H + 255) / 256);
+  // 128x256 tiles: ceil((E+H+1)/128) x ceil(4H/256) of them; split-K so that ~one wave of 148 CTAs covers the contraction
+  int tiles = ((E + H + 1 + 127) / 128) * ((4 * H + 255) / 256);
   int splits = (int)std::max<long>(1, std::min<long>(std::min<long>(16, 148 / std::max(1, tiles)), Ntok / 1024));
   for (int d = 0; d < 2; d++) {
     float* dK = m->G + m->params[m->pK[d]].off;
-    GemmArgs gk = mk_gemm(m->XH[d], m->ldx, m->Z[d], 4 * H, dK, 4 * H, E + H, 4 * H, (int)Ntok);   // dKernel = [Xd | Hprev]^T dZ
+    // [dKernel; dbias] = [Xd | Hprev | 1]^T dZ  (the bias follows the kernel in the flat buffers)
+    if (m->params[m->pBias[d]].off != m->params[m->pK[d]].off + (int64_t)(E + H) * 4 * H) return fail("kernel/bias not contiguous");
+    GemmArgs gk = mk_gemm(m->XH[d], m->ldx, m->Z[d], 4 * H, dK, 4 * H, E + H + 1, 4 * H, (int)Ntok);
     CKI(gemm(m, st, true, true, gk, -1, splits));
-    float* db = m->G + m->params[m->pBias[d]].off;
-    CK(cudaMemsetAsync(db, 0, (size_t)4 * H * 4, st));
-    int rpb = 256;
-    dim3 grid((4 * H + 127) / 128, (unsigned)((Ntok + rpb - 1) / rpb));
-    k_colsum_atomic<<<grid, 128, 0, st>>>(m->Z[d], Ntok, 4 * H, 4 * H, db, rpb); LAUNCHED(m);
   }
   PH_END(m, PH_WGRAD);
   return 0;
