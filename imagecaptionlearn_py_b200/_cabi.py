@@ -43,7 +43,7 @@ class HeadBatch(C.Structure):
                 ("box", C.c_void_p), ("box_dtype", C.c_int32),
                 ("bfeats", C.c_void_p), ("bfeats_dtype", C.c_int32),
                 ("labels", C.c_void_p), ("labels_dtype", C.c_int32),
-                ("sent_offset", C.c_int32)]
+                ("sent_offset", C.c_int32), ("inactive", C.c_int32)]
 
 
 class Batch(C.Structure):

@@ -294,16 +294,21 @@ class Session(object):
             __cuda_array_interface__ = dict(shape=(n.value,), typestr="<f4", data=(p.value, False), version=2)
         return torch.as_tensor(_Arr(), device="cuda:%d" % self.device)
 
-    def build_batch(self, batch_tensor_list, include_labels, keepalive):
+    def build_batch(self, batch_tensor_list, include_labels, keepalive, head_ids=None):
+        """batch_tensor_list[i] feeds head head_ids[i] (default: heads 0..n-1 in creation order); heads that are not fed are
+        marked inactive, like TF evaluating only the fetched task's subgraph (icl_multitask_lstm.py:327-334)."""
         g = self.graph
         b = _cabi.Batch()
+        head_ids = list(range(len(batch_tensor_list))) if head_ids is None else list(head_ids)
         first = batch_tensor_list[0]
         packed = "sentences_packed" in first
         sents, lens = [], []
         off = 0
-        b.n_heads = len(batch_tensor_list)
+        b.n_heads = len(g.heads)
+        for i in range(len(g.heads)):
+            b.heads[i].inactive = 0 if i in head_ids else 1
         T = 0
-        for i, bt in enumerate(batch_tensor_list):
+        for i, bt in zip(head_ids, batch_tensor_list):
             hb = b.heads[i]
             hb.sent_offset = off
             ln = np.asarray(bt["seq_lengths"])
@@ -366,16 +371,16 @@ class Session(object):
         b.ex_gid_offset = rank * max(h["batch_size"] for h in g.heads)
         return b
 
-    def run(self, op_kind, batch_tensor_list, keep_in, keep, include_labels, want=("proba", "pred")):
+    def run(self, op_kind, batch_tensor_list, keep_in, keep, include_labels, head_ids=None):
         L = _cabi.lib()
         g = self.graph
-        if len(batch_tensor_list) != len(g.heads):
+        if head_ids is None and len(batch_tensor_list) != len(g.heads):
             raise ValueError("got %d batches for %d heads" % (len(batch_tensor_list), len(g.heads)))
         keepalive = []
         need_T = max((bt["sentences"].shape[1] if "sentences" in bt else int(np.max(bt["seq_lengths"])))
                      for bt in batch_tensor_list)
         self.ensure(need_T)
-        b = self.build_batch(batch_tensor_list, include_labels, keepalive)
+        b = self.build_batch(batch_tensor_list, include_labels, keepalive, head_ids)
         self._bind_stream()
         outs = (_cabi.HeadOut * _cabi.MAX_HEADS)()
         res = []
@@ -406,21 +411,32 @@ def run_op(sess, op, batch_tensor_list, lstm_input_dropout, dropout, encoding_sc
     """core.py:517-626.  `tasks`/`scope_names` must list the heads in the order they were set up (as the
     reference's scripts do); `encoding_scheme` was fixed at setup time and is checked, not re-applied."""
     g = sess.graph
-    if [h["task"] for h in g.heads] != list(tasks):
-        raise ValueError("run_op tasks %r do not match the graph's heads %r" % (tasks, [h["task"] for h in g.heads]))
+    scopes = [h["scope"] for h in g.heads]
+    all_tasks = [h["task"] for h in g.heads]
+    if list(tasks) == all_tasks:
+        head_ids = None
+    else:       # a subset of the heads is fed (multitask predict / alternate training): match by scope name, then by task
+        head_ids = []
+        for t, sc in zip(tasks, scope_names):
+            cand = [i for i, h in enumerate(g.heads) if h["task"] == t and (h["scope"] == sc or sc == "")]
+            if not cand:
+                raise ValueError("run_op: no head for task %r (scope %r) in the graph's heads %r" % (t, sc, all_tasks))
+            head_ids.append(cand[0])
     for h in g.heads:
         if h["encoding_scheme"] != encoding_scheme:
             raise ValueError("encoding_scheme differs from the one the graph was built with")
     kind = {"train_op": _cabi.OP_TRAIN}.get(op.kind, _cabi.OP_PREDICT)
     if kind == _cabi.OP_TRAIN and not include_labels:
         raise ValueError("train_op needs include_labels=True")
-    res = sess.run(kind, batch_tensor_list, float(lstm_input_dropout), float(dropout), include_labels)
+    res = sess.run(kind, batch_tensor_list, float(lstm_input_dropout), float(dropout), include_labels, head_ids)
     if op.kind == "train_op":
         return None
-    scopes = [h["scope"] for h in g.heads]
-    if op.kind == "loss" and op.scope == "" and len(g.heads) > 1:
+    if op.kind == "loss" and op.scope == "" and len(g.heads) > 1 and head_ids is None:
         return np.float32(sum(r["loss"] for r in res))       # simple_joint: sum of the task losses
-    i = scopes.index(op.scope) if op.scope in scopes else 0
+    if op.scope in scopes:
+        i = scopes.index(op.scope)
+    else:
+        i = head_ids[0] if head_ids else 0
     return res[i][{"predicted_proba": "proba"}.get(op.kind, op.kind)]
 
 

@@ -56,7 +56,7 @@ struct Head {
   long long* pred = nullptr;
   int* idx[ICL_N_INDEX] = {};
   float *feats = nullptr, *box = nullptr, *bfeats = nullptr, *labels = nullptr;
-  bool has_labels = false;
+  bool has_labels = false, active = true;
   // pinned staging
   int* h_idx = nullptr; float* h_dense = nullptr; float* h_out = nullptr; long long* h_pred = nullptr;
   size_t h_dense_floats = 0;
@@ -563,6 +563,8 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
     Head& h = m->heads[hi];
     const icl_head_batch& hb = b->heads[hi];
     int B = h.c.batch_size, C = h.c.n_classes;
+    h.active = !hb.inactive;
+    if (!h.active) { h.has_labels = false; continue; }
     for (int sl = 0; sl < h.slots.n_slots; sl++) {
       int id = h.slot_index_id[sl];
       if (id < 0) continue;
@@ -727,6 +729,7 @@ static int heads_forward(icl_model* m, float keep, uint64_t seed) {
   PH_BEGIN(m, PH_HEADS_FWD);
   for (size_t hi = 0; hi < m->heads.size(); hi++) {
     Head& h = m->heads[hi];
+    if (!h.active) continue;
     int B = h.c.batch_size, C = h.c.n_classes, L = h.c.n_hidden;
     k_gather_concat<<<B, 128, 0, st>>>(h.slots, m->Hx[0], m->Hx[1], mk_layout(m), H, m->T_cap, h.D0, mk_drop(seed, 0, keep, m->seq_gid0),
                                       m->round_ops, h.bi);
@@ -770,6 +773,14 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
   for (int d = 0; d < 2; d++) CK(cudaMemsetAsync(m->dHout[d], 0, (size_t)m->NtokP * H * 4, st));
   for (size_t hi = 0; hi < m->heads.size(); hi++) {
     Head& h = m->heads[hi];
+    if (!h.active) {                          // not fed in this call: its parameters get a zero gradient
+      for (size_t k = 0; k < h.pW.size(); k++) {
+        const Param &pw = m->params[h.pW[k]], &pb = m->params[h.pB[k]];
+        CK(cudaMemsetAsync(m->G + pw.off, 0, (size_t)pw.rows * pw.cols * 4, st));
+        CK(cudaMemsetAsync(m->G + pb.off, 0, (size_t)pb.rows * pb.cols * 4, st));
+      }
+      continue;
+    }
     if (!h.has_labels) return fail("backward needs labels for head %zu", hi);
     int B = h.c.batch_size, L = h.c.n_hidden;
     const float* dz = h.dlogits;       // gradient w.r.t. the pre-activation of layer k+1 (softmax layer first)
@@ -948,6 +959,11 @@ extern "C" int icl_fetch(icl_model* m, icl_head_out* out) {
     int B = h.c.batch_size, C = h.c.n_classes;
     if (out[hi].proba) memcpy(out[hi].proba, h.h_out, (size_t)B * C * 4);
     if (out[hi].pred) memcpy(out[hi].pred, h.h_pred, (size_t)B * 8);
+    if (!h.active) {
+      if (out[hi].proba) for (size_t i = 0; i < (size_t)B * C; i++) out[hi].proba[i] = NAN;
+      out[hi].loss = out[hi].accuracy = NAN;
+      continue;
+    }
     out[hi].loss = h.has_labels ? h.h_out[(size_t)B * C] : NAN;
     out[hi].accuracy = h.has_labels ? h.h_out[(size_t)B * C + 1] : NAN;
   }

@@ -71,6 +71,8 @@ typedef struct icl_head_batch {
   const void* bfeats; int32_t bfeats_dtype;     /* b_feats or NULL */
   const void* labels; int32_t labels_dtype;     /* one-hot [B,C] or NULL (include_labels=False) */
   int32_t sent_offset;                           /* added to the `sent` column (multi-head shared encoder pass) */
+  int32_t inactive;                              /* 1: this head is not fed in this call (TF evaluates only the fetched
+                                                    task's subgraph, icl_multitask_lstm.py:327-334); its outputs are NaN */
 } icl_head_batch;
 
 typedef struct icl_batch {
