@@ -4,6 +4,7 @@
 #include "icl_kernels.cuh"
 #include "gemm_tcgen05.cuh"
 #include "lstm_persistent.cuh"
+#include "lstm_bptt.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -108,6 +109,10 @@ struct icl_model {
   RecBwdMaps rp_bmaps;
   unsigned* rp_bar = nullptr;
   bool rp_bwd_on = false;       // k_rec_bwd is correct but measured slower (0.84 ms) than the per-step path (0.56 ms): opt-in
+  // fused BPTT step kernel (lstm_bptt.cuh): default backward recurrence in tensor-core mode
+  bool bp_on = false;
+  int bp_cs = 4;
+  BpttMaps bp_maps;
   int n_sms = 148;
   int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
   float last_ms = 0.f;
@@ -281,6 +286,24 @@ static int rec_init(icl_model* m) {
   return U == 20 ? rec_set_attr<20>() : rec_set_attr<16>();
 }
 
+static int bptt_init(icl_model* m) {
+  m->bp_on = m->cfg.gemm_mode == ICL_GEMM_TCGEN05_TF32;
+  if (const char* e = getenv("ICL_BPTT_FUSED")) m->bp_on = m->bp_on && atoi(e) != 0;
+  if (const char* e = getenv("ICL_BPTT_CS")) { int c = atoi(e); if (c == 1 || c == 2 || c == 4) m->bp_cs = c; }
+  if (!m->bp_on) return 0;
+  const int H = m->H, SW128 = (int)CU_TENSOR_MAP_SWIZZLE_128B;
+  for (int d = 0; d < 2; d++) {
+    CKI(box_map(m, m->Z[d], 4 * H, (uint64_t)m->rows_cap, 32, 128, SW128, &m->bp_maps.za[d]));
+    const float* Whh = m->Pr + m->params[m->pK[d]].off + (size_t)m->E * 4 * H;
+    CKI(box_map(m, Whh, 4 * H, H, 32, BP_BN, SW128, &m->bp_maps.wb[d]));
+  }
+  if (cudaFuncSetAttribute(k_bptt_step<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(k_bptt_step<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(k_bptt_step<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM) != cudaSuccess)
+    return fail("cudaFuncSetAttribute(k_bptt_step) failed");
+  return 0;
+}
+
 // ----------------------------------------------------------------------------- API
 extern "C" const char* icl_last_error(void) { return g_err; }
 extern "C" int icl_version(void) { return 2; }
@@ -442,6 +465,7 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   for (int i = 0; i < PH_N; i++) for (int j = 0; j < 2; j++) CKD(cudaEventCreate(&m->ev_ph[i][j]));
   if (tcgen05_gemm_init() != 0) { fail("icl_create: cannot resolve cuTensorMapEncodeTiled"); icl_destroy(m); *out = nullptr; return -1; }
   if (m->rp_U && rec_init(m) != 0) { icl_destroy(m); *out = nullptr; return -1; }
+  if (bptt_init(m) != 0) { icl_destroy(m); *out = nullptr; return -1; }
 #undef CKD
   return 0;
 }
@@ -836,7 +860,38 @@ static int rec_backward_persistent(icl_model* m) {
   return 0;
 }
 
-// K3 (default): one cell kernel + one split-K GEMM per step and direction, directions interleaved on two streams
+// K3 (default in tensor-core mode): one fused launch per step for both directions -- dh_rec = dZ_{k+1} W_hh^T with the
+// contraction split over a thread-block cluster, reduced through distributed shared memory, cell backward in the epilogue
+static int rec_backward_fused(icl_model* m) {
+  const int H = m->H, S = m->S, cs = m->bp_cs;
+  cudaStream_t st = m->stream;
+  for (int d = 0; d < 2; d++) CK(cudaMemsetAsync(m->dcc[d], 0, (size_t)S * H * 4, st));
+  const int Nt = (H + BP_BN - 1) / BP_BN;
+  for (int k = m->Tmax - 1; k >= 0; k--) {
+    BpttArgs a;
+    for (int d = 0; d < 2; d++) { a.Z[d] = m->Z[d]; a.Cc[d] = m->Cc[d]; a.dHout[d] = m->dHout[d]; a.dcc[d] = m->dcc[d]; }
+    a.H = H; a.k = k; a.o_k = m->off[k]; a.o_kp1 = m->off[k + 1]; a.o_km1 = k > 0 ? m->off[k - 1] : 0;
+    a.n_k = m->n_active[k]; a.n_kp1 = k + 1 < m->Tmax ? m->n_active[k + 1] : 0;
+    a.n_km1 = k > 0 ? m->n_active[k - 1] : 0; a.o_km2 = k > 1 ? m->off[k - 2] : 0;
+    a.round_ops = m->round_ops; a.cs = cs;
+    { static const char* e = getenv("ICL_BPTT_DBG"); a.dbg = e ? atoi(e) : 0; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(Nt * cs), (unsigned)((a.n_k + 127) / 128), 2);
+    cfg.blockDim = dim3(BP_THREADS); cfg.dynamicSmemBytes = BP_SMEM; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 2;
+    cudaError_t e = cs == 4 ? cudaLaunchKernelEx(&cfg, k_bptt_step<4>, m->bp_maps, a)
+                    : cs == 2 ? cudaLaunchKernelEx(&cfg, k_bptt_step<2>, m->bp_maps, a)
+                              : cudaLaunchKernelEx(&cfg, k_bptt_step<1>, m->bp_maps, a);
+    if (e != cudaSuccess) return fail("k_bptt_step launch failed (step %d): %s", k, cudaGetErrorString(e));
+    m->launches++;
+  }
+  return 0;
+}
+
+// K3 (fp32 validation mode): one cell kernel + one split-K GEMM per step and direction, directions interleaved on two streams
 static int rec_backward_steps(icl_model* m) {
   const int E = m->E, H = m->H, S = m->S;
   cudaStream_t st = m->stream;
@@ -885,10 +940,13 @@ static int lstm_backward(icl_model* m) {
   cudaStream_t st = m->stream;
   if (m->Ntok == 0) return 0;
   PH_BEGIN(m, PH_REC_BWD);
-  if (m->rp_U != 0 && m->rp_on && m->rp_bwd_on && m->Tmax <= RP_MAXT) CKI(rec_backward_persistent(m));
-  else CKI(rec_backward_steps(m));
-  // pad rows of dZ must be exactly zero for the time-batched weight-gradient GEMM (they still hold gates / Zx)
-  for (int d = 0; d < 2; d++) { k_zero_pad_rows<<<m->Tmax, 256, 0, st>>>(m->Z[d], mk_layout(m), 4 * H); LAUNCHED(m); }
+  if (m->bp_on) CKI(rec_backward_fused(m));                // writes the pad rows of dZ as zeros itself
+  else {
+    if (m->rp_U != 0 && m->rp_on && m->rp_bwd_on && m->Tmax <= RP_MAXT) CKI(rec_backward_persistent(m));
+    else CKI(rec_backward_steps(m));
+    // pad rows of dZ must be exactly zero for the time-batched weight-gradient GEMM (they still hold gates / Zx)
+    for (int d = 0; d < 2; d++) { k_zero_pad_rows<<<m->Tmax, 256, 0, st>>>(m->Z[d], mk_layout(m), 4 * H); LAUNCHED(m); }
+  }
   PH_END(m, PH_REC_BWD);
   // time-batched weight gradients: ONE split-K GEMM per direction (contraction over all tokens)
   PH_BEGIN(m, PH_WGRAD);
