@@ -321,7 +321,9 @@ def main():
                     phases_ms={n: float(v) for n, v in zip(_cabi.PHASES, ph_ms)}, roofline=roof,
                     e2e=dict(value=world * n_seqs * e2e_steps / e2e_s, unit="captions/s", h2d_bytes_per_step=h2d.value,
                              d2h_bytes_per_step=d2h.value, ms_per_step=1e3 * e2e_s / e2e_steps, steps=e2e_steps,
-                             api="core.run_op(sess, train_op, [batch_tensors], ...) with host float32 NumPy buffers"),
+                             api="core.run_op(sess, train_op, [batch_tensors], ...) with host float32 NumPy buffers; pipelined: the batch is "
+                                 "packed into pinned memory and copied on a copy stream into the idle input set while the previous "
+                                 "step computes, loss/accuracy of the previous step are read back (D2H) every step"),
                     gpu_launches=launches, clocks=clocks_summary(clk))
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = {k: v for k, v in cpu_sample(wl, min(wl["B"], 256), 3, 1).items()

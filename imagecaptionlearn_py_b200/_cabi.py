@@ -63,7 +63,8 @@ SYMBOLS = ["icl_last_error", "icl_version", "icl_create", "icl_destroy", "icl_se
            "icl_param_info", "icl_get_tensor", "icl_set_tensor", "icl_get_step", "icl_set_step", "icl_run",
            "icl_upload", "icl_run_resident", "icl_fetch", "icl_grad_buffer", "icl_param_buffer", "icl_apply_update",
            "icl_sync", "icl_get_lstm_outputs", "icl_get_batch_input", "icl_get_activation", "icl_rec_trace", "icl_debug_mask", "icl_gemm",
-           "icl_kernel_launches", "icl_last_step_ms", "icl_phase_ms", "icl_copy_bytes", "icl_batch_stats"]
+           "icl_kernel_launches", "icl_last_step_ms", "icl_phase_ms", "icl_copy_bytes", "icl_batch_stats", "icl_train_async",
+           "icl_poll_stats"]
 N_PHASES = 8
 PHASES = ("prep", "proj_gemm", "rec_fwd", "heads_fwd", "heads_bwd", "rec_bwd", "wgrad", "update")
 
@@ -93,6 +94,8 @@ def lib():
         L.icl_upload.argtypes = [C.c_void_p, C.POINTER(Batch)]
         L.icl_run_resident.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_uint64]
         L.icl_fetch.argtypes = [C.c_void_p, C.POINTER(HeadOut)]
+        L.icl_train_async.argtypes = [C.c_void_p, C.POINTER(Batch), C.c_float, C.c_float, C.c_uint64, C.POINTER(HeadOut)]
+        L.icl_poll_stats.argtypes = [C.c_void_p, C.POINTER(HeadOut)]
         L.icl_grad_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
         L.icl_param_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
         L.icl_apply_update.argtypes = [C.c_void_p]

@@ -24,6 +24,7 @@ shared-weight encoder pass (concatenated) and each head indexes its own slice --
 import contextlib
 import ctypes as C
 import math
+import os
 
 import numpy as np
 
@@ -138,6 +139,7 @@ class Session(object):
         self.device = device
         self.handle = None
         self.run_counter = 0
+        self.last_train_stats = None
         self.base_seed = self.graph.seed if seed is None else seed
         self._grad_view = None
 
@@ -406,6 +408,38 @@ class Session(object):
                 for i, r in enumerate(res)]
 
 
+    def train_async(self, batch_tensor_list, keep_in, keep, head_ids=None):
+        """One pipelined `train_op` step (the reference discards its result, icl_core_lstm.py:138-150): the batch is packed
+        and copied on the copy stream into the idle input set while the previous step still computes, the step is enqueued
+        and the call returns.  `last_train_stats` holds loss / accuracy per head of the PREVIOUS step (read back
+        asynchronously every step)."""
+        L = _cabi.lib()
+        g = self.graph
+        if head_ids is None and len(batch_tensor_list) != len(g.heads):
+            raise ValueError("got %d batches for %d heads" % (len(batch_tensor_list), len(g.heads)))
+        keepalive = []
+        need_T = max((bt["sentences"].shape[1] if "sentences" in bt else int(np.max(bt["seq_lengths"])))
+                     for bt in batch_tensor_list)
+        self.ensure(need_T)
+        b = self.build_batch(batch_tensor_list, True, keepalive, head_ids)
+        self._bind_stream()
+        prev = (_cabi.HeadOut * _cabi.MAX_HEADS)()
+        self.run_counter += 1
+        seed = (self.base_seed * 1000003 + self.run_counter) & 0xFFFFFFFFFFFFFFFF
+        self.last_seed = seed
+        if self.dist:
+            import torch.distributed as td
+            _cabi.check(L.icl_upload(self.handle, C.byref(b)))
+            _cabi.check(L.icl_run_resident(self.handle, _cabi.OP_GRADS, keep_in, keep, seed))
+            td.all_reduce(self.grad_tensor(), op=td.ReduceOp.SUM)       # loss is a SUM over examples (core.py:267)
+            _cabi.check(L.icl_apply_update(self.handle))
+            _cabi.check(L.icl_poll_stats(self.handle, prev))
+        else:
+            _cabi.check(L.icl_train_async(self.handle, C.byref(b), keep_in, keep, seed, prev))
+        self.last_train_stats = [dict(loss=np.float32(prev[i].loss), accuracy=np.float32(prev[i].accuracy))
+                                 for i in range(len(g.heads))]
+
+
 def run_op(sess, op, batch_tensor_list, lstm_input_dropout, dropout, encoding_scheme, tasks, scope_names,
            include_labels=False):
     """core.py:517-626.  `tasks`/`scope_names` must list the heads in the order they were set up (as the
@@ -428,6 +462,9 @@ def run_op(sess, op, batch_tensor_list, lstm_input_dropout, dropout, encoding_sc
     kind = {"train_op": _cabi.OP_TRAIN}.get(op.kind, _cabi.OP_PREDICT)
     if kind == _cabi.OP_TRAIN and not include_labels:
         raise ValueError("train_op needs include_labels=True")
+    if op.kind == "train_op" and not os.environ.get("ICL_SYNC_TRAIN"):
+        sess.train_async(batch_tensor_list, float(lstm_input_dropout), float(dropout), head_ids)
+        return None                                           # sess.run(train_op) returns None (core.py:625)
     res = sess.run(kind, batch_tensor_list, float(lstm_input_dropout), float(dropout), include_labels, head_ids)
     if op.kind == "train_op":
         return None

@@ -44,6 +44,26 @@ static int fail(const char* fmt, ...) {
 
 struct Param { std::string name; int rows, cols; int64_t off; };
 
+// Inputs are double-buffered (device buffers + pinned staging): icl_upload packs batch i+1 and copies it on a separate copy
+// stream while the compute stream still runs step i.  The "current" pointers below (Head::idx, icl_model::xraw, ...) are
+// switched to the freshly uploaded set at the end of icl_upload.
+// One set = ONE device allocation and its pinned mirror with the same layout: [ x | meta ], meta = the small integer arrays
+// of the step layout followed by every head's index matrices / dense features / labels.  The sentence rows go up in chunks
+// while they are being packed; everything else is ONE copy (a dozen small cudaMemcpyAsync calls on the copy stream stalled the
+// concurrently running compute stream by ~80 us each -- measured 1.3 ms per step).
+struct HeadIn {                                             // byte offsets into the set's blob
+  size_t idx[ICL_N_INDEX] = {}, feats = 0, box = 0, bfeats = 0, labels = 0;
+};
+struct InSet {
+  char *d_blob = nullptr, *h_blob = nullptr;
+  size_t o_x = 0, o_lens = 0, o_rank = 0, o_tokstart = 0, o_tokseq = 0, o_off = 0, o_nact = 0, meta_off = 0, bytes = 0;
+  template <typename T> T* dev(size_t o) const { return reinterpret_cast<T*>(d_blob + o); }
+  template <typename T> T* host(size_t o) const { return reinterpret_cast<T*>(h_blob + o); }
+  cudaEvent_t ev_copied = nullptr, ev_done = nullptr, ev_stats = nullptr;
+  cudaEvent_t ev_c0 = nullptr, ev_s0 = nullptr;           // timing: first H2D copy issued / first kernel of the step
+  bool copied_pending = false, done_pending = false, stats_pending = false;
+};
+
 struct Head {
   icl_head_config c;
   int D0 = 0, D0g = 0;               // input width; width of the prefix that carries gathered LSTM columns
@@ -58,9 +78,8 @@ struct Head {
   int* idx[ICL_N_INDEX] = {};
   float *feats = nullptr, *box = nullptr, *bfeats = nullptr, *labels = nullptr;
   bool has_labels = false, active = true;
-  // pinned staging
-  int* h_idx = nullptr; float* h_dense = nullptr; float* h_out = nullptr; long long* h_pred = nullptr;
-  size_t h_dense_floats = 0;
+  HeadIn in[2];
+  float* h_out = nullptr; long long* h_pred = nullptr;   // pinned staging of the results
 };
 
 enum { PH_PREP = 0, PH_PROJ, PH_REC_FWD, PH_HEADS_FWD, PH_HEADS_BWD, PH_REC_BWD, PH_WGRAD, PH_UPDATE, PH_N };
@@ -86,7 +105,10 @@ struct icl_model {
   float *xraw = nullptr, *xd[2] = {}, *Z[2] = {}, *Hx[2] = {}, *Hp[2] = {}, *Cc[2] = {}, *dHout[2] = {}, *dhrec[2] = {}, *dcc[2] = {},
         *R[2] = {};
   int *d_off = nullptr, *d_nact = nullptr, *d_rank = nullptr, *d_lens = nullptr, *d_tokseq = nullptr, *d_tokstart = nullptr;
-  float* h_x = nullptr; int* h_ints = nullptr;         // pinned
+  InSet in[2];
+  int cur = -1;                                         // input set of the resident batch
+  cudaStream_t copy = nullptr;
+  float* h_stats = nullptr;                             // pinned [2 sets][ICL_MAX_HEADS][loss, accuracy]
   double* d_partial = nullptr; float* d_gnorm = nullptr;
   std::vector<Head> heads;
   // resident batch
@@ -135,7 +157,9 @@ static void to_f32(float* dst, const void* src, int dtype, size_t n) {
 }
 
 // Host worker pool for the batch marshalling (pack / convert sentences into pinned memory).  Threads are created once
-// per process: spawning them per call costs more than the 30 MB copy they parallelise.
+// per process: spawning them per call costs more than the 30 MB copy they parallelise.  FOUR threads by default
+// (ICL_HOST_THREADS): packing overlaps the previous step's kernels, and with 16 threads saturating host DRAM the GPU's
+// command fetches over PCIe slowed so much that a 1.77 ms step stretched to 3.0 ms (2 threads: 1.85, 4: 2.0, 8: 2.1-2.4).
 struct HostPool {
   std::vector<std::thread> th;
   std::mutex mu;
@@ -146,7 +170,8 @@ struct HostPool {
   uint64_t gen = 0;
   bool stop = false;
   HostPool() {
-    int n = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency())) - 1;
+    int n = (int)std::max(1u, std::min(4u, std::thread::hardware_concurrency())) - 1;
+    if (const char* e = getenv("ICL_HOST_THREADS")) n = std::max(0, atoi(e) - 1);
     for (int i = 0; i < n; i++) th.emplace_back([this] { worker(); });
   }
   ~HostPool() {
@@ -212,6 +237,33 @@ static int add_param(icl_model* m, const std::string& name, int rows, int cols) 
 
 template <typename T> static cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
 
+// ----------------------------------------------------------------------------- zero fills on the SMs
+// cudaMemsetAsync may be executed by a copy engine: with the next batch's H2D transfer in flight on the copy stream the
+// compute stream's memsets queued behind 4 MB chunks (measured: a 1.77 ms step stretched to 2.9 ms).  These run as kernels.
+__global__ void k_zero_words(uint32_t* __restrict__ p, size_t n_words) {
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    uint4* p4 = reinterpret_cast<uint4*>(p);
+    const size_t n4 = n_words >> 2;
+    for (size_t i = i0; i < n4; i += stride) p4[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (size_t i = (n4 << 2) + i0; i < n_words; i += stride) p[i] = 0u;
+  } else {
+    for (size_t i = i0; i < n_words; i += stride) p[i] = 0u;
+  }
+}
+__global__ void k_zero_2d(float* __restrict__ p, long pitch, int width, long rows) {   // width, pitch in floats (multiples of 4)
+  const long w4 = width >> 2, n = rows * w4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    *reinterpret_cast<float4*>(p + (i / w4) * pitch + (i % w4) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+static cudaError_t zero_async(void* p, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return cudaSuccess;
+  const size_t words = bytes / 4;
+  const unsigned blocks = (unsigned)std::min<size_t>(1184, (words / 4 + 255) / 256 + 1);
+  k_zero_words<<<blocks, 256, 0, st>>>(reinterpret_cast<uint32_t*>(p), words);
+  return cudaGetLastError();
+}
+
 // ----------------------------------------------------------------------------- GEMM dispatch
 // splits > 1: split-K over gridDim.z with a red.global epilogue (plain epilogue only; C is zeroed here)
 // prezeroed: C already holds zeros (split-K accumulates into it); pdl: programmatic dependent launch
@@ -227,7 +279,7 @@ static int gemm(icl_model* m, cudaStream_t st, bool a_mn, bool b_mn, const GemmA
   if (mode == ICL_GEMM_TCGEN05_TF32 && tcgen05_gemm_supported(g, a_mn, b_mn)) {
     if (splits > 1) {
       if (g.ldc != g.N) return fail("split-K gemm needs a dense C");
-      if (!prezeroed) CK(cudaMemsetAsync(g.C, 0, (size_t)g.M * g.N * 4, st));
+      if (!prezeroed) CK(zero_async(g.C, (size_t)g.M * g.N * 4, st));
     }
     int r = tcgen05_gemm_launch(m->tma, st, a_mn, b_mn, g, splits, pdl);
     if (r != 0) return fail("tcgen05 gemm launch failed (%d): %s", r, cudaGetErrorString(cudaGetLastError()));
@@ -286,6 +338,24 @@ static int rec_init(icl_model* m) {
   return U == 20 ? rec_set_attr<20>() : rec_set_attr<16>();
 }
 
+// make input set s the "current" one: the device pointers every launch site reads
+static void use_input_set(icl_model* m, int s) {
+  InSet& I = m->in[s];
+  m->xraw = I.dev<float>(I.o_x); m->d_off = I.dev<int>(I.o_off); m->d_nact = I.dev<int>(I.o_nact); m->d_rank = I.dev<int>(I.o_rank);
+  m->d_lens = I.dev<int>(I.o_lens); m->d_tokseq = I.dev<int>(I.o_tokseq); m->d_tokstart = I.dev<int>(I.o_tokstart);
+  for (Head& h : m->heads) {
+    HeadIn& hin = h.in[s];
+    for (int i = 0; i < ICL_N_INDEX; i++) h.idx[i] = I.dev<int>(hin.idx[i]);
+    h.feats = I.dev<float>(hin.feats); h.box = I.dev<float>(hin.box); h.bfeats = I.dev<float>(hin.bfeats);
+    h.labels = I.dev<float>(hin.labels);
+    for (int i = 0; i < h.slots.n_slots; i++) {
+      int id = h.slot_index_id[i];
+      if (id >= 0) h.slots.idx[i] = h.idx[id];
+      else h.slots.dense[i] = id == -1 ? h.feats : id == -2 ? h.box : h.bfeats;
+    }
+  }
+}
+
 static int bptt_init(icl_model* m) {
   m->bp_on = m->cfg.gemm_mode == ICL_GEMM_TCGEN05_TF32;
   if (const char* e = getenv("ICL_BPTT_FUSED")) m->bp_on = m->bp_on && atoi(e) != 0;
@@ -312,21 +382,22 @@ extern "C" void icl_destroy(icl_model* m) {
   if (!m) return;
   cudaDeviceSynchronize();
   auto F = [](void* p) { if (p) cudaFree(p); };
-  F(m->P); F(m->G); F(m->M); F(m->V); F(m->Pr); F(m->xraw);
+  F(m->P); F(m->G); F(m->M); F(m->V); F(m->Pr);
+  for (InSet& I : m->in) {
+    F(I.d_blob);
+    if (I.h_blob) cudaFreeHost(I.h_blob);
+    for (cudaEvent_t e : {I.ev_copied, I.ev_done, I.ev_stats, I.ev_c0, I.ev_s0}) if (e) cudaEventDestroy(e);
+  }
+  if (m->h_stats) cudaFreeHost(m->h_stats);
+  if (m->copy) cudaStreamDestroy(m->copy);
   for (int d = 0; d < 2; d++) {
     F(m->XH[d]); F(m->Z[d]); F(m->Hx[d]); F(m->Cc[d]); F(m->dHout[d]); F(m->dhrec[d]); F(m->dcc[d]); F(m->R[d]);
   }
   F(m->Wp[0]); F(m->Wp[1]); F(m->rp_flags); F(m->rp_trace); F(m->rp_bar);
-  F(m->d_off); F(m->d_nact); F(m->d_rank); F(m->d_lens); F(m->d_tokseq); F(m->d_tokstart); F(m->d_partial); F(m->d_gnorm);
-  if (m->h_x) cudaFreeHost(m->h_x);
-  if (m->h_ints) cudaFreeHost(m->h_ints);
+  F(m->d_partial); F(m->d_gnorm);
   for (auto& h : m->heads) {
     F(h.bi); F(h.dbi); F(h.dA); F(h.dBuf); for (auto a : h.act) F(a);
     F(h.proba); F(h.dlogits); F(h.row_loss); F(h.row_correct); F(h.scalars); F(h.pred);
-    for (int i = 0; i < ICL_N_INDEX; i++) F(h.idx[i]);
-    F(h.feats); F(h.box); F(h.bfeats); F(h.labels);
-    if (h.h_idx) cudaFreeHost(h.h_idx);
-    if (h.h_dense) cudaFreeHost(h.h_dense);
     if (h.h_out) cudaFreeHost(h.h_out);
     if (h.h_pred) cudaFreeHost(h.h_pred);
   }
@@ -402,7 +473,6 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   CKD(dmalloc(&m->P, np)); CKD(dmalloc(&m->G, np)); CKD(dmalloc(&m->M, np)); CKD(dmalloc(&m->V, np)); CKD(dmalloc(&m->Pr, np));
   CKD(cudaMemset(m->P, 0, np * 4)); CKD(cudaMemset(m->G, 0, np * 4)); CKD(cudaMemset(m->M, 0, np * 4)); CKD(cudaMemset(m->V, 0, np * 4));
   CKD(cudaMemset(m->Pr, 0, np * 4));
-  CKD(dmalloc(&m->xraw, (size_t)m->Ntok_cap * E));
   const size_t RC = (size_t)m->rows_cap, SP = (size_t)(m->S_cap + 127) / 128 * 128;
   // zero-filled once: rows past nact[k] of a step block only ever hold finite don't-care values
 #define ZALLOC(p, n) do { CKD(dmalloc(&(p), (n))); CKD(cudaMemset((p), 0, (n) * 4)); } while (0)
@@ -428,11 +498,31 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
     CKD(dmalloc(&m->rp_bar, 4));
   }
 #undef ZALLOC
-  CKD(dmalloc(&m->d_off, m->T_cap + 1)); CKD(dmalloc(&m->d_nact, m->T_cap + 1)); CKD(dmalloc(&m->d_rank, m->S_cap));
-  CKD(dmalloc(&m->d_lens, m->S_cap)); CKD(dmalloc(&m->d_tokstart, m->S_cap)); CKD(dmalloc(&m->d_tokseq, m->Ntok_cap));
+  for (InSet& I : m->in) {
+    size_t o = 0;
+    auto take = [&o](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+    I.o_x = take((size_t)m->Ntok_cap * E * 4);
+    I.meta_off = o;
+    I.o_lens = take((size_t)m->S_cap * 4); I.o_rank = take((size_t)m->S_cap * 4); I.o_tokstart = take((size_t)m->S_cap * 4);
+    I.o_off = take((size_t)(m->T_cap + 1) * 4); I.o_nact = take((size_t)(m->T_cap + 1) * 4);
+    const int si = (int)(&I - m->in);
+    for (Head& h : m->heads) {
+      HeadIn& hin = h.in[si];
+      const size_t B = h.c.batch_size;
+      for (int i = 0; i < ICL_N_INDEX; i++) hin.idx[i] = take(B * 3 * 4);
+      hin.feats = take(B * h.c.n_feats * 4); hin.box = take(B * h.c.box_width * 4); hin.bfeats = take(B * h.c.n_box_feats * 4);
+      hin.labels = take(B * h.c.n_classes * 4);
+    }
+    I.o_tokseq = take((size_t)m->Ntok_cap * 4);              // last: only its used prefix is copied
+    I.bytes = o;
+    CKD(cudaMalloc((void**)&I.d_blob, I.bytes));
+    CKD(cudaMallocHost((void**)&I.h_blob, I.bytes));
+    CKD(cudaEventCreate(&I.ev_copied)); CKD(cudaEventCreate(&I.ev_done)); CKD(cudaEventCreate(&I.ev_c0)); CKD(cudaEventCreate(&I.ev_s0));
+    CKD(cudaEventCreateWithFlags(&I.ev_stats, cudaEventDisableTiming));
+  }
+  CKD(cudaMallocHost((void**)&m->h_stats, (size_t)2 * ICL_MAX_HEADS * 2 * 4));
+  CKD(cudaStreamCreateWithFlags(&m->copy, cudaStreamNonBlocking));
   CKD(dmalloc(&m->d_partial, 1024)); CKD(dmalloc(&m->d_gnorm, 4));
-  CKD(cudaMallocHost((void**)&m->h_x, (size_t)m->Ntok_cap * E * 4));
-  CKD(cudaMallocHost((void**)&m->h_ints, ((size_t)m->S_cap * 3 + m->Ntok_cap + 2 * (m->T_cap + 1)) * 4));
   for (auto& h : m->heads) {
     int B = h.c.batch_size, C = h.c.n_classes;
     int maxw = 0;
@@ -442,22 +532,10 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
     for (int k = 1; k <= h.c.n_hidden; k++) { float* a; CKD(dmalloc(&a, (size_t)B * h.dims[k])); h.act.push_back(a); }
     CKD(dmalloc(&h.proba, (size_t)B * C)); CKD(dmalloc(&h.dlogits, (size_t)B * C));
     CKD(dmalloc(&h.row_loss, B)); CKD(dmalloc(&h.row_correct, B)); CKD(dmalloc(&h.scalars, 4)); CKD(dmalloc(&h.pred, B));
-    for (int i = 0; i < ICL_N_INDEX; i++) CKD(dmalloc(&h.idx[i], (size_t)B * 3));
-    CKD(dmalloc(&h.feats, (size_t)B * std::max(h.c.n_feats, 1)));
-    CKD(dmalloc(&h.box, (size_t)B * std::max(h.c.box_width, 1)));
-    CKD(dmalloc(&h.bfeats, (size_t)B * std::max(h.c.n_box_feats, 1)));
-    CKD(dmalloc(&h.labels, (size_t)B * C));
-    h.h_dense_floats = (size_t)B * (h.c.n_feats + h.c.box_width + h.c.n_box_feats + C);
-    CKD(cudaMallocHost((void**)&h.h_idx, (size_t)B * 3 * ICL_N_INDEX * 4));
-    CKD(cudaMallocHost((void**)&h.h_dense, std::max<size_t>(h.h_dense_floats, 1) * 4));
     CKD(cudaMallocHost((void**)&h.h_out, ((size_t)B * C + 4) * 4));
     CKD(cudaMallocHost((void**)&h.h_pred, (size_t)B * 8));
-    for (int i = 0; i < h.slots.n_slots; i++) {
-      int id = h.slot_index_id[i];
-      if (id >= 0) h.slots.idx[i] = h.idx[id];
-      else h.slots.dense[i] = id == -1 ? h.feats : id == -2 ? h.box : h.bfeats;
-    }
   }
+  use_input_set(m, 0);
   CKD(cudaStreamCreateWithFlags(&m->aux, cudaStreamNonBlocking));
   CKD(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
   CKD(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
@@ -529,10 +607,19 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
   if (b->n_heads != m->cfg.n_heads) return fail("icl_upload: batch has %d heads, model has %d", b->n_heads, m->cfg.n_heads);
   if (!b->sent_packed && (b->padded_T < 1 || b->padded_T > m->T_cap)) return fail("icl_upload: padded_T=%d exceeds capacity %d", b->padded_T, m->T_cap);
   int T = b->sent_packed ? m->T_cap : b->padded_T;
-  CK(cudaStreamSynchronize(m->stream));          // pinned staging is reused
+  // next input set: its pinned staging is free once the copies issued from it two uploads ago have completed, its device
+  // buffers once the step that consumed them has (the copy stream waits for that; the host does not)
+  const int set = (m->cur + 1) & 1;
+  InSet& I = m->in[set];
+  if (I.copied_pending) { CK(cudaEventSynchronize(I.ev_copied)); I.copied_pending = false; }
+  if (I.done_pending) { CK(cudaStreamWaitEvent(m->copy, I.ev_done, 0)); I.done_pending = false; }
+  m->resident = false;
+  m->cur = set;
+  use_input_set(m, set);
   m->h2d_bytes = 0;
-  int* lens = m->h_ints; int* rank = lens + m->S_cap; int* tokstart = rank + m->S_cap; int* tokseq = tokstart + m->S_cap;
-  int* offs = tokseq + m->Ntok_cap; int* nact = offs + m->T_cap + 1;
+  int *lens = I.host<int>(I.o_lens), *rank = I.host<int>(I.o_rank), *tokstart = I.host<int>(I.o_tokstart),
+      *tokseq = I.host<int>(I.o_tokseq), *offs = I.host<int>(I.o_off), *nact = I.host<int>(I.o_nact);
+  float* const h_x = I.host<float>(I.o_x);
   long ntok = 0; int tmax = 0;
   for (int s = 0; s < S; s++) {
     double l = read_num(b->seq_lengths, b->len_dtype, s);
@@ -555,7 +642,8 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
   size_t esz = b->sent_dtype == ICL_F64 ? 8 : 4;
   if (b->sent_dtype != ICL_F32 && b->sent_dtype != ICL_F64) return fail("icl_upload: sentences must be float32/float64");
   // pack + convert on several host threads, in chunks, so the H2D copy of chunk i overlaps the packing of chunk i+1
-  cudaStream_t st = m->stream;
+  cudaStream_t st = m->copy;
+  CK(cudaEventRecord(I.ev_c0, st));
   {
     const int n_chunks = ntok * (long)E * 4 > (4 << 20) ? 8 : 1;
     int s0 = 0;
@@ -568,23 +656,18 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
       host_pool().run(items, [&, s0, s1](int it) {
         for (int s = s0 + it * per; s < std::min(s1, s0 + (it + 1) * per); s++) {
           const char* src = (const char*)b->sentences + (b->sent_packed ? (size_t)tokstart[s] * E : (size_t)s * T * E) * esz;
-          to_f32(m->h_x + (size_t)tokstart[s] * E, src, b->sent_dtype, (size_t)lens[s] * E);
+          to_f32(h_x + (size_t)tokstart[s] * E, src, b->sent_dtype, (size_t)lens[s] * E);
           for (int t = 0; t < lens[s]; t++) tokseq[tokstart[s] + t] = s;
         }
       });
       const long t0 = tokstart[s0], t1 = (long)tokstart[s1 - 1] + lens[s1 - 1];
-      if (t1 > t0) H2D(m->xraw + t0 * E, m->h_x + t0 * E, (size_t)(t1 - t0) * E * 4, st);
+      if (t1 > t0) H2D(m->xraw + t0 * E, h_x + t0 * E, (size_t)(t1 - t0) * E * 4, st);
       s0 = s1;
     }
   }
-  H2D(m->d_lens, lens, (size_t)S * 4, st);
-  H2D(m->d_rank, rank, (size_t)S * 4, st);
-  H2D(m->d_tokstart, tokstart, (size_t)S * 4, st);
-  H2D(m->d_tokseq, tokseq, (size_t)ntok * 4, st);
-  H2D(m->d_off, offs, (size_t)(tmax + 1) * 4, st);
-  H2D(m->d_nact, nact, (size_t)(tmax + 1) * 4, st);
   for (int hi = 0; hi < b->n_heads; hi++) {
     Head& h = m->heads[hi];
+    HeadIn& hin = h.in[set];
     const icl_head_batch& hb = b->heads[hi];
     int B = h.c.batch_size, C = h.c.n_classes;
     h.active = !hb.inactive;
@@ -593,7 +676,7 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
       int id = h.slot_index_id[sl];
       if (id < 0) continue;
       if (!hb.idx[id]) return fail("icl_upload: head %d is missing index matrix %d", hi, id);
-      int* dst = h.h_idx + (size_t)id * B * 3;
+      int* dst = I.host<int>(hin.idx[id]);
       for (int r = 0; r < B; r++) {
         double d = read_num(hb.idx[id], hb.idx_dtype, r * 3), sq = read_num(hb.idx[id], hb.idx_dtype, r * 3 + 1) + hb.sent_offset,
                w = read_num(hb.idx[id], hb.idx_dtype, r * 3 + 2);
@@ -602,24 +685,23 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
           return fail("icl_upload: head %d index matrix %d row %d = [%g,%g,%g] out of range (S=%d,T=%d)", hi, id, r, d, sq, w, S, T);
         dst[r * 3] = (int)d; dst[r * 3 + 1] = (int)sq; dst[r * 3 + 2] = (int)w;
       }
-      H2D(h.idx[id], dst, (size_t)B * 3 * 4, st);
     }
-    float* hd = h.h_dense;
-    auto up = [&](const void* src, int dt, float* dev, size_t n, const char* what) -> int {
+    auto up = [&](const void* src, int dt, size_t off, size_t n, const char* what) -> int {
       if (n == 0) return 0;
       if (!src) return fail("icl_upload: head %d is missing %s", hi, what);
-      to_f32(hd, src, dt, n);
-      cudaError_t e = cudaMemcpyAsync(dev, hd, n * 4, cudaMemcpyHostToDevice, st);
-      m->h2d_bytes += (int64_t)n * 4;
-      hd += n;
-      return e == cudaSuccess ? 0 : fail("icl_upload: copy of %s failed: %s", what, cudaGetErrorString(e));
+      to_f32(I.host<float>(off), src, dt, n);
+      return 0;
     };
-    CKI(up(hb.feats, hb.feats_dtype, h.feats, (size_t)B * h.c.n_feats, "m_feats/ij_feats"));
-    CKI(up(hb.box, hb.box_dtype, h.box, (size_t)B * h.c.box_width, "box_embeddings"));
-    CKI(up(hb.bfeats, hb.bfeats_dtype, h.bfeats, (size_t)B * h.c.n_box_feats, "b_feats"));
+    CKI(up(hb.feats, hb.feats_dtype, hin.feats, (size_t)B * h.c.n_feats, "m_feats/ij_feats"));
+    CKI(up(hb.box, hb.box_dtype, hin.box, (size_t)B * h.c.box_width, "box_embeddings"));
+    CKI(up(hb.bfeats, hb.bfeats_dtype, hin.bfeats, (size_t)B * h.c.n_box_feats, "b_feats"));
     h.has_labels = hb.labels != nullptr;
-    if (h.has_labels) CKI(up(hb.labels, hb.labels_dtype, h.labels, (size_t)B * C, "labels"));
+    if (h.has_labels) CKI(up(hb.labels, hb.labels_dtype, hin.labels, (size_t)B * C, "labels"));
   }
+  // everything but the sentence rows: ONE copy of the meta region (the token->sequence map is last: only its used prefix)
+  H2D(I.d_blob + I.meta_off, I.h_blob + I.meta_off, I.o_tokseq - I.meta_off + (size_t)ntok * 4, st);
+  CK(cudaEventRecord(I.ev_copied, st));
+  I.copied_pending = true;
   m->S = S; m->Tmax = tmax; m->Ntok = ntok; m->NtokP = m->off[tmax];
   m->seq_gid0 = b->seq_gid_offset; m->ex_gid0 = b->ex_gid_offset;
   m->resident = true;
@@ -677,7 +759,7 @@ static int rec_forward_persistent(icl_model* m, int training) {
     }
     m->wp_dirty = false;
   }
-  CK(cudaMemsetAsync(m->rp_flags, 0, (size_t)2 * m->rp_max_tiles * 4, st));
+  CK(zero_async(m->rp_flags, (size_t)2 * m->rp_max_tiles * 4, st));
   RecArgs a = rec_args(m, training);
   void* args[] = {(void*)&m->rp_fmaps, (void*)&a};
   dim3 grid(2 * a.P * a.nsl), block(RP_FWD_THREADS);
@@ -701,7 +783,7 @@ static int lstm_forward(icl_model* m, float keep_in, uint64_t seed, int training
   for (int d = 0; d < 2; d++) {
     k_zero_pad_rows<<<m->Tmax, 256, 0, st>>>(m->XH[d], mk_layout(m), m->ldx); LAUNCHED(m);
     // h_prev of step 0 is the zero state: step 0's block of Hp stays zero (these are A rows of dW_hh)
-    CK(cudaMemset2DAsync(m->Hp[d], (size_t)m->ldx * 4, 0, (size_t)H * 4, (size_t)m->off[1], st));
+    k_zero_2d<<<148, 256, 0, st>>>(m->Hp[d], m->ldx, H, m->off[1]); LAUNCHED(m);
   }
   PH_END(m, PH_PREP);
   // K1: time-batched input projection  Z = Xd * W_ih + b   (W_ih = kernel rows [0,E)), both directions
@@ -782,7 +864,7 @@ static int heads_forward(icl_model* m, float keep, uint64_t seed) {
 }
 
 static int colsum(icl_model* m, cudaStream_t st, const float* X, long rows, int N, long ld, float* out) {
-  CK(cudaMemsetAsync(out, 0, (size_t)N * 4, st));
+  CK(zero_async(out, (size_t)N * 4, st));
   int rpb = 64;
   dim3 grid((N + 127) / 128, (unsigned)((rows + rpb - 1) / rpb));
   k_colsum_atomic<<<grid, 128, 0, st>>>(X, rows, N, ld, out, rpb);
@@ -794,14 +876,14 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
   cudaStream_t st = m->stream;
   int H = m->H;
   PH_BEGIN(m, PH_HEADS_BWD);
-  for (int d = 0; d < 2; d++) CK(cudaMemsetAsync(m->dHout[d], 0, (size_t)m->NtokP * H * 4, st));
+  for (int d = 0; d < 2; d++) CK(zero_async(m->dHout[d], (size_t)m->NtokP * H * 4, st));
   for (size_t hi = 0; hi < m->heads.size(); hi++) {
     Head& h = m->heads[hi];
     if (!h.active) {                          // not fed in this call: its parameters get a zero gradient
       for (size_t k = 0; k < h.pW.size(); k++) {
         const Param &pw = m->params[h.pW[k]], &pb = m->params[h.pB[k]];
-        CK(cudaMemsetAsync(m->G + pw.off, 0, (size_t)pw.rows * pw.cols * 4, st));
-        CK(cudaMemsetAsync(m->G + pb.off, 0, (size_t)pb.rows * pb.cols * 4, st));
+        CK(zero_async(m->G + pw.off, (size_t)pw.rows * pw.cols * 4, st));
+        CK(zero_async(m->G + pb.off, (size_t)pb.rows * pb.cols * 4, st));
       }
       continue;
     }
@@ -845,10 +927,10 @@ static int rec_backward_persistent(icl_model* m) {
   const int H = m->H, S = m->S;
   cudaStream_t st = m->stream;
   for (int d = 0; d < 2; d++) {
-    CK(cudaMemsetAsync(m->dhrec[d], 0, (size_t)S * H * 4, st));
-    CK(cudaMemsetAsync(m->dcc[d], 0, (size_t)S * H * 4, st));
+    CK(zero_async(m->dhrec[d], (size_t)S * H * 4, st));
+    CK(zero_async(m->dcc[d], (size_t)S * H * 4, st));
   }
-  CK(cudaMemsetAsync(m->rp_bar, 0, 4, st));
+  CK(zero_async(m->rp_bar, 4, st));
   RecBwdArgs a;
   a.off = m->d_off; a.nact = m->d_nact; a.Tmax = m->Tmax; a.H = H; a.round_ops = m->round_ops; a.bar = m->rp_bar;
   a.trace = m->rp_trace; a.trace_cta = m->rp_trace_cta;
@@ -865,7 +947,7 @@ static int rec_backward_persistent(icl_model* m) {
 static int rec_backward_fused(icl_model* m) {
   const int H = m->H, S = m->S, cs = m->bp_cs;
   cudaStream_t st = m->stream;
-  for (int d = 0; d < 2; d++) CK(cudaMemsetAsync(m->dcc[d], 0, (size_t)S * H * 4, st));
+  for (int d = 0; d < 2; d++) CK(zero_async(m->dcc[d], (size_t)S * H * 4, st));
   const int Nt = (H + BP_BN - 1) / BP_BN;
   for (int k = m->Tmax - 1; k >= 0; k--) {
     BpttArgs a;
@@ -899,8 +981,8 @@ static int rec_backward_steps(icl_model* m) {
   CK(cudaStreamWaitEvent(m->aux, m->ev_fork, 0));
   for (int d = 0; d < 2; d++) {
     cudaStream_t sd = d ? m->aux : st;
-    CK(cudaMemsetAsync(m->dhrec[d], 0, (size_t)S * H * 4, sd));
-    CK(cudaMemsetAsync(m->dcc[d], 0, (size_t)S * H * 4, sd));
+    CK(zero_async(m->dhrec[d], (size_t)S * H * 4, sd));
+    CK(zero_async(m->dcc[d], (size_t)S * H * 4, sd));
   }
   for (int k = m->Tmax - 1; k >= 0; k--) {
     for (int d = 0; d < 2; d++) {        // directions interleaved on two streams so the host feeds both concurrently
@@ -986,6 +1068,9 @@ extern "C" int icl_run_resident(icl_model* m, int op, float keep_in, float keep,
   if (!m->resident) return fail("icl_run_resident: no batch uploaded");
   if (!(keep_in > 0 && keep_in <= 1 && keep > 0 && keep <= 1)) return fail("keep probabilities must be in (0,1]");
   for (int i = 0; i < PH_N; i++) m->ph_used[i] = false;
+  InSet& I = m->in[m->cur];
+  CK(cudaStreamWaitEvent(m->stream, I.ev_copied, 0));          // the batch's H2D copies (copy stream) have landed
+  CK(cudaEventRecord(I.ev_s0, m->stream));
   CK(cudaEventRecord(m->ev_t0, m->stream));
   CKI(refresh_rounded_params(m));
   CKI(lstm_forward(m, keep_in, seed, op >= ICL_OP_GRADS));
@@ -996,7 +1081,52 @@ extern "C" int icl_run_resident(icl_model* m, int op, float keep_in, float keep,
   }
   if (op == ICL_OP_TRAIN) CKI(icl_apply_update(m));
   CK(cudaEventRecord(m->ev_t1, m->stream));
+  CK(cudaEventRecord(I.ev_done, m->stream));                   // this set's device buffers may be overwritten after this point
+  I.done_pending = true;
   return 0;
+}
+
+// Asynchronous read-back of the step's scalars: enqueues a D2H copy of (loss, accuracy) of every head of the step just issued
+// and hands out the scalars of the PREVIOUS call (NaN when there is none) -- the host never waits for the step in flight.
+extern "C" int icl_poll_stats(icl_model* m, icl_head_out* prev) {
+  if (m->cur < 0) return fail("icl_poll_stats: no batch uploaded");
+  InSet& I = m->in[m->cur];
+  float* hs = m->h_stats + (size_t)m->cur * ICL_MAX_HEADS * 2;
+  m->d2h_bytes = 0;
+  for (size_t hi = 0; hi < m->heads.size(); hi++) {
+    CK(cudaMemcpyAsync(hs + hi * 2, m->heads[hi].scalars, 8, cudaMemcpyDeviceToHost, m->stream));
+    m->d2h_bytes += 8;
+  }
+  CK(cudaEventRecord(I.ev_stats, m->stream));
+  I.stats_pending = true;
+  InSet& Pv = m->in[m->cur ^ 1];
+  const float* ps = m->h_stats + (size_t)(m->cur ^ 1) * ICL_MAX_HEADS * 2;
+  const bool have = Pv.stats_pending;
+  if (have) { CK(cudaEventSynchronize(Pv.ev_stats)); Pv.stats_pending = false; }
+  for (size_t hi = 0; hi < m->heads.size() && prev; hi++) {
+    prev[hi].loss = have ? ps[hi * 2] : NAN;
+    prev[hi].accuracy = have ? ps[hi * 2 + 1] : NAN;
+  }
+  return 0;
+}
+
+// bring-up: device timeline of the two most recent pipelined steps, ms relative to the older step's first copy:
+// out[0..3] = older {copy start, copy end, compute start, compute end}, out[4..7] = newer.  Synchronises.
+extern "C" int icl_debug_timeline(icl_model* m, float* out) {
+  CK(cudaDeviceSynchronize());
+  if (m->cur < 0) return fail("no batch");
+  InSet &A = m->in[m->cur ^ 1], &B = m->in[m->cur];
+  cudaEvent_t ev[8] = {A.ev_c0, A.ev_copied, A.ev_s0, A.ev_done, B.ev_c0, B.ev_copied, B.ev_s0, B.ev_done};
+  for (int i = 0; i < 8; i++) if (cudaEventElapsedTime(&out[i], A.ev_c0, ev[i]) != cudaSuccess) { out[i] = NAN; cudaGetLastError(); }
+  return 0;
+}
+
+// One pipelined train step: upload (copy stream, double-buffered) + forward/BPTT/update on the compute stream + icl_poll_stats.
+// Returns as soon as the work is enqueued; errors of the device work surface at the next synchronising call.
+extern "C" int icl_train_async(icl_model* m, const icl_batch* b, float keep_in, float keep, uint64_t seed, icl_head_out* prev) {
+  CKI(icl_upload(m, b));
+  CKI(icl_run_resident(m, ICL_OP_TRAIN, keep_in, keep, seed));
+  return icl_poll_stats(m, prev);
 }
 
 extern "C" int icl_fetch(icl_model* m, icl_head_out* out) {

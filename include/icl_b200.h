@@ -113,6 +113,13 @@ int icl_run(icl_model* m, int op, const icl_batch* b, float keep_in, float keep,
 int icl_upload(icl_model* m, const icl_batch* b);
 int icl_run_resident(icl_model* m, int op, float keep_in, float keep, uint64_t seed);
 int icl_fetch(icl_model* m, icl_head_out* out);
+/* pipelined training (the reference's loop calls run_op(train_op) per batch and discards the result, icl_core_lstm.py:138-150):
+   inputs are double-buffered, icl_upload copies on its own stream while the previous step still computes, and
+   icl_train_async returns once the step is enqueued.  `prev` (may be NULL) receives loss / accuracy of the PREVIOUS
+   icl_poll_stats / icl_train_async call (NaN when there is none); icl_poll_stats is the read-back half for callers that
+   compose upload / run_resident / all-reduce / apply_update themselves (data parallel). */
+int icl_train_async(icl_model* m, const icl_batch* b, float keep_in, float keep, uint64_t seed, icl_head_out* prev);
+int icl_poll_stats(icl_model* m, icl_head_out* prev);
 /* data-parallel: flat fp32 gradient buffer on the device (all-reduce SUM it), then apply clip + Adam */
 int icl_grad_buffer(icl_model* m, void** dev_ptr, int64_t* n_floats);
 int icl_param_buffer(icl_model* m, void** dev_ptr, int64_t* n_floats);

@@ -316,19 +316,57 @@ def test_multitask_shared_encoder_matches_oracle(mode, H):
     sess.close()
 
 
-def test_persistent_backward_kernel_matches_per_step_path(monkeypatch):
-    """k_rec_bwd (opt-in: ICL_PERSISTENT_BWD=1; one cooperative launch for the whole BPTT recurrence) against the default
-    per-step path on the same batch: same gradients up to split-K summation order (a different fp32 summation order can
-    move a dZ element across a TF32 rounding boundary, 2^-11 relative, before it enters the next step: 5e-4)."""
+def test_backward_recurrence_variants_agree(monkeypatch):
+    """The BPTT recurrence has three implementations: the fused per-step kernel k_bptt_step (default; cluster split-K over
+    1, 2 or 4 CTAs reduced through distributed shared memory), the per-step cell + split-K GEMM pair (ICL_BPTT_FUSED=0) and
+    the opt-in cooperative k_rec_bwd (ICL_PERSISTENT_BWD=1).  Same batch, same masks: same gradients up to fp32 summation
+    order (which can move a dZ element across a TF32 rounding boundary, 2^-11 relative, before the next step: 5e-4)."""
     from imagecaptionlearn_py_b200 import _cabi
     p = tiny_problem(seed=27, dropout=True, **CASES[5])
     grads = {}
-    for flag in ("0", "1"):
-        monkeypatch.setenv("ICL_PERSISTENT_BWD", flag)
+    variants = {"steps": dict(ICL_BPTT_FUSED="0", ICL_PERSISTENT_BWD="0"), "coop": dict(ICL_BPTT_FUSED="0", ICL_PERSISTENT_BWD="1"),
+                "fused4": dict(ICL_BPTT_FUSED="1", ICL_BPTT_CS="4"), "fused2": dict(ICL_BPTT_FUSED="1", ICL_BPTT_CS="2"),
+                "fused1": dict(ICL_BPTT_FUSED="1", ICL_BPTT_CS="1")}
+    for name, env in variants.items():
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
         core, sess = make_session(p, "tf32")
         sess.base_seed, sess.run_counter = 77, 0
         sess.run(_cabi.OP_GRADS, [dict(p["batch"])], p["keep_in"], p["keep"], True)
-        grads[flag] = {k: sess.get_tensor(k, 1) for k in p["params"]}
+        grads[name] = {k: sess.get_tensor(k, 1) for k in p["params"]}
         sess.close()
-    for k in grads["0"]:
-        assert relerr(grads["1"][k], grads["0"][k]) < 5e-4, k
+    for name in variants:
+        for k in grads["steps"]:
+            assert relerr(grads[name][k], grads["steps"][k]) < 5e-4, (name, k)
+
+
+def test_pipelined_train_op_matches_synchronous_steps(monkeypatch):
+    """run_op(train_op) is pipelined (double-buffered inputs, copy stream, no host wait: icl_train_async).  Four steps over
+    two alternating batches must leave the same parameters as the synchronous icl_run path with the same seeds, and
+    `last_train_stats` must report the previous step's loss."""
+    from imagecaptionlearn_py_b200 import _cabi, core as core_mod
+    pa = tiny_problem(seed=31, dropout=True, **CASES[1])
+    pb = tiny_problem(seed=32, dropout=True, **CASES[1])
+    hc = pa["cfg"]["heads"][0]
+    out = {}
+    for mode in ("sync", "async"):
+        core, sess = make_session(pa, "tf32")
+        sess.base_seed, sess.run_counter = 5, 0
+        losses = []
+        for step in range(4):
+            bt = dict((pa if step % 2 == 0 else pb)["batch"])
+            if mode == "sync":
+                losses.append(float(sess.run(_cabi.OP_TRAIN, [bt], pa["keep_in"], pa["keep"], True)[0]["loss"]))
+            else:
+                r = core.run_op(sess, core.get_collection("train_op")[0], [bt], pa["keep_in"], pa["keep"], hc["encoding_scheme"],
+                                [hc["task"]], [""], True)
+                assert r is None
+                losses.append(float(sess.last_train_stats[0]["loss"]))
+        out[mode] = ({k: sess.get_tensor(k) for k in pa["params"]}, losses)
+        sess.close()
+    assert np.isnan(out["async"][1][0])                                   # no previous step yet
+    for a, b in zip(out["async"][1][1:], out["sync"][1][:-1]):             # async reports the PREVIOUS step's loss
+        assert abs(a - b) <= 1e-4 * max(1.0, abs(b)), (out["async"][1], out["sync"][1])
+    for k in pa["params"]:
+        # same kernels, same seeds; only the red.global order of the split-K weight-gradient GEMMs may differ
+        assert np.max(np.abs(out["async"][0][k] - out["sync"][0][k])) <= 2e-3 * 4e-3 + 1e-6, k
