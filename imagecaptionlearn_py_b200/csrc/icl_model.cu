@@ -132,7 +132,7 @@ struct icl_model {
   unsigned* rp_bar = nullptr;
   bool rp_bwd_on = false;       // k_rec_bwd is correct but measured slower (0.84 ms) than the per-step path (0.56 ms): opt-in
   // fused BPTT step kernel (lstm_bptt.cuh): default backward recurrence in tensor-core mode
-  bool bp_on = false;
+  bool bp_on = false, bp_cluster = true;     // bp_cluster: k_bptt_cluster (whole recurrence in one launch) when H <= 336
   int bp_cs = 4;
   BpttMaps bp_maps;
   int n_sms = 148;
@@ -360,6 +360,8 @@ static int bptt_init(icl_model* m) {
   m->bp_on = m->cfg.gemm_mode == ICL_GEMM_TCGEN05_TF32;
   if (const char* e = getenv("ICL_BPTT_FUSED")) m->bp_on = m->bp_on && atoi(e) != 0;
   if (const char* e = getenv("ICL_BPTT_CS")) { int c = atoi(e); if (c == 1 || c == 2 || c == 4) m->bp_cs = c; }
+  if (const char* e = getenv("ICL_BPTT_MODE")) m->bp_cluster = strcmp(e, "step") != 0;
+  if (m->H > BC_NACC * BP_BN) m->bp_cluster = false;
   if (!m->bp_on) return 0;
   const int H = m->H, SW128 = (int)CU_TENSOR_MAP_SWIZZLE_128B;
   for (int d = 0; d < 2; d++) {
@@ -371,6 +373,8 @@ static int bptt_init(icl_model* m) {
       cudaFuncSetAttribute(k_bptt_step<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(k_bptt_step<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM) != cudaSuccess)
     return fail("cudaFuncSetAttribute(k_bptt_step) failed");
+  if (cudaFuncSetAttribute(k_bptt_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM) != cudaSuccess)
+    return fail("cudaFuncSetAttribute(k_bptt_cluster) failed");
   return 0;
 }
 
@@ -973,6 +977,28 @@ static int rec_backward_fused(icl_model* m) {
   return 0;
 }
 
+// K3 (default in tensor-core mode, H <= 336): the whole backward recurrence in ONE launch, a cluster of 4 CTAs per
+// (direction, 128-row tile) walking all of the tile's time steps with cluster barriers only (lstm_bptt.cuh)
+static int rec_backward_cluster(icl_model* m) {
+  const int H = m->H, S = m->S;
+  cudaStream_t st = m->stream;
+  for (int d = 0; d < 2; d++) CK(zero_async(m->dcc[d], (size_t)S * H * 4, st));
+  BpttClusterArgs a;
+  for (int d = 0; d < 2; d++) { a.Z[d] = m->Z[d]; a.Cc[d] = m->Cc[d]; a.dHout[d] = m->dHout[d]; a.dcc[d] = m->dcc[d]; }
+  a.off = m->d_off; a.nact = m->d_nact; a.H = H; a.Tmax = m->Tmax; a.round_ops = m->round_ops;
+  a.trace = m->rp_trace; a.trace_cta = m->rp_trace_cta;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(BC_CS, (unsigned)((m->n_active[0] + 127) / 128), 2);
+  cfg.blockDim = dim3(BC_THREADS); cfg.dynamicSmemBytes = BC_SMEM; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = BC_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_bptt_cluster, m->bp_maps, a);
+  if (e != cudaSuccess) return fail("k_bptt_cluster launch failed: %s", cudaGetErrorString(e));
+  m->launches++;
+  return 0;
+}
+
 // K3 (fp32 validation mode): one cell kernel + one split-K GEMM per step and direction, directions interleaved on two streams
 static int rec_backward_steps(icl_model* m) {
   const int E = m->E, H = m->H, S = m->S;
@@ -1022,7 +1048,8 @@ static int lstm_backward(icl_model* m) {
   cudaStream_t st = m->stream;
   if (m->Ntok == 0) return 0;
   PH_BEGIN(m, PH_REC_BWD);
-  if (m->bp_on) CKI(rec_backward_fused(m));                // writes the pad rows of dZ as zeros itself
+  if (m->bp_on && m->bp_cluster && m->Tmax <= RP_MAXT) CKI(rec_backward_cluster(m));   // both write the pad rows of dZ as zeros
+  else if (m->bp_on) CKI(rec_backward_fused(m));
   else {
     if (m->rp_U != 0 && m->rp_on && m->rp_bwd_on && m->Tmax <= RP_MAXT) CKI(rec_backward_persistent(m));
     else CKI(rec_backward_steps(m));

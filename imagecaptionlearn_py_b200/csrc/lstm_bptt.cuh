@@ -247,4 +247,249 @@ __global__ void __launch_bounds__(BP_THREADS, 2) k_bptt_step(const __grid_consta
   if (has_mma) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");      // nobody still reads my parked partial
 }
 
+
+// =====================================================================================================================
+// k_bptt_cluster: the WHOLE backward recurrence in one launch, one thread-block cluster per (direction, 128-row tile).
+//
+// dZ_k of a row tile depends only on dZ_{k+1} of the SAME rows, so a cluster that owns a row tile can walk all of its time
+// steps with nothing but cluster barriers -- no grid barrier, no flags in global memory, no launch per step.  Per step:
+//   K-loop   : the cluster's 4 CTAs split the contraction (K = 4H) into k-block ranges; per k-block one TMA box of dZ_{k+1}
+//              [128 x 32] and three boxes of W_hh [112 units x 32] feed UMMAs into THREE TMEM accumulators (all H <= 336 units
+//              of the tile: dZ is read once, not once per 112-unit column tile as in k_bptt_step);
+//   park     : TMEM -> the CTA's own (idle) operand ring as a [128 x 340] fp32 tile;             cluster barrier S1
+//   pull     : every CTA finishes 32 rows: it sums the 4 partials of its rows with coalesced ld.shared::cluster
+//              (barrier S2 = "my pulls are done", waited for before the ring is refilled);
+//   cell bwd : gates/c/dH rows (L2-prefetched one step ahead) -> dZ_k in place, dc carry;  fence.proxy.async + barrier S3
+//              make dZ_k visible to the TMA loads of step k-1 issued by the other CTAs of the cluster.
+// Clusters are independent: the launch needs no co-residency (a batch with more than 18 row tiles per direction simply
+// runs in waves).
+// =====================================================================================================================
+constexpr int BC_CS = 4, BC_NACC = 3, BC_STAGES = 3, BC_THREADS = 320;
+constexpr int BC_STAGE_BYTES = BP_A_BYTES + BC_NACC * BP_B_BYTES;          // 16 KB + 3 x 14 KB
+constexpr int BC_PARK_LD = BC_NACC * BP_BN + 4;                            // 340 floats per parked row
+constexpr int BC_SMEM = 1024 + BC_STAGES * BC_STAGE_BYTES + 128;
+static_assert(128 * BC_PARK_LD * 4 <= BC_STAGES * BC_STAGE_BYTES, "the parked tile reuses the operand ring");
+
+struct BpttClusterArgs {
+  float* Z[2]; const float* Cc[2]; const float* dHout[2]; float* dcc[2];
+  const int* off; const int* nact;       // [Tmax+1] step offsets / running rows
+  int H, Tmax, round_ops;
+  long long* trace; int trace_cta;      // optional bring-up trace (see Tracer): CTA index = (z * gridDim.y + y) * gridDim.x + x
+};
+
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(BC_THREADS, 1) k_bptt_cluster(const __grid_constant__ BpttMaps maps, const BpttClusterArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ int s_off[RP_MAXT + 2], s_n[RP_MAXT + 2];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + BC_STAGES * BC_STAGE_BYTES;
+  const uint32_t full0 = bars, empty0 = bars + 8 * BC_STAGES, tmem_full = bars + 16 * BC_STAGES, tmem_slot = tmem_full + 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = g.H, Tmax = g.Tmax, HQ = H >> 2;
+  const int rank = (int)cluster_ctarank();
+  const int m0 = blockIdx.y * 128, d = blockIdx.z;
+  const int total_kb = (4 * H + 31) / 32, kb_per = (total_kb + BC_CS - 1) / BC_CS;
+  const int kb0 = rank * kb_per, num_kb = max(0, min(kb_per, total_kb - kb0));
+  const int nacc = (H + BP_BN - 1) / BP_BN;                                   // accumulators in use (<= BC_NACC)
+  constexpr int ROWS_OWN = 128 / BC_CS;
+
+  for (int i = threadIdx.x; i <= Tmax; i += blockDim.x) { s_off[i] = g.off[i]; s_n[i] = g.nact[i]; }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < BC_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.za[d]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.wb[d]) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_acc;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot));
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  float* const Zd = g.Z[d];
+  const float* const Cd = g.Cc[d];
+  const float* const dHd = g.dHout[d];
+  float* const dcc = g.dcc[d];
+  const int n_items = ROWS_OWN * HQ;                    // (row of my 32 rows, group of 4 hidden units)
+  uint32_t it = 0, nfull = 0;                           // running k-block / accumulator-phase counters (mbarrier parities)
+
+  Tracer tr;
+  {
+    const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    tr.p = (g.trace && cta == g.trace_cta && lane == 0 && warp <= 2) ? g.trace + (long)warp * RP_TRACE_EV * 4 : nullptr;
+    tr.n = 0;
+  }
+  // first step in which this tile has running rows (n_k grows as k decreases)
+  int k_first = -1;
+  for (int k = Tmax - 1; k >= 0; k--) if (m0 < s_n[k]) { k_first = k; break; }
+
+  // L2 prefetch of the cell-backward operands of step k for my rows (one row per lane of warp 2)
+  auto prefetch_step = [&](int k) {
+    if (warp != 2 || k < 0) return;
+    const int grow = m0 + rank * ROWS_OWN + lane;
+    if (grow >= s_n[k]) return;
+    prefetch_l2_bulk(Zd + ((long)s_off[k] + grow) * 4 * H, (uint32_t)(4 * H * 4));
+    prefetch_l2_bulk(dHd + ((long)s_off[k] + grow) * H, (uint32_t)(H * 4));
+    if (k > 0) prefetch_l2_bulk(Cd + ((long)s_off[k - 1] + grow) * H, (uint32_t)(H * 4));
+    if (k == k_first) prefetch_l2_bulk(Cd + ((long)s_off[k] + grow) * H, (uint32_t)(H * 4));
+  };
+  prefetch_step(k_first);
+
+  for (int k = k_first; k >= 0; k--) {
+    const int n_k = s_n[k], n_kp1 = k + 1 < Tmax ? s_n[k + 1] : 0;
+    const long o_k = s_off[k];
+    const bool has_mma = m0 < n_kp1;                  // uniform over the cluster
+    prefetch_step(k - 1);
+    tr.ev(0, k, 0);
+    if (has_mma) {
+      if (warp == 0) {
+        if (lane == 0) {                                               // ---- TMA producer
+          for (int kb = 0; kb < num_kb; kb++, it++) {
+            const int s = it % BC_STAGES;
+            mbar_wait(empty0 + 8 * s, ((it / BC_STAGES) & 1) ^ 1);
+            const uint32_t fb = full0 + 8 * s, st = base + s * BC_STAGE_BYTES;
+            mbar_expect_tx(fb, BP_A_BYTES + nacc * BP_B_BYTES);
+            tma_load_2d(st, &maps.za[d], (kb0 + kb) * 32, s_off[k + 1] + m0, fb);
+            for (int a = 0; a < nacc; a++) tma_load_2d(st + BP_A_BYTES + a * BP_B_BYTES, &maps.wb[d], (kb0 + kb) * 32, a * BP_BN, fb);
+          }
+        }
+        __syncwarp();
+      } else if (warp == 1) {
+        if (lane == 0) {                                               // ---- MMA issuer
+          constexpr uint32_t idesc = make_idesc(2, false, false, 128, BP_BN);
+          for (int kb = 0; kb < num_kb; kb++, it++) {
+            const int s = it % BC_STAGES;
+            mbar_wait(full0 + 8 * s, (it / BC_STAGES) & 1);
+            tc_fence_after();
+            const uint32_t a = base + s * BC_STAGE_BYTES;
+            for (int ac = 0; ac < nacc; ac++) {
+              const uint32_t b = a + BP_A_BYTES + ac * BP_B_BYTES;
+#pragma unroll
+              for (int kk = 0; kk < 4; kk++)
+                tc_mma_tf32(tmem_acc + ac * 128, make_smem_desc(a + kk * 32, 16, 1024), make_smem_desc(b + kk * 32, 16, 1024), idesc,
+                            (kb | kk) != 0);
+            }
+            tc_commit(empty0 + 8 * s);
+          }
+          if (num_kb > 0) tc_commit(tmem_full);
+        }
+        __syncwarp();
+      } else {
+        // park my partial [128 rows][BC_PARK_LD] in my own operand ring (idle once my MMAs have retired)
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const uint32_t dst = base + (uint32_t)((q * 32 + lane) * BC_PARK_LD) * 4;
+        if (num_kb > 0) { mbar_wait(tmem_full, nfull & 1); tc_fence_after(); }
+        tr.ev(1, k, 0);
+        for (int ac = 0; ac < nacc; ac++) {
+#pragma unroll 1
+          for (int c = half * 32; c < BP_BN; c += 64) {
+            uint32_t r[32];
+            if (num_kb > 0) tc_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + ac * 128 + c, r);
+            else {
+#pragma unroll
+              for (int j = 0; j < 32; j++) r[j] = 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (c + j < BP_BN)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)(ac * BP_BN + c + j) * 4), "r"(r[j]),
+                             "r"(r[j + 1]), "r"(r[j + 2]), "r"(r[j + 3]) : "memory");
+          }
+        }
+        tc_fence_before();
+        tr.ev(2, k, 0);
+      }
+      nfull++;
+      cluster_arrive(); cluster_wait();                                // S1: every partial of the tile is parked
+      tr.ev(3, k, 0);
+    }
+
+    // ---- pull + cell backward, all threads; items in batches of 2
+#pragma unroll 1
+    for (int i0 = threadIdx.x; i0 < n_items; i0 += 2 * BC_THREADS) {
+      float4 g4[2][4], c4[2], cp4[2], dh4[2], dc4[2], dhr[2];
+      int kind[2];                                                     // 0: nothing, 1: pad row (dZ = 0), 2: cell backward
+      long ro[2]; int uu[2];
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        const int item = i0 + b * BC_THREADS;
+        const int row = item / HQ, u = (item % HQ) * 4, grow = m0 + rank * ROWS_OWN + row;
+        kind[b] = item >= n_items ? 0 : grow >= n_k ? 1 : 2;
+        ro[b] = grow; uu[b] = u;
+        if (kind[b] == 2) {
+          const float* z = Zd + (o_k + grow) * 4 * H + u;
+#pragma unroll
+          for (int a = 0; a < 4; a++) g4[b][a] = *reinterpret_cast<const float4*>(z + a * H);
+          c4[b] = *reinterpret_cast<const float4*>(Cd + (o_k + grow) * H + u);
+          cp4[b] = k > 0 ? *reinterpret_cast<const float4*>(Cd + ((long)s_off[k - 1] + grow) * H + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+          dh4[b] = *reinterpret_cast<const float4*>(dHd + (o_k + grow) * H + u);
+          dc4[b] = *reinterpret_cast<const float4*>(dcc + (long)grow * H + u);
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        dhr[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int item = i0 + b * BC_THREADS;
+        if (has_mma && item < n_items) {
+          const uint32_t la = base + (uint32_t)(((rank * ROWS_OWN + item / HQ) * BC_PARK_LD) + (item % HQ) * 4) * 4;
+          float4 p[BC_CS];
+#pragma unroll
+          for (int s = 0; s < BC_CS; s++) p[s] = ld_cluster_f4(mapa_shared(la, (uint32_t)s));
+#pragma unroll
+          for (int s = 0; s < BC_CS; s++) { dhr[b].x += p[s].x; dhr[b].y += p[s].y; dhr[b].z += p[s].z; dhr[b].w += p[s].w; }
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        if (kind[b] == 0) continue;
+        float* z = Zd + (o_k + ro[b]) * 4 * H + uu[b];
+        if (kind[b] == 1) {
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(z) = z4; *reinterpret_cast<float4*>(z + H) = z4;
+          *reinterpret_cast<float4*>(z + 2 * H) = z4; *reinterpret_cast<float4*>(z + 3 * H) = z4;
+          continue;
+        }
+        if (ro[b] < n_kp1) { dh4[b].x += dhr[b].x; dh4[b].y += dhr[b].y; dh4[b].z += dhr[b].z; dh4[b].w += dhr[b].w; }
+        const float *si = &g4[b][0].x, *tj = &g4[b][1].x, *sf = &g4[b][2].x, *so = &g4[b][3].x, *c = &c4[b].x, *cp = &cp4[b].x,
+                    *dh = &dh4[b].x, *dc = &dc4[b].x;
+        float di[4], dj[4], df[4], dgo[4], dcp[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const CellGrad cg_ = lstm_cell_bwd(si[j], tj[j], sf[j], so[j], c[j], cp[j], dh[j], dc[j]);
+          di[j] = maybe_round(cg_.di, g.round_ops); dj[j] = maybe_round(cg_.dj, g.round_ops); df[j] = maybe_round(cg_.df, g.round_ops);
+          dgo[j] = maybe_round(cg_.dg_o, g.round_ops); dcp[j] = cg_.dc_prev;
+        }
+        *reinterpret_cast<float4*>(z) = make_float4(di[0], di[1], di[2], di[3]);
+        *reinterpret_cast<float4*>(z + H) = make_float4(dj[0], dj[1], dj[2], dj[3]);
+        *reinterpret_cast<float4*>(z + 2 * H) = make_float4(df[0], df[1], df[2], df[3]);
+        *reinterpret_cast<float4*>(z + 3 * H) = make_float4(dgo[0], dgo[1], dgo[2], dgo[3]);
+        *reinterpret_cast<float4*>(dcc + ro[b] * H + uu[b]) = make_float4(dcp[0], dcp[1], dcp[2], dcp[3]);
+      }
+    }
+    tr.ev(4, k, 0);
+    if (k > 0) {
+      // S2/S3 merged: my pulls are done (the ring may be refilled) and my dZ_k rows are visible to the async proxy of every
+      // CTA of the cluster (their TMA loads of step k-1)
+      fence_async_all();
+      cluster_arrive(); cluster_wait();
+      tr.ev(5, k, 0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_acc) : "memory");
+  }
+  cluster_arrive(); cluster_wait();                                    // nobody still reads my parked tile
+}
+
 }  // namespace icl
