@@ -31,7 +31,7 @@ import numpy as np
 from . import _cabi
 from . import data as nn_data
 
-__all__ = ["set_random_seeds", "get_widths", "setup_bidirectional_lstm", "setup_core_architecture", "add_train_op",
+__all__ = ["set_random_seeds", "get_widths", "setup_bidirectional_lstm", "setup_core_architecture", "add_train_op", "setup_joint_loss",
            "run_op", "get_pred_scores_mcc", "get_collection", "variable_scope", "reset_default_graph", "Session",
            "Saver", "Op"]
 
@@ -49,6 +49,7 @@ class Graph(object):
         self.lstm = None            # dict(n_hidden, data_norm, E)
         self.heads = []             # list of dicts, in creation order
         self.train = {}             # scope -> dict(lr, eps, clip)
+        self.joint = None           # None / "simple_joint" / "weighted_joint" (setup_joint_loss)
         self.scope_stack = []
         self.seed = 20171201
 
@@ -122,8 +123,21 @@ def setup_core_architecture(task, encoding_scheme, batch_size, start_hidden_widt
                              n_box_feats=int(n_box_feats or 0) if task == "affinity" else 0, scope=_scope()))
 
 
+def setup_joint_loss(multitask_scheme):
+    """icl_multitask_lstm.py:248-255: the joint loss over all heads.  'simple_joint' = sum of the task losses;
+    'weighted_joint' = reduce_sum(setup_ffw(stack(losses)[None, :], [n_heads])): a trainable linear map (variables
+    'hdn_1/Variable' [n,n] and 'hdn_1/Variable_1' [1,n], Xavier-initialised like every other weight, core.py:22-71) applied to
+    the loss vector and summed, so d joint / d loss_t = sum_j W[t, j].  The n*n+n mixing variables live on the host (Session)."""
+    if multitask_scheme not in ("simple_joint", "weighted_joint"):
+        raise ValueError("unknown joint scheme %r" % (multitask_scheme,))
+    _graph.joint = multitask_scheme
+    return Op("loss", "")
+
+
 def add_train_op(loss, lrn_rate, adam_epsilon, clip_norm):
-    """core.py:74-106: Adam(lr, eps) with optional clip_by_global_norm.  One optimizer over all variables."""
+    """core.py:74-106: Adam(lr, eps) with optional clip_by_global_norm over all variables that have a gradient.  Every call
+    creates one optimizer = one slot of Adam state on the device (the `alternate` multitask scheme calls this once per task
+    under that task's variable_scope, icl_multitask_lstm.py:387-393); learn rate / epsilon / clip of the first call apply."""
     _graph.train[_scope()] = dict(lr=float(lrn_rate), eps=float(adam_epsilon),
                                   clip=-1.0 if clip_norm is None else float(clip_norm))
 
@@ -140,6 +154,8 @@ class Session(object):
         self.handle = None
         self.run_counter = 0
         self.last_train_stats = None
+        self._slot = 0
+        self.joint_vars = None          # weighted_joint: dict(W, b, mW, vW, mb, vb) on the host
         self.base_seed = self.graph.seed if seed is None else seed
         self._grad_view = None
 
@@ -195,6 +211,7 @@ class Session(object):
         h = C.c_void_p()
         _cabi.check(_cabi.lib().icl_create(C.byref(cfg), C.byref(h)))
         self.handle = h
+        self._slot = 0
         self._grad_view = None
         if state is None:
             self.initialize()
@@ -231,7 +248,71 @@ class Session(object):
                 v = rng.uniform(-lim, lim, (r, c)).astype(np.float32)
             self.set_tensor(name, v)
 
+    JOINT_NAMES = ("hdn_1/Variable", "hdn_1/Variable_1")
+
+    def _joint(self):
+        """Host-side variables of the weighted_joint loss mixer (created on first use, Xavier like core.py:32-36,59-63)."""
+        if self.joint_vars is None:
+            n = len(self.graph.heads)
+            rng = np.random.RandomState((self.graph.seed + 17) % (2 ** 32))
+            lw, lb = math.sqrt(6.0 / (n + n)), math.sqrt(6.0 / (1 + n))
+            self.joint_vars = dict(W=rng.uniform(-lw, lw, (n, n)).astype(np.float32), b=rng.uniform(-lb, lb, (1, n)).astype(np.float32),
+                                   mW=np.zeros((n, n), np.float32), vW=np.zeros((n, n), np.float32),
+                                   mb=np.zeros((1, n), np.float32), vb=np.zeros((1, n), np.float32))
+        return self.joint_vars
+
+    def train_weighted_joint(self, batch_tensor_list, keep_in, keep):
+        """One synchronous train step of the weighted_joint scheme: device gradients with per-head weights sum_j W[t,j], the
+        mixer's own gradients (dW[t,j] = loss_t, db_j = 1) take part in the global-norm clip and get the same TF-Adam step."""
+        L = _cabi.lib()
+        g = self.graph
+        jv = self._joint()
+        n = len(g.heads)
+        w = (C.c_float * n)(*[float(x) for x in jv["W"].sum(1)])
+        _cabi.check(L.icl_set_loss_weights(self.handle, w))
+        keepalive = []
+        b = self.build_batch(batch_tensor_list, True, keepalive)
+        self._bind_stream()
+        self.run_counter += 1
+        seed = (self.base_seed * 1000003 + self.run_counter) & 0xFFFFFFFFFFFFFFFF
+        self.last_seed = seed
+        outs = (_cabi.HeadOut * _cabi.MAX_HEADS)()
+        _cabi.check(L.icl_upload(self.handle, C.byref(b)))
+        _cabi.check(L.icl_run_resident(self.handle, _cabi.OP_GRADS, keep_in, keep, seed))
+        if self.dist:
+            import torch.distributed as td
+            td.all_reduce(self.grad_tensor(), op=td.ReduceOp.SUM)
+        _cabi.check(L.icl_fetch(self.handle, outs))
+        losses = np.array([outs[i].loss for i in range(n)], np.float32)
+        if self.dist:
+            import torch
+            import torch.distributed as td
+            t = torch.tensor(losses, device="cuda:%d" % self.device)
+            td.all_reduce(t, op=td.ReduceOp.SUM)
+            losses = t.cpu().numpy()
+        dW = np.repeat(losses[:, None], n, 1).astype(np.float32)
+        db = np.ones((1, n), np.float32)
+        gn = C.c_float()
+        _cabi.check(L.icl_apply_update_ex(self.handle, float(np.sum(dW.astype(np.float64) ** 2) + n), C.byref(gn)))
+        tr = next(iter(g.train.values()))
+        scale = tr["clip"] / max(gn.value, tr["clip"]) if tr["clip"] > 0 else 1.0
+        t = C.c_int64()
+        _cabi.check(L.icl_get_step(self.handle, C.byref(t)))
+        lr_t = tr["lr"] * math.sqrt(1.0 - 0.999 ** t.value) / (1.0 - 0.9 ** t.value)
+        for name, grad in (("W", dW), ("b", db)):
+            gs = (grad * scale).astype(np.float32)
+            jv["m" + name] = (0.9 * jv["m" + name] + 0.1 * gs).astype(np.float32)
+            jv["v" + name] = (0.999 * jv["v" + name] + 0.001 * gs * gs).astype(np.float32)
+            jv[name] = (jv[name] - lr_t * jv["m" + name] / (np.sqrt(jv["v" + name]) + tr["eps"])).astype(np.float32)
+        _cabi.check(L.icl_set_loss_weights(self.handle, None))
+        self.last_train_stats = [dict(loss=np.float32(outs[i].loss), accuracy=np.float32(outs[i].accuracy)) for i in range(n)]
+        return losses
+
     def get_tensor(self, name, kind=0):
+        if name in self.JOINT_NAMES and self.graph.joint == "weighted_joint":
+            jv = self._joint()
+            key = "W" if name == self.JOINT_NAMES[0] else "b"
+            return jv[{0: key, 2: "m" + key, 3: "v" + key}[kind]].copy()
         for n, r, c, _ in self.param_info():
             if n == name:
                 out = np.empty((r, c), np.float32)
@@ -240,29 +321,69 @@ class Session(object):
         raise KeyError(name)
 
     def set_tensor(self, name, value, kind=0):
+        if name in self.JOINT_NAMES and self.graph.joint == "weighted_joint":
+            jv = self._joint()
+            key = "W" if name == self.JOINT_NAMES[0] else "b"
+            k2 = {0: key, 2: "m" + key, 3: "v" + key}[kind]
+            jv[k2] = np.asarray(value, np.float32).reshape(jv[k2].shape).copy()
+            return
         v = np.ascontiguousarray(np.asarray(value, dtype=np.float32))
         _cabi.check(_cabi.lib().icl_set_tensor(self.handle, kind, name.encode(), _cabi.np_ptr(v)))
 
+    def set_optimizer_slot(self, slot):
+        """Select the Adam state (m, v, step) used by the next updates / get_tensor(kind 2, 3) calls."""
+        if slot != self._slot:
+            _cabi.check(_cabi.lib().icl_set_optimizer_slot(self.handle, int(slot)))
+            self._slot = int(slot)
+
     def state_dict(self):
+        """Parameters under their TF variable names + the Adam state of every optimizer slot (slot 0: 'adam_m/<name>',
+        'adam_v/<name>', 'adam_step'; slot s > 0: the same keys with an '@s' suffix on the prefix)."""
+        L = _cabi.lib()
         st = {}
-        for n, _, _, _ in self.param_info():
+        info = self.param_info()
+        for n, _, _, _ in info:
             st[n] = self.get_tensor(n, 0)
-            st["adam_m/" + n] = self.get_tensor(n, 2)
-            st["adam_v/" + n] = self.get_tensor(n, 3)
-        t = C.c_int64()
-        _cabi.check(_cabi.lib().icl_get_step(self.handle, C.byref(t)))
-        st["adam_step"] = np.int64(t.value)
+        keep = self._slot
+        for s in range(L.icl_optimizer_slots(self.handle)):
+            self.set_optimizer_slot(s)
+            sfx = "" if s == 0 else "@%d" % s
+            for n, _, _, _ in info:
+                st["adam_m%s/%s" % (sfx, n)] = self.get_tensor(n, 2)
+                st["adam_v%s/%s" % (sfx, n)] = self.get_tensor(n, 3)
+            t = C.c_int64()
+            _cabi.check(L.icl_get_step(self.handle, C.byref(t)))
+            st["adam_step" + sfx] = np.int64(t.value)
+        self.set_optimizer_slot(keep)
+        if self.graph.joint == "weighted_joint":
+            jv = self._joint()
+            for name, key in zip(self.JOINT_NAMES, ("W", "b")):
+                st[name], st["adam_m/" + name], st["adam_v/" + name] = jv[key].copy(), jv["m" + key].copy(), jv["v" + key].copy()
         return st
 
     def load_state(self, st):
-        for n, r, c, _ in self.param_info():
+        info = self.param_info()
+        if self.graph.joint == "weighted_joint":
+            for name in self.JOINT_NAMES:
+                for kind, pre in ((0, ""), (2, "adam_m/"), (3, "adam_v/")):
+                    if pre + name in st:
+                        self.set_tensor(name, st[pre + name], kind)
+        for n, r, c, _ in info:
             if n in st:
                 self.set_tensor(n, np.asarray(st[n]).reshape(r, c), 0)
-            if "adam_m/" + n in st:
-                self.set_tensor(n, np.asarray(st["adam_m/" + n]).reshape(r, c), 2)
-                self.set_tensor(n, np.asarray(st["adam_v/" + n]).reshape(r, c), 3)
-        if "adam_step" in st:
-            _cabi.check(_cabi.lib().icl_set_step(self.handle, int(st["adam_step"])))
+        keep = self._slot
+        slots = sorted(set([0] + [int(k.split("@")[1]) for k in st if k.startswith("adam_step@")]))
+        for s in slots:
+            sfx = "" if s == 0 else "@%d" % s
+            if "adam_step" + sfx not in st:
+                continue
+            self.set_optimizer_slot(s)
+            for n, r, c, _ in info:
+                if "adam_m%s/%s" % (sfx, n) in st:
+                    self.set_tensor(n, np.asarray(st["adam_m%s/%s" % (sfx, n)]).reshape(r, c), 2)
+                    self.set_tensor(n, np.asarray(st["adam_v%s/%s" % (sfx, n)]).reshape(r, c), 3)
+            _cabi.check(_cabi.lib().icl_set_step(self.handle, int(st["adam_step" + sfx])))
+        self.set_optimizer_slot(keep)
 
     # -- execution ---------------------------------------------------------------------------------------------------
     def _bind_stream(self):
@@ -462,6 +583,13 @@ def run_op(sess, op, batch_tensor_list, lstm_input_dropout, dropout, encoding_sc
     kind = {"train_op": _cabi.OP_TRAIN}.get(op.kind, _cabi.OP_PREDICT)
     if kind == _cabi.OP_TRAIN and not include_labels:
         raise ValueError("train_op needs include_labels=True")
+    if op.kind == "train_op":
+        keys = list(g.train.keys())
+        sess.ensure()
+        sess.set_optimizer_slot(keys.index(op.scope) if op.scope in keys else 0)
+    if op.kind == "train_op" and g.joint == "weighted_joint" and head_ids is None and len(g.heads) > 1:
+        sess.train_weighted_joint(batch_tensor_list, float(lstm_input_dropout), float(dropout))
+        return None
     if op.kind == "train_op" and not os.environ.get("ICL_SYNC_TRAIN"):
         sess.train_async(batch_tensor_list, float(lstm_input_dropout), float(dropout), head_ids)
         return None                                           # sess.run(train_op) returns None (core.py:625)
@@ -469,6 +597,9 @@ def run_op(sess, op, batch_tensor_list, lstm_input_dropout, dropout, encoding_sc
     if op.kind == "train_op":
         return None
     if op.kind == "loss" and op.scope == "" and len(g.heads) > 1 and head_ids is None:
+        if g.joint == "weighted_joint":
+            jv = sess._joint()
+            return np.float32(np.sum(np.array([r["loss"] for r in res], np.float32)[None, :] @ jv["W"] + jv["b"]))
         return np.float32(sum(r["loss"] for r in res))       # simple_joint: sum of the task losses
     if op.scope in scopes:
         i = scopes.index(op.scope)

@@ -445,9 +445,10 @@ __global__ void k_scatter_spans(SlotTable st, const float* __restrict__ dbi, Ste
 }
 
 // ----------------------------------------------------------------------------- softmax layer + CE + metrics (core.py:202-268,509-511)
-// one warp per example: logits = a*W + b, softmax, argmax, per-row CE, dlogits = (p - y) * scale
+// one warp per example: logits = a*W + b, softmax, argmax, per-row CE * scale, dlogits = (p - y) * scale * gscale
+// (gscale = d joint_loss / d loss of this head: 1, or the row sum of the trainable loss-mixing matrix of `weighted_joint`)
 __global__ void k_softmax_ce(const float* __restrict__ a, int K, const float* __restrict__ W, const float* __restrict__ bias,
-                             int C, const float* __restrict__ y, int B, float scale, float* __restrict__ proba,
+                             int C, const float* __restrict__ y, int B, float scale, float gscale, float* __restrict__ proba,
                              long long* __restrict__ pred, float* __restrict__ row_loss, float* __restrict__ row_correct,
                              float* __restrict__ dlogits) {
   int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -476,7 +477,7 @@ __global__ void k_softmax_ce(const float* __restrict__ a, int K, const float* __
       float yc = y[(long)b * C + c];
       if (yc > besty) { besty = yc; ay = c; }
       loss -= yc * (logit[c] - mx - lse);
-      dlogits[(long)b * C + c] = (p - yc) * scale;
+      dlogits[(long)b * C + c] = (p - yc) * (scale * gscale);
     }
   }
   pred[b] = am;
@@ -528,7 +529,7 @@ __global__ void k_sumsq_partial(const float* __restrict__ g, long n, double* __r
   }
   if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
-__global__ void k_sumsq_final(const double* __restrict__ partial, int n, float* __restrict__ gnorm) {
+__global__ void k_sumsq_final(const double* __restrict__ partial, int n, float* __restrict__ gnorm, double extra) {
   __shared__ double sh[256];
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s += partial[i];
@@ -538,7 +539,7 @@ __global__ void k_sumsq_final(const double* __restrict__ partial, int n, float* 
     if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) gnorm[0] = (float)sqrt(sh[0]);
+  if (threadIdx.x == 0) gnorm[0] = (float)sqrt(sh[0] + extra);      // extra: squared norm of gradients kept on the host
 }
 // TF-1.x Adam: theta -= lr_t * m / (sqrt(v) + eps), lr_t computed on the host from the step count.  Also writes the
 // TF32-rounded copy of the new parameters that the next step's GEMMs read (pr; may be null).

@@ -78,6 +78,7 @@ struct Head {
   int* idx[ICL_N_INDEX] = {};
   float *feats = nullptr, *box = nullptr, *bfeats = nullptr, *labels = nullptr;
   bool has_labels = false, active = true;
+  float loss_w = 1.0f;               // d joint_loss / d loss of this head (icl_set_loss_weights)
   HeadIn in[2];
   float* h_out = nullptr; long long* h_pred = nullptr;   // pinned staging of the results
 };
@@ -96,6 +97,11 @@ struct icl_model {
   int round_ops = 1;
   int pK[2], pBias[2];
   int64_t step = 0;
+  // optimizer slots: the reference's `alternate` multitask scheme builds one AdamOptimizer per task (icl_multitask_lstm.py:387-393),
+  // i.e. separate m / v slots and beta-power accumulators for every variable each of them touches.  Slot 0 = M, V, step above.
+  struct OptSlot { float *M = nullptr, *V = nullptr; int64_t step = 0; };
+  std::vector<OptSlot> slots;
+  int cur_slot = 0;
   // workspaces (step-major, see icl_kernels.cuh)
   // XH[d] = [rows, E+H+4]: columns [0,E) the prepared inputs (xd), [E,E+H) the TF32 h_{k-1} operand rows (Hp), column E+H = 1
   // on valid rows -- one matrix so that [dKernel; dbias] = XH^T dZ is a single GEMM (the ones column sums dZ into the bias
@@ -386,7 +392,12 @@ extern "C" void icl_destroy(icl_model* m) {
   if (!m) return;
   cudaDeviceSynchronize();
   auto F = [](void* p) { if (p) cudaFree(p); };
-  F(m->P); F(m->G); F(m->M); F(m->V); F(m->Pr);
+  F(m->P); F(m->G); F(m->Pr);
+  if (m->slots.empty()) { F(m->M); F(m->V); }
+  else {                       // m->M / m->V alias the live slot
+    m->slots[m->cur_slot].M = m->M; m->slots[m->cur_slot].V = m->V;
+    for (auto& o : m->slots) { F(o.M); F(o.V); }
+  }
   for (InSet& I : m->in) {
     F(I.d_blob);
     if (I.h_blob) cudaFreeHost(I.h_blob);
@@ -855,7 +866,7 @@ static int heads_forward(icl_model* m, float keep, uint64_t seed) {
     }
     float scale = h.c.weighted_classes ? 1.0f / B : 1.0f;   // "weighted" as executed == mean CE (core.py:244-267)
     k_softmax_ce<<<(B * 32 + 127) / 128, 128, 0, st>>>(in, h.dims[L], m->P + m->params[h.pW[L]].off, m->P + m->params[h.pB[L]].off, C,
-                                                      h.has_labels ? h.labels : nullptr, B, scale, h.proba, h.pred, h.row_loss,
+                                                      h.has_labels ? h.labels : nullptr, B, scale, h.loss_w, h.proba, h.pred, h.row_loss,
                                                       h.row_correct, h.dlogits);
     LAUNCHED(m);
     if (h.has_labels) {
@@ -1073,20 +1084,72 @@ static int lstm_backward(icl_model* m) {
   return 0;
 }
 
-extern "C" int icl_apply_update(icl_model* m) {
+// Select the Adam state (m, v, step) the next updates use; slots are created zeroed on first use.  icl_get/set_tensor kinds 2, 3
+// and icl_get/set_step address the selected slot.
+extern "C" int icl_set_optimizer_slot(icl_model* m, int slot) {
+  if (slot < 0 || slot >= 64) return fail("optimizer slot out of range");
+  if (m->slots.empty()) m->slots.resize(1);
+  m->slots[m->cur_slot].M = m->M; m->slots[m->cur_slot].V = m->V; m->slots[m->cur_slot].step = m->step;     // park the live one
+  while ((int)m->slots.size() <= slot) {
+    icl_model::OptSlot o;
+    CK(dmalloc(&o.M, (size_t)m->n_params)); CK(dmalloc(&o.V, (size_t)m->n_params));
+    CK(cudaMemset(o.M, 0, (size_t)m->n_params * 4)); CK(cudaMemset(o.V, 0, (size_t)m->n_params * 4));
+    m->slots.push_back(o);
+  }
+  m->cur_slot = slot;
+  m->M = m->slots[slot].M; m->V = m->slots[slot].V; m->step = m->slots[slot].step;
+  return 0;
+}
+extern "C" int icl_optimizer_slots(icl_model* m) { return std::max<int>(1, (int)m->slots.size()); }
+
+extern "C" int icl_set_loss_weights(icl_model* m, const float* w) {
+  for (size_t hi = 0; hi < m->heads.size(); hi++) m->heads[hi].loss_w = w ? w[hi] : 1.0f;
+  return 0;
+}
+
+static int apply_update(icl_model* m, double extra_sumsq);
+extern "C" int icl_apply_update(icl_model* m) { return apply_update(m, 0.0); }
+// extra_sumsq: squared norm of gradients the caller keeps on the host (they take part in clip_by_global_norm);
+// gnorm_out (may be NULL): the global norm used, read back synchronously
+extern "C" int icl_apply_update_ex(icl_model* m, double extra_sumsq, float* gnorm_out) {
+  CKI(apply_update(m, extra_sumsq));
+  if (gnorm_out) {
+    *gnorm_out = 0.f;
+    if (m->cfg.clip_norm > 0) {
+      CK(cudaMemcpyAsync(gnorm_out, m->d_gnorm, 4, cudaMemcpyDeviceToHost, m->stream));
+      CK(cudaStreamSynchronize(m->stream));
+    }
+  }
+  return 0;
+}
+static int apply_update(icl_model* m, double extra_sumsq) {
   cudaStream_t st = m->stream;
   long n = (long)m->n_params;
   PH_BEGIN(m, PH_UPDATE);
-  if (m->cfg.clip_norm > 0) {
+  if (m->cfg.clip_norm > 0) {       // heads that were not fed have an all-zero gradient: the norm over everything is the norm TF takes
     k_sumsq_partial<<<592, 256, 0, st>>>(m->G, n, m->d_partial); LAUNCHED(m);
-    k_sumsq_final<<<1, 256, 0, st>>>(m->d_partial, 592, m->d_gnorm); LAUNCHED(m);
+    k_sumsq_final<<<1, 256, 0, st>>>(m->d_partial, 592, m->d_gnorm, extra_sumsq); LAUNCHED(m);
   }
   m->step++;
   double b1 = m->cfg.beta1, b2 = m->cfg.beta2;
   float lr_t = (float)(m->cfg.learn_rate * std::sqrt(1.0 - std::pow(b2, (double)m->step)) / (1.0 - std::pow(b1, (double)m->step)));
-  k_adam<<<592, 256, 0, st>>>(m->P, m->G, m->M, m->V, m->round_ops ? m->Pr : nullptr, n, m->d_gnorm, m->cfg.clip_norm, lr_t, (float)b1,
-                             (float)b2, m->cfg.adam_epsilon);
-  LAUNCHED(m);
+  // variables without a gradient (the heads that were not fed in this step) are not touched by the optimizer -- neither the
+  // weights nor their m / v (tf.train.Optimizer skips None gradients): update the contiguous runs of live parameters only
+  std::vector<std::pair<int64_t, int64_t>> runs;      // [begin, end) in floats
+  auto add_run = [&](int64_t b0, int64_t e0) { if (!runs.empty() && runs.back().second == b0) runs.back().second = e0; else runs.push_back({b0, e0}); };
+  add_run(0, m->heads.empty() ? m->n_params : m->params[m->heads[0].pW[0]].off);
+  for (size_t hi = 0; hi < m->heads.size(); hi++) {
+    const int64_t b0 = m->params[m->heads[hi].pW[0]].off;
+    const int64_t e0 = hi + 1 < m->heads.size() ? m->params[m->heads[hi + 1].pW[0]].off : m->n_params;
+    if (m->heads[hi].active) add_run(b0, e0);
+  }
+  for (auto& r : runs) {
+    const long len = (long)(r.second - r.first);
+    const int blocks = (int)std::max<long>(1, std::min<long>(592, (len / 4 + 255) / 256));
+    k_adam<<<blocks, 256, 0, st>>>(m->P + r.first, m->G + r.first, m->M + r.first, m->V + r.first, m->round_ops ? m->Pr + r.first : nullptr,
+                                  len, m->d_gnorm, m->cfg.clip_norm, lr_t, (float)b1, (float)b2, m->cfg.adam_epsilon);
+    LAUNCHED(m);
+  }
   PH_END(m, PH_UPDATE);
   return 0;
 }

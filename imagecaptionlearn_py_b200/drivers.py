@@ -4,7 +4,7 @@
     icl_core_lstm.py      --task nonvis|card                 icl_core_lstm.py:21-254,257-406
     icl_relation_lstm.py  --rel_type intra|ordered_intra|cross   icl_relation_lstm.py:21-327,330-495
     icl_affinity_lstm.py                                      icl_affinity_lstm.py:77-343,346-508
-    icl_multitask_lstm.py (simple_joint)                      icl_multitask_lstm.py:28-93,213-358
+    icl_multitask_lstm.py --multitask_scheme simple_joint|weighted_joint|alternate     icl_multitask_lstm.py:28-93,213-476
 
 Same flags, defaults, data_dir/{raw,feats,scores} path scheme, model-file naming, epoch loop (tail batch dropped,
 evaluation every 10th epoch, best-average-F1 bookkeeping with the 0.005 slack, early stopping after 10 epochs) and
@@ -319,3 +319,174 @@ def main_affinity(argv=None):
             out = args.data_dir + "/scores/" + root + "_affinity.scores"
             nn_eval.write_scores_file(out, scores)
             return out
+
+
+# ------------------------------------------------------------------------------------------- icl_multitask_lstm.py
+MT_TASKS = ["rel_intra", "rel_cross", "nonvis", "affinity", "card"]                  # icl_multitask_lstm.py:22
+MT_CLASSES = {"rel_intra": CLASSES_REL, "rel_cross": CLASSES_REL, "nonvis": CLASSES_VISUAL, "affinity": CLASSES_AFFINITY,
+              "card": CLASSES_CARD}
+
+
+def mt_load_data(args, data, split, label_file=None):
+    """icl_multitask_lstm.py:149-209 (file naming of the joint data set; one shared `_relation.feats` for both pair tasks)."""
+    d, root = args.data_dir + "/", data + "_" + split
+    emb = load_embeddings(args, args.data_dir, root)
+    out = {}
+    for task in MT_TASKS:
+        if task.startswith("rel"):
+            midx = d + "raw/" + root + "_mentionPairs_" + task.split("_")[1] + ".txt"
+            froot = d + "feats/" + root + "_relation"
+        else:
+            midx = d + "raw/" + root + "_mentions_" + task + ".txt"
+            froot = d + "feats/" + root + "_" + task
+        dd = loaders.load_sentences(d + "raw/" + root + "_captions.txt", emb)
+        dd.update(loaders.load_mentions(midx, task, froot + ".feats", froot + "_meta.json", len(MT_CLASSES[task])))
+        if task.startswith("rel"):
+            lab = d + "raw/" + root + "_mentionPair_labels.txt"
+            dd["gold_label_dict"] = loaders.load_relation_labels(lab) if os.path.exists(lab) else {}
+        elif task == "affinity":
+            dd.update(loaders.load_boxes(label_file or d + "raw/" + root + "_mention_box_labels.txt",
+                                         d + "feats/" + data + "_boxes/" + split + "/"))
+        out[task] = dd
+    return out
+
+
+def mt_task_ids(dicts):
+    return {t: (nn_data.get_valid_mention_box_pairs(dicts[t]) if t == "affinity" else list(dicts[t]["mention_indices"].keys()))
+            for t in MT_TASKS}
+
+
+def mt_setup(args, dicts, batch_sizes):
+    """icl_multitask_lstm.py:28-93: one shared BiLSTM scope, one head per task under a variable_scope named like the task."""
+    nn_util.reset_default_graph()
+    nn_util.set_random_seeds()
+    with nn_util.variable_scope("bidirectional_lstm"):
+        nn_util.setup_bidirectional_lstm(args.lstm_hidden_width, args.data_norm)
+    for task in MT_TASKS:
+        dd = dicts[task]
+        with nn_util.variable_scope(task):
+            nn_util.setup_core_architecture(task, args.encoding_scheme, batch_sizes[task], args.start_hidden_width, args.hidden_depth,
+                                            args.weighted_classes, args.activation, len(MT_CLASSES[task]), dd["n_mention_feats"],
+                                            dd.get("box_embedding_width"), dd.get("n_box_feats"))
+
+
+def mt_evaluate(sess, args, dicts, ids, batch_sizes, log, write_scores=False):
+    """icl_multitask_lstm.py:327-358,479-535: per-task prediction through the shared encoder + the task's own head."""
+    f1 = {}
+    for task in MT_TASKS:
+        with nn_util.variable_scope(task):
+            scores, gold = nn_util.get_pred_scores_mcc(task, args.encoding_scheme, sess, batch_sizes[task], ids[task], dicts[task],
+                                                       len(MT_CLASSES[task]))
+        keys = list(scores.keys())
+        pred = [int(np.argmax(scores[k])) for k in keys]
+        if task.startswith("rel"):
+            sd = evaluate_relations(keys, pred, dicts[task]["gold_label_dict"], log)
+            f1[task] = (sd.get_score("coref").f1 + sd.get_score("subset").f1) / 2.0
+        else:
+            sd = nn_eval.evaluate_multiclass([int(np.argmax(gold[k])) for k in keys], pred, MT_CLASSES[task], log)
+            f1[task] = float(np.mean([sd.get_score(i).f1 for i in range(len(MT_CLASSES[task]))]))
+        if write_scores:
+            nn_eval.write_scores_file(dicts[task]["scores_file"], scores)
+            log.info("Wrote scores file %s", dicts[task]["scores_file"])
+    return f1
+
+
+def main_multitask(argv=None):
+    """icl_multitask_lstm.py:538-760.  The reference's as-written defects (only the last task's sentences
+    reach the encoder; the predict call passes its arguments in the wrong positions) are not reproduced: this implements the
+    intended semantics -- one shared-weight encoder pass over the concatenation of every task's sentence batch."""
+    log = _log()
+    p = argparse.ArgumentParser("ImageCaptionLearn_py: Neural Network for multitask learning; shared bidirectional LSTM to hidden "
+                                "layers to softmax over labels")
+    common_args(p)
+    p.add_argument("--data", required=True)
+    p.add_argument("--split", required=True)
+    p.add_argument("--eval_data", required=True)
+    p.add_argument("--eval_split", required=True)
+    p.add_argument("--multitask_scheme", choices=["simple_joint", "weighted_joint", "alternate"], default="simple_joint")
+    p.add_argument("--mention_box_label_file", type=str)
+    p.add_argument("--eval_mention_box_label_file", type=str)
+    p.add_argument("--box_category_file", type=str)
+    p.add_argument("--eval_box_category_file", type=str)
+    args = p.parse_args(argv)
+    arg_dict = vars(args)
+    scheme = args.multitask_scheme
+    model_file = _model_file(args, arg_dict, "multitask_" + scheme + "_lstm")
+    dicts = mt_load_data(args, args.data, args.split, args.mention_box_label_file)
+    ids = mt_task_ids(dicts)
+    batch_sizes = {t: (512 if scheme == "alternate" and args.batch_size == 512 else args.batch_size) for t in MT_TASKS}
+    T = max(dd["max_seq_len"] for dd in dicts.values())
+    if args.train:
+        ev = mt_load_data(args, args.eval_data, args.eval_split, args.eval_mention_box_label_file)
+        ev_ids = mt_task_ids(ev)
+        T = max([T] + [dd["max_seq_len"] for dd in ev.values()])
+        mt_setup(args, dicts, batch_sizes)
+        saver = nn_util.Saver(max_to_keep=100)
+        B = args.batch_size
+        if scheme == "alternate":                                       # one optimizer per task (icl_multitask_lstm.py:387-393)
+            train_ops = {}
+            for task in MT_TASKS:
+                with nn_util.variable_scope(task):
+                    nn_util.add_train_op(nn_util.get_collection(task + "/loss")[0], args.learn_rate, args.adam_epsilon, args.clip_norm)
+                train_ops[task] = nn_util.get_collection(task + "/train_op")[0]
+        else:
+            nn_util.add_train_op(nn_util.setup_joint_loss(scheme), args.learn_rate, args.adam_epsilon, args.clip_norm)
+            train_op = nn_util.get_collection("train_op")[0]
+        f1 = {}
+        with nn_util.Session(max_seq_len=T) as sess:
+            sess.ensure()
+            for i in range(args.epochs):
+                log.info("--- Epoch %d ----", i + 1)
+                if scheme == "alternate":                               # icl_multitask_lstm.py:405-437
+                    batches = []
+                    for task in MT_TASKS:
+                        t_ids = nn_data.shuffle_mention_box_pairs(ids[task]) if task == "affinity" else list(ids[task])
+                        bs = batch_sizes[task]
+                        pad = bs * (len(t_ids) // bs + 1) - len(t_ids)
+                        mat = np.pad(np.asarray(t_ids, dtype=object), (0, pad), "wrap").reshape(-1, bs)
+                        batches.extend((task, list(row)) for row in mat)
+                    order = np.random.permutation(len(batches))
+                    for j in order:
+                        task, row = batches[j]
+                        bt = nn_data.load_batch(row, dicts[task], task, len(MT_CLASSES[task]))
+                        nn_util.run_op(sess, train_ops[task], [bt], args.lstm_input_dropout, args.dropout, args.encoding_scheme,
+                                       [task], [task], True)
+                else:                                                   # icl_multitask_lstm.py:268-323
+                    pos, max_samples = {}, 0
+                    for task in MT_TASKS:
+                        ids[task] = (nn_data.shuffle_mention_box_pairs(ids[task]) if task == "affinity"
+                                     else list(np.random.permutation(np.asarray(ids[task], dtype=object))))
+                        max_samples = max(max_samples, len(ids[task]))
+                        pos[task] = 0
+                    for j in range(max_samples // B):
+                        bts = []
+                        for task in MT_TASKS:
+                            t_ids, n, st = ids[task], len(ids[task]), pos[task]
+                            if st + B < n:
+                                row = t_ids[st:st + B]
+                                pos[task] += B
+                            else:                                       # wrap-around as written (skips the last id of the list)
+                                rem = st + B - n + 1
+                                row = list(t_ids[st:n - 1]) + list(t_ids[0:rem])
+                                pos[task] = rem
+                            bts.append(nn_data.load_batch(row, dicts[task], task, len(MT_CLASSES[task])))
+                        nn_util.run_op(sess, train_op, bts, args.lstm_input_dropout, args.dropout, args.encoding_scheme, MT_TASKS,
+                                       MT_TASKS, True)
+                log.info("Saving model")
+                saver.save(sess, model_file)
+                if not args.skip_epoch_eval and (i + 1) % max(1, args.eval_every if args.eval_every != 10 else 1) == 0:
+                    f1 = mt_evaluate(sess, args, ev, ev_ids, batch_sizes, log)
+            log.info("Saving final model")
+            saver.save(sess, model_file)
+        return f1
+    if args.predict:
+        mt_setup(args, dicts, batch_sizes)
+        if scheme != "alternate":
+            nn_util.setup_joint_loss(scheme)
+        for task in MT_TASKS:
+            dicts[task]["scores_file"] = (args.data_dir + "/scores/" + args.data + "_" + args.split + "_" + task + "_mulit_" + scheme +
+                                          "_lstm.scores")                # sic (icl_multitask_lstm.py:741-744)
+        with nn_util.Session(max_seq_len=T) as sess:
+            nn_util.Saver().restore(sess, model_file)
+            mt_evaluate(sess, args, dicts, ids, batch_sizes, log, write_scores=True)
+        return [dicts[t]["scores_file"] for t in MT_TASKS]

@@ -131,13 +131,15 @@ def example_ids(dd, task):
     return list(dd["mention_indices"].keys())
 
 
-def write_dataset(corpus, data_dir, data_root, task, F=None, seed=7):
+def write_dataset(corpus, data_dir, data_root, task, F=None, seed=7, naming="single"):
     """Emit the synthetic corpus in the reference's file formats and directory scheme (icl_core_lstm.py:333-345,
     icl_relation_lstm.py:403-430, icl_affinity_lstm.py:412-433) so the drop-in CLIs run on it unmodified:
     raw/<root>_captions.txt, raw/<root>_mentions_<task>.txt, feats/<root>_<task>_neural.feats + _meta.json
     (relations: raw/<root>_mentionPairs_<rel>.txt, feats/<root>_relation_neural_<rel>.feats, raw/<root>_mentionPair_labels.txt),
     raw/<root>_embeddings.npz (stand-in for the word2vec binary), and for affinity raw/<root>_affinity_labels.txt +
-    feats/<data>_boxes/<split>/<img>.feats."""
+    feats/<data>_boxes/<split>/<img>.feats.
+    naming="multitask": the file names icl_multitask_lstm.py:153-209 reads instead -- feats/<root>_<task>.feats (no "_neural"),
+    ONE shared feats/<root>_relation.feats for both relation tasks (appended to), raw/<root>_mention_box_labels.txt."""
     import json
     import os
     dd = make_data_dict(corpus, task, F=F)
@@ -157,13 +159,16 @@ def write_dataset(corpus, data_dir, data_root, task, F=None, seed=7):
             lab = int(np.argmax(dd["labels"][mid])) if mid in dd["labels"] else 0
             f.write("%s\t%s\t%d\n" % (mid, ",".join(str(i) for i in idx), lab))
     froot = "%s_%s_neural" % (data_root, task) if not task.startswith("rel") else "%s_relation_neural_%s" % (data_root, tag)
-    with open(os.path.join(data_dir, "feats", froot + ".feats"), "w") as f:
+    if naming == "multitask":
+        froot = "%s_%s" % (data_root, task) if not task.startswith("rel") else "%s_relation" % data_root
+    with open(os.path.join(data_dir, "feats", froot + ".feats"), "a" if naming == "multitask" and task.startswith("rel") else "w") as f:
         for mid, v in dd["mention_features"].items():
             nz = np.nonzero(v)[0]
             f.write("0 %s # %s\n" % (" ".join("%d:%g" % (k, v[k]) for k in nz), mid))
     json.dump({"max_idx": F - 1}, open(os.path.join(data_dir, "feats", froot + "_meta.json"), "w"))
     if task == "affinity":
-        with open(os.path.join(data_dir, "raw", data_root + "_affinity_labels.txt"), "w") as f:
+        lab_name = "_mention_box_labels.txt" if naming == "multitask" else "_affinity_labels.txt"
+        with open(os.path.join(data_dir, "raw", data_root + lab_name), "w") as f:
             for k, v in dd["labels"].items():
                 f.write("%s\t%d\n" % (k, int(np.argmax(v))))
         data, split = data_root.rsplit("_", 1)

@@ -124,6 +124,16 @@ int icl_poll_stats(icl_model* m, icl_head_out* prev);
 int icl_grad_buffer(icl_model* m, void** dev_ptr, int64_t* n_floats);
 int icl_param_buffer(icl_model* m, void** dev_ptr, int64_t* n_floats);
 int icl_apply_update(icl_model* m);
+/* Adam state selection: one (m, v, beta-power) set per tf.train.AdamOptimizer instance -- the `alternate` multitask scheme has
+   one per task (icl_multitask_lstm.py:387-393).  Slot 0 exists from the start; others are created zeroed on first use.
+   Parameters of heads that were not fed (icl_head_batch.inactive) are never touched by an update. */
+/* weighted_joint (icl_multitask_lstm.py:248-255): joint = sum_j (sum_t loss_t W[t,j] + b_j) with a trainable 5x5 W kept by the
+   caller.  icl_set_loss_weights gives every head its d joint / d loss_t (row sums of W; NULL = all 1); icl_apply_update_ex adds
+   the caller's squared gradient norm (of W, b) to clip_by_global_norm and returns the global norm used. */
+int icl_set_loss_weights(icl_model* m, const float* w /*[n_heads]*/);
+int icl_apply_update_ex(icl_model* m, double extra_sumsq, float* gnorm_out);
+int icl_set_optimizer_slot(icl_model* m, int slot);
+int icl_optimizer_slots(icl_model* m);
 int icl_sync(icl_model* m);
 
 /* test / profiling hooks */

@@ -277,12 +277,12 @@ def head_forward(params, scope, batch_input, y, n_layers, act, keep=1.0, masks=N
     return res
 
 
-def head_backward(params, res, act_grad_override=None):
+def head_backward(params, res, act_grad_override=None, loss_weight=1.0):
     """act_grad_override: optional list (per hidden layer) of arrays replacing activate_grad -- used by the parity
     tests to evaluate a piecewise-linear activation on the same side of its kink as the device did."""
     layers, a_last, proba, y, scale, names, act, keep, masks = res["_bwd"]
     grads = {}
-    dlog = (proba * y.sum(1, keepdims=True) - y) * scale
+    dlog = (proba * y.sum(1, keepdims=True) - y) * scale * loss_weight     # loss_weight = d joint / d loss of this head
     W = params[names[-1][0]]
     grads[names[-1][0]] = a_last.T @ dlog
     grads[names[-1][1]] = dlog.sum(0, keepdims=True)
@@ -337,13 +337,16 @@ def model_forward(params, cfg, sentences, seq_lengths, head_batches, keep_in=1.0
     return dict(heads=results, loss=total, out_fw=out_fw, out_bw=out_bw, _lstm=lcache)
 
 
-def model_backward(params, cfg, fwd, head_batches, act_grad_override=None):
+def model_backward(params, cfg, fwd, head_batches, act_grad_override=None, head_weights=None):
+    """head_weights: d joint_loss / d loss_t per head (None = the plain sum of the task losses; the `weighted_joint` scheme of
+    icl_multitask_lstm.py:248-255 passes the row sums of its trainable mixing matrix)."""
     grads = {}
     H = cfg["H"]
     d_fw = np.zeros_like(fwd["out_fw"])
     d_bw = np.zeros_like(fwd["out_bw"])
     for hi, (hc, hb, r) in enumerate(zip(cfg["heads"], head_batches, fwd["heads"])):
-        g, d_bi = head_backward(params, r, None if act_grad_override is None else act_grad_override[hi])
+        g, d_bi = head_backward(params, r, None if act_grad_override is None else act_grad_override[hi],
+                                1.0 if head_weights is None else head_weights[hi])
         grads.update(g)
         a, b = scatter_spans(d_bi, r["plan"], hb, d_fw.shape, H)
         d_fw += a

@@ -89,3 +89,48 @@ def test_cli_train_then_predict_writes_scores(tmp_path, which):
     for ln in lines[:20]:
         f = ln.split(",")
         assert len(f) == C + 1 and abs(sum(np.exp(float(x)) for x in f[1:]) - 1.0) < 1e-4     # "<id>,<ln p_0>,..."
+
+
+def _write_multitask(tmp, data, split, n_img=4, F=16):
+    from imagecaptionlearn_py_b200 import drivers
+    corpus = synth.make_corpus(n_img, seed=5, with_boxes=True, box_width=64)
+    for task in drivers.MT_TASKS:
+        synth.write_dataset(corpus, str(tmp), data + "_" + split, task, F=F, naming="multitask")
+
+
+def test_multitask_files_load_for_every_task(tmp_path):
+    """icl_multitask_lstm.py:153-209: the joint data set's file naming (shared `_relation.feats`, `_mention_box_labels.txt`)."""
+    import argparse
+    from imagecaptionlearn_py_b200 import drivers
+    _write_multitask(tmp_path, "flickr30k", "train")
+    p = argparse.ArgumentParser()
+    drivers.common_args(p)
+    args = p.parse_args(["--data_dir", str(tmp_path)])
+    dicts = drivers.mt_load_data(args, "flickr30k", "train")
+    ids = drivers.mt_task_ids(dicts)
+    assert set(dicts) == set(drivers.MT_TASKS) and all(len(ids[t]) > 0 for t in drivers.MT_TASKS)
+    for t in drivers.MT_TASKS:
+        bt = nn_data.load_batch(ids[t][:8], dicts[t], t, len(drivers.MT_CLASSES[t]))
+        assert bt["labels"].shape == (8, len(drivers.MT_CLASSES[t]))
+        assert bt["sentences"].shape[0] == (16 if t == "rel_cross" else 8)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scheme", ["simple_joint", "weighted_joint", "alternate"])
+def test_multitask_cli_train_then_predict(tmp_path, scheme):
+    from imagecaptionlearn_py_b200 import drivers
+    for split in ("train", "dev"):
+        _write_multitask(tmp_path, "flickr30k", split)
+    common = ["--data_dir", str(tmp_path), "--batch_size", "16", "--lstm_hidden_width", "20", "--start_hidden_width", "32",
+              "--hidden_depth", "1", "--epochs", "1", "--model_file", str(tmp_path / "mt.model"), "--data", "flickr30k",
+              "--split", "train", "--eval_data", "flickr30k", "--eval_split", "dev", "--multitask_scheme", scheme]
+    f1 = drivers.main_multitask(common + ["--train"])
+    assert set(f1) == set(drivers.MT_TASKS)
+    outs = drivers.main_multitask(common + ["--predict"])
+    assert len(outs) == 5
+    for out, task in zip(outs, drivers.MT_TASKS):
+        assert "_mulit_" + scheme + "_lstm.scores" in out
+        lines = open(out).read().strip().split("\n")
+        C = len(drivers.MT_CLASSES[task])
+        f = lines[0].split(",")
+        assert len(f) == C + 1 and abs(sum(np.exp(float(x)) for x in f[1:]) - 1.0) < 1e-4

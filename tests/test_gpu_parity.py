@@ -373,3 +373,93 @@ def test_pipelined_train_op_matches_synchronous_steps(monkeypatch):
     for k in pa["params"]:
         # same kernels, same seeds; only the red.global order of the split-K weight-gradient GEMMs may differ
         assert np.max(np.abs(out["async"][0][k] - out["sync"][0][k])) <= 2e-3 * 4e-3 + 1e-6, k
+
+
+def _two_task_setup(mode, joint=None, per_task_optimizers=False):
+    """A shared encoder with a nonvis and a card head under their own scopes; returns (core, sess, probs, specs, params)."""
+    from imagecaptionlearn_py_b200 import core
+    E, T, H = 12, 9, 8
+    specs = [dict(task="nonvis", S=11, F=4, widths=(8, 4)), dict(task="card", S=9, F=4, widths=(8,))]
+    probs = [tiny_problem(seed=60 + i, T=T, E=E, H=H, act="tanh", **s) for i, s in enumerate(specs)]
+    core.reset_default_graph()
+    with core.variable_scope("bidirectional_lstm"):
+        core.setup_bidirectional_lstm(H, False, n_embedding_width=E)
+    for p, s in zip(probs, specs):
+        with core.variable_scope(s["task"]):
+            core.setup_core_architecture(s["task"], "first_last_mention", p["B"], s["widths"][0], 0, False, "tanh", p["C"], p["F"])
+            core._graph.heads[-1]["widths"] = list(s["widths"])
+            if per_task_optimizers:
+                core.add_train_op(core.get_collection(s["task"] + "/loss")[0], 1e-3, 1e-8, 5.0)
+    if not per_task_optimizers:
+        core.add_train_op(core.setup_joint_loss(joint or "simple_joint"), 1e-3, 1e-8, 5.0)
+    sess = core.Session(max_seq_len=T, gemm_mode=_mode(mode))
+    sess.ensure()
+    params = {k: v.copy() for k, v in probs[0]["params"].items() if "lstm" in k}
+    for p, s in zip(probs, specs):
+        for k, v in p["params"].items():
+            if "lstm" not in k:
+                params[s["task"] + "/" + k] = v.copy()
+    for k, v in params.items():
+        sess.set_tensor(k, v.reshape(1, -1) if v.ndim == 1 else v)
+    return core, sess, probs, specs, params
+
+
+def test_alternate_scheme_keeps_one_adam_state_per_task():
+    """icl_multitask_lstm.py:387-437 (`alternate`): one AdamOptimizer per task -- own m / v / beta powers for the shared encoder
+    and its head -- and a step only touches the variables that have a gradient (the other heads keep weights AND moments).
+    Steps A, B, A, B against the oracle run with two independent Adam states."""
+    core, sess, probs, specs, params = _two_task_setup("simt", per_task_optimizers=True)
+    start = {k: v.copy() for k, v in params.items()}
+    states = [{}, {}]
+    for step in range(4):
+        i = step % 2
+        p, s = probs[i], specs[i]
+        core.run_op(sess, core.get_collection(s["task"] + "/train_op")[0], [dict(p["batch"])], 1.0, 1.0, "first_last_mention",
+                    [s["task"]], [s["task"]], True)
+        cfg = dict(H=p["H"], data_norm=False, heads=[dict(p["cfg"]["heads"][0], scope=s["task"])])
+        f = O.model_forward(params, cfg, p["x"], p["lens"], [p["batch"]])
+        g = O.model_backward(params, cfg, f, [p["batch"]])
+        O.clip_and_adam(params, g, states[i], 1e-3, 1e-8, 5.0)
+    for name, ref in params.items():
+        got = sess.get_tensor(name).reshape(ref.shape)
+        err = np.max(np.abs((got - start[name]) - (ref - start[name])))
+        assert err < 0.05 * 2e-3 + 1e-6, (name, err)
+    sess.close()
+
+
+def test_weighted_joint_scheme_matches_oracle():
+    """icl_multitask_lstm.py:248-255 (`weighted_joint`): joint = sum_j (sum_t loss_t W[t,j] + b_j) with trainable W, b.  One
+    train step: device gradients are the task gradients weighted by the row sums of W, dW[t,j] = loss_t and db_j = 1 take part
+    in clip_by_global_norm, and every variable (device and mixer) gets the same TF-Adam step."""
+    core, sess, probs, specs, params = _two_task_setup("simt", joint="weighted_joint")
+    W0, b0 = sess.get_tensor("hdn_1/Variable"), sess.get_tensor("hdn_1/Variable_1")
+    start = {k: v.copy() for k, v in params.items()}
+    core.run_op(sess, core.get_collection("train_op")[0], [dict(p["batch"]) for p in probs], 1.0, 1.0, "first_last_mention",
+                [s["task"] for s in specs], [s["task"] for s in specs], True)
+    cfg = dict(H=probs[0]["H"], data_norm=False, heads=[dict(p["cfg"]["heads"][0], scope=s["task"]) for p, s in zip(probs, specs)])
+    x = np.concatenate([p["x"] for p in probs], 0)
+    lens = np.concatenate([p["lens"] for p in probs], 0)
+    off, hbs = 0, []
+    for p in probs:
+        hb = {}
+        for k, v in p["batch"].items():
+            v = np.array(v)
+            if v.ndim == 2 and v.shape[1] == 3 and k.split("_")[0] in ("first", "last", "sent"):
+                v = v.copy()
+                v[:, 1] += off
+            hb[k] = v
+        hbs.append(hb)
+        off += p["S"]
+    f = O.model_forward(params, cfg, x, lens, hbs)
+    g = O.model_backward(params, cfg, f, hbs, head_weights=list(W0.astype(np.float64).sum(1)))
+    losses = np.array([r["loss"] for r in f["heads"]], np.float64)
+    params["hdn_1/Variable"], params["hdn_1/Variable_1"] = W0.astype(np.float64), b0.astype(np.float64)
+    start["hdn_1/Variable"], start["hdn_1/Variable_1"] = W0.copy(), b0.copy()
+    g["hdn_1/Variable"] = np.repeat(losses[:, None], len(probs), 1)
+    g["hdn_1/Variable_1"] = np.ones((1, len(probs)))
+    O.clip_and_adam(params, g, {}, 1e-3, 1e-8, 5.0)
+    for name, ref in params.items():
+        got = sess.get_tensor(name).reshape(ref.shape)
+        err = np.max(np.abs((got - start[name]) - (ref - start[name])))
+        assert err < 0.05 * 1e-3 + 1e-6, (name, err)
+    sess.close()
