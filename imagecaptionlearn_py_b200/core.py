@@ -155,6 +155,7 @@ class Session(object):
         self.run_counter = 0
         self.last_train_stats = None
         self._slot = 0
+        self._table_ref = None
         self.joint_vars = None          # weighted_joint: dict(W, b, mW, vW, mb, vb) on the host
         self.base_seed = self.graph.seed if seed is None else seed
         self._grad_view = None
@@ -212,6 +213,7 @@ class Session(object):
         _cabi.check(_cabi.lib().icl_create(C.byref(cfg), C.byref(h)))
         self.handle = h
         self._slot = 0
+        self._table_ref = None
         self._grad_view = None
         if state is None:
             self.initialize()
@@ -330,6 +332,14 @@ class Session(object):
         v = np.ascontiguousarray(np.asarray(value, dtype=np.float32))
         _cabi.check(_cabi.lib().icl_set_tensor(self.handle, kind, name.encode(), _cabi.np_ptr(v)))
 
+    def set_token_table(self, table):
+        """Keep `table` ([n_rows, E] float32: e.g. every caption matrix of the corpus concatenated, data._flat_table) resident
+        on the device; batches with 'token_rows' then ship 4 bytes per token instead of an embedding row."""
+        if self._table_ref is not table:
+            t = np.ascontiguousarray(table, dtype=np.float32)
+            _cabi.check(_cabi.lib().icl_set_token_table(self.handle, _cabi.np_ptr(t), int(t.shape[0])))
+            self._table_ref = table
+
     def set_optimizer_slot(self, slot):
         """Select the Adam state (m, v, step) used by the next updates / get_tensor(kind 2, 3) calls."""
         if slot != self._slot:
@@ -424,7 +434,13 @@ class Session(object):
         b = _cabi.Batch()
         head_ids = list(range(len(batch_tensor_list))) if head_ids is None else list(head_ids)
         first = batch_tensor_list[0]
-        packed = "sentences_packed" in first
+        by_rows = "token_rows" in first
+        if by_rows:
+            table = first["token_table"]
+            if any(bt.get("token_table") is not table for bt in batch_tensor_list):
+                raise ValueError("token_rows batches of one call must share one token_table")
+            self.set_token_table(table)
+        packed = by_rows or "sentences_packed" in first
         sents, lens = [], []
         off = 0
         b.n_heads = len(g.heads)
@@ -436,7 +452,7 @@ class Session(object):
             hb.sent_offset = off
             ln = np.asarray(bt["seq_lengths"])
             lens.append(ln)
-            s = bt["sentences_packed"] if packed else bt["sentences"]
+            s = bt["token_rows"] if by_rows else bt["sentences_packed"] if packed else bt["sentences"]
             sents.append(s)
             if not packed:
                 T = max(T, s.shape[1])
@@ -479,10 +495,15 @@ class Session(object):
                 sents = [np.pad(s, ((0, 0), (0, Tm - s.shape[1]), (0, 0))) for s in sents]
             x = _cabi.as_supported(np.concatenate(sents, 0))
             ln = _cabi.as_supported(np.concatenate(lens, 0))
-        if x.dtype.kind != "f":
+        if by_rows:
+            x = np.ascontiguousarray(x, dtype=np.int32)
+        elif x.dtype.kind != "f":
             x = x.astype(np.float32)
         keepalive += [x, ln]
-        b.sentences, b.sent_dtype, b.sent_packed = x.ctypes.data, _cabi.dtype_code(x), int(packed)
+        if by_rows:
+            b.token_rows, b.sentences, b.sent_packed = x.ctypes.data, None, 1
+        else:
+            b.sentences, b.sent_dtype, b.sent_packed = x.ctypes.data, _cabi.dtype_code(x), int(packed)
         b.seq_lengths, b.len_dtype = ln.ctypes.data, _cabi.dtype_code(ln)
         b.n_seqs = len(ln)
         b.padded_T = T if not packed else int(ln.max()) if len(ln) else 0
@@ -617,7 +638,7 @@ def get_pred_scores_mcc(task, encoding_scheme, sess, batch_size, ids, data_dict,
     for i in range(id_matrix.shape[0]):
         if log is not None:
             log.log_status('info', None, 'Predicting; %d batches complete (%.2f%%)', i, 100.0 * i / id_matrix.shape[0])
-        bt = nn_data.load_batch(list(id_matrix[i]), data_dict, task, n_classes)
+        bt = nn_data.load_batch(list(id_matrix[i]), data_dict, task, n_classes, packed=nn_data.default_packing())
         scores = run_op(sess, Op("predicted_proba", scope), [bt], 1.0, 1.0, encoding_scheme, [task], [scope], False)
         n_rows = len(scores) if i < id_matrix.shape[0] - 1 else batch_size - pad
         for j in range(n_rows):

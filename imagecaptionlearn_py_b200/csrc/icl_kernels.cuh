@@ -244,12 +244,14 @@ __device__ __forceinline__ long token_row(const StepLayout& L, int dir, int s, i
 // (core.py:309-312), written to each direction's step-major row; TF32-rounded when the rows feed the tensor cores.
 __global__ void k_prep_x(const float* __restrict__ xraw, const int* __restrict__ tok_seq, const int* __restrict__ tokstart,
                          StepLayout L, int ntok, int E, int Tcap, int data_norm, float keep_in, uint64_t seed,
-                         int64_t seq_gid0, int round_ops, float* __restrict__ xfw, float* __restrict__ xbw, int ldx, int ones_col) {
+                         int64_t seq_gid0, int round_ops, float* __restrict__ xfw, float* __restrict__ xbw, int ldx, int ones_col,
+                         const int* __restrict__ tok_row, const float* __restrict__ table) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= ntok) return;
   int s = tok_seq[warp];
   int t = warp - tokstart[s];
-  const float* src = xraw + (long)warp * E;
+  // the token's embedding row: from this batch's uploaded rows, or gathered from the device-resident token table
+  const float* src = tok_row ? table + (long)tok_row[warp] * E : xraw + (long)warp * E;
   float scale = 1.0f;
   if (data_norm) {
     float ss = 0.0f;

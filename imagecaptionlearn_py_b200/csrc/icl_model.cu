@@ -56,7 +56,7 @@ struct HeadIn {                                             // byte offsets into
 };
 struct InSet {
   char *d_blob = nullptr, *h_blob = nullptr;
-  size_t o_x = 0, o_lens = 0, o_rank = 0, o_tokstart = 0, o_tokseq = 0, o_off = 0, o_nact = 0, meta_off = 0, bytes = 0;
+  size_t o_x = 0, o_lens = 0, o_rank = 0, o_tokstart = 0, o_tokseq = 0, o_tokrow = 0, o_off = 0, o_nact = 0, meta_off = 0, bytes = 0;
   template <typename T> T* dev(size_t o) const { return reinterpret_cast<T*>(d_blob + o); }
   template <typename T> T* host(size_t o) const { return reinterpret_cast<T*>(h_blob + o); }
   cudaEvent_t ev_copied = nullptr, ev_done = nullptr, ev_stats = nullptr;
@@ -111,6 +111,9 @@ struct icl_model {
   float *xraw = nullptr, *xd[2] = {}, *Z[2] = {}, *Hx[2] = {}, *Hp[2] = {}, *Cc[2] = {}, *dHout[2] = {}, *dhrec[2] = {}, *dcc[2] = {},
         *R[2] = {};
   int *d_off = nullptr, *d_nact = nullptr, *d_rank = nullptr, *d_lens = nullptr, *d_tokseq = nullptr, *d_tokstart = nullptr;
+  // device-resident token table (icl_set_token_table): batches then carry int32 row numbers instead of embedding rows
+  float* tok_table = nullptr; int64_t tok_table_rows = 0;
+  int* d_tokrow = nullptr; bool use_rows = false;
   InSet in[2];
   int cur = -1;                                         // input set of the resident batch
   cudaStream_t copy = nullptr;
@@ -349,6 +352,7 @@ static void use_input_set(icl_model* m, int s) {
   InSet& I = m->in[s];
   m->xraw = I.dev<float>(I.o_x); m->d_off = I.dev<int>(I.o_off); m->d_nact = I.dev<int>(I.o_nact); m->d_rank = I.dev<int>(I.o_rank);
   m->d_lens = I.dev<int>(I.o_lens); m->d_tokseq = I.dev<int>(I.o_tokseq); m->d_tokstart = I.dev<int>(I.o_tokstart);
+  m->d_tokrow = I.dev<int>(I.o_tokrow);
   for (Head& h : m->heads) {
     HeadIn& hin = h.in[s];
     for (int i = 0; i < ICL_N_INDEX; i++) h.idx[i] = I.dev<int>(hin.idx[i]);
@@ -392,7 +396,7 @@ extern "C" void icl_destroy(icl_model* m) {
   if (!m) return;
   cudaDeviceSynchronize();
   auto F = [](void* p) { if (p) cudaFree(p); };
-  F(m->P); F(m->G); F(m->Pr);
+  F(m->P); F(m->G); F(m->Pr); F(m->tok_table);
   if (m->slots.empty()) { F(m->M); F(m->V); }
   else {                       // m->M / m->V alias the live slot
     m->slots[m->cur_slot].M = m->M; m->slots[m->cur_slot].V = m->V;
@@ -528,6 +532,7 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
       hin.feats = take(B * h.c.n_feats * 4); hin.box = take(B * h.c.box_width * 4); hin.bfeats = take(B * h.c.n_box_feats * 4);
       hin.labels = take(B * h.c.n_classes * 4);
     }
+    I.o_tokrow = take((size_t)m->Ntok_cap * 4);
     I.o_tokseq = take((size_t)m->Ntok_cap * 4);              // last: only its used prefix is copied
     I.bytes = o;
     CKD(cudaMalloc((void**)&I.d_blob, I.bytes));
@@ -560,6 +565,18 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   if (m->rp_U && rec_init(m) != 0) { icl_destroy(m); *out = nullptr; return -1; }
   if (bptt_init(m) != 0) { icl_destroy(m); *out = nullptr; return -1; }
 #undef CKD
+  return 0;
+}
+
+// Device-resident token table [n_rows, E] (fp32): e.g. every caption matrix of the corpus concatenated (nn_utils/data.py keeps
+// them per caption in data_dict['sentences']), uploaded ONCE; batches then reference rows (icl_batch.token_rows).
+extern "C" int icl_set_token_table(icl_model* m, const float* table, int64_t n_rows) {
+  CK(cudaStreamSynchronize(m->stream));
+  if (m->tok_table) { CK(cudaFree(m->tok_table)); m->tok_table = nullptr; m->tok_table_rows = 0; }
+  if (!table || n_rows <= 0) return 0;
+  CK(dmalloc(&m->tok_table, (size_t)n_rows * m->E));
+  CK(cudaMemcpy(m->tok_table, table, (size_t)n_rows * m->E * 4, cudaMemcpyHostToDevice));
+  m->tok_table_rows = n_rows;
   return 0;
 }
 
@@ -620,8 +637,11 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
   int S = b->n_seqs, E = m->E;
   if (S < 1 || S > m->S_cap) return fail("icl_upload: n_seqs=%d exceeds capacity %d", S, m->S_cap);
   if (b->n_heads != m->cfg.n_heads) return fail("icl_upload: batch has %d heads, model has %d", b->n_heads, m->cfg.n_heads);
-  if (!b->sent_packed && (b->padded_T < 1 || b->padded_T > m->T_cap)) return fail("icl_upload: padded_T=%d exceeds capacity %d", b->padded_T, m->T_cap);
-  int T = b->sent_packed ? m->T_cap : b->padded_T;
+  const bool by_rows = b->token_rows != nullptr;
+  if (by_rows && !m->tok_table) return fail("icl_upload: token_rows given but no token table was set (icl_set_token_table)");
+  if (!by_rows && !b->sentences) return fail("icl_upload: neither sentences nor token_rows given");
+  if (!by_rows && !b->sent_packed && (b->padded_T < 1 || b->padded_T > m->T_cap)) return fail("icl_upload: padded_T=%d exceeds capacity %d", b->padded_T, m->T_cap);
+  int T = (by_rows || b->sent_packed) ? m->T_cap : b->padded_T;
   // next input set: its pinned staging is free once the copies issued from it two uploads ago have completed, its device
   // buffers once the step that consumed them has (the copy stream waits for that; the host does not)
   const int set = (m->cur + 1) & 1;
@@ -655,11 +675,21 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
   for (int k = 0; k <= tmax; k++) { offs[k] = m->off[k]; nact[k] = m->n_active[k]; }
   // pack valid tokens (caption-major) into pinned memory as fp32
   size_t esz = b->sent_dtype == ICL_F64 ? 8 : 4;
-  if (b->sent_dtype != ICL_F32 && b->sent_dtype != ICL_F64) return fail("icl_upload: sentences must be float32/float64");
+  if (!by_rows && b->sent_dtype != ICL_F32 && b->sent_dtype != ICL_F64) return fail("icl_upload: sentences must be float32/float64");
   // pack + convert on several host threads, in chunks, so the H2D copy of chunk i overlaps the packing of chunk i+1
   cudaStream_t st = m->copy;
   CK(cudaEventRecord(I.ev_c0, st));
-  {
+  m->use_rows = by_rows;
+  if (by_rows) {                      // packed caption-major row numbers into the resident token table: 4 bytes per token
+    int* tokrow = I.host<int>(I.o_tokrow);
+    for (int s = 0; s < S; s++)
+      for (int t = 0; t < lens[s]; t++) {
+        const int32_t r = b->token_rows[tokstart[s] + t];
+        if (r < 0 || r >= m->tok_table_rows) return fail("icl_upload: token_rows[%d]=%d outside the token table [0,%lld)", tokstart[s] + t, r, (long long)m->tok_table_rows);
+        tokrow[tokstart[s] + t] = r;
+        tokseq[tokstart[s] + t] = s;
+      }
+  } else {
     const int n_chunks = ntok * (long)E * 4 > (4 << 20) ? 8 : 1;
     int s0 = 0;
     for (int c = 0; c < n_chunks; c++) {
@@ -793,7 +823,8 @@ static int lstm_forward(icl_model* m, float keep_in, uint64_t seed, int training
   if (Ntok == 0) return 0;
   PH_BEGIN(m, PH_PREP);
   k_prep_x<<<(unsigned)((Ntok * 32 + 255) / 256), 256, 0, st>>>(m->xraw, m->d_tokseq, m->d_tokstart, mk_layout(m), (int)Ntok, E, m->T_cap,
-                                                               m->cfg.data_norm, keep_in, seed, m->seq_gid0, m->round_ops, m->xd[0], m->xd[1], m->ldx, E + H);
+                                                               m->cfg.data_norm, keep_in, seed, m->seq_gid0, m->round_ops, m->xd[0], m->xd[1], m->ldx, E + H,
+                                                               m->use_rows ? m->d_tokrow : nullptr, m->tok_table);
   LAUNCHED(m);
   for (int d = 0; d < 2; d++) {
     k_zero_pad_rows<<<m->Tmax, 256, 0, st>>>(m->XH[d], mk_layout(m), m->ldx); LAUNCHED(m);

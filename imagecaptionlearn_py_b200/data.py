@@ -31,11 +31,20 @@ def _flat_table(data_dict):
     return ft
 
 
+def default_packing():
+    """What the drop-in drivers ask `load_batch` for: "rows" (device-resident token table, 4 bytes per token on the wire) unless
+    ICL_HOST_SENTENCES=1 asks for the reference's padded [S,T,300] host tensor."""
+    import os
+    return False if os.environ.get("ICL_HOST_SENTENCES") else "rows"
+
+
 def load_batch(ids, data_dict, task, n_classes, packed=False):
     """Vectorised equivalent of nn_utils/data.py:349-528.
 
-    packed=True additionally returns 'sentences_packed' [sum(len),E] (caption-major valid tokens) and skips
-    materialising the zero-padded 'sentences' tensor -- the fast path `core.run_op` understands."""
+    packed=True returns 'sentences_packed' [sum(len),E] (caption-major valid tokens) instead of materialising the zero-padded
+    'sentences' tensor; packed="rows" returns 'token_rows' (int32 [sum(len)], row numbers into 'token_table' = the corpus'
+    caption matrices concatenated, which `core.Session` keeps resident on the device).  `core.run_op` understands all three;
+    the integer index matrices, lengths, features and labels are identical in every mode."""
     B = len(ids)
     cross = task == "rel_cross"
     n_seq = 2 * B if cross else B
@@ -62,7 +71,10 @@ def load_batch(ids, data_dict, task, n_classes, packed=False):
     src = np.repeat(ol[:, 0], lens) + cols
 
     out = {}
-    if packed:
+    if packed == "rows":
+        out["token_rows"] = src.astype(np.int32)
+        out["token_table"] = flat
+    elif packed:
         out["sentences_packed"] = flat[src]
     else:
         sent = np.zeros([n_seq, T, E], np.float32)

@@ -105,7 +105,8 @@ def train_loop(task, args, data_dict, eval_dict, classes, ids, log, shuffle=None
             ids = shuffle(ids) if shuffle else list(np.random.permutation(np.asarray(ids, dtype=object)))
             n_iter = len(ids) // args.batch_size                     # the tail batch is dropped (py2 integer division)
             for j in range(n_iter):
-                bt = nn_data.load_batch(ids[j * args.batch_size:(j + 1) * args.batch_size], data_dict, task, n_classes)
+                bt = nn_data.load_batch(ids[j * args.batch_size:(j + 1) * args.batch_size], data_dict, task, n_classes,
+                                        packed=nn_data.default_packing())
                 nn_util.run_op(sess, train_op, [bt], args.lstm_input_dropout, args.dropout, args.encoding_scheme, [task], [""], True)
                 if (j + 1) % 100 == 0 or j == n_iter - 1:
                     losses.append(nn_util.run_op(sess, loss_op, [bt], args.lstm_input_dropout, args.dropout,
@@ -332,6 +333,8 @@ def mt_load_data(args, data, split, label_file=None):
     d, root = args.data_dir + "/", data + "_" + split
     emb = load_embeddings(args, args.data_dir, root)
     out = {}
+    sent = loaders.load_sentences(d + "raw/" + root + "_captions.txt", emb)       # one caption file for all five tasks
+    nn_data._flat_table(sent)                                                    # ... and one token table (resident on the device)
     for task in MT_TASKS:
         if task.startswith("rel"):
             midx = d + "raw/" + root + "_mentionPairs_" + task.split("_")[1] + ".txt"
@@ -339,7 +342,7 @@ def mt_load_data(args, data, split, label_file=None):
         else:
             midx = d + "raw/" + root + "_mentions_" + task + ".txt"
             froot = d + "feats/" + root + "_" + task
-        dd = loaders.load_sentences(d + "raw/" + root + "_captions.txt", emb)
+        dd = dict(sent)
         dd.update(loaders.load_mentions(midx, task, froot + ".feats", froot + "_meta.json", len(MT_CLASSES[task])))
         if task.startswith("rel"):
             lab = d + "raw/" + root + "_mentionPair_labels.txt"
@@ -448,7 +451,7 @@ def main_multitask(argv=None):
                     order = np.random.permutation(len(batches))
                     for j in order:
                         task, row = batches[j]
-                        bt = nn_data.load_batch(row, dicts[task], task, len(MT_CLASSES[task]))
+                        bt = nn_data.load_batch(row, dicts[task], task, len(MT_CLASSES[task]), packed=nn_data.default_packing())
                         nn_util.run_op(sess, train_ops[task], [bt], args.lstm_input_dropout, args.dropout, args.encoding_scheme,
                                        [task], [task], True)
                 else:                                                   # icl_multitask_lstm.py:268-323
@@ -469,7 +472,7 @@ def main_multitask(argv=None):
                                 rem = st + B - n + 1
                                 row = list(t_ids[st:n - 1]) + list(t_ids[0:rem])
                                 pos[task] = rem
-                            bts.append(nn_data.load_batch(row, dicts[task], task, len(MT_CLASSES[task])))
+                            bts.append(nn_data.load_batch(row, dicts[task], task, len(MT_CLASSES[task]), packed=nn_data.default_packing()))
                         nn_util.run_op(sess, train_op, bts, args.lstm_input_dropout, args.dropout, args.encoding_scheme, MT_TASKS,
                                        MT_TASKS, True)
                 log.info("Saving model")

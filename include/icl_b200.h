@@ -78,6 +78,8 @@ typedef struct icl_head_batch {
 typedef struct icl_batch {
   const void* sentences;  int32_t sent_dtype;   /* padded [S,T,E] (sent_packed=0) or packed [sum(len),E] (=1) */
   int32_t sent_packed;
+  const int32_t* token_rows;                    /* or (sentences == NULL): packed caption-major [sum(len)] row numbers into the
+                                                   device-resident token table (icl_set_token_table) -- 4 bytes per token on the wire */
   const void* seq_lengths; int32_t len_dtype;   /* [S] */
   int32_t n_seqs, padded_T;
   int64_t seq_gid_offset, ex_gid_offset;        /* global ids of row 0 (dropout RNG is keyed on global ids) */
@@ -97,6 +99,9 @@ const char* icl_last_error(void);
 int icl_version(void);
 int icl_create(const icl_config* cfg, icl_model** out);          /* replaces graph construction, core.py:271-514,74-106 */
 void icl_destroy(icl_model* m);
+/* corpus cache: the embedding rows of every caption token, concatenated, stay resident in HBM;
+   nn_utils/data.py:397-403 copies them row by row into a fresh [S,T,300] tensor per batch instead */
+int icl_set_token_table(icl_model* m, const float* table_rows_by_E, int64_t n_rows);
 int icl_set_stream(icl_model* m, void* cuda_stream);             /* cudaStream_t of the caller (e.g. torch's current) */
 
 /* parameters are named like the TF variables so checkpoints map 1:1 (tf.train.Saver, icl_core_lstm.py:107,155) */

@@ -105,3 +105,30 @@ def test_model_filename():
     assert D.build_model_filename(a, "rel_lstm") == (
         "flickr30k_train_rel_intra_lstm_flm_relu_epch100_lrn0.001_btch512_drp5050_lstm200_hdn1024-3_"
         "admEps1e-08_clip5.0_dataNorm_early.model")
+
+
+def test_token_rows_mode_addresses_the_same_embedding_rows():
+    """load_batch(packed="rows"): 'token_rows' index the concatenated caption matrices ('token_table') and reproduce the packed /
+    padded sentence tensors exactly; every other entry of the dict is identical."""
+    from imagecaptionlearn_py_b200 import data as nn_data
+    from imagecaptionlearn_py_b200 import synth
+    corpus = synth.make_corpus(6, seed=11)
+    for task in ("card", "rel_cross"):
+        dd = synth.make_data_dict(corpus, task, F=8)
+        ids = synth.example_ids(dd, task)[:24]
+        C = synth.N_CLASSES[task]
+        a = nn_data.load_batch(ids, dd, task, C)
+        b = nn_data.load_batch(ids, dd, task, C, packed=True)
+        c = nn_data.load_batch(ids, dd, task, C, packed="rows")
+        assert c["token_rows"].dtype == np.int32 and c["token_table"].dtype == np.float32
+        assert np.array_equal(c["token_table"][c["token_rows"]], b["sentences_packed"])
+        lens = a["seq_lengths"]
+        rebuilt = np.zeros_like(a["sentences"])
+        pos = 0
+        for s, l in enumerate(lens):
+            rebuilt[s, :l] = c["token_table"][c["token_rows"][pos:pos + l]]
+            pos += l
+        assert np.array_equal(rebuilt, a["sentences"])
+        for k in a:
+            if k != "sentences":
+                assert np.array_equal(a[k], c[k]), k

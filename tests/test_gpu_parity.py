@@ -463,3 +463,33 @@ def test_weighted_joint_scheme_matches_oracle():
         err = np.max(np.abs((got - start[name]) - (ref - start[name])))
         assert err < 0.05 * 1e-3 + 1e-6, (name, err)
     sess.close()
+
+
+def test_resident_token_table_gives_identical_results():
+    """The corpus cache (icl_set_token_table + 'token_rows'): the embedding rows are gathered on the device from the resident
+    table instead of being uploaded with every batch -- same rows, same kernels, bit-identical probabilities and gradients."""
+    from imagecaptionlearn_py_b200 import _cabi, core, synth
+    from imagecaptionlearn_py_b200 import data as nn_data
+    corpus = synth.make_corpus(8, seed=13, E=12)
+    dd = synth.make_data_dict(corpus, "card", F=8)
+    ids = synth.example_ids(dd, "card")[:32]
+    res = {}
+    for mode in (False, True, "rows"):
+        bt = nn_data.load_batch(ids, dd, "card", 12, packed=mode)
+        core.reset_default_graph()
+        core.set_random_seeds()
+        with core.variable_scope("bidirectional_lstm"):
+            core.setup_bidirectional_lstm(8, True, n_embedding_width=12)
+        core.setup_core_architecture("card", "first_last_mention", 32, 16, 1, False, "relu", 12, 8)
+        core.add_train_op(core.get_collection("loss")[0], 1e-3, 1e-8, 5.0)
+        sess = core.Session(max_seq_len=dd["max_seq_len"], gemm_mode=_cabi.GEMM_SIMT_FP32)
+        sess.ensure()
+        sess.initialize()
+        sess.base_seed, sess.run_counter = 9, 0
+        r = sess.run(_cabi.OP_GRADS, [bt], 0.5, 0.5, True)[0]
+        res[mode] = (r["proba"].copy(), {n: sess.get_tensor(n, 1) for n, _, _, _ in sess.param_info()})
+        sess.close()
+    for mode in (True, "rows"):
+        assert np.array_equal(res[mode][0], res[False][0])
+        for k, v in res[False][1].items():
+            assert np.array_equal(res[mode][1][k], v), k
