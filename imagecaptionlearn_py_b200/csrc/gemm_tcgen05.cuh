@@ -11,6 +11,7 @@
 // Configurations (picked per call by tcgen05_gemm_launch):
 //   <128,3>  97 KB smem, two CTAs per SM: many-tile GEMMs, one CTA's epilogue overlaps the other's main loop
 //   <128,6> 193 KB smem, one CTA per SM: few tiles with a long K loop -- latency-bound, so a deeper ring
+//   <64,4>   97 KB / <64,8> 193 KB: narrow tiles for few-tile problems (the head layers): more CTAs share the streaming
 //   <256,2>  97 KB / <256,4> 193 KB: wide tiles halve the L2->SM bytes per MMA cycle (TF32 tiles of 128x128 need ~128 B/clk
 //            per SM, more than one SM can ingest); used when N >= 512.
 // Epilogue: TMEM -> registers (one accumulator row per thread) -> a per-warp 32x33 staging tile in the (by then idle)
@@ -317,6 +318,8 @@ template <bool A_MN, bool B_MN> static cudaError_t tg_set_attrs() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tcgen05<A_MN, B_MN, 128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg_smem(128, 6));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tcgen05<A_MN, B_MN, 256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg_smem(256, 2));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tcgen05<A_MN, B_MN, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg_smem(256, 4));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tcgen05<A_MN, B_MN, 64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg_smem(64, 4));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tcgen05<A_MN, B_MN, 64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg_smem(64, 8));
   return e;
 }
 static int tcgen05_gemm_init() {
@@ -377,13 +380,22 @@ template <bool A_MN, bool B_MN>
 static void tg_dispatch(int BN, bool deep, dim3 grid, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g,
                         bool pdl) {
   if (BN == 256) { if (deep) tg_launch<A_MN, B_MN, 256, 4>(grid, st, ta, tb, g, pdl); else tg_launch<A_MN, B_MN, 256, 2>(grid, st, ta, tb, g, pdl); }
+  else if (BN == 64) { if (deep) tg_launch<A_MN, B_MN, 64, 8>(grid, st, ta, tb, g, pdl); else tg_launch<A_MN, B_MN, 64, 4>(grid, st, ta, tb, g, pdl); }
   else { if (deep) tg_launch<A_MN, B_MN, 128, 6>(grid, st, ta, tb, g, pdl); else tg_launch<A_MN, B_MN, 128, 3>(grid, st, ta, tb, g, pdl); }
 }
 
 // splits == 0: choose a split-K factor for few-tile / long-K problems (the caller must then accept a red.global epilogue)
 static int tcgen05_gemm_launch(TmaCache& cache, cudaStream_t st, bool a_mn, bool b_mn, const GemmArgs& g, int splits = 1,
                                bool pdl = false) {
-  const int BN = g.N >= 512 ? 256 : 128;
+  // tile width: the widest of 256 / 128 / 64 that still yields about a wave of CTAs.  The head GEMMs (M = batch, N <= 512) are
+  // bound by what ONE CTA can stream through its ring, not by the tensor pipe: 2048x1456x512 as 32 CTAs of 128x256 took 57 us
+  const int rows_t = (g.M + TG_BM - 1) / TG_BM;
+  auto tiles_for = [&](int bn) { return (long)rows_t * ((g.N + bn - 1) / bn) * splits; };
+  int BN = g.N >= 512 ? 256 : 128;
+  if (getenv("ICL_GEMM_NO_BN64") == nullptr) {
+    if (BN == 256 && tiles_for(256) < 100) BN = 128;
+    if (BN == 128 && tiles_for(128) < 100 && g.N > 64) BN = 64;
+  }
   CUtensorMap ta, tb;
   int r;
   const int swk = (int)CU_TENSOR_MAP_SWIZZLE_128B, swmn = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
