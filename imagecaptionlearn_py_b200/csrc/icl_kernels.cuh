@@ -486,6 +486,20 @@ __global__ void k_softmax_ce(const float* __restrict__ a, int K, const float* __
   if (y) { row_loss[b] = loss * scale; row_correct[b] = (am == ay) ? 1.0f : 0.0f; }
 }
 
+// deterministic single-block sums: block 0 sums v0 into out[0], block 1 sums v1 into out[1] divided by mean_div
+__global__ void k_reduce_sum2(const float* __restrict__ v0, const float* __restrict__ v1, int n, float* out, float mean_div1) {
+  __shared__ double sh[256];
+  const float* v = blockIdx.x ? v1 : v0;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = (float)(blockIdx.x && mean_div1 > 0 ? sh[0] / mean_div1 : sh[0]);
+}
 // deterministic single-block sum of n floats into out[0] (divided by mean_div when > 0)
 __global__ void k_reduce_sum(const float* __restrict__ v, int n, float* out, float mean_div) {
   __shared__ double sh[256];

@@ -260,7 +260,8 @@ __global__ void k_zero_words(uint32_t* __restrict__ p, size_t n_words) {
     for (size_t i = i0; i < n_words; i += stride) p[i] = 0u;
   }
 }
-__global__ void k_zero_2d(float* __restrict__ p, long pitch, int width, long rows) {   // width, pitch in floats (multiples of 4)
+__global__ void k_zero_2d(float* __restrict__ p0, float* __restrict__ p1, long pitch, int width, long rows) {   // floats, % 4 == 0
+  float* p = blockIdx.y ? p1 : p0;
   const long w4 = width >> 2, n = rows * w4;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
     *reinterpret_cast<float4*>(p + (i / w4) * pitch + (i % w4) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -770,8 +771,9 @@ static int refresh_rounded_params(icl_model* m) {
 }
 
 // rows [nact[k], padded end) of every step block -> 0 (operands of the time-batched weight-gradient GEMMs)
-__global__ void k_zero_pad_rows(float* __restrict__ buf, StepLayout L, int W) {
+__global__ void k_zero_pad_rows(float* __restrict__ buf0, float* __restrict__ buf1, StepLayout L, int W) {
   const int k = blockIdx.x;
+  float* buf = blockIdx.y ? buf1 : buf0;
   const long r0 = (long)L.off[k] + L.nact[k], r1 = L.off[k + 1];
   float4* p = reinterpret_cast<float4*>(buf + r0 * W);
   const long n4 = (r1 - r0) * W / 4;
@@ -826,11 +828,9 @@ static int lstm_forward(icl_model* m, float keep_in, uint64_t seed, int training
                                                                m->cfg.data_norm, keep_in, seed, m->seq_gid0, m->round_ops, m->xd[0], m->xd[1], m->ldx, E + H,
                                                                m->use_rows ? m->d_tokrow : nullptr, m->tok_table);
   LAUNCHED(m);
-  for (int d = 0; d < 2; d++) {
-    k_zero_pad_rows<<<m->Tmax, 256, 0, st>>>(m->XH[d], mk_layout(m), m->ldx); LAUNCHED(m);
-    // h_prev of step 0 is the zero state: step 0's block of Hp stays zero (these are A rows of dW_hh)
-    k_zero_2d<<<148, 256, 0, st>>>(m->Hp[d], m->ldx, H, m->off[1]); LAUNCHED(m);
-  }
+  k_zero_pad_rows<<<dim3(m->Tmax, 2), 256, 0, st>>>(m->XH[0], m->XH[1], mk_layout(m), m->ldx); LAUNCHED(m);
+  // h_prev of step 0 is the zero state: step 0's block of Hp stays zero (these are A rows of dW_hh)
+  k_zero_2d<<<dim3(74, 2), 256, 0, st>>>(m->Hp[0], m->Hp[1], m->ldx, H, m->off[1]); LAUNCHED(m);
   PH_END(m, PH_PREP);
   // K1: time-batched input projection  Z = Xd * W_ih + b   (W_ih = kernel rows [0,E)), both directions
   PH_BEGIN(m, PH_PROJ);
@@ -901,16 +901,14 @@ static int heads_forward(icl_model* m, float keep, uint64_t seed) {
                                                       h.row_correct, h.dlogits);
     LAUNCHED(m);
     if (h.has_labels) {
-      k_reduce_sum<<<1, 256, 0, st>>>(h.row_loss, B, h.scalars, 0.f); LAUNCHED(m);
-      k_reduce_sum<<<1, 256, 0, st>>>(h.row_correct, B, h.scalars + 1, (float)B); LAUNCHED(m);
+      k_reduce_sum2<<<2, 256, 0, st>>>(h.row_loss, h.row_correct, B, h.scalars, (float)B); LAUNCHED(m);   // loss sum, accuracy mean
     }
   }
   PH_END(m, PH_HEADS_FWD);
   return 0;
 }
 
-static int colsum(icl_model* m, cudaStream_t st, const float* X, long rows, int N, long ld, float* out) {
-  CK(zero_async(out, (size_t)N * 4, st));
+static int colsum(icl_model* m, cudaStream_t st, const float* X, long rows, int N, long ld, float* out) {   // out pre-zeroed
   int rpb = 64;
   dim3 grid((N + 127) / 128, (unsigned)((rows + rpb - 1) / rpb));
   k_colsum_atomic<<<grid, 128, 0, st>>>(X, rows, N, ld, out, rpb);
@@ -935,6 +933,10 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
     }
     if (!h.has_labels) return fail("backward needs labels for head %zu", hi);
     int B = h.c.batch_size, L = h.c.n_hidden;
+    {   // ONE zero fill of the head's whole gradient range (split-K weight gradients and bias column sums accumulate into it)
+      const int64_t g0 = m->params[h.pW[0]].off, g1 = hi + 1 < m->heads.size() ? m->params[m->heads[hi + 1].pW[0]].off : m->n_params;
+      CK(zero_async(m->G + g0, (size_t)(g1 - g0) * 4, st));
+    }
     const float* dz = h.dlogits;       // gradient w.r.t. the pre-activation of layer k+1 (softmax layer first)
     float* bufs[2] = {h.dA, h.dBuf};
     int cur = 0;
@@ -944,7 +946,7 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
       const Param& pw = m->params[h.pW[k]];
       // dW = in^T * dz   (contraction over the batch: both operands MN-major)
       GemmArgs gw = mk_gemm(in, din, dz, dout, m->G + pw.off, dout, din, dout, B);
-      CKI(gemm(m, st, true, true, gw, -1, 0));
+      CKI(gemm(m, st, true, true, gw, -1, 0, true));
       CKI(colsum(m, st, dz, B, dout, dout, m->G + m->params[h.pB[k]].off));
       // d(in) = dz * W^T  (W [din,dout] row-major is K-major as the B operand)
       if (k > 0) {
@@ -1096,7 +1098,7 @@ static int lstm_backward(icl_model* m) {
     if (m->rp_U != 0 && m->rp_on && m->rp_bwd_on && m->Tmax <= RP_MAXT) CKI(rec_backward_persistent(m));
     else CKI(rec_backward_steps(m));
     // pad rows of dZ must be exactly zero for the time-batched weight-gradient GEMM (they still hold gates / Zx)
-    for (int d = 0; d < 2; d++) { k_zero_pad_rows<<<m->Tmax, 256, 0, st>>>(m->Z[d], mk_layout(m), 4 * H); LAUNCHED(m); }
+    k_zero_pad_rows<<<dim3(m->Tmax, 2), 256, 0, st>>>(m->Z[0], m->Z[1], mk_layout(m), 4 * H); LAUNCHED(m);
   }
   PH_END(m, PH_REC_BWD);
   // time-batched weight gradients: ONE split-K GEMM per direction (contraction over all tokens)
