@@ -384,7 +384,8 @@ static int bptt_init(icl_model* m) {
       cudaFuncSetAttribute(k_bptt_step<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM) != cudaSuccess ||
       cudaFuncSetAttribute(k_bptt_step<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM) != cudaSuccess)
     return fail("cudaFuncSetAttribute(k_bptt_step) failed");
-  if (cudaFuncSetAttribute(k_bptt_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM) != cudaSuccess)
+  if (cudaFuncSetAttribute(k_bptt_cluster<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(k_bptt_cluster<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM) != cudaSuccess)
     return fail("cudaFuncSetAttribute(k_bptt_cluster) failed");
   return 0;
 }
@@ -1031,13 +1032,19 @@ static int rec_backward_cluster(icl_model* m) {
   for (int d = 0; d < 2; d++) { a.Z[d] = m->Z[d]; a.Cc[d] = m->Cc[d]; a.dHout[d] = m->dHout[d]; a.dcc[d] = m->dcc[d]; }
   a.off = m->d_off; a.nact = m->d_nact; a.H = H; a.Tmax = m->Tmax; a.round_ops = m->round_ops;
   a.trace = m->rp_trace; a.trace_cta = m->rp_trace_cta;
+  // the chain of the longest sequences (T_max dependent steps) bounds the launch, so 8 CTAs per tile (half the contraction and
+  // half the cell-backward rows per CTA and step) beat 4 even when the 2 x tiles clusters no longer fit at once (measured:
+  // B=512: 0.41 -> 0.30 ms, B=2048: 0.50 -> 0.48 ms); clusters are independent, so later ones simply start as earlier ones end
+  const int tiles = (m->n_active[0] + 127) / 128;
+  int cs = 8;
+  if (const char* e = getenv("ICL_BPTT_CLUSTER_CS")) cs = atoi(e) == 8 ? 8 : 4;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(BC_CS, (unsigned)((m->n_active[0] + 127) / 128), 2);
+  cfg.gridDim = dim3(cs, (unsigned)(2 * tiles), 1);
   cfg.blockDim = dim3(BC_THREADS); cfg.dynamicSmemBytes = BC_SMEM; cfg.stream = st;
   cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = BC_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, k_bptt_cluster, m->bp_maps, a);
+  cudaError_t e = cs == 8 ? cudaLaunchKernelEx(&cfg, k_bptt_cluster<8>, m->bp_maps, a) : cudaLaunchKernelEx(&cfg, k_bptt_cluster<4>, m->bp_maps, a);
   if (e != cudaSuccess) return fail("k_bptt_cluster launch failed: %s", cudaGetErrorString(e));
   m->launches++;
   return 0;

@@ -253,18 +253,18 @@ __global__ void __launch_bounds__(BP_THREADS, 2) k_bptt_step(const __grid_consta
 //
 // dZ_k of a row tile depends only on dZ_{k+1} of the SAME rows, so a cluster that owns a row tile can walk all of its time
 // steps with nothing but cluster barriers -- no grid barrier, no flags in global memory, no launch per step.  Per step:
-//   K-loop   : the cluster's 4 CTAs split the contraction (K = 4H) into k-block ranges; per k-block one TMA box of dZ_{k+1}
+//   K-loop   : the cluster's CS (4, or 8 when the batch has few row tiles) CTAs split the contraction (K = 4H) into k-block ranges; per k-block one TMA box of dZ_{k+1}
 //              [128 x 32] and three boxes of W_hh [112 units x 32] feed UMMAs into THREE TMEM accumulators (all H <= 336 units
 //              of the tile: dZ is read once, not once per 112-unit column tile as in k_bptt_step);
 //   park     : TMEM -> the CTA's own (idle) operand ring as a [128 x 340] fp32 tile;             cluster barrier S1
-//   pull     : every CTA finishes 32 rows: it sums the 4 partials of its rows with coalesced ld.shared::cluster
+//   pull     : every CTA finishes 128/CS rows: it sums the CS partials of its rows with coalesced ld.shared::cluster
 //              (barrier S2 = "my pulls are done", waited for before the ring is refilled);
 //   cell bwd : gates/c/dH rows (L2-prefetched one step ahead) -> dZ_k in place, dc carry;  fence.proxy.async + barrier S3
 //              make dZ_k visible to the TMA loads of step k-1 issued by the other CTAs of the cluster.
 // Clusters are independent: the launch needs no co-residency (a batch with more than 18 row tiles per direction simply
 // runs in waves).
 // =====================================================================================================================
-constexpr int BC_CS = 4, BC_NACC = 3, BC_STAGES = 3, BC_THREADS = 320;
+constexpr int BC_NACC = 3, BC_STAGES = 3, BC_THREADS = 320;     // cluster size CS = 4 or 8 (template parameter)
 constexpr int BC_STAGE_BYTES = BP_A_BYTES + BC_NACC * BP_B_BYTES;          // 16 KB + 3 x 14 KB
 constexpr int BC_PARK_LD = BC_NACC * BP_BN + 4;                            // 340 floats per parked row
 constexpr int BC_SMEM = 1024 + BC_STAGES * BC_STAGE_BYTES + 128;
@@ -274,12 +274,13 @@ struct BpttClusterArgs {
   float* Z[2]; const float* Cc[2]; const float* dHout[2]; float* dcc[2];
   const int* off; const int* nact;       // [Tmax+1] step offsets / running rows
   int H, Tmax, round_ops;
-  long long* trace; int trace_cta;      // optional bring-up trace (see Tracer): CTA index = (z * gridDim.y + y) * gridDim.x + x
+  long long* trace; int trace_cta;      // optional bring-up trace (see Tracer): CTA index = y * gridDim.x + x
 };
 
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
+template <int BC_CS>
 __global__ void __launch_bounds__(BC_THREADS, 1) k_bptt_cluster(const __grid_constant__ BpttMaps maps, const BpttClusterArgs g) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ int s_off[RP_MAXT + 2], s_n[RP_MAXT + 2];
@@ -289,7 +290,8 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bptt_cluster(const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = g.H, Tmax = g.Tmax, HQ = H >> 2;
   const int rank = (int)cluster_ctarank();
-  const int m0 = blockIdx.y * 128, d = blockIdx.z;
+  // grid.y = 2 * tiles with the direction in the low bit: the long chains (low tiles) of BOTH directions are scheduled first
+  const int m0 = (blockIdx.y >> 1) * 128, d = blockIdx.y & 1;
   const int total_kb = (4 * H + 31) / 32, kb_per = (total_kb + BC_CS - 1) / BC_CS;
   const int kb0 = rank * kb_per, num_kb = max(0, min(kb_per, total_kb - kb0));
   const int nacc = (H + BP_BN - 1) / BP_BN;                                   // accumulators in use (<= BC_NACC)
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bptt_cluster(const __grid_con
 
   Tracer tr;
   {
-    const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const int cta = blockIdx.y * gridDim.x + blockIdx.x;
     tr.p = (g.trace && cta == g.trace_cta && lane == 0 && warp <= 2) ? g.trace + (long)warp * RP_TRACE_EV * 4 : nullptr;
     tr.n = 0;
   }
