@@ -311,22 +311,43 @@ def main():
             pass
         bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)           # fallback: the profiling guide's sustained figure
         tf32_peak = bf16_peak / 2.0                                       # kind::tf32 issues at half the kind::f16 rate
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
         ph_ms = phases / args.steps
-        dom = int(np.argmax(ph_ms))
         H = wl["H"]
-        phase_flops = {                                                  # algorithmic FLOPs per step, per kernel group
-            "proj_gemm": 2.0 * n_tok * E * 4 * H * 2, "rec_fwd": 2.0 * n_tok * H * 4 * H * 2,
-            "rec_bwd": 2.0 * n_tok * H * 4 * H * 2, "wgrad": 2.0 * n_tok * (E + H) * 4 * H * 2}
-        name = _cabi.PHASES[dom]
-        roof = dict(kernel=name, bound="tensor", unit="TFLOP/s", peak=tf32_peak,
-                    peak_source=("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32 issues at half the bf16 rate)"
-                                 if peaks else "fallback 1400/2"), traffic=None,
-                    ms_per_launch_group=float(ph_ms[dom]))
-        if name in phase_flops:
-            roof["achieved"] = phase_flops[name] / (ph_ms[dom] * 1e-3) / 1e12
-            roof["frac"] = roof["achieved"] / tf32_peak
+        # ALGORITHMIC work per step of each kernel group: FLOPs of the contraction and the bytes that must
+        # cross HBM once (fp32), per valid token and direction, x 2 directions
+        tok2 = 2.0 * n_tok
+        work = {   # phase: (flops, bytes, kernel, launches of that kernel per step)
+            "proj_gemm": (tok2 * 2 * E * 4 * H, tok2 * (E + 4 * H) * 4, "k_gemm_tcgen05<0, 1, 256, 2>", 2),
+            "rec_fwd": (tok2 * 2 * H * 4 * H, tok2 * (4 * H + 4 * H + 3 * H) * 4, "k_rec_fwd", 1),        # Zx in; gates, c, h, TF32(h) out
+            "rec_bwd": (tok2 * 2 * H * 4 * H, tok2 * (4 * H + 3 * H + 4 * H) * 4, "k_bptt_cluster", 1),   # gates, c, c_prev, dH in; dZ out
+            "wgrad": (tok2 * 2 * (E + H) * 4 * H, tok2 * (E + H + 4 * H) * 4, "k_gemm_tcgen05<1, 1, 256, 4>", 2)}
+        dom = max(work, key=lambda k: ph_ms[_cabi.PHASES.index(k)])     # the dominant kernel group of the step
+        name = dom
+        t_ms = float(ph_ms[_cabi.PHASES.index(dom)])
+        flops, nbytes, kernel, n_launch = work[dom]
+        t_tensor, t_hbm = flops / (tf32_peak * 1e12), nbytes / (hbm_peak * 1e9)
+        traffic = None
+        try:       # DRAM bytes of that kernel from the committed `ncu --set full` capture of this workload (profiles/)
+            if args.workload == "card2048" and world == 1:
+                for e in json.load(open(os.path.join(ROOT, "profiles", "r1f_ncu_full_summary.json"))):
+                    if e["kernel"].startswith(kernel) and (dom != "wgrad" or e["grid"].replace(" ", "") == "(5,5,5)"):
+                        traffic = e["dram_bytes"]
+                        break
+        except Exception:
+            pass
+        if t_hbm >= t_tensor:
+            roof = dict(kernel=kernel, phase=name, bound="hbm", unit="GB/s", peak=hbm_peak,
+                        achieved=nbytes / n_launch / (t_ms / n_launch * 1e-3) / 1e9)
         else:
-            roof["achieved"], roof["frac"] = None, None
+            roof = dict(kernel=kernel, phase=name, bound="tensor", unit="TFLOP/s", peak=tf32_peak,
+                        achieved=flops / n_launch / (t_ms / n_launch * 1e-3) / 1e12)
+        roof.update(frac=roof["achieved"] / roof["peak"], traffic=traffic, launches_per_step=n_launch,
+                    ms_per_launch=t_ms / n_launch, algorithmic_bytes_per_launch=nbytes / n_launch, algorithmic_flops_per_launch=flops / n_launch,
+                    tensor_frac=flops / (t_ms * 1e-3) / 1e12 / tf32_peak, hbm_frac=nbytes / (t_ms * 1e-3) / 1e9 / hbm_peak,
+                    peak_source=("MEASURED_PEAKS.json: hbm_gbs; bf16_tflops_sustained / 2 for kind::tf32" if peaks
+                                 else "fallback 6650 GB/s, 1400/2 TFLOP/s"),
+                    note="time = CUDA events around the kernel group on its launch stream (icl_phase_ms), averaged over the timed steps")
         step_flops = flops_per_token(H) * n_tok
         line = dict(metric="bilstm_train_captions_per_sec", value=value, unit="captions/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
