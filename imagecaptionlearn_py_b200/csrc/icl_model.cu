@@ -1032,21 +1032,37 @@ static int rec_backward_cluster(icl_model* m) {
   for (int d = 0; d < 2; d++) { a.Z[d] = m->Z[d]; a.Cc[d] = m->Cc[d]; a.dHout[d] = m->dHout[d]; a.dcc[d] = m->dcc[d]; }
   a.off = m->d_off; a.nact = m->d_nact; a.H = H; a.Tmax = m->Tmax; a.round_ops = m->round_ops;
   a.trace = m->rp_trace; a.trace_cta = m->rp_trace_cta;
-  // the chain of the longest sequences (T_max dependent steps) bounds the launch, so 8 CTAs per tile (half the contraction and
-  // half the cell-backward rows per CTA and step) beat 4 even when the 2 x tiles clusters no longer fit at once (measured:
-  // B=512: 0.41 -> 0.30 ms, B=2048: 0.50 -> 0.48 ms); clusters are independent, so later ones simply start as earlier ones end
+  // The chain of the longest sequences (T_max dependent steps) bounds the phase: 8 CTAs per tile halve every step's contraction
+  // and cell-backward share (12 vs 20 us per step), but 2 x tiles x 8 CTAs do not fit at once for large batches.  So the first
+  // n8 tiles (the longest chains) run as 8-CTA clusters and the rest as 4-CTA clusters in a second, concurrent launch, sized so
+  // that all clusters are co-resident.  Clusters are independent of each other.
   const int tiles = (m->n_active[0] + 127) / 128;
-  int cs = 8;
-  if (const char* e = getenv("ICL_BPTT_CLUSTER_CS")) cs = atoi(e) == 8 ? 8 : 4;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cs, (unsigned)(2 * tiles), 1);
-  cfg.blockDim = dim3(BC_THREADS); cfg.dynamicSmemBytes = BC_SMEM; cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  cudaError_t e = cs == 8 ? cudaLaunchKernelEx(&cfg, k_bptt_cluster<8>, m->bp_maps, a) : cudaLaunchKernelEx(&cfg, k_bptt_cluster<4>, m->bp_maps, a);
-  if (e != cudaSuccess) return fail("k_bptt_cluster launch failed: %s", cudaGetErrorString(e));
-  m->launches++;
+  int n8 = std::max(0, std::min(tiles, (m->n_sms / 2 - 4 * tiles) / 4));
+  if (const char* e = getenv("ICL_BPTT_CLUSTER_CS")) n8 = atoi(e) == 8 ? tiles : atoi(e) == 4 ? 0 : n8;
+  if (const char* e = getenv("ICL_BPTT_N8")) n8 = std::max(0, std::min(tiles, atoi(e)));
+  auto launch = [&](int cs, int tile0, int ntiles, cudaStream_t s) -> int {
+    a.tile0 = tile0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs, (unsigned)(2 * ntiles), 1);
+    cfg.blockDim = dim3(BC_THREADS); cfg.dynamicSmemBytes = BC_SMEM; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cs == 8 ? cudaLaunchKernelEx(&cfg, k_bptt_cluster<8>, m->bp_maps, a) : cudaLaunchKernelEx(&cfg, k_bptt_cluster<4>, m->bp_maps, a);
+    if (e != cudaSuccess) return fail("k_bptt_cluster<%d> launch failed: %s", cs, cudaGetErrorString(e));
+    m->launches++;
+    return 0;
+  };
+  const bool two = n8 > 0 && n8 < tiles;
+  if (two) {
+    CK(cudaEventRecord(m->ev_fork, st));
+    CK(cudaStreamWaitEvent(m->aux, m->ev_fork, 0));
+    CKI(launch(4, n8, tiles - n8, m->aux));
+    CK(cudaEventRecord(m->ev_join, m->aux));
+  }
+  if (n8 > 0) CKI(launch(8, 0, n8, st));
+  else CKI(launch(4, 0, tiles, st));
+  if (two) CK(cudaStreamWaitEvent(st, m->ev_join, 0));
   return 0;
 }
 
