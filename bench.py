@@ -36,6 +36,7 @@ WORKLOADS = {
     "card2048": dict(task="card", B=2048, H=300, start=512, depth=2, C=12, F=256, data_norm=False, cfg="configs[1]"),
     "rel_intra512": dict(task="rel_intra", B=512, H=200, start=1024, depth=3, C=4, F=512, data_norm=True, cfg="configs[2]"),
     "rel_cross512": dict(task="rel_cross", B=512, H=200, start=1024, depth=3, C=4, F=512, data_norm=True, cfg="configs[2]"),
+    "card2048_h200": dict(task="card", B=2048, H=200, start=512, depth=2, C=12, F=256, data_norm=False, cfg="(bring-up)"),
     "affinity512": dict(task="affinity", B=512, H=300, start=512, depth=2, C=2, F=256, data_norm=False, cfg="configs[3]"),
 }
 E, T_PAD, KEEP_IN, KEEP = 300, 50, 0.5, 0.5

@@ -19,7 +19,7 @@ OP_PREDICT, OP_GRADS, OP_TRAIN = 0, 1, 2
 GEMM_TCGEN05_TF32, GEMM_SIMT_FP32 = 0, 1
 _DT = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.int32): 2, np.dtype(np.int64): 3}
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libicl_b200.so")
+LIB_PATH = os.environ.get("ICL_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libicl_b200.so")
 
 
 class HeadConfig(C.Structure):

@@ -321,8 +321,8 @@ static int box_map(icl_model* m, const float* ptr, uint64_t cols, uint64_t rows,
   return r ? fail("cuTensorMapEncodeTiled failed (%d) for a {%u,%u} box over [%llu,%llu]", r, box_c, box_r,
                   (unsigned long long)rows, (unsigned long long)cols) : 0;
 }
-template <int U> static int rec_set_attr() {
-  cudaError_t e = cudaFuncSetAttribute(k_rec_fwd<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, rec_fwd_smem<U>(10));
+template <int U> static int rec_set_attr(int nkb) {
+  cudaError_t e = cudaFuncSetAttribute(k_rec_fwd<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, rec_fwd_smem<U>(nkb));
   return e == cudaSuccess ? 0 : fail("cudaFuncSetAttribute(k_rec_fwd): %s", cudaGetErrorString(e));
 }
 static int rec_init(icl_model* m) {
@@ -345,7 +345,7 @@ static int rec_init(icl_model* m) {
   }
   if (cudaFuncSetAttribute(k_rec_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM) != cudaSuccess)
     return fail("cudaFuncSetAttribute(k_rec_bwd) failed");
-  return U == 20 ? rec_set_attr<20>() : rec_set_attr<16>();
+  return U == 20 ? rec_set_attr<20>(m->rp_nkb) : rec_set_attr<16>(m->rp_nkb);
 }
 
 // make input set s the "current" one: the device pointers every launch site reads

@@ -22,7 +22,10 @@
 
 namespace icl {
 
-constexpr int RP_ROWS = 128, RP_ASTAGES = 3, RP_THREADS = 224, RP_MAXT = 128, RP_MAXACC = 8;
+#ifndef RP_ASTAGES_OVERRIDE
+#define RP_ASTAGES_OVERRIDE 3
+#endif
+constexpr int RP_ROWS = 128, RP_ASTAGES = RP_ASTAGES_OVERRIDE, RP_THREADS = 224, RP_MAXT = 128, RP_MAXACC = 8;
 
 struct RecMaps {          // [direction]
   CUtensorMap a[2];       // A operand: box {32 k, 128 rows}, SWIZZLE_128B, over Hp (fwd) / unused (bwd)
@@ -139,8 +142,8 @@ __global__ void __launch_bounds__(RP_FWD_THREADS, 1) k_rec_fwd(const __grid_cons
   const uint32_t sA = sW + (uint32_t)g.nkb * N * 128;
   const uint32_t sE = sA + RP_ASTAGES * 16384;                           // 4 quarters x 7 boxes [32 rows x U]
   const uint32_t bars = sE + 7 * RP_ROWS * U * 4;
-  const uint32_t full0 = bars, empty0 = bars + 24, wfull = bars + 48, efull0 = bars + 56, tfull0 = bars + 56 + 8 * RP_EW,
-                 tempty0 = tfull0 + 8 * RP_MAXACC, tmem_slot = tempty0 + 8 * RP_MAXACC;
+  const uint32_t full0 = bars, empty0 = bars + 8 * RP_ASTAGES, wfull = bars + 16 * RP_ASTAGES, efull0 = wfull + 8,
+                 tfull0 = efull0 + 8 * RP_EW, tempty0 = tfull0 + 8 * RP_MAXACC, tmem_slot = tempty0 + 8 * RP_MAXACC;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per_dir = g.P * g.nsl;
   const int d = blockIdx.x / per_dir, p = (blockIdx.x % per_dir) / g.nsl, j = blockIdx.x % g.nsl;
