@@ -221,7 +221,7 @@ def main():
         seed = 1000 + i
         if dist:
             _cabi.check(L.icl_run_resident(sess.handle, _cabi.OP_GRADS, KEEP_IN, KEEP, seed))
-            dist.all_reduce(sess.grad_tensor(), op=dist.ReduceOp.SUM)
+            sess.allreduce_grads()          # heads' slice overlapped with the BPTT, LSTM slice after it
             _cabi.check(L.icl_apply_update(sess.handle))
         else:
             _cabi.check(L.icl_run_resident(sess.handle, _cabi.OP_TRAIN, KEEP_IN, KEEP, seed))

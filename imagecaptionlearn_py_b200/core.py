@@ -156,6 +156,7 @@ class Session(object):
         self.last_train_stats = None
         self._slot = 0
         self._table_ref = None
+        self._side = None
         self.joint_vars = None          # weighted_joint: dict(W, b, mW, vW, mb, vb) on the host
         self.base_seed = self.graph.seed if seed is None else seed
         self._grad_view = None
@@ -283,7 +284,7 @@ class Session(object):
         _cabi.check(L.icl_run_resident(self.handle, _cabi.OP_GRADS, keep_in, keep, seed))
         if self.dist:
             import torch.distributed as td
-            td.all_reduce(self.grad_tensor(), op=td.ReduceOp.SUM)
+            self.allreduce_grads()
         _cabi.check(L.icl_fetch(self.handle, outs))
         losses = np.array([outs[i].loss for i in range(n)], np.float32)
         if self.dist:
@@ -417,6 +418,31 @@ class Session(object):
             self._grad_view = torch.as_tensor(_Arr(), device="cuda:%d" % self.device)
         return self._grad_view
 
+    def allreduce_grads(self):
+        """SUM all-reduce of the flat gradient buffer of the step just enqueued (the loss is a SUM over examples, core.py:267).
+        ICL_AR_OVERLAP=1 overlaps it with the backward pass: the heads' slice is reduced on a side stream as soon as the heads'
+        backward has run -- while the BPTT and the weight-gradient GEMMs still compute -- and the LSTM slice after them.
+        Measured on 2 x B200 (card2048): 1.598 ms/step with the overlap vs 1.551 ms without -- the NCCL kernel takes SMs away
+        from the BPTT clusters, which are sized to be co-resident on all 148 -- so one all-reduce after the backward is the default."""
+        import torch
+        import torch.distributed as td
+        L = _cabi.lib()
+        g = self.grad_tensor()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+            split = C.c_int64()
+            _cabi.check(L.icl_grad_split(self.handle, C.byref(split)))
+            self._split = int(split.value)
+        main = torch.cuda.current_stream()
+        if self._split >= g.numel() or not os.environ.get("ICL_AR_OVERLAP"):
+            td.all_reduce(g, op=td.ReduceOp.SUM)
+            return
+        _cabi.check(L.icl_wait_head_grads(self.handle, C.c_void_p(self._side.cuda_stream)))
+        with torch.cuda.stream(self._side):
+            td.all_reduce(g[self._split:], op=td.ReduceOp.SUM)
+        td.all_reduce(g[:self._split], op=td.ReduceOp.SUM)
+        main.wait_stream(self._side)
+
     def param_tensor(self):
         """torch view of the flat device parameter buffer (rank-0 broadcast of the initial weights)."""
         import torch
@@ -541,7 +567,7 @@ class Session(object):
             import torch.distributed as td
             _cabi.check(L.icl_upload(self.handle, C.byref(b)))
             _cabi.check(L.icl_run_resident(self.handle, _cabi.OP_GRADS, keep_in, keep, seed))
-            td.all_reduce(self.grad_tensor(), op=td.ReduceOp.SUM)       # loss is a SUM over examples (core.py:267)
+            self.allreduce_grads()
             _cabi.check(L.icl_apply_update(self.handle))
             _cabi.check(L.icl_fetch(self.handle, outs))
         else:
@@ -573,7 +599,7 @@ class Session(object):
             import torch.distributed as td
             _cabi.check(L.icl_upload(self.handle, C.byref(b)))
             _cabi.check(L.icl_run_resident(self.handle, _cabi.OP_GRADS, keep_in, keep, seed))
-            td.all_reduce(self.grad_tensor(), op=td.ReduceOp.SUM)       # loss is a SUM over examples (core.py:267)
+            self.allreduce_grads()
             _cabi.check(L.icl_apply_update(self.handle))
             _cabi.check(L.icl_poll_stats(self.handle, prev))
         else:

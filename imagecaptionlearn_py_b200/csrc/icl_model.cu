@@ -127,6 +127,7 @@ struct icl_model {
   bool resident = false;
   cudaStream_t stream = nullptr, aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaEvent_t ev_heads = nullptr;      // recorded when the heads' parameter gradients are complete (before the BPTT)
   cudaEvent_t ev_ph[PH_N][2] = {};
   bool ph_used[PH_N] = {};
   // persistent recurrent kernels
@@ -423,7 +424,7 @@ extern "C" void icl_destroy(icl_model* m) {
     if (h.h_pred) cudaFreeHost(h.h_pred);
   }
   if (m->aux) cudaStreamDestroy(m->aux);
-  for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_t0, m->ev_t1}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_t0, m->ev_t1, m->ev_heads}) if (e) cudaEventDestroy(e);
   for (int i = 0; i < PH_N; i++) for (int j = 0; j < 2; j++) if (m->ev_ph[i][j]) cudaEventDestroy(m->ev_ph[i][j]);
   delete m;
 }
@@ -561,6 +562,7 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   CKD(cudaStreamCreateWithFlags(&m->aux, cudaStreamNonBlocking));
   CKD(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
   CKD(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+  CKD(cudaEventCreateWithFlags(&m->ev_heads, cudaEventDisableTiming));
   CKD(cudaEventCreate(&m->ev_t0)); CKD(cudaEventCreate(&m->ev_t1));
   for (int i = 0; i < PH_N; i++) for (int j = 0; j < 2; j++) CKD(cudaEventCreate(&m->ev_ph[i][j]));
   if (tcgen05_gemm_init() != 0) { fail("icl_create: cannot resolve cuTensorMapEncodeTiled"); icl_destroy(m); *out = nullptr; return -1; }
@@ -615,6 +617,18 @@ extern "C" int icl_set_tensor(icl_model* m, int kind, const char* name, const fl
 extern "C" int icl_get_step(icl_model* m, int64_t* t) { *t = m->step; return 0; }
 extern "C" int icl_set_step(icl_model* m, int64_t t) { m->step = t; return 0; }
 extern "C" int icl_grad_buffer(icl_model* m, void** p, int64_t* n) { *p = m->G; *n = m->n_params; return 0; }
+// Overlapping the gradient all-reduce with the backward pass: the flat gradient buffer is [LSTM | heads]; the heads' part is
+// final once the heads' backward has run, long before the BPTT and the weight-gradient GEMMs finish.  `first_head_float` = where
+// the heads' gradients start; icl_wait_head_grads makes `cuda_stream` wait for them (cudaStreamWaitEvent), so a collective
+// enqueued on that stream afterwards runs concurrently with the rest of the step on the compute stream.
+extern "C" int icl_grad_split(icl_model* m, int64_t* first_head_float) {
+  *first_head_float = m->heads.empty() ? m->n_params : m->params[m->heads[0].pW[0]].off;
+  return 0;
+}
+extern "C" int icl_wait_head_grads(icl_model* m, void* cuda_stream) {
+  CK(cudaStreamWaitEvent((cudaStream_t)cuda_stream, m->ev_heads, 0));
+  return 0;
+}
 extern "C" int icl_param_buffer(icl_model* m, void** p, int64_t* n) { *p = m->P; *n = m->n_params; m->pr_dirty = m->wp_dirty = true; return 0; }
 extern "C" int icl_kernel_launches(icl_model* m, int64_t* n) { *n = m->launches; return 0; }
 extern "C" int icl_last_step_ms(icl_model* m, float* ms) { *ms = m->last_ms; return 0; }
@@ -968,6 +982,7 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
     }
   }
   PH_END(m, PH_HEADS_BWD);
+  CK(cudaEventRecord(m->ev_heads, st));       // the head gradients can be all-reduced while the BPTT runs (icl_wait_head_grads)
   return 0;
 }
 

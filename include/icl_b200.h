@@ -128,6 +128,11 @@ int icl_poll_stats(icl_model* m, icl_head_out* prev);
 /* data-parallel: flat fp32 gradient buffer on the device (all-reduce SUM it), then apply clip + Adam */
 int icl_grad_buffer(icl_model* m, void** dev_ptr, int64_t* n_floats);
 int icl_param_buffer(icl_model* m, void** dev_ptr, int64_t* n_floats);
+/* all-reduce overlapped with the backward pass: the buffer is [LSTM | heads]; the heads' gradients are final before the BPTT
+   starts.  icl_wait_head_grads makes the given stream wait for them, so a collective on floats [first_head_float, n) enqueued
+   there overlaps the BPTT + weight-gradient GEMMs of the compute stream; the LSTM part is reduced after icl_run_resident. */
+int icl_grad_split(icl_model* m, int64_t* first_head_float);
+int icl_wait_head_grads(icl_model* m, void* cuda_stream);
 int icl_apply_update(icl_model* m);
 /* Adam state selection: one (m, v, beta-power) set per tf.train.AdamOptimizer instance -- the `alternate` multitask scheme has
    one per task (icl_multitask_lstm.py:387-393).  Slot 0 exists from the start; others are created zeroed on first use.
