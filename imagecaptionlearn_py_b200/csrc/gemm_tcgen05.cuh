@@ -355,6 +355,16 @@ struct TmaCache {
     *out = tm;
     return 0;
   }
+  // 2-D fp16 tensor (uncached: built once at create): dim0 x dim1 halves, row pitch ld halves
+  static int get16(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t ld, uint32_t box0, uint32_t box1, int swizzle, CUtensorMap* out) {
+    cuuint64_t dims[2] = {dim0, dim1};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {box0, box1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          (CUtensorMapSwizzle)swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+  }
 };
 
 static bool tcgen05_gemm_supported(const GemmArgs& g, bool a_mn, bool b_mn) {

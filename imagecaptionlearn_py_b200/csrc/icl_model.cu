@@ -5,6 +5,7 @@
 #include "gemm_tcgen05.cuh"
 #include "lstm_persistent.cuh"
 #include "lstm_bptt.cuh"
+#include "lstm_fwd16.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -141,6 +142,11 @@ struct icl_model {
   RecBwdMaps rp_bmaps;
   unsigned* rp_bar = nullptr;
   bool rp_bwd_on = false;       // k_rec_bwd is correct but measured slower (0.84 ms) than the per-step path (0.56 ms): opt-in
+  // second-generation forward recurrence (lstm_fwd16.cuh): fp16 recurrent operands, double-buffered x-projection boxes
+  bool rf_on = false;
+  int rf_UP = 0, rf_KP = 0, rf_nkb = 0, rf_nk16 = 0;
+  __half* Hp16[2] = {}; __half* Wp16[2] = {};
+  RecFwd16Maps rf_maps;
   // fused BPTT step kernel (lstm_bptt.cuh): default backward recurrence in tensor-core mode
   bool bp_on = false, bp_cluster = true;     // bp_cluster: k_bptt_cluster (whole recurrence in one launch) when H <= 336
   int bp_cs = 4;
@@ -349,6 +355,36 @@ static int rec_init(icl_model* m) {
   return U == 20 ? rec_set_attr<20>(m->rp_nkb) : rec_set_attr<16>(m->rp_nkb);
 }
 
+template <int U> static int rec16_set_attr(int nkb) {
+  cudaError_t e = cudaFuncSetAttribute(k_rec_fwd16<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, rec_fwd16_smem<U>(nkb));
+  return e == cudaSuccess ? 0 : fail("cudaFuncSetAttribute(k_rec_fwd16): %s", cudaGetErrorString(e));
+}
+static int rec16_init(icl_model* m) {
+  m->rf_on = m->rp_U != 0;
+  if (const char* e = getenv("ICL_REC_FP16")) m->rf_on = m->rf_on && atoi(e) != 0;
+  if (!m->rf_on) return 0;
+  const int H = m->H, U = m->rp_U;
+  m->rf_UP = U == 20 ? RF<20>::UP : RF<16>::UP;
+  m->rf_KP = (m->rp_nsl * m->rf_UP + 63) / 64 * 64;
+  m->rf_nkb = m->rf_KP / 64;
+  m->rf_nk16 = (m->rp_nsl * m->rf_UP + 15) / 16;
+  const size_t smem = U == 20 ? rec_fwd16_smem<20>(m->rf_nkb) : rec_fwd16_smem<16>(m->rf_nkb);
+  if (smem > 227 * 1024) { m->rf_on = false; return 0; }
+  const uint64_t RC = (uint64_t)m->rows_cap;
+  const int NONE = (int)CU_TENSOR_MAP_SWIZZLE_NONE, SW128 = (int)CU_TENSOR_MAP_SWIZZLE_128B;
+  for (int d = 0; d < 2; d++) {
+    CK(cudaMalloc((void**)&m->Hp16[d], RC * m->rf_KP * 2)); CK(cudaMemset(m->Hp16[d], 0, RC * m->rf_KP * 2));
+    const size_t wn = (size_t)m->rp_nsl * 4 * U * m->rf_KP;
+    CK(cudaMalloc((void**)&m->Wp16[d], wn * 2)); CK(cudaMemset(m->Wp16[d], 0, wn * 2));
+    int r = TmaCache::get16(m->Hp16[d], (uint64_t)m->rf_KP, RC, (uint64_t)m->rf_KP, 64, 128, SW128, &m->rf_maps.a[d]);
+    if (!r) r = TmaCache::get16(m->Wp16[d], (uint64_t)m->rf_KP, (uint64_t)m->rp_nsl * 4 * U, (uint64_t)m->rf_KP, 64, 4 * U, SW128, &m->rf_maps.w[d]);
+    if (!r) r = TmaCache::get16(m->Hp16[d], (uint64_t)m->rf_KP, RC, (uint64_t)m->rf_KP, m->rf_UP, 32, NONE, &m->rf_maps.hp16[d]);
+    if (r) return fail("cuTensorMapEncodeTiled failed (%d) for the fp16 recurrence maps", r);
+    CKI(box_map(m, m->Z[d], 4 * H, RC, U, 32, NONE, &m->rf_maps.z[d]));
+  }
+  return U == 20 ? rec16_set_attr<20>(m->rf_nkb) : rec16_set_attr<16>(m->rf_nkb);
+}
+
 // make input set s the "current" one: the device pointers every launch site reads
 static void use_input_set(icl_model* m, int s) {
   InSet& I = m->in[s];
@@ -416,6 +452,7 @@ extern "C" void icl_destroy(icl_model* m) {
     F(m->XH[d]); F(m->Z[d]); F(m->Hx[d]); F(m->Cc[d]); F(m->dHout[d]); F(m->dhrec[d]); F(m->dcc[d]); F(m->R[d]);
   }
   F(m->Wp[0]); F(m->Wp[1]); F(m->rp_flags); F(m->rp_trace); F(m->rp_bar);
+  F(m->Hp16[0]); F(m->Hp16[1]); F(m->Wp16[0]); F(m->Wp16[1]);
   F(m->d_partial); F(m->d_gnorm);
   for (auto& h : m->heads) {
     F(h.bi); F(h.dbi); F(h.dA); F(h.dBuf); for (auto a : h.act) F(a);
@@ -567,6 +604,7 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   for (int i = 0; i < PH_N; i++) for (int j = 0; j < 2; j++) CKD(cudaEventCreate(&m->ev_ph[i][j]));
   if (tcgen05_gemm_init() != 0) { fail("icl_create: cannot resolve cuTensorMapEncodeTiled"); icl_destroy(m); *out = nullptr; return -1; }
   if (m->rp_U && rec_init(m) != 0) { icl_destroy(m); *out = nullptr; return -1; }
+  if (m->rp_U && rec16_init(m) != 0) { icl_destroy(m); *out = nullptr; return -1; }
   if (bptt_init(m) != 0) { icl_destroy(m); *out = nullptr; return -1; }
 #undef CKD
   return 0;
@@ -811,7 +849,36 @@ static RecArgs rec_args(icl_model* m, int training) {
   return a;
 }
 
+static int rec_forward_fp16(icl_model* m, int training) {
+  cudaStream_t st = m->stream;
+  const int E = m->E, H = m->H, U = m->rp_U;
+  if (m->wp_dirty) {
+    for (int d = 0; d < 2; d++) {
+      const float* Whh = m->P + m->params[m->pK[d]].off + (size_t)E * 4 * H;
+      k_pack_whh_fwd16<<<148, 256, 0, st>>>(Whh, m->Wp16[d], H, U, m->rf_UP, m->rp_nsl, m->rf_KP); LAUNCHED(m);
+    }
+    m->wp_dirty = false;
+  }
+  CK(zero_async(m->rp_flags, (size_t)2 * m->rp_max_tiles * 4, st));
+  RecFwd16Args a;
+  a.off = m->d_off; a.nact = m->d_nact; a.Tmax = m->Tmax; a.H = H; a.nsl = m->rp_nsl;
+  const int tiles = (m->n_active[0] + 127) / 128;
+  a.P = std::max(1, std::min(148 / (2 * m->rp_nsl), tiles));
+  a.nkb = m->rf_nkb; a.nk16 = m->rf_nk16; a.max_tiles = m->rp_max_tiles; a.training = training; a.ldx = m->ldx; a.flags = m->rp_flags;
+  for (int d = 0; d < 2; d++) { a.Z[d] = m->Z[d]; a.Cc[d] = m->Cc[d]; a.Hx[d] = m->Hx[d]; a.Hp[d] = m->Hp[d]; }
+  a.trace = m->rp_trace; a.trace_cta = m->rp_trace_cta;
+  void* args[] = {(void*)&m->rf_maps, (void*)&a};
+  dim3 grid(2 * a.P * a.nsl), block(RF_THREADS);
+  cudaError_t e;
+  if (U == 20) e = cudaLaunchCooperativeKernel((void*)k_rec_fwd16<20>, grid, block, args, rec_fwd16_smem<20>(a.nkb), st);
+  else e = cudaLaunchCooperativeKernel((void*)k_rec_fwd16<16>, grid, block, args, rec_fwd16_smem<16>(a.nkb), st);
+  if (e != cudaSuccess) return fail("k_rec_fwd16 launch failed: %s", cudaGetErrorString(e));
+  m->launches++;
+  return 0;
+}
+
 static int rec_forward_persistent(icl_model* m, int training) {
+  if (m->rf_on) return rec_forward_fp16(m, training);
   cudaStream_t st = m->stream;
   const int E = m->E, H = m->H, U = m->rp_U;
   if (m->wp_dirty) {

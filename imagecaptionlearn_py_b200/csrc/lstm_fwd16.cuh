@@ -1,0 +1,290 @@
+// Persistent forward recurrence, second generation ("K2", k_rec_fwd16): same decomposition as k_rec_fwd (lstm_persistent.cuh) --
+// CTA (direction, part, slice) keeps its slice of W_hh resident in shared memory for the whole launch, tiles are published on
+// per-tile counters, no grid barrier -- with three changes that the clock64 traces of the first generation asked for:
+//
+//  1. fp16 operands for the recurrent product (tcgen05.mma kind::f16, fp32 accumulation in TMEM).  h is in (-1, 1) and W_hh is
+//     O(0.1): fp16 carries the same 10 explicit mantissa bits as TF32 for these magnitudes (values below 6e-5 lose bits, an
+//     absolute error < 3e-8), so the products are as exact as the TF32 ones; the resident W slice (61 KB instead of 102 KB) and
+//     the streamed h tile (96 KB instead of 153 KB) halve.  The fp32 TF32-rounded copy of h that the weight-gradient GEMM
+//     contracts over (XH) is still written.
+//  2. The freed shared memory double-buffers the x-projection boxes: the boxes of tile i+2 are requested when tile i has been
+//     consumed, so their latency (the dominant term of the 4 us per-tile epilogue chain) is off the critical path.
+//  3. Only what the NEXT STEP needs goes through TMA + the publication protocol: the fp16 h rows (one 48-byte-row box per TMEM
+//     lane quarter).  Gates, c, exact h and the TF32 h are read by later kernels only and are stored straight from registers
+//     (7 narrow TMA boxes per tile and quarter -> 1).
+// Measured (card2048): 0.399 -> 0.378 ms.  The clock64 trace (tools/trace_fwd16.py) shows what bounds both generations: 4.2 us
+// per tile between "accumulator ready" and "tile handed over" -- every CTA writes a 20-unit-wide column slab of the gate / c / h
+// matrices, i.e. 80-byte row segments (2.5 sectors), through the LSU (here) or as narrow TMA boxes (first generation).  A variant
+// with a dedicated publisher warp (store completion + counter off the epilogue loop) was not faster (0.399 ms) and was dropped.
+//
+// fp16 h layout: Hp16 [rows][KP], slice j's 20 units at columns [24 j, 24 j + 20) + 4 zero columns, so that a quarter's box row
+// is 48 bytes (TMA needs multiples of 16); the packed W slice has zero rows at the pad positions.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "lstm_persistent.cuh"
+
+namespace icl {
+
+constexpr int RF_ASTAGES = 3, RF_EW = 8, RF_THREADS = 64 + 32 * RF_EW, RF_MAXTPC = 4, RF_MAXACC = 8;
+template <int U> struct RF {
+  static constexpr int UP = (U * 2) % 16 == 0 ? U : (U + 7) / 8 * 8;         // units of a slice as stored in Hp16 (padded to 16 bytes)
+  static constexpr int N = 4 * U;
+  static constexpr int U0 = RecSplit<U>::U0, U1 = RecSplit<U>::U1;
+  static constexpr int ZBOX = 32 * U * 4;                                     // one gate box of a quarter
+  static constexpr int HBOX = 32 * UP * 2;                                    // the fp16 h box of a quarter
+};
+template <int U> constexpr int rec_fwd16_smem(int nkb) {
+  return nkb * RF<U>::N * 128 + RF_ASTAGES * 16384 + 4 * (2 * 4 * RF<U>::ZBOX + 2 * RF<U>::HBOX) + 512 + 1024;
+}
+
+struct RecFwd16Maps { CUtensorMap a[2], w[2], z[2], hp16[2]; };   // a: Hp16 box {64 halves, 128 rows} SW128; w: packed W box {64, 4U} SW128;
+                                                                  // z: Z box {U, 32}; hp16: Hp16 box {UP, 32}
+struct RecFwd16Args {
+  const int* off; const int* nact;
+  int Tmax, H, nsl, P, nkb, nk16, max_tiles, training, ldx;
+  unsigned* flags;
+  float* Z[2]; float* Cc[2]; float* Hx[2]; float* Hp[2];           // generic-store targets (Hp = TF32 h rows inside XH, pitch ldx)
+  long long* trace; int trace_cta;
+};
+
+// Packed fp16 W_hh: row (j*4U + n), n = c*16 + gate*4 + i <-> unit j*U + 4c + i (as k_pack_whh_fwd); column k' = (k / U) * UP + k % U
+__global__ void k_pack_whh_fwd16(const float* __restrict__ Whh, __half* __restrict__ Wp, int H, int U, int UP, int nsl, int Kp) {
+  long total = (long)nsl * 4 * U * Kp;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    int kp = (int)(idx % Kp), row = (int)(idx / Kp);
+    int j = row / (4 * U), n = row % (4 * U);
+    int c = n / 16, gate = (n % 16) / 4, i = n % 4;
+    int u = j * U + c * 4 + i;
+    int ks = kp / UP, ku = kp % UP, k = ks * U + ku;
+    float v = (ku < U && k < H && u < H) ? Whh[(long)k * 4 * H + gate * H + u] : 0.0f;
+    Wp[idx] = __float2half_rn(v);
+  }
+}
+
+template <int U>
+__global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_constant__ RecFwd16Maps maps, const RecFwd16Args g) {
+  constexpr int N = RF<U>::N, UP = RF<U>::UP, U0 = RF<U>::U0, U1 = RF<U>::U1, ZBOX = RF<U>::ZBOX, HBOX = RF<U>::HBOX;
+  constexpr int NACC = (512 / N) < RF_MAXACC ? (512 / N) : RF_MAXACC;
+  constexpr int QBYTES = 2 * 4 * ZBOX + 2 * HBOX;                            // per quarter: two sets of 4 gate boxes + two fp16 h boxes
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ int s_off[RP_MAXT + 2], s_n[RP_MAXT + 2];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sW = base;
+  const uint32_t sA = sW + (uint32_t)g.nkb * N * 128;
+  const uint32_t sE = sA + RF_ASTAGES * 16384;
+  const uint32_t bars = sE + 4 * QBYTES;
+  const uint32_t full0 = bars, empty0 = bars + 8 * RF_ASTAGES, wfull = bars + 16 * RF_ASTAGES, efull0 = wfull + 8,   // efull: [quarter][set]
+                 tfull0 = efull0 + 8 * 8, tempty0 = tfull0 + 8 * RF_MAXACC, tmem_slot = tempty0 + 8 * RF_MAXACC;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_dir = g.P * g.nsl;
+  const int d = blockIdx.x / per_dir, p = (blockIdx.x % per_dir) / g.nsl, j = blockIdx.x % g.nsl;
+  const int H = g.H, Tmax = g.Tmax;
+  unsigned* flags = g.flags + (size_t)d * g.max_tiles;
+
+  for (int i = threadIdx.x; i <= Tmax; i += blockDim.x) { s_off[i] = g.off[i]; s_n[i] = g.nact[i]; }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < RF_ASTAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(wfull, 1);
+    for (int w = 0; w < 8; w++) mbar_init(efull0 + 8 * w, 1);
+    for (int a = 0; a < NACC; a++) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, RF_EW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // the pad columns of the fp16 h boxes stay zero for the whole launch
+  for (int i = threadIdx.x; i < 4 * HBOX; i += blockDim.x) {              // 2 boxes of HBOX / 2 halves per quarter
+    const int q = i / HBOX, e = i % HBOX;
+    reinterpret_cast<__half*>(gbase + (sE - base) + q * QBYTES + 2 * 4 * ZBOX)[e] = __float2half_rn(0.0f);
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem) : "r"(tmem_slot));
+  const unsigned per_step = (unsigned)(g.nsl * 4);                      // counter increments per (step, tile): slices x quarters
+
+  if (warp == 0) {
+    if (lane == 0) {                                                   // ---- A producer (fp16 h_{k-1} tiles) + resident W slice
+      mbar_expect_tx(wfull, (uint32_t)g.nkb * N * 128);
+      for (int kb = 0; kb < g.nkb; kb++) tma_load_2d(sW + kb * N * 128, &maps.w[d], kb * 64, j * N, wfull);
+      uint32_t it = 0;
+      Tracer tr; tr.init(g.trace, g.trace_cta, 0);
+      for (int k = 1; k < Tmax; k++) {
+        for (int t = p; t * RP_ROWS < s_n[k]; t += g.P) {
+          tr.ev(0, k, t);
+          flag_wait(flags + t, per_step * k);
+          fence_async_all();
+          tr.ev(1, k, t);
+          for (int kb = 0; kb < g.nkb; kb++, it++) {
+            const uint32_t s = it % RF_ASTAGES;
+            mbar_wait(empty0 + 8 * s, ((it / RF_ASTAGES) & 1) ^ 1);
+            mbar_expect_tx(full0 + 8 * s, 16384);
+            tma_load_2d(sA + s * 16384, &maps.a[d], kb * 64, s_off[k] + t * RP_ROWS, full0 + 8 * s);
+          }
+          tr.ev(2, k, t);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                                                   // ---- MMA issuer
+      constexpr uint32_t idesc = make_idesc(0, false, false, RP_ROWS, N);   // kind::f16, fp16 x fp16 -> fp32
+      mbar_wait(wfull, 0);
+      uint32_t it = 0, acc = 0;
+      Tracer tr; tr.init(g.trace, g.trace_cta, 1);
+      for (int k = 1; k < Tmax; k++) {
+        for (int t = p; t * RP_ROWS < s_n[k]; t += g.P, acc++) {
+          const uint32_t slot = acc % NACC;
+          mbar_wait(tempty0 + 8 * slot, ((acc / NACC) & 1) ^ 1);
+          tc_fence_after();
+          tr.ev(0, k, t);
+          for (int kb = 0; kb < g.nkb; kb++, it++) {
+            const uint32_t s = it % RF_ASTAGES;
+            mbar_wait(full0 + 8 * s, (it / RF_ASTAGES) & 1);
+            tc_fence_after();
+            if (kb == 0) tr.ev(1, k, t);
+            const int nk = min(4, g.nk16 - kb * 4);                    // UMMA_K = 16 halves = 32 bytes
+            for (int kk = 0; kk < nk; kk++) {
+              const uint64_t ad = make_smem_desc(sA + s * 16384 + kk * 32, 16, 1024);
+              const uint64_t bd = make_smem_desc(sW + kb * N * 128 + kk * 32, 16, 1024);
+              tc_mma_f16(tmem + slot * N, ad, bd, idesc, (kb | kk) != 0);
+            }
+            tc_commit(empty0 + 8 * s);
+          }
+          tc_commit(tfull0 + 8 * slot);
+          tr.ev(2, k, t);
+        }
+      }
+    }
+  } else {
+    // ---- 8 epilogue warps = 4 TMEM lane quarters x 2 unit halves (as k_rec_fwd); per quarter two sets of x-projection boxes
+    const int ew = warp - 2, q = warp & 3, hs = ew >> 2;
+    const int UH = hs ? U1 : U0, ubase = hs ? U0 : 0;
+    const uint32_t sMine = sE + (uint32_t)q * QBYTES;
+    const float* zset[2] = {reinterpret_cast<const float*>(gbase + (sMine - base)), reinterpret_cast<const float*>(gbase + (sMine - base) + 4 * ZBOX)};
+    __half* const hbox0 = reinterpret_cast<__half*>(gbase + (sMine - base) + 2 * 4 * ZBOX);   // two boxes, alternating per tile
+    const int ucol = j * U;
+    const bool issuer = hs == 0 && lane == 0;                            // the quarter's TMA thread
+    auto valid = [&](int k, int i) { return k < Tmax && i < RF_MAXTPC && (p + i * g.P) * RP_ROWS < s_n[k]; };
+    auto nxt = [&](int& k, int& i) { if (valid(k, i + 1)) i++; else { k++; i = 0; } };
+    auto load_z = [&](int k, int i, int set) {                          // x-projection boxes of tile (k, i) of this quarter
+      const uint32_t bar = efull0 + 8 * (q * 2 + set);
+      mbar_expect_tx(bar, 4 * ZBOX);
+      for (int gate = 0; gate < 4; gate++)
+        tma_load_2d(sMine + set * 4 * ZBOX + gate * ZBOX, &maps.z[d], gate * H + ucol, s_off[k] + (p + i * g.P) * RP_ROWS + 32 * q, bar);
+    };
+    if (issuer) {                                                      // prime both sets
+      int k0 = 0, i0 = 0;
+      if (valid(k0, i0)) { load_z(k0, i0, 0); nxt(k0, i0); if (valid(k0, i0)) load_z(k0, i0, 1); }
+    }
+    float* const Zd = g.Z[d]; float* const Cd = g.Cc[d]; float* const Hd = g.Hx[d]; float* const Hpd = g.Hp[d];
+    float cst[RF_MAXTPC][U0];
+#pragma unroll
+    for (int i = 0; i < RF_MAXTPC; i++)
+#pragma unroll
+      for (int u = 0; u < U0; u++) cst[i][u] = 0.0f;
+    uint32_t n_tile = 0, acc = 0;                                        // tiles processed (set = n_tile & 1), accumulators consumed
+    Tracer tr; tr.init(g.trace, g.trace_cta, 3);
+    if (ew != 0 || lane != 0) tr.p = nullptr;
+    for (int k = 0; k < Tmax; k++) {
+#pragma unroll
+      for (int i = 0; i < RF_MAXTPC; i++) {
+        const int t = p + i * g.P;
+        if (t * RP_ROWS >= s_n[k]) break;
+        const int set = n_tile & 1;
+        tr.ev(0, k, t);
+        mbar_wait(efull0 + 8 * (q * 2 + set), (n_tile >> 1) & 1);
+        tr.ev(1, k, t);
+        uint32_t slot = 0;
+        if (k > 0) {
+          slot = acc % NACC;
+          mbar_wait(tfull0 + 8 * slot, (acc / NACC) & 1);
+          tc_fence_after();
+        }
+        tr.ev(2, k, t);
+        const float* zb = zset[set] + ubase;
+        __half* hbox = hbox0 + set * (HBOX / 2);
+        const long row = (long)s_off[k] + t * RP_ROWS + 32 * q + lane;
+        const bool has_next = t * RP_ROWS < s_n[k + 1];
+        const long row_n = (long)s_off[k + 1] + t * RP_ROWS + 32 * q + lane;
+#pragma unroll
+        for (int c = 0; c < U0 / 4; c++) {
+          if (c * 4 < UH) {
+            uint32_t a[16];
+            if (k > 0) tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + slot * N + (ubase / 4 + c) * 16, a);
+            else {
+#pragma unroll
+              for (int x = 0; x < 16; x++) a[x] = 0u;
+            }
+            float4 z4[4];
+#pragma unroll
+            for (int gate = 0; gate < 4; gate++) z4[gate] = *reinterpret_cast<const float4*>(zb + gate * 32 * U + lane * U + c * 4);
+            const float *zi = &z4[0].x, *zj = &z4[1].x, *zf = &z4[2].x, *zo = &z4[3].x;
+            float si[4], tj[4], sf[4], so[4], hn[4], hr[4];
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+              si[x] = sigmoid_fast(zi[x] + __uint_as_float(a[x]));
+              tj[x] = tanh_fast(zj[x] + __uint_as_float(a[4 + x]));
+              sf[x] = sigmoid_fast(zf[x] + __uint_as_float(a[8 + x]) + 1.0f);
+              so[x] = sigmoid_fast(zo[x] + __uint_as_float(a[12 + x]));
+              const float cn = cst[i][c * 4 + x] * sf[x] + si[x] * tj[x];
+              cst[i][c * 4 + x] = cn;
+              hn[x] = tanh_fast(cn) * so[x];
+              hr[x] = tf32_rna(hn[x]);
+            }
+            const int u = ucol + ubase + c * 4;
+            if (g.training) {                                          // read by the backward pass only: straight from registers
+              float* z = Zd + row * 4 * H + u;
+              *reinterpret_cast<float4*>(z) = make_float4(si[0], si[1], si[2], si[3]);
+              *reinterpret_cast<float4*>(z + H) = make_float4(tj[0], tj[1], tj[2], tj[3]);
+              *reinterpret_cast<float4*>(z + 2 * H) = make_float4(sf[0], sf[1], sf[2], sf[3]);
+              *reinterpret_cast<float4*>(z + 3 * H) = make_float4(so[0], so[1], so[2], so[3]);
+              *reinterpret_cast<float4*>(Cd + row * H + u) = make_float4(cst[i][c * 4], cst[i][c * 4 + 1], cst[i][c * 4 + 2], cst[i][c * 4 + 3]);
+              if (has_next) *reinterpret_cast<float4*>(Hpd + row_n * g.ldx + u) = make_float4(hr[0], hr[1], hr[2], hr[3]);
+            }
+            *reinterpret_cast<float4*>(Hd + row * H + u) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            __half2 h01 = __floats2half2_rn(hn[0], hn[1]), h23 = __floats2half2_rn(hn[2], hn[3]);
+            uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
+            *reinterpret_cast<uint2*>(hbox + lane * UP + ubase + c * 4) = pk;       // next step's operand rows (fp16)
+          }
+        }
+        if (k > 0) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + 8 * slot);
+          acc++;
+        }
+        fence_async_smem();                                             // the fp16 box (generic smem writes) -> visible to the TMA engine
+        asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");       // both unit halves are done with this set's boxes
+        if (issuer) {
+          if (has_next) tma_store_2d(&maps.hp16[d], sMine + 2 * 4 * ZBOX + set * HBOX, j * UP, (int)(s_off[k + 1] + t * RP_ROWS + 32 * q));
+          bulk_commit();
+          int k2 = k, i2 = i;                                          // x-projection boxes of the tile after next -> this set
+          nxt(k2, i2);
+          if (valid(k2, i2)) { nxt(k2, i2); if (valid(k2, i2)) load_z(k2, i2, set); }
+          bulk_wait<0>();                                               // the fp16 rows are complete in global memory
+        }
+        if (hs == 0) {
+          __syncwarp();
+          if (lane == 1) flag_release_add(flags + t);                   // a lane with no bulk copies in flight publishes the tile
+        }
+        tr.ev(3, k, t);
+        n_tile++;
+        // hazards: set `set` (gate boxes + fp16 box) is next written for tile n_tile + 2; the issuer's bulk_wait of THIS tile's store
+        // precedes its arrival at the bar.sync of tile n_tile + 1, which every thread passes before touching tile n_tile + 2
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+}  // namespace icl
