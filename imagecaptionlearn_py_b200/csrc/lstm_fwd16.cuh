@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
     const int ew = warp - 2, q = warp & 3, hs = ew >> 2;
     const int UH = hs ? U1 : U0, ubase = hs ? U0 : 0;
     const uint32_t sMine = sE + (uint32_t)q * QBYTES;
-    const float* zset[2] = {reinterpret_cast<const float*>(gbase + (sMine - base)), reinterpret_cast<const float*>(gbase + (sMine - base) + 4 * ZBOX)};
+    float* zset[2] = {reinterpret_cast<float*>(gbase + (sMine - base)), reinterpret_cast<float*>(gbase + (sMine - base) + 4 * ZBOX)};
     __half* const hbox0 = reinterpret_cast<__half*>(gbase + (sMine - base) + 2 * 4 * ZBOX);   // two boxes, alternating per tile
     const int ucol = j * U;
     const bool issuer = hs == 0 && lane == 0;                            // the quarter's TMA thread
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
       int k0 = 0, i0 = 0;
       if (valid(k0, i0)) { load_z(k0, i0, 0); nxt(k0, i0); if (valid(k0, i0)) load_z(k0, i0, 1); }
     }
-    float* const Zd = g.Z[d]; float* const Cd = g.Cc[d]; float* const Hd = g.Hx[d]; float* const Hpd = g.Hp[d];
+    float* const Cd = g.Cc[d]; float* const Hd = g.Hx[d]; float* const Hpd = g.Hp[d];
     float cst[RF_MAXTPC][U0];
 #pragma unroll
     for (int i = 0; i < RF_MAXTPC; i++)
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
           tc_fence_after();
         }
         tr.ev(2, k, t);
-        const float* zb = zset[set] + ubase;
+        float* zb = zset[set] + ubase;
         __half* hbox = hbox0 + set * (HBOX / 2);
         const long row = (long)s_off[k] + t * RP_ROWS + 32 * q + lane;
         const bool has_next = t * RP_ROWS < s_n[k + 1];
@@ -238,11 +238,12 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
             }
             const int u = ucol + ubase + c * 4;
             if (g.training) {                                          // read by the backward pass only: straight from registers
-              float* z = Zd + row * 4 * H + u;
-              *reinterpret_cast<float4*>(z) = make_float4(si[0], si[1], si[2], si[3]);
-              *reinterpret_cast<float4*>(z + H) = make_float4(tj[0], tj[1], tj[2], tj[3]);
-              *reinterpret_cast<float4*>(z + 2 * H) = make_float4(sf[0], sf[1], sf[2], sf[3]);
-              *reinterpret_cast<float4*>(z + 3 * H) = make_float4(so[0], so[1], so[2], so[3]);
+              // the gates go back into the x-projection boxes and out as four TMA boxes (the LSU path alone was the bottleneck:
+              // every lane-per-row float4 store is 32 wavefronts); c / h / TF32 h stay on the LSU, the two engines overlap
+              *reinterpret_cast<float4*>(zb + 0 * 32 * U + lane * U + c * 4) = make_float4(si[0], si[1], si[2], si[3]);
+              *reinterpret_cast<float4*>(zb + 1 * 32 * U + lane * U + c * 4) = make_float4(tj[0], tj[1], tj[2], tj[3]);
+              *reinterpret_cast<float4*>(zb + 2 * 32 * U + lane * U + c * 4) = make_float4(sf[0], sf[1], sf[2], sf[3]);
+              *reinterpret_cast<float4*>(zb + 3 * 32 * U + lane * U + c * 4) = make_float4(so[0], so[1], so[2], so[3]);
               *reinterpret_cast<float4*>(Cd + row * H + u) = make_float4(cst[i][c * 4], cst[i][c * 4 + 1], cst[i][c * 4 + 2], cst[i][c * 4 + 3]);
               if (has_next) *reinterpret_cast<float4*>(Hpd + row_n * g.ldx + u) = make_float4(hr[0], hr[1], hr[2], hr[3]);
             }
@@ -262,11 +263,17 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
         asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");       // both unit halves are done with this set's boxes
         if (issuer) {
           if (has_next) tma_store_2d(&maps.hp16[d], sMine + 2 * 4 * ZBOX + set * HBOX, j * UP, (int)(s_off[k + 1] + t * RP_ROWS + 32 * q));
-          bulk_commit();
+          bulk_commit();                                               // group A: what the next step of the other slices waits for
+          if (g.training) {
+            for (int gate = 0; gate < 4; gate++)
+              tma_store_2d(&maps.z[d], sMine + set * 4 * ZBOX + gate * ZBOX, gate * H + ucol, (int)(s_off[k] + t * RP_ROWS + 32 * q));
+            bulk_commit();                                             // group B: the gates (read by the backward pass)
+            bulk_wait_read<0>();                                       // the boxes of this set may be refilled
+          }
           int k2 = k, i2 = i;                                          // x-projection boxes of the tile after next -> this set
           nxt(k2, i2);
           if (valid(k2, i2)) { nxt(k2, i2); if (valid(k2, i2)) load_z(k2, i2, set); }
-          bulk_wait<0>();                                               // the fp16 rows are complete in global memory
+          if (g.training) bulk_wait<1>(); else bulk_wait<0>();          // group A: the fp16 rows are complete in global memory
         }
         if (hs == 0) {
           __syncwarp();
@@ -278,6 +285,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
         // precedes its arrival at the bar.sync of tile n_tile + 1, which every thread passes before touching tile n_tile + 2
       }
     }
+    if (issuer) bulk_wait<0>();                                          // the last gate boxes have left shared memory
   }
   tc_fence_before();
   __syncthreads();
