@@ -381,6 +381,7 @@ static int rec16_init(icl_model* m) {
     if (!r) r = TmaCache::get16(m->Hp16[d], (uint64_t)m->rf_KP, RC, (uint64_t)m->rf_KP, m->rf_UP, 32, NONE, &m->rf_maps.hp16[d]);
     if (r) return fail("cuTensorMapEncodeTiled failed (%d) for the fp16 recurrence maps", r);
     CKI(box_map(m, m->Z[d], 4 * H, RC, U, 32, NONE, &m->rf_maps.z[d]));
+    CKI(box_map(m, m->Cc[d], H, RC, U, 32, NONE, &m->rf_maps.cc[d]));
   }
   return U == 20 ? rec16_set_attr<20>(m->rf_nkb) : rec16_set_attr<16>(m->rf_nkb);
 }

@@ -35,10 +35,10 @@ template <int U> struct RF {
   static constexpr int HBOX = 32 * UP * 2;                                    // the fp16 h box of a quarter
 };
 template <int U> constexpr int rec_fwd16_smem(int nkb) {
-  return nkb * RF<U>::N * 128 + RF_ASTAGES * 16384 + 4 * (2 * 4 * RF<U>::ZBOX + 2 * RF<U>::HBOX) + 512 + 1024;
+  return nkb * RF<U>::N * 128 + RF_ASTAGES * 16384 + 4 * (2 * 5 * RF<U>::ZBOX + 2 * RF<U>::HBOX) + 512 + 1024;
 }
 
-struct RecFwd16Maps { CUtensorMap a[2], w[2], z[2], hp16[2]; };   // a: Hp16 box {64 halves, 128 rows} SW128; w: packed W box {64, 4U} SW128;
+struct RecFwd16Maps { CUtensorMap a[2], w[2], z[2], cc[2], hp16[2]; };   // a: Hp16 box {64 halves, 128 rows} SW128; w: packed W box {64, 4U} SW128;
                                                                   // z: Z box {U, 32}; hp16: Hp16 box {UP, 32}
 struct RecFwd16Args {
   const int* off; const int* nact;
@@ -66,7 +66,7 @@ template <int U>
 __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_constant__ RecFwd16Maps maps, const RecFwd16Args g) {
   constexpr int N = RF<U>::N, UP = RF<U>::UP, U0 = RF<U>::U0, U1 = RF<U>::U1, ZBOX = RF<U>::ZBOX, HBOX = RF<U>::HBOX;
   constexpr int NACC = (512 / N) < RF_MAXACC ? (512 / N) : RF_MAXACC;
-  constexpr int QBYTES = 2 * 4 * ZBOX + 2 * HBOX;                            // per quarter: two sets of 4 gate boxes + two fp16 h boxes
+  constexpr int QBYTES = 2 * 5 * ZBOX + 2 * HBOX;                            // per quarter: two sets of (4 gate boxes + c box) + two fp16 h boxes
   extern __shared__ uint8_t smem_raw[];
   __shared__ int s_off[RP_MAXT + 2], s_n[RP_MAXT + 2];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
   // the pad columns of the fp16 h boxes stay zero for the whole launch
   for (int i = threadIdx.x; i < 4 * HBOX; i += blockDim.x) {              // 2 boxes of HBOX / 2 halves per quarter
     const int q = i / HBOX, e = i % HBOX;
-    reinterpret_cast<__half*>(gbase + (sE - base) + q * QBYTES + 2 * 4 * ZBOX)[e] = __float2half_rn(0.0f);
+    reinterpret_cast<__half*>(gbase + (sE - base) + q * QBYTES + 2 * 5 * ZBOX)[e] = __float2half_rn(0.0f);
   }
   fence_async_smem();
   tc_fence_before();
@@ -165,8 +165,8 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
     const int ew = warp - 2, q = warp & 3, hs = ew >> 2;
     const int UH = hs ? U1 : U0, ubase = hs ? U0 : 0;
     const uint32_t sMine = sE + (uint32_t)q * QBYTES;
-    float* zset[2] = {reinterpret_cast<float*>(gbase + (sMine - base)), reinterpret_cast<float*>(gbase + (sMine - base) + 4 * ZBOX)};
-    __half* const hbox0 = reinterpret_cast<__half*>(gbase + (sMine - base) + 2 * 4 * ZBOX);   // two boxes, alternating per tile
+    float* zset[2] = {reinterpret_cast<float*>(gbase + (sMine - base)), reinterpret_cast<float*>(gbase + (sMine - base) + 5 * ZBOX)};
+    __half* const hbox0 = reinterpret_cast<__half*>(gbase + (sMine - base) + 2 * 5 * ZBOX);   // two boxes, alternating per tile
     const int ucol = j * U;
     const bool issuer = hs == 0 && lane == 0;                            // the quarter's TMA thread
     auto valid = [&](int k, int i) { return k < Tmax && i < RF_MAXTPC && (p + i * g.P) * RP_ROWS < s_n[k]; };
@@ -175,13 +175,13 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
       const uint32_t bar = efull0 + 8 * (q * 2 + set);
       mbar_expect_tx(bar, 4 * ZBOX);
       for (int gate = 0; gate < 4; gate++)
-        tma_load_2d(sMine + set * 4 * ZBOX + gate * ZBOX, &maps.z[d], gate * H + ucol, s_off[k] + (p + i * g.P) * RP_ROWS + 32 * q, bar);
+        tma_load_2d(sMine + set * 5 * ZBOX + gate * ZBOX, &maps.z[d], gate * H + ucol, s_off[k] + (p + i * g.P) * RP_ROWS + 32 * q, bar);
     };
     if (issuer) {                                                      // prime both sets
       int k0 = 0, i0 = 0;
       if (valid(k0, i0)) { load_z(k0, i0, 0); nxt(k0, i0); if (valid(k0, i0)) load_z(k0, i0, 1); }
     }
-    float* const Cd = g.Cc[d]; float* const Hd = g.Hx[d]; float* const Hpd = g.Hp[d];
+    float* const Hd = g.Hx[d]; float* const Hpd = g.Hp[d];
     float cst[RF_MAXTPC][U0];
 #pragma unroll
     for (int i = 0; i < RF_MAXTPC; i++)
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
               *reinterpret_cast<float4*>(zb + 1 * 32 * U + lane * U + c * 4) = make_float4(tj[0], tj[1], tj[2], tj[3]);
               *reinterpret_cast<float4*>(zb + 2 * 32 * U + lane * U + c * 4) = make_float4(sf[0], sf[1], sf[2], sf[3]);
               *reinterpret_cast<float4*>(zb + 3 * 32 * U + lane * U + c * 4) = make_float4(so[0], so[1], so[2], so[3]);
-              *reinterpret_cast<float4*>(Cd + row * H + u) = make_float4(cst[i][c * 4], cst[i][c * 4 + 1], cst[i][c * 4 + 2], cst[i][c * 4 + 3]);
+              *reinterpret_cast<float4*>(zb + 4 * 32 * U + lane * U + c * 4) = make_float4(cst[i][c * 4], cst[i][c * 4 + 1], cst[i][c * 4 + 2], cst[i][c * 4 + 3]);
               if (has_next) *reinterpret_cast<float4*>(Hpd + row_n * g.ldx + u) = make_float4(hr[0], hr[1], hr[2], hr[3]);
             }
             *reinterpret_cast<float4*>(Hd + row * H + u) = make_float4(hn[0], hn[1], hn[2], hn[3]);
@@ -262,12 +262,13 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
         fence_async_smem();                                             // the fp16 box (generic smem writes) -> visible to the TMA engine
         asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");       // both unit halves are done with this set's boxes
         if (issuer) {
-          if (has_next) tma_store_2d(&maps.hp16[d], sMine + 2 * 4 * ZBOX + set * HBOX, j * UP, (int)(s_off[k + 1] + t * RP_ROWS + 32 * q));
+          if (has_next) tma_store_2d(&maps.hp16[d], sMine + 2 * 5 * ZBOX + set * HBOX, j * UP, (int)(s_off[k + 1] + t * RP_ROWS + 32 * q));
           bulk_commit();                                               // group A: what the next step of the other slices waits for
           if (g.training) {
             for (int gate = 0; gate < 4; gate++)
-              tma_store_2d(&maps.z[d], sMine + set * 4 * ZBOX + gate * ZBOX, gate * H + ucol, (int)(s_off[k] + t * RP_ROWS + 32 * q));
-            bulk_commit();                                             // group B: the gates (read by the backward pass)
+              tma_store_2d(&maps.z[d], sMine + set * 5 * ZBOX + gate * ZBOX, gate * H + ucol, (int)(s_off[k] + t * RP_ROWS + 32 * q));
+            tma_store_2d(&maps.cc[d], sMine + set * 5 * ZBOX + 4 * ZBOX, ucol, (int)(s_off[k] + t * RP_ROWS + 32 * q));
+            bulk_commit();                                             // group B: the gates and c (read by the backward pass)
             bulk_wait_read<0>();                                       // the boxes of this set may be refilled
           }
           int k2 = k, i2 = i;                                          // x-projection boxes of the tile after next -> this set
