@@ -1289,6 +1289,8 @@ static int apply_update(icl_model* m, double extra_sumsq) {
                                   len, m->d_gnorm, m->cfg.clip_norm, lr_t, (float)b1, (float)b2, m->cfg.adam_epsilon);
     LAUNCHED(m);
   }
+  if (!getenv("ICL_DEBUG_STALE_WP")) m->wp_dirty = true;   // the packed recurrent weights of the persistent forward kernel follow
+                                                             // the update (the env knob exists so that a test can prove it catches staleness)
   PH_END(m, PH_UPDATE);
   return 0;
 }

@@ -184,14 +184,20 @@ def test_gradients_match_oracle(case, mode, dropout):
     sess.close()
 
 
+TRAIN_CASES = {"H12-per-step": CASES[1],
+               # H % 20 == 0: the persistent forward kernel, whose packed copy of W_hh must follow every update
+               "H20-persistent": dict(task="nonvis", enc="first_last_mention", act="tanh", S=40, T=9, E=12, H=20, F=4, widths=(16, 8))}
+
+
+@pytest.mark.parametrize("case", list(TRAIN_CASES), ids=list(TRAIN_CASES))
 @pytest.mark.parametrize("mode", ["simt", "tf32"])
-def test_train_steps_match_oracle_adam(mode):
+def test_train_steps_match_oracle_adam(mode, case):
     """Three train_op steps (no dropout) on the same batch: parameter updates track the oracle's clip + TF-Adam.
     Adam normalises every gradient to ~lr, so an element whose gradient is at the TF32 noise floor can move either
     way: the 5% bound is asserted where the first-step gradient is above 2% of its tensor's maximum (everywhere in
     fp32 mode), and all other elements must stay within the 3-step Adam bound 3*lr."""
     from imagecaptionlearn_py_b200 import _cabi
-    p = tiny_problem(seed=23, **CASES[1])
+    p = tiny_problem(seed=23, **TRAIN_CASES[case])
     core, sess = make_session(p, mode)
     params = {k: v.copy() for k, v in p["params"].items()}
     state, g1 = {}, None
@@ -493,3 +499,29 @@ def test_resident_token_table_gives_identical_results():
         assert np.array_equal(res[mode][0], res[False][0])
         for k, v in res[False][1].items():
             assert np.array_equal(res[mode][1][k], v), k
+
+
+@pytest.mark.parametrize("stale", [False, True])
+def test_forward_follows_the_updated_recurrent_weights(stale, monkeypatch):
+    """The persistent forward kernel keeps a packed copy of W_hh resident: after parameter updates the next forward must use the
+    NEW weights.  30 Adam steps (each moves every weight by ~lr), then the device probabilities against the oracle evaluated
+    with the parameters read back from the device.  stale=True disables the re-packing (ICL_DEBUG_STALE_WP) and must FAIL the
+    comparison: the check has teeth."""
+    from imagecaptionlearn_py_b200 import _cabi
+    if stale:
+        monkeypatch.setenv("ICL_DEBUG_STALE_WP", "1")
+    p = tiny_problem(seed=29, **TRAIN_CASES["H20-persistent"])
+    core, sess = make_session(p, "tf32")
+    for step in range(30):
+        sess.run(_cabi.OP_TRAIN, [dict(p["batch"])], 1.0, 1.0, True)
+    params = {k: sess.get_tensor(k).reshape(v.shape).astype(np.float64) for k, v in p["params"].items()}
+    moved = max(float(np.max(np.abs(params[k] - p["params"][k]))) for k in params if "lstm" in k and "kernel" in k)
+    assert moved > 5e-3                                                   # the recurrent kernels did move
+    r = sess.run(_cabi.OP_PREDICT, [dict(p["batch"])], 1.0, 1.0, True)[0]
+    f = O.model_forward(params, p["cfg"], p["x"], p["lens"], [p["batch"]])
+    err = relerr(r["proba"], f["heads"][0]["proba"])
+    sess.close()
+    if stale:
+        assert err > 3 * TOL["tf32"]["fwd"], err
+    else:
+        assert err < TOL["tf32"]["fwd"], err
