@@ -122,7 +122,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, bool a_mn, bool b_mn,
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <bool A_MN, bool B_MN, int BN, int STAGES>
+// F16: both operands are fp16, K-major, k-blocks of 64 halves (the same 128-byte rows / descriptors / 32-byte MMA steps as TF32):
+// tcgen05.mma kind::f16 with fp32 accumulation -- for contractions whose operands fit fp16's 10-bit mantissa + range exactly as
+// well as TF32's (the input projection: embeddings x W_ih), at half the operand bytes and twice the MMA rate.  g.K counts halves.
+template <bool A_MN, bool B_MN, int BN, int STAGES, bool F16 = false>
 __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
   constexpr int B_BYTES = BN * TG_BK * 4;
@@ -134,7 +137,9 @@ __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TG_BM, n0 = blockIdx.x * BN;
   // split-K (gridDim.z > 1): this CTA contracts k-blocks [kb0, kb0+num_kb) and adds its partial tile to C with red.global
-  const int total_kb = (g.K + TG_BK - 1) / TG_BK;
+  constexpr int KB_ELEMS = F16 ? 2 * TG_BK : TG_BK;                      // elements per 128-byte k-block row
+  static_assert(!F16 || (!A_MN && !B_MN), "the fp16 path is K-major only");
+  const int total_kb = (g.K + KB_ELEMS - 1) / KB_ELEMS;
   const int kb_per = (total_kb + gridDim.z - 1) / gridDim.z;
   const int kb0 = blockIdx.z * kb_per;
   const int num_kb = max(0, min(kb_per, total_kb - kb0));
@@ -173,19 +178,19 @@ __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_consta
 #pragma unroll
           for (int j = 0; j < TG_BM / 32; j++) tma_load_2d(a + j * (32 * TG_BK * 4), &tmA, m0 + 32 * j, (kb0 + kb) * TG_BK, fb);
         } else {
-          tma_load_2d(a, &tmA, (kb0 + kb) * TG_BK, m0, fb);
+          tma_load_2d(a, &tmA, (kb0 + kb) * KB_ELEMS, m0, fb);
         }
         if (B_MN) {
 #pragma unroll
           for (int j = 0; j < BN / 32; j++) tma_load_2d(b + j * (32 * TG_BK * 4), &tmB, n0 + 32 * j, (kb0 + kb) * TG_BK, fb);
         } else {
-          tma_load_2d(b, &tmB, (kb0 + kb) * TG_BK, n0, fb);
+          tma_load_2d(b, &tmB, (kb0 + kb) * KB_ELEMS, n0, fb);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {                                                   // ---- MMA issuer (one thread)
-      constexpr uint32_t idesc = make_idesc(2, A_MN, B_MN, TG_BM, BN);
+      constexpr uint32_t idesc = make_idesc(F16 ? 0 : 2, A_MN, B_MN, TG_BM, BN);
       for (int kb = 0; kb < num_kb; kb++) {
         const int s = kb % STAGES;
         mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
@@ -195,7 +200,8 @@ __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_consta
         for (int kk = 0; kk < TG_BK / 8; kk++) {                       // UMMA_K = 8 for tf32
           const uint64_t ad = A_MN ? make_smem_desc(a + kk * MN_KSTEP, MN_LBO, MN_SBO, MN_LAYOUT) : make_smem_desc(a + kk * 32, 16, 1024);
           const uint64_t bd = B_MN ? make_smem_desc(b + kk * MN_KSTEP, MN_LBO, MN_SBO, MN_LAYOUT) : make_smem_desc(b + kk * 32, 16, 1024);
-          tc_mma_tf32(tmem_acc, ad, bd, idesc, (kb | kk) != 0);
+          if (F16) tc_mma_f16(tmem_acc, ad, bd, idesc, (kb | kk) != 0);
+          else tc_mma_tf32(tmem_acc, ad, bd, idesc, (kb | kk) != 0);
         }
         tc_commit(empty0 + 8 * s);                                     // frees the smem stage when these MMAs retire
       }
@@ -332,6 +338,8 @@ static int tcgen05_gemm_init() {
   if (e == cudaSuccess) e = tg_set_attrs<false, true>();
   if (e == cudaSuccess) e = tg_set_attrs<true, false>();
   if (e == cudaSuccess) e = tg_set_attrs<true, true>();
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tcgen05<false, false, 256, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg_smem(256, 2));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tcgen05<false, false, 256, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tg_smem(256, 4));
   return e == cudaSuccess ? 0 : -2;
 }
 
@@ -392,6 +400,14 @@ static void tg_dispatch(int BN, bool deep, dim3 grid, cudaStream_t st, const CUt
   if (BN == 256) { if (deep) tg_launch<A_MN, B_MN, 256, 4>(grid, st, ta, tb, g, pdl); else tg_launch<A_MN, B_MN, 256, 2>(grid, st, ta, tb, g, pdl); }
   else if (BN == 64) { if (deep) tg_launch<A_MN, B_MN, 64, 8>(grid, st, ta, tb, g, pdl); else tg_launch<A_MN, B_MN, 64, 4>(grid, st, ta, tb, g, pdl); }
   else { if (deep) tg_launch<A_MN, B_MN, 128, 6>(grid, st, ta, tb, g, pdl); else tg_launch<A_MN, B_MN, 128, 3>(grid, st, ta, tb, g, pdl); }
+}
+
+// fp16 K-major GEMM with prebuilt tensor maps (A: [M, K] halves box {64,128}; B: [N, K] halves box {64,256}); 128x256 tiles
+static int tcgen05_gemm_f16_launch(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g) {
+  dim3 grid((g.N + 255) / 256, (g.M + TG_BM - 1) / TG_BM, 1);
+  if ((long)grid.x * grid.y <= 148) k_gemm_tcgen05<false, false, 256, 4, true><<<grid, TG_THREADS, tg_smem(256, 4), st>>>(ta, tb, g);
+  else k_gemm_tcgen05<false, false, 256, 2, true><<<grid, TG_THREADS, tg_smem(256, 2), st>>>(ta, tb, g);
+  return cudaGetLastError() == cudaSuccess ? 0 : 3000;
 }
 
 // splits == 0: choose a split-K factor for few-tile / long-K problems (the caller must then accept a red.global epilogue)

@@ -9,6 +9,7 @@
 // at row off[d ? len[s]-1-t : t] + rank[s].  Every per-step operand is therefore one dense row block that a single
 // TMA box can fetch -- no gathers inside the recurrence.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -245,7 +246,8 @@ __device__ __forceinline__ long token_row(const StepLayout& L, int dir, int s, i
 __global__ void k_prep_x(const float* __restrict__ xraw, const int* __restrict__ tok_seq, const int* __restrict__ tokstart,
                          StepLayout L, int ntok, int E, int Tcap, int data_norm, float keep_in, uint64_t seed,
                          int64_t seq_gid0, int round_ops, float* __restrict__ xfw, float* __restrict__ xbw, int ldx, int ones_col,
-                         const int* __restrict__ tok_row, const float* __restrict__ table) {
+                         const int* __restrict__ tok_row, const float* __restrict__ table, __half* __restrict__ x16fw,
+                         __half* __restrict__ x16bw, int ld16) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= ntok) return;
   int s = tok_seq[warp];
@@ -279,6 +281,12 @@ __global__ void k_prep_x(const float* __restrict__ xraw, const int* __restrict__
     }
     *reinterpret_cast<float4*>(xfw + rfw * ldx + e4) = make_float4(vf[0], vf[1], vf[2], vf[3]);
     *reinterpret_cast<float4*>(xbw + rbw * ldx + e4) = make_float4(vb[0], vb[1], vb[2], vb[3]);
+    if (x16fw) {               // fp16 copies for the input-projection GEMM (the fp32 rows above feed the weight-gradient GEMM)
+      __half2 f01 = __floats2half2_rn(vf[0], vf[1]), f23 = __floats2half2_rn(vf[2], vf[3]);
+      __half2 b01 = __floats2half2_rn(vb[0], vb[1]), b23 = __floats2half2_rn(vb[2], vb[3]);
+      *reinterpret_cast<uint2*>(x16fw + rfw * ld16 + e4) = make_uint2(*reinterpret_cast<uint32_t*>(&f01), *reinterpret_cast<uint32_t*>(&f23));
+      *reinterpret_cast<uint2*>(x16bw + rbw * ld16 + e4) = make_uint2(*reinterpret_cast<uint32_t*>(&b01), *reinterpret_cast<uint32_t*>(&b23));
+    }
   }
 }
 
@@ -581,6 +589,14 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
     reinterpret_cast<float4*>(v)[i] = v4;
     reinterpret_cast<float4*>(p)[i] = p4;
     if (pr) reinterpret_cast<float4*>(pr)[i] = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+// W_ih (rows [0,E) of the TF kernel [E+H, 4H]) as fp16, transposed to K-major [4H][Kp] for the fp16 input-projection GEMM
+__global__ void k_pack_wih16(const float* __restrict__ K, __half* __restrict__ out, int E, int N4H, int Kp) {
+  long total = (long)N4H * Kp;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    int k = (int)(idx % Kp), n = (int)(idx / Kp);
+    out[idx] = __float2half_rn(k < E ? K[(long)k * N4H + n] : 0.0f);
   }
 }
 __global__ void k_round_copy(const float* __restrict__ src, float* __restrict__ dst, long n) {

@@ -142,6 +142,11 @@ struct icl_model {
   RecBwdMaps rp_bmaps;
   unsigned* rp_bar = nullptr;
   bool rp_bwd_on = false;       // k_rec_bwd is correct but measured slower (0.84 ms) than the per-step path (0.56 ms): opt-in
+  // fp16 input projection (K1): fp16 copies of the prepared inputs and of W_ih^T, kind::f16 GEMM
+  bool k1_f16 = false, wih_dirty = true;
+  int k1_Kp = 0;
+  __half* X16[2] = {}; __half* Wih16[2] = {};
+  CUtensorMap k1_ta[2], k1_tb[2];
   // second-generation forward recurrence (lstm_fwd16.cuh): fp16 recurrent operands, double-buffered x-projection boxes
   bool rf_on = false;
   int rf_UP = 0, rf_KP = 0, rf_nkb = 0, rf_nk16 = 0;
@@ -355,6 +360,23 @@ static int rec_init(icl_model* m) {
   return U == 20 ? rec_set_attr<20>(m->rp_nkb) : rec_set_attr<16>(m->rp_nkb);
 }
 
+static int k1_init(icl_model* m) {
+  m->k1_f16 = m->cfg.gemm_mode == ICL_GEMM_TCGEN05_TF32;
+  if (const char* e = getenv("ICL_K1_FP16")) m->k1_f16 = m->k1_f16 && atoi(e) != 0;
+  if (!m->k1_f16) return 0;
+  const int E = m->E, H = m->H, SW128 = (int)CU_TENSOR_MAP_SWIZZLE_128B;
+  m->k1_Kp = (E + 63) / 64 * 64;
+  const uint64_t RC = (uint64_t)m->rows_cap;
+  for (int d = 0; d < 2; d++) {
+    CK(cudaMalloc((void**)&m->X16[d], RC * m->k1_Kp * 2)); CK(cudaMemset(m->X16[d], 0, RC * m->k1_Kp * 2));
+    CK(cudaMalloc((void**)&m->Wih16[d], (size_t)4 * H * m->k1_Kp * 2));
+    int r = TmaCache::get16(m->X16[d], (uint64_t)m->k1_Kp, RC, (uint64_t)m->k1_Kp, 64, 128, SW128, &m->k1_ta[d]);
+    if (!r) r = TmaCache::get16(m->Wih16[d], (uint64_t)m->k1_Kp, (uint64_t)4 * H, (uint64_t)m->k1_Kp, 64, 256, SW128, &m->k1_tb[d]);
+    if (r) return fail("cuTensorMapEncodeTiled failed (%d) for the fp16 input-projection maps", r);
+  }
+  return 0;
+}
+
 template <int U> static int rec16_set_attr(int nkb) {
   cudaError_t e = cudaFuncSetAttribute(k_rec_fwd16<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, rec_fwd16_smem<U>(nkb));
   return e == cudaSuccess ? 0 : fail("cudaFuncSetAttribute(k_rec_fwd16): %s", cudaGetErrorString(e));
@@ -453,7 +475,7 @@ extern "C" void icl_destroy(icl_model* m) {
     F(m->XH[d]); F(m->Z[d]); F(m->Hx[d]); F(m->Cc[d]); F(m->dHout[d]); F(m->dhrec[d]); F(m->dcc[d]); F(m->R[d]);
   }
   F(m->Wp[0]); F(m->Wp[1]); F(m->rp_flags); F(m->rp_trace); F(m->rp_bar);
-  F(m->Hp16[0]); F(m->Hp16[1]); F(m->Wp16[0]); F(m->Wp16[1]);
+  F(m->Hp16[0]); F(m->Hp16[1]); F(m->Wp16[0]); F(m->Wp16[1]); F(m->X16[0]); F(m->X16[1]); F(m->Wih16[0]); F(m->Wih16[1]);
   F(m->d_partial); F(m->d_gnorm);
   for (auto& h : m->heads) {
     F(h.bi); F(h.dbi); F(h.dA); F(h.dBuf); for (auto a : h.act) F(a);
@@ -606,6 +628,7 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   if (tcgen05_gemm_init() != 0) { fail("icl_create: cannot resolve cuTensorMapEncodeTiled"); icl_destroy(m); *out = nullptr; return -1; }
   if (m->rp_U && rec_init(m) != 0) { icl_destroy(m); *out = nullptr; return -1; }
   if (m->rp_U && rec16_init(m) != 0) { icl_destroy(m); *out = nullptr; return -1; }
+  if (k1_init(m) != 0) { icl_destroy(m); *out = nullptr; return -1; }
   if (bptt_init(m) != 0) { icl_destroy(m); *out = nullptr; return -1; }
 #undef CKD
   return 0;
@@ -650,7 +673,7 @@ extern "C" int icl_set_tensor(icl_model* m, int kind, const char* name, const fl
   const Param& p = m->params[it->second];
   CK(cudaStreamSynchronize(m->stream));
   CK(cudaMemcpy(kind_buf(m, kind) + p.off, host, (size_t)p.rows * p.cols * 4, cudaMemcpyHostToDevice));
-  if (kind == 0) m->pr_dirty = m->wp_dirty = true;
+  if (kind == 0) m->pr_dirty = m->wp_dirty = m->wih_dirty = true;
   return 0;
 }
 extern "C" int icl_get_step(icl_model* m, int64_t* t) { *t = m->step; return 0; }
@@ -668,7 +691,7 @@ extern "C" int icl_wait_head_grads(icl_model* m, void* cuda_stream) {
   CK(cudaStreamWaitEvent((cudaStream_t)cuda_stream, m->ev_heads, 0));
   return 0;
 }
-extern "C" int icl_param_buffer(icl_model* m, void** p, int64_t* n) { *p = m->P; *n = m->n_params; m->pr_dirty = m->wp_dirty = true; return 0; }
+extern "C" int icl_param_buffer(icl_model* m, void** p, int64_t* n) { *p = m->P; *n = m->n_params; m->pr_dirty = m->wp_dirty = m->wih_dirty = true; return 0; }
 extern "C" int icl_kernel_launches(icl_model* m, int64_t* n) { *n = m->launches; return 0; }
 extern "C" int icl_last_step_ms(icl_model* m, float* ms) { *ms = m->last_ms; return 0; }
 extern "C" int icl_copy_bytes(icl_model* m, int64_t* h2d, int64_t* d2h) { *h2d = m->h2d_bytes; *d2h = m->d2h_bytes; return 0; }
@@ -909,7 +932,8 @@ static int lstm_forward(icl_model* m, float keep_in, uint64_t seed, int training
   PH_BEGIN(m, PH_PREP);
   k_prep_x<<<(unsigned)((Ntok * 32 + 255) / 256), 256, 0, st>>>(m->xraw, m->d_tokseq, m->d_tokstart, mk_layout(m), (int)Ntok, E, m->T_cap,
                                                                m->cfg.data_norm, keep_in, seed, m->seq_gid0, m->round_ops, m->xd[0], m->xd[1], m->ldx, E + H,
-                                                               m->use_rows ? m->d_tokrow : nullptr, m->tok_table);
+                                                               m->use_rows ? m->d_tokrow : nullptr, m->tok_table, m->k1_f16 ? m->X16[0] : nullptr,
+                                                               m->k1_f16 ? m->X16[1] : nullptr, m->k1_Kp);
   LAUNCHED(m);
   k_zero_pad_rows<<<dim3(m->Tmax, 2), 256, 0, st>>>(m->XH[0], m->XH[1], mk_layout(m), m->ldx); LAUNCHED(m);
   // h_prev of step 0 is the zero state: step 0's block of Hp stays zero (these are A rows of dW_hh)
@@ -917,11 +941,20 @@ static int lstm_forward(icl_model* m, float keep_in, uint64_t seed, int training
   PH_END(m, PH_PREP);
   // K1: time-batched input projection  Z = Xd * W_ih + b   (W_ih = kernel rows [0,E)), both directions
   PH_BEGIN(m, PH_PROJ);
+  if (m->k1_f16 && m->wih_dirty) {
+    for (int d = 0; d < 2; d++) {
+      k_pack_wih16<<<148, 256, 0, st>>>(m->P + m->params[m->pK[d]].off, m->Wih16[d], E, 4 * H, m->k1_Kp); LAUNCHED(m);
+    }
+    m->wih_dirty = false;
+  }
   for (int d = 0; d < 2; d++) {
     const float* K = wbase(m) + m->params[m->pK[d]].off;
-    GemmArgs g = mk_gemm(m->xd[d], m->ldx, K, 4 * H, m->Z[d], 4 * H, (int)NP, 4 * H, E);
+    GemmArgs g = mk_gemm(m->xd[d], m->ldx, K, 4 * H, m->Z[d], 4 * H, (int)NP, 4 * H, m->k1_f16 ? m->k1_Kp : E);
     g.epi.bias = m->P + m->params[m->pBias[d]].off;
-    CKI(gemm(m, st, false, true, g));
+    if (m->k1_f16) {        // fp16 operands (prepared inputs and W_ih^T), kind::f16, fp32 accumulate: half the operand traffic of TF32
+      if (tcgen05_gemm_f16_launch(st, m->k1_ta[d], m->k1_tb[d], g) != 0) return fail("fp16 input-projection GEMM launch failed");
+      m->launches++;
+    } else CKI(gemm(m, st, false, true, g));
   }
   PH_END(m, PH_PROJ);
   // K2: the recurrence
@@ -1289,6 +1322,7 @@ static int apply_update(icl_model* m, double extra_sumsq) {
                                   len, m->d_gnorm, m->cfg.clip_norm, lr_t, (float)b1, (float)b2, m->cfg.adam_epsilon);
     LAUNCHED(m);
   }
+  m->wih_dirty = true;
   if (!getenv("ICL_DEBUG_STALE_WP")) m->wp_dirty = true;   // the packed recurrent weights of the persistent forward kernel follow
                                                              // the update (the env knob exists so that a test can prove it catches staleness)
   PH_END(m, PH_UPDATE);
