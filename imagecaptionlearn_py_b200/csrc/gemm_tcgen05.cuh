@@ -127,7 +127,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, bool a_mn, bool b_mn,
 // well as TF32's (the input projection: embeddings x W_ih), at half the operand bytes and twice the MMA rate.  g.K counts halves.
 template <bool A_MN, bool B_MN, int BN, int STAGES, bool F16 = false>
 __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_constant__ CUtensorMap tmA,
-                                                             const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+                                                             const __grid_constant__ CUtensorMap tmB,
+                                                             const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
   constexpr int B_BYTES = BN * TG_BK * 4;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-byte alignment
@@ -212,6 +213,44 @@ __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_consta
     tc_fence_after();
     const int q = warp & 3;                                            // a warp may only touch TMEM lanes [32*(warp%4), +32)
     const int ehalf = (warp - 2) >> 2;                                 // which of the quarter's two warps
+    if constexpr (F16) {
+      // Output path of the input projection (plain epilogue + bias, dense C): the 128 x BN fp32 tile leaves as 32x32 TMA boxes.
+      // Each warp stages a chunk in the 128B-swizzled layout of tmC (16-byte piece j of row r at r*128 + ((j ^ (r & 7)) << 4)),
+      // two buffers per warp in the idle operand ring, so the store of chunk i overlaps the TMEM read of chunk i+1.  (The scalar
+      // row loop below issues one 128-byte store per row and chunk: 1024 LSU stores per tile.)
+      const uint32_t sbuf = base + (uint32_t)(warp - 2) * 8192;
+      const float* bias = g.epi.bias;
+      int ci = 0;
+#pragma unroll 1
+      for (int c = ehalf * 32; c < BN; c += 32 * TG_EPW, ci++) {
+        if (n0 + c >= g.N) break;
+        const uint32_t buf = sbuf + (ci & 1) * 4096;
+        if (ci >= 2) {                                                 // the store issued two chunks ago has read this buffer
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+        }
+        uint32_t r[32];
+        tc_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + c, r);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; j4++) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias && n0 + c + j4 * 4 < g.N) b4 = *reinterpret_cast<const float4*>(bias + n0 + c + j4 * 4);
+          const float x0 = __uint_as_float(r[j4 * 4]) + b4.x, x1 = __uint_as_float(r[j4 * 4 + 1]) + b4.y,
+                      x2 = __uint_as_float(r[j4 * 4 + 2]) + b4.z, x3 = __uint_as_float(r[j4 * 4 + 3]) + b4.w;
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(buf + lane * 128 + ((j4 ^ (lane & 7)) << 4)), "f"(x0), "f"(x1),
+                       "f"(x2), "f"(x3) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC), "r"(buf), "r"(n0 + c),
+                       "r"(m0 + q * 32) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+    } else {
     float* stg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))) + (warp - 2) * (32 * 33);
     const int mrow0 = m0 + q * 32;
     // everything the row loop needs lives in registers: kernel parameters sit in the constant bank and a dependent
@@ -304,6 +343,7 @@ __global__ void __launch_bounds__(TG_THREADS) k_gemm_tcgen05(const __grid_consta
       }
       __syncwarp();
     }
+    }   // !F16
   }
   tc_fence_before();
   __syncthreads();
@@ -386,13 +426,13 @@ static bool tcgen05_gemm_supported(const GemmArgs& g, bool a_mn, bool b_mn) {
 // pdl: launch with programmatic stream serialization so the kernel's prologue overlaps its predecessor's tail
 template <bool A_MN, bool B_MN, int BN, int STAGES>
 static void tg_launch(dim3 grid, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, bool pdl) {
-  if (!pdl) { k_gemm_tcgen05<A_MN, B_MN, BN, STAGES><<<grid, TG_THREADS, tg_smem(BN, STAGES), st>>>(ta, tb, g); return; }
+  if (!pdl) { k_gemm_tcgen05<A_MN, B_MN, BN, STAGES><<<grid, TG_THREADS, tg_smem(BN, STAGES), st>>>(ta, tb, ta, g); return; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(TG_THREADS); cfg.dynamicSmemBytes = tg_smem(BN, STAGES); cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, k_gemm_tcgen05<A_MN, B_MN, BN, STAGES>, ta, tb, g);
+  cudaLaunchKernelEx(&cfg, k_gemm_tcgen05<A_MN, B_MN, BN, STAGES>, ta, tb, ta, g);      // tmC is only used by the fp16 variant
 }
 template <bool A_MN, bool B_MN>
 static void tg_dispatch(int BN, bool deep, dim3 grid, cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g,
@@ -403,10 +443,11 @@ static void tg_dispatch(int BN, bool deep, dim3 grid, cudaStream_t st, const CUt
 }
 
 // fp16 K-major GEMM with prebuilt tensor maps (A: [M, K] halves box {64,128}; B: [N, K] halves box {64,256}); 128x256 tiles
-static int tcgen05_gemm_f16_launch(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g) {
+// C: fp32 [rows, N] box {32, 32} SWIZZLE_128B (the tile leaves through TMA stores; rows beyond the tensor are clipped)
+static int tcgen05_gemm_f16_launch(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& g) {
   dim3 grid((g.N + 255) / 256, (g.M + TG_BM - 1) / TG_BM, 1);
-  if ((long)grid.x * grid.y <= 148) k_gemm_tcgen05<false, false, 256, 4, true><<<grid, TG_THREADS, tg_smem(256, 4), st>>>(ta, tb, g);
-  else k_gemm_tcgen05<false, false, 256, 2, true><<<grid, TG_THREADS, tg_smem(256, 2), st>>>(ta, tb, g);
+  if ((long)grid.x * grid.y <= 148) k_gemm_tcgen05<false, false, 256, 4, true><<<grid, TG_THREADS, tg_smem(256, 4), st>>>(ta, tb, tc, g);
+  else k_gemm_tcgen05<false, false, 256, 2, true><<<grid, TG_THREADS, tg_smem(256, 2), st>>>(ta, tb, tc, g);
   return cudaGetLastError() == cudaSuccess ? 0 : 3000;
 }
 

@@ -146,7 +146,7 @@ struct icl_model {
   bool k1_f16 = false, wih_dirty = true;
   int k1_Kp = 0;
   __half* X16[2] = {}; __half* Wih16[2] = {};
-  CUtensorMap k1_ta[2], k1_tb[2];
+  CUtensorMap k1_ta[2], k1_tb[2], k1_tc[2];
   // second-generation forward recurrence (lstm_fwd16.cuh): fp16 recurrent operands, double-buffered x-projection boxes
   bool rf_on = false;
   int rf_UP = 0, rf_KP = 0, rf_nkb = 0, rf_nk16 = 0;
@@ -373,6 +373,7 @@ static int k1_init(icl_model* m) {
     int r = TmaCache::get16(m->X16[d], (uint64_t)m->k1_Kp, RC, (uint64_t)m->k1_Kp, 64, 128, SW128, &m->k1_ta[d]);
     if (!r) r = TmaCache::get16(m->Wih16[d], (uint64_t)m->k1_Kp, (uint64_t)4 * H, (uint64_t)m->k1_Kp, 64, 256, SW128, &m->k1_tb[d]);
     if (r) return fail("cuTensorMapEncodeTiled failed (%d) for the fp16 input-projection maps", r);
+    CKI(box_map(m, m->Z[d], 4 * H, RC, 32, 32, SW128, &m->k1_tc[d]));
   }
   return 0;
 }
@@ -952,7 +953,7 @@ static int lstm_forward(icl_model* m, float keep_in, uint64_t seed, int training
     GemmArgs g = mk_gemm(m->xd[d], m->ldx, K, 4 * H, m->Z[d], 4 * H, (int)NP, 4 * H, m->k1_f16 ? m->k1_Kp : E);
     g.epi.bias = m->P + m->params[m->pBias[d]].off;
     if (m->k1_f16) {        // fp16 operands (prepared inputs and W_ih^T), kind::f16, fp32 accumulate: half the operand traffic of TF32
-      if (tcgen05_gemm_f16_launch(st, m->k1_ta[d], m->k1_tb[d], g) != 0) return fail("fp16 input-projection GEMM launch failed");
+      if (tcgen05_gemm_f16_launch(st, m->k1_ta[d], m->k1_tb[d], m->k1_tc[d], g) != 0) return fail("fp16 input-projection GEMM launch failed");
       m->launches++;
     } else CKI(gemm(m, st, false, true, g));
   }
