@@ -592,7 +592,10 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
   }
 }
 // W_ih (rows [0,E) of the TF kernel [E+H, 4H]) as fp16, transposed to K-major [4H][Kp] for the fp16 input-projection GEMM
-__global__ void k_pack_wih16(const float* __restrict__ K, __half* __restrict__ out, int E, int N4H, int Kp) {
+__global__ void k_pack_wih16(const float* __restrict__ K0, const float* __restrict__ K1, __half* __restrict__ out0,
+                             __half* __restrict__ out1, int E, int N4H, int Kp) {     // blockIdx.y = direction
+  const float* K = blockIdx.y ? K1 : K0;
+  __half* out = blockIdx.y ? out1 : out0;
   long total = (long)N4H * Kp;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     int k = (int)(idx % Kp), n = (int)(idx / Kp);

@@ -49,7 +49,10 @@ struct RecFwd16Args {
 };
 
 // Packed fp16 W_hh: row (j*4U + n), n = c*16 + gate*4 + i <-> unit j*U + 4c + i (as k_pack_whh_fwd); column k' = (k / U) * UP + k % U
-__global__ void k_pack_whh_fwd16(const float* __restrict__ Whh, __half* __restrict__ Wp, int H, int U, int UP, int nsl, int Kp) {
+__global__ void k_pack_whh_fwd16(const float* __restrict__ Whh0, const float* __restrict__ Whh1, __half* __restrict__ Wp0,
+                                 __half* __restrict__ Wp1, int H, int U, int UP, int nsl, int Kp) {     // blockIdx.y = direction
+  const float* Whh = blockIdx.y ? Whh1 : Whh0;
+  __half* Wp = blockIdx.y ? Wp1 : Wp0;
   long total = (long)nsl * 4 * U * Kp;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     int kp = (int)(idx % Kp), row = (int)(idx / Kp);
