@@ -681,11 +681,20 @@ class Saver(object):
 
     def save(self, sess, path):
         sess.ensure()
-        np.savez(path + ".npz", **sess.state_dict())
+        st = sess.state_dict()
+        np.savez(path + ".npz", **st)
+        if os.environ.get("ICL_SAVE_TF_BUNDLE"):        # additionally a TensorFlow Saver-V2 bundle (<path>.index / .data-*)
+            from . import tf_checkpoint
+            tf_checkpoint.write_bundle(path, tf_checkpoint.from_state_dict(st))
         return path
 
     def restore(self, sess, path):
+        """Restores `<path>.npz` (ours) or, if only `<path>.index` exists, a TensorFlow Saver-V2 checkpoint of the reference."""
         sess.ensure()
+        if not os.path.exists(path + ".npz") and os.path.exists(path + ".index"):
+            from . import tf_checkpoint
+            sess.load_state(tf_checkpoint.to_state_dict(tf_checkpoint.read_bundle(path)))
+            return
         with np.load(path + ".npz") as z:
             sess.load_state({k: z[k] for k in z.files})
 

@@ -647,6 +647,34 @@ extern "C" int icl_set_token_table(icl_model* m, const float* table, int64_t n_r
   return 0;
 }
 
+// CRC-32C (Castagnoli), host only: the tensor checksums of TensorFlow Saver-V2 checkpoints (tf_checkpoint.py).  Slice-by-8 tables.
+extern "C" uint32_t icl_crc32c(const void* data, uint64_t n, uint32_t crc) {
+  static uint32_t T[8][256];
+  static bool init = false;
+  if (!init) {
+    for (uint32_t i = 0; i < 256; i++) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      T[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; i++)
+      for (int t = 1; t < 8; t++) T[t][i] = (T[t - 1][i] >> 8) ^ T[0][T[t - 1][i] & 0xFF];
+    init = true;
+  }
+  const uint8_t* p = (const uint8_t*)data;
+  crc = ~crc;
+  while (n >= 8) {
+    uint32_t lo, hi;
+    memcpy(&lo, p, 4); memcpy(&hi, p + 4, 4);
+    lo ^= crc;
+    crc = T[7][lo & 0xFF] ^ T[6][(lo >> 8) & 0xFF] ^ T[5][(lo >> 16) & 0xFF] ^ T[4][lo >> 24] ^ T[3][hi & 0xFF] ^ T[2][(hi >> 8) & 0xFF] ^
+          T[1][(hi >> 16) & 0xFF] ^ T[0][hi >> 24];
+    p += 8; n -= 8;
+  }
+  while (n--) crc = T[0][(crc ^ *p++) & 0xFF] ^ (crc >> 8);
+  return ~crc;
+}
+
 extern "C" int icl_set_stream(icl_model* m, void* s) { m->stream = (cudaStream_t)s; return 0; }
 extern "C" int icl_sync(icl_model* m) { CK(cudaStreamSynchronize(m->stream)); CK(cudaStreamSynchronize(m->aux)); return 0; }
 extern "C" int icl_param_count(icl_model* m) { return (int)m->params.size(); }

@@ -102,6 +102,7 @@ void icl_destroy(icl_model* m);
 /* corpus cache: the embedding rows of every caption token, concatenated, stay resident in HBM;
    nn_utils/data.py:397-403 copies them row by row into a fresh [S,T,300] tensor per batch instead */
 int icl_set_token_table(icl_model* m, const float* table_rows_by_E, int64_t n_rows);
+uint32_t icl_crc32c(const void* data, uint64_t n, uint32_t crc0);  /* host: CRC-32C of TF Saver-V2 checkpoint tensors (tf_checkpoint.py) */
 int icl_set_stream(icl_model* m, void* cuda_stream);             /* cudaStream_t of the caller (e.g. torch's current) */
 
 /* parameters are named like the TF variables so checkpoints map 1:1 (tf.train.Saver, icl_core_lstm.py:107,155) */

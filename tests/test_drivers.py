@@ -134,3 +134,36 @@ def test_multitask_cli_train_then_predict(tmp_path, scheme):
         C = len(drivers.MT_CLASSES[task])
         f = lines[0].split(",")
         assert len(f) == C + 1 and abs(sum(np.exp(float(x)) for x in f[1:]) - 1.0) < 1e-4
+
+
+@pytest.mark.gpu
+def test_saver_restores_a_tf_saver_v2_bundle(tmp_path, monkeypatch):
+    """Saver.save with ICL_SAVE_TF_BUNDLE=1 also writes `<path>.index` / `.data-00000-of-00001` under the TF variable names (Adam
+    slots as `<var>/Adam`, `<var>/Adam_1`); Saver.restore falls back to such a bundle when there is no .npz -- the route by which a
+    checkpoint of the reference (tf.train.Saver, icl_core_lstm.py:107,155) is loaded."""
+    import os
+    from imagecaptionlearn_py_b200 import core, tf_checkpoint
+    from tests.helpers import tiny_problem
+    from tests.test_gpu_parity import make_session
+    from imagecaptionlearn_py_b200 import _cabi
+    p = tiny_problem(seed=3, task="nonvis", enc="first_last_mention", act="relu", S=16, T=7, E=8, H=4, F=4, widths=(8, 4))
+    core_, sess = make_session(p, "simt")
+    sess.run(_cabi.OP_TRAIN, [dict(p["batch"])], 1.0, 1.0, True)
+    monkeypatch.setenv("ICL_SAVE_TF_BUNDLE", "1")
+    path = str(tmp_path / "m.model")
+    core.Saver().save(sess, path)
+    want = sess.state_dict()
+    proba = sess.run(_cabi.OP_PREDICT, [dict(p["batch"])], 1.0, 1.0, True)[0]["proba"].copy()
+    sess.close()
+    names = tf_checkpoint.read_bundle(path)
+    assert "hdn_1/Variable/Adam" in names and "bidirectional_lstm/bidirectional_rnn/fw/basic_lstm_cell/kernel" in names
+    os.remove(path + ".npz")
+    core_, sess2 = make_session(p, "simt")
+    for k in p["params"]:
+        sess2.set_tensor(k, np.zeros_like(p["params"][k]).reshape(1, -1) if p["params"][k].ndim == 1 else np.zeros_like(p["params"][k]))
+    core.Saver().restore(sess2, path)
+    got = sess2.state_dict()
+    for k, v in want.items():
+        assert np.array_equal(np.asarray(got[k]), np.asarray(v)), k
+    assert np.array_equal(sess2.run(_cabi.OP_PREDICT, [dict(p["batch"])], 1.0, 1.0, True)[0]["proba"], proba)
+    sess2.close()
