@@ -319,10 +319,11 @@ def main():
         # cross HBM once (fp32), per valid token and direction, x 2 directions
         tok2 = 2.0 * n_tok
         work = {   # phase: (flops, bytes, kernel, launches of that kernel per step)
-            "proj_gemm": (tok2 * 2 * E * 4 * H, tok2 * (E + 4 * H) * 4, "k_gemm_tcgen05<0, 1, 256, 2>", 2),
-            "rec_fwd": (tok2 * 2 * H * 4 * H, tok2 * (4 * H + 4 * H + 3 * H) * 4, "k_rec_fwd", 1),        # Zx in; gates, c, h, TF32(h) out
+            "proj_gemm": (tok2 * 2 * E * 4 * H, tok2 * (E * 2 + 4 * H * 4), "k_gemm_tcgen05<0, 0, 256, 2, 1>", 2),   # fp16 x in, fp32 out
+            "rec_fwd": (tok2 * 2 * H * 4 * H, tok2 * (4 * H + 4 * H + 3 * H) * 4, "k_rec_fwd16", 1),      # Zx in; gates, c, h, TF32(h) out
+            # the BPTT is one launch pair (8-CTA clusters for the longest chains + 4-CTA clusters, concurrent): counted as one
             "rec_bwd": (tok2 * 2 * H * 4 * H, tok2 * (4 * H + 3 * H + 4 * H) * 4, "k_bptt_cluster", 1),   # gates, c, c_prev, dH in; dZ out
-            "wgrad": (tok2 * 2 * (E + H) * 4 * H, tok2 * (E + H + 4 * H) * 4, "k_gemm_tcgen05<1, 1, 256, 4>", 2)}
+            "wgrad": (tok2 * 2 * (E + H) * 4 * H, tok2 * (E + H + 4 * H) * 4, "k_gemm_tcgen05<1, 1, 256, 4, 0>", 2)}
         dom = max(work, key=lambda k: ph_ms[_cabi.PHASES.index(k)])     # the dominant kernel group of the step
         name = dom
         t_ms = float(ph_ms[_cabi.PHASES.index(dom)])
@@ -331,10 +332,16 @@ def main():
         traffic = None
         try:       # DRAM bytes of that kernel from the committed `ncu --set full` capture of this workload (profiles/)
             if args.workload == "card2048" and world == 1:
-                for e in json.load(open(os.path.join(ROOT, "profiles", "r1f_ncu_full_summary.json"))):
+                seen = set()
+                for e in json.load(open(os.path.join(ROOT, "profiles", "r1g_ncu_full_summary.json"))):
                     if e["kernel"].startswith(kernel) and (dom != "wgrad" or e["grid"].replace(" ", "") == "(5,5,5)"):
-                        traffic = e["dram_bytes"]
-                        break
+                        if dom == "rec_bwd":                   # sum over the two concurrent launches of one step
+                            if e["kernel"] not in seen:
+                                traffic = (traffic or 0) + e["dram_bytes"]
+                                seen.add(e["kernel"])
+                        else:
+                            traffic = e["dram_bytes"]
+                            break
         except Exception:
             pass
         if t_hbm >= t_tensor:
