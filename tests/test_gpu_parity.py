@@ -525,3 +525,59 @@ def test_forward_follows_the_updated_recurrent_weights(stale, monkeypatch):
         assert err > 3 * TOL["tf32"]["fwd"], err
     else:
         assert err < TOL["tf32"]["fwd"], err
+
+
+EDGE = {
+    "zero-length-and-past-the-end": dict(S=37, T=9, zero=(3, 20), past_end=True),
+    "one-sequence": dict(S=1, T=5),
+    "uniform-full-length-T50": dict(S=12, T=50, uniform=True),
+    "129-sequences-two-row-tiles": dict(S=129, T=11),
+    "256-sequences-exact-tiles": dict(S=256, T=6),
+}
+
+
+@pytest.mark.parametrize("name", list(EDGE), ids=list(EDGE))
+def test_edge_case_batches_match_oracle(name):
+    """Ragged / degenerate batches through the persistent kernels (H = 20: k_rec_fwd16 + k_bptt_cluster): empty sequences
+    (dynamic_rnn: all-zero outputs, no state update), span indices past the end of a sequence (TF gathers the zero output rows
+    there), a single sequence, every sequence at the padded length T = 50, batch sizes at and one past a 128-row tile boundary."""
+    from imagecaptionlearn_py_b200 import _cabi
+    e = EDGE[name]
+    p = tiny_problem(seed=71, task="nonvis", enc="first_last_mention", act="tanh", S=e["S"], T=e["T"], E=12, H=20, F=4, widths=(16, 8))
+    lens = p["lens"].copy()
+    if e.get("uniform"):
+        lens[:] = e["T"]
+        rng = np.random.default_rng(5)
+        p["x"][:] = rng.standard_normal(p["x"].shape)
+    for s_ in e.get("zero", ()):
+        lens[s_] = 0
+        p["x"][s_] = 0.0
+    hb = p["batch"]
+    if e.get("past_end"):                       # every last_i index one past the end of its sequence; empty sequences: all indices
+        hb["last_i_fw"][:, 2] = lens
+        hb["last_i_bw"][:, 2] = lens
+        hb["last_i_fw"][:, 2] = np.minimum(hb["last_i_fw"][:, 2], e["T"] - 1)
+        hb["last_i_bw"][:, 2] = np.minimum(hb["last_i_bw"][:, 2], e["T"] - 1)
+    else:
+        for k in ("first_i_fw", "first_i_bw", "last_i_fw", "last_i_bw"):
+            hb[k][:, 2] = np.minimum(hb[k][:, 2], np.maximum(lens - 1, 0))
+    p["lens"] = lens
+    hb["sentences"], hb["seq_lengths"] = p["x"], lens.astype(np.float64)
+    core, sess = make_session(p, "tf32")
+    r = sess.run(_cabi.OP_GRADS, [dict(hb)], 1.0, 1.0, True)[0]
+    f = O.model_forward(p["params"], p["cfg"], p["x"], lens, [hb])
+    g = O.model_backward(p["params"], p["cfg"], f, [hb])
+    assert np.all(np.isfinite(r["proba"]))
+    assert relerr(r["proba"], f["heads"][0]["proba"]) < TOL["tf32"]["fwd"]
+    assert abs(r["loss"] - f["loss"]) < TOL["tf32"]["fwd"] * max(1.0, abs(f["loss"]))
+    for d, key in ((0, "out_fw"), (1, "out_bw")):
+        got = np.empty((e["S"], sess.max_seq_len, 20), np.float32)
+        _cabi.check(_cabi.lib().icl_get_lstm_outputs(sess.handle, d, _cabi.np_ptr(got)))
+        got = got[:, :e["T"]]
+        assert relerr(got, f[key]) < TOL["tf32"]["fwd"], key
+        for s_ in range(e["S"]):
+            assert not np.any(got[s_, lens[s_]:]), (key, s_)          # exact zeros past the length
+    bad = {k: relerr(sess.get_tensor(k, 1).reshape(v.shape), v) for k, v in g.items()}
+    bad = {k: v for k, v in bad.items() if v > TOL["tf32"]["grad"]}
+    assert not bad, bad
+    sess.close()
