@@ -664,7 +664,9 @@ def get_pred_scores_mcc(task, encoding_scheme, sess, batch_size, ids, data_dict,
     for i in range(id_matrix.shape[0]):
         if log is not None:
             log.log_status('info', None, 'Predicting; %d batches complete (%.2f%%)', i, 100.0 * i / id_matrix.shape[0])
-        bt = nn_data.load_batch(list(id_matrix[i]), data_dict, task, n_classes, packed=nn_data.default_packing())
+        # keep-probabilities are 1.0 here, so every distinct caption of the batch is encoded once (exact; data.load_batch)
+        bt = nn_data.load_batch(list(id_matrix[i]), data_dict, task, n_classes, packed=nn_data.default_packing(),
+                                dedup=not os.environ.get("ICL_NO_DEDUP"))
         scores = run_op(sess, Op("predicted_proba", scope), [bt], 1.0, 1.0, encoding_scheme, [task], [scope], False)
         n_rows = len(scores) if i < id_matrix.shape[0] - 1 else batch_size - pad
         for j in range(n_rows):

@@ -38,13 +38,19 @@ def default_packing():
     return False if os.environ.get("ICL_HOST_SENTENCES") else "rows"
 
 
-def load_batch(ids, data_dict, task, n_classes, packed=False):
+def load_batch(ids, data_dict, task, n_classes, packed=False, dedup=False):
     """Vectorised equivalent of nn_utils/data.py:349-528.
 
     packed=True returns 'sentences_packed' [sum(len),E] (caption-major valid tokens) instead of materialising the zero-padded
     'sentences' tensor; packed="rows" returns 'token_rows' (int32 [sum(len)], row numbers into 'token_table' = the corpus'
     caption matrices concatenated, which `core.Session` keeps resident on the device).  `core.run_op` understands all three;
-    the integer index matrices, lengths, features and labels are identical in every mode."""
+    the integer index matrices, lengths, features and labels are identical in every mode.
+
+    dedup=True encodes every distinct caption of the batch ONCE: the reference gives each mention / pair / mention-box example its
+    own copy of its caption (nn_utils/data.py:367-403; an affinity batch repeats a caption ~60 times).  The sentence tensors then
+    hold the distinct captions in order of first use and the `sent` column of every index matrix points at them.  Exact whenever
+    the keep probabilities are 1.0 (prediction): the copies' LSTM outputs are identical.  Not for training: the reference draws
+    an independent dropout mask per copy."""
     B = len(ids)
     cross = task == "rel_cross"
     n_seq = 2 * B if cross else B
@@ -63,6 +69,12 @@ def load_batch(ids, data_dict, task, n_classes, packed=False):
         sids = [cap_of[m][0] for m in m_ids]
     else:
         sids = [cap_of[m] for m in m_ids]
+    seq_of = np.arange(n_seq)                                    # index-matrix sentence number -> row of the sentence tensors
+    if dedup:
+        first = {}
+        seq_of = np.array([first.setdefault(s, len(first)) for s in sids], dtype=np.int64)
+        sids = list(first.keys())
+        n_seq = len(sids)
     ol = np.array([offs[s] for s in sids], dtype=np.int64).reshape(n_seq, 2)
     lens = ol[:, 1]
     rows = np.repeat(np.arange(n_seq), lens)
@@ -86,6 +98,7 @@ def load_batch(ids, data_dict, task, n_classes, packed=False):
     mi = np.array([data_dict["mention_indices"][m] for m in m_ids], dtype=np.int32)
     ar = np.arange(B, dtype=np.int32)
     si, sj = (2 * ar, 2 * ar + 1) if cross else (ar, ar)
+    si, sj = seq_of[si].astype(np.int32), seq_of[sj].astype(np.int32)
     zeros, ones = np.zeros(B, np.int32), np.ones(B, np.int32)
 
     def rows3(d, s, w):

@@ -132,3 +132,27 @@ def test_token_rows_mode_addresses_the_same_embedding_rows():
         for k in a:
             if k != "sentences":
                 assert np.array_equal(a[k], c[k]), k
+
+
+def test_dedup_batches_address_the_same_tokens():
+    """load_batch(dedup=True): distinct captions once, index matrices remapped -- every (sentence, word) an example addresses is
+    the same token as without de-duplication, and everything that is not a sentence index is unchanged."""
+    from imagecaptionlearn_py_b200 import data as nn_data
+    from imagecaptionlearn_py_b200 import synth
+    corpus = synth.make_corpus(4, seed=17, with_boxes=True, box_width=8)
+    for task in ("nonvis", "rel_intra", "rel_cross", "affinity"):
+        dd = synth.make_data_dict(corpus, task, F=8)
+        ids = synth.example_ids(dd, task)[:64]
+        C = synth.N_CLASSES[task]
+        a = nn_data.load_batch(ids, dd, task, C)
+        b = nn_data.load_batch(ids, dd, task, C, dedup=True)
+        assert b["sentences"].shape[0] < a["sentences"].shape[0] and b["sentences"].shape[0] == len(b["seq_lengths"])
+        for k in nn_data.INDEX_NAMES:
+            ia, ib = a[k], b[k]
+            assert np.array_equal(ia[:, [0, 2]], ib[:, [0, 2]]), k
+            assert np.array_equal(a["seq_lengths"][ia[:, 1]], b["seq_lengths"][ib[:, 1]]), k
+            assert np.array_equal(a["sentences"][ia[:, 1], ia[:, 2]], b["sentences"][ib[:, 1], ib[:, 2]]), k
+            assert np.array_equal(a["sentences"][ia[:, 1]], b["sentences"][ib[:, 1]]), k         # the whole caption matches
+        for k in a:
+            if k not in nn_data.INDEX_NAMES and k not in ("sentences", "seq_lengths"):
+                assert np.array_equal(a[k], b[k]), k

@@ -581,3 +581,32 @@ def test_edge_case_batches_match_oracle(name):
     bad = {k: v for k, v in bad.items() if v > TOL["tf32"]["grad"]}
     assert not bad, bad
     sess.close()
+
+
+def test_caption_dedup_gives_identical_predictions():
+    """get_pred_scores_mcc encodes every distinct caption of a batch once (data.load_batch(dedup=True)); with keep-probabilities
+    1.0 the probabilities are bit-identical to the reference's one-copy-per-example batches (ICL_NO_DEDUP=1)."""
+    import os
+    from imagecaptionlearn_py_b200 import core, synth
+    corpus = synth.make_corpus(3, seed=19, E=12, with_boxes=True, box_width=16)
+    dd = synth.make_data_dict(corpus, "affinity", F=8)
+    ids = synth.example_ids(dd, "affinity")[:150]
+    out = {}
+    for mode in ("dedup", "copies"):
+        if mode == "copies":
+            os.environ["ICL_NO_DEDUP"] = "1"
+        try:
+            core.reset_default_graph()
+            core.set_random_seeds()
+            with core.variable_scope("bidirectional_lstm"):
+                core.setup_bidirectional_lstm(20, False, n_embedding_width=12)
+            core.setup_core_architecture("affinity", "first_last_mention", 64, 16, 1, False, "relu", 2, 8, box_embedding_width=16)
+            with core.Session(max_seq_len=dd["max_seq_len"]) as sess:
+                sess.ensure()
+                sess.initialize()
+                out[mode], _ = core.get_pred_scores_mcc("affinity", "first_last_mention", sess, 64, ids, dd, 2)
+        finally:
+            os.environ.pop("ICL_NO_DEDUP", None)
+    assert set(out["dedup"]) == set(out["copies"]) == set(ids)
+    for k in ids:
+        assert np.array_equal(out["dedup"][k], out["copies"][k]), k
