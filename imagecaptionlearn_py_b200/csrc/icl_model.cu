@@ -191,7 +191,9 @@ struct HostPool {
   uint64_t gen = 0;
   bool stop = false;
   HostPool() {
-    int n = (int)std::max(1u, std::min(4u, std::thread::hardware_concurrency())) - 1;
+    unsigned share = std::thread::hardware_concurrency();            // one process per GPU: split the host cores between the ranks
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) share /= (unsigned)std::max(1, atoi(e));
+    int n = (int)std::max(1u, std::min(4u, share)) - 1;
     if (const char* e = getenv("ICL_HOST_THREADS")) n = std::max(0, atoi(e) - 1);
     for (int i = 0; i < n; i++) th.emplace_back([this] { worker(); });
   }
