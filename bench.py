@@ -43,7 +43,7 @@ E, T_PAD, KEEP_IN, KEEP = 300, 50, 0.5, 0.5
 LR, ADAM_EPS, CLIP = 1e-3, 1e-8, 5.0
 
 
-def make_batch(wl, seed, packed=False):
+def make_batch(wl, seed, packed=False, dedup=False):
     """One reference-shaped batch_tensors dict (nn_utils/data.py:349-528) from the synthetic corpus."""
     from imagecaptionlearn_py_b200 import data as nn_data
     from imagecaptionlearn_py_b200 import synth
@@ -60,7 +60,7 @@ def make_batch(wl, seed, packed=False):
         ids = list(np.asarray(ids, dtype=object)[rng.permutation(len(ids))])
     if len(ids) < B:
         raise RuntimeError("synthetic corpus too small: %d ids for batch %d" % (len(ids), B))
-    return nn_data.load_batch(ids[:B], dd, task, wl["C"], packed=packed)
+    return nn_data.load_batch(ids[:B], dd, task, wl["C"], packed=packed, dedup=dedup)
 
 
 def flops_per_token(H, train=True):
@@ -159,6 +159,62 @@ def run_reference(args, wl):
                 cpu_baseline=dict(value=r["value"], unit="captions/s", cores=r["cores"], kind="port", sample=r["sample"]),
                 e2e=dict(value=r["value"], unit="captions/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
+
+
+def affinity_pairs_per_sec(local, steps=10, warmup=3):
+    """BASELINE.json's second metric, "mention-box pairs/sec", on configs[3] shapes (icl_affinity_lstm: B=512 mention-box pairs per
+    step, 4096-d box features, H=300, pairs grouped by image): train pairs/s with the batch resident in HBM (CUDA events), train
+    pairs/s end to end through run_op with host buffers, and predict pairs/s end to end through get_pred_scores_mcc's batch path
+    (keep 1.0, every distinct caption of a batch encoded once)."""
+    import ctypes as C
+    import torch
+    from imagecaptionlearn_py_b200 import _cabi, core
+    wl = WORKLOADS["affinity512"]
+    bt = make_batch(wl, 20171201, packed="rows")
+    core.reset_default_graph()
+    core.set_random_seeds()
+    with core.variable_scope("bidirectional_lstm"):
+        core.setup_bidirectional_lstm(wl["H"], wl["data_norm"], n_embedding_width=E)
+    core.setup_core_architecture(wl["task"], "first_last_mention", wl["B"], wl["start"], wl["depth"], False, "relu", wl["C"], wl["F"],
+                                 box_embedding_width=bt["box_embeddings"].shape[1])
+    core.add_train_op(core.get_collection("loss")[0], LR, ADAM_EPS, CLIP)
+    sess = core.Session(max_seq_len=T_PAD, device=local)
+    sess.ensure()
+    L = _cabi.lib()
+    train_op, proba_op = core.get_collection("train_op")[0], core.get_collection("predicted_proba")[0]
+    ka = []
+    b = sess.build_batch([bt], True, ka)
+    sess._bind_stream()
+    _cabi.check(L.icl_upload(sess.handle, C.byref(b)))
+    for i in range(warmup):
+        _cabi.check(L.icl_run_resident(sess.handle, _cabi.OP_TRAIN, KEEP_IN, KEEP, 1 + i))
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
+        ev[i][0].record()
+        _cabi.check(L.icl_run_resident(sess.handle, _cabi.OP_TRAIN, KEEP_IN, KEEP, 100 + i))
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(c) for a, c in ev) / steps
+    out = dict(workload="affinity512", baseline_config=wl["cfg"], unit="pairs/s", pairs_per_step=wl["B"],
+               train_resident=wl["B"] / (ms * 1e-3), train_resident_ms_per_step=ms)
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / steps
+    dt = timed(lambda: core.run_op(sess, train_op, [bt], KEEP_IN, KEEP, "first_last_mention", [wl["task"]], [""], True))
+    out.update(train_e2e=wl["B"] / dt, train_e2e_ms_per_step=1e3 * dt)
+    bt_pred = make_batch(wl, 20171201, packed="rows", dedup=True)      # what get_pred_scores_mcc builds: distinct captions once
+    dt = timed(lambda: core.run_op(sess, proba_op, [bt_pred], 1.0, 1.0, "first_last_mention", [wl["task"]], [""], False))
+    out.update(predict_e2e=wl["B"] / dt, predict_e2e_ms_per_step=1e3 * dt, predict_distinct_captions=int(len(bt_pred["seq_lengths"])))
+    sess.close()
+    return out
 
 
 # ----------------------------------------------------------------------------------------------- our arm (B200)
@@ -378,6 +434,9 @@ def main():
                                              api="same run_op call; load_batch(packed='rows'): int32 token rows into the device-resident "
                                                  "token table (icl_set_token_table) instead of the padded [S,T,300] host tensor"),
                     gpu_launches=launches, clocks=clocks_summary(clk))
+        if world == 1 and args.workload == "card2048":
+            sess.close()
+            line["mention_box_pairs_per_sec"] = affinity_pairs_per_sec(local)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = {k: v for k, v in cpu_sample(wl, min(wl["B"], 256), 3, 1).items()
                                     if k in ("value", "unit", "cores", "kind", "sample")}
