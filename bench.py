@@ -165,7 +165,8 @@ def affinity_pairs_per_sec(local, steps=10, warmup=3):
     """BASELINE.json's second metric, "mention-box pairs/sec", on configs[3] shapes (icl_affinity_lstm: B=512 mention-box pairs per
     step, 4096-d box features, H=300, pairs grouped by image): train pairs/s with the batch resident in HBM (CUDA events), train
     pairs/s end to end through run_op with host buffers, and predict pairs/s end to end through get_pred_scores_mcc's batch path
-    (keep 1.0, every distinct caption of a batch encoded once)."""
+    (keep 1.0, every distinct caption of a batch encoded once).  The e2e legs use what the drop-in CLI uses with ICL_BOX_TABLE=1:
+    token rows + box rows into the device-resident token / box tables (3 MB instead of 12 MB per step on the wire)."""
     import ctypes as C
     import torch
     from imagecaptionlearn_py_b200 import _cabi, core
@@ -176,7 +177,7 @@ def affinity_pairs_per_sec(local, steps=10, warmup=3):
     with core.variable_scope("bidirectional_lstm"):
         core.setup_bidirectional_lstm(wl["H"], wl["data_norm"], n_embedding_width=E)
     core.setup_core_architecture(wl["task"], "first_last_mention", wl["B"], wl["start"], wl["depth"], False, "relu", wl["C"], wl["F"],
-                                 box_embedding_width=bt["box_embeddings"].shape[1])
+                                 box_embedding_width=(bt["box_table"] if "box_table" in bt else bt["box_embeddings"]).shape[1])
     core.add_train_op(core.get_collection("loss")[0], LR, ADAM_EPS, CLIP)
     sess = core.Session(max_seq_len=T_PAD, device=local)
     sess.ensure()
@@ -250,7 +251,7 @@ def main():
     core.set_random_seeds()
     with core.variable_scope("bidirectional_lstm"):
         core.setup_bidirectional_lstm(wl["H"], wl["data_norm"], n_embedding_width=E)
-    box_w = bt["box_embeddings"].shape[1] if "box_embeddings" in bt else None
+    box_w = bt["box_embeddings"].shape[1] if "box_embeddings" in bt else bt["box_table"].shape[1] if "box_table" in bt else None
     core.setup_core_architecture(wl["task"], "first_last_mention", wl["B"], wl["start"], wl["depth"], False, "relu", wl["C"],
                                  wl["F"], box_embedding_width=box_w)
     core.add_train_op(core.get_collection("loss")[0], LR, ADAM_EPS, CLIP)

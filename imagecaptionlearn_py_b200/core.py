@@ -156,6 +156,7 @@ class Session(object):
         self.last_train_stats = None
         self._slot = 0
         self._table_ref = None
+        self._box_ref = None
         self._side = None
         self.joint_vars = None          # weighted_joint: dict(W, b, mW, vW, mb, vb) on the host
         self.base_seed = self.graph.seed if seed is None else seed
@@ -215,6 +216,7 @@ class Session(object):
         self.handle = h
         self._slot = 0
         self._table_ref = None
+        self._box_ref = None
         self._grad_view = None
         if state is None:
             self.initialize()
@@ -340,6 +342,14 @@ class Session(object):
             t = np.ascontiguousarray(table, dtype=np.float32)
             _cabi.check(_cabi.lib().icl_set_token_table(self.handle, _cabi.np_ptr(t), int(t.shape[0])))
             self._table_ref = table
+
+    def set_box_table(self, table):
+        """Keep the corpus' box features ([n_boxes, box_width] float32) resident on the device; affinity batches with 'box_rows'
+        then ship one int32 per mention-box pair instead of a 4096-float row."""
+        if self._box_ref is not table:
+            t = np.ascontiguousarray(table, dtype=np.float32)
+            _cabi.check(_cabi.lib().icl_set_box_table(self.handle, _cabi.np_ptr(t), int(t.shape[0]), int(t.shape[1])))
+            self._box_ref = table
 
     def set_optimizer_slot(self, slot):
         """Select the Adam state (m, v, step) used by the next updates / get_tensor(kind 2, 3) calls."""
@@ -508,7 +518,13 @@ class Session(object):
                     setattr(hb, field + "_dtype", _cabi.dtype_code(a))
             put("feats", "ij_feats" if "rel" in task else "m_feats")
             if task == "affinity":
-                put("box", "box_embeddings")
+                if "box_rows" in bt:                       # rows of the device-resident box table instead of [B, 4096] floats
+                    self.set_box_table(bt["box_table"])
+                    a = np.ascontiguousarray(bt["box_rows"], dtype=np.int32)
+                    keepalive.append(a)
+                    hb.box_rows = a.ctypes.data
+                else:
+                    put("box", "box_embeddings")
                 put("bfeats", "b_feats")
             if include_labels:
                 put("labels", "labels")

@@ -394,7 +394,8 @@ struct SlotTable {
   int col[16];         // first column in batch_input
   int width[16];
   const int* idx[16];  // kind 0: [B,3] int32 on device
-  const float* dense[16];  // kind 1: [B,width]
+  const float* dense[16];  // kind 1: [B,width], or (rowidx set) a resident table [n_rows,width]
+  const int* rowidx[16];   // kind 1, optional: [B] row of example b in the resident table (icl_set_box_table)
 };
 
 // one block per example; the LSTM's output dropout (core.py:312) is applied here, on the gathered rows.
@@ -405,7 +406,7 @@ __global__ void k_gather_concat(SlotTable st, const float* __restrict__ h_fw, co
   float* o = out + (long)b * D0;
   for (int sl = 0; sl < st.n_slots; sl++) {
     if (st.kind[sl] == 1) {
-      const float* src = st.dense[sl] + (long)b * st.width[sl];
+      const float* src = st.dense[sl] + (long)(st.rowidx[sl] ? st.rowidx[sl][b] : b) * st.width[sl];
       for (int e = threadIdx.x; e < st.width[sl]; e += blockDim.x) o[st.col[sl] + e] = maybe_round(src[e], round_ops);
     } else {
       const int* ix = st.idx[sl] + b * 3;

@@ -53,7 +53,7 @@ struct Param { std::string name; int rows, cols; int64_t off; };
 // while they are being packed; everything else is ONE copy (a dozen small cudaMemcpyAsync calls on the copy stream stalled the
 // concurrently running compute stream by ~80 us each -- measured 1.3 ms per step).
 struct HeadIn {                                             // byte offsets into the set's blob
-  size_t idx[ICL_N_INDEX] = {}, feats = 0, box = 0, bfeats = 0, labels = 0;
+  size_t idx[ICL_N_INDEX] = {}, feats = 0, box = 0, bfeats = 0, labels = 0, boxrow = 0;
 };
 struct InSet {
   char *d_blob = nullptr, *h_blob = nullptr;
@@ -115,6 +115,8 @@ struct icl_model {
   // device-resident token table (icl_set_token_table): batches then carry int32 row numbers instead of embedding rows
   float* tok_table = nullptr; int64_t tok_table_rows = 0;
   int* d_tokrow = nullptr; bool use_rows = false;
+  // device-resident box-feature table (icl_set_box_table): affinity batches then carry one int32 row per pair
+  float* box_table = nullptr; int64_t box_table_rows = 0;
   InSet in[2];
   int cur = -1;                                         // input set of the resident batch
   cudaStream_t copy = nullptr;
@@ -424,6 +426,7 @@ static void use_input_set(icl_model* m, int s) {
     h.labels = I.dev<float>(hin.labels);
     for (int i = 0; i < h.slots.n_slots; i++) {
       int id = h.slot_index_id[i];
+      h.slots.rowidx[i] = nullptr;
       if (id >= 0) h.slots.idx[i] = h.idx[id];
       else h.slots.dense[i] = id == -1 ? h.feats : id == -2 ? h.box : h.bfeats;
     }
@@ -461,7 +464,7 @@ extern "C" void icl_destroy(icl_model* m) {
   if (!m) return;
   cudaDeviceSynchronize();
   auto F = [](void* p) { if (p) cudaFree(p); };
-  F(m->P); F(m->G); F(m->Pr); F(m->tok_table);
+  F(m->P); F(m->G); F(m->Pr); F(m->tok_table); F(m->box_table);
   if (m->slots.empty()) { F(m->M); F(m->V); }
   else {                       // m->M / m->V alias the live slot
     m->slots[m->cur_slot].M = m->M; m->slots[m->cur_slot].V = m->V;
@@ -597,6 +600,7 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
       for (int i = 0; i < ICL_N_INDEX; i++) hin.idx[i] = take(B * 3 * 4);
       hin.feats = take(B * h.c.n_feats * 4); hin.box = take(B * h.c.box_width * 4); hin.bfeats = take(B * h.c.n_box_feats * 4);
       hin.labels = take(B * h.c.n_classes * 4);
+      hin.boxrow = take(B * 4);
     }
     I.o_tokrow = take((size_t)m->Ntok_cap * 4);
     I.o_tokseq = take((size_t)m->Ntok_cap * 4);              // last: only its used prefix is copied
@@ -634,6 +638,19 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   if (k1_init(m) != 0) { icl_destroy(m); *out = nullptr; return -1; }
   if (bptt_init(m) != 0) { icl_destroy(m); *out = nullptr; return -1; }
 #undef CKD
+  return 0;
+}
+
+// Device-resident box-feature table [n_rows, box_width] (fp32): every box of the corpus once (the reference re-reads and re-parses
+// the per-image feature files for every batch, nn_utils/data.py:506-524); affinity batches then reference rows (icl_head_batch.box_rows).
+extern "C" int icl_set_box_table(icl_model* m, const float* table, int64_t n_rows, int32_t width) {
+  CK(cudaStreamSynchronize(m->stream));
+  if (m->box_table) { CK(cudaFree(m->box_table)); m->box_table = nullptr; m->box_table_rows = 0; }
+  if (!table || n_rows <= 0) return 0;
+  for (auto& h : m->heads) if (h.c.box_width > 0 && h.c.box_width != width) return fail("icl_set_box_table: width %d != the head's box_width %d", width, h.c.box_width);
+  CK(dmalloc(&m->box_table, (size_t)n_rows * width));
+  CK(cudaMemcpy(m->box_table, table, (size_t)n_rows * width * 4, cudaMemcpyHostToDevice));
+  m->box_table_rows = n_rows;
   return 0;
 }
 
@@ -847,6 +864,17 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
       return 0;
     };
     CKI(up(hb.feats, hb.feats_dtype, hin.feats, (size_t)B * h.c.n_feats, "m_feats/ij_feats"));
+    if (hb.box_rows && h.c.box_width > 0) {                 // rows of the resident box table instead of [B, 4096] floats
+      if (!m->box_table) return fail("icl_upload: head %d gives box_rows but no box table was set (icl_set_box_table)", hi);
+      int* br = I.host<int>(hin.boxrow);
+      for (int r = 0; r < B; r++) {
+        if (hb.box_rows[r] < 0 || hb.box_rows[r] >= m->box_table_rows)
+          return fail("icl_upload: head %d box_rows[%d]=%d outside the box table [0,%lld)", hi, r, hb.box_rows[r], (long long)m->box_table_rows);
+        br[r] = hb.box_rows[r];
+      }
+      for (int sl = 0; sl < h.slots.n_slots; sl++)
+        if (h.slot_index_id[sl] == -2) { h.slots.dense[sl] = m->box_table; h.slots.rowidx[sl] = I.dev<int>(hin.boxrow); }
+    } else
     CKI(up(hb.box, hb.box_dtype, hin.box, (size_t)B * h.c.box_width, "box_embeddings"));
     CKI(up(hb.bfeats, hb.bfeats_dtype, hin.bfeats, (size_t)B * h.c.n_box_feats, "b_feats"));
     h.has_labels = hb.labels != nullptr;

@@ -123,7 +123,12 @@ def load_batch(ids, data_dict, task, n_classes, packed=False, dedup=False):
     feats = np.stack([data_dict["mention_features"][m] for m in m_ids]).astype(np.float32)
     out["ij_feats" if "rel" in task else "m_feats"] = feats
     if task == "affinity":
-        out["box_embeddings"] = _box_rows(b_ids, data_dict)
+        bm = _box_matrix(data_dict) if packed == "rows" else None
+        if bm is not None:                    # device-resident box table: one row number per pair
+            out["box_rows"] = np.array([bm[1][b] for b in b_ids], dtype=np.int32)
+            out["box_table"] = bm[0]
+        else:
+            out["box_embeddings"] = _box_rows(b_ids, data_dict)
         if data_dict.get("box_categories"):
             bf = np.zeros([B, data_dict["n_box_feats"]], np.float32)
             for i, b in enumerate(b_ids):
@@ -131,6 +136,21 @@ def load_batch(ids, data_dict, task, n_classes, packed=False, dedup=False):
                     bf[i] = data_dict["box_categories"][b]
             out["b_feats"] = bf
     return out
+
+
+def _box_matrix(data_dict):
+    """(matrix [n_boxes, W] float32, {box id: row}) when every box of the data set is in memory ('box_table': {id: vector},
+    e.g. loaders.load_all_boxes), else None (the per-image files are streamed per batch like the reference does)."""
+    table = data_dict.get("box_table")
+    if not table:
+        return None
+    bm = data_dict.get("_box_matrix")
+    if bm is None or bm[2] != len(table):
+        ids = list(table.keys())
+        mat = np.stack([np.asarray(table[b], dtype=np.float32) for b in ids]) if ids else np.zeros((0, data_dict["box_embedding_width"]), np.float32)
+        bm = (mat, {b: i for i, b in enumerate(ids)}, len(table))
+        data_dict["_box_matrix"] = bm
+    return bm
 
 
 def _box_rows(b_ids, data_dict):

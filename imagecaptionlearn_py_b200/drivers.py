@@ -297,6 +297,8 @@ def main_affinity(argv=None):
         dd.update(loaders.load_mentions(d + "raw/" + root + "_mentions_affinity.txt", task, d + "feats/" + root + "_affinity_neural.feats",
                                         d + "feats/" + root + "_affinity_neural_meta.json", 2))
         dd.update(loaders.load_boxes(d + "raw/" + root + "_affinity_labels.txt", d + "feats/" + data + "_boxes/" + split + "/"))
+        if os.environ.get("ICL_BOX_TABLE"):
+            loaders.load_all_boxes(dd)                    # box features resident on the device instead of re-read per batch
         return dd, root
 
     def eval_fn(sess, ed):

@@ -141,3 +141,20 @@ def load_relation_labels(filename):
             sp = line.split(" ")
             gold[(sp[0].strip(), sp[1].strip())] = sp[2].strip()
     return gold
+
+
+def load_all_boxes(data_dict):
+    """Read every per-image box feature file of `box_dir` into data_dict['box_table'] ({box id: vector}) so that the box features
+    can stay resident on the device (core.Session.set_box_table): 4096 floats per box, ~20 boxes per image -- Flickr30k-Entities is
+    ~10 GB, which the 180 GB of a B200 hold easily; the reference re-parses the text files for every batch instead
+    (nn_utils/data.py:506-524).  Opt-in (ICL_BOX_TABLE=1 in the drop-in CLIs) because it needs the same amount of host memory."""
+    import os
+    from . import data as nn_data
+    table = {}
+    imgs = sorted(set(k.split("|")[1].split(";")[0] for k in data_dict["labels"].keys()))
+    for img in imgs:
+        path = os.path.join(data_dict["box_dir"], img.replace(".jpg", ".feats"))
+        if os.path.exists(path):
+            table.update(nn_data.read_box_feats(path, data_dict["box_embedding_width"]))
+    data_dict["box_table"] = table
+    return data_dict

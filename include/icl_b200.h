@@ -71,6 +71,7 @@ typedef struct icl_head_batch {
   const void* bfeats; int32_t bfeats_dtype;     /* b_feats or NULL */
   const void* labels; int32_t labels_dtype;     /* one-hot [B,C] or NULL (include_labels=False) */
   int32_t sent_offset;                           /* added to the `sent` column (multi-head shared encoder pass) */
+  const int32_t* box_rows;                       /* or (box == NULL): [B] rows of the device-resident box table (icl_set_box_table) */
   int32_t inactive;                              /* 1: this head is not fed in this call (TF evaluates only the fetched
                                                     task's subgraph, icl_multitask_lstm.py:327-334); its outputs are NaN */
 } icl_head_batch;
@@ -102,6 +103,7 @@ void icl_destroy(icl_model* m);
 /* corpus cache: the embedding rows of every caption token, concatenated, stay resident in HBM;
    nn_utils/data.py:397-403 copies them row by row into a fresh [S,T,300] tensor per batch instead */
 int icl_set_token_table(icl_model* m, const float* table_rows_by_E, int64_t n_rows);
+int icl_set_box_table(icl_model* m, const float* table_rows_by_W, int64_t n_rows, int32_t box_width);   /* affinity box features, once */
 uint32_t icl_crc32c(const void* data, uint64_t n, uint32_t crc0);  /* host: CRC-32C of TF Saver-V2 checkpoint tensors (tf_checkpoint.py) */
 int icl_set_stream(icl_model* m, void* cuda_stream);             /* cudaStream_t of the caller (e.g. torch's current) */
 

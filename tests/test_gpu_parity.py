@@ -610,3 +610,39 @@ def test_caption_dedup_gives_identical_predictions():
     assert set(out["dedup"]) == set(out["copies"]) == set(ids)
     for k in ids:
         assert np.array_equal(out["dedup"][k], out["copies"][k]), k
+
+
+def test_resident_box_table_gives_identical_results():
+    """Affinity with the box features resident on the device (icl_set_box_table + 'box_rows'): same rows, same kernels,
+    bit-identical probabilities and gradients as with the [B, box_width] host tensor; an out-of-range row is a validated error."""
+    from imagecaptionlearn_py_b200 import _cabi, core, synth
+    from imagecaptionlearn_py_b200 import data as nn_data
+    corpus = synth.make_corpus(3, seed=23, E=12, with_boxes=True, box_width=32)
+    dd = synth.make_data_dict(corpus, "affinity", F=8)
+    ids = synth.example_ids(dd, "affinity")[:48]
+    res = {}
+    for mode in (False, "rows"):
+        bt = nn_data.load_batch(ids, dd, "affinity", 2, packed=mode)
+        assert ("box_rows" in bt) == (mode == "rows") and ("box_embeddings" in bt) == (mode is False)
+        core.reset_default_graph()
+        core.set_random_seeds()
+        with core.variable_scope("bidirectional_lstm"):
+            core.setup_bidirectional_lstm(8, False, n_embedding_width=12)
+        core.setup_core_architecture("affinity", "first_last_mention", 48, 16, 1, False, "relu", 2, 8, box_embedding_width=32)
+        core.add_train_op(core.get_collection("loss")[0], 1e-3, 1e-8, 5.0)
+        sess = core.Session(max_seq_len=dd["max_seq_len"], gemm_mode=_cabi.GEMM_SIMT_FP32)
+        sess.ensure()
+        sess.initialize()
+        sess.base_seed, sess.run_counter = 9, 0
+        r = sess.run(_cabi.OP_GRADS, [bt], 0.5, 0.5, True)[0]
+        res[mode] = (r["proba"].copy(), {n: sess.get_tensor(n, 1) for n, _, _, _ in sess.param_info()})
+        if mode == "rows":
+            bad = dict(bt)
+            bad["box_rows"] = bt["box_rows"].copy()
+            bad["box_rows"][3] = len(bt["box_table"])
+            with pytest.raises(RuntimeError, match="box_rows"):
+                sess.run(_cabi.OP_PREDICT, [bad], 1.0, 1.0, False)
+        sess.close()
+    assert np.array_equal(res["rows"][0], res[False][0])
+    for k, v in res[False][1].items():
+        assert np.array_equal(res["rows"][1][k], v), k
