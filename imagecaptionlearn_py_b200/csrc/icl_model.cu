@@ -74,6 +74,8 @@ struct Head {
   std::vector<int> slot_index_id;    // per slot: index-matrix id or -1
   float *bi = nullptr, *dbi = nullptr, *dA = nullptr, *dBuf = nullptr;
   std::vector<float*> act;           // y_k [B,w_k]
+  std::vector<float*> dzb;           // gradient w.r.t. the pre-activation of hidden layer k [B,w_k] (one buffer per layer: the weight
+                                     // gradients read it on the aux stream while the main stream already computes the next layer's)
   float *proba = nullptr, *dlogits = nullptr, *row_loss = nullptr, *row_correct = nullptr, *scalars = nullptr;
   long long* pred = nullptr;
   int* idx[ICL_N_INDEX] = {};
@@ -128,9 +130,11 @@ struct icl_model {
   int64_t seq_gid0 = 0, ex_gid0 = 0;
   std::vector<int> n_active, off;
   bool resident = false;
-  cudaStream_t stream = nullptr, aux = nullptr;
+  cudaStream_t stream = nullptr, aux = nullptr, aux2 = nullptr;      // aux2: the heads' weight gradients
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   cudaEvent_t ev_heads = nullptr;      // recorded when the heads' parameter gradients are complete (before the BPTT)
+  cudaEvent_t ev_dz[ICL_MAX_LAYERS + 2] = {};   // heads' backward: "dz of this layer is ready" (main stream -> aux stream)
+  bool heads_aux_pending = false;      // the aux stream holds weight-gradient work the main stream has not joined yet
   cudaEvent_t ev_ph[PH_N][2] = {};
   bool ph_used[PH_N] = {};
   // persistent recurrent kernels
@@ -484,13 +488,15 @@ extern "C" void icl_destroy(icl_model* m) {
   F(m->Hp16[0]); F(m->Hp16[1]); F(m->Wp16[0]); F(m->Wp16[1]); F(m->X16[0]); F(m->X16[1]); F(m->Wih16[0]); F(m->Wih16[1]);
   F(m->d_partial); F(m->d_gnorm);
   for (auto& h : m->heads) {
-    F(h.bi); F(h.dbi); F(h.dA); F(h.dBuf); for (auto a : h.act) F(a);
+    F(h.bi); F(h.dbi); F(h.dA); F(h.dBuf); for (auto a : h.act) F(a); for (auto a : h.dzb) F(a);
     F(h.proba); F(h.dlogits); F(h.row_loss); F(h.row_correct); F(h.scalars); F(h.pred);
     if (h.h_out) cudaFreeHost(h.h_out);
     if (h.h_pred) cudaFreeHost(h.h_pred);
   }
   if (m->aux) cudaStreamDestroy(m->aux);
+  if (m->aux2) cudaStreamDestroy(m->aux2);
   for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_t0, m->ev_t1, m->ev_heads}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : m->ev_dz) if (e) cudaEventDestroy(e);
   for (int i = 0; i < PH_N; i++) for (int j = 0; j < 2; j++) if (m->ev_ph[i][j]) cudaEventDestroy(m->ev_ph[i][j]);
   delete m;
 }
@@ -620,6 +626,7 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
     CKD(dmalloc(&h.bi, (size_t)B * h.D0)); CKD(dmalloc(&h.dbi, (size_t)B * std::max(h.D0g, 1)));
     CKD(dmalloc(&h.dA, (size_t)B * maxw)); CKD(dmalloc(&h.dBuf, (size_t)B * maxw));
     for (int k = 1; k <= h.c.n_hidden; k++) { float* a; CKD(dmalloc(&a, (size_t)B * h.dims[k])); h.act.push_back(a); }
+    for (int k = 1; k <= h.c.n_hidden; k++) { float* a; CKD(dmalloc(&a, (size_t)B * h.dims[k])); h.dzb.push_back(a); }
     CKD(dmalloc(&h.proba, (size_t)B * C)); CKD(dmalloc(&h.dlogits, (size_t)B * C));
     CKD(dmalloc(&h.row_loss, B)); CKD(dmalloc(&h.row_correct, B)); CKD(dmalloc(&h.scalars, 4)); CKD(dmalloc(&h.pred, B));
     CKD(cudaMallocHost((void**)&h.h_out, ((size_t)B * C + 4) * 4));
@@ -627,9 +634,11 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   }
   use_input_set(m, 0);
   CKD(cudaStreamCreateWithFlags(&m->aux, cudaStreamNonBlocking));
+  CKD(cudaStreamCreateWithFlags(&m->aux2, cudaStreamNonBlocking));
   CKD(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
   CKD(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
   CKD(cudaEventCreateWithFlags(&m->ev_heads, cudaEventDisableTiming));
+  for (auto& e : m->ev_dz) CKD(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CKD(cudaEventCreate(&m->ev_t0)); CKD(cudaEventCreate(&m->ev_t1));
   for (int i = 0; i < PH_N; i++) for (int j = 0; j < 2; j++) CKD(cudaEventCreate(&m->ev_ph[i][j]));
   if (tcgen05_gemm_init() != 0) { fail("icl_create: cannot resolve cuTensorMapEncodeTiled"); icl_destroy(m); *out = nullptr; return -1; }
@@ -695,7 +704,7 @@ extern "C" uint32_t icl_crc32c(const void* data, uint64_t n, uint32_t crc) {
 }
 
 extern "C" int icl_set_stream(icl_model* m, void* s) { m->stream = (cudaStream_t)s; return 0; }
-extern "C" int icl_sync(icl_model* m) { CK(cudaStreamSynchronize(m->stream)); CK(cudaStreamSynchronize(m->aux)); return 0; }
+extern "C" int icl_sync(icl_model* m) { CK(cudaStreamSynchronize(m->stream)); CK(cudaStreamSynchronize(m->aux)); CK(cudaStreamSynchronize(m->aux2)); return 0; }
 extern "C" int icl_param_count(icl_model* m) { return (int)m->params.size(); }
 extern "C" int icl_param_info(icl_model* m, int i, const char** name, int32_t* rows, int32_t* cols, int64_t* off) {
   if (i < 0 || i >= (int)m->params.size()) return fail("param index out of range");
@@ -1111,26 +1120,29 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
       const int64_t g0 = m->params[h.pW[0]].off, g1 = hi + 1 < m->heads.size() ? m->params[m->heads[hi + 1].pW[0]].off : m->n_params;
       CK(zero_async(m->G + g0, (size_t)(g1 - g0) * 4, st));
     }
+    // Layer by layer from the softmax down: the chain dz_k -> dz_{k-1} = (dz_k W_k^T) * act' stays on the main stream; the weight
+    // and bias gradients of layer k only need dz_k, so they run on the aux stream concurrently with the rest of the chain
+    // (joined before the weight-gradient phase of the LSTM / the update).
     const float* dz = h.dlogits;       // gradient w.r.t. the pre-activation of layer k+1 (softmax layer first)
-    float* bufs[2] = {h.dA, h.dBuf};
-    int cur = 0;
     for (int k = L; k >= 0; k--) {
       const float* in = k == 0 ? h.bi : h.act[k - 1];
       int din = h.dims[k], dout = h.dims[k + 1];
       const Param& pw = m->params[h.pW[k]];
+      CK(cudaEventRecord(m->ev_dz[k], st));
+      CK(cudaStreamWaitEvent(m->aux2, m->ev_dz[k], 0));
       // dW = in^T * dz   (contraction over the batch: both operands MN-major)
       GemmArgs gw = mk_gemm(in, din, dz, dout, m->G + pw.off, dout, din, dout, B);
-      CKI(gemm(m, st, true, true, gw, -1, 0, true));
-      CKI(colsum(m, st, dz, B, dout, dout, m->G + m->params[h.pB[k]].off));
+      CKI(gemm(m, m->aux2, true, true, gw, -1, 0, true));
+      CKI(colsum(m, m->aux2, dz, B, dout, dout, m->G + m->params[h.pB[k]].off));
+      m->heads_aux_pending = true;
       // d(in) = dz * W^T  (W [din,dout] row-major is K-major as the B operand)
       if (k > 0) {
-        GemmArgs gx = mk_gemm(dz, dout, wbase(m) + pw.off, dout, bufs[cur], din, B, din, dout);
+        GemmArgs gx = mk_gemm(dz, dout, wbase(m) + pw.off, dout, h.dzb[k - 1], din, B, din, dout);
         gx.epi.mode = EPI_DACT; gx.epi.act = h.c.activation; gx.epi.aux = h.act[k - 1]; gx.epi.ldaux = din;
         gx.epi.drop = mk_drop(seed, STREAM_HEAD + (uint32_t)hi * 8 + (k - 1), keep, m->ex_gid0);
         gx.epi.round_out = m->round_ops;
         CKI(gemm(m, st, false, false, gx));
-        dz = bufs[cur];
-        cur ^= 1;
+        dz = h.dzb[k - 1];
       } else if (h.D0g > 0) {
         GemmArgs gx = mk_gemm(dz, dout, wbase(m) + pw.off, dout, h.dbi, h.D0g, B, h.D0g, dout);
         CKI(gemm(m, st, false, false, gx));
@@ -1141,7 +1153,12 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
     }
   }
   PH_END(m, PH_HEADS_BWD);
-  CK(cudaEventRecord(m->ev_heads, st));       // the head gradients can be all-reduced while the BPTT runs (icl_wait_head_grads)
+  CK(cudaEventRecord(m->ev_heads, m->heads_aux_pending ? m->aux2 : st));   // the head gradients can be all-reduced while the BPTT runs
+  return 0;
+}
+// the heads' weight gradients (aux stream) must be complete before anything reads the gradient buffer on the main stream
+static int join_heads_aux(icl_model* m) {
+  if (m->heads_aux_pending) { CK(cudaStreamWaitEvent(m->stream, m->ev_heads, 0)); m->heads_aux_pending = false; }
   return 0;
 }
 
@@ -1299,6 +1316,7 @@ static int lstm_backward(icl_model* m) {
   }
   PH_END(m, PH_REC_BWD);
   // time-batched weight gradients: ONE split-K GEMM per direction (contraction over all tokens)
+  CKI(join_heads_aux(m));
   PH_BEGIN(m, PH_WGRAD);
   // 128x256 tiles: ceil((E+H+1)/128) x ceil(4H/256) of them; split-K so that ~one wave of 148 CTAs covers the contraction
   int tiles = ((E + H + 1 + 127) / 128) * ((4 * H + 255) / 256);
@@ -1401,6 +1419,7 @@ extern "C" int icl_run_resident(icl_model* m, int op, float keep_in, float keep,
   if (op >= ICL_OP_GRADS) {
     CKI(heads_backward(m, keep, seed));
     CKI(lstm_backward(m));
+    CKI(join_heads_aux(m));
   }
   if (op == ICL_OP_TRAIN) CKI(icl_apply_update(m));
   CK(cudaEventRecord(m->ev_t1, m->stream));
