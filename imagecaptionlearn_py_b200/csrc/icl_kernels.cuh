@@ -398,16 +398,26 @@ struct SlotTable {
   const int* rowidx[16];   // kind 1, optional: [B] row of example b in the resident table (icl_set_box_table)
 };
 
-// one block per example; the LSTM's output dropout (core.py:312) is applied here, on the gathered rows.
+// one block per (example, slot) -- every slot's index chain (index row -> length / rank / step offset -> state row) resolves
+// concurrently instead of one after the other; the LSTM's output dropout (core.py:312) is applied here, on the gathered rows.
 // batch_input is only ever a GEMM operand (layer-1 forward, layer-1 weight gradient): stored TF32-rounded.
 __global__ void k_gather_concat(SlotTable st, const float* __restrict__ h_fw, const float* __restrict__ h_bw, StepLayout L,
                                 int H, int Tcap, int D0, Drop drop, int round_ops, float* __restrict__ out) {
   int b = blockIdx.x;
   float* o = out + (long)b * D0;
-  for (int sl = 0; sl < st.n_slots; sl++) {
+  {
+    const int sl = blockIdx.y;
     if (st.kind[sl] == 1) {
       const float* src = st.dense[sl] + (long)(st.rowidx[sl] ? st.rowidx[sl][b] : b) * st.width[sl];
-      for (int e = threadIdx.x; e < st.width[sl]; e += blockDim.x) o[st.col[sl] + e] = maybe_round(src[e], round_ops);
+      if ((st.width[sl] & 3) == 0 && (st.col[sl] & 3) == 0 && (D0 & 3) == 0) {
+        for (int e = threadIdx.x * 4; e < st.width[sl]; e += blockDim.x * 4) {
+          float4 v = *reinterpret_cast<const float4*>(src + e);
+          *reinterpret_cast<float4*>(o + st.col[sl] + e) =
+              make_float4(maybe_round(v.x, round_ops), maybe_round(v.y, round_ops), maybe_round(v.z, round_ops), maybe_round(v.w, round_ops));
+        }
+      } else {
+        for (int e = threadIdx.x; e < st.width[sl]; e += blockDim.x) o[st.col[sl] + e] = maybe_round(src[e], round_ops);
+      }
     } else {
       const int* ix = st.idx[sl] + b * 3;
       int d = ix[0], s = ix[1], w = ix[2];
@@ -435,22 +445,25 @@ __global__ void k_scatter_spans(SlotTable st, const float* __restrict__ dbi, Ste
                                 float* __restrict__ dh_fw, float* __restrict__ dh_bw) {
   int b = blockIdx.x;
   const float* g = dbi + (long)b * D0;
-  for (int sl = 0; sl < st.n_slots; sl++) {
-    if (st.kind[sl] == 1) continue;
+  {                                                  // one block per (example, slot), like k_gather_concat
+    const int sl = blockIdx.y;
+    if (st.kind[sl] == 1) return;
     const int* ix = st.idx[sl] + b * 3;
     int d = ix[0], s = ix[1], w = ix[2];
-    if (w >= L.lens[s]) continue;
+    if (w >= L.lens[s]) return;
     float* dst = (d ? dh_bw : dh_fw) + token_row(L, d, s, w) * H;
     uint64_t base = (uint64_t)((drop.row_gid0 + s) * Tcap + w) * (uint64_t)H;
     for (int u = threadIdx.x * 4; u < H; u += blockDim.x * 4) {
       float mk[4] = {1.f, 1.f, 1.f, 1.f};
       if (drop.keep < 1.0f) drop4(drop.seed, STREAM_OUT_FW + d, (base + u) >> 2, drop.keep, mk);
+      float v[4];
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        float v = g[st.col[sl] + u + j];
-        if (drop.keep < 1.0f) v = v / drop.keep * mk[j];
-        if (v != 0.0f) atomicAdd(dst + u + j, v);
+        v[j] = g[st.col[sl] + u + j];
+        if (drop.keep < 1.0f) v[j] = v[j] / drop.keep * mk[j];
       }
+      if (v[0] != 0.0f || v[1] != 0.0f || v[2] != 0.0f || v[3] != 0.0f)
+        atomicAdd(reinterpret_cast<float4*>(dst + u), make_float4(v[0], v[1], v[2], v[3]));     // one 16-byte red (sm_90+)
     }
   }
 }

@@ -1066,7 +1066,7 @@ static int heads_forward(icl_model* m, float keep, uint64_t seed) {
     Head& h = m->heads[hi];
     if (!h.active) continue;
     int B = h.c.batch_size, C = h.c.n_classes, L = h.c.n_hidden;
-    k_gather_concat<<<B, 128, 0, st>>>(h.slots, m->Hx[0], m->Hx[1], mk_layout(m), H, m->T_cap, h.D0, mk_drop(seed, 0, keep, m->seq_gid0),
+    k_gather_concat<<<dim3(B, h.slots.n_slots), 96, 0, st>>>(h.slots, m->Hx[0], m->Hx[1], mk_layout(m), H, m->T_cap, h.D0, mk_drop(seed, 0, keep, m->seq_gid0),
                                       m->round_ops, h.bi);
     LAUNCHED(m);
     const float* in = h.bi;
@@ -1146,7 +1146,7 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
       } else if (h.D0g > 0) {
         GemmArgs gx = mk_gemm(dz, dout, wbase(m) + pw.off, dout, h.dbi, h.D0g, B, h.D0g, dout);
         CKI(gemm(m, st, false, false, gx));
-        k_scatter_spans<<<B, 128, 0, st>>>(h.slots, h.dbi, mk_layout(m), H, m->T_cap, h.D0g, mk_drop(seed, 0, keep, m->seq_gid0),
+        k_scatter_spans<<<dim3(B, h.slots.n_slots), 96, 0, st>>>(h.slots, h.dbi, mk_layout(m), H, m->T_cap, h.D0g, mk_drop(seed, 0, keep, m->seq_gid0),
                                           m->dHout[0], m->dHout[1]);
         LAUNCHED(m);
       }
