@@ -130,8 +130,8 @@ struct icl_model {
   int64_t seq_gid0 = 0, ex_gid0 = 0;
   std::vector<int> n_active, off;
   bool resident = false;
-  cudaStream_t stream = nullptr, aux = nullptr, aux2 = nullptr;      // aux2: the heads' weight gradients
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaStream_t stream = nullptr, aux = nullptr, aux2 = nullptr, aux3 = nullptr;      // aux2: the heads' weight gradients
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   cudaEvent_t ev_heads = nullptr;      // recorded when the heads' parameter gradients are complete (before the BPTT)
   cudaEvent_t ev_dz[ICL_MAX_LAYERS + 2] = {};   // heads' backward: "dz of this layer is ready" (main stream -> aux stream)
   bool heads_aux_pending = false;      // the aux stream holds weight-gradient work the main stream has not joined yet
@@ -455,7 +455,8 @@ static int bptt_init(icl_model* m) {
       cudaFuncSetAttribute(k_bptt_step<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BP_SMEM) != cudaSuccess)
     return fail("cudaFuncSetAttribute(k_bptt_step) failed");
   if (cudaFuncSetAttribute(k_bptt_cluster<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM) != cudaSuccess ||
-      cudaFuncSetAttribute(k_bptt_cluster<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM) != cudaSuccess)
+      cudaFuncSetAttribute(k_bptt_cluster<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(k_bptt_cluster<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM) != cudaSuccess)
     return fail("cudaFuncSetAttribute(k_bptt_cluster) failed");
   return 0;
 }
@@ -495,7 +496,8 @@ extern "C" void icl_destroy(icl_model* m) {
   }
   if (m->aux) cudaStreamDestroy(m->aux);
   if (m->aux2) cudaStreamDestroy(m->aux2);
-  for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_t0, m->ev_t1, m->ev_heads}) if (e) cudaEventDestroy(e);
+  if (m->aux3) cudaStreamDestroy(m->aux3);
+  for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_join2, m->ev_t0, m->ev_t1, m->ev_heads}) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : m->ev_dz) if (e) cudaEventDestroy(e);
   for (int i = 0; i < PH_N; i++) for (int j = 0; j < 2; j++) if (m->ev_ph[i][j]) cudaEventDestroy(m->ev_ph[i][j]);
   delete m;
@@ -635,8 +637,10 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   use_input_set(m, 0);
   CKD(cudaStreamCreateWithFlags(&m->aux, cudaStreamNonBlocking));
   CKD(cudaStreamCreateWithFlags(&m->aux2, cudaStreamNonBlocking));
+  CKD(cudaStreamCreateWithFlags(&m->aux3, cudaStreamNonBlocking));
   CKD(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
   CKD(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+  CKD(cudaEventCreateWithFlags(&m->ev_join2, cudaEventDisableTiming));
   CKD(cudaEventCreateWithFlags(&m->ev_heads, cudaEventDisableTiming));
   for (auto& e : m->ev_dz) CKD(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CKD(cudaEventCreate(&m->ev_t0)); CKD(cudaEventCreate(&m->ev_t1));
@@ -1223,14 +1227,31 @@ static int rec_backward_cluster(icl_model* m) {
   for (int d = 0; d < 2; d++) { a.Z[d] = m->Z[d]; a.Cc[d] = m->Cc[d]; a.dHout[d] = m->dHout[d]; a.dcc[d] = m->dcc[d]; }
   a.off = m->d_off; a.nact = m->d_nact; a.H = H; a.Tmax = m->Tmax; a.round_ops = m->round_ops;
   a.trace = m->rp_trace; a.trace_cta = m->rp_trace_cta;
-  // The chain of the longest sequences (T_max dependent steps) bounds the phase: 8 CTAs per tile halve every step's contraction
-  // and cell-backward share (12 vs 20 us per step), but 2 x tiles x 8 CTAs do not fit at once for large batches.  So the first
-  // n8 tiles (the longest chains) run as 8-CTA clusters and the rest as 4-CTA clusters in a second, concurrent launch, sized so
-  // that all clusters are co-resident.  Clusters are independent of each other.
+  // The dependent chain of a tile's time steps bounds the phase, and a step is the faster the more CTAs share the tile (measured
+  // 12 / 20 / 35 us per step with 8 / 4 / 2 CTAs), but everything must be co-resident on the 148 SMs to run concurrently.  Tiles
+  // are ordered by chain length (the longest sequences come first), so: the first n8 tiles get 8-CTA clusters, the last n2 tiles
+  // (a handful of steps each) 2-CTA clusters, the rest 4 -- the split that minimises the longest chain time under the SM budget.
+  // Three concurrent launches (clusters are independent of each other).
   const int tiles = (m->n_active[0] + 127) / 128;
-  int n8 = std::max(0, std::min(tiles, (m->n_sms / 2 - 4 * tiles) / 4));
-  if (const char* e = getenv("ICL_BPTT_CLUSTER_CS")) n8 = atoi(e) == 8 ? tiles : atoi(e) == 4 ? 0 : n8;
-  if (const char* e = getenv("ICL_BPTT_N8")) n8 = std::max(0, std::min(tiles, atoi(e)));
+  auto chain = [&](int t) { int k = 0; while (k < m->Tmax && m->n_active[k] > t * 128) k++; return k; };   // steps of tile t
+  int n8 = 0, n2 = 0;
+  {
+    const double t8 = 12.0, t4 = 20.0, t2 = 35.0;
+    double best = 1e30;
+    int best_ctas = 1 << 30;
+    const int budget = m->n_sms - 8;                 // a few SMs of slack: exactly 148 CTAs measured 0.41 ms, 140 CTAs 0.36 ms
+    for (int a8 = 0; a8 <= tiles; a8++)
+      for (int a2 = 0; a8 + a2 <= tiles; a2++) {
+        const int a4 = tiles - a8 - a2, ctas = 2 * (8 * a8 + 4 * a4 + 2 * a2);
+        if (ctas > budget && !(a8 == 0 && a2 == tiles)) continue;
+        const double cost = std::max({a8 ? chain(0) * t8 : 0.0, a4 ? chain(a8) * t4 : 0.0, a2 ? chain(a8 + a4) * t2 : 0.0});
+        if (cost < best - 1e-9 || (cost < best + 1e-9 && ctas < best_ctas)) { best = cost; best_ctas = ctas; n8 = a8; n2 = a2; }
+      }
+  }
+  if (const char* e = getenv("ICL_BPTT_CLUSTER_CS")) { n2 = 0; n8 = atoi(e) == 8 ? tiles : atoi(e) == 4 ? 0 : n8; }
+  if (const char* e = getenv("ICL_BPTT_N8")) { n8 = std::max(0, std::min(tiles, atoi(e))); n2 = std::min(n2, tiles - n8); }
+  if (const char* e = getenv("ICL_BPTT_N2")) n2 = std::max(0, std::min(tiles - n8, atoi(e)));
+  const int n4 = tiles - n8 - n2;
   auto launch = [&](int cs, int tile0, int ntiles, cudaStream_t s) -> int {
     a.tile0 = tile0;
     cudaLaunchConfig_t cfg = {};
@@ -1239,21 +1260,29 @@ static int rec_backward_cluster(icl_model* m) {
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cs == 8 ? cudaLaunchKernelEx(&cfg, k_bptt_cluster<8>, m->bp_maps, a) : cudaLaunchKernelEx(&cfg, k_bptt_cluster<4>, m->bp_maps, a);
+    cudaError_t e = cs == 8   ? cudaLaunchKernelEx(&cfg, k_bptt_cluster<8>, m->bp_maps, a)
+                    : cs == 4 ? cudaLaunchKernelEx(&cfg, k_bptt_cluster<4>, m->bp_maps, a)
+                              : cudaLaunchKernelEx(&cfg, k_bptt_cluster<2>, m->bp_maps, a);
     if (e != cudaSuccess) return fail("k_bptt_cluster<%d> launch failed: %s", cs, cudaGetErrorString(e));
     m->launches++;
     return 0;
   };
-  const bool two = n8 > 0 && n8 < tiles;
-  if (two) {
-    CK(cudaEventRecord(m->ev_fork, st));
-    CK(cudaStreamWaitEvent(m->aux, m->ev_fork, 0));
-    CKI(launch(4, n8, tiles - n8, m->aux));
-    CK(cudaEventRecord(m->ev_join, m->aux));
+  // the group with the longest chains stays on the main stream; the others fork to the side streams and join
+  struct Grp { int cs, t0, n; } grp[3] = {{8, 0, n8}, {4, n8, n4}, {2, n8 + n4, n2}};
+  cudaStream_t side[2] = {m->aux, m->aux3};
+  cudaEvent_t join[2] = {m->ev_join, m->ev_join2};
+  int used = 0, first = -1;
+  for (int i = 0; i < 3; i++) if (grp[i].n > 0 && first < 0) first = i;
+  CK(cudaEventRecord(m->ev_fork, st));
+  for (int i = 0; i < 3; i++) {
+    if (grp[i].n == 0 || i == first) continue;
+    CK(cudaStreamWaitEvent(side[used], m->ev_fork, 0));
+    CKI(launch(grp[i].cs, grp[i].t0, grp[i].n, side[used]));
+    CK(cudaEventRecord(join[used], side[used]));
+    used++;
   }
-  if (n8 > 0) CKI(launch(8, 0, n8, st));
-  else CKI(launch(4, 0, tiles, st));
-  if (two) CK(cudaStreamWaitEvent(st, m->ev_join, 0));
+  CKI(launch(grp[first].cs, grp[first].t0, grp[first].n, st));
+  for (int i = 0; i < used; i++) CK(cudaStreamWaitEvent(st, join[i], 0));
   return 0;
 }
 

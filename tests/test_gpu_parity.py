@@ -335,8 +335,14 @@ def test_backward_recurrence_variants_agree(monkeypatch):
                 "fused4": dict(ICL_BPTT_FUSED="1", ICL_BPTT_MODE="step", ICL_BPTT_CS="4"),
                 "fused2": dict(ICL_BPTT_FUSED="1", ICL_BPTT_MODE="step", ICL_BPTT_CS="2"),
                 "fused1": dict(ICL_BPTT_FUSED="1", ICL_BPTT_MODE="step", ICL_BPTT_CS="1"),
-                "cluster": dict(ICL_BPTT_FUSED="1", ICL_BPTT_MODE="cluster")}
+                "cluster": dict(ICL_BPTT_FUSED="1", ICL_BPTT_MODE="cluster"),
+                # the cluster kernel's three sizes (S = 160 is two row tiles): all 4-CTA, all 2-CTA, one 8-CTA + one 2-CTA tile
+                "cluster4": dict(ICL_BPTT_FUSED="1", ICL_BPTT_MODE="cluster", ICL_BPTT_N8="0", ICL_BPTT_N2="0"),
+                "cluster2": dict(ICL_BPTT_FUSED="1", ICL_BPTT_MODE="cluster", ICL_BPTT_N8="0", ICL_BPTT_N2="2"),
+                "cluster8+2": dict(ICL_BPTT_FUSED="1", ICL_BPTT_MODE="cluster", ICL_BPTT_N8="1", ICL_BPTT_N2="1")}
     for name, env in variants.items():
+        for k in ("ICL_BPTT_N8", "ICL_BPTT_N2"):
+            monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         core, sess = make_session(p, "tf32")
