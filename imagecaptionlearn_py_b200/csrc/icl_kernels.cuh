@@ -605,15 +605,23 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
     if (pr) reinterpret_cast<float4*>(pr)[i] = make_float4(r[0], r[1], r[2], r[3]);
   }
 }
-// W_ih (rows [0,E) of the TF kernel [E+H, 4H]) as fp16, transposed to K-major [4H][Kp] for the fp16 input-projection GEMM
+// W_ih (rows [0,E) of the TF kernel [E+H, 4H]) as fp16, transposed to K-major [4H][Kp] for the fp16 input-projection GEMM.
+// 32x32 shared-memory tile transpose: reads coalesced along the 4H columns, writes coalesced along k.  grid (4H/32, Kp/32, 2 dirs),
+// block (32, 8).  Columns k >= E are written as zeros.
 __global__ void k_pack_wih16(const float* __restrict__ K0, const float* __restrict__ K1, __half* __restrict__ out0,
-                             __half* __restrict__ out1, int E, int N4H, int Kp) {     // blockIdx.y = direction
-  const float* K = blockIdx.y ? K1 : K0;
-  __half* out = blockIdx.y ? out1 : out0;
-  long total = (long)N4H * Kp;
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    int k = (int)(idx % Kp), n = (int)(idx / Kp);
-    out[idx] = __float2half_rn(k < E ? K[(long)k * N4H + n] : 0.0f);
+                             __half* __restrict__ out1, int E, int N4H, int Kp) {
+  __shared__ float tile[32][33];
+  const float* K = blockIdx.z ? K1 : K0;
+  __half* out = blockIdx.z ? out1 : out0;
+  const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int k = k0 + r, n = n0 + threadIdx.x;
+    tile[r][threadIdx.x] = (k < E && n < N4H) ? K[(long)k * N4H + n] : 0.0f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int n = n0 + r, k = k0 + threadIdx.x;
+    if (n < N4H && k < Kp) out[(long)n * Kp + k] = __float2half_rn(tile[threadIdx.x][r]);
   }
 }
 __global__ void k_round_copy(const float* __restrict__ src, float* __restrict__ dst, long n) {

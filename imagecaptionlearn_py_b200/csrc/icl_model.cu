@@ -951,7 +951,9 @@ static int rec_forward_fp16(icl_model* m, int training) {
   if (m->wp_dirty) {
     const float* W0 = m->P + m->params[m->pK[0]].off + (size_t)E * 4 * H;
     const float* W1 = m->P + m->params[m->pK[1]].off + (size_t)E * 4 * H;
-    k_pack_whh_fwd16<<<dim3(74, 2), 256, 0, st>>>(W0, W1, m->Wp16[0], m->Wp16[1], H, U, m->rf_UP, m->rp_nsl, m->rf_KP); LAUNCHED(m);
+    k_pack_whh_fwd16<<<dim3((4 * H + 31) / 32, (H + 31) / 32, 2), dim3(32, 8), 0, st>>>(W0, W1, m->Wp16[0], m->Wp16[1], H, U, m->rf_UP, m->rp_nsl,
+                                                                                      m->rf_KP);
+    LAUNCHED(m);
     m->wp_dirty = false;
   }
   CK(zero_async(m->rp_flags, (size_t)2 * m->rp_max_tiles * 4, st));
@@ -1013,8 +1015,8 @@ static int lstm_forward(icl_model* m, float keep_in, uint64_t seed, int training
   // K1: time-batched input projection  Z = Xd * W_ih + b   (W_ih = kernel rows [0,E)), both directions
   PH_BEGIN(m, PH_PROJ);
   if (m->k1_f16 && m->wih_dirty) {
-    k_pack_wih16<<<dim3(74, 2), 256, 0, st>>>(m->P + m->params[m->pK[0]].off, m->P + m->params[m->pK[1]].off, m->Wih16[0], m->Wih16[1], E,
-                                             4 * H, m->k1_Kp);
+    k_pack_wih16<<<dim3((4 * H + 31) / 32, m->k1_Kp / 32, 2), dim3(32, 8), 0, st>>>(m->P + m->params[m->pK[0]].off, m->P + m->params[m->pK[1]].off,
+                                                                                   m->Wih16[0], m->Wih16[1], E, 4 * H, m->k1_Kp);
     LAUNCHED(m);
     m->wih_dirty = false;
   }

@@ -48,20 +48,27 @@ struct RecFwd16Args {
   long long* trace; int trace_cta;
 };
 
-// Packed fp16 W_hh: row (j*4U + n), n = c*16 + gate*4 + i <-> unit j*U + 4c + i (as k_pack_whh_fwd); column k' = (k / U) * UP + k % U
+// Packed fp16 W_hh: row (j*4U + n), n = c*16 + gate*4 + i <-> unit j*U + 4c + i (as k_pack_whh_fwd); column k' = (k / U) * UP + k % U.
+// 32x32 tile transpose: reads coalesced along the 4H gate columns of W_hh [H, 4H], writes coalesced along k'.  The pad columns
+// (k' % UP >= U, k' >= nsl*UP) are never written: the buffer is zeroed once at allocation.  grid (4H/32, H/32, 2 dirs), block (32, 8).
 __global__ void k_pack_whh_fwd16(const float* __restrict__ Whh0, const float* __restrict__ Whh1, __half* __restrict__ Wp0,
-                                 __half* __restrict__ Wp1, int H, int U, int UP, int nsl, int Kp) {     // blockIdx.y = direction
-  const float* Whh = blockIdx.y ? Whh1 : Whh0;
-  __half* Wp = blockIdx.y ? Wp1 : Wp0;
-  long total = (long)nsl * 4 * U * Kp;
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    int kp = (int)(idx % Kp), row = (int)(idx / Kp);
-    int j = row / (4 * U), n = row % (4 * U);
-    int c = n / 16, gate = (n % 16) / 4, i = n % 4;
-    int u = j * U + c * 4 + i;
-    int ks = kp / UP, ku = kp % UP, k = ks * U + ku;
-    float v = (ku < U && k < H && u < H) ? Whh[(long)k * 4 * H + gate * H + u] : 0.0f;
-    Wp[idx] = __float2half_rn(v);
+                                 __half* __restrict__ Wp1, int H, int U, int UP, int nsl, int Kp) {
+  __shared__ float tile[32][33];
+  const float* Whh = blockIdx.z ? Whh1 : Whh0;
+  __half* Wp = blockIdx.z ? Wp1 : Wp0;
+  const int col0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int k = k0 + r, col = col0 + threadIdx.x;
+    tile[r][threadIdx.x] = (k < H && col < 4 * H) ? Whh[(long)k * 4 * H + col] : 0.0f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int col = col0 + r, k = k0 + threadIdx.x;
+    if (col < 4 * H && k < H) {
+      const int gate = col / H, u = col % H, j = u / U, uu = u % U;
+      const int row = j * 4 * U + (uu / 4) * 16 + gate * 4 + (uu % 4);
+      Wp[(long)row * Kp + (k / U) * UP + k % U] = __float2half_rn(tile[threadIdx.x][r]);
+    }
   }
 }
 
