@@ -199,6 +199,7 @@ struct HostPool {
   HostPool() {
     unsigned share = std::thread::hardware_concurrency();            // one process per GPU: split the host cores between the ranks
     if (const char* e = getenv("LOCAL_WORLD_SIZE")) share /= (unsigned)std::max(1, atoi(e));
+    if (share > 2) share -= 1;                                       // leave a core per rank to the thread that drives the GPU
     int n = (int)std::max(1u, std::min(4u, share)) - 1;
     if (const char* e = getenv("ICL_HOST_THREADS")) n = std::max(0, atoi(e) - 1);
     for (int i = 0; i < n; i++) th.emplace_back([this] { worker(); });
