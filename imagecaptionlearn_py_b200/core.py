@@ -209,8 +209,33 @@ class Session(object):
         cfg.device, cfg.gemm_mode = self.device, self.gemm_mode
         return cfg
 
+    @staticmethod
+    def _bind_to_gpu_numa_node(device):
+        """One process per GPU on a multi-socket host: run this rank (and allocate its pinned staging buffers, first touch) on the
+        NUMA node its GPU hangs off, so the host packing and the H2D DMA of the ranks do not all cross one socket's memory
+        controllers.  Silently does nothing when the topology is not visible (containers) or ICL_NO_NUMA_BIND is set."""
+        if os.environ.get("ICL_NO_NUMA_BIND") or int(os.environ.get("LOCAL_WORLD_SIZE", "1")) < 2:
+            return
+        try:
+            import torch
+            p = torch.cuda.get_device_properties(device)
+            bdf = "%04x:%02x:%02x.0" % (getattr(p, "pci_domain_id", 0), p.pci_bus_id, p.pci_device_id)
+            node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+            if node < 0:
+                return
+            cpus = set()
+            for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+        except Exception:
+            pass
+
     def _create(self, state=None):
         cfg = self._config()
+        self._bind_to_gpu_numa_node(cfg.device)
         h = C.c_void_p()
         _cabi.check(_cabi.lib().icl_create(C.byref(cfg), C.byref(h)))
         self.handle = h
