@@ -109,8 +109,9 @@ def oracle_train_step(params, cfg, bt, state, keep_in, keep, rng):
     return float(f["loss"])
 
 
-def cpu_sample(wl, sample_B, steps, warmup):
-    """Time the NumPy oracle (port of the reference TF graph) on the first `sample_B` examples of the workload."""
+def cpu_sample(wl, sample_B, steps, warmup, target_s=None):
+    """Time the NumPy oracle (port of the reference TF graph) on the first `sample_B` examples of the workload.  With `target_s` the
+    number of timed steps is chosen from the last warm-up step so that the sample is about that many seconds of CPU work."""
     from oracle import icl_oracle as O
     from imagecaptionlearn_py_b200 import core
     small = dict(wl, B=sample_B)
@@ -127,8 +128,13 @@ def cpu_sample(wl, sample_B, steps, warmup):
     rng = np.random.default_rng(7)
     params = O.init_params(rng, cfg, E, np.float32)
     state = {}
+    t1 = 0.0
     for _ in range(warmup):
+        t0 = time.perf_counter()
         oracle_train_step(params, cfg, bt, state, KEEP_IN, KEEP, rng)
+        t1 = time.perf_counter() - t0
+    if target_s and t1 > 0:
+        steps = int(max(steps, min(60, round(target_s / t1))))
     t0 = time.perf_counter()
     for _ in range(steps):
         oracle_train_step(params, cfg, bt, state, KEEP_IN, KEEP, rng)
@@ -416,6 +422,15 @@ def main():
                     peak_source=("MEASURED_PEAKS.json: hbm_gbs; bf16_tflops_sustained / 2 for kind::tf32" if peaks
                                  else "fallback 6650 GB/s, 1400/2 TFLOP/s"),
                     note="time = CUDA events around the kernel group on its launch stream (icl_phase_ms), averaged over the timed steps")
+        # every kernel group against both roofs (same algorithmic work / CUDA-event time as `roofline` above)
+        tpeak = dict(proj_gemm=bf16_peak, rec_fwd=bf16_peak, rec_bwd=tf32_peak, wgrad=tf32_peak)    # kind::f16 / kind::tf32 operands
+        by_phase = {}
+        for k, w in work.items():
+            ms_k = float(ph_ms[_cabi.PHASES.index(k)])
+            if ms_k > 0:
+                by_phase[k] = dict(kernel=w[2], ms=ms_k, hbm_frac=w[1] / (ms_k * 1e-3) / 1e9 / hbm_peak,
+                                   tensor_frac=w[0] / (ms_k * 1e-3) / 1e12 / tpeak[k], tensor_peak_tflops=tpeak[k],
+                                   bound="hbm" if w[1] / (hbm_peak * 1e9) >= w[0] / (tpeak[k] * 1e12) else "tensor")
         step_flops = flops_per_token(H) * n_tok
         line = dict(metric="bilstm_train_captions_per_sec", value=value, unit="captions/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -427,7 +442,7 @@ def main():
                                 tokens_per_sec=world * n_tok / (ms_per_step * 1e-3),
                                 bilstm_tflops=step_flops / (ms_per_step * 1e-3) / 1e12,
                                 wall_ms_per_step_incl_flush=1e3 * wall / args.steps),
-                    phases_ms={n: float(v) for n, v in zip(_cabi.PHASES, ph_ms)}, roofline=roof,
+                    phases_ms={n: float(v) for n, v in zip(_cabi.PHASES, ph_ms)}, roofline=roof, roofline_by_phase=by_phase,
                     e2e=dict(value=world * n_seqs * e2e_steps / e2e_s, unit="captions/s", h2d_bytes_per_step=h2d.value,
                              d2h_bytes_per_step=d2h.value, ms_per_step=1e3 * e2e_s / e2e_steps, steps=e2e_steps,
                              api="core.run_op(sess, train_op, [batch_tensors], ...) with host float32 NumPy buffers; pipelined: the batch is "
@@ -441,8 +456,8 @@ def main():
         if world == 1 and args.workload == "card2048":
             sess.close()
             line["mention_box_pairs_per_sec"] = affinity_pairs_per_sec(local)
-        if not args.no_cpu_baseline:
-            line["cpu_baseline"] = {k: v for k, v in cpu_sample(wl, min(wl["B"], 256), 3, 1).items()
+        if world == 1 and not args.no_cpu_baseline:        # rank 0 at N=1 only: the other ranks would idle behind it
+            line["cpu_baseline"] = {k: v for k, v in cpu_sample(wl, min(wl["B"], 512), 3, 2, target_s=12.0).items()
                                     if k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
     sess.close()

@@ -20,6 +20,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <xmmintrin.h>
 #include <vector>
 
 using namespace icl;
@@ -177,8 +178,23 @@ static double read_num(const void* p, int dtype, size_t i) {
     default: return (double)((const int64_t*)p)[i];
   }
 }
+// Streaming variant of the fp32 row copy (ICL_PACK_NT=1): whole 64-byte lines of the pinned destination are written with
+// non-temporal stores (no read-for-ownership of a buffer the CPU never reads back); the caller fences before the DMA is queued.
+static const bool g_pack_nt = [] { const char* e = getenv("ICL_PACK_NT"); return e && atoi(e) != 0; }();
+static void copy_f32_stream(float* dst, const float* src, size_t n) {
+  size_t i = 0;
+  while (i < n && ((uintptr_t)(dst + i) & 63)) { dst[i] = src[i]; i++; }
+  for (; i + 16 <= n; i += 16) {
+    __m128 a = _mm_loadu_ps(src + i), b = _mm_loadu_ps(src + i + 4), c = _mm_loadu_ps(src + i + 8), d = _mm_loadu_ps(src + i + 12);
+    _mm_stream_ps(dst + i, a); _mm_stream_ps(dst + i + 4, b); _mm_stream_ps(dst + i + 8, c); _mm_stream_ps(dst + i + 12, d);
+  }
+  for (; i < n; i++) dst[i] = src[i];
+}
 static void to_f32(float* dst, const void* src, int dtype, size_t n) {
-  if (dtype == ICL_F32) { memcpy(dst, src, n * sizeof(float)); return; }
+  if (dtype == ICL_F32) {
+    if (g_pack_nt && n >= 64) copy_f32_stream(dst, (const float*)src, n); else memcpy(dst, src, n * sizeof(float));
+    return;
+  }
   if (dtype == ICL_F64) { const double* s = (const double*)src; for (size_t i = 0; i < n; i++) dst[i] = (float)s[i]; return; }
   for (size_t i = 0; i < n; i++) dst[i] = (float)read_num(src, dtype, i);
 }
@@ -844,6 +860,7 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
           to_f32(h_x + (size_t)tokstart[s] * E, src, b->sent_dtype, (size_t)lens[s] * E);
           for (int t = 0; t < lens[s]; t++) tokseq[tokstart[s] + t] = s;
         }
+        if (g_pack_nt) _mm_sfence();
       });
       const long t0 = tokstart[s0], t1 = (long)tokstart[s1 - 1] + lens[s1 - 1];
       if (t1 > t0) H2D(m->xraw + t0 * E, h_x + t0 * E, (size_t)(t1 - t0) * E * 4, st);
