@@ -20,7 +20,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
-#include <xmmintrin.h>
+#include <emmintrin.h>
 #include <vector>
 
 using namespace icl;
@@ -178,9 +178,11 @@ static double read_num(const void* p, int dtype, size_t i) {
     default: return (double)((const int64_t*)p)[i];
   }
 }
-// Streaming variant of the fp32 row copy (ICL_PACK_NT=1): whole 64-byte lines of the pinned destination are written with
-// non-temporal stores (no read-for-ownership of a buffer the CPU never reads back); the caller fences before the DMA is queued.
-static const bool g_pack_nt = [] { const char* e = getenv("ICL_PACK_NT"); return e && atoi(e) != 0; }();
+// Streaming row copies into the pinned input mirror: whole 64-byte lines of the destination are written with non-temporal stores
+// (no read-for-ownership of a buffer the CPU never reads back, no cache pollution next to the thread that drives the GPU); the
+// worker fences before the DMA is queued.  card2048 end to end: 1.80 -> 1.575 ms per step (profiles/r1i_pack_ab.txt).
+// ICL_PACK_NT=0 restores memcpy.
+static const bool g_pack_nt = [] { const char* e = getenv("ICL_PACK_NT"); return !e || atoi(e) != 0; }();
 static void copy_f32_stream(float* dst, const float* src, size_t n) {
   size_t i = 0;
   while (i < n && ((uintptr_t)(dst + i) & 63)) { dst[i] = src[i]; i++; }
@@ -190,12 +192,25 @@ static void copy_f32_stream(float* dst, const float* src, size_t n) {
   }
   for (; i < n; i++) dst[i] = src[i];
 }
+// float64 -> float32 (the reference feeds np.zeros() float64 arrays, nn_utils/data.py:375): cvtpd2ps rounds to nearest even like the cast
+static void cvt_f64_stream(float* dst, const double* src, size_t n) {
+  size_t i = 0;
+  while (i < n && ((uintptr_t)(dst + i) & 63)) { dst[i] = (float)src[i]; i++; }
+  for (; i + 16 <= n; i += 16)
+    for (int k = 0; k < 16; k += 4)
+      _mm_stream_ps(dst + i + k, _mm_movelh_ps(_mm_cvtpd_ps(_mm_loadu_pd(src + i + k)), _mm_cvtpd_ps(_mm_loadu_pd(src + i + k + 2))));
+  for (; i < n; i++) dst[i] = (float)src[i];
+}
 static void to_f32(float* dst, const void* src, int dtype, size_t n) {
   if (dtype == ICL_F32) {
     if (g_pack_nt && n >= 64) copy_f32_stream(dst, (const float*)src, n); else memcpy(dst, src, n * sizeof(float));
     return;
   }
-  if (dtype == ICL_F64) { const double* s = (const double*)src; for (size_t i = 0; i < n; i++) dst[i] = (float)s[i]; return; }
+  if (dtype == ICL_F64) {
+    const double* s = (const double*)src;
+    if (g_pack_nt && n >= 64) cvt_f64_stream(dst, s, n); else for (size_t i = 0; i < n; i++) dst[i] = (float)s[i];
+    return;
+  }
   for (size_t i = 0; i < n; i++) dst[i] = (float)read_num(src, dtype, i);
 }
 
@@ -892,6 +907,7 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
       if (n == 0) return 0;
       if (!src) return fail("icl_upload: head %d is missing %s", hi, what);
       to_f32(I.host<float>(off), src, dt, n);
+      if (g_pack_nt) _mm_sfence();
       return 0;
     };
     CKI(up(hb.feats, hb.feats_dtype, hin.feats, (size_t)B * h.c.n_feats, "m_feats/ij_feats"));

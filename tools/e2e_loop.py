@@ -6,6 +6,8 @@ import bench, torch
 from imagecaptionlearn_py_b200 import core
 wl = bench.WORKLOADS["card2048"]
 bt = bench.make_batch(wl, 20171201)
+if os.environ.get("E2E_F64"):                      # what the reference feeds: np.zeros() float64 sentence tensors
+    bt["sentences"] = bt["sentences"].astype("float64")
 core.reset_default_graph(); core.set_random_seeds()
 with core.variable_scope("bidirectional_lstm"):
     core.setup_bidirectional_lstm(wl["H"], wl["data_norm"], n_embedding_width=300)
@@ -21,5 +23,5 @@ for rep in range(4):
     for _ in range(20):
         core.run_op(sess, op, [bt], 0.5, 0.5, "first_last_mention", [wl["task"]], [""], True)
     torch.cuda.synchronize(); res.append(1e3 * (time.perf_counter() - t0) / 20)
-print("ICL_PACK_NT=%s ICL_HOST_THREADS=%s: %s ms/step" % (os.environ.get("ICL_PACK_NT", "-"), os.environ.get("ICL_HOST_THREADS", "-"),
+print("ICL_PACK_NT=%s ICL_HOST_THREADS=%s %s: %s ms/step" % (os.environ.get("ICL_PACK_NT", "-"), os.environ.get("ICL_HOST_THREADS", "-"), bt["sentences"].dtype,
                                                         " ".join("%.3f" % r for r in res)))
