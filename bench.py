@@ -447,7 +447,8 @@ def main():
                              d2h_bytes_per_step=d2h.value, ms_per_step=1e3 * e2e_s / e2e_steps, steps=e2e_steps,
                              api="core.run_op(sess, train_op, [batch_tensors], ...) with host float32 NumPy buffers; pipelined: the batch is "
                                  "packed into pinned memory and copied on a copy stream into the idle input set while the previous "
-                                 "step computes, loss/accuracy of the previous step are read back (D2H) every step"),
+                                 "step computes, loss/accuracy of the previous step are read back (D2H) every step; the packing threads round the "
+                                 "rows to fp16 (what the device's tensor-core operands keep anyway), so the copy is 2 bytes per element"),
                     e2e_resident_corpus=dict(value=world * n_seqs * e2e_steps / rows_s, unit="captions/s", ms_per_step=1e3 * rows_s / e2e_steps,
                                              h2d_bytes_per_step=h2d_rows.value, d2h_bytes_per_step=d2h.value,
                                              api="same run_op call; load_batch(packed='rows'): int32 token rows into the device-resident "

@@ -247,17 +247,19 @@ __global__ void k_prep_x(const float* __restrict__ xraw, const int* __restrict__
                          StepLayout L, int ntok, int E, int Tcap, int data_norm, float keep_in, uint64_t seed,
                          int64_t seq_gid0, int round_ops, float* __restrict__ xfw, float* __restrict__ xbw, int ldx, int ones_col,
                          const int* __restrict__ tok_row, const float* __restrict__ table, __half* __restrict__ x16fw,
-                         __half* __restrict__ x16bw, int ld16) {
+                         __half* __restrict__ x16bw, int ld16, int raw_half) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= ntok) return;
   int s = tok_seq[warp];
   int t = warp - tokstart[s];
   // the token's embedding row: from this batch's uploaded rows, or gathered from the device-resident token table
+  // raw_half: the uploaded rows crossed PCIe as fp16 (icl_upload's half-width wire format; never together with the token table)
   const float* src = tok_row ? table + (long)tok_row[warp] * E : xraw + (long)warp * E;
+  const __half* src16 = reinterpret_cast<const __half*>(xraw) + (long)warp * E;
   float scale = 1.0f;
   if (data_norm) {
     float ss = 0.0f;
-    for (int e = lane; e < E; e += 32) { float v = src[e]; ss += v * v; }
+    for (int e = lane; e < E; e += 32) { float v = raw_half ? __half2float(src16[e]) : src[e]; ss += v * v; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     scale = rsqrtf(fmaxf(ss, 1e-12f));
@@ -271,7 +273,12 @@ __global__ void k_prep_x(const float* __restrict__ xraw, const int* __restrict__
       drop4(seed, STREAM_IN_FW, (base + e4) >> 2, keep_in, mf);
       drop4(seed, STREAM_IN_BW, (base + e4) >> 2, keep_in, mb);
     }
-    float4 x = *reinterpret_cast<const float4*>(src + e4);
+    float4 x;
+    if (raw_half) {
+      const uint2 u = *reinterpret_cast<const uint2*>(src16 + e4);
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+      x = make_float4(a.x, a.y, b.x, b.y);
+    } else x = *reinterpret_cast<const float4*>(src + e4);
     float xv[4] = {x.x * scale, x.y * scale, x.z * scale, x.w * scale}, vf[4], vb[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {

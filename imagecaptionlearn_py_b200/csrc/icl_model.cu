@@ -20,7 +20,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
-#include <emmintrin.h>
+#include <immintrin.h>
 #include <vector>
 
 using namespace icl;
@@ -112,6 +112,7 @@ struct icl_model {
   // gradient, which follows the kernel in the flat gradient buffer); xd / Hp are views with row pitch ldx
   float *XH[2] = {};
   int ldx = 0;
+  bool x_half = false;               // the current input set's sentence rows are fp16 (half-width wire format)
   float *xraw = nullptr, *xd[2] = {}, *Z[2] = {}, *Hx[2] = {}, *Hp[2] = {}, *Cc[2] = {}, *dHout[2] = {}, *dhrec[2] = {}, *dcc[2] = {},
         *R[2] = {};
   int *d_off = nullptr, *d_nact = nullptr, *d_rank = nullptr, *d_lens = nullptr, *d_tokseq = nullptr, *d_tokstart = nullptr;
@@ -200,6 +201,33 @@ static void cvt_f64_stream(float* dst, const double* src, size_t n) {
     for (int k = 0; k < 16; k += 4)
       _mm_stream_ps(dst + i + k, _mm_movelh_ps(_mm_cvtpd_ps(_mm_loadu_pd(src + i + k)), _mm_cvtpd_ps(_mm_loadu_pd(src + i + k + 2))));
   for (; i < n; i++) dst[i] = (float)src[i];
+}
+// Half-width wire format of the sentence rows (ICL_WIRE_FP16, default on where it applies: see icl_upload): the rows are rounded to
+// fp16 (round to nearest even, F16C) while they are packed, so the pinned mirror and the H2D copy carry 2 bytes per element.  The
+// device rounds the prepared inputs to 10 mantissa bits anyway (fp16 operand of the projection GEMM, TF32 operand of the weight
+// gradient), so this moves that rounding in front of the input scaling instead of behind it.
+__attribute__((target("avx,f16c"))) static void cvt_f32_h16_stream(uint16_t* dst, const float* src, size_t n) {
+  size_t i = 0;
+  while (i < n && ((uintptr_t)(dst + i) & 63)) { dst[i] = _cvtss_sh(src[i], _MM_FROUND_TO_NEAREST_INT); i++; }
+  for (; i + 32 <= n; i += 32)
+    for (int k = 0; k < 32; k += 8)
+      _mm_stream_si128((__m128i*)(dst + i + k), _mm256_cvtps_ph(_mm256_loadu_ps(src + i + k), _MM_FROUND_TO_NEAREST_INT));
+  for (; i < n; i++) dst[i] = _cvtss_sh(src[i], _MM_FROUND_TO_NEAREST_INT);
+}
+__attribute__((target("avx,f16c"))) static void cvt_f64_h16_stream(uint16_t* dst, const double* src, size_t n) {
+  size_t i = 0;
+  while (i < n && ((uintptr_t)(dst + i) & 63)) { dst[i] = _cvtss_sh((float)src[i], _MM_FROUND_TO_NEAREST_INT); i++; }
+  for (; i + 32 <= n; i += 32)
+    for (int k = 0; k < 32; k += 8) {
+      const __m256 f = _mm256_set_m128(_mm256_cvtpd_ps(_mm256_loadu_pd(src + i + k + 4)), _mm256_cvtpd_ps(_mm256_loadu_pd(src + i + k)));
+      _mm_stream_si128((__m128i*)(dst + i + k), _mm256_cvtps_ph(f, _MM_FROUND_TO_NEAREST_INT));
+    }
+  for (; i < n; i++) dst[i] = _cvtss_sh((float)src[i], _MM_FROUND_TO_NEAREST_INT);
+}
+static bool wire16_enabled() {            // read per upload, so a test can switch it
+  static const bool cpu_ok = __builtin_cpu_supports("avx") && __builtin_cpu_supports("f16c");
+  const char* e = getenv("ICL_WIRE_FP16");
+  return cpu_ok && (!e || atoi(e) != 0);
 }
 static void to_f32(float* dst, const void* src, int dtype, size_t n) {
   if (dtype == ICL_F32) {
@@ -851,6 +879,10 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
   cudaStream_t st = m->copy;
   CK(cudaEventRecord(I.ev_c0, st));
   m->use_rows = by_rows;
+  // half-width wire (see cvt_f32_h16_stream): only where the device would round these rows to 10 mantissa bits next anyway (product
+  // mode with the fp16 projection operands) and no l2-normalisation sits in between (its sum of squares keeps the fp32 inputs)
+  const bool wire16 = !by_rows && wire16_enabled() && m->round_ops && m->k1_f16 && !m->cfg.data_norm;
+  m->x_half = wire16;
   if (by_rows) {                      // packed caption-major row numbers into the resident token table: 4 bytes per token
     int* tokrow = I.host<int>(I.o_tokrow);
     for (int s = 0; s < S; s++)
@@ -872,13 +904,20 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
       host_pool().run(items, [&, s0, s1](int it) {
         for (int s = s0 + it * per; s < std::min(s1, s0 + (it + 1) * per); s++) {
           const char* src = (const char*)b->sentences + (b->sent_packed ? (size_t)tokstart[s] * E : (size_t)s * T * E) * esz;
-          to_f32(h_x + (size_t)tokstart[s] * E, src, b->sent_dtype, (size_t)lens[s] * E);
+          if (wire16) {
+            uint16_t* d16 = reinterpret_cast<uint16_t*>(h_x) + (size_t)tokstart[s] * E;
+            if (b->sent_dtype == ICL_F32) cvt_f32_h16_stream(d16, (const float*)src, (size_t)lens[s] * E);
+            else cvt_f64_h16_stream(d16, (const double*)src, (size_t)lens[s] * E);
+          } else to_f32(h_x + (size_t)tokstart[s] * E, src, b->sent_dtype, (size_t)lens[s] * E);
           for (int t = 0; t < lens[s]; t++) tokseq[tokstart[s] + t] = s;
         }
-        if (g_pack_nt) _mm_sfence();
+        if (g_pack_nt || wire16) _mm_sfence();
       });
       const long t0 = tokstart[s0], t1 = (long)tokstart[s1 - 1] + lens[s1 - 1];
-      if (t1 > t0) H2D(m->xraw + t0 * E, h_x + t0 * E, (size_t)(t1 - t0) * E * 4, st);
+      if (t1 > t0) {
+        if (wire16) H2D(reinterpret_cast<uint16_t*>(m->xraw) + t0 * E, reinterpret_cast<uint16_t*>(h_x) + t0 * E, (size_t)(t1 - t0) * E * 2, st);
+        else H2D(m->xraw + t0 * E, h_x + t0 * E, (size_t)(t1 - t0) * E * 4, st);
+      }
       s0 = s1;
     }
   }
@@ -1040,7 +1079,7 @@ static int lstm_forward(icl_model* m, float keep_in, uint64_t seed, int training
   k_prep_x<<<(unsigned)((Ntok * 32 + 255) / 256), 256, 0, st>>>(m->xraw, m->d_tokseq, m->d_tokstart, mk_layout(m), (int)Ntok, E, m->T_cap,
                                                                m->cfg.data_norm, keep_in, seed, m->seq_gid0, m->round_ops, m->xd[0], m->xd[1], m->ldx, E + H,
                                                                m->use_rows ? m->d_tokrow : nullptr, m->tok_table, m->k1_f16 ? m->X16[0] : nullptr,
-                                                               m->k1_f16 ? m->X16[1] : nullptr, m->k1_Kp);
+                                                               m->k1_f16 ? m->X16[1] : nullptr, m->k1_Kp, m->x_half && !m->use_rows);
   LAUNCHED(m);
   k_zero_pad_rows<<<dim3(m->Tmax, 2), 256, 0, st>>>(m->XH[0], m->XH[1], mk_layout(m), m->ldx); LAUNCHED(m);
   // h_prev of step 0 is the zero state: step 0's block of Hp stays zero (these are A rows of dW_hh)

@@ -652,3 +652,45 @@ def test_resident_box_table_gives_identical_results():
     assert np.array_equal(res["rows"][0], res[False][0])
     for k, v in res[False][1].items():
         assert np.array_equal(res["rows"][1][k], v), k
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_half_width_wire_format_of_the_sentence_rows(monkeypatch, dtype):
+    """Product mode without data_norm sends the sentence rows over PCIe as fp16 (rounded while they are packed into pinned
+    memory; ICL_WIRE_FP16=0 keeps fp32): the device rounds the prepared inputs to 10 mantissa bits next anyway, and with a
+    power-of-two input-dropout scale (keep 0.5) the two orders of rounding agree except on exact ties.  The H2D byte count of the
+    rows halves, probabilities and gradients stay within the TF32 tolerance of each other and of the oracle; with data_norm the
+    fp32 wire is kept (the l2 norm is taken over the fp32 inputs)."""
+    import ctypes as C
+    from imagecaptionlearn_py_b200 import _cabi
+    p = tiny_problem(seed=31, dropout=True, **CASES[5])
+    E, ntok = p["E"], int(np.sum(p["batch"]["seq_lengths"]))
+    out = {}
+    for wire in ("0", "1"):
+        monkeypatch.setenv("ICL_WIRE_FP16", wire)
+        core, sess = make_session(p, "tf32")
+        sess.base_seed, sess.run_counter = 5, 0
+        bt = dict(p["batch"])
+        bt["sentences"] = np.asarray(bt["sentences"], dtype=dtype)
+        r = sess.run(_cabi.OP_GRADS, [bt], p["keep_in"], p["keep"], True)[0]
+        h2d, d2h = C.c_int64(), C.c_int64()
+        _cabi.lib().icl_copy_bytes(sess.handle, C.byref(h2d), C.byref(d2h))
+        out[wire] = (r["proba"].copy(), {k: sess.get_tensor(k, 1) for k in p["params"]}, h2d.value)
+        sess.close()
+    assert out["0"][2] - out["1"][2] == ntok * E * 2                     # the rows went up at 2 instead of 4 bytes per element
+    assert relerr(out["1"][0], out["0"][0]) < 1e-3
+    for k in out["0"][1]:
+        assert relerr(out["1"][1][k], out["0"][1][k]) < 2e-3, k
+    # data_norm: the switch must not apply
+    pn = tiny_problem(seed=32, dropout=True, **CASES[6])
+    nb = {}
+    for wire in ("0", "1"):
+        monkeypatch.setenv("ICL_WIRE_FP16", wire)
+        core, sess = make_session(pn, "tf32")
+        sess.base_seed, sess.run_counter = 5, 0
+        r = sess.run(_cabi.OP_GRADS, [dict(pn["batch"])], pn["keep_in"], pn["keep"], True)[0]
+        h2d, d2h = C.c_int64(), C.c_int64()
+        _cabi.lib().icl_copy_bytes(sess.handle, C.byref(h2d), C.byref(d2h))
+        nb[wire] = (r["proba"].copy(), h2d.value)
+        sess.close()
+    assert nb["0"][1] == nb["1"][1] and np.array_equal(nb["0"][0], nb["1"][0])

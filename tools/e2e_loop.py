@@ -23,5 +23,5 @@ for rep in range(4):
     for _ in range(20):
         core.run_op(sess, op, [bt], 0.5, 0.5, "first_last_mention", [wl["task"]], [""], True)
     torch.cuda.synchronize(); res.append(1e3 * (time.perf_counter() - t0) / 20)
-print("ICL_PACK_NT=%s ICL_HOST_THREADS=%s %s: %s ms/step" % (os.environ.get("ICL_PACK_NT", "-"), os.environ.get("ICL_HOST_THREADS", "-"), bt["sentences"].dtype,
+print("ICL_WIRE_FP16=%s ICL_PACK_NT=%s ICL_HOST_THREADS=%s %s: %s ms/step" % (os.environ.get("ICL_WIRE_FP16", "-"), os.environ.get("ICL_PACK_NT", "-"), os.environ.get("ICL_HOST_THREADS", "-"), bt["sentences"].dtype,
                                                         " ".join("%.3f" % r for r in res)))
