@@ -164,7 +164,7 @@ def run_reference(args, wl):
                                  "restated in NumPy (oracle/icl_oracle.py) and timed on the host cores"),
                 cpu_baseline=dict(value=r["value"], unit="captions/s", cores=r["cores"], kind="port", sample=r["sample"]),
                 e2e=dict(value=r["value"], unit="captions/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line))
+    _JSON_OUT.write(json.dumps(line) + "\n"); _JSON_OUT.flush()
 
 
 def affinity_pairs_per_sec(local, steps=10, warmup=3):
@@ -236,6 +236,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
+    # stdout carries the ONE JSON line and nothing else: whatever a library writes to fd 1 during the run (NCCL prints its version
+    # there when the box sets NCCL_DEBUG) goes to stderr instead
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args, wl)
     args.warmup = max(args.warmup, 3)
@@ -460,7 +466,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:        # rank 0 at N=1 only: the other ranks would idle behind it
             line["cpu_baseline"] = {k: v for k, v in cpu_sample(wl, min(wl["B"], 512), 3, 2, target_s=12.0).items()
                                     if k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
+        _JSON_OUT.write(json.dumps(line) + "\n"); _JSON_OUT.flush()
     sess.close()
     if dist:
         dist.destroy_process_group()
