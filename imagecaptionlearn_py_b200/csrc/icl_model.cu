@@ -1649,6 +1649,17 @@ extern "C" int icl_rec_trace(icl_model* m, int cta, long long* host) {
   m->rp_trace_cta = cta;
   return 0;
 }
+extern "C" int icl_pack_rows(const void* src, int32_t src_dtype, int64_t n, void* dst, int32_t half) {
+  if (!src || !dst || n < 0) return fail("icl_pack_rows: null buffer or negative count");
+  if (src_dtype != ICL_F32 && src_dtype != ICL_F64) return fail("icl_pack_rows: sentences must be float32/float64");
+  if (!half) { to_f32((float*)dst, src, src_dtype, (size_t)n); _mm_sfence(); return 0; }
+  if (!(__builtin_cpu_supports("avx") && __builtin_cpu_supports("f16c"))) return fail("icl_pack_rows: this CPU has no F16C");
+  if (src_dtype == ICL_F32) cvt_f32_h16_stream((uint16_t*)dst, (const float*)src, (size_t)n);
+  else cvt_f64_h16_stream((uint16_t*)dst, (const double*)src, (size_t)n);
+  _mm_sfence();
+  return 0;
+}
+
 extern "C" int icl_debug_mask(icl_model* m, uint64_t seed, uint32_t stream, int64_t first, int64_t n, float keep, float* host) {
   float* tmp;
   CK(dmalloc(&tmp, (size_t)n));

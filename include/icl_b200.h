@@ -168,6 +168,9 @@ int icl_last_step_ms(icl_model* m, float* ms);                           /* devi
 #define ICL_N_PHASES 8   /* prep, input-projection GEMM, recurrence fwd, heads fwd, heads bwd, BPTT, weight grads, clip+Adam */
 int icl_phase_ms(icl_model* m, float* ms /*[ICL_N_PHASES]*/);            /* per-phase device time of the last run_resident */
 int icl_copy_bytes(icl_model* m, int64_t* h2d, int64_t* d2h);            /* bytes copied by the last upload / fetch */
+/* the host conversion icl_upload applies to sentence rows (run_op's float64 -> float32 feed conversion, core.py:558-561), exposed
+   so that it is testable without a GPU: n elements of src (ICL_F32 / ICL_F64) -> float32 (half = 0) or fp16 bits (half = 1) at dst */
+int icl_pack_rows(const void* src, int32_t src_dtype, int64_t n, void* dst, int32_t half);
 int icl_batch_stats(icl_model* m, int64_t* n_seqs, int64_t* n_tokens, int32_t* t_max);   /* of the resident batch */
 
 #ifdef __cplusplus

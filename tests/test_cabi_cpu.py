@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
 import pytest
 
 
@@ -74,3 +75,36 @@ def test_graph_layer_mirrors_reference_names():
         assert callable(getattr(core, fn))
     assert core.get_widths(512, 2) == [512, 256, 128]
     assert core.get_collection("nonvis/loss")[0].scope == "nonvis"
+
+
+@pytest.mark.parametrize("src_dtype", ["float32", "float64"])
+def test_host_row_packing_is_bit_exact(built, src_dtype):
+    """icl_upload's host conversion of the sentence rows (icl_pack_rows = the same routines, no GPU needed): float32 out equals
+    NumPy's cast (run_op's feed conversion, core.py:558-561), fp16 out (the half-width wire) equals NumPy's round-to-nearest-even
+    float16 cast -- for every destination alignment / length remainder of the 64-byte streaming loop, and for values that hit
+    ties, subnormal halves, overflow to inf and signed zeros."""
+    import ctypes as C
+    from imagecaptionlearn_py_b200 import _cabi
+    L = _cabi.lib()
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal(4099) * 0.15).astype(np.float32)
+    x[:12] = [0.0, -0.0, 1.0, 1.0 + 2.0 ** -11, 1.0 + 3 * 2.0 ** -11, 65504.0, 65520.0, 1e-7, -3e-8, 6.1e-5, 70000.0, -2.0 ** -25]   # ties, limits
+    x = x.astype(src_dtype)
+    if src_dtype == "float64":
+        x[20:40] += rng.standard_normal(20) * 1e-9              # not representable in float32
+    code = 0 if src_dtype == "float32" else 1
+    for start in (0, 1, 3, 16, 31):
+        for n in (0, 1, 15, 63, 64, 65, 300, 4099 - start):
+            src = np.ascontiguousarray(x[start:start + n])
+            for off in (0, 1, 5):                                 # destination misalignment in elements
+                f32 = np.full(n + off + 8, 7.0, np.float32)
+                assert L.icl_pack_rows(src.ctypes.data_as(C.c_void_p), code, n, C.c_void_p(f32.ctypes.data + 4 * off), 0) == 0
+                assert np.array_equal(f32[off:off + n].view(np.uint32), src.astype(np.float32).view(np.uint32))
+                assert np.all(f32[:off] == 7.0) and np.all(f32[off + n:] == 7.0)
+                h16 = np.full(n + off + 8, 0x7777, np.uint16)
+                assert L.icl_pack_rows(src.ctypes.data_as(C.c_void_p), code, n, C.c_void_p(h16.ctypes.data + 2 * off), 1) == 0
+                with np.errstate(over="ignore"):
+                    want = src.astype(np.float32).astype(np.float16).view(np.uint16)
+                assert np.array_equal(h16[off:off + n], want), (start, n, off)
+                assert np.all(h16[:off] == 0x7777) and np.all(h16[off + n:] == 0x7777)
+    assert L.icl_pack_rows(None, 0, 4, None, 0) != 0
