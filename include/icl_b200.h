@@ -119,7 +119,8 @@ int icl_set_step(icl_model* m, int64_t t);
 int icl_run(icl_model* m, int op, const icl_batch* b, float keep_in, float keep, uint64_t seed, icl_head_out* out);
 /* split form: stage the batch in HBM once, then run on resident data (bench `value`, DP overlap).
    Wire format of the sentence rows: the valid tokens are packed (and float64 -> float32 converted, run_op's feed conversion,
-   core.py:558-561) into pinned memory by a small host thread pool (ICL_HOST_THREADS, default 4 shared between the ranks of a node)
+   core.py:558-561) into pinned memory by a small host thread pool (ICL_HOST_THREADS; default up to 4 per process, the ranks of a node
+   split the host cores)
    with non-temporal stores (ICL_PACK_NT=0: memcpy).  In ICL_GEMM_TCGEN05_TF32 mode without data_norm the rows are rounded to fp16
    while they are packed (ICL_WIRE_FP16=0: keep fp32): the device's next step rounds the prepared inputs to 10 mantissa bits for
    the tensor cores anyway, so the copy carries 2 bytes per element instead of 4.  The fp32 validation mode and data_norm models
