@@ -58,11 +58,15 @@ class Embeddings(object):
 
 
 def load_sentences(sentence_file, embeddings):
+    """nn_utils/data.py:77-120.  As written, the reference splits the raw line -- `line.split("\\t")[1].split(" ")`, :92-93 --
+    without stripping it, so the LAST token of every caption still carries its "\\n", is not found in the embedding model and
+    becomes the UNK row (utils/Word2Vec.py:36-39).  Reproduced here token for token (pinned against the reference's own
+    load_sentences by tests/test_ref_fixtures.py): a checkpoint trained by the reference saw UNK there."""
     data_dict = dict(sentences={})
     if sentence_file is not None:
         with open(sentence_file, "r") as f:
             for line in f:
-                id_split = line.rstrip("\n").split("\t")
+                id_split = line.split("\t")
                 data_dict["sentences"][id_split[0].strip()] = embeddings.sentence_matrix(id_split[1].split(" "))
     data_dict["max_seq_len"] = max([len(m) for m in data_dict["sentences"].values()] or [-1])
     data_dict["word_embedding_width"] = embeddings.matrix.shape[1]
