@@ -244,36 +244,7 @@ def main_relation(argv=None):
             return out
 
 
-def evaluate_relations(mention_pairs, pred_labels, gold_label_dict, log=None):
-    """nn_utils/eval.py:10-93: pairwise (ij, ji) scoring into null / coref / subset / -invalid- / -reverse_sub-."""
-    sd = nn_eval.ScoreDict()
-    pred = dict(zip(mention_pairs, pred_labels))
-    for pair, gold in gold_label_dict.items():
-        if pair[0] not in pred or pair[1] not in pred:
-            continue
-        ij, ji = pred[pair[0]], pred[pair[1]]
-        p = "invalid"
-        if ij == ji == 0:
-            p = "null"
-        elif ij == ji == 1:
-            p = "coref"
-        elif ij + ji == 5:
-            if ij == 2:
-                p = "subset_ij"
-            elif ji == 2:
-                p = "subset_ji"
-        if gold.startswith("subset_") and p.startswith("subset_"):
-            p = "subset" if gold == p else "-reverse_sub-"
-            gold = "subset"
-        if gold.startswith("subset_"):
-            gold = "subset"
-        if p.startswith("subset_"):
-            p = "subset"
-        sd.increment(gold, p)
-    if log is not None:
-        for l in ("-invalid-", "-reverse_sub-", "null", "coref", "subset"):
-            log.info("%10s: %s", l, sd.get_score(l).to_string())
-    return sd
+evaluate_relations = nn_eval.evaluate_relations          # nn_utils/eval.py:10-93
 
 
 # -------------------------------------------------------------------------------------------- icl_affinity_lstm.py
