@@ -1,19 +1,21 @@
 #!/usr/bin/env python
-"""Benchmark of the BiLSTM + mention-span-head hot path (BASELINE.json metric: BiLSTM train captions/sec).
+"""Benchmark of the BiLSTM + mention-span-head hot path (BASELINE.json metric: BiLSTM train captions/sec; mention-box pairs/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload card2048|nonvis512|...]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload card2048|nonvis512|...] [--no-by-config]
 
 One "step" = one `train_op` pass (forward + BPTT + clip + TF-Adam, dropout 0.5/0.5) of the hot path over one synthetic
-F30kE-shaped batch.  At N=1 the workload is BASELINE.json configs[1] (icl_core_lstm cardinality head, H=300,
-batch 2048 captions on one B200).  N>1: one process per GPU (torchrun), each rank trains on its own batch of the same
-size (weak scaling) and the flat gradient buffer is all-reduced (SUM: the loss is a sum over examples,
-nn_utils/core.py:267) over NCCL before the fused clip+Adam update.
+F30kE-shaped batch.  The headline workload is BASELINE.json configs[1] (icl_core_lstm cardinality head, H=300, batch 2048
+captions on one B200).  N>1: one process per GPU (torchrun), each rank trains on its own batch of the same size (weak
+scaling) and the flat gradient buffer is all-reduced (SUM: the loss is a sum over examples, nn_utils/core.py:267) over NCCL
+before the fused clip+Adam update.
 
-JSON line keys: see the contract in the task description.  `value` = captions/s with the batch resident in HBM
-(icl_run_resident), `e2e` = the same step through the reference-facing call `run_op(sess, train_op, [batch_tensors], ...)`
-with host NumPy buffers (H2D of the batch + D2H of loss/proba inside the timed region), `roofline` = the dominant
-kernel group's algorithmic FLOPs / its CUDA-event time, `cpu_baseline` = the NumPy oracle (a port of the reference's
-TF graph; TensorFlow 1.x cannot run here) timed on a bounded sample of the same workload.
+JSON line: `value` = captions/s with the batch resident in HBM (icl_run_resident, CUDA events, max over ranks); `e2e` = the same
+step through the reference-facing call `run_op(sess, train_op, [batch_tensors], ...)` with host NumPy buffers (H2D of the batch
+and D2H of loss/accuracy inside the timed region, a rotation of distinct host batches); `e2e_variants` = that call with the
+reference's own float64 feed, with `load_batch` inside the timed region, and with the corpus cache; `roofline` = the dominant
+kernel group's algorithmic work / its CUDA-event time; `by_config` = the other BASELINE configs (C1 nonvis512, C3 intra / cross,
+C4 affinity, C5 multitask) measured the same way in short runs; `cpu_baseline` = the NumPy oracle (a port of the reference's TF
+graph; TensorFlow 1.x cannot run here) timed on a bounded sample of the same workload.
 """
 import argparse
 import ctypes as C
@@ -30,28 +32,51 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+
+def _head(task, B, start, depth, C_, F, scope=""):
+    return dict(task=task, B=B, start=start, depth=depth, C=C_, F=F, scope=scope)
+
+
 WORKLOADS = {
-    # name: (task, B, H, start_width, depth, n_classes, F, data_norm, BASELINE.json config it instantiates)
-    "nonvis512": dict(task="nonvis", B=512, H=300, start=512, depth=2, C=2, F=256, data_norm=False, cfg="configs[0]"),
-    "card2048": dict(task="card", B=2048, H=300, start=512, depth=2, C=12, F=256, data_norm=False, cfg="configs[1]"),
-    "rel_intra512": dict(task="rel_intra", B=512, H=200, start=1024, depth=3, C=4, F=512, data_norm=True, cfg="configs[2]"),
-    "rel_cross512": dict(task="rel_cross", B=512, H=200, start=1024, depth=3, C=4, F=512, data_norm=True, cfg="configs[2]"),
-    "card2048_h200": dict(task="card", B=2048, H=200, start=512, depth=2, C=12, F=256, data_norm=False, cfg="(bring-up)"),
-    "affinity512": dict(task="affinity", B=512, H=300, start=512, depth=2, C=2, F=256, data_norm=False, cfg="configs[3]"),
+    # BASELINE.json configs; hyper-parameters: the CLI defaults (icl_core_lstm.py:265-321) / config/lstm_{intra,cross}_params.config:96 /
+    # icl_multitask_lstm.py:560-583 (H=200, 512-2, five heads in TASKS order :22)
+    "nonvis512": dict(cfg="configs[0]", H=300, data_norm=False, heads=[_head("nonvis", 512, 512, 2, 2, 256)]),
+    "card2048": dict(cfg="configs[1]", H=300, data_norm=False, heads=[_head("card", 2048, 512, 2, 12, 256)]),
+    "rel_intra512": dict(cfg="configs[2]", H=200, data_norm=True, heads=[_head("rel_intra", 512, 1024, 3, 4, 512)]),
+    "rel_cross512": dict(cfg="configs[2]", H=200, data_norm=True, heads=[_head("rel_cross", 512, 1024, 3, 4, 512)]),
+    "affinity512": dict(cfg="configs[3]", H=300, data_norm=False, heads=[_head("affinity", 512, 512, 2, 2, 256)]),
+    "multitask512": dict(cfg="configs[4]", H=200, data_norm=False, joint="simple_joint",
+                         heads=[_head("rel_intra", 512, 512, 2, 4, 512, "rel_intra"), _head("rel_cross", 512, 512, 2, 4, 512, "rel_cross"),
+                                _head("nonvis", 512, 512, 2, 2, 256, "nonvis"), _head("affinity", 512, 512, 2, 2, 256, "affinity"),
+                                _head("card", 512, 512, 2, 12, 256, "card")]),
+    "card2048_h200": dict(cfg="(bring-up)", H=200, data_norm=False, heads=[_head("card", 2048, 512, 2, 12, 256)]),
 }
+BY_CONFIG = ("nonvis512", "rel_intra512", "rel_cross512", "affinity512", "multitask512")
 E, T_PAD, KEEP_IN, KEEP = 300, 50, 0.5, 0.5
 LR, ADAM_EPS, CLIP = 1e-3, 1e-8, 5.0
+BOX_W = 4096
+ENC = "first_last_mention"
+
+# legacy single-head view used by tests/test_gpu_full_size.py
+for _n, _w in WORKLOADS.items():
+    _h = _w["heads"][0]
+    _w.update(task=_h["task"], B=_h["B"], start=_h["start"], depth=_h["depth"], C=_h["C"], F=_h["F"])
 
 
-def make_batch(wl, seed, packed=False, dedup=False):
-    """One reference-shaped batch_tensors dict (nn_utils/data.py:349-528) from the synthetic corpus."""
-    from imagecaptionlearn_py_b200 import data as nn_data
+def _corpus_for(head, seed):
     from imagecaptionlearn_py_b200 import synth
-    task, B = wl["task"], wl["B"]
+    task, B = head["task"], head["B"]
     n_img = {"affinity": max(4, B // 200), "rel_cross": max(6, B // 60)}.get(task, max(8, B // 10))
     corpus = synth.make_corpus(n_img, seed=seed, with_boxes=(task == "affinity"))
-    dd = synth.make_data_dict(corpus, task, F=wl["F"])
+    dd = synth.make_data_dict(corpus, task, F=head["F"])
     dd["max_seq_len"] = T_PAD                      # the reference pads to the dataset-global maximum (data.py:375)
+    return dd
+
+
+def _ids_for(head, dd, seed):
+    from imagecaptionlearn_py_b200 import data as nn_data
+    from imagecaptionlearn_py_b200 import synth
+    task, B = head["task"], head["B"]
     ids = synth.example_ids(dd, task)
     rng = np.random.Generator(np.random.PCG64(seed + 1))
     if task == "affinity":
@@ -60,13 +85,57 @@ def make_batch(wl, seed, packed=False, dedup=False):
         ids = list(np.asarray(ids, dtype=object)[rng.permutation(len(ids))])
     if len(ids) < B:
         raise RuntimeError("synthetic corpus too small: %d ids for batch %d" % (len(ids), B))
-    return nn_data.load_batch(ids[:B], dd, task, wl["C"], packed=packed, dedup=dedup)
+    return ids
+
+
+def make_batch(wl, seed, packed=False, dedup=False, head=0):
+    """One reference-shaped batch_tensors dict (nn_utils/data.py:349-528) from the synthetic corpus, for head `head` of `wl`."""
+    from imagecaptionlearn_py_b200 import data as nn_data
+    h = wl["heads"][head]
+    dd = _corpus_for(h, seed)
+    ids = _ids_for(h, dd, seed)
+    return nn_data.load_batch(ids[:h["B"]], dd, h["task"], h["C"], packed=packed, dedup=dedup)
+
+
+def make_batches(wl, seed, packed=False):
+    """The list run_op takes: one batch_tensors dict per head, in head order."""
+    return [make_batch(wl, seed + 17 * i, packed=packed, head=i) for i in range(len(wl["heads"]))]
+
+
+def build_graph(wl):
+    from imagecaptionlearn_py_b200 import core
+    core.reset_default_graph()
+    core.set_random_seeds()
+    with core.variable_scope("bidirectional_lstm"):
+        core.setup_bidirectional_lstm(wl["H"], wl["data_norm"], n_embedding_width=E)
+    for h in wl["heads"]:
+        args = (h["task"], ENC, h["B"], h["start"], h["depth"], False, "relu", h["C"], h["F"])
+        kw = dict(box_embedding_width=BOX_W) if h["task"] == "affinity" else {}
+        if h["scope"]:
+            with core.variable_scope(h["scope"]):
+                core.setup_core_architecture(*args, **kw)
+        else:
+            core.setup_core_architecture(*args, **kw)
+    loss = core.setup_joint_loss(wl["joint"]) if wl.get("joint") else core.get_collection("loss")[0]
+    core.add_train_op(loss, LR, ADAM_EPS, CLIP)
+    return core.get_collection("train_op")[0]
+
+
+def run_train(core, sess, train_op, wl, bts):
+    core.run_op(sess, train_op, bts, KEEP_IN, KEEP, ENC, [h["task"] for h in wl["heads"]], [h["scope"] for h in wl["heads"]], True)
 
 
 def flops_per_token(H, train=True):
     """valid-token FLOPs of the BiLSTM, both directions."""
     fwd = 4 * (E + H) * 4 * H
     return fwd * 2 + 4 * H * 4 * H if train else fwd
+
+
+def head_dims(wl, h):
+    from imagecaptionlearn_py_b200 import core
+    H = wl["H"]
+    d0 = (8 * H if h["task"].startswith("rel") else 4 * H) + h["F"] + (BOX_W if h["task"] == "affinity" else 0)
+    return [d0] + core.get_widths(h["start"], h["depth"]) + [h["C"]]
 
 
 def sample_clocks(stop, out):
@@ -109,6 +178,19 @@ def clocks_summary(samples):
 
 
 # ----------------------------------------------------------------------------------------------- reference arm (CPU)
+def host_threads():
+    """All the host cores for the CPU arm: torchrun exports OMP_NUM_THREADS=1, which would pin the BLAS behind NumPy to one
+    thread -- lift the limit explicitly and report what is actually in effect."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=n)
+        n = max([p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()] or [n])
+    except Exception:
+        pass
+    return int(n)
+
+
 def oracle_train_step(params, cfg, bt, state, keep_in, keep, rng):
     from oracle import icl_oracle as O
     S, T = bt["sentences"].shape[:2]
@@ -124,21 +206,23 @@ def oracle_train_step(params, cfg, bt, state, keep_in, keep, rng):
 
 
 def cpu_sample(wl, sample_B, steps, warmup, target_s=None):
-    """Time the NumPy oracle (port of the reference TF graph) on the first `sample_B` examples of the workload.  With `target_s` the
-    number of timed steps is chosen from the last warm-up step so that the sample is about that many seconds of CPU work."""
+    """Time the NumPy oracle (port of the reference TF graph) on the first `sample_B` examples of the (single-head) workload.  With
+    `target_s` the number of timed steps is chosen from the last warm-up step so that the sample is about that many seconds."""
     from oracle import icl_oracle as O
     from imagecaptionlearn_py_b200 import core
-    small = dict(wl, B=sample_B)
+    cores = host_threads()
+    h = dict(wl["heads"][0], B=sample_B)
+    small = dict(wl, heads=[h])
     bt = make_batch(small, 20171201)
     tl = int(bt["seq_lengths"].max())
     bt["sentences"] = bt["sentences"][:, :tl]              # dynamic_rnn stops at the batch maximum (sequence_length)
-    widths = core.get_widths(wl["start"], wl["depth"])
+    widths = core.get_widths(h["start"], h["depth"])
     H = wl["H"]
     box_w = bt["box_embeddings"].shape[1] if "box_embeddings" in bt else 0
     cfg = dict(H=H, data_norm=wl["data_norm"],
-               heads=[dict(task=wl["task"], scope="", encoding_scheme="first_last_mention", n_layers=len(widths),
+               heads=[dict(task=h["task"], scope="", encoding_scheme=ENC, n_layers=len(widths),
                            widths=widths, activation="relu", weighted_classes=False,
-                           in_width=O.head_in_width(wl["task"], "first_last_mention", H, wl["F"], box_w), n_classes=wl["C"])])
+                           in_width=O.head_in_width(h["task"], ENC, H, h["F"], box_w), n_classes=h["C"])])
     rng = np.random.default_rng(7)
     params = O.init_params(rng, cfg, E, np.float32)
     state = {}
@@ -153,92 +237,271 @@ def cpu_sample(wl, sample_B, steps, warmup, target_s=None):
     for _ in range(steps):
         oracle_train_step(params, cfg, bt, state, KEEP_IN, KEEP, rng)
     dt = time.perf_counter() - t0
-    try:
-        from threadpoolctl import threadpool_info
-        cores = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
-    except Exception:
-        cores = os.cpu_count() or 1
     return dict(value=sample_B * steps / dt, unit="captions/s", cores=int(cores), kind="port",
                 sample="%d train steps of the NumPy oracle (fp32, BLAS threads=%d) on %d captions of the same workload"
-                       % (steps, cores, sample_B), ms_per_step=1e3 * dt / steps, steps=steps)
+                       % (steps, cores, sample_B), ms_per_step=1e3 * dt / steps, steps=steps, batch=sample_B)
 
 
 def run_reference(args, wl):
+    """The reference arm: the NumPy restatement of the reference's TF CPU graph on ALL host cores, on the same workload and the same
+    batch per step as the B200 arm (rank 0 only; the other ranks exit)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_B = min(wl["B"], 256)
-    r = cpu_sample(wl, sample_B, args.steps, args.warmup)
+    B = wl["heads"][0]["B"]
+    r = cpu_sample(wl, B, args.steps, args.warmup)
     line = dict(metric="bilstm_train_captions_per_sec", value=r["value"], unit="captions/s", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic", impl="reference",
-                config=dict(workload=args.workload, baseline_config=wl["cfg"], task=wl["task"], batch_per_step=sample_B,
-                            lstm_hidden=wl["H"], embed=E, padded_T=T_PAD,
+                config=dict(workload=args.workload, baseline_config=wl["cfg"], task=wl["heads"][0]["task"], batch_per_step=B,
+                            batch_per_gpu=B, lstm_hidden=wl["H"], embed=E, padded_T=T_PAD, host_threads=r["cores"],
                             note="TensorFlow 1.x / Python 2 are not installable here: the reference's TF CPU graph is "
-                                 "restated in NumPy (oracle/icl_oracle.py) and timed on the host cores"),
+                                 "restated in NumPy (oracle/icl_oracle.py) and timed on the host cores; one host runs one batch per "
+                                 "step whatever --gpus says (the reference has no multi-GPU path)"),
                 cpu_baseline=dict(value=r["value"], unit="captions/s", cores=r["cores"], kind="port", sample=r["sample"]),
                 e2e=dict(value=r["value"], unit="captions/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     _JSON_OUT.write(json.dumps(line) + "\n"); _JSON_OUT.flush()
 
 
-def affinity_pairs_per_sec(local, steps=10, warmup=3):
-    """BASELINE.json's second metric, "mention-box pairs/sec", on configs[3] shapes (icl_affinity_lstm: B=512 mention-box pairs per
-    step, 4096-d box features, H=300, pairs grouped by image): train pairs/s with the batch resident in HBM (CUDA events), train
-    pairs/s end to end through run_op with host buffers, and predict pairs/s end to end through get_pred_scores_mcc's batch path
-    (keep 1.0, every distinct caption of a batch encoded once).  The e2e legs use what the drop-in CLI uses with ICL_BOX_TABLE=1:
-    token rows + box rows into the device-resident token / box tables (3 MB instead of 12 MB per step on the wire)."""
-    import ctypes as C
+# ----------------------------------------------------------------------------------------------- our arm (B200)
+class Ctx(object):
+    pass
+
+
+def peaks():
+    p = {}
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    bf16 = p.get("bf16_tflops_sustained", 1400.0)            # fallback: the profiling guide's sustained figure
+    return dict(bf16=bf16, tf32=bf16 / 2.0, hbm=p.get("hbm_gbs", 6650.0),        # kind::tf32 issues at half the kind::f16 rate
+                source=("MEASURED_PEAKS.json: hbm_gbs; bf16_tflops_sustained (kind::f16), / 2 for kind::tf32" if p
+                        else "fallback 6650 GB/s, 1400 (f16) / 700 (tf32) TFLOP/s"))
+
+
+def phase_work(wl, n_tok):
+    """ALGORITHMIC work per step of each kernel group: FLOPs of the contraction and the bytes that must cross
+    HBM once, per valid token and direction x 2 directions; heads: per example.  phase -> (flops, bytes, kernel, launches, tensor peak key)"""
+    H = wl["H"]
+    tok2 = 2.0 * n_tok
+    w = {"proj_gemm": (tok2 * 2 * E * 4 * H, tok2 * (E * 2 + 4 * H * 4), "k_gemm_tcgen05<0, 0, 256, 2, 1>", 2, "bf16"),    # fp16 x in, fp32 out
+         "rec_fwd": (tok2 * 2 * H * 4 * H, tok2 * (4 * H + 4 * H + 3 * H) * 4, "k_rec_fwd16", 1, "bf16"),       # Zx in; gates, c, h, TF32(h) out
+         "rec_bwd": (tok2 * 2 * H * 4 * H, tok2 * (4 * H + 3 * H + 4 * H) * 4, "k_bptt_cluster", 1, "tf32"),    # gates, c, c_prev, dH in; dZ out
+         "wgrad": (tok2 * 2 * (E + H) * 4 * H, tok2 * (E + H + 4 * H) * 4, "k_gemm_tcgen05<1, 1, 256, 4, 0>", 2, "tf32")}
+    fl = by = 0.0
+    for h in wl["heads"]:
+        d = head_dims(wl, h)
+        mm = sum(d[k] * d[k + 1] for k in range(len(d) - 1))
+        fl += 2.0 * h["B"] * mm                                      # SURVEY section 8d: 2 * sum_k w_k w_{k+1} per example (forward)
+        # gather + concat (read the sources, write batch_input), weights once, activations once
+        by += h["B"] * (2.0 * d[0] + sum(d[1:])) * 4 + mm * 4
+    w["heads_fwd"] = (fl, by, "k_gather_concat + k_gemm_tcgen05 x L + k_softmax_ce", len(wl["heads"]), "tf32")
+    w["heads_bwd"] = (2 * fl, 2 * by, "k_softmax_bwd + k_gemm_tcgen05 (dz chain, dW) + k_scatter_spans", len(wl["heads"]), "tf32")
+    return w
+
+
+def roofline_of(wl, n_tok, ph_ms, pk, traffic=None):
+    from imagecaptionlearn_py_b200 import _cabi
+    work = phase_work(wl, n_tok)
+    dom = max(work, key=lambda k: ph_ms[_cabi.PHASES.index(k)])
+    t_ms = float(ph_ms[_cabi.PHASES.index(dom)])
+    flops, nbytes, kernel, n_launch, tp = work[dom]
+    t_tensor, t_hbm = flops / (pk[tp] * 1e12), nbytes / (pk["hbm"] * 1e9)
+    if t_hbm >= t_tensor:
+        roof = dict(kernel=kernel, phase=dom, bound="hbm", unit="GB/s", peak=pk["hbm"], achieved=nbytes / (t_ms * 1e-3) / 1e9)
+    else:
+        roof = dict(kernel=kernel, phase=dom, bound="tensor", unit="TFLOP/s", peak=pk[tp], achieved=flops / (t_ms * 1e-3) / 1e12)
+    roof.update(frac=roof["achieved"] / roof["peak"], traffic=traffic, launches_per_step=n_launch, ms_per_launch=t_ms / n_launch,
+                algorithmic_bytes_per_launch=nbytes / n_launch, algorithmic_flops_per_launch=flops / n_launch,
+                tensor_frac=flops / (t_ms * 1e-3) / 1e12 / pk[tp], hbm_frac=nbytes / (t_ms * 1e-3) / 1e9 / pk["hbm"], peak_source=pk["source"],
+                note="time = CUDA events around the kernel group on its launch stream (icl_phase_ms), averaged over the timed steps; the "
+                     "algorithmic bytes of the recurrences are this repo's accounting (SURVEY 8d gives none): gates, c, h / dH in and out once")
+    by_phase = {}
+    for k, wk in work.items():
+        ms_k = float(ph_ms[_cabi.PHASES.index(k)])
+        if ms_k > 0:
+            by_phase[k] = dict(kernel=wk[2], ms=ms_k, hbm_frac=wk[1] / (ms_k * 1e-3) / 1e9 / pk["hbm"],
+                               tensor_frac=wk[0] / (ms_k * 1e-3) / 1e12 / pk[wk[4]], tensor_peak_tflops=pk[wk[4]],
+                               bound="hbm" if wk[1] / (pk["hbm"] * 1e9) >= wk[0] / (pk[wk[4]] * 1e12) else "tensor")
+    return roof, by_phase
+
+
+def measure(name, steps, warmup, ctx, clocks=None, e2e_variants=False):
+    """One workload on this rank's GPU: device-timed resident steps (CUDA events, L2 flushed between steps, max over ranks) and the
+    end-to-end run_op loop with host buffers.  Returns a dict (rank 0 fills the JSON from it)."""
     import torch
     from imagecaptionlearn_py_b200 import _cabi, core
-    wl = WORKLOADS["affinity512"]
-    bt = make_batch(wl, 20171201, packed="rows")
-    core.reset_default_graph()
-    core.set_random_seeds()
-    with core.variable_scope("bidirectional_lstm"):
-        core.setup_bidirectional_lstm(wl["H"], wl["data_norm"], n_embedding_width=E)
-    core.setup_core_architecture(wl["task"], "first_last_mention", wl["B"], wl["start"], wl["depth"], False, "relu", wl["C"], wl["F"],
-                                 box_embedding_width=(bt["box_table"] if "box_table" in bt else bt["box_embeddings"]).shape[1])
-    core.add_train_op(core.get_collection("loss")[0], LR, ADAM_EPS, CLIP)
-    sess = core.Session(max_seq_len=T_PAD, device=local)
+    from imagecaptionlearn_py_b200 import data as nn_data
+    wl = WORKLOADS[name]
+    dist, rank, world, local = ctx.dist, ctx.rank, ctx.world, ctx.local
+    seed0 = 20171201 + 1000 * rank
+    bts = make_batches(wl, seed0)
+    train_op = build_graph(wl)
+    sess = core.Session(max_seq_len=T_PAD, device=local, dist=bool(dist), gemm_mode=ctx.gemm_mode)
     sess.ensure()
     L = _cabi.lib()
-    train_op, proba_op = core.get_collection("train_op")[0], core.get_collection("predicted_proba")[0]
-    ka = []
-    b = sess.build_batch([bt], True, ka)
+    if dist:                                   # identical initial weights on every rank
+        dist.broadcast(sess.param_tensor(), 0)
+    keepalive = []
+    b = sess.build_batch(bts, True, keepalive)
     sess._bind_stream()
     _cabi.check(L.icl_upload(sess.handle, C.byref(b)))
+    ns, nt, tm = C.c_int64(), C.c_int64(), C.c_int32()
+    _cabi.check(L.icl_batch_stats(sess.handle, C.byref(ns), C.byref(nt), C.byref(tm)))
+    n_seqs, n_tok, t_max = ns.value, nt.value, tm.value
+    n_examples = sum(h["B"] for h in wl["heads"])
+
+    def resident_step(i):
+        seed = 1000 + i
+        if dist:
+            _cabi.check(L.icl_run_resident(sess.handle, _cabi.OP_GRADS, KEEP_IN, KEEP, seed))
+            sess.allreduce_grads()
+            _cabi.check(L.icl_apply_update(sess.handle))
+        else:
+            _cabi.check(L.icl_run_resident(sess.handle, _cabi.OP_TRAIN, KEEP_IN, KEEP, seed))
+
     for i in range(warmup):
-        _cabi.check(L.icl_run_resident(sess.handle, _cabi.OP_TRAIN, KEEP_IN, KEEP, 1 + i))
+        resident_step(i)
+    torch.cuda.synchronize()
+    n0 = C.c_int64()
+    L.icl_kernel_launches(sess.handle, C.byref(n0))
+    stop = threading.Event()
+    th = None
+    if clocks is not None and rank == 0:
+        th = threading.Thread(target=sample_clocks, args=(stop, clocks), daemon=True)
+        th.start()
+    if dist:
+        dist.barrier()
     torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    phases = np.zeros(_cabi.N_PHASES)
+    wall0 = time.perf_counter()
     for i in range(steps):
+        ctx.flush.zero_()                       # L2 flush between timed iterations (untimed)
         ev[i][0].record()
-        _cabi.check(L.icl_run_resident(sess.handle, _cabi.OP_TRAIN, KEEP_IN, KEEP, 100 + i))
+        resident_step(warmup + i)
         ev[i][1].record()
+        ph = (C.c_float * _cabi.N_PHASES)()
+        _cabi.check(L.icl_phase_ms(sess.handle, ph))     # synchronises; CUDA-event time of each kernel group of this step
+        phases += np.array(list(ph))
     torch.cuda.synchronize()
-    ms = sum(a.elapsed_time(c) for a, c in ev) / steps
-    out = dict(workload="affinity512", baseline_config=wl["cfg"], unit="pairs/s", pairs_per_step=wl["B"],
-               train_resident=wl["B"] / (ms * 1e-3), train_resident_ms_per_step=ms)
+    if dist:
+        dist.barrier()
+    wall = time.perf_counter() - wall0
+    stop.set()          # the clocks are sampled during the device-timed region only
+    total_ms = sum(a.elapsed_time(b_) for a, b_ in ev)
+    n1 = C.c_int64()
+    L.icl_kernel_launches(sess.handle, C.byref(n1))
 
-    def timed(fn):
-        for _ in range(2):
-            fn()
+    def max_over_ranks(x):
+        if not dist:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    ms_per_step = max_over_ranks(total_ms) / steps
+    out = dict(wl=wl, n_seqs=n_seqs, n_tok=n_tok, t_max=t_max, n_examples=n_examples, ms_per_step=ms_per_step, ph_ms=phases / steps,
+               launches=n1.value - n0.value, wall_ms=1e3 * wall / steps, value=world * n_seqs / (ms_per_step * 1e-3))
+
+    # ---- end-to-end through the reference-facing API with host buffers: a rotation of N_ROT distinct host batches (a real
+    # training loop never re-feeds a cache-warm buffer), as many timed steps as the device-timed leg
+    N_ROT = 4
+    rot = [bts] + [make_batches(wl, seed0 + 101 * r) for r in range(1, N_ROT)]
+
+    def e2e_loop(batches_of, n, before=None):
+        for i in range(2):
+            run_train(core, sess, train_op, wl, batches_of(i))
         torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
         t0 = time.perf_counter()
-        for _ in range(steps):
-            fn()
+        for i in range(n):
+            run_train(core, sess, train_op, wl, batches_of(i))
         torch.cuda.synchronize()
-        return (time.perf_counter() - t0) / steps
-    dt = timed(lambda: core.run_op(sess, train_op, [bt], KEEP_IN, KEEP, "first_last_mention", [wl["task"]], [""], True))
-    out.update(train_e2e=wl["B"] / dt, train_e2e_ms_per_step=1e3 * dt)
-    bt_pred = make_batch(wl, 20171201, packed="rows", dedup=True)      # what get_pred_scores_mcc builds: distinct captions once
-    dt = timed(lambda: core.run_op(sess, proba_op, [bt_pred], 1.0, 1.0, "first_last_mention", [wl["task"]], [""], False))
-    out.update(predict_e2e=wl["B"] / dt, predict_e2e_ms_per_step=1e3 * dt, predict_distinct_captions=int(len(bt_pred["seq_lengths"])))
+        s = max_over_ranks(time.perf_counter() - t0)
+        h2d, d2h = C.c_int64(), C.c_int64()
+        L.icl_copy_bytes(sess.handle, C.byref(h2d), C.byref(d2h))
+        return dict(value=world * n_seqs * n / s, unit="captions/s", ms_per_step=1e3 * s / n, steps=n, h2d_bytes_per_step=h2d.value,
+                    d2h_bytes_per_step=d2h.value, distinct_host_batches=N_ROT)
+    out["e2e"] = e2e_loop(lambda i: rot[i % N_ROT], steps)
+    out["e2e"]["api"] = ("core.run_op(sess, train_op, [batch_tensors], ...) with host float32 NumPy buffers ('sentences' [S,50,300]); "
+                         "pipelined: the batch is packed into pinned memory and copied on a copy stream into the idle input set while the "
+                         "previous step computes; loss/accuracy of the previous step are read back (D2H) every step")
+    if e2e_variants:
+        var = {}
+        rot64 = [[dict(bt, sentences=bt["sentences"].astype(np.float64)) for bt in bl] for bl in rot]   # what nn_utils/data.py:375 builds
+        var["float64_feed"] = e2e_loop(lambda i: rot64[i % N_ROT], steps)
+        var["float64_feed"]["api"] = "same call, 'sentences' as float64 (np.zeros default of the reference's load_batch, nn_utils/data.py:375)"
+        del rot64
+        # host batch build inside the timed region: data.load_batch (vectorised) on fresh ids every step + run_op
+        h0 = wl["heads"][0]
+        if len(wl["heads"]) == 1:
+            dd = _corpus_for(h0, seed0)
+            ids = _ids_for(h0, dd, seed0)
+            nb = max(1, len(ids) // h0["B"])
+            for packed, key in ((False, "with_load_batch"), ("rows", "with_load_batch_corpus_cache")):
+                def fresh(i, packed=packed):
+                    lo = (i % nb) * h0["B"]
+                    return [nn_data.load_batch(ids[lo:lo + h0["B"]], dd, h0["task"], h0["C"], packed=packed)]
+                var[key] = e2e_loop(fresh, steps)
+                var[key]["api"] = ("data.load_batch(ids, data_dict, task, n_classes%s) + run_op(train_op) per step, both inside the timed region"
+                                   % (", packed='rows'" if packed else ""))
+        rows = [make_batches(wl, seed0 + 101 * r, packed="rows") for r in range(N_ROT)]
+        var["corpus_cache"] = e2e_loop(lambda i: rows[i % N_ROT], steps)
+        var["corpus_cache"]["api"] = ("same run_op call; load_batch(packed='rows'): int32 token rows into the device-resident token table "
+                                      "(icl_set_token_table) instead of the padded [S,T,300] host tensor")
+        out["e2e_variants"] = var
     sess.close()
     return out
 
 
-# ----------------------------------------------------------------------------------------------- our arm (B200)
+def summarise(name, r, pk, world, traffic=None):
+    """The by_config entry / the body of the headline line for one measured workload."""
+    wl = r["wl"]
+    roof, by_phase = roofline_of(wl, r["n_tok"], r["ph_ms"], pk, traffic)
+    from imagecaptionlearn_py_b200 import _cabi
+    d = dict(baseline_config=wl["cfg"], tasks=[h["task"] for h in wl["heads"]], batch_per_gpu=[h["B"] for h in wl["heads"]],
+             lstm_hidden=wl["H"], sequences_per_step_per_gpu=r["n_seqs"], tokens_per_step_per_gpu=r["n_tok"],
+             value=r["value"], unit="captions/s", ms_per_step=r["ms_per_step"],
+             examples_per_sec=world * r["n_examples"] / (r["ms_per_step"] * 1e-3),
+             e2e=dict(value=r["e2e"]["value"], unit="captions/s", ms_per_step=r["e2e"]["ms_per_step"],
+                      examples_per_sec=world * r["n_examples"] / (r["e2e"]["ms_per_step"] * 1e-3),
+                      h2d_bytes_per_step=r["e2e"]["h2d_bytes_per_step"], d2h_bytes_per_step=r["e2e"]["d2h_bytes_per_step"]),
+             phases_ms={n: float(v) for n, v in zip(_cabi.PHASES, r["ph_ms"])},
+             roofline=dict(kernel=roof["kernel"], phase=roof["phase"], bound=roof["bound"], frac=roof["frac"], achieved=roof["achieved"],
+                           peak=roof["peak"], unit=roof["unit"]),
+             gpu_launches_per_step=r["launches"] / max(1, r.get("steps", 1)))
+    if wl["heads"][0]["task"] == "affinity" and len(wl["heads"]) == 1:
+        d["unit_pairs"] = "mention-box pairs/s = examples_per_sec"
+    return d, roof, by_phase
+
+
+def affinity_predict_pairs_per_sec(local, steps=10):
+    """BASELINE.json's second metric on the PREDICT side: pairs/s end to end through get_pred_scores_mcc's batch path (keep 1.0, every
+    distinct caption of a batch encoded once, token rows + box rows into the device-resident tables)."""
+    import torch
+    from imagecaptionlearn_py_b200 import core
+    wl = WORKLOADS["affinity512"]
+    h = wl["heads"][0]
+    build_graph(wl)
+    proba_op = core.get_collection("predicted_proba")[0]
+    sess = core.Session(max_seq_len=T_PAD, device=local)
+    sess.ensure()
+    bt_pred = make_batch(wl, 20171201, packed="rows", dedup=True)
+    fn = lambda: core.run_op(sess, proba_op, [bt_pred], 1.0, 1.0, ENC, [h["task"]], [""], False)
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    sess.close()
+    return dict(predict_e2e=h["B"] / dt, unit="pairs/s", predict_e2e_ms_per_step=1e3 * dt, predict_distinct_captions=int(len(bt_pred["seq_lengths"])))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -248,6 +511,8 @@ def main():
     ap.add_argument("--workload", default="card2048", choices=sorted(WORKLOADS))
     ap.add_argument("--gemm", default="tf32", choices=["tf32", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-by-config", action="store_true")
+    ap.add_argument("--by-config-steps", type=int, default=8)
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     # stdout carries the ONE JSON line and nothing else: whatever a library writes to fd 1 during the run (NCCL prints its version
@@ -261,229 +526,92 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     import torch
-    from imagecaptionlearn_py_b200 import _cabi, core
-    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from imagecaptionlearn_py_b200 import _cabi
+    ctx = Ctx()
+    ctx.rank, ctx.world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    ctx.local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the hot path has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
+    torch.cuda.set_device(ctx.local)
+    ctx.dist = None
+    if ctx.world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", ctx.local))
+        ctx.dist = dist
+    ctx.gemm_mode = _cabi.GEMM_TCGEN05_TF32 if args.gemm == "tf32" else _cabi.GEMM_SIMT_FP32
+    ctx.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+    rank, world = ctx.rank, ctx.world
 
-    bt = make_batch(wl, 20171201 + 1000 * rank)
-    core.reset_default_graph()
-    core.set_random_seeds()
-    with core.variable_scope("bidirectional_lstm"):
-        core.setup_bidirectional_lstm(wl["H"], wl["data_norm"], n_embedding_width=E)
-    box_w = bt["box_embeddings"].shape[1] if "box_embeddings" in bt else bt["box_table"].shape[1] if "box_table" in bt else None
-    core.setup_core_architecture(wl["task"], "first_last_mention", wl["B"], wl["start"], wl["depth"], False, "relu", wl["C"],
-                                 wl["F"], box_embedding_width=box_w)
-    core.add_train_op(core.get_collection("loss")[0], LR, ADAM_EPS, CLIP)
-    sess = core.Session(max_seq_len=T_PAD, device=local, dist=bool(dist),
-                        gemm_mode=_cabi.GEMM_TCGEN05_TF32 if args.gemm == "tf32" else _cabi.GEMM_SIMT_FP32)
-    sess.ensure()
-    L = _cabi.lib()
-    train_op = core.get_collection("train_op")[0]
-    if dist:                                   # identical initial weights on every rank
-        flat = sess.param_tensor()
-        dist.broadcast(flat, 0)
-
-    # ---- resident-data throughput (`value`)
-    keepalive = []
-    b = sess.build_batch([bt], True, keepalive)
-    sess._bind_stream()
-    _cabi.check(L.icl_upload(sess.handle, C.byref(b)))
-    ns, nt, tm = C.c_int64(), C.c_int64(), C.c_int32()
-    _cabi.check(L.icl_batch_stats(sess.handle, C.byref(ns), C.byref(nt), C.byref(tm)))
-    n_seqs, n_tok, t_max = ns.value, nt.value, tm.value
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
-
-    def resident_step(i):
-        seed = 1000 + i
-        if dist:
-            _cabi.check(L.icl_run_resident(sess.handle, _cabi.OP_GRADS, KEEP_IN, KEEP, seed))
-            sess.allreduce_grads()          # heads' slice overlapped with the BPTT, LSTM slice after it
-            _cabi.check(L.icl_apply_update(sess.handle))
-        else:
-            _cabi.check(L.icl_run_resident(sess.handle, _cabi.OP_TRAIN, KEEP_IN, KEEP, seed))
-
-    for i in range(args.warmup):
-        resident_step(i)
-    torch.cuda.synchronize()
-    n0 = C.c_int64()
-    L.icl_kernel_launches(sess.handle, C.byref(n0))
-    clk, stop = [], threading.Event()
-    th = threading.Thread(target=sample_clocks, args=(stop, clk), daemon=True)
-    if rank == 0:
-        th.start()
-    if dist:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    phases = np.zeros(_cabi.N_PHASES)
-    wall0 = time.perf_counter()
-    for i in range(args.steps):
-        flush.zero_()                           # L2 flush between timed iterations (untimed)
-        ev[i][0].record()
-        resident_step(args.warmup + i)
-        ev[i][1].record()
-        ph = (C.c_float * _cabi.N_PHASES)()
-        _cabi.check(L.icl_phase_ms(sess.handle, ph))     # synchronises; CUDA-event time of each kernel group of this step
-        phases += np.array(list(ph))
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
-    wall = time.perf_counter() - wall0
-    stop.set()          # the clocks are sampled during the device-timed region only: the host-driven e2e legs below run undisturbed
-    total_ms = sum(a.elapsed_time(b_) for a, b_ in ev)
-    n1 = C.c_int64()
-    L.icl_kernel_launches(sess.handle, C.byref(n1))
-    launches = n1.value - n0.value
-    if dist:
-        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = world * n_seqs / (ms_per_step * 1e-3)
-
-    # ---- end-to-end through the reference-facing API with host buffers (`e2e`)
-    e2e_steps = max(5, args.steps // 3)
-    for i in range(2):
-        core.run_op(sess, train_op, [bt], KEEP_IN, KEEP, "first_last_mention", [wl["task"]], [""], True)
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        core.run_op(sess, train_op, [bt], KEEP_IN, KEEP, "first_last_mention", [wl["task"]], [""], True)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if dist:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    h2d, d2h = C.c_int64(), C.c_int64()
-    L.icl_copy_bytes(sess.handle, C.byref(h2d), C.byref(d2h))
-
-    # ---- the same call with the corpus cache: the caption token rows stay resident in HBM and the
-    # batch_tensors dict carries int32 row numbers ('token_rows') instead of the [S,T,300] tensor
-    bt_rows = make_batch(wl, 20171201 + 1000 * rank, packed="rows")
-    for i in range(2):
-        core.run_op(sess, train_op, [bt_rows], KEEP_IN, KEEP, "first_last_mention", [wl["task"]], [""], True)
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        core.run_op(sess, train_op, [bt_rows], KEEP_IN, KEEP, "first_last_mention", [wl["task"]], [""], True)
-    torch.cuda.synchronize()
-    rows_s = time.perf_counter() - t0
-    if dist:
-        t = torch.tensor([rows_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        rows_s = float(t.item())
-    h2d_rows = C.c_int64()
-    L.icl_copy_bytes(sess.handle, C.byref(h2d_rows), C.byref(d2h))
+    clk = []
+    main_r = measure(args.workload, args.steps, args.warmup, ctx, clocks=clk, e2e_variants=True)
+    main_r["steps"] = args.steps
+    others = {}
+    if not args.no_by_config:
+        for name in BY_CONFIG:
+            if name != args.workload:
+                others[name] = measure(name, args.by_config_steps, 3, ctx)
+                others[name]["steps"] = args.by_config_steps
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)           # fallback: the profiling guide's sustained figure
-        tf32_peak = bf16_peak / 2.0                                       # kind::tf32 issues at half the kind::f16 rate
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        ph_ms = phases / args.steps
-        H = wl["H"]
-        # ALGORITHMIC work per step of each kernel group: FLOPs of the contraction and the bytes that must
-        # cross HBM once (fp32), per valid token and direction, x 2 directions
-        tok2 = 2.0 * n_tok
-        work = {   # phase: (flops, bytes, kernel, launches of that kernel per step)
-            "proj_gemm": (tok2 * 2 * E * 4 * H, tok2 * (E * 2 + 4 * H * 4), "k_gemm_tcgen05<0, 0, 256, 2, 1>", 2),   # fp16 x in, fp32 out
-            "rec_fwd": (tok2 * 2 * H * 4 * H, tok2 * (4 * H + 4 * H + 3 * H) * 4, "k_rec_fwd16", 1),      # Zx in; gates, c, h, TF32(h) out
-            # the BPTT is one launch pair (8-CTA clusters for the longest chains + 4-CTA clusters, concurrent): counted as one
-            "rec_bwd": (tok2 * 2 * H * 4 * H, tok2 * (4 * H + 3 * H + 4 * H) * 4, "k_bptt_cluster", 1),   # gates, c, c_prev, dH in; dZ out
-            "wgrad": (tok2 * 2 * (E + H) * 4 * H, tok2 * (E + H + 4 * H) * 4, "k_gemm_tcgen05<1, 1, 256, 4, 0>", 2)}
-        dom = max(work, key=lambda k: ph_ms[_cabi.PHASES.index(k)])     # the dominant kernel group of the step
-        name = dom
-        t_ms = float(ph_ms[_cabi.PHASES.index(dom)])
-        flops, nbytes, kernel, n_launch = work[dom]
-        t_tensor, t_hbm = flops / (tf32_peak * 1e12), nbytes / (hbm_peak * 1e9)
+        pk = peaks()
         traffic = None
-        try:       # DRAM bytes of that kernel from the committed `ncu --set full` capture of this workload (profiles/)
-            if args.workload == "card2048" and world == 1:
-                seen = set()
-                ents = json.load(open(os.path.join(ROOT, "profiles", "r1h_ncu_full_summary.json")))       # recurrences, gather, ... (final code)
-                if not any(e["kernel"].startswith(kernel) for e in ents):
-                    ents = json.load(open(os.path.join(ROOT, "profiles", "r1g_ncu_full_summary.json")))   # the GEMMs (unchanged since)
-                for e in ents:
-                    if e["kernel"].startswith(kernel) and (dom != "wgrad" or e["grid"].replace(" ", "") == "(5,5,5)"):
-                        if dom == "rec_bwd":                   # sum over the two concurrent launches of one step
-                            if e["kernel"] not in seen:
-                                traffic = (traffic or 0) + e["dram_bytes"]
-                                seen.add(e["kernel"])
-                        else:
-                            traffic = e["dram_bytes"]
+        try:       # DRAM bytes of the dominant kernel from the committed `ncu --set full` capture of this workload (profiles/)
+            if args.workload == "card2048":
+                for fn in ("r2_ncu_full_summary.json", "r1h_ncu_full_summary.json"):
+                    path = os.path.join(ROOT, "profiles", fn)
+                    if os.path.exists(path):
+                        ents = json.load(open(path))
+                        work = phase_work(wl, main_r["n_tok"])
+                        dom = max(work, key=lambda k: main_r["ph_ms"][_cabi.PHASES.index(k)])
+                        seen = {}
+                        for e in ents:
+                            if e["kernel"].startswith(work[dom][2]) and e["kernel"] not in seen:
+                                seen[e["kernel"]] = e["dram_bytes"]
+                        if seen:
+                            traffic = sum(seen.values())
                             break
         except Exception:
             pass
-        if t_hbm >= t_tensor:
-            roof = dict(kernel=kernel, phase=name, bound="hbm", unit="GB/s", peak=hbm_peak,
-                        achieved=nbytes / n_launch / (t_ms / n_launch * 1e-3) / 1e9)
-        else:
-            roof = dict(kernel=kernel, phase=name, bound="tensor", unit="TFLOP/s", peak=tf32_peak,
-                        achieved=flops / n_launch / (t_ms / n_launch * 1e-3) / 1e12)
-        roof.update(frac=roof["achieved"] / roof["peak"], traffic=traffic, launches_per_step=n_launch,
-                    ms_per_launch=t_ms / n_launch, algorithmic_bytes_per_launch=nbytes / n_launch, algorithmic_flops_per_launch=flops / n_launch,
-                    tensor_frac=flops / (t_ms * 1e-3) / 1e12 / tf32_peak, hbm_frac=nbytes / (t_ms * 1e-3) / 1e9 / hbm_peak,
-                    peak_source=("MEASURED_PEAKS.json: hbm_gbs; bf16_tflops_sustained / 2 for kind::tf32" if peaks
-                                 else "fallback 6650 GB/s, 1400/2 TFLOP/s"),
-                    note="time = CUDA events around the kernel group on its launch stream (icl_phase_ms), averaged over the timed steps")
-        # every kernel group against both roofs (same algorithmic work / CUDA-event time as `roofline` above)
-        tpeak = dict(proj_gemm=bf16_peak, rec_fwd=bf16_peak, rec_bwd=tf32_peak, wgrad=tf32_peak)    # kind::f16 / kind::tf32 operands
-        by_phase = {}
-        for k, w in work.items():
-            ms_k = float(ph_ms[_cabi.PHASES.index(k)])
-            if ms_k > 0:
-                by_phase[k] = dict(kernel=w[2], ms=ms_k, hbm_frac=w[1] / (ms_k * 1e-3) / 1e9 / hbm_peak,
-                                   tensor_frac=w[0] / (ms_k * 1e-3) / 1e12 / tpeak[k], tensor_peak_tflops=tpeak[k],
-                                   bound="hbm" if w[1] / (hbm_peak * 1e9) >= w[0] / (tpeak[k] * 1e12) else "tensor")
-        step_flops = flops_per_token(H) * n_tok
-        line = dict(metric="bilstm_train_captions_per_sec", value=value, unit="captions/s", n_gpus=world, steps=args.steps,
+        body, roof, by_phase = summarise(args.workload, main_r, pk, world, traffic)
+        if traffic is not None:
+            roof["traffic_source"] = "profiles/: dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full capture (N=1, card2048)"
+        H = wl["H"]
+        step_flops = flops_per_token(H) * main_r["n_tok"]
+        ms_per_step = main_r["ms_per_step"]
+        line = dict(metric="bilstm_train_captions_per_sec", value=main_r["value"], unit="captions/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="tf32" if args.gemm == "tf32" else "f32", data="synthetic",
-                    config=dict(workload=args.workload, baseline_config=wl["cfg"], task=wl["task"], batch_per_gpu=wl["B"],
-                                global_batch=wl["B"] * world, lstm_hidden=H, embed=E, padded_T=T_PAD, t_max=t_max,
-                                tokens_per_step_per_gpu=n_tok, keep_prob=[KEEP_IN, KEEP], clip_norm=CLIP,
+                    config=dict(workload=args.workload, baseline_config=wl["cfg"], task=wl["heads"][0]["task"], batch_per_gpu=wl["heads"][0]["B"],
+                                global_batch=wl["heads"][0]["B"] * world, lstm_hidden=H, embed=E, padded_T=T_PAD, t_max=main_r["t_max"],
+                                tokens_per_step_per_gpu=main_r["n_tok"], keep_prob=[KEEP_IN, KEEP], clip_norm=CLIP,
                                 parallelism="dp%d" % world, l2="flushed between timed steps (256 MiB memset, untimed)",
-                                tokens_per_sec=world * n_tok / (ms_per_step * 1e-3),
+                                tokens_per_sec=world * main_r["n_tok"] / (ms_per_step * 1e-3),
                                 bilstm_tflops=step_flops / (ms_per_step * 1e-3) / 1e12,
-                                wall_ms_per_step_incl_flush=1e3 * wall / args.steps),
-                    phases_ms={n: float(v) for n, v in zip(_cabi.PHASES, ph_ms)}, roofline=roof, roofline_by_phase=by_phase,
-                    e2e=dict(value=world * n_seqs * e2e_steps / e2e_s, unit="captions/s", h2d_bytes_per_step=h2d.value,
-                             d2h_bytes_per_step=d2h.value, ms_per_step=1e3 * e2e_s / e2e_steps, steps=e2e_steps,
-                             api="core.run_op(sess, train_op, [batch_tensors], ...) with host float32 NumPy buffers; pipelined: the batch is "
-                                 "packed into pinned memory and copied on a copy stream into the idle input set while the previous "
-                                 "step computes, loss/accuracy of the previous step are read back (D2H) every step; the packing threads round the "
-                                 "rows to fp16 (what the device's tensor-core operands keep anyway), so the copy is 2 bytes per element"),
-                    e2e_resident_corpus=dict(value=world * n_seqs * e2e_steps / rows_s, unit="captions/s", ms_per_step=1e3 * rows_s / e2e_steps,
-                                             h2d_bytes_per_step=h2d_rows.value, d2h_bytes_per_step=d2h.value,
-                                             api="same run_op call; load_batch(packed='rows'): int32 token rows into the device-resident "
-                                                 "token table (icl_set_token_table) instead of the padded [S,T,300] host tensor"),
-                    gpu_launches=launches, clocks=clocks_summary(clk))
-        if world == 1 and args.workload == "card2048":
-            sess.close()
-            line["mention_box_pairs_per_sec"] = affinity_pairs_per_sec(local)
+                                wall_ms_per_step_incl_flush=main_r["wall_ms"]),
+                    phases_ms=body["phases_ms"], roofline=roof, roofline_by_phase=by_phase,
+                    e2e=main_r["e2e"], e2e_variants=main_r.get("e2e_variants"),
+                    gpu_launches=main_r["launches"], clocks=clocks_summary(clk))
+        if "corpus_cache" in (main_r.get("e2e_variants") or {}):
+            line["e2e_resident_corpus"] = main_r["e2e_variants"]["corpus_cache"]
+        if others:
+            line["by_config"] = {}
+            for name, r in others.items():
+                line["by_config"][name] = summarise(name, r, pk, world)[0]
+            if "affinity512" in others:
+                a = line["by_config"]["affinity512"]
+                line["mention_box_pairs_per_sec"] = dict(workload="affinity512", baseline_config=WORKLOADS["affinity512"]["cfg"], unit="pairs/s",
+                                                         pairs_per_step_per_gpu=512, train_resident=a["examples_per_sec"],
+                                                         train_resident_ms_per_step=a["ms_per_step"], train_e2e=a["e2e"]["examples_per_sec"],
+                                                         train_e2e_ms_per_step=a["e2e"]["ms_per_step"])
+                if world == 1:
+                    line["mention_box_pairs_per_sec"].update(affinity_predict_pairs_per_sec(ctx.local))
         if world == 1 and not args.no_cpu_baseline:        # rank 0 at N=1 only: the other ranks would idle behind it
-            line["cpu_baseline"] = {k: v for k, v in cpu_sample(wl, min(wl["B"], 512), 3, 2, target_s=12.0).items()
+            line["cpu_baseline"] = {k: v for k, v in cpu_sample(wl, min(wl["heads"][0]["B"], 512), 3, 2, target_s=12.0).items()
                                     if k in ("value", "unit", "cores", "kind", "sample")}
         _JSON_OUT.write(json.dumps(line) + "\n"); _JSON_OUT.flush()
-    sess.close()
-    if dist:
-        dist.destroy_process_group()
+    if ctx.dist:
+        ctx.dist.barrier()
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

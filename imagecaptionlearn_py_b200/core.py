@@ -247,13 +247,35 @@ class Session(object):
             self.initialize()
         else:
             self.load_state(state)
+        self._set_loss_weights(None)
+
+    def _world(self):
+        if not self.dist:
+            return 1
+        import torch.distributed as td
+        return td.get_world_size()
+
+    def _set_loss_weights(self, base):
+        """d joint / d loss_t per head (`base`, None = 1) times the data-parallel factor: a `weighted_classes` head's loss is the
+        MEAN over its local batch (core.py:244-267 as executed), so the SUM all-reduce over N ranks must carry 1/N of each rank's
+        gradient to equal the gradient of the global-batch mean; summed-CE heads need no factor."""
+        n, world = len(self.graph.heads), self._world()
+        w = [1.0 if base is None else float(base[i]) for i in range(n)]
+        if world > 1:
+            w = [w[i] / world if self.graph.heads[i]["weighted"] else w[i] for i in range(n)]
+        if base is None and all(x == 1.0 for x in w):
+            _cabi.check(_cabi.lib().icl_set_loss_weights(self.handle, None))
+        else:
+            _cabi.check(_cabi.lib().icl_set_loss_weights(self.handle, (C.c_float * n)(*w)))
 
     def ensure(self, T=None):
         if T is not None and T > self.max_seq_len:
             state = self.state_dict() if self.handle is not None else None
+            slot = self._slot
             self.close()
             self.max_seq_len = int(T)
             self._create(state)
+            self.set_optimizer_slot(slot)          # _create starts on slot 0: the `alternate` scheme had already selected one
         elif self.handle is None:
             self._create()
 
@@ -296,10 +318,11 @@ class Session(object):
         mixer's own gradients (dW[t,j] = loss_t, db_j = 1) take part in the global-norm clip and get the same TF-Adam step."""
         L = _cabi.lib()
         g = self.graph
+        self.ensure(max((bt["sentences"].shape[1] if "sentences" in bt else int(np.max(bt["seq_lengths"])))
+                        for bt in batch_tensor_list))
         jv = self._joint()
         n = len(g.heads)
-        w = (C.c_float * n)(*[float(x) for x in jv["W"].sum(1)])
-        _cabi.check(L.icl_set_loss_weights(self.handle, w))
+        self._set_loss_weights(jv["W"].sum(1))
         keepalive = []
         b = self.build_batch(batch_tensor_list, True, keepalive)
         self._bind_stream()
@@ -320,6 +343,9 @@ class Session(object):
             t = torch.tensor(losses, device="cuda:%d" % self.device)
             td.all_reduce(t, op=td.ReduceOp.SUM)
             losses = t.cpu().numpy()
+            for i, h in enumerate(g.heads):                      # mean-CE heads: the global-batch mean, not the sum of local means
+                if h["weighted"]:
+                    losses[i] /= td.get_world_size()
         dW = np.repeat(losses[:, None], n, 1).astype(np.float32)
         db = np.ones((1, n), np.float32)
         gn = C.c_float()
@@ -334,7 +360,7 @@ class Session(object):
             jv["m" + name] = (0.9 * jv["m" + name] + 0.1 * gs).astype(np.float32)
             jv["v" + name] = (0.999 * jv["v" + name] + 0.001 * gs * gs).astype(np.float32)
             jv[name] = (jv[name] - lr_t * jv["m" + name] / (np.sqrt(jv["v" + name]) + tr["eps"])).astype(np.float32)
-        _cabi.check(L.icl_set_loss_weights(self.handle, None))
+        self._set_loss_weights(None)
         self.last_train_stats = [dict(loss=np.float32(outs[i].loss), accuracy=np.float32(outs[i].accuracy)) for i in range(n)]
         return losses
 
@@ -407,16 +433,42 @@ class Session(object):
                 st[name], st["adam_m/" + name], st["adam_v/" + name] = jv[key].copy(), jv["m" + key].copy(), jv["v" + key].copy()
         return st
 
-    def load_state(self, st):
+    @staticmethod
+    def _alias(name):
+        """'<s>/<s>/rest' <-> '<s>/rest': checkpoints written before the multitask heads carried TensorFlow's doubled scope."""
+        p = name.split("/")
+        if len(p) >= 3 and p[0] == p[1]:
+            return "/".join(p[1:])
+        return None
+
+    def load_state(self, st, strict=True):
+        """Loads parameters (+ Adam state of every optimizer slot) by TF variable name.  strict (default): every model parameter
+        must be present and every key must be recognised -- a checkpoint whose names do not match raises instead of silently
+        leaving heads at their random initialisation.  strict=False restores what matches and returns (missing, unexpected)."""
         info = self.param_info()
+        st = dict(st)
+        canon = {self._alias(n): n for n, _, _, _ in info if self._alias(n) is not None}
+        for k in list(st.keys()):                                # accept the single-scope spelling of older files
+            pre, name = (k.split("/", 1)[0] + "/", k.split("/", 1)[1]) if k.startswith(("adam_m", "adam_v")) and "/" in k else ("", k)
+            if name in canon and pre + canon[name] not in st:
+                st[pre + canon[name]] = st.pop(k)
+        used = set()
         if self.graph.joint == "weighted_joint":
             for name in self.JOINT_NAMES:
                 for kind, pre in ((0, ""), (2, "adam_m/"), (3, "adam_v/")):
                     if pre + name in st:
                         self.set_tensor(name, st[pre + name], kind)
+                        used.add(pre + name)
+        missing = []
         for n, r, c, _ in info:
             if n in st:
-                self.set_tensor(n, np.asarray(st[n]).reshape(r, c), 0)
+                a = np.asarray(st[n])
+                if a.size != r * c:
+                    raise ValueError("load_state: %r has %d elements, the model's tensor is [%d, %d]" % (n, a.size, r, c))
+                self.set_tensor(n, a.reshape(r, c), 0)
+                used.add(n)
+            else:
+                missing.append(n)
         keep = self._slot
         slots = sorted(set([0] + [int(k.split("@")[1]) for k in st if k.startswith("adam_step@")]))
         for s in slots:
@@ -425,14 +477,25 @@ class Session(object):
                 continue
             self.set_optimizer_slot(s)
             for n, r, c, _ in info:
-                if "adam_m%s/%s" % (sfx, n) in st:
-                    self.set_tensor(n, np.asarray(st["adam_m%s/%s" % (sfx, n)]).reshape(r, c), 2)
-                    self.set_tensor(n, np.asarray(st["adam_v%s/%s" % (sfx, n)]).reshape(r, c), 3)
+                km, kv = "adam_m%s/%s" % (sfx, n), "adam_v%s/%s" % (sfx, n)
+                if km in st and kv in st:
+                    self.set_tensor(n, np.asarray(st[km]).reshape(r, c), 2)
+                    self.set_tensor(n, np.asarray(st[kv]).reshape(r, c), 3)
+                    used.update((km, kv))
             _cabi.check(_cabi.lib().icl_set_step(self.handle, int(st["adam_step" + sfx])))
+            used.add("adam_step" + sfx)
         self.set_optimizer_slot(keep)
+        unexpected = sorted(k for k in st if k not in used)
+        if strict and (missing or unexpected):
+            raise KeyError("load_state: the checkpoint does not match the graph: %d model tensors missing (%s), %d unrecognised keys "
+                           "(%s); pass strict=False to restore the intersection" %
+                           (len(missing), ", ".join(missing[:4]), len(unexpected), ", ".join(unexpected[:4])))
+        return missing, unexpected
 
     # -- execution ---------------------------------------------------------------------------------------------------
     def _bind_stream(self):
+        if os.environ.get("ICL_NO_TORCH_STREAM"):       # tools run under compute-sanitizer: the library's default stream, no torch
+            return
         try:
             import torch
             if torch.cuda.is_available():
@@ -519,10 +582,30 @@ class Session(object):
                 T = max(T, s.shape[1])
             off += len(ln)
             task = g.heads[i]["task"]
+            hd = g.heads[i]
+            Bh, E = hd["batch_size"], g.lstm["E"]
+
+            def want(key, arr, shape):
+                # the reference's placeholders have static shapes (core.py:348,476): a wrong batch raises there, and must not
+                # become an out-of-bounds host read in icl_upload here
+                if tuple(np.shape(arr)) != tuple(shape):
+                    raise ValueError("run_op: %r of task %r has shape %r, the graph was built for %r" %
+                                     (key, task, tuple(np.shape(arr)), tuple(shape)))
+            n_sent = Bh * (2 if task == "rel_cross" else 1)
+            if "sentences" in bt and not packed:
+                if len(ln) > n_sent or s.ndim != 3 or s.shape[0] != len(ln) or s.shape[2] != E:
+                    raise ValueError("run_op: 'sentences' of task %r has shape %r for %d lengths; the graph takes at most [%d, T, %d]" %
+                                     (task, tuple(s.shape), len(ln), n_sent, E))
+            else:
+                if len(ln) > n_sent:
+                    raise ValueError("run_op: task %r feeds %d sequences, the graph was built for %d" % (task, len(ln), n_sent))
+                n_tok = int(np.sum(ln))
+                want("token_rows" if by_rows else "sentences_packed", s, (n_tok,) if by_rows else (n_tok, E))
             idxs = []
             for k, name in enumerate(_cabi.INDEX_ORDER):
                 if name in bt:
                     a = _cabi.as_supported(bt[name])
+                    want(name, a, (Bh, 3))
                     idxs.append(a)
                 else:
                     idxs.append(None)
@@ -535,24 +618,26 @@ class Session(object):
                     hb.idx[k] = a.ctypes.data
                     hb.idx_dtype = _cabi.dtype_code(a)
 
-            def put(field, key):
+            def put(field, key, width):
                 if key in bt and bt[key] is not None:
                     a = _cabi.as_supported(bt[key])
+                    want(key, a, (Bh, width))
                     keepalive.append(a)
                     setattr(hb, field, a.ctypes.data)
                     setattr(hb, field + "_dtype", _cabi.dtype_code(a))
-            put("feats", "ij_feats" if "rel" in task else "m_feats")
+            put("feats", "ij_feats" if "rel" in task else "m_feats", hd["F"])
             if task == "affinity":
                 if "box_rows" in bt:                       # rows of the device-resident box table instead of [B, 4096] floats
                     self.set_box_table(bt["box_table"])
                     a = np.ascontiguousarray(bt["box_rows"], dtype=np.int32)
+                    want("box_rows", a, (Bh,))
                     keepalive.append(a)
                     hb.box_rows = a.ctypes.data
                 else:
-                    put("box", "box_embeddings")
-                put("bfeats", "b_feats")
+                    put("box", "box_embeddings", hd["box_width"])
+                put("bfeats", "b_feats", hd["n_box_feats"])
             if include_labels:
-                put("labels", "labels")
+                put("labels", "labels", hd["n_classes"])
         if len(sents) == 1:
             x = _cabi.as_supported(sents[0])
             ln = _cabi.as_supported(lens[0])

@@ -515,6 +515,58 @@ __global__ void k_softmax_ce(const float* __restrict__ a, int K, const float* __
   if (y) { row_loss[b] = loss * scale; row_correct[b] = (am == ay) ? 1.0f : 0.0f; }
 }
 
+// Softmax layer backward (core.py:202-232 in reverse), ONE kernel: with dl = dlogits [B,C] (C = 2..32 classes),
+//   dz_{L-1}[b,k] = (sum_c dl[b,c] W[k,c]) * dropout-mask/keep * act'(...)   (the EPI_DACT epilogue of the hidden layers' GEMMs)
+//   dW[k,c] = sum_b a[b,k] dl[b,c],   db[c] = sum_b dl[b,c]
+// A C-column product is bandwidth work, not a tensor-core tile (and C = 2 cannot even be a TMA row pitch): every block takes
+// SMB_ROWS examples, thread k owns hidden unit k (coalesced along k), the per-block partial sums of dW / db go to a scratch
+// buffer and the LAST block to arrive (arrival counter) adds them up in block order -- deterministic, no float atomics.
+constexpr int SMB_ROWS = 64, SMB_THREADS = 128;
+__global__ void __launch_bounds__(SMB_THREADS) k_softmax_bwd(const float* __restrict__ a, const float* __restrict__ dl,
+                                                             const float* __restrict__ W, int B, int K, int C, Epilogue e,
+                                                             float* __restrict__ dz, float* __restrict__ dW, float* __restrict__ db,
+                                                             float* part, unsigned* count) {
+  extern __shared__ float sm_dyn[];
+  float* s_dl = sm_dyn;                         // [SMB_ROWS][C]
+  float* s_W = sm_dyn + SMB_ROWS * C;           // [K][C]
+  __shared__ bool s_last;
+  const int r0 = blockIdx.x * SMB_ROWS, nr = min(SMB_ROWS, B - r0);
+  for (int i = threadIdx.x; i < nr * C; i += blockDim.x) s_dl[i] = dl[(long)r0 * C + i];
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x) s_W[i] = W[i];
+  __syncthreads();
+  const size_t pstride = (size_t)(K + 1) * C;
+  float* mine = part + blockIdx.x * pstride;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    for (int r = 0; r < nr; r++) {
+      float v = 0.0f;
+      for (int c = 0; c < C; c++) v = fmaf(s_dl[r * C + c], s_W[k * C + c], v);
+      dz[(long)(r0 + r) * K + k] = epilogue_apply(e, v, r0 + r, k, K);
+    }
+    for (int c = 0; c < C; c++) {
+      float acc = 0.0f;
+      for (int r = 0; r < nr; r++) acc = fmaf(a[(long)(r0 + r) * K + k], s_dl[r * C + c], acc);
+      mine[k * C + c] = acc;
+    }
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.0f;
+    for (int r = 0; r < nr; r++) acc += s_dl[r * C + c];
+    mine[K * C + c] = acc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(count, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int i = threadIdx.x; i < (int)pstride; i += blockDim.x) {
+    float acc = 0.0f;
+    for (unsigned b = 0; b < gridDim.x; b++) acc += __ldcg(part + b * pstride + i);
+    if (i < K * C) dW[i] = acc; else db[i - K * C] = acc;
+  }
+  if (threadIdx.x == 0) *count = 0u;            // ready for the next launch
+}
+
 // deterministic single-block sums: block 0 sums v0 into out[0], block 1 sums v1 into out[1] divided by mean_div
 __global__ void k_reduce_sum2(const float* __restrict__ v0, const float* __restrict__ v1, int n, float* out, float mean_div1) {
   __shared__ double sh[256];

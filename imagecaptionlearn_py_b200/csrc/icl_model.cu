@@ -69,6 +69,10 @@ struct InSet {
 struct Head {
   icl_head_config c;
   int D0 = 0, D0g = 0;               // input width; width of the prefix that carries gathered LSTM columns
+  int ldbi = 0, lddbi = 0;           // row pitches of bi / dbi: D0 / D0g rounded up to 4 floats.  n_mention_feats is data-defined
+                                     // (nn_utils/data.py:187), so D0 = 4H + F need not be a multiple of 4, and a TMA tensor map needs
+                                     // 16-byte row pitches -- with a dense pitch layer 1 (the largest head GEMM) fell back to SIMT
+  float* sm_part = nullptr; unsigned* sm_count = nullptr;   // softmax-layer backward: per-block partial sums + arrival counter
   std::vector<int> dims;             // D0, w1..wL, C
   std::vector<int> pW, pB;           // param indices per layer (L hidden + softmax)
   SlotTable slots;                   // device pointers filled at create
@@ -549,7 +553,7 @@ extern "C" void icl_destroy(icl_model* m) {
   F(m->Hp16[0]); F(m->Hp16[1]); F(m->Wp16[0]); F(m->Wp16[1]); F(m->X16[0]); F(m->X16[1]); F(m->Wih16[0]); F(m->Wih16[1]);
   F(m->d_partial); F(m->d_gnorm);
   for (auto& h : m->heads) {
-    F(h.bi); F(h.dbi); F(h.dA); F(h.dBuf); for (auto a : h.act) F(a); for (auto a : h.dzb) F(a);
+    F(h.bi); F(h.dbi); F(h.dA); F(h.dBuf); F(h.sm_part); F(h.sm_count); for (auto a : h.act) F(a); for (auto a : h.dzb) F(a);
     F(h.proba); F(h.dlogits); F(h.row_loss); F(h.row_correct); F(h.scalars); F(h.pred);
     if (h.h_out) cudaFreeHost(h.h_out);
     if (h.h_pred) cudaFreeHost(h.h_pred);
@@ -613,10 +617,14 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
     h.slots.n_slots = (int)plan.size();
     h.slot_index_id = plan;
     h.D0 = col;
+    h.ldbi = (h.D0 + 3) / 4 * 4; h.lddbi = (std::max(h.D0g, 1) + 3) / 4 * 4;
     h.dims.push_back(h.D0);
     for (int k = 0; k < h.c.n_hidden; k++) h.dims.push_back(h.c.widths[k]);
     h.dims.push_back(h.c.n_classes);
-    std::string pre = h.c.scope[0] ? std::string(h.c.scope) + "/" : "";
+    // multitask heads: setup_ffw / the softmax layer open tf.variable_scope(scope_name + "hdn_k") with scope_name = "<task>/" while
+    // ALREADY inside `with tf.variable_scope(task)` (core.py:166-172,497 under icl_multitask_lstm.py:62), and TF nests a string
+    // scope under the current one: the variables of a checkpoint are "<task>/<task>/hdn_k/Variable"
+    std::string pre = h.c.scope[0] ? std::string(h.c.scope) + "/" + std::string(h.c.scope) + "/" : "";
     for (int k = 0; k <= h.c.n_hidden; k++) {
       std::string sc = k < h.c.n_hidden ? pre + "hdn_" + std::to_string(k + 1) : pre + "softmax";
       h.pW.push_back(add_param(m, sc + "/Variable", h.dims[k], h.dims[k + 1]));
@@ -685,7 +693,12 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
     int B = h.c.batch_size, C = h.c.n_classes;
     int maxw = 0;
     for (int k = 1; k <= h.c.n_hidden; k++) maxw = std::max(maxw, h.dims[k]);
-    CKD(dmalloc(&h.bi, (size_t)B * h.D0)); CKD(dmalloc(&h.dbi, (size_t)B * std::max(h.D0g, 1)));
+    CKD(dmalloc(&h.bi, (size_t)B * h.ldbi)); CKD(dmalloc(&h.dbi, (size_t)B * h.lddbi));
+    CKD(cudaMemset(h.bi, 0, (size_t)B * h.ldbi * 4)); CKD(cudaMemset(h.dbi, 0, (size_t)B * h.lddbi * 4));
+    {
+      const int Kl = h.dims[h.c.n_hidden], nb = (B + SMB_ROWS - 1) / SMB_ROWS;
+      CKD(dmalloc(&h.sm_part, (size_t)nb * (Kl + 1) * C)); CKD(dmalloc(&h.sm_count, 1)); CKD(cudaMemset(h.sm_count, 0, 4));
+    }
     CKD(dmalloc(&h.dA, (size_t)B * maxw)); CKD(dmalloc(&h.dBuf, (size_t)B * maxw));
     for (int k = 1; k <= h.c.n_hidden; k++) { float* a; CKD(dmalloc(&a, (size_t)B * h.dims[k])); h.act.push_back(a); }
     for (int k = 1; k <= h.c.n_hidden; k++) { float* a; CKD(dmalloc(&a, (size_t)B * h.dims[k])); h.dzb.push_back(a); }
@@ -1145,13 +1158,13 @@ static int heads_forward(icl_model* m, float keep, uint64_t seed) {
     Head& h = m->heads[hi];
     if (!h.active) continue;
     int B = h.c.batch_size, C = h.c.n_classes, L = h.c.n_hidden;
-    k_gather_concat<<<dim3(B, h.slots.n_slots), 96, 0, st>>>(h.slots, m->Hx[0], m->Hx[1], mk_layout(m), H, m->T_cap, h.D0, mk_drop(seed, 0, keep, m->seq_gid0),
+    k_gather_concat<<<dim3(B, h.slots.n_slots), 96, 0, st>>>(h.slots, m->Hx[0], m->Hx[1], mk_layout(m), H, m->T_cap, h.ldbi, mk_drop(seed, 0, keep, m->seq_gid0),
                                       m->round_ops, h.bi);
     LAUNCHED(m);
     const float* in = h.bi;
     for (int k = 0; k < L; k++) {
       const Param& pw = m->params[h.pW[k]];
-      GemmArgs g = mk_gemm(in, h.dims[k], wbase(m) + pw.off, h.dims[k + 1], h.act[k], h.dims[k + 1], B, h.dims[k + 1], h.dims[k]);
+      GemmArgs g = mk_gemm(in, k == 0 ? h.ldbi : h.dims[k], wbase(m) + pw.off, h.dims[k + 1], h.act[k], h.dims[k + 1], B, h.dims[k + 1], h.dims[k]);
       g.epi.mode = EPI_BIAS_ACT_DROP; g.epi.bias = m->P + m->params[h.pB[k]].off; g.epi.act = h.c.activation;
       g.epi.drop = mk_drop(seed, STREAM_HEAD + (uint32_t)hi * 8 + k, keep, m->ex_gid0);
       CKI(gemm(m, st, false, true, g));
@@ -1202,15 +1215,27 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
     // Layer by layer from the softmax down: the chain dz_k -> dz_{k-1} = (dz_k W_k^T) * act' stays on the main stream; the weight
     // and bias gradients of layer k only need dz_k, so they run on the aux stream concurrently with the rest of the chain
     // (joined before the weight-gradient phase of the LSTM / the update).
-    const float* dz = h.dlogits;       // gradient w.r.t. the pre-activation of layer k+1 (softmax layer first)
-    for (int k = L; k >= 0; k--) {
+    // The softmax layer (N = n_classes, 2..12 columns) never goes near a GEMM: ONE fused kernel computes its weight and bias
+    // gradients and dz of the last hidden layer (k_softmax_bwd, deterministic block partials reduced by the last block to arrive).
+    {
+      const Param &pw = m->params[h.pW[L]], &pb = m->params[h.pB[L]];
+      const int Kl = h.dims[L], C = h.dims[L + 1], nb = (B + SMB_ROWS - 1) / SMB_ROWS;
+      Epilogue e; memset(&e, 0, sizeof(e));
+      e.mode = EPI_DACT; e.act = h.c.activation; e.aux = h.act[L - 1]; e.ldaux = Kl;
+      e.drop = mk_drop(seed, STREAM_HEAD + (uint32_t)hi * 8 + (L - 1), keep, m->ex_gid0); e.round_out = m->round_ops;
+      k_softmax_bwd<<<nb, SMB_THREADS, (size_t)(SMB_ROWS * C + Kl * C) * 4, st>>>(h.act[L - 1], h.dlogits, m->P + pw.off, B, Kl, C, e, h.dzb[L - 1],
+                                                                                   m->G + pw.off, m->G + pb.off, h.sm_part, h.sm_count);
+      LAUNCHED(m);
+    }
+    const float* dz = h.dzb[L - 1];    // gradient w.r.t. the pre-activation of layer k+1
+    for (int k = L - 1; k >= 0; k--) {
       const float* in = k == 0 ? h.bi : h.act[k - 1];
       int din = h.dims[k], dout = h.dims[k + 1];
       const Param& pw = m->params[h.pW[k]];
       CK(cudaEventRecord(m->ev_dz[k], st));
       CK(cudaStreamWaitEvent(m->aux2, m->ev_dz[k], 0));
       // dW = in^T * dz   (contraction over the batch: both operands MN-major)
-      GemmArgs gw = mk_gemm(in, din, dz, dout, m->G + pw.off, dout, din, dout, B);
+      GemmArgs gw = mk_gemm(in, k == 0 ? h.ldbi : din, dz, dout, m->G + pw.off, dout, din, dout, B);
       CKI(gemm(m, m->aux2, true, true, gw, -1, 0, true));
       CKI(colsum(m, m->aux2, dz, B, dout, dout, m->G + m->params[h.pB[k]].off));
       m->heads_aux_pending = true;
@@ -1223,9 +1248,9 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
         CKI(gemm(m, st, false, false, gx));
         dz = h.dzb[k - 1];
       } else if (h.D0g > 0) {
-        GemmArgs gx = mk_gemm(dz, dout, wbase(m) + pw.off, dout, h.dbi, h.D0g, B, h.D0g, dout);
+        GemmArgs gx = mk_gemm(dz, dout, wbase(m) + pw.off, dout, h.dbi, h.lddbi, B, h.D0g, dout);
         CKI(gemm(m, st, false, false, gx));
-        k_scatter_spans<<<dim3(B, h.slots.n_slots), 96, 0, st>>>(h.slots, h.dbi, mk_layout(m), H, m->T_cap, h.D0g, mk_drop(seed, 0, keep, m->seq_gid0),
+        k_scatter_spans<<<dim3(B, h.slots.n_slots), 96, 0, st>>>(h.slots, h.dbi, mk_layout(m), H, m->T_cap, h.lddbi, mk_drop(seed, 0, keep, m->seq_gid0),
                                           m->dHout[0], m->dHout[1]);
         LAUNCHED(m);
       }
@@ -1627,7 +1652,7 @@ extern "C" int icl_get_lstm_outputs(icl_model* m, int dir, float* host) {
 extern "C" int icl_get_batch_input(icl_model* m, int head, float* host) {
   Head& h = m->heads[head];
   CK(cudaStreamSynchronize(m->stream));
-  CK(cudaMemcpy(host, h.bi, (size_t)h.c.batch_size * h.D0 * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy2D(host, (size_t)h.D0 * 4, h.bi, (size_t)h.ldbi * 4, (size_t)h.D0 * 4, h.c.batch_size, cudaMemcpyDeviceToHost));
   return 0;
 }
 extern "C" int icl_get_activation(icl_model* m, int head, int layer, float* host) {

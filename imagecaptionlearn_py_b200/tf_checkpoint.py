@@ -243,8 +243,10 @@ def write_bundle(prefix, tensors):
     return prefix
 
 
-# names of the Adam slots tf.train.AdamOptimizer creates next to each variable, and of its two accumulators
-def from_state_dict(st):
+# names of the Adam slots tf.train.AdamOptimizer creates next to each variable, and of its two accumulators.
+# TF 1.x initialises beta1_power / beta2_power to beta1 / beta2 and multiplies them by beta at the END of every apply
+# (AdamOptimizer._create_slots / _finish), so after t update steps a checkpoint holds beta ** (t + 1).
+def from_state_dict(st, beta1=0.9, beta2=0.999):
     """core.Session.state_dict() -> TF variable names (Adam slots as '<var>/Adam', '<var>/Adam_1', 'beta1_power', 'beta2_power')."""
     out = {}
     for k, v in st.items():
@@ -254,26 +256,45 @@ def from_state_dict(st):
             out[k[7:] + "/Adam_1"] = v
         elif k == "adam_step":
             t = int(v)
-            out["beta1_power"] = np.float32(0.9 ** t)
-            out["beta2_power"] = np.float32(0.999 ** t)
+            out["beta1_power"] = np.float32(beta1 ** (t + 1))
+            out["beta2_power"] = np.float32(beta2 ** (t + 1))
         elif "@" not in k.split("/")[0]:
             out[k] = v
     return out
 
 
-def to_state_dict(tensors):
-    """TF checkpoint variables -> the keys core.Session.load_state understands (Adam step recovered from beta1_power)."""
+def _steps_from_power(b, beta):
+    """t with beta ** (t + 1) == b, or None when b carries no information (0 after float32 underflow, or outside (0, 1))."""
+    if not (0.0 < b < 1.0):
+        return None
+    return max(0, int(round(np.log(b) / np.log(beta))) - 1)
+
+
+def to_state_dict(tensors, beta1=0.9, beta2=0.999):
+    """TF checkpoint variables -> the keys core.Session.load_state understands.  The Adam step count is recovered from
+    beta2_power (0.999 ** t stays a normal float32 for ~87 000 steps; 0.9 ** t underflows to 0 near t = 980), falling back to
+    beta1_power; when neither is usable the moments are restored with step 0 and a warning (bias correction restarts)."""
     st = {}
+    t2 = t1 = None
+    have_power = False
     for k, v in tensors.items():
         if k.endswith("/Adam"):
             st["adam_m/" + k[:-5]] = v
         elif k.endswith("/Adam_1"):
             st["adam_v/" + k[:-7]] = v
         elif k == "beta1_power":
-            b = float(np.asarray(v).reshape(-1)[0])
-            st["adam_step"] = np.int64(round(np.log(b) / np.log(0.9))) if 0 < b < 1 else np.int64(0)
+            have_power = True
+            t1 = _steps_from_power(float(np.asarray(v).reshape(-1)[0]), beta1)
         elif k == "beta2_power":
-            pass
+            have_power = True
+            t2 = _steps_from_power(float(np.asarray(v).reshape(-1)[0]), beta2)
         else:
             st[k] = v
+    if have_power:
+        t = t2 if t2 is not None else t1
+        if t is None:
+            import warnings
+            warnings.warn("TF checkpoint: beta1_power / beta2_power are not in (0, 1); Adam step count set to 0")
+            t = 0
+        st["adam_step"] = np.int64(t)
     return st

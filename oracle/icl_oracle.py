@@ -46,9 +46,16 @@ def lstm_names(direction):
     return base + "kernel", base + "bias"
 
 
+def scoped(scope, name):
+    """Name of head variable `name` ('hdn_1/Variable', ...) created under the task scope `scope` (see head_names)."""
+    return (scope + "/" + scope + "/" + name) if scope else name
+
+
 def head_names(scope, n_layers):
-    """TF variable names in creation order: hdn_k/Variable (W), hdn_k/Variable_1 (b), softmax/..."""
-    pre = (scope + "/") if scope else ""
+    """TF variable names in creation order: hdn_k/Variable (W), hdn_k/Variable_1 (b), softmax/...  Under a task scope
+    (icl_multitask_lstm.py:62) the prefix is DOUBLED: core.py:166-172 opens variable_scope("<task>/hdn_k") inside
+    variable_scope("<task>"), and TensorFlow nests it -> "<task>/<task>/hdn_k/Variable"."""
+    pre = (scope + "/" + scope + "/") if scope else ""
     names = []
     for k in range(1, n_layers + 1):
         names.append((pre + "hdn_%d/Variable" % k, pre + "hdn_%d/Variable_1" % k))

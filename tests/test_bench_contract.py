@@ -31,6 +31,17 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["gpu_launches"] == 0
 
 
+def test_reference_arm_uses_every_host_core_and_the_b200_arms_batch_under_torchrun():
+    """torchrun exports OMP_NUM_THREADS=1: the CPU arm must lift that limit itself (round 1's N>1 ratios were taken against a
+    single-threaded BLAS), and it runs the same batch per step as the B200 arm (2048 captions of card2048)."""
+    r = run(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+            env=dict(RANK="0", WORLD_SIZE="2", LOCAL_RANK="0", OMP_NUM_THREADS="1"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip())
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert d["config"]["batch_per_step"] == 2048 and d["config"]["batch_per_gpu"] == 2048
+
+
 def test_reference_arm_runs_on_rank_zero_only():
     r = run(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"], env=dict(RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
     assert r.returncode == 0 and r.stdout.strip() == ""

@@ -41,18 +41,43 @@ def _slice_problem(p, b, e):
     return q
 
 
-def _worker(rank, world, port, ret):
+def _shim_loss_weight(weighted):
+    """What core.Session hands icl_set_loss_weights for a one-head graph under the live process group (the C library is replaced
+    by a recorder: no GPU here)."""
+    from imagecaptionlearn_py_b200 import _cabi, core
+
+    class Rec(object):
+        w = None
+
+        def icl_set_loss_weights(self, handle, arr):
+            Rec.w = None if arr is None else [float(arr[i]) for i in range(1)]
+            return 0
+    g = core.Graph()
+    g.lstm = dict(n_hidden=4, data_norm=False, E=5)
+    g.heads = [dict(task="card", weighted=weighted)]
+    sess = core.Session(graph=g, dist=True)
+    real = _cabi.lib
+    _cabi.lib = lambda: Rec()
+    try:
+        sess._set_loss_weights(None)
+    finally:
+        _cabi.lib = real
+    return 1.0 if Rec.w is None else Rec.w[0]
+
+
+def _worker(rank, world, port, ret, weighted=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     td.init_process_group("gloo", rank=rank, world_size=world)
-    p = tiny_problem(seed=31, S=10, T=6, E=5, H=4, F=3, task="card", act="tanh", dropout=True)
+    p = tiny_problem(seed=31, S=10, T=6, E=5, H=4, F=3, task="card", act="tanh", dropout=True, weighted=weighted)
     b, e = D.shard_range(p["S"], rank, world)
     q = _slice_problem(p, b, e)
     f = O.model_forward(q["params"], q["cfg"], q["x"], q["lens"], [q["batch"]], q["keep_in"], q["keep"], q["masks"])
     g = O.model_backward(q["params"], q["cfg"], f, [q["batch"]])
     names = sorted(g)
-    flat = torch.from_numpy(np.concatenate([g[n].ravel() for n in names]))
+    lw = _shim_loss_weight(weighted)                  # d joint / d loss of the head, as the shim sets it on the device
+    flat = torch.from_numpy(np.concatenate([g[n].ravel() for n in names]) * lw)
     D.allreduce_sum_(flat)
-    loss = torch.tensor([float(f["loss"])], dtype=torch.float64)
+    loss = torch.tensor([float(f["loss"]) * lw], dtype=torch.float64)
     td.all_reduce(loss)
     if rank == 0:
         ret["flat"], ret["loss"], ret["names"] = flat.numpy().copy(), float(loss), names
@@ -69,6 +94,24 @@ def test_two_rank_sum_allreduce_equals_full_batch():
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     p = tiny_problem(seed=31, S=10, T=6, E=5, H=4, F=3, task="card", act="tanh", dropout=True)
+    f = O.model_forward(p["params"], p["cfg"], p["x"], p["lens"], [p["batch"]], p["keep_in"], p["keep"], p["masks"])
+    g = O.model_backward(p["params"], p["cfg"], f, [p["batch"]])
+    full = np.concatenate([g[n].ravel() for n in ret["names"]])
+    np.testing.assert_allclose(ret["flat"], full, rtol=1e-10, atol=1e-12)
+    assert abs(ret["loss"] - float(f["loss"])) < 1e-10
+
+
+def test_two_rank_weighted_classes_equals_full_batch_mean():
+    """weighted_classes as executed = MEAN cross-entropy (core.py:244-267): each rank's gradient is of its local mean, so the shim
+    gives that head the loss weight 1/world_size and the SUM all-reduce then equals the gradient of the global-batch mean."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, ret, True), nprocs=2, join=True)
+    p = tiny_problem(seed=31, S=10, T=6, E=5, H=4, F=3, task="card", act="tanh", dropout=True, weighted=True)
     f = O.model_forward(p["params"], p["cfg"], p["x"], p["lens"], [p["batch"]], p["keep_in"], p["keep"], p["masks"])
     g = O.model_backward(p["params"], p["cfg"], f, [p["batch"]])
     full = np.concatenate([g[n].ravel() for n in ret["names"]])

@@ -1,0 +1,192 @@
+"""Parity at BASELINE.json's FULL shapes for the configs other than configs[1] (that one: tests/test_gpu_full_size.py):
+
+    C1  icl_core_lstm nonvis, B = 512, H = 300, widths [512,256,128]                       (also with dropout 0.5/0.5)
+    C3  icl_relation_lstm intra / cross, config/lstm_{intra,cross}_params.config:96: H = 200, [1024,512,256,128], data_norm,
+        B = 512 (cross: S = 1024 sentences)
+    C4  icl_affinity_lstm, B = 512 mention-box pairs, 4096-d box rows: D0 = 4*300 + 256 + 4096 = 5552
+    C5  icl_multitask_lstm simple_joint: five heads (icl_multitask_lstm.py:22 order), B = 512 each, S = 3072, H = 200
+
+Every one runs ONE forward + backward through the C-ABI in product mode (tcgen05 TF32 / fp16 operands) on the synthetic
+F30kE-shaped batch bench.py measures, and is compared with the fp64 oracle on the same inputs and weights: loss, probabilities,
+predictions on clear margins, and EVERY gradient tensor -- per tensor (max error over the tensor's max, north_star's 1e-3) and
+per row (rarely-hit feature rows and small rows must be right relative to THEIR OWN scale, not the tensor's).  The measured
+errors are written to gpurun_out/r2_config_parity.json when that directory exists."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_FWD = 1e-3          # probabilities, loss (relative)
+TOL_GRAD = 1e-3         # max |got - ref| over the tensor's max |ref|
+TOL_ROW_P999 = 4e-3     # 99.9th percentile over rows of max |got_r - ref_r| / max |ref_r| (rows above 1e-4 of the tensor's max)
+TOL_ROW_MAX = 2e-2      # the worst such row
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MEASURED = {}
+
+
+def oracle_cfg(wl):
+    import bench
+    from imagecaptionlearn_py_b200 import core
+    from oracle import icl_oracle as O
+    heads = []
+    for h in wl["heads"]:
+        widths = core.get_widths(h["start"], h["depth"])
+        heads.append(dict(task=h["task"], scope=h["scope"], encoding_scheme=bench.ENC, n_layers=len(widths), widths=widths,
+                          activation="relu", weighted_classes=False,
+                          in_width=O.head_in_width(h["task"], bench.ENC, wl["H"], h["F"], bench.BOX_W if h["task"] == "affinity" else 0),
+                          n_classes=h["C"]))
+    return dict(H=wl["H"], data_norm=wl["data_norm"], heads=heads)
+
+
+def shared_inputs(bts):
+    """One sentence tensor for all heads (the shim concatenates them in head order) + per-head dicts whose sentence column is offset."""
+    tl = max(int(bt["seq_lengths"].max()) for bt in bts)
+    x = np.concatenate([bt["sentences"][:, :tl] for bt in bts], 0).astype(np.float64)
+    lens = np.concatenate([bt["seq_lengths"] for bt in bts], 0)
+    off, hbs = 0, []
+    for bt in bts:
+        hb = {}
+        for k, v in bt.items():
+            if isinstance(v, np.ndarray) and v.ndim == 2 and v.shape[1] == 3 and k.split("_")[0] in ("first", "last", "sent"):
+                v = v.copy()
+                v[:, 1] += off
+            hb[k] = v
+        hbs.append(hb)
+        off += len(bt["seq_lengths"])
+    return x, lens, hbs
+
+
+def kink_overrides(sess, cfg, f, masks, tol):
+    """relu: hand the oracle the device's side of the kink for pre-activations within rounding distance of 0 (see
+    tests/test_gpu_parity.py:kink_override); asserts every disagreement IS at the kink."""
+    from imagecaptionlearn_py_b200 import _cabi
+    over, flips = [], 0
+    for hi, hc in enumerate(cfg["heads"]):
+        layers = f["heads"][hi]["_bwd"][0]
+        B = layers[0][0].shape[0]
+        ho = []
+        for k, w in enumerate(hc["widths"]):
+            y = np.empty((B, w), np.float32)
+            _cabi.check(_cabi.lib().icl_get_activation(sess.handle, hi, k, _cabi.np_ptr(y)))
+            z = layers[k][1]
+            kept = np.ones_like(z, bool) if masks is None else masks["heads"][hi][k] > 0
+            dev_pos, orc_pos = y > 0, z > 0
+            differ = kept & (dev_pos != orc_pos)
+            assert np.all(np.abs(z[differ]) <= tol * np.max(np.abs(z))), "activation sign differs away from the kink"
+            flips += int(differ.sum())
+            ho.append(np.where(np.where(differ, dev_pos, orc_pos), 1.0, 0.0))
+        over.append(ho)
+    return over, flips
+
+
+def grad_errors(got, ref):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64).reshape(got.shape)
+    scale = max(float(np.max(np.abs(ref))), 1e-300)
+    out = dict(tensor=float(np.max(np.abs(got - ref))) / scale, max_ref=scale)
+    if ref.ndim == 2 and ref.shape[0] > 1:
+        rmax = np.max(np.abs(ref), 1)
+        rows = rmax > 1e-4 * scale
+        if rows.any():
+            rr = np.max(np.abs(got - ref), 1)[rows] / rmax[rows]
+            out.update(row_p999=float(np.quantile(rr, 0.999)), row_max=float(rr.max()), rows=int(rows.sum()))
+    return out
+
+
+def run_config(name, dropout):
+    import bench
+    from imagecaptionlearn_py_b200 import _cabi, core
+    from oracle import icl_oracle as O
+    from tests.test_gpu_parity import relerr
+    wl = bench.WORKLOADS[name]
+    bts = bench.make_batches(wl, 20171201)
+    bench.build_graph(wl)
+    sess = core.Session(max_seq_len=bench.T_PAD)
+    sess.ensure()
+    weights = {n: sess.get_tensor(n) for n, _, _, _ in sess.param_info()}
+    # non-zero LSTM biases (TF initialises them to zero; a trained model does not keep them there)
+    rng = np.random.default_rng(3)
+    for n in weights:
+        if n.endswith("basic_lstm_cell/bias"):
+            weights[n] = (rng.standard_normal(weights[n].shape) * 0.1).astype(np.float32)
+            sess.set_tensor(n, weights[n])
+    keep_in, keep = (bench.KEEP_IN, bench.KEEP) if dropout else (1.0, 1.0)
+    res = sess.run(_cabi.OP_GRADS, [dict(bt) for bt in bts], keep_in, keep, True)
+    cfg = oracle_cfg(wl)
+    x, lens, hbs = shared_inputs(bts)
+    masks = None
+    if dropout:
+        S, T, H = x.shape[0], sess.max_seq_len, wl["H"]
+        masks = {}
+        for key, stream, W, kp in (("in_fw", 0, bench.E, keep_in), ("in_bw", 1, bench.E, keep_in), ("out_fw", 2, H, keep), ("out_bw", 3, H, keep)):
+            masks[key] = sess.debug_mask(stream, S * T * W, kp).reshape(S, T, W)[:, :x.shape[1]].astype(np.float64)
+        masks["heads"] = [[sess.debug_mask(16 + 8 * hi + k, h["B"] * w, keep).reshape(h["B"], w).astype(np.float64)
+                           for k, w in enumerate(cfg["heads"][hi]["widths"])] for hi, h in enumerate(wl["heads"])]
+    params = {k: (v.astype(np.float64).reshape(-1) if k.endswith("basic_lstm_cell/bias") else v.astype(np.float64)) for k, v in weights.items()}
+    f = O.model_forward(params, cfg, x, lens, hbs, keep_in, keep, masks)
+    over, flips = kink_overrides(sess, cfg, f, masks, TOL_FWD)
+    g = O.model_backward(params, cfg, f, hbs, over)
+    rec = dict(flips=flips, loss=[float(sum(r["loss"] for r in res)), float(f["loss"])], proba=[], grads={})
+    assert abs(rec["loss"][0] - rec["loss"][1]) < TOL_FWD * abs(rec["loss"][1]), rec["loss"]
+    for hi, r in enumerate(res):
+        ref = f["heads"][hi]
+        e = float(np.max(np.abs(r["proba"] - ref["proba"])))
+        rec["proba"].append(e)
+        assert e < TOL_FWD, (name, hi, e)
+        margin = np.sort(ref["proba"], 1)
+        clear = (margin[:, -1] - margin[:, -2]) > 2 * TOL_FWD
+        assert np.array_equal(r["pred"][clear], ref["pred"][clear])              # predicted labels identical on clear margins
+        assert np.mean(r["pred"] == ref["pred"]) > 0.99
+    for d, key in ((0, "out_fw"), (1, "out_bw")):
+        out = np.empty((x.shape[0], sess.max_seq_len, wl["H"]), np.float32)
+        _cabi.check(_cabi.lib().icl_get_lstm_outputs(sess.handle, d, _cabi.np_ptr(out)))
+        rec[key] = relerr(out[:, :x.shape[1]], f[key])
+        assert rec[key] < TOL_FWD, (key, rec[key])
+    bad = {}
+    for k, ref in g.items():
+        e = grad_errors(sess.get_tensor(k, 1), ref)
+        rec["grads"][k] = e
+        if e["tensor"] > TOL_GRAD or e.get("row_p999", 0) > TOL_ROW_P999 or e.get("row_max", 0) > TOL_ROW_MAX:
+            bad[k] = e
+    sess.close()
+    MEASURED["%s%s" % (name, "+dropout" if dropout else "")] = rec
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        json.dump(MEASURED, open(os.path.join(out_dir, "r2_config_parity.json"), "w"), indent=1)
+    assert not bad, (name, bad)
+
+
+@pytest.mark.parametrize("name,dropout", [("nonvis512", False), ("nonvis512", True), ("rel_intra512", False), ("rel_cross512", False),
+                                          ("affinity512", False), ("multitask512", False)],
+                         ids=["C1-nonvis512", "C1-nonvis512-dropout", "C3-rel_intra512", "C3-rel_cross512", "C4-affinity512", "C5-multitask512"])
+def test_baseline_config_matches_oracle_with_gradients(name, dropout):
+    run_config(name, dropout)
+
+
+def test_card2048_gradients_match_oracle():
+    """configs[1] at full size: every gradient tensor against the oracle (tests/test_gpu_full_size.py checks its forward and the
+    size-independent properties)."""
+    run_config("card2048", False)
+
+
+def test_forward_is_bit_reproducible_over_50_runs():
+    """The forward pass has no atomics by design (flag-published tiles in k_rec_fwd16, ordered reductions everywhere): 50 predict
+    runs of card2048 must give bit-identical probabilities -- any race in the tile publication protocol would show here."""
+    import bench
+    from imagecaptionlearn_py_b200 import _cabi, core
+    wl = bench.WORKLOADS["card2048"]
+    bts = bench.make_batches(wl, 20171201)
+    bench.build_graph(wl)
+    sess = core.Session(max_seq_len=bench.T_PAD)
+    sess.ensure()
+    first = None
+    for i in range(50):
+        r = sess.run(_cabi.OP_PREDICT, [dict(bts[0])], 1.0, 1.0, True)[0]
+        if first is None:
+            first = (r["proba"].copy(), float(r["loss"]))
+        else:
+            assert np.array_equal(r["proba"], first[0]), "run %d differs" % i
+            assert float(r["loss"]) == first[1]
+    sess.close()

@@ -55,3 +55,17 @@ def test_state_dict_mapping_uses_tf_slot_names():
     assert int(back["adam_step"]) == 12
     for k in ("hdn_1/Variable", "adam_m/hdn_1/Variable", "adam_v/hdn_1/Variable"):
         assert np.array_equal(back[k], st[k])
+
+
+def test_adam_step_round_trips_through_tf_beta_powers():
+    """TF 1.x stores beta ** (t + 1) after t steps (initial value beta, multiplied once per apply).  t = 0 must give beta1 --
+    not 1.0, which would make a TensorFlow resume divide by 1 - 1 -- and t > 1000 must survive the float32 underflow of 0.9 ** t."""
+    for t in (0, 1, 12, 979, 1500, 50000):
+        tf_vars = T.from_state_dict({"adam_step": np.int64(t)})
+        assert tf_vars["beta1_power"] == np.float32(0.9 ** (t + 1)) and tf_vars["beta2_power"] == np.float32(0.999 ** (t + 1))
+        assert int(T.to_state_dict(tf_vars)["adam_step"]) == t, t
+    assert T.from_state_dict({"adam_step": np.int64(0)})["beta1_power"] == np.float32(0.9)
+    # only beta1_power present (an optimizer saved without beta2): still recovered while representable
+    assert int(T.to_state_dict({"beta1_power": np.float32(0.9 ** 13)})["adam_step"]) == 12
+    with pytest.warns(UserWarning):
+        assert int(T.to_state_dict({"beta1_power": np.float32(0.0), "beta2_power": np.float32(0.0)})["adam_step"]) == 0
