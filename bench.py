@@ -102,6 +102,25 @@ def make_batches(wl, seed, packed=False):
     return [make_batch(wl, seed + 17 * i, packed=packed, head=i) for i in range(len(wl["heads"]))]
 
 
+def make_rotation(wl, seed, n_rot, packed=False):
+    """n_rot DISTINCT host batch lists over ONE corpus per head (one token / box table, as in a training run): rotation r takes the
+    id list rolled by r * len / n_rot.  Rotation 0 equals make_batches(wl, seed, packed)."""
+    from imagecaptionlearn_py_b200 import data as nn_data
+    per_head = []
+    for i, h in enumerate(wl["heads"]):
+        dd = _corpus_for(h, seed + 17 * i)
+        per_head.append((h, dd, _ids_for(h, dd, seed + 17 * i)))
+    rot = []
+    for r in range(n_rot):
+        bl = []
+        for h, dd, ids in per_head:
+            k = (r * len(ids)) // n_rot
+            rolled = ids[k:] + ids[:k]
+            bl.append(nn_data.load_batch(rolled[:h["B"]], dd, h["task"], h["C"], packed=packed))
+        rot.append(bl)
+    return rot
+
+
 def build_graph(wl):
     from imagecaptionlearn_py_b200 import core
     core.reset_default_graph()
@@ -407,7 +426,7 @@ def measure(name, steps, warmup, ctx, clocks=None, e2e_variants=False):
     # ---- end-to-end through the reference-facing API with host buffers: a rotation of N_ROT distinct host batches (a real
     # training loop never re-feeds a cache-warm buffer), as many timed steps as the device-timed leg
     N_ROT = 4
-    rot = [bts] + [make_batches(wl, seed0 + 101 * r) for r in range(1, N_ROT)]
+    rot = make_rotation(wl, seed0, N_ROT)
 
     def e2e_loop(batches_of, n, before=None):
         for i in range(2):
@@ -447,7 +466,7 @@ def measure(name, steps, warmup, ctx, clocks=None, e2e_variants=False):
                 var[key] = e2e_loop(fresh, steps)
                 var[key]["api"] = ("data.load_batch(ids, data_dict, task, n_classes%s) + run_op(train_op) per step, both inside the timed region"
                                    % (", packed='rows'" if packed else ""))
-        rows = [make_batches(wl, seed0 + 101 * r, packed="rows") for r in range(N_ROT)]
+        rows = make_rotation(wl, seed0, N_ROT, packed="rows")
         var["corpus_cache"] = e2e_loop(lambda i: rows[i % N_ROT], steps)
         var["corpus_cache"]["api"] = ("same run_op call; load_batch(packed='rows'): int32 token rows into the device-resident token table "
                                       "(icl_set_token_table) instead of the padded [S,T,300] host tensor")

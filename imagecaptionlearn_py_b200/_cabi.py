@@ -43,7 +43,8 @@ class HeadBatch(C.Structure):
                 ("box", C.c_void_p), ("box_dtype", C.c_int32),
                 ("bfeats", C.c_void_p), ("bfeats_dtype", C.c_int32),
                 ("labels", C.c_void_p), ("labels_dtype", C.c_int32),
-                ("sent_offset", C.c_int32), ("box_rows", C.c_void_p), ("inactive", C.c_int32)]
+                ("sent_offset", C.c_int32), ("box_rows", C.c_void_p), ("inactive", C.c_int32),
+                ("sentences", C.c_void_p), ("n_seqs", C.c_int32), ("padded_T", C.c_int32)]
 
 
 class Batch(C.Structure):

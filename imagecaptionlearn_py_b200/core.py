@@ -638,13 +638,21 @@ class Session(object):
                 put("bfeats", "b_feats", hd["n_box_feats"])
             if include_labels:
                 put("labels", "labels", hd["n_classes"])
+        per_head = len(sents) > 1 and not packed
         if len(sents) == 1:
             x = _cabi.as_supported(sents[0])
             ln = _cabi.as_supported(lens[0])
+        elif per_head:
+            # every task's load_batch built its own padded tensor: the library reads them in place (icl_head_batch.sentences)
+            arrs = [_cabi.as_supported(s_) for s_ in sents]
+            if len(set(a.dtype for a in arrs)) > 1 or arrs[0].dtype.kind != "f":
+                arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in arrs]
+            for i, a in zip(head_ids, arrs):
+                b.heads[i].sentences, b.heads[i].n_seqs, b.heads[i].padded_T = a.ctypes.data, a.shape[0], a.shape[1]
+            keepalive += arrs
+            x = arrs[0]
+            ln = _cabi.as_supported(np.concatenate(lens, 0))
         else:
-            if not packed:
-                Tm = max(s.shape[1] for s in sents)
-                sents = [np.pad(s, ((0, 0), (0, Tm - s.shape[1]), (0, 0))) for s in sents]
             x = _cabi.as_supported(np.concatenate(sents, 0))
             ln = _cabi.as_supported(np.concatenate(lens, 0))
         if by_rows:
@@ -654,6 +662,8 @@ class Session(object):
         keepalive += [x, ln]
         if by_rows:
             b.token_rows, b.sentences, b.sent_packed = x.ctypes.data, None, 1
+        elif per_head:
+            b.sentences, b.sent_dtype, b.sent_packed = None, _cabi.dtype_code(x), 0
         else:
             b.sentences, b.sent_dtype, b.sent_packed = x.ctypes.data, _cabi.dtype_code(x), int(packed)
         b.seq_lengths, b.len_dtype = ln.ctypes.data, _cabi.dtype_code(ln)

@@ -519,52 +519,57 @@ __global__ void k_softmax_ce(const float* __restrict__ a, int K, const float* __
 //   dz_{L-1}[b,k] = (sum_c dl[b,c] W[k,c]) * dropout-mask/keep * act'(...)   (the EPI_DACT epilogue of the hidden layers' GEMMs)
 //   dW[k,c] = sum_b a[b,k] dl[b,c],   db[c] = sum_b dl[b,c]
 // A C-column product is bandwidth work, not a tensor-core tile (and C = 2 cannot even be a TMA row pitch): every block takes
-// SMB_ROWS examples, thread k owns hidden unit k (coalesced along k), the per-block partial sums of dW / db go to a scratch
-// buffer and the LAST block to arrive (arrival counter) adds them up in block order -- deterministic, no float atomics.
-constexpr int SMB_ROWS = 64, SMB_THREADS = 128;
+// SMB_ROWS examples, thread k owns hidden unit k (coalesced along k) and adds its partial sums of dW / db to the pre-zeroed
+// gradient buffer with one red.global per element and block (like the split-K epilogue of the other layers' weight gradients).
+constexpr int SMB_ROWS = 8, SMB_THREADS = 128;
 __global__ void __launch_bounds__(SMB_THREADS) k_softmax_bwd(const float* __restrict__ a, const float* __restrict__ dl,
                                                              const float* __restrict__ W, int B, int K, int C, Epilogue e,
-                                                             float* __restrict__ dz, float* __restrict__ dW, float* __restrict__ db,
-                                                             float* part, unsigned* count) {
+                                                             float* __restrict__ dz, float* __restrict__ dW, float* __restrict__ db) {
   extern __shared__ float sm_dyn[];
   float* s_dl = sm_dyn;                         // [SMB_ROWS][C]
-  float* s_W = sm_dyn + SMB_ROWS * C;           // [K][C]
-  __shared__ bool s_last;
-  const int r0 = blockIdx.x * SMB_ROWS, nr = min(SMB_ROWS, B - r0);
+  float* s_W = sm_dyn + SMB_ROWS * C;           // [K][C + 1]  (odd pitch: no bank conflicts between neighbouring k)
+  const int r0 = blockIdx.x * SMB_ROWS, nr = min(SMB_ROWS, B - r0), CP = C + 1;
+  // the epilogue's parameters in registers (kernel parameters live in the constant bank: a dependent load per use otherwise)
+  const int act = e.act, round_out = e.round_out;
+  const float keep = e.drop.keep, inv_keep = 1.0f / e.drop.keep;
+  const bool drop = keep < 1.0f;
+  const uint64_t seed = e.drop.seed;
+  const uint32_t stream = e.drop.stream;
+  const long gid0 = e.drop.row_gid0;
   for (int i = threadIdx.x; i < nr * C; i += blockDim.x) s_dl[i] = dl[(long)r0 * C + i];
-  for (int i = threadIdx.x; i < K * C; i += blockDim.x) s_W[i] = W[i];
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x) s_W[(i / C) * CP + i % C] = W[i];
   __syncthreads();
-  const size_t pstride = (size_t)(K + 1) * C;
-  float* mine = part + blockIdx.x * pstride;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    for (int r = 0; r < nr; r++) {
-      float v = 0.0f;
-      for (int c = 0; c < C; c++) v = fmaf(s_dl[r * C + c], s_W[k * C + c], v);
-      dz[(long)(r0 + r) * K + k] = epilogue_apply(e, v, r0 + r, k, K);
+    float av[SMB_ROWS];                         // a = the last hidden layer's post-dropout output: operand of dW AND `aux` of the epilogue
+#pragma unroll
+    for (int r = 0; r < SMB_ROWS; r++) av[r] = r < nr ? a[(long)(r0 + r) * K + k] : 0.0f;
+#pragma unroll
+    for (int r = 0; r < SMB_ROWS; r++) {
+      if (r < nr) {
+        float v = 0.0f;
+        for (int c = 0; c < C; c++) v = fmaf(s_dl[r * C + c], s_W[k * CP + c], v);
+        float y = av[r];
+        if (drop) {                              // EPI_DACT (see epilogue_apply): mask of the layer whose output is a
+          const float mk = drop1(seed, stream, (uint64_t)((gid0 + r0 + r) * K + k), keep);
+          y *= keep;
+          v = v * inv_keep * mk;
+        }
+        v *= act_bwd_from_out(y, act);
+        dz[(long)(r0 + r) * K + k] = round_out ? tf32_rna(v) : v;
+      }
     }
     for (int c = 0; c < C; c++) {
       float acc = 0.0f;
-      for (int r = 0; r < nr; r++) acc = fmaf(a[(long)(r0 + r) * K + k], s_dl[r * C + c], acc);
-      mine[k * C + c] = acc;
+#pragma unroll
+      for (int r = 0; r < SMB_ROWS; r++) acc = fmaf(av[r], r < nr ? s_dl[r * C + c] : 0.0f, acc);
+      atomicAdd(dW + (long)k * C + c, acc);
     }
   }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float acc = 0.0f;
     for (int r = 0; r < nr; r++) acc += s_dl[r * C + c];
-    mine[K * C + c] = acc;
+    atomicAdd(db + c, acc);
   }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(count, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (int i = threadIdx.x; i < (int)pstride; i += blockDim.x) {
-    float acc = 0.0f;
-    for (unsigned b = 0; b < gridDim.x; b++) acc += __ldcg(part + b * pstride + i);
-    if (i < K * C) dW[i] = acc; else db[i - K * C] = acc;
-  }
-  if (threadIdx.x == 0) *count = 0u;            // ready for the next launch
 }
 
 // deterministic single-block sums: block 0 sums v0 into out[0], block 1 sums v1 into out[1] divided by mean_div

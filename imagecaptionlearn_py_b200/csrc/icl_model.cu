@@ -72,7 +72,6 @@ struct Head {
   int ldbi = 0, lddbi = 0;           // row pitches of bi / dbi: D0 / D0g rounded up to 4 floats.  n_mention_feats is data-defined
                                      // (nn_utils/data.py:187), so D0 = 4H + F need not be a multiple of 4, and a TMA tensor map needs
                                      // 16-byte row pitches -- with a dense pitch layer 1 (the largest head GEMM) fell back to SIMT
-  float* sm_part = nullptr; unsigned* sm_count = nullptr;   // softmax-layer backward: per-block partial sums + arrival counter
   std::vector<int> dims;             // D0, w1..wL, C
   std::vector<int> pW, pB;           // param indices per layer (L hidden + softmax)
   SlotTable slots;                   // device pointers filled at create
@@ -553,7 +552,7 @@ extern "C" void icl_destroy(icl_model* m) {
   F(m->Hp16[0]); F(m->Hp16[1]); F(m->Wp16[0]); F(m->Wp16[1]); F(m->X16[0]); F(m->X16[1]); F(m->Wih16[0]); F(m->Wih16[1]);
   F(m->d_partial); F(m->d_gnorm);
   for (auto& h : m->heads) {
-    F(h.bi); F(h.dbi); F(h.dA); F(h.dBuf); F(h.sm_part); F(h.sm_count); for (auto a : h.act) F(a); for (auto a : h.dzb) F(a);
+    F(h.bi); F(h.dbi); F(h.dA); F(h.dBuf); for (auto a : h.act) F(a); for (auto a : h.dzb) F(a);
     F(h.proba); F(h.dlogits); F(h.row_loss); F(h.row_correct); F(h.scalars); F(h.pred);
     if (h.h_out) cudaFreeHost(h.h_out);
     if (h.h_pred) cudaFreeHost(h.h_pred);
@@ -695,10 +694,6 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
     for (int k = 1; k <= h.c.n_hidden; k++) maxw = std::max(maxw, h.dims[k]);
     CKD(dmalloc(&h.bi, (size_t)B * h.ldbi)); CKD(dmalloc(&h.dbi, (size_t)B * h.lddbi));
     CKD(cudaMemset(h.bi, 0, (size_t)B * h.ldbi * 4)); CKD(cudaMemset(h.dbi, 0, (size_t)B * h.lddbi * 4));
-    {
-      const int Kl = h.dims[h.c.n_hidden], nb = (B + SMB_ROWS - 1) / SMB_ROWS;
-      CKD(dmalloc(&h.sm_part, (size_t)nb * (Kl + 1) * C)); CKD(dmalloc(&h.sm_count, 1)); CKD(cudaMemset(h.sm_count, 0, 4));
-    }
     CKD(dmalloc(&h.dA, (size_t)B * maxw)); CKD(dmalloc(&h.dBuf, (size_t)B * maxw));
     for (int k = 1; k <= h.c.n_hidden; k++) { float* a; CKD(dmalloc(&a, (size_t)B * h.dims[k])); h.act.push_back(a); }
     for (int k = 1; k <= h.c.n_hidden; k++) { float* a; CKD(dmalloc(&a, (size_t)B * h.dims[k])); h.dzb.push_back(a); }
@@ -851,9 +846,30 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
   if (b->n_heads != m->cfg.n_heads) return fail("icl_upload: batch has %d heads, model has %d", b->n_heads, m->cfg.n_heads);
   const bool by_rows = b->token_rows != nullptr;
   if (by_rows && !m->tok_table) return fail("icl_upload: token_rows given but no token table was set (icl_set_token_table)");
-  if (!by_rows && !b->sentences) return fail("icl_upload: neither sentences nor token_rows given");
-  if (!by_rows && !b->sent_packed && (b->padded_T < 1 || b->padded_T > m->T_cap)) return fail("icl_upload: padded_T=%d exceeds capacity %d", b->padded_T, m->T_cap);
-  int T = (by_rows || b->sent_packed) ? m->T_cap : b->padded_T;
+  // per-head sentence tensors (multi-head calls): sequence s lives in the tensor of the head whose range contains it
+  const bool per_head = !by_rows && !b->sentences;
+  std::vector<const char*> seq_src;               // per sequence: first byte of its padded row block (per_head only)
+  std::vector<int> seq_T;
+  if (per_head) {
+    seq_src.assign(S, nullptr); seq_T.assign(S, 0);
+    const size_t es = b->sent_dtype == ICL_F64 ? 8 : 4;
+    int tmaxp = 0;
+    for (int hi = 0; hi < b->n_heads; hi++) {
+      const icl_head_batch& hb = b->heads[hi];
+      if (hb.inactive || !hb.sentences) continue;
+      if (hb.n_seqs < 0 || hb.sent_offset < 0 || hb.sent_offset + hb.n_seqs > S) return fail("icl_upload: head %d sentence range [%d,%d) outside [0,%d)", hi, hb.sent_offset, hb.sent_offset + hb.n_seqs, S);
+      if (hb.padded_T < 1 || hb.padded_T > m->T_cap) return fail("icl_upload: head %d padded_T=%d exceeds capacity %d", hi, hb.padded_T, m->T_cap);
+      for (int s = 0; s < hb.n_seqs; s++) {
+        seq_src[hb.sent_offset + s] = (const char*)hb.sentences + (size_t)s * hb.padded_T * E * es;
+        seq_T[hb.sent_offset + s] = hb.padded_T;
+      }
+      tmaxp = std::max(tmaxp, hb.padded_T);
+    }
+    for (int s = 0; s < S; s++) if (!seq_src[s]) return fail("icl_upload: neither sentences nor token_rows given (sequence %d has no source)", s);
+    if (b->sent_packed) return fail("icl_upload: per-head sentence tensors must be padded, not packed");
+  }
+  if (!by_rows && !per_head && !b->sent_packed && (b->padded_T < 1 || b->padded_T > m->T_cap)) return fail("icl_upload: padded_T=%d exceeds capacity %d", b->padded_T, m->T_cap);
+  int T = (by_rows || b->sent_packed) ? m->T_cap : per_head ? *std::max_element(seq_T.begin(), seq_T.end()) : b->padded_T;
   // next input set: its pinned staging is free once the copies issued from it two uploads ago have completed, its device
   // buffers once the step that consumed them has (the copy stream waits for that; the host does not)
   const int set = (m->cur + 1) & 1;
@@ -871,7 +887,7 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
   for (int s = 0; s < S; s++) {
     double l = read_num(b->seq_lengths, b->len_dtype, s);
     int li = (int)l;
-    if (li != l || li < 0 || li > T) return fail("icl_upload: seq_lengths[%d]=%g outside [0,%d]", s, l, T);
+    if (li != l || li < 0 || li > (per_head ? seq_T[s] : T)) return fail("icl_upload: seq_lengths[%d]=%g outside [0,%d]", s, l, per_head ? seq_T[s] : T);
     lens[s] = li; tokstart[s] = (int)ntok;
     ntok += li; tmax = std::max(tmax, li);
   }
@@ -916,7 +932,7 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
       const int per = 16, items = (s1 - s0 + per - 1) / per;           // 16 sequences per work item
       host_pool().run(items, [&, s0, s1](int it) {
         for (int s = s0 + it * per; s < std::min(s1, s0 + (it + 1) * per); s++) {
-          const char* src = (const char*)b->sentences + (b->sent_packed ? (size_t)tokstart[s] * E : (size_t)s * T * E) * esz;
+          const char* src = per_head ? seq_src[s] : (const char*)b->sentences + (b->sent_packed ? (size_t)tokstart[s] * E : (size_t)s * T * E) * esz;
           if (wire16) {
             uint16_t* d16 = reinterpret_cast<uint16_t*>(h_x) + (size_t)tokstart[s] * E;
             if (b->sent_dtype == ICL_F32) cvt_f32_h16_stream(d16, (const float*)src, (size_t)lens[s] * E);
@@ -1216,15 +1232,15 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
     // and bias gradients of layer k only need dz_k, so they run on the aux stream concurrently with the rest of the chain
     // (joined before the weight-gradient phase of the LSTM / the update).
     // The softmax layer (N = n_classes, 2..12 columns) never goes near a GEMM: ONE fused kernel computes its weight and bias
-    // gradients and dz of the last hidden layer (k_softmax_bwd, deterministic block partials reduced by the last block to arrive).
+    // gradients and dz of the last hidden layer (k_softmax_bwd).
     {
       const Param &pw = m->params[h.pW[L]], &pb = m->params[h.pB[L]];
       const int Kl = h.dims[L], C = h.dims[L + 1], nb = (B + SMB_ROWS - 1) / SMB_ROWS;
       Epilogue e; memset(&e, 0, sizeof(e));
       e.mode = EPI_DACT; e.act = h.c.activation; e.aux = h.act[L - 1]; e.ldaux = Kl;
       e.drop = mk_drop(seed, STREAM_HEAD + (uint32_t)hi * 8 + (L - 1), keep, m->ex_gid0); e.round_out = m->round_ops;
-      k_softmax_bwd<<<nb, SMB_THREADS, (size_t)(SMB_ROWS * C + Kl * C) * 4, st>>>(h.act[L - 1], h.dlogits, m->P + pw.off, B, Kl, C, e, h.dzb[L - 1],
-                                                                                   m->G + pw.off, m->G + pb.off, h.sm_part, h.sm_count);
+      k_softmax_bwd<<<nb, SMB_THREADS, (size_t)(SMB_ROWS * C + Kl * (C + 1)) * 4, st>>>(h.act[L - 1], h.dlogits, m->P + pw.off, B, Kl, C, e,
+                                                                                         h.dzb[L - 1], m->G + pw.off, m->G + pb.off);
       LAUNCHED(m);
     }
     const float* dz = h.dzb[L - 1];    // gradient w.r.t. the pre-activation of layer k+1

@@ -74,6 +74,11 @@ typedef struct icl_head_batch {
   const int32_t* box_rows;                       /* or (box == NULL): [B] rows of the device-resident box table (icl_set_box_table) */
   int32_t inactive;                              /* 1: this head is not fed in this call (TF evaluates only the fetched
                                                     task's subgraph, icl_multitask_lstm.py:327-334); its outputs are NaN */
+  /* multi-head calls (icl_multitask_lstm.py:213-358): every task's load_batch builds its OWN padded 'sentences' tensor.  When
+     icl_batch.sentences and token_rows are both NULL the library reads each fed head's tensor in place -- its sequences are
+     numbered [sent_offset, sent_offset + n_seqs) -- instead of making the caller concatenate them (184 MB per step for C5). */
+  const void* sentences;                         /* padded [n_seqs, padded_T, E], dtype = icl_batch.sent_dtype */
+  int32_t n_seqs, padded_T;
 } icl_head_batch;
 
 typedef struct icl_batch {
