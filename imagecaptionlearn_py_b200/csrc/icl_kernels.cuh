@@ -519,13 +519,15 @@ __global__ void k_softmax_ce(const float* __restrict__ a, int K, const float* __
 //   dz_{L-1}[b,k] = (sum_c dl[b,c] W[k,c]) * dropout-mask/keep * act'(...)   (the EPI_DACT epilogue of the hidden layers' GEMMs)
 //   dW[k,c] = sum_b a[b,k] dl[b,c],   db[c] = sum_b dl[b,c]
 // A C-column product is bandwidth work, not a tensor-core tile (and C = 2 cannot even be a TMA row pitch): every block takes
-// SMB_ROWS examples, thread k owns hidden unit k (coalesced along k) and adds its partial sums of dW / db to the pre-zeroed
-// gradient buffer with one red.global per element and block (like the split-K epilogue of the other layers' weight gradients).
+// SMB_ROWS examples, thread k owns hidden unit k (coalesced along k) and writes its partial sums of dW / db to the block's row of
+// `part` [blocks][K*C + C]; k_softmax_bwd_reduce adds the rows in block order (no atomics: the gradient is bit-reproducible).
 constexpr int SMB_ROWS = 8, SMB_THREADS = 128;
 __global__ void __launch_bounds__(SMB_THREADS) k_softmax_bwd(const float* __restrict__ a, const float* __restrict__ dl,
                                                              const float* __restrict__ W, int B, int K, int C, Epilogue e,
-                                                             float* __restrict__ dz, float* __restrict__ dW, float* __restrict__ db) {
+                                                             float* __restrict__ dz, float* __restrict__ part) {
   extern __shared__ float sm_dyn[];
+  float* const dW = part + (long)blockIdx.x * (K * C + C);
+  float* const db = dW + K * C;
   float* s_dl = sm_dyn;                         // [SMB_ROWS][C]
   float* s_W = sm_dyn + SMB_ROWS * C;           // [K][C + 1]  (odd pitch: no bank conflicts between neighbouring k)
   const int r0 = blockIdx.x * SMB_ROWS, nr = min(SMB_ROWS, B - r0), CP = C + 1;
@@ -562,14 +564,27 @@ __global__ void __launch_bounds__(SMB_THREADS) k_softmax_bwd(const float* __rest
       float acc = 0.0f;
 #pragma unroll
       for (int r = 0; r < SMB_ROWS; r++) acc = fmaf(av[r], r < nr ? s_dl[r * C + c] : 0.0f, acc);
-      atomicAdd(dW + (long)k * C + c, acc);
+      dW[k * C + c] = acc;
     }
   }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float acc = 0.0f;
     for (int r = 0; r < nr; r++) acc += s_dl[r * C + c];
-    atomicAdd(db + c, acc);
+    db[c] = acc;
   }
+}
+// dW [K*C] and db [C] of the softmax layer = the sum of the nb partial rows of k_softmax_bwd, in block order
+__global__ void k_softmax_bwd_reduce(const float* __restrict__ part, int nb, int KC, int C, float* __restrict__ dW, float* __restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, n = KC + C;
+  if (i >= n) return;
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+  int b = 0;
+  for (; b + 4 <= nb; b += 4) {
+    s0 += part[(long)b * n + i]; s1 += part[(long)(b + 1) * n + i]; s2 += part[(long)(b + 2) * n + i]; s3 += part[(long)(b + 3) * n + i];
+  }
+  for (; b < nb; b++) s0 += part[(long)b * n + i];
+  const float s = (s0 + s1) + (s2 + s3);
+  if (i < KC) dW[i] = s; else db[i - KC] = s;
 }
 
 // deterministic single-block sums: block 0 sums v0 into out[0], block 1 sums v1 into out[1] divided by mean_div

@@ -80,7 +80,7 @@ struct Head {
   std::vector<float*> act;           // y_k [B,w_k]
   std::vector<float*> dzb;           // gradient w.r.t. the pre-activation of hidden layer k [B,w_k] (one buffer per layer: the weight
                                      // gradients read it on the aux stream while the main stream already computes the next layer's)
-  float *proba = nullptr, *dlogits = nullptr, *row_loss = nullptr, *row_correct = nullptr, *scalars = nullptr;
+  float *proba = nullptr, *dlogits = nullptr, *smb_part = nullptr, *row_loss = nullptr, *row_correct = nullptr, *scalars = nullptr;
   long long* pred = nullptr;
   int* idx[ICL_N_INDEX] = {};
   float *feats = nullptr, *box = nullptr, *bfeats = nullptr, *labels = nullptr;
@@ -553,7 +553,7 @@ extern "C" void icl_destroy(icl_model* m) {
   F(m->d_partial); F(m->d_gnorm);
   for (auto& h : m->heads) {
     F(h.bi); F(h.dbi); F(h.dA); F(h.dBuf); for (auto a : h.act) F(a); for (auto a : h.dzb) F(a);
-    F(h.proba); F(h.dlogits); F(h.row_loss); F(h.row_correct); F(h.scalars); F(h.pred);
+    F(h.proba); F(h.dlogits); F(h.smb_part); F(h.row_loss); F(h.row_correct); F(h.scalars); F(h.pred);
     if (h.h_out) cudaFreeHost(h.h_out);
     if (h.h_pred) cudaFreeHost(h.h_pred);
   }
@@ -698,6 +698,7 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
     for (int k = 1; k <= h.c.n_hidden; k++) { float* a; CKD(dmalloc(&a, (size_t)B * h.dims[k])); h.act.push_back(a); }
     for (int k = 1; k <= h.c.n_hidden; k++) { float* a; CKD(dmalloc(&a, (size_t)B * h.dims[k])); h.dzb.push_back(a); }
     CKD(dmalloc(&h.proba, (size_t)B * C)); CKD(dmalloc(&h.dlogits, (size_t)B * C));
+    CKD(dmalloc(&h.smb_part, (size_t)((B + SMB_ROWS - 1) / SMB_ROWS) * ((size_t)h.dims[h.c.n_hidden] * C + C)));
     CKD(dmalloc(&h.row_loss, B)); CKD(dmalloc(&h.row_correct, B)); CKD(dmalloc(&h.scalars, 4)); CKD(dmalloc(&h.pred, B));
     CKD(cudaMallocHost((void**)&h.h_out, ((size_t)B * C + 4) * 4));
     CKD(cudaMallocHost((void**)&h.h_pred, (size_t)B * 8));
@@ -1063,7 +1064,7 @@ static int rec_forward_fp16(icl_model* m, int training) {
   a.off = m->d_off; a.nact = m->d_nact; a.Tmax = m->Tmax; a.H = H; a.nsl = m->rp_nsl;
   const int tiles = (m->n_active[0] + 127) / 128;
   a.P = std::max(1, std::min(148 / (2 * m->rp_nsl), tiles));
-  a.nkb = m->rf_nkb; a.nk16 = m->rf_nk16; a.max_tiles = m->rp_max_tiles; a.training = training; a.ldx = m->ldx; a.flags = m->rp_flags;
+  a.nkb = m->rf_nkb; a.nk16 = m->rf_nk16; a.nst = U == 20 ? rec_fwd16_stages<20>(a.nkb) : rec_fwd16_stages<16>(a.nkb); a.max_tiles = m->rp_max_tiles; a.training = training; a.ldx = m->ldx; a.flags = m->rp_flags;
   for (int d = 0; d < 2; d++) { a.Z[d] = m->Z[d]; a.Cc[d] = m->Cc[d]; a.Hx[d] = m->Hx[d]; a.Hp[d] = m->Hp[d]; }
   a.trace = m->rp_trace; a.trace_cta = m->rp_trace_cta;
   void* args[] = {(void*)&m->rf_maps, (void*)&a};
@@ -1240,7 +1241,9 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
       e.mode = EPI_DACT; e.act = h.c.activation; e.aux = h.act[L - 1]; e.ldaux = Kl;
       e.drop = mk_drop(seed, STREAM_HEAD + (uint32_t)hi * 8 + (L - 1), keep, m->ex_gid0); e.round_out = m->round_ops;
       k_softmax_bwd<<<nb, SMB_THREADS, (size_t)(SMB_ROWS * C + Kl * (C + 1)) * 4, st>>>(h.act[L - 1], h.dlogits, m->P + pw.off, B, Kl, C, e,
-                                                                                         h.dzb[L - 1], m->G + pw.off, m->G + pb.off);
+                                                                                         h.dzb[L - 1], h.smb_part);
+      LAUNCHED(m);
+      k_softmax_bwd_reduce<<<(Kl * C + C + 127) / 128, 128, 0, st>>>(h.smb_part, nb, Kl * C, C, m->G + pw.off, m->G + pb.off);
       LAUNCHED(m);
     }
     const float* dz = h.dzb[L - 1];    // gradient w.r.t. the pre-activation of layer k+1
@@ -1368,8 +1371,10 @@ static int rec_backward_cluster(icl_model* m) {
   if (const char* e = getenv("ICL_BPTT_N8")) { n8 = std::max(0, std::min(tiles, atoi(e))); n2 = std::min(n2, tiles - n8); }
   if (const char* e = getenv("ICL_BPTT_N2")) n2 = std::max(0, std::min(tiles - n8, atoi(e)));
   const int n4 = tiles - n8 - n2;
+  static const int trace_cs = getenv("ICL_TRACE_CS") ? atoi(getenv("ICL_TRACE_CS")) : 8;     // bring-up trace: one of the three launches
   auto launch = [&](int cs, int tile0, int ntiles, cudaStream_t s) -> int {
     a.tile0 = tile0;
+    a.trace = cs == trace_cs ? m->rp_trace : nullptr;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(cs, (unsigned)(2 * ntiles), 1);
     cfg.blockDim = dim3(BC_THREADS); cfg.dynamicSmemBytes = BC_SMEM; cfg.stream = s;

@@ -334,15 +334,24 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bptt_cluster(const __grid_con
   int k_first = -1;
   for (int k = Tmax - 1; k >= 0; k--) if (m0 < s_n[k]) { k_first = k; break; }
 
-  // L2 prefetch of the cell-backward operands of step k for my rows (one row per lane of warp 2)
+  // L2 prefetch of the cell-backward operands of step k for my rows.  The rows of a CTA are contiguous in the step-major layout, so
+  // each operand is ONE region: four bulk prefetches per step (two halves of the gate rows, dH, c) from four lanes of warp 2.  (One
+  // prefetch per row -- 96 per step -- kept the CTA's TMA unit busy for 3.7 us in front of the K-loop's operand loads,
+  // profiles/r1g_bptt_cluster_trace.txt: "S23 -> step start".)
   auto prefetch_step = [&](int k) {
-    if (warp != 2 || k < 0) return;
-    const int grow = m0 + rank * ROWS_OWN + lane;
-    if (grow >= s_n[k]) return;
-    prefetch_l2_bulk(Zd + ((long)s_off[k] + grow) * 4 * H, (uint32_t)(4 * H * 4));
-    prefetch_l2_bulk(dHd + ((long)s_off[k] + grow) * H, (uint32_t)(H * 4));
-    if (k > 0) prefetch_l2_bulk(Cd + ((long)s_off[k - 1] + grow) * H, (uint32_t)(H * 4));
-    if (k == k_first) prefetch_l2_bulk(Cd + ((long)s_off[k] + grow) * H, (uint32_t)(H * 4));
+    if (warp != 2 || k < 0 || lane > 3) return;
+    const int r0 = m0 + rank * ROWS_OWN, nr = min(ROWS_OWN, s_n[k] - r0);
+    if (nr <= 0) return;
+    const long row0 = (long)s_off[k] + r0;
+    if (lane < 2) {
+      const int h0 = lane ? nr / 2 : 0, h1 = lane ? nr : nr / 2;
+      if (h1 > h0) prefetch_l2_bulk(Zd + (row0 + h0) * 4 * H, (uint32_t)((h1 - h0) * 4 * H * 4));
+    } else if (lane == 2) {
+      prefetch_l2_bulk(dHd + row0 * H, (uint32_t)(nr * H * 4));
+    } else {
+      if (k > 0) prefetch_l2_bulk(Cd + ((long)s_off[k - 1] + r0) * H, (uint32_t)(nr * H * 4));
+      if (k == k_first) prefetch_l2_bulk(Cd + row0 * H, (uint32_t)(nr * H * 4));
+    }
   };
   prefetch_step(k_first);
 

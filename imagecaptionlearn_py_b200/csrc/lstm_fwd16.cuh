@@ -26,7 +26,7 @@
 
 namespace icl {
 
-constexpr int RF_ASTAGES = 3, RF_EW = 8, RF_THREADS = 64 + 32 * RF_EW, RF_MAXTPC = 4, RF_MAXACC = 8;
+constexpr int RF_MAXST = 6, RF_EW = 8, RF_SW = 4, RF_THREADS = 64 + 32 * (RF_EW + RF_SW), RF_MAXTPC = 4, RF_MAXACC = 8;
 template <int U> struct RF {
   static constexpr int UP = (U * 2) % 16 == 0 ? U : (U + 7) / 8 * 8;         // units of a slice as stored in Hp16 (padded to 16 bytes)
   static constexpr int N = 4 * U;
@@ -34,15 +34,19 @@ template <int U> struct RF {
   static constexpr int ZBOX = 32 * U * 4;                                     // one gate box of a quarter
   static constexpr int HBOX = 32 * UP * 2;                                    // the fp16 h box of a quarter
 };
-template <int U> constexpr int rec_fwd16_smem(int nkb) {
-  return nkb * RF<U>::N * 128 + RF_ASTAGES * 16384 + 4 * (2 * 5 * RF<U>::ZBOX + 2 * RF<U>::HBOX) + 512 + 1024;
+// The h_{k-1} ring is as deep as shared memory allows, up to a whole tile (H = 300: 3 of 6 k-blocks, H = 200: all 4)
+template <int U> constexpr int rec_fwd16_fixed(int nkb) { return nkb * RF<U>::N * 128 + 4 * (2 * 5 * RF<U>::ZBOX + 2 * RF<U>::HBOX) + 512 + 1024; }
+template <int U> constexpr int rec_fwd16_stages(int nkb) {
+  int st = (227 * 1024 - rec_fwd16_fixed<U>(nkb)) / 16384;
+  return st > RF_MAXST ? RF_MAXST : st > nkb ? nkb : st;
 }
+template <int U> constexpr int rec_fwd16_smem(int nkb) { return rec_fwd16_fixed<U>(nkb) + rec_fwd16_stages<U>(nkb) * 16384; }
 
 struct RecFwd16Maps { CUtensorMap a[2], w[2], z[2], cc[2], hp16[2]; };   // a: Hp16 box {64 halves, 128 rows} SW128; w: packed W box {64, 4U} SW128;
                                                                   // z: Z box {U, 32}; hp16: Hp16 box {UP, 32}
 struct RecFwd16Args {
   const int* off; const int* nact;
-  int Tmax, H, nsl, P, nkb, nk16, max_tiles, training, ldx;
+  int Tmax, H, nsl, P, nkb, nk16, nst, max_tiles, training, ldx;
   unsigned* flags;
   float* Z[2]; float* Cc[2]; float* Hx[2]; float* Hp[2];           // generic-store targets (Hp = TF32 h rows inside XH, pitch ldx)
   long long* trace; int trace_cta;
@@ -83,10 +87,12 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t sW = base;
   const uint32_t sA = sW + (uint32_t)g.nkb * N * 128;
-  const uint32_t sE = sA + RF_ASTAGES * 16384;
+  const int NST = g.nst;                                                    // stages of the h_{k-1} ring
+  const uint32_t sE = sA + (uint32_t)NST * 16384;
   const uint32_t bars = sE + 4 * QBYTES;
-  const uint32_t full0 = bars, empty0 = bars + 8 * RF_ASTAGES, wfull = bars + 16 * RF_ASTAGES, efull0 = wfull + 8,   // efull: [quarter][set]
-                 tfull0 = efull0 + 8 * 8, tempty0 = tfull0 + 8 * RF_MAXACC, tmem_slot = tempty0 + 8 * RF_MAXACC;
+  const uint32_t full0 = bars, empty0 = bars + 8 * RF_MAXST, wfull = bars + 16 * RF_MAXST, efull0 = wfull + 8,   // efull: [quarter][set]
+                 sready0 = efull0 + 8 * 8,                                                    // sready: [quarter][set], as efull
+                 tfull0 = sready0 + 8 * 8, tempty0 = tfull0 + 8 * RF_MAXACC, tmem_slot = tempty0 + 8 * RF_MAXACC;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per_dir = g.P * g.nsl;
   const int d = blockIdx.x / per_dir, p = (blockIdx.x % per_dir) / g.nsl, j = blockIdx.x % g.nsl;
@@ -95,9 +101,9 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
 
   for (int i = threadIdx.x; i <= Tmax; i += blockDim.x) { s_off[i] = g.off[i]; s_n[i] = g.nact[i]; }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < RF_ASTAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < RF_MAXST; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     mbar_init(wfull, 1);
-    for (int w = 0; w < 8; w++) mbar_init(efull0 + 8 * w, 1);
+    for (int w = 0; w < 8; w++) { mbar_init(efull0 + 8 * w, 1); mbar_init(sready0 + 8 * w, 2); }
     for (int a = 0; a < NACC; a++) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, RF_EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -131,8 +137,8 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
           fence_async_all();
           tr.ev(1, k, t);
           for (int kb = 0; kb < g.nkb; kb++, it++) {
-            const uint32_t s = it % RF_ASTAGES;
-            mbar_wait(empty0 + 8 * s, ((it / RF_ASTAGES) & 1) ^ 1);
+            const uint32_t s = it % NST;
+            mbar_wait(empty0 + 8 * s, ((it / NST) & 1) ^ 1);
             mbar_expect_tx(full0 + 8 * s, 16384);
             tma_load_2d(sA + s * 16384, &maps.a[d], kb * 64, s_off[k] + t * RP_ROWS, full0 + 8 * s);
           }
@@ -153,8 +159,8 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
           tc_fence_after();
           tr.ev(0, k, t);
           for (int kb = 0; kb < g.nkb; kb++, it++) {
-            const uint32_t s = it % RF_ASTAGES;
-            mbar_wait(full0 + 8 * s, (it / RF_ASTAGES) & 1);
+            const uint32_t s = it % NST;
+            mbar_wait(full0 + 8 * s, (it / NST) & 1);
             tc_fence_after();
             if (kb == 0) tr.ev(1, k, t);
             const int nk = min(4, g.nk16 - kb * 4);                    // UMMA_K = 16 halves = 32 bytes
@@ -170,27 +176,15 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
         }
       }
     }
-  } else {
-    // ---- 8 epilogue warps = 4 TMEM lane quarters x 2 unit halves (as k_rec_fwd); per quarter two sets of x-projection boxes
+  } else if (warp < 2 + RF_EW) {
+    // ---- 8 cell warps = 4 TMEM lane quarters x 2 unit halves (as k_rec_fwd).  They only compute: a tile's boxes (gates, c, fp16 h)
+    // are handed to the quarter's store warp through the `sready` mbarrier, so the next tile's cells start at once
     const int ew = warp - 2, q = warp & 3, hs = ew >> 2;
     const int UH = hs ? U1 : U0, ubase = hs ? U0 : 0;
     const uint32_t sMine = sE + (uint32_t)q * QBYTES;
     float* zset[2] = {reinterpret_cast<float*>(gbase + (sMine - base)), reinterpret_cast<float*>(gbase + (sMine - base) + 5 * ZBOX)};
     __half* const hbox0 = reinterpret_cast<__half*>(gbase + (sMine - base) + 2 * 5 * ZBOX);   // two boxes, alternating per tile
     const int ucol = j * U;
-    const bool issuer = hs == 0 && lane == 0;                            // the quarter's TMA thread
-    auto valid = [&](int k, int i) { return k < Tmax && i < RF_MAXTPC && (p + i * g.P) * RP_ROWS < s_n[k]; };
-    auto nxt = [&](int& k, int& i) { if (valid(k, i + 1)) i++; else { k++; i = 0; } };
-    auto load_z = [&](int k, int i, int set) {                          // x-projection boxes of tile (k, i) of this quarter
-      const uint32_t bar = efull0 + 8 * (q * 2 + set);
-      mbar_expect_tx(bar, 4 * ZBOX);
-      for (int gate = 0; gate < 4; gate++)
-        tma_load_2d(sMine + set * 5 * ZBOX + gate * ZBOX, &maps.z[d], gate * H + ucol, s_off[k] + (p + i * g.P) * RP_ROWS + 32 * q, bar);
-    };
-    if (issuer) {                                                      // prime both sets
-      int k0 = 0, i0 = 0;
-      if (valid(k0, i0)) { load_z(k0, i0, 0); nxt(k0, i0); if (valid(k0, i0)) load_z(k0, i0, 1); }
-    }
     float* const Hd = g.Hx[d]; float* const Hpd = g.Hp[d];
     float cst[RF_MAXTPC][U0];
 #pragma unroll
@@ -201,10 +195,12 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
     Tracer tr; tr.init(g.trace, g.trace_cta, 3);
     if (ew != 0 || lane != 0) tr.p = nullptr;
     for (int k = 0; k < Tmax; k++) {
+      const int n_k = s_n[k], n_k1 = s_n[k + 1];
+      const long o_k = s_off[k], o_k1 = s_off[k + 1];
 #pragma unroll
       for (int i = 0; i < RF_MAXTPC; i++) {
         const int t = p + i * g.P;
-        if (t * RP_ROWS >= s_n[k]) break;
+        if (t * RP_ROWS >= n_k) break;
         const int set = n_tile & 1;
         tr.ev(0, k, t);
         mbar_wait(efull0 + 8 * (q * 2 + set), (n_tile >> 1) & 1);
@@ -218,9 +214,9 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
         tr.ev(2, k, t);
         float* zb = zset[set] + ubase;
         __half* hbox = hbox0 + set * (HBOX / 2);
-        const long row = (long)s_off[k] + t * RP_ROWS + 32 * q + lane;
-        const bool has_next = t * RP_ROWS < s_n[k + 1];
-        const long row_n = (long)s_off[k + 1] + t * RP_ROWS + 32 * q + lane;
+        const long row = o_k + t * RP_ROWS + 32 * q + lane;
+        const bool has_next = t * RP_ROWS < n_k1;
+        const long row_n = o_k1 + t * RP_ROWS + 32 * q + lane;
 #pragma unroll
         for (int c = 0; c < U0 / 4; c++) {
           if (c * 4 < UH) {
@@ -237,19 +233,18 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
             float si[4], tj[4], sf[4], so[4], hn[4], hr[4];
 #pragma unroll
             for (int x = 0; x < 4; x++) {
-              si[x] = sigmoid_fast(zi[x] + __uint_as_float(a[x]));
-              tj[x] = tanh_fast(zj[x] + __uint_as_float(a[4 + x]));
-              sf[x] = sigmoid_fast(zf[x] + __uint_as_float(a[8 + x]) + 1.0f);
-              so[x] = sigmoid_fast(zo[x] + __uint_as_float(a[12 + x]));
+              lstm_gates_fast(zi[x] + __uint_as_float(a[x]), zj[x] + __uint_as_float(a[4 + x]), zf[x] + __uint_as_float(a[8 + x]) + 1.0f,
+                              zo[x] + __uint_as_float(a[12 + x]), si[x], tj[x], sf[x], so[x]);
               const float cn = cst[i][c * 4 + x] * sf[x] + si[x] * tj[x];
               cst[i][c * 4 + x] = cn;
               hn[x] = tanh_fast(cn) * so[x];
               hr[x] = tf32_rna(hn[x]);
             }
             const int u = ucol + ubase + c * 4;
-            if (g.training) {                                          // read by the backward pass only: straight from registers
+            if (g.training) {                                          // read by the backward pass only
               // the gates go back into the x-projection boxes and out as four TMA boxes (the LSU path alone was the bottleneck:
-              // every lane-per-row float4 store is 32 wavefronts); c / h / TF32 h stay on the LSU, the two engines overlap
+              // every lane-per-row float4 store is 32 wavefronts); c / h / TF32 h stay on the LSU, the two engines overlap (moving
+              // c to the LSU as well to free a 4th stage of the h_{k-1} ring measured slower: 0.337 vs 0.321 ms)
               *reinterpret_cast<float4*>(zb + 0 * 32 * U + lane * U + c * 4) = make_float4(si[0], si[1], si[2], si[3]);
               *reinterpret_cast<float4*>(zb + 1 * 32 * U + lane * U + c * 4) = make_float4(tj[0], tj[1], tj[2], tj[3]);
               *reinterpret_cast<float4*>(zb + 2 * 32 * U + lane * U + c * 4) = make_float4(sf[0], sf[1], sf[2], sf[3]);
@@ -263,40 +258,89 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
             *reinterpret_cast<uint2*>(hbox + lane * UP + ubase + c * 4) = pk;       // next step's operand rows (fp16)
           }
         }
-        if (k > 0) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty0 + 8 * slot);
-          acc++;
+        tr.ev(4, k, t);
+        if (k > 0) tc_fence_before();
+        fence_async_smem();                                             // the boxes (generic smem writes) -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+          if (k > 0) mbar_arrive(tempty0 + 8 * slot);
+          mbar_arrive(sready0 + 8 * (q * 2 + set));                     // this half of the quarter's boxes is ready to leave
         }
-        fence_async_smem();                                             // the fp16 box (generic smem writes) -> visible to the TMA engine
-        asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");       // both unit halves are done with this set's boxes
-        if (issuer) {
-          if (has_next) tma_store_2d(&maps.hp16[d], sMine + 2 * 5 * ZBOX + set * HBOX, j * UP, (int)(s_off[k + 1] + t * RP_ROWS + 32 * q));
+        if (k > 0) acc++;
+        tr.ev(3, k, t);
+        n_tile++;
+        // hazards: set `set` (gate boxes + fp16 box) is next written for tile n_tile + 2, after its `efull` barrier has fired; the
+        // store warp requests that refill only when the TMA stores of THIS tile have read the boxes
+      }
+    }
+  } else {
+    // ---- 4 store warps, one per TMEM lane quarter (lane 0 drives the TMA engine, lane 1 publishes): x-projection boxes in, gate /
+    // c / fp16-h boxes out, the tile's publication counter.  Everything here used to sit at the end of the cell warps' tile loop
+    // (1.6 - 2 us of the 3.4 - 4 us per tile, profiles/r2b_rec_fwd16_trace.txt).
+    const int q = warp & 3;
+    const uint32_t sMine = sE + (uint32_t)q * QBYTES;
+    const int ucol = j * U;
+    auto tile_rows = [&](int k, int i) { return s_off[k] + (p + i * g.P) * RP_ROWS + 32 * q; };
+    auto load_z = [&](int k, int i, int set) {                          // x-projection boxes of tile (k, i) of this quarter
+      const uint32_t bar = efull0 + 8 * (q * 2 + set);
+      const int r0 = tile_rows(k, i);
+      mbar_expect_tx(bar, 4 * ZBOX);
+      for (int gate = 0; gate < 4; gate++) tma_load_2d(sMine + set * 5 * ZBOX + gate * ZBOX, &maps.z[d], gate * H + ucol, r0, bar);
+    };
+    // (k2, i2) runs two tiles ahead of the tile being stored: the boxes it names are requested into the set that has just left
+    int k2 = 0, i2 = 0;
+    auto ahead_valid = [&]() { return k2 < Tmax; };
+    auto ahead_next = [&]() {
+      i2++;
+      if (i2 >= RF_MAXTPC || (p + i2 * g.P) * RP_ROWS >= s_n[k2]) {
+        i2 = 0; k2++;
+        if (k2 < Tmax && p * RP_ROWS >= s_n[k2]) k2 = Tmax;             // running rows only shrink: nothing left for this part
+      }
+    };
+    if (p * RP_ROWS >= s_n[0]) k2 = Tmax;
+    if (lane == 0) {                                                    // prime both sets
+      if (ahead_valid()) { load_z(k2, i2, 0); ahead_next(); }
+      if (ahead_valid()) { load_z(k2, i2, 1); ahead_next(); }
+    }
+    uint32_t n_tile = 0;
+    Tracer tr; tr.init(g.trace, g.trace_cta, 2);
+    if (q != 2 || lane != 0) tr.p = nullptr;                              // the quarter of cell warp 0 (warp 2)
+    for (int k = 0; k < Tmax; k++) {
+      const int n_k = s_n[k], n_k1 = s_n[k + 1];
+#pragma unroll 1
+      for (int i = 0; i < RF_MAXTPC; i++) {
+        const int t = p + i * g.P;
+        if (t * RP_ROWS >= n_k) break;
+        const int set = n_tile & 1;
+        const bool has_next = t * RP_ROWS < n_k1;
+        mbar_wait(sready0 + 8 * (q * 2 + set), (n_tile >> 1) & 1);
+        tr.ev(0, k, t);
+        if (lane == 0) {
+          const int r0 = tile_rows(k, i);
+          if (has_next) tma_store_2d(&maps.hp16[d], sMine + 2 * 5 * ZBOX + set * HBOX, j * UP, s_off[k + 1] + (p + i * g.P) * RP_ROWS + 32 * q);
           bulk_commit();                                               // group A: what the next step of the other slices waits for
           if (g.training) {
-            for (int gate = 0; gate < 4; gate++)
-              tma_store_2d(&maps.z[d], sMine + set * 5 * ZBOX + gate * ZBOX, gate * H + ucol, (int)(s_off[k] + t * RP_ROWS + 32 * q));
-            tma_store_2d(&maps.cc[d], sMine + set * 5 * ZBOX + 4 * ZBOX, ucol, (int)(s_off[k] + t * RP_ROWS + 32 * q));
+            for (int gate = 0; gate < 4; gate++) tma_store_2d(&maps.z[d], sMine + set * 5 * ZBOX + gate * ZBOX, gate * H + ucol, r0);
+            tma_store_2d(&maps.cc[d], sMine + set * 5 * ZBOX + 4 * ZBOX, ucol, r0);
             bulk_commit();                                             // group B: the gates and c (read by the backward pass)
-            bulk_wait_read<0>();                                       // the boxes of this set may be refilled
+            bulk_wait<1>();                                            // group A: the fp16 rows are complete in global memory
+          } else {
+            bulk_wait<0>();
           }
-          int k2 = k, i2 = i;                                          // x-projection boxes of the tile after next -> this set
-          nxt(k2, i2);
-          if (valid(k2, i2)) { nxt(k2, i2); if (valid(k2, i2)) load_z(k2, i2, set); }
-          if (g.training) bulk_wait<1>(); else bulk_wait<0>();          // group A: the fp16 rows are complete in global memory
         }
-        if (hs == 0) {
-          __syncwarp();
-          if (lane == 1) flag_release_add(flags + t);                   // a lane with no bulk copies in flight publishes the tile
+        tr.ev(1, k, t);
+        __syncwarp();
+        if (lane == 1) flag_release_add(flags + t);                     // a lane with no bulk copies in flight publishes the tile
+        if (lane == 0) {
+          if (g.training) bulk_wait_read<0>();                         // the boxes of this set may be refilled
+          tr.ev(2, k, t);
+          if (ahead_valid()) { load_z(k2, i2, set); ahead_next(); }
         }
         tr.ev(3, k, t);
         n_tile++;
-        // hazards: set `set` (gate boxes + fp16 box) is next written for tile n_tile + 2; the issuer's bulk_wait of THIS tile's store
-        // precedes its arrival at the bar.sync of tile n_tile + 1, which every thread passes before touching tile n_tile + 2
       }
     }
-    if (issuer) bulk_wait<0>();                                          // the last gate boxes have left shared memory
+    if (lane == 0) bulk_wait<0>();                                       // the last gate boxes have left shared memory
   }
   tc_fence_before();
   __syncthreads();

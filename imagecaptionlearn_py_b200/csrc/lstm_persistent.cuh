@@ -113,6 +113,27 @@ __global__ void k_pack_whh_fwd(const float* __restrict__ Whh, float* __restrict_
 // fast gate nonlinearities for the fused epilogues: ex2.approx-based, abs. error ~2e-7 (vs 1e-3 parity tolerance)
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// The four gate nonlinearities of one LSTM cell with ONE reciprocal (Montgomery's batch inversion): sigma(x) = 1/(1+e^-x) and
+// tanh(x) = 1 - 2/(1+e^2x) share r = 1/((1+a)(1+b)(1+c)(1+d)), so a cell costs 4 ex2 + 1 rcp on the MUFU pipe (16 lanes per
+// clock per SM, the scarce unit of the fused epilogue) instead of 4 ex2 + 4 rcp; the extra products run on the FMA pipe.  Inputs are
+// clamped to +-20 (sigma) / +-10 (tanh) so that the product of the four denominators stays below 6e34: the clamped functions differ
+// from the exact ones by < 5e-9.  xf already includes the forget bias.
+__device__ __forceinline__ void lstm_gates_fast(float xi, float xj, float xf, float xo, float& si, float& tj, float& sf, float& so) {
+  constexpr float L2E = 1.4426950408889634f;
+  xi = fminf(fmaxf(xi, -20.0f), 20.0f); xf = fminf(fmaxf(xf, -20.0f), 20.0f); xo = fminf(fmaxf(xo, -20.0f), 20.0f);
+  xj = fminf(fmaxf(xj, -10.0f), 10.0f);
+  const float A = 1.0f + ex2_approx(-L2E * xi), B = 1.0f + ex2_approx(2.0f * L2E * xj);
+  const float Cf = 1.0f + ex2_approx(-L2E * xf), D = 1.0f + ex2_approx(-L2E * xo);
+  const float AB = A * B, CD = Cf * D;
+  const float r = rcp_approx(AB * CD);
+  const float rAB = r * CD, rCD = r * AB;            // 1 / (A B), 1 / (C D)
+  si = rAB * B;
+  tj = fmaf(-2.0f * rAB, A, 1.0f);
+  sf = rCD * D;
+  so = rCD * Cf;
+}
 
 constexpr int RP_EW = 8;          // epilogue warps: two per TMEM lane quarter, splitting the slice's units
 constexpr int RP_MAXTPC = 4;      // tiles per CTA whose cell state c is carried in registers across the steps

@@ -25,14 +25,14 @@ buf = np.zeros((4, 2048, 4), np.int64)
 _cabi.check(L.icl_rec_trace(sess.handle, cta, _cabi.np_ptr(buf)))
 ph = (C.c_float * 8)(); L.icl_phase_ms(sess.handle, ph); print("phases", [round(x, 3) for x in ph])
 names = ["producer: 0 wait flag, 1 flag seen, 2 loads issued", "mma: 0 slot free, 1 first k-block landed, 2 committed",
-         "publisher: 0 tile handed over, 1 published", "epilogue(q0,h0): 0 start, 1 x-proj boxes landed, 2 accumulator ready, 3 handed over"]
+         "store warp: 0 boxes ready, 1 stores issued + fp16 rows complete, 2 store reads done, 3 next x-proj requested", "cell warp 0: 0 start, 1 x-proj boxes landed, 2 accumulator ready, 4 cells done, 3 handed to the store warp"]
 t0 = min(buf[r][buf[r][:, 0] >= 0][:, 3].min() for r in range(4) if (buf[r][:, 0] >= 0).any())
-K = int(os.environ.get("KSTEP", "5"))
+KS = [int(x) for x in os.environ.get("KSTEP", "5").split(",")]
 for r in range(4):
     ev = buf[r][buf[r][:, 0] >= 0]
     print("==", names[r], "|", len(ev), "events")
     for e, k, t, c in ev:
-        if k in (K, K + 1):
+        if k in KS:
             print("   k=%d t=%2d ev%d %9.2f us" % (k, t, e, (c - t0) / 1965.0))
     if len(ev):
         print("   last: %.2f us" % ((ev[-1, 3] - t0) / 1965.0))
