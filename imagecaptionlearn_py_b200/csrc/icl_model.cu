@@ -5,6 +5,9 @@
 #include "gemm_tcgen05.cuh"
 #include "lstm_persistent.cuh"
 #include "lstm_bptt.cuh"
+#ifdef ICL_EXPERIMENTS
+#include "lstm_bptt_ns.cuh"     // k_bptt_nsplit: measured slower than k_bptt_cluster (0.66 vs 0.36 ms), see DESIGN.md section 7
+#endif
 #include "lstm_fwd16.cuh"
 
 #include <algorithm>
@@ -167,6 +170,13 @@ struct icl_model {
   bool bp_on = false, bp_cluster = true;     // bp_cluster: k_bptt_cluster (whole recurrence in one launch) when H <= 336
   int bp_cs = 4;
   BpttMaps bp_maps;
+  // K3 second generation (lstm_bptt_ns.cuh): output units split over an 8-CTA cluster, fp16 operands with per-row scales
+  bool ns_on = false, wb_dirty = true;
+  int ns_UN = 0;
+  __half* dZ16[2] = {}; float* S16[2] = {}; __half* Wb16[2] = {};
+#ifdef ICL_EXPERIMENTS
+  BpttNsMaps ns_maps;
+#endif
   int n_sms = 148;
   int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
   float last_ms = 0.f;
@@ -524,6 +534,42 @@ static int bptt_init(icl_model* m) {
   return 0;
 }
 
+
+#ifdef ICL_EXPERIMENTS
+template <int UN> static int ns_setup(icl_model* m) {
+  using C = BNS<UN>;
+  const int SW128 = (int)CU_TENSOR_MAP_SWIZZLE_128B;
+  const uint64_t RC = (uint64_t)m->rows_cap;
+  for (int d = 0; d < 2; d++) {
+    CK(cudaMalloc((void**)&m->dZ16[d], RC * C::KTOT * 2)); CK(cudaMemset(m->dZ16[d], 0, RC * C::KTOT * 2));
+    CK(cudaMalloc((void**)&m->S16[d], RC * BN_CS * 4)); CK(cudaMemset(m->S16[d], 0, RC * BN_CS * 4));
+    CK(cudaMalloc((void**)&m->Wb16[d], (size_t)BN_CS * C::NP * C::KTOT * 2));
+    int r = TmaCache::get16(m->dZ16[d], (uint64_t)C::KTOT, RC, (uint64_t)C::KTOT, 64, 128, SW128, &m->ns_maps.a[d]);
+    if (!r) r = TmaCache::get16(m->Wb16[d], (uint64_t)C::KTOT, (uint64_t)BN_CS * C::NP, (uint64_t)C::KTOT, 64, C::NP, SW128, &m->ns_maps.w[d]);
+    if (r) return fail("cuTensorMapEncodeTiled failed (k_bptt_nsplit)");
+  }
+  if (cudaFuncSetAttribute(k_bptt_nsplit<UN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(k_bptt_nsplit<UN>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
+    return fail("cudaFuncSetAttribute(k_bptt_nsplit) failed");
+  return 0;
+}
+static int ns_init(icl_model* m) {
+  const int H = m->H;
+  m->ns_on = m->bp_on && H % 4 == 0 && H <= 320 && getenv("ICL_BPTT_NSPLIT") && atoi(getenv("ICL_BPTT_NSPLIT")) != 0;
+  if (!m->ns_on) return 0;
+  m->ns_UN = H <= 64 ? 8 : H <= 128 ? 16 : H <= 224 ? 28 : 40;
+  switch (m->ns_UN) {
+    case 8: return ns_setup<8>(m);
+    case 16: return ns_setup<16>(m);
+    case 28: return ns_setup<28>(m);
+    default: return ns_setup<40>(m);
+  }
+}
+
+#else
+static int ns_init(icl_model*) { return 0; }
+#endif
+
 // ----------------------------------------------------------------------------- API
 extern "C" const char* icl_last_error(void) { return g_err; }
 extern "C" int icl_version(void) { return 2; }
@@ -549,7 +595,7 @@ extern "C" void icl_destroy(icl_model* m) {
     F(m->XH[d]); F(m->Z[d]); F(m->Hx[d]); F(m->Cc[d]); F(m->dHout[d]); F(m->dhrec[d]); F(m->dcc[d]); F(m->R[d]);
   }
   F(m->Wp[0]); F(m->Wp[1]); F(m->rp_flags); F(m->rp_trace); F(m->rp_bar);
-  F(m->Hp16[0]); F(m->Hp16[1]); F(m->Wp16[0]); F(m->Wp16[1]); F(m->X16[0]); F(m->X16[1]); F(m->Wih16[0]); F(m->Wih16[1]);
+  F(m->Hp16[0]); F(m->Hp16[1]); F(m->Wp16[0]); F(m->Wp16[1]); F(m->dZ16[0]); F(m->dZ16[1]); F(m->S16[0]); F(m->S16[1]); F(m->Wb16[0]); F(m->Wb16[1]); F(m->X16[0]); F(m->X16[1]); F(m->Wih16[0]); F(m->Wih16[1]);
   F(m->d_partial); F(m->d_gnorm);
   for (auto& h : m->heads) {
     F(h.bi); F(h.dbi); F(h.dA); F(h.dBuf); for (auto a : h.act) F(a); for (auto a : h.dzb) F(a);
@@ -719,6 +765,7 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   if (m->rp_U && rec16_init(m) != 0) { icl_destroy(m); *out = nullptr; return -1; }
   if (k1_init(m) != 0) { icl_destroy(m); *out = nullptr; return -1; }
   if (bptt_init(m) != 0) { icl_destroy(m); *out = nullptr; return -1; }
+  if (ns_init(m) != 0) { icl_destroy(m); *out = nullptr; return -1; }
 #undef CKD
   return 0;
 }
@@ -803,7 +850,7 @@ extern "C" int icl_set_tensor(icl_model* m, int kind, const char* name, const fl
   const Param& p = m->params[it->second];
   CK(cudaStreamSynchronize(m->stream));
   CK(cudaMemcpy(kind_buf(m, kind) + p.off, host, (size_t)p.rows * p.cols * 4, cudaMemcpyHostToDevice));
-  if (kind == 0) m->pr_dirty = m->wp_dirty = m->wih_dirty = true;
+  if (kind == 0) m->pr_dirty = m->wp_dirty = m->wih_dirty = m->wb_dirty = true;
   return 0;
 }
 extern "C" int icl_get_step(icl_model* m, int64_t* t) { *t = m->step; return 0; }
@@ -821,7 +868,7 @@ extern "C" int icl_wait_head_grads(icl_model* m, void* cuda_stream) {
   CK(cudaStreamWaitEvent((cudaStream_t)cuda_stream, m->ev_heads, 0));
   return 0;
 }
-extern "C" int icl_param_buffer(icl_model* m, void** p, int64_t* n) { *p = m->P; *n = m->n_params; m->pr_dirty = m->wp_dirty = m->wih_dirty = true; return 0; }
+extern "C" int icl_param_buffer(icl_model* m, void** p, int64_t* n) { *p = m->P; *n = m->n_params; m->pr_dirty = m->wp_dirty = m->wih_dirty = m->wb_dirty = true; return 0; }
 extern "C" int icl_kernel_launches(icl_model* m, int64_t* n) { *n = m->launches; return 0; }
 extern "C" int icl_last_step_ms(icl_model* m, float* ms) { *ms = m->last_ms; return 0; }
 extern "C" int icl_copy_bytes(icl_model* m, int64_t* h2d, int64_t* d2h) { *h2d = m->h2d_bytes; *d2h = m->d2h_bytes; return 0; }
@@ -1407,6 +1454,50 @@ static int rec_backward_cluster(icl_model* m) {
   return 0;
 }
 
+
+#ifdef ICL_EXPERIMENTS
+// K3 experiment (ICL_BPTT_NSPLIT=1 in an -DICL_EXPERIMENTS build): k_bptt_nsplit (lstm_bptt_ns.cuh), ONE launch: an 8-CTA cluster per (direction,
+// 128-row tile), the clusters in chain-length order (the longest sequences first; a batch with more than 18 clusters runs in waves)
+template <int UN> static int ns_launch(icl_model* m, const BpttNsArgs& a, int tiles, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(BN_CS, (unsigned)(2 * tiles), 1);
+  cfg.blockDim = dim3(BN_THREADS); cfg.dynamicSmemBytes = BNS<UN>::SMEM; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = BN_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_bptt_nsplit<UN>, m->ns_maps, a);
+  if (e != cudaSuccess) return fail("k_bptt_nsplit<%d> launch failed: %s", UN, cudaGetErrorString(e));
+  m->launches++;
+  return 0;
+}
+static int rec_backward_nsplit(icl_model* m) {
+  const int E = m->E, H = m->H, UN = m->ns_UN;
+  cudaStream_t st = m->stream;
+  if (m->wb_dirty) {
+    const float* W0 = m->P + m->params[m->pK[0]].off + (size_t)E * 4 * H;
+    const float* W1 = m->P + m->params[m->pK[1]].off + (size_t)E * 4 * H;
+    const int NP = (UN + 15) / 16 * 16;
+    k_pack_whh_bwd16<<<dim3(148, 2), 256, 0, st>>>(W0, W1, m->Wb16[0], m->Wb16[1], H, UN, NP, BN_CS * 4 * UN);
+    LAUNCHED(m);
+    m->wb_dirty = false;
+  }
+  BpttNsArgs a;
+  for (int d = 0; d < 2; d++) { a.Z[d] = m->Z[d]; a.Cc[d] = m->Cc[d]; a.dHout[d] = m->dHout[d]; a.dZ16[d] = m->dZ16[d]; a.S16[d] = m->S16[d]; }
+  a.off = m->d_off; a.nact = m->d_nact; a.H = H; a.Tmax = m->Tmax; a.round_ops = m->round_ops; a.tile0 = 0;
+  a.trace = m->rp_trace; a.trace_cta = m->rp_trace_cta;
+  const int tiles = (m->n_active[0] + 127) / 128;
+  switch (UN) {
+    case 8: return ns_launch<8>(m, a, tiles, st);
+    case 16: return ns_launch<16>(m, a, tiles, st);
+    case 28: return ns_launch<28>(m, a, tiles, st);
+    default: return ns_launch<40>(m, a, tiles, st);
+  }
+}
+
+#else
+static int rec_backward_nsplit(icl_model*) { return fail("k_bptt_nsplit is not in this build"); }
+#endif
+
 // K3 (fp32 validation mode): one cell kernel + one split-K GEMM per step and direction, directions interleaved on two streams
 static int rec_backward_steps(icl_model* m) {
   const int E = m->E, H = m->H, S = m->S;
@@ -1456,7 +1547,8 @@ static int lstm_backward(icl_model* m) {
   cudaStream_t st = m->stream;
   if (m->Ntok == 0) return 0;
   PH_BEGIN(m, PH_REC_BWD);
-  if (m->bp_on && m->bp_cluster && m->Tmax <= RP_MAXT) CKI(rec_backward_cluster(m));   // both write the pad rows of dZ as zeros
+  if (m->ns_on && m->Tmax <= RP_MAXT) CKI(rec_backward_nsplit(m));                       // all three write the pad rows of dZ as zeros
+  else if (m->bp_on && m->bp_cluster && m->Tmax <= RP_MAXT) CKI(rec_backward_cluster(m));
   else if (m->bp_on) CKI(rec_backward_fused(m));
   else {
     if (m->rp_U != 0 && m->rp_on && m->rp_bwd_on && m->Tmax <= RP_MAXT) CKI(rec_backward_persistent(m));
@@ -1549,7 +1641,8 @@ static int apply_update(icl_model* m, double extra_sumsq) {
     LAUNCHED(m);
   }
   m->wih_dirty = true;
-  if (!getenv("ICL_DEBUG_STALE_WP")) m->wp_dirty = true;   // the packed recurrent weights of the persistent forward kernel follow
+  if (!getenv("ICL_DEBUG_STALE_WP")) m->wp_dirty = true;
+  m->wb_dirty = true;   // the packed recurrent weights of the persistent forward kernel follow
                                                              // the update (the env knob exists so that a test can prove it catches staleness)
   PH_END(m, PH_UPDATE);
   return 0;

@@ -1,4 +1,4 @@
-"""Bring-up: per-step timeline of one CTA of k_bptt_cluster on the card2048 bench batch (clock64 events)."""
+"""Bring-up: per-step timeline of one CTA of k_bptt_nsplit (ICL_BPTT_NSPLIT=0: k_bptt_cluster) on the card2048 bench batch (clock64 events of cell warp 0)."""
 import ctypes as C, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -28,7 +28,8 @@ ph = (C.c_float * 8)(); L.icl_phase_ms(sess.handle, ph); print("phases", list(ph
 names = ["producer", "mma", "epilogue(w2)"]
 ev = buf[2][buf[2][:, 0] >= 0]
 t0 = ev[0, 3]
-labels = {0: "step start", 1: "tmem_full", 2: "parked", 3: "S1", 4: "final done", 5: "S23"}
+labels = ({0: "step start", 1: "tmem_full", 2: "staged", 3: "bounds done", 4: "cells done", 5: "cluster barrier"} if os.environ.get("ICL_BPTT_NSPLIT", "1") != "0"
+          else {0: "step start", 1: "tmem_full", 2: "parked", 3: "S1", 4: "final done", 5: "S23"})
 last = t0
 for e, k, t, c in ev[:int(os.environ.get("NEV", "80"))]:
     print("  k=%2d %-11s %8.2f us  (+%.2f)" % (k, labels.get(int(e), str(e)), (c - t0) / 1965.0, (c - last) / 1965.0))
