@@ -677,7 +677,11 @@ class Session(object):
         b.ex_gid_offset = rank * max(h["batch_size"] for h in g.heads)
         return b
 
-    def run(self, op_kind, batch_tensor_list, keep_in, keep, include_labels, head_ids=None):
+    def run(self, op_kind, batch_tensor_list=None, keep_in=1.0, keep=1.0, include_labels=False, head_ids=None):
+        if isinstance(op_kind, Op) and op_kind.kind == "init":        # sess.run(tf.global_variables_initializer()), icl_core_lstm.py:110
+            self.ensure()
+            self.initialize()
+            return None
         L = _cabi.lib()
         g = self.graph
         if head_ids is None and len(batch_tensor_list) != len(g.heads):
@@ -835,6 +839,23 @@ class Saver(object):
             return
         with np.load(path + ".npz") as z:
             sess.load_state({k: z[k] for k in z.files})
+
+
+class train(object):
+    """`tf.train` as the reference scripts use it: `tf.train.Saver(max_to_keep=100)` (icl_core_lstm.py:107)."""
+    Saver = Saver
+
+
+def global_variables_initializer():
+    """`sess.run(tf.global_variables_initializer())` (icl_core_lstm.py:110): creates the device model and initialises it."""
+    return Op("init")
+
+
+def dump_tf_vars():
+    """nn_utils/core.py:684-697 prints the graph's trainable variables; here: the heads the graph holds (the variables get their
+    TF names when a Session creates the device model)."""
+    g = _graph
+    print("bidirectional_lstm: %s; heads: %s" % (g.lstm, [(h.get("scope", ""), h.get("task")) for h in g.heads]))
 
 
 def _debug_mask(sess, stream, n, keep, seed=None):

@@ -403,6 +403,17 @@ struct TmaCache {
     *out = tm;
     return 0;
   }
+  // 3-D fp32 tensor (uncached): dims {d0, d1, d2}, byte strides of dims 1 and 2, box {b0, b1, b2}; OOB reads give zeros, OOB writes are dropped
+  static int get3(const float* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes, uint64_t s2_bytes, uint32_t b0, uint32_t b1,
+                  uint32_t b2, int swizzle, CUtensorMap* out) {
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {s1_bytes, s2_bytes};
+    cuuint32_t box[3] = {b0, b1, b2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          (CUtensorMapSwizzle)swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+  }
   // 2-D fp16 tensor (uncached: built once at create): dim0 x dim1 halves, row pitch ld halves
   static int get16(const void* ptr, uint64_t dim0, uint64_t dim1, uint64_t ld, uint32_t box0, uint32_t box1, int swizzle, CUtensorMap* out) {
     cuuint64_t dims[2] = {dim0, dim1};

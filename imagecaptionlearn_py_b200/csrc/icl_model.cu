@@ -163,9 +163,12 @@ struct icl_model {
   CUtensorMap k1_ta[2], k1_tb[2], k1_tc[2];
   // second-generation forward recurrence (lstm_fwd16.cuh): fp16 recurrent operands, double-buffered x-projection boxes
   bool rf_on = false;
-  int rf_UP = 0, rf_KP = 0, rf_nkb = 0, rf_nk16 = 0;
-  __half* Hp16[2] = {}; __half* Wp16[2] = {};
-  RecFwd16Maps rf_maps;
+  struct RfVar {                 // one slicing of the fp16 forward recurrence (k_rec_fwd16<U>): U = 20 (H % 20 == 0) and / or U = 16 (any H)
+    bool on = false, dirty = true;
+    int U = 0, UP = 0, nsl = 0, KP = 0, nkb = 0, nk16 = 0, maxtpc = 0;
+    __half* Hp16[2] = {}; __half* Wp16[2] = {};
+    RecFwd16Maps maps;
+  } rf20, rf16;
   // fused BPTT step kernel (lstm_bptt.cuh): default backward recurrence in tensor-core mode
   bool bp_on = false, bp_cluster = true;     // bp_cluster: k_bptt_cluster (whole recurrence in one launch) when H <= 336
   int bp_cs = 4;
@@ -463,31 +466,63 @@ template <int U> static int rec16_set_attr(int nkb) {
   cudaError_t e = cudaFuncSetAttribute(k_rec_fwd16<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, rec_fwd16_smem<U>(nkb));
   return e == cudaSuccess ? 0 : fail("cudaFuncSetAttribute(k_rec_fwd16): %s", cudaGetErrorString(e));
 }
+static int rec16_setup(icl_model* m, icl_model::RfVar& v, int U) {
+  const int H = m->H;
+  v.U = U; v.UP = U == 20 ? RF<20>::UP : RF<16>::UP; v.maxtpc = U == 20 ? RF<20>::MAXTPC : RF<16>::MAXTPC;
+  v.nsl = (H + U - 1) / U;
+  v.KP = (v.nsl * v.UP + 63) / 64 * 64;
+  v.nkb = v.KP / 64;
+  v.nk16 = (v.nsl * v.UP + 15) / 16;
+  const size_t smem = U == 20 ? rec_fwd16_smem<20>(v.nkb) : rec_fwd16_smem<16>(v.nkb);
+  if (smem > 227 * 1024 || v.nkb > 10) return 0;                     // stays off
+  const uint64_t RC = (uint64_t)m->rows_cap;
+  const int NONE = (int)CU_TENSOR_MAP_SWIZZLE_NONE, SW128 = (int)CU_TENSOR_MAP_SWIZZLE_128B, SW64 = (int)CU_TENSOR_MAP_SWIZZLE_64B;
+  for (int d = 0; d < 2; d++) {
+    CK(cudaMalloc((void**)&v.Hp16[d], RC * v.KP * 2)); CK(cudaMemset(v.Hp16[d], 0, RC * v.KP * 2));
+    const size_t wn = (size_t)v.nsl * 4 * U * v.KP;
+    CK(cudaMalloc((void**)&v.Wp16[d], wn * 2)); CK(cudaMemset(v.Wp16[d], 0, wn * 2));
+    int r = TmaCache::get16(v.Hp16[d], (uint64_t)v.KP, RC, (uint64_t)v.KP, 64, 128, SW128, &v.maps.a[d]);
+    if (!r) r = TmaCache::get16(v.Wp16[d], (uint64_t)v.KP, (uint64_t)v.nsl * 4 * U, (uint64_t)v.KP, 64, 4 * U, SW128, &v.maps.w[d]);
+    if (!r) r = TmaCache::get16(v.Hp16[d], (uint64_t)v.KP, RC, (uint64_t)v.KP, v.UP, 32, NONE, &v.maps.hp16[d]);
+    if (r) return fail("cuTensorMapEncodeTiled failed (%d) for the fp16 recurrence maps", r);
+    if (U == 16) {      // [rows][4 gates][H] as a 3-D tensor / [rows][H]: boxes of the last slice are clipped at H; 64-byte rows, swizzled
+      r = TmaCache::get3(m->Z[d], (uint64_t)H, 4, RC, (uint64_t)H * 4, (uint64_t)4 * H * 4, 16, 1, 32, SW64, &v.maps.z[d]);
+      if (r) return fail("cuTensorMapEncodeTiled failed (%d) for the 3-D gate map", r);
+      CKI(box_map(m, m->Cc[d], H, RC, 16, 32, SW64, &v.maps.cc[d]));
+    } else {
+      CKI(box_map(m, m->Z[d], 4 * H, RC, U, 32, NONE, &v.maps.z[d]));
+      CKI(box_map(m, m->Cc[d], H, RC, U, 32, NONE, &v.maps.cc[d]));
+    }
+  }
+  CKI(U == 20 ? rec16_set_attr<20>(v.nkb) : rec16_set_attr<16>(v.nkb));
+  v.on = true;
+  return 0;
+}
 static int rec16_init(icl_model* m) {
   m->rf_on = m->rp_U != 0;
   if (const char* e = getenv("ICL_REC_FP16")) m->rf_on = m->rf_on && atoi(e) != 0;
   if (!m->rf_on) return 0;
-  const int H = m->H, U = m->rp_U;
-  m->rf_UP = U == 20 ? RF<20>::UP : RF<16>::UP;
-  m->rf_KP = (m->rp_nsl * m->rf_UP + 63) / 64 * 64;
-  m->rf_nkb = m->rf_KP / 64;
-  m->rf_nk16 = (m->rp_nsl * m->rf_UP + 15) / 16;
-  const size_t smem = U == 20 ? rec_fwd16_smem<20>(m->rf_nkb) : rec_fwd16_smem<16>(m->rf_nkb);
-  if (smem > 227 * 1024) { m->rf_on = false; return 0; }
-  const uint64_t RC = (uint64_t)m->rows_cap;
-  const int NONE = (int)CU_TENSOR_MAP_SWIZZLE_NONE, SW128 = (int)CU_TENSOR_MAP_SWIZZLE_128B;
-  for (int d = 0; d < 2; d++) {
-    CK(cudaMalloc((void**)&m->Hp16[d], RC * m->rf_KP * 2)); CK(cudaMemset(m->Hp16[d], 0, RC * m->rf_KP * 2));
-    const size_t wn = (size_t)m->rp_nsl * 4 * U * m->rf_KP;
-    CK(cudaMalloc((void**)&m->Wp16[d], wn * 2)); CK(cudaMemset(m->Wp16[d], 0, wn * 2));
-    int r = TmaCache::get16(m->Hp16[d], (uint64_t)m->rf_KP, RC, (uint64_t)m->rf_KP, 64, 128, SW128, &m->rf_maps.a[d]);
-    if (!r) r = TmaCache::get16(m->Wp16[d], (uint64_t)m->rf_KP, (uint64_t)m->rp_nsl * 4 * U, (uint64_t)m->rf_KP, 64, 4 * U, SW128, &m->rf_maps.w[d]);
-    if (!r) r = TmaCache::get16(m->Hp16[d], (uint64_t)m->rf_KP, RC, (uint64_t)m->rf_KP, m->rf_UP, 32, NONE, &m->rf_maps.hp16[d]);
-    if (r) return fail("cuTensorMapEncodeTiled failed (%d) for the fp16 recurrence maps", r);
-    CKI(box_map(m, m->Z[d], 4 * H, RC, U, 32, NONE, &m->rf_maps.z[d]));
-    CKI(box_map(m, m->Cc[d], H, RC, U, 32, NONE, &m->rf_maps.cc[d]));
-  }
-  return U == 20 ? rec16_set_attr<20>(m->rf_nkb) : rec16_set_attr<16>(m->rf_nkb);
+  if (m->H % 20 == 0) CKI(rec16_setup(m, m->rf20, 20));
+  if (m->H % 4 == 0) CKI(rec16_setup(m, m->rf16, 16));
+  m->rf_on = m->rf20.on || m->rf16.on;
+  return 0;
+}
+// the slicing for this batch: U = 20 where H allows it, else U = 16 (any H; the whole h tile fits its ring).  On card2048 the two
+// measure the same (0.314 - 0.330 vs 0.319 - 0.322 ms, profiles/r2j_*): ICL_RF_U=16|20 forces one for A/B runs
+static icl_model::RfVar* rf_pick(icl_model* m) {
+  if (!m->rf_on || !m->rp_on || m->Tmax > RP_MAXT) return nullptr;
+  const int tiles = (m->n_active[0] + 127) / 128;
+  auto fits = [&](icl_model::RfVar& v) {
+    if (!v.on) return false;
+    const int P = std::max(1, std::min(148 / (2 * v.nsl), tiles));
+    return (tiles + P - 1) / P <= v.maxtpc;
+  };
+  static const int force = getenv("ICL_RF_U") ? atoi(getenv("ICL_RF_U")) : 0;      // A/B: 16 or 20
+  if (force == 20 && fits(m->rf20)) return &m->rf20;
+  if (force == 16 && fits(m->rf16)) return &m->rf16;
+  if (fits(m->rf20)) return &m->rf20;
+  if (fits(m->rf16)) return &m->rf16;
+  return nullptr;
 }
 
 // make input set s the "current" one: the device pointers every launch site reads
@@ -595,7 +630,7 @@ extern "C" void icl_destroy(icl_model* m) {
     F(m->XH[d]); F(m->Z[d]); F(m->Hx[d]); F(m->Cc[d]); F(m->dHout[d]); F(m->dhrec[d]); F(m->dcc[d]); F(m->R[d]);
   }
   F(m->Wp[0]); F(m->Wp[1]); F(m->rp_flags); F(m->rp_trace); F(m->rp_bar);
-  F(m->Hp16[0]); F(m->Hp16[1]); F(m->Wp16[0]); F(m->Wp16[1]); F(m->dZ16[0]); F(m->dZ16[1]); F(m->S16[0]); F(m->S16[1]); F(m->Wb16[0]); F(m->Wb16[1]); F(m->X16[0]); F(m->X16[1]); F(m->Wih16[0]); F(m->Wih16[1]);
+  for (auto* v : {&m->rf20, &m->rf16}) { F(v->Hp16[0]); F(v->Hp16[1]); F(v->Wp16[0]); F(v->Wp16[1]); } F(m->dZ16[0]); F(m->dZ16[1]); F(m->S16[0]); F(m->S16[1]); F(m->Wb16[0]); F(m->Wb16[1]); F(m->X16[0]); F(m->X16[1]); F(m->Wih16[0]); F(m->Wih16[1]);
   F(m->d_partial); F(m->d_gnorm);
   for (auto& h : m->heads) {
     F(h.bi); F(h.dbi); F(h.dA); F(h.dBuf); for (auto a : h.act) F(a); for (auto a : h.dzb) F(a);
@@ -1080,6 +1115,7 @@ __global__ void k_zero_pad_rows(float* __restrict__ buf0, float* __restrict__ bu
 }
 
 static bool rec_usable(icl_model* m) {
+  if (m->rf_on) return rf_pick(m) != nullptr;
   if (m->rp_U == 0 || !m->rp_on || m->Tmax > RP_MAXT) return false;
   int tiles = (m->n_active[0] + 127) / 128, P = std::max(1, std::min(148 / (2 * m->rp_nsl), tiles));
   return (tiles + P - 1) / P <= RP_MAXTPC;          // the kernel carries the cell state of <= RP_MAXTPC tiles per CTA in registers
@@ -1097,29 +1133,33 @@ static RecArgs rec_args(icl_model* m, int training) {
 
 static int rec_forward_fp16(icl_model* m, int training) {
   cudaStream_t st = m->stream;
-  const int E = m->E, H = m->H, U = m->rp_U;
-  if (m->wp_dirty) {
+  icl_model::RfVar* vp = rf_pick(m);
+  if (!vp) return fail("k_rec_fwd16: no slicing fits this batch");
+  icl_model::RfVar& v = *vp;
+  const int E = m->E, H = m->H, U = v.U;
+  if (m->wp_dirty) { m->rf20.dirty = m->rf16.dirty = true; m->wp_dirty = false; }
+  if (v.dirty) {
     const float* W0 = m->P + m->params[m->pK[0]].off + (size_t)E * 4 * H;
     const float* W1 = m->P + m->params[m->pK[1]].off + (size_t)E * 4 * H;
-    k_pack_whh_fwd16<<<dim3((4 * H + 31) / 32, (H + 31) / 32, 2), dim3(32, 8), 0, st>>>(W0, W1, m->Wp16[0], m->Wp16[1], H, U, m->rf_UP, m->rp_nsl,
-                                                                                      m->rf_KP);
+    k_pack_whh_fwd16<<<dim3((4 * H + 31) / 32, (H + 31) / 32, 2), dim3(32, 8), 0, st>>>(W0, W1, v.Wp16[0], v.Wp16[1], H, U, v.UP, v.nsl, v.KP);
     LAUNCHED(m);
-    m->wp_dirty = false;
+    v.dirty = false;
   }
   CK(zero_async(m->rp_flags, (size_t)2 * m->rp_max_tiles * 4, st));
   RecFwd16Args a;
-  a.off = m->d_off; a.nact = m->d_nact; a.Tmax = m->Tmax; a.H = H; a.nsl = m->rp_nsl;
+  a.off = m->d_off; a.nact = m->d_nact; a.Tmax = m->Tmax; a.H = H; a.nsl = v.nsl;
   const int tiles = (m->n_active[0] + 127) / 128;
-  a.P = std::max(1, std::min(148 / (2 * m->rp_nsl), tiles));
-  a.nkb = m->rf_nkb; a.nk16 = m->rf_nk16; a.nst = U == 20 ? rec_fwd16_stages<20>(a.nkb) : rec_fwd16_stages<16>(a.nkb); a.max_tiles = m->rp_max_tiles; a.training = training; a.ldx = m->ldx; a.flags = m->rp_flags;
+  a.P = std::max(1, std::min(148 / (2 * v.nsl), tiles));
+  a.nkb = v.nkb; a.nk16 = v.nk16; a.nst = U == 20 ? rec_fwd16_stages<20>(a.nkb) : rec_fwd16_stages<16>(a.nkb);
+  a.max_tiles = m->rp_max_tiles; a.training = training; a.ldx = m->ldx; a.flags = m->rp_flags;
   for (int d = 0; d < 2; d++) { a.Z[d] = m->Z[d]; a.Cc[d] = m->Cc[d]; a.Hx[d] = m->Hx[d]; a.Hp[d] = m->Hp[d]; }
   a.trace = m->rp_trace; a.trace_cta = m->rp_trace_cta;
-  void* args[] = {(void*)&m->rf_maps, (void*)&a};
+  void* args[] = {(void*)&v.maps, (void*)&a};
   dim3 grid(2 * a.P * a.nsl), block(RF_THREADS);
   cudaError_t e;
   if (U == 20) e = cudaLaunchCooperativeKernel((void*)k_rec_fwd16<20>, grid, block, args, rec_fwd16_smem<20>(a.nkb), st);
   else e = cudaLaunchCooperativeKernel((void*)k_rec_fwd16<16>, grid, block, args, rec_fwd16_smem<16>(a.nkb), st);
-  if (e != cudaSuccess) return fail("k_rec_fwd16 launch failed: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) return fail("k_rec_fwd16<%d> launch failed: %s", U, cudaGetErrorString(e));
   m->launches++;
   return 0;
 }

@@ -26,11 +26,14 @@
 
 namespace icl {
 
-constexpr int RF_MAXST = 6, RF_EW = 8, RF_SW = 4, RF_THREADS = 64 + 32 * (RF_EW + RF_SW), RF_MAXTPC = 4, RF_MAXACC = 8;
+constexpr int RF_MAXST = 6, RF_EW = 8, RF_SW = 4, RF_THREADS = 64 + 32 * (RF_EW + RF_SW) + 32 /* counter-polling warp */, RF_MAXACC = 8;
 template <int U> struct RF {
   static constexpr int UP = (U * 2) % 16 == 0 ? U : (U + 7) / 8 * 8;         // units of a slice as stored in Hp16 (padded to 16 bytes)
   static constexpr int N = 4 * U;
   static constexpr int U0 = RecSplit<U>::U0, U1 = RecSplit<U>::U1;
+  static constexpr bool SWZ = U == 16;        // 64-byte box rows: SWIZZLE_64B boxes (a lane-per-row float4 read of plain 64-byte rows is a
+                                              // 4-way bank conflict; 80-byte rows are conflict-free as they are) + the ragged-H tensor maps
+  static constexpr int MAXTPC = U == 16 ? 6 : 4;                              // tiles per CTA whose cell state is carried in registers
   static constexpr int ZBOX = 32 * U * 4;                                     // one gate box of a quarter
   static constexpr int HBOX = 32 * UP * 2;                                    // the fp16 h box of a quarter
 };
@@ -76,13 +79,29 @@ __global__ void k_pack_whh_fwd16(const float* __restrict__ Whh0, const float* __
   }
 }
 
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+               "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
+// U = 20: H must be a multiple of 20; the x-projection / gate map `z` is 2-D over [rows][4H].
+// U = 16: any H (multiple of 4): `z` is 3-D over [rows][4 gates][H] and `cc` 2-D over [rows][H], so the boxes of the LAST slice are
+// clipped at H (loads read zeros, stores skip) instead of running into the next gate's columns; the slice's pad units compute
+// finite values that are never stored (their W_hh rows and fp16 h columns are zero).
 template <int U>
 __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_constant__ RecFwd16Maps maps, const RecFwd16Args g) {
   constexpr int N = RF<U>::N, UP = RF<U>::UP, U0 = RF<U>::U0, U1 = RF<U>::U1, ZBOX = RF<U>::ZBOX, HBOX = RF<U>::HBOX;
+  constexpr int RF_MAXTPC = RF<U>::MAXTPC;
+  constexpr bool SWZ = RF<U>::SWZ;
   constexpr int NACC = (512 / N) < RF_MAXACC ? (512 / N) : RF_MAXACC;
   constexpr int QBYTES = 2 * 5 * ZBOX + 2 * HBOX;                            // per quarter: two sets of (4 gate boxes + c box) + two fp16 h boxes
   extern __shared__ uint8_t smem_raw[];
   __shared__ int s_off[RP_MAXT + 2], s_n[RP_MAXT + 2];
+  __shared__ int s_flagged;                                                 // tiles whose h_{k-1} rows are known to be published
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t sW = base;
@@ -101,6 +120,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
 
   for (int i = threadIdx.x; i <= Tmax; i += blockDim.x) { s_off[i] = g.off[i]; s_n[i] = g.nact[i]; }
   if (threadIdx.x == 0) {
+    s_flagged = 0;
     for (int s = 0; s < RF_MAXST; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     mbar_init(wfull, 1);
     for (int w = 0; w < 8; w++) { mbar_init(efull0 + 8 * w, 1); mbar_init(sready0 + 8 * w, 2); }
@@ -125,16 +145,51 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
   const unsigned per_step = (unsigned)(g.nsl * 4);                      // counter increments per (step, tile): slices x quarters
 
   if (warp == 0) {
-    if (lane == 0) {                                                   // ---- A producer (fp16 h_{k-1} tiles) + resident W slice
+    // ---- A producer (fp16 h_{k-1} tiles) + resident W slice.  The tile rate of the kernel is set HERE.  What the clock64 traces
+    // and tools/probe_tma.cu (profiles/r2_probe_tma*.txt) say: ONE thread gets a TMA load accepted every 300 - 430 ns whatever its
+    // size or the ring depth, several lanes issue concurrently (100 ns per load from six lanes); an ld.acquire.gpu of a publication
+    // counter is an L2 round trip of 1.2 - 1.6 us even when the tile was published long ago.  So: the counters are polled AHEAD by
+    // the last warp, which reports in shared memory how far the producer may go, and when the whole tile fits the ring (U = 16:
+    // NST == nkb) its k-blocks are requested by nkb lanes at once.  With a shallower ring (U = 20, H = 300: 3 stages for 6
+    // k-blocks) a stage's turn-around (~1.2 us) bounds the tile and one lane issues in order (parallel lanes measured slower there).
+    if (lane == 0) {
       mbar_expect_tx(wfull, (uint32_t)g.nkb * N * 128);
       for (int kb = 0; kb < g.nkb; kb++) tma_load_2d(sW + kb * N * 128, &maps.w[d], kb * 64, j * N, wfull);
+    }
+    auto wait_published = [&](int seq) {
+      const long long t0 = clock64();
+      for (;;) {
+        int v;
+        asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&s_flagged)) : "memory");
+        if (v > seq) break;
+        if (clock64() - t0 > 4000000000LL) __trap();
+      }
+      fence_async_all();
+    };
+    Tracer tr; tr.init(g.trace, g.trace_cta, 0);
+    if (lane != 0) tr.p = nullptr;
+    if (NST >= g.nkb) {
+      if (lane < g.nkb) {                                              // lane = k-block = ring stage
+        int seq = 0;
+        for (int k = 1; k < Tmax; k++) {
+          for (int t = p; t * RP_ROWS < s_n[k]; t += g.P, seq++) {
+            tr.ev(0, k, t);
+            wait_published(seq);
+            tr.ev(1, k, t);
+            mbar_wait(empty0 + 8 * lane, (seq & 1) ^ 1);
+            mbar_expect_tx(full0 + 8 * lane, 16384);
+            tma_load_2d(sA + lane * 16384, &maps.a[d], lane * 64, s_off[k] + t * RP_ROWS, full0 + 8 * lane);
+            tr.ev(2, k, t);
+          }
+        }
+      }
+    } else if (lane == 0) {
       uint32_t it = 0;
-      Tracer tr; tr.init(g.trace, g.trace_cta, 0);
+      int seq = 0;
       for (int k = 1; k < Tmax; k++) {
-        for (int t = p; t * RP_ROWS < s_n[k]; t += g.P) {
+        for (int t = p; t * RP_ROWS < s_n[k]; t += g.P, seq++) {
           tr.ev(0, k, t);
-          flag_wait(flags + t, per_step * k);
-          fence_async_all();
+          wait_published(seq);
           tr.ev(1, k, t);
           for (int kb = 0; kb < g.nkb; kb++, it++) {
             const uint32_t s = it % NST;
@@ -151,6 +206,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
       constexpr uint32_t idesc = make_idesc(0, false, false, RP_ROWS, N);   // kind::f16, fp16 x fp16 -> fp32
       mbar_wait(wfull, 0);
       uint32_t it = 0, acc = 0;
+      const bool par = NST >= g.nkb;                                   // lane-parallel producer: stage = k-block, phase = tile
       Tracer tr; tr.init(g.trace, g.trace_cta, 1);
       for (int k = 1; k < Tmax; k++) {
         for (int t = p; t * RP_ROWS < s_n[k]; t += g.P, acc++) {
@@ -159,8 +215,8 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
           tc_fence_after();
           tr.ev(0, k, t);
           for (int kb = 0; kb < g.nkb; kb++, it++) {
-            const uint32_t s = it % NST;
-            mbar_wait(full0 + 8 * s, (it / NST) & 1);
+            const uint32_t s = par ? (uint32_t)kb : it % NST;
+            mbar_wait(full0 + 8 * s, par ? (acc & 1) : ((it / NST) & 1));
             tc_fence_after();
             if (kb == 0) tr.ev(1, k, t);
             const int nk = min(4, g.nk16 - kb * 4);                    // UMMA_K = 16 halves = 32 bytes
@@ -212,8 +268,10 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
           tc_fence_after();
         }
         tr.ev(2, k, t);
-        float* zb = zset[set] + ubase;
+        float* zb = zset[set];
         __half* hbox = hbox0 + set * (HBOX / 2);
+        // position of unit chunk ch (4 floats) of this lane's row inside a gate box: plain, or XOR-ed as SWIZZLE_64B stores it
+        auto zpos = [&](int gate, int ch) { return gate * 32 * U + lane * U + (SWZ ? ((ch ^ ((lane >> 1) & 3)) << 2) : (ch << 2)); };
         const long row = o_k + t * RP_ROWS + 32 * q + lane;
         const bool has_next = t * RP_ROWS < n_k1;
         const long row_n = o_k1 + t * RP_ROWS + 32 * q + lane;
@@ -228,7 +286,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
             }
             float4 z4[4];
 #pragma unroll
-            for (int gate = 0; gate < 4; gate++) z4[gate] = *reinterpret_cast<const float4*>(zb + gate * 32 * U + lane * U + c * 4);
+            for (int gate = 0; gate < 4; gate++) z4[gate] = *reinterpret_cast<const float4*>(zb + zpos(gate, ubase / 4 + c));
             const float *zi = &z4[0].x, *zj = &z4[1].x, *zf = &z4[2].x, *zo = &z4[3].x;
             float si[4], tj[4], sf[4], so[4], hn[4], hr[4];
 #pragma unroll
@@ -245,14 +303,14 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
               // the gates go back into the x-projection boxes and out as four TMA boxes (the LSU path alone was the bottleneck:
               // every lane-per-row float4 store is 32 wavefronts); c / h / TF32 h stay on the LSU, the two engines overlap (moving
               // c to the LSU as well to free a 4th stage of the h_{k-1} ring measured slower: 0.337 vs 0.321 ms)
-              *reinterpret_cast<float4*>(zb + 0 * 32 * U + lane * U + c * 4) = make_float4(si[0], si[1], si[2], si[3]);
-              *reinterpret_cast<float4*>(zb + 1 * 32 * U + lane * U + c * 4) = make_float4(tj[0], tj[1], tj[2], tj[3]);
-              *reinterpret_cast<float4*>(zb + 2 * 32 * U + lane * U + c * 4) = make_float4(sf[0], sf[1], sf[2], sf[3]);
-              *reinterpret_cast<float4*>(zb + 3 * 32 * U + lane * U + c * 4) = make_float4(so[0], so[1], so[2], so[3]);
-              *reinterpret_cast<float4*>(zb + 4 * 32 * U + lane * U + c * 4) = make_float4(cst[i][c * 4], cst[i][c * 4 + 1], cst[i][c * 4 + 2], cst[i][c * 4 + 3]);
-              if (has_next) *reinterpret_cast<float4*>(Hpd + row_n * g.ldx + u) = make_float4(hr[0], hr[1], hr[2], hr[3]);
+              *reinterpret_cast<float4*>(zb + zpos(0, ubase / 4 + c)) = make_float4(si[0], si[1], si[2], si[3]);
+              *reinterpret_cast<float4*>(zb + zpos(1, ubase / 4 + c)) = make_float4(tj[0], tj[1], tj[2], tj[3]);
+              *reinterpret_cast<float4*>(zb + zpos(2, ubase / 4 + c)) = make_float4(sf[0], sf[1], sf[2], sf[3]);
+              *reinterpret_cast<float4*>(zb + zpos(3, ubase / 4 + c)) = make_float4(so[0], so[1], so[2], so[3]);
+              *reinterpret_cast<float4*>(zb + zpos(4, ubase / 4 + c)) = make_float4(cst[i][c * 4], cst[i][c * 4 + 1], cst[i][c * 4 + 2], cst[i][c * 4 + 3]);
+              if (has_next && u < H) *reinterpret_cast<float4*>(Hpd + row_n * g.ldx + u) = make_float4(hr[0], hr[1], hr[2], hr[3]);
             }
-            *reinterpret_cast<float4*>(Hd + row * H + u) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            if (u < H) *reinterpret_cast<float4*>(Hd + row * H + u) = make_float4(hn[0], hn[1], hn[2], hn[3]);
             __half2 h01 = __floats2half2_rn(hn[0], hn[1]), h23 = __floats2half2_rn(hn[2], hn[3]);
             uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
             *reinterpret_cast<uint2*>(hbox + lane * UP + ubase + c * 4) = pk;       // next step's operand rows (fp16)
@@ -273,19 +331,35 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
         // store warp requests that refill only when the TMA stores of THIS tile have read the boxes
       }
     }
+  } else if (warp == 2 + RF_EW + RF_SW) {
+    if (lane == 0) {                                                   // ---- publication counters, polled ahead of the producer
+      int seq = 0;
+      for (int k = 1; k < Tmax; k++) {
+        for (int t = p; t * RP_ROWS < s_n[k]; t += g.P) {
+          flag_wait(flags + t, per_step * k);
+          seq++;
+          asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(&s_flagged)), "r"(seq) : "memory");
+        }
+      }
+    }
   } else {
-    // ---- 4 store warps, one per TMEM lane quarter (lane 0 drives the TMA engine, lane 1 publishes): x-projection boxes in, gate /
-    // c / fp16-h boxes out, the tile's publication counter.  Everything here used to sit at the end of the cell warps' tile loop
-    // (1.6 - 2 us of the 3.4 - 4 us per tile, profiles/r2b_rec_fwd16_trace.txt).
+    // ---- 4 store warps, one per TMEM lane quarter: x-projection boxes in, gate / c / fp16-h boxes out, the tile's publication
+    // counter.  Everything here used to sit at the end of the cell warps' tile loop (1.6 - 2 us of the 3.4 - 4 us per tile,
+    // profiles/r2b_rec_fwd16_trace.txt).  The TMA operations of a tile are spread over SIX LANES (a thread's bulk copies are
+    // processed about two at a time): lane g < 4 stores gate box g and requests the x-projection box that replaces it, lane 4
+    // stores the c box, lane 5 stores the fp16 h box and publishes the tile.
     const int q = warp & 3;
     const uint32_t sMine = sE + (uint32_t)q * QBYTES;
     const int ucol = j * U;
     auto tile_rows = [&](int k, int i) { return s_off[k] + (p + i * g.P) * RP_ROWS + 32 * q; };
-    auto load_z = [&](int k, int i, int set) {                          // x-projection boxes of tile (k, i) of this quarter
+    auto load_z = [&](int k, int i, int set) {                          // x-projection boxes of tile (k, i) of this quarter: lanes 0-3
       const uint32_t bar = efull0 + 8 * (q * 2 + set);
       const int r0 = tile_rows(k, i);
-      mbar_expect_tx(bar, 4 * ZBOX);
-      for (int gate = 0; gate < 4; gate++) tma_load_2d(sMine + set * 5 * ZBOX + gate * ZBOX, &maps.z[d], gate * H + ucol, r0, bar);
+      if (lane == 0) mbar_expect_tx(bar, 4 * ZBOX);
+      if (lane < 4) {
+        if constexpr (SWZ) tma_load_3d(sMine + set * 5 * ZBOX + lane * ZBOX, &maps.z[d], ucol, lane, r0, bar);
+        else tma_load_2d(sMine + set * 5 * ZBOX + lane * ZBOX, &maps.z[d], lane * H + ucol, r0, bar);
+      }
     };
     // (k2, i2) runs two tiles ahead of the tile being stored: the boxes it names are requested into the set that has just left
     int k2 = 0, i2 = 0;
@@ -298,13 +372,11 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
       }
     };
     if (p * RP_ROWS >= s_n[0]) k2 = Tmax;
-    if (lane == 0) {                                                    // prime both sets
-      if (ahead_valid()) { load_z(k2, i2, 0); ahead_next(); }
-      if (ahead_valid()) { load_z(k2, i2, 1); ahead_next(); }
-    }
+    if (ahead_valid()) { load_z(k2, i2, 0); ahead_next(); }             // prime both sets
+    if (ahead_valid()) { load_z(k2, i2, 1); ahead_next(); }
     uint32_t n_tile = 0;
     Tracer tr; tr.init(g.trace, g.trace_cta, 2);
-    if (q != 2 || lane != 0) tr.p = nullptr;                              // the quarter of cell warp 0 (warp 2)
+    if (q != 2 || lane != 5) tr.p = nullptr;                              // the publishing lane of the quarter of cell warp 0 (warp 2)
     for (int k = 0; k < Tmax; k++) {
       const int n_k = s_n[k], n_k1 = s_n[k + 1];
 #pragma unroll 1
@@ -315,32 +387,30 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_rec_fwd16(const __grid_consta
         const bool has_next = t * RP_ROWS < n_k1;
         mbar_wait(sready0 + 8 * (q * 2 + set), (n_tile >> 1) & 1);
         tr.ev(0, k, t);
-        if (lane == 0) {
-          const int r0 = tile_rows(k, i);
+        const int r0 = tile_rows(k, i);
+        if (lane == 5) {
           if (has_next) tma_store_2d(&maps.hp16[d], sMine + 2 * 5 * ZBOX + set * HBOX, j * UP, s_off[k + 1] + (p + i * g.P) * RP_ROWS + 32 * q);
-          bulk_commit();                                               // group A: what the next step of the other slices waits for
-          if (g.training) {
-            for (int gate = 0; gate < 4; gate++) tma_store_2d(&maps.z[d], sMine + set * 5 * ZBOX + gate * ZBOX, gate * H + ucol, r0);
-            tma_store_2d(&maps.cc[d], sMine + set * 5 * ZBOX + 4 * ZBOX, ucol, r0);
-            bulk_commit();                                             // group B: the gates and c (read by the backward pass)
-            bulk_wait<1>();                                            // group A: the fp16 rows are complete in global memory
-          } else {
-            bulk_wait<0>();
+          bulk_commit();
+          bulk_wait<0>();                                              // the fp16 rows are complete in global memory
+          tr.ev(1, k, t);
+          flag_release_add(flags + t);                                  // what the next step of the other slices waits for
+        } else if (g.training && lane < 5) {
+          if (lane < 4) {
+            if constexpr (SWZ) tma_store_3d(&maps.z[d], sMine + set * 5 * ZBOX + lane * ZBOX, ucol, lane, r0);
+            else tma_store_2d(&maps.z[d], sMine + set * 5 * ZBOX + lane * ZBOX, lane * H + ucol, r0);
           }
+          else tma_store_2d(&maps.cc[d], sMine + set * 5 * ZBOX + 4 * ZBOX, ucol, r0);
+          bulk_commit();
+          bulk_wait_read<0>();                                         // the box has left shared memory
         }
-        tr.ev(1, k, t);
-        __syncwarp();
-        if (lane == 1) flag_release_add(flags + t);                     // a lane with no bulk copies in flight publishes the tile
-        if (lane == 0) {
-          if (g.training) bulk_wait_read<0>();                         // the boxes of this set may be refilled
-          tr.ev(2, k, t);
-          if (ahead_valid()) { load_z(k2, i2, set); ahead_next(); }
-        }
+        __syncwarp();                                                   // every box of this set has been read: it may be refilled
+        tr.ev(2, k, t);
+        if (ahead_valid()) { load_z(k2, i2, set); ahead_next(); }
         tr.ev(3, k, t);
         n_tile++;
       }
     }
-    if (lane == 0) bulk_wait<0>();                                       // the last gate boxes have left shared memory
+    if (lane < 5) bulk_wait<0>();                                        // the last gate boxes have left shared memory
   }
   tc_fence_before();
   __syncthreads();

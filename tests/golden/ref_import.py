@@ -20,7 +20,11 @@ import types
 
 import numpy as np
 
-REF = "/root/reference"
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# /root/reference in the build container; on a GPU box the UNMODIFIED copy that tools/stage_reference.sh puts under baseline/_ref/
+# (git-ignored, travels with gpurun like the contract's own `pip install --target baseline/_ref`)
+REF = os.environ.get("ICL_REF_DIR") or ("/root/reference" if os.path.isdir("/root/reference/nn_utils") else
+                                        os.path.join(os.path.dirname(os.path.dirname(_HERE)), "baseline", "_ref", "ImageCaptionLearn_py"))
 
 
 def available():
@@ -62,7 +66,7 @@ def install(tensorflow=None, nn_core=None):
     register as `nn_utils.core` INSTEAD of the reference's (the import swap of INTEGRATION.md: the B200 shim); default = the
     reference's own file (its function bodies need a real TensorFlow, importing it does not).  Returns a dict of the modules."""
     if not available():
-        raise RuntimeError("/root/reference is not present (build container only)")
+        raise RuntimeError("the reference sources are not present (%s)" % REF)
     gensim = types.ModuleType("gensim")
     gm = types.ModuleType("gensim.models")
     gm.KeyedVectors = _KeyedVectors
