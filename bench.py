@@ -496,6 +496,31 @@ def summarise(name, r, pk, world, traffic=None):
     return d, roof, by_phase
 
 
+def host_memory_bandwidth(ctx, threads=4, mb=256, reps=4):
+    """STREAM-style copy on the host, on every rank at the same time with the thread count a rank's packing pool uses: what the box's
+    memory system gives the ranks when all of them pack.  Returns GB/s (read + written bytes) of this rank and the sum over ranks."""
+    import torch
+    old = torch.get_num_threads()
+    torch.set_num_threads(threads)
+    a = torch.empty(mb << 18, dtype=torch.float32).fill_(1.0)
+    b = torch.empty_like(a)
+    b.copy_(a)
+    if ctx.dist:
+        ctx.dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        b.copy_(a)
+    dt = time.perf_counter() - t0
+    torch.set_num_threads(old)
+    mine = 2.0 * a.numel() * 4 * reps / dt / 1e9
+    total = mine
+    if ctx.dist:
+        t = torch.tensor([mine], device="cuda", dtype=torch.float64)
+        ctx.dist.all_reduce(t)
+        total = float(t.item())
+    return dict(per_rank_gbs=mine, all_ranks_gbs=total, threads_per_rank=threads, how="torch CPU copy of %d MiB x %d on every rank at once" % (mb, reps))
+
+
 def affinity_predict_pairs_per_sec(local, steps=10):
     """BASELINE.json's second metric on the PREDICT side: pairs/s end to end through get_pred_scores_mcc's batch path (keep 1.0, every
     distinct caption of a batch encoded once, token rows + box rows into the device-resident tables)."""
@@ -564,6 +589,7 @@ def main():
     clk = []
     main_r = measure(args.workload, args.steps, args.warmup, ctx, clocks=clk, e2e_variants=True)
     main_r["steps"] = args.steps
+    host_bw = host_memory_bandwidth(ctx)
     others = {}
     if not args.no_by_config:
         for name in BY_CONFIG:
@@ -576,7 +602,7 @@ def main():
         traffic = None
         try:       # DRAM bytes of the dominant kernel from the committed `ncu --set full` capture of this workload (profiles/)
             if args.workload == "card2048":
-                for fn in ("r2_ncu_full_summary.json", "r1h_ncu_full_summary.json"):
+                for fn in ("r2_ncu_full_summary.json", "r2a_ncu_recurrences.json", "r1h_ncu_full_summary.json"):
                     path = os.path.join(ROOT, "profiles", fn)
                     if os.path.exists(path):
                         ents = json.load(open(path))
@@ -610,6 +636,16 @@ def main():
                     phases_ms=body["phases_ms"], roofline=roof, roofline_by_phase=by_phase,
                     e2e=main_r["e2e"], e2e_variants=main_r.get("e2e_variants"),
                     gpu_launches=main_r["launches"], clocks=clocks_summary(clk))
+        # the host-tensor e2e path per rank and step: reads the valid rows of 'sentences' (4 B/elem), writes the packed pinned mirror
+        # (fp16 wire: 2 B/elem), and the DMA engine reads that mirror again -- against what the box's memory system gives all ranks
+        e = main_r["e2e"]
+        elems = main_r["n_tok"] * E
+        traffic = elems * 4 + 2 * (e["h2d_bytes_per_step"])
+        line["e2e_host_limit"] = dict(host_bytes_per_rank_step=int(traffic), all_ranks_gbs_needed_at_device_rate=world * traffic / (ms_per_step * 1e-3) / 1e9,
+                                      all_ranks_gbs_achieved=world * traffic / (e["ms_per_step"] * 1e-3) / 1e9, host_copy_bandwidth=host_bw,
+                                      note="host sentence tensors: valid rows read (fp32) + packed mirror written + mirror read by the DMA engine; "
+                                           "when achieved ~ host_copy_bandwidth.all_ranks_gbs the host memory system is the limiter (the corpus-cache "
+                                           "path sends 4-byte token rows instead)")
         if "corpus_cache" in (main_r.get("e2e_variants") or {}):
             line["e2e_resident_corpus"] = main_r["e2e_variants"]["corpus_cache"]
         if others:

@@ -516,30 +516,60 @@ class Session(object):
             self._grad_view = torch.as_tensor(_Arr(), device="cuda:%d" % self.device)
         return self._grad_view
 
+    def _overlap_group(self):
+        """A second NCCL communicator capped at a few CTAs (ncclConfig_t.maxCTAs) for the collectives that run WHILE the backward
+        pass computes: the BPTT clusters leave 8 of the 148 SMs idle, and an uncapped all-reduce kernel would take SMs from them
+        (measured in round 1: 1.598 vs 1.551 ms per step on 2 x B200).  None when the installed torch cannot configure it."""
+        if getattr(self, "_ar_group", False) is False:
+            self._ar_group = None
+            try:
+                import torch.distributed as td
+                opts = td.ProcessGroupNCCL.Options()
+                opts.config.max_ctas = int(os.environ.get("ICL_AR_CTAS", "4"))
+                opts.config.min_ctas = 1
+                self._ar_group = td.new_group(backend="nccl", pg_options=opts)
+            except Exception:
+                self._ar_group = None
+        return self._ar_group
+
     def allreduce_grads(self):
-        """SUM all-reduce of the flat gradient buffer of the step just enqueued (the loss is a SUM over examples, core.py:267).
-        ICL_AR_OVERLAP=1 overlaps it with the backward pass: the heads' slice is reduced on a side stream as soon as the heads'
-        backward has run -- while the BPTT and the weight-gradient GEMMs still compute -- and the LSTM slice after them.
-        Measured on 2 x B200 (card2048): 1.598 ms/step with the overlap vs 1.551 ms without -- the NCCL kernel takes SMs away
-        from the BPTT clusters, which are sized to be co-resident on all 148 -- so one all-reduce after the backward is the default."""
+        """SUM all-reduce of the flat gradient buffer of the step just enqueued (the loss is a SUM over examples, core.py:267), in
+        three buckets released as the backward pass produces them:
+          heads' slice      -- complete before the BPTT starts: reduced on a side stream while the BPTT and the weight-gradient GEMMs run;
+          LSTM fw slice     -- complete after the forward direction's weight-gradient GEMM: reduced while the backward direction's runs;
+          LSTM bw slice     -- the only exposed collective, on the main stream.
+        The two overlapped buckets go through a CTA-capped communicator (`_overlap_group`).  ICL_AR_OVERLAP=0: one all-reduce after
+        the backward pass."""
         import torch
         import torch.distributed as td
         L = _cabi.lib()
         g = self.grad_tensor()
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device)
-            split = C.c_int64()
+            self._side2 = torch.cuda.Stream(device=self.device)
+            split, bw = C.c_int64(), C.c_int64()
             _cabi.check(L.icl_grad_split(self.handle, C.byref(split)))
-            self._split = int(split.value)
+            _cabi.check(L.icl_grad_split_lstm(self.handle, C.byref(bw)))
+            self._split, self._bw = int(split.value), int(bw.value)
         main = torch.cuda.current_stream()
-        if self._split >= g.numel() or not os.environ.get("ICL_AR_OVERLAP"):
+        # measured (card2048, profiles/r2_allreduce_overlap.md): 8 GPUs 1.453 -> 1.428 ms per step, 2 GPUs 1.403 -> 1.422 (three launches
+        # instead of one cost more than a 9 MB all-reduce between two GPUs): on by default from 4 ranks up
+        ov = os.environ.get("ICL_AR_OVERLAP")
+        overlap = (ov != "0" if ov is not None else td.get_world_size() >= 4) and self._split < g.numel()
+        grp = self._overlap_group() if overlap else None
+        if grp is None:
             td.all_reduce(g, op=td.ReduceOp.SUM)
             return
         _cabi.check(L.icl_wait_head_grads(self.handle, C.c_void_p(self._side.cuda_stream)))
         with torch.cuda.stream(self._side):
-            td.all_reduce(g[self._split:], op=td.ReduceOp.SUM)
-        td.all_reduce(g[:self._split], op=td.ReduceOp.SUM)
+            td.all_reduce(g[self._split:], op=td.ReduceOp.SUM, group=grp)
+        _cabi.check(L.icl_wait_fw_lstm_grads(self.handle, C.c_void_p(self._side2.cuda_stream)))
+        with torch.cuda.stream(self._side2):
+            self._side2.wait_stream(self._side)               # one communicator: its collectives stay in issue order
+            td.all_reduce(g[:self._bw], op=td.ReduceOp.SUM, group=grp)
+        td.all_reduce(g[self._bw:self._split], op=td.ReduceOp.SUM)
         main.wait_stream(self._side)
+        main.wait_stream(self._side2)
 
     def param_tensor(self):
         """torch view of the flat device parameter buffer (rank-0 broadcast of the initial weights)."""

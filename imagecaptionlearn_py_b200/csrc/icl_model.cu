@@ -141,6 +141,7 @@ struct icl_model {
   cudaStream_t stream = nullptr, aux = nullptr, aux2 = nullptr, aux3 = nullptr;      // aux2: the heads' weight gradients
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   cudaEvent_t ev_heads = nullptr;      // recorded when the heads' parameter gradients are complete (before the BPTT)
+  cudaEvent_t ev_wg0 = nullptr;        // recorded when the forward direction's LSTM weight gradient is complete (before the backward direction's)
   cudaEvent_t ev_dz[ICL_MAX_LAYERS + 2] = {};   // heads' backward: "dz of this layer is ready" (main stream -> aux stream)
   bool heads_aux_pending = false;      // the aux stream holds weight-gradient work the main stream has not joined yet
   cudaEvent_t ev_ph[PH_N][2] = {};
@@ -641,7 +642,7 @@ extern "C" void icl_destroy(icl_model* m) {
   if (m->aux) cudaStreamDestroy(m->aux);
   if (m->aux2) cudaStreamDestroy(m->aux2);
   if (m->aux3) cudaStreamDestroy(m->aux3);
-  for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_join2, m->ev_t0, m->ev_t1, m->ev_heads}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_join2, m->ev_t0, m->ev_t1, m->ev_heads, m->ev_wg0}) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : m->ev_dz) if (e) cudaEventDestroy(e);
   for (int i = 0; i < PH_N; i++) for (int j = 0; j < 2; j++) if (m->ev_ph[i][j]) cudaEventDestroy(m->ev_ph[i][j]);
   delete m;
@@ -792,6 +793,7 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   CKD(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
   CKD(cudaEventCreateWithFlags(&m->ev_join2, cudaEventDisableTiming));
   CKD(cudaEventCreateWithFlags(&m->ev_heads, cudaEventDisableTiming));
+  CKD(cudaEventCreateWithFlags(&m->ev_wg0, cudaEventDisableTiming));
   for (auto& e : m->ev_dz) CKD(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CKD(cudaEventCreate(&m->ev_t0)); CKD(cudaEventCreate(&m->ev_t1));
   for (int i = 0; i < PH_N; i++) for (int j = 0; j < 2; j++) CKD(cudaEventCreate(&m->ev_ph[i][j]));
@@ -901,6 +903,17 @@ extern "C" int icl_grad_split(icl_model* m, int64_t* first_head_float) {
 }
 extern "C" int icl_wait_head_grads(icl_model* m, void* cuda_stream) {
   CK(cudaStreamWaitEvent((cudaStream_t)cuda_stream, m->ev_heads, 0));
+  return 0;
+}
+// The LSTM's gradient floats are [0, first_head_float): the forward direction's kernel + bias first, then the backward direction's
+// from *first_bw_float on.  The weight-gradient GEMM of the forward direction runs first; icl_wait_fw_lstm_grads makes the given
+// stream wait for it, so a collective on floats [0, first_bw_float) overlaps the backward direction's GEMM.
+extern "C" int icl_grad_split_lstm(icl_model* m, int64_t* first_bw_float) {
+  *first_bw_float = m->params[m->pK[1]].off;
+  return 0;
+}
+extern "C" int icl_wait_fw_lstm_grads(icl_model* m, void* cuda_stream) {
+  CK(cudaStreamWaitEvent((cudaStream_t)cuda_stream, m->ev_wg0, 0));
   return 0;
 }
 extern "C" int icl_param_buffer(icl_model* m, void** p, int64_t* n) { *p = m->P; *n = m->n_params; m->pr_dirty = m->wp_dirty = m->wih_dirty = m->wb_dirty = true; return 0; }
@@ -1609,6 +1622,7 @@ static int lstm_backward(icl_model* m) {
     if (m->params[m->pBias[d]].off != m->params[m->pK[d]].off + (int64_t)(E + H) * 4 * H) return fail("kernel/bias not contiguous");
     GemmArgs gk = mk_gemm(m->XH[d], m->ldx, m->Z[d], 4 * H, dK, 4 * H, E + H + 1, 4 * H, (int)Ntok);
     CKI(gemm(m, st, true, true, gk, -1, splits));
+    if (d == 0) CK(cudaEventRecord(m->ev_wg0, st));
   }
   PH_END(m, PH_WGRAD);
   return 0;

@@ -363,14 +363,19 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bptt_cluster(const __grid_con
     tr.ev(0, k, 0);
     if (has_mma) {
       if (warp == 0) {
-        if (lane == 0) {                                               // ---- TMA producer
+        // ---- TMA producer: the 1 + nacc boxes of a k-block are requested by 1 + nacc LANES (one thread gets a load accepted every
+        // 0.3 - 0.4 us, several lanes issue concurrently: tools/probe_tma.cu); lane 0 arms the stage's barrier for all of them
+        if (lane <= nacc) {
           for (int kb = 0; kb < num_kb; kb++, it++) {
             const int s = it % BC_STAGES;
             mbar_wait(empty0 + 8 * s, ((it / BC_STAGES) & 1) ^ 1);
             const uint32_t fb = full0 + 8 * s, st = base + s * BC_STAGE_BYTES;
-            mbar_expect_tx(fb, BP_A_BYTES + nacc * BP_B_BYTES);
-            tma_load_2d(st, &maps.za[d], (kb0 + kb) * 32, s_off[k + 1] + m0, fb);
-            for (int a = 0; a < nacc; a++) tma_load_2d(st + BP_A_BYTES + a * BP_B_BYTES, &maps.wb[d], (kb0 + kb) * 32, a * BP_BN, fb);
+            if (lane == 0) {
+              mbar_expect_tx(fb, BP_A_BYTES + nacc * BP_B_BYTES);
+              tma_load_2d(st, &maps.za[d], (kb0 + kb) * 32, s_off[k + 1] + m0, fb);
+            } else {
+              tma_load_2d(st + BP_A_BYTES + (lane - 1) * BP_B_BYTES, &maps.wb[d], (kb0 + kb) * 32, (lane - 1) * BP_BN, fb);
+            }
           }
         }
         __syncwarp();

@@ -148,6 +148,10 @@ int icl_param_buffer(icl_model* m, void** dev_ptr, int64_t* n_floats);
    there overlaps the BPTT + weight-gradient GEMMs of the compute stream; the LSTM part is reduced after icl_run_resident. */
 int icl_grad_split(icl_model* m, int64_t* first_head_float);
 int icl_wait_head_grads(icl_model* m, void* cuda_stream);
+/* LSTM slice of the gradient: floats [0, first_bw_float) belong to the forward direction, whose weight-gradient GEMM finishes first;
+   icl_wait_fw_lstm_grads makes the given stream wait for it (its collective then overlaps the backward direction's GEMM). */
+int icl_grad_split_lstm(icl_model* m, int64_t* first_bw_float);
+int icl_wait_fw_lstm_grads(icl_model* m, void* cuda_stream);
 int icl_apply_update(icl_model* m);
 /* Adam state selection: one (m, v, beta-power) set per tf.train.AdamOptimizer instance -- the `alternate` multitask scheme has
    one per task (icl_multitask_lstm.py:387-393).  Slot 0 exists from the start; others are created zeroed on first use.
