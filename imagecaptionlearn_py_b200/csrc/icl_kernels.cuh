@@ -573,18 +573,23 @@ __global__ void __launch_bounds__(SMB_THREADS) k_softmax_bwd(const float* __rest
     db[c] = acc;
   }
 }
-// dW [K*C] and db [C] of the softmax layer = the sum of the nb partial rows of k_softmax_bwd, in block order
-__global__ void k_softmax_bwd_reduce(const float* __restrict__ part, int nb, int KC, int C, float* __restrict__ dW, float* __restrict__ db) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x, n = KC + C;
-  if (i >= n) return;
-  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-  int b = 0;
-  for (; b + 4 <= nb; b += 4) {
-    s0 += part[(long)b * n + i]; s1 += part[(long)(b + 1) * n + i]; s2 += part[(long)(b + 2) * n + i]; s3 += part[(long)(b + 3) * n + i];
+// dW [K*C] and db [C] of the softmax layer = the sum of the nb partial rows of k_softmax_bwd in a FIXED association order (bit-
+// reproducible): block (32 columns, 16 row groups); group y adds rows y, y+16, ... in order, then the 16 group sums are added in order.
+__global__ void __launch_bounds__(512) k_softmax_bwd_reduce(const float* __restrict__ part, int nb, int KC, int C, float* __restrict__ dW,
+                                                            float* __restrict__ db) {
+  __shared__ float sh[16][33];
+  const int i = blockIdx.x * 32 + threadIdx.x, n = KC + C;
+  float s = 0.0f;
+  if (i < n)
+    for (int b = threadIdx.y; b < nb; b += 16) s += part[(long)b * n + i];
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < n) {
+    float t = 0.0f;
+#pragma unroll
+    for (int y = 0; y < 16; y++) t += sh[y][threadIdx.x];
+    if (i < KC) dW[i] = t; else db[i - KC] = t;
   }
-  for (; b < nb; b++) s0 += part[(long)b * n + i];
-  const float s = (s0 + s1) + (s2 + s3);
-  if (i < KC) dW[i] = s; else db[i - KC] = s;
 }
 
 // deterministic single-block sums: block 0 sums v0 into out[0], block 1 sums v1 into out[1] divided by mean_div

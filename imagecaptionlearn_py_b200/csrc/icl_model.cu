@@ -153,8 +153,10 @@ struct icl_model {
   float* Wp[2] = {};
   unsigned* rp_flags = nullptr;
   long long* rp_trace = nullptr; int rp_trace_cta = 0;
+#ifdef ICL_EXPERIMENTS
   RecFwdMaps rp_fmaps;
   RecBwdMaps rp_bmaps;
+#endif
   unsigned* rp_bar = nullptr;
   bool rp_bwd_on = false;       // k_rec_bwd is correct but measured slower (0.84 ms) than the per-step path (0.56 ms): opt-in
   // fp16 input projection (K1): fp16 copies of the prepared inputs and of W_ih^T, kind::f16 GEMM
@@ -363,6 +365,30 @@ __global__ void k_zero_2d(float* __restrict__ p0, float* __restrict__ p1, long p
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
     *reinterpret_cast<float4*>(p + (i / w4) * pitch + (i % w4) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
 }
+// several zero fills in ONE launch (blockIdx.y = range): the backward pass needs five cleared buffers before its first kernel, and
+// a launch costs more than clearing 9 MB
+struct ZeroRanges { uint32_t* p[6]; size_t n[6]; };
+__global__ void k_zero_multi(const ZeroRanges r) {
+  uint32_t* p = r.p[blockIdx.y];
+  const size_t n_words = r.n[blockIdx.y];
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    uint4* p4 = reinterpret_cast<uint4*>(p);
+    const size_t n4 = n_words >> 2;
+    for (size_t i = i0; i < n4; i += stride) p4[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (size_t i = (n4 << 2) + i0; i < n_words; i += stride) p[i] = 0u;
+  } else {
+    for (size_t i = i0; i < n_words; i += stride) p[i] = 0u;
+  }
+}
+static cudaError_t zero_multi_async(std::initializer_list<std::pair<void*, size_t>> ranges, cudaStream_t st) {
+  ZeroRanges r; int n = 0; size_t mx = 0;
+  for (auto& pr : ranges) if (pr.second) { r.p[n] = reinterpret_cast<uint32_t*>(pr.first); r.n[n] = pr.second / 4; mx = std::max(mx, r.n[n]); n++; }
+  if (n == 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)std::min<size_t>(296, (mx / 4 + 255) / 256 + 1);
+  k_zero_multi<<<dim3(blocks, n), 256, 0, st>>>(r);
+  return cudaGetLastError();
+}
 static cudaError_t zero_async(void* p, size_t bytes, cudaStream_t st) {
   if (bytes == 0) return cudaSuccess;
   const size_t words = bytes / 4;
@@ -418,6 +444,7 @@ static int box_map(icl_model* m, const float* ptr, uint64_t cols, uint64_t rows,
   return r ? fail("cuTensorMapEncodeTiled failed (%d) for a {%u,%u} box over [%llu,%llu]", r, box_c, box_r,
                   (unsigned long long)rows, (unsigned long long)cols) : 0;
 }
+#ifdef ICL_EXPERIMENTS
 template <int U> static int rec_set_attr(int nkb) {
   cudaError_t e = cudaFuncSetAttribute(k_rec_fwd<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, rec_fwd_smem<U>(nkb));
   return e == cudaSuccess ? 0 : fail("cudaFuncSetAttribute(k_rec_fwd): %s", cudaGetErrorString(e));
@@ -444,6 +471,10 @@ static int rec_init(icl_model* m) {
     return fail("cudaFuncSetAttribute(k_rec_bwd) failed");
   return U == 20 ? rec_set_attr<20>(m->rp_nkb) : rec_set_attr<16>(m->rp_nkb);
 }
+
+#else
+static int rec_init(icl_model*) { return 0; }
+#endif
 
 static int k1_init(icl_model* m) {
   m->k1_f16 = m->cfg.gemm_mode == ICL_GEMM_TCGEN05_TF32;
@@ -1129,11 +1160,15 @@ __global__ void k_zero_pad_rows(float* __restrict__ buf0, float* __restrict__ bu
 
 static bool rec_usable(icl_model* m) {
   if (m->rf_on) return rf_pick(m) != nullptr;
+#ifndef ICL_EXPERIMENTS
+  return false;
+#endif
   if (m->rp_U == 0 || !m->rp_on || m->Tmax > RP_MAXT) return false;
   int tiles = (m->n_active[0] + 127) / 128, P = std::max(1, std::min(148 / (2 * m->rp_nsl), tiles));
   return (tiles + P - 1) / P <= RP_MAXTPC;          // the kernel carries the cell state of <= RP_MAXTPC tiles per CTA in registers
 }
 
+#ifdef ICL_EXPERIMENTS
 static RecArgs rec_args(icl_model* m, int training) {
   RecArgs a;
   a.off = m->d_off; a.nact = m->d_nact; a.Tmax = m->Tmax; a.H = m->H; a.nsl = m->rp_nsl;
@@ -1143,6 +1178,8 @@ static RecArgs rec_args(icl_model* m, int training) {
   a.trace = m->rp_trace; a.trace_cta = m->rp_trace_cta;
   return a;
 }
+
+#endif
 
 static int rec_forward_fp16(icl_model* m, int training) {
   cudaStream_t st = m->stream;
@@ -1179,6 +1216,9 @@ static int rec_forward_fp16(icl_model* m, int training) {
 
 static int rec_forward_persistent(icl_model* m, int training) {
   if (m->rf_on) return rec_forward_fp16(m, training);
+#ifndef ICL_EXPERIMENTS
+  return fail("the TF32 first-generation recurrence (ICL_REC_FP16=0) is only in -DICL_EXPERIMENTS builds");
+#else
   cudaStream_t st = m->stream;
   const int E = m->E, H = m->H, U = m->rp_U;
   if (m->wp_dirty) {
@@ -1198,6 +1238,7 @@ static int rec_forward_persistent(icl_model* m, int training) {
   if (e != cudaSuccess) return fail("k_rec_fwd launch failed: %s", cudaGetErrorString(e));
   m->launches++;
   return 0;
+#endif
 }
 
 static int lstm_forward(icl_model* m, float keep_in, uint64_t seed, int training) {
@@ -1312,23 +1353,17 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
   cudaStream_t st = m->stream;
   int H = m->H;
   PH_BEGIN(m, PH_HEADS_BWD);
-  for (int d = 0; d < 2; d++) CK(zero_async(m->dHout[d], (size_t)m->NtokP * H * 4, st));
+  // ONE launch clears everything the backward pass accumulates into: dHout of both directions (span scatter), the WHOLE flat
+  // gradient buffer (split-K weight gradients and bias column sums of every head and of the LSTM add into it; heads that are not
+  // fed keep a zero gradient) and the dc carry of the BPTT
+  CK(zero_multi_async({{m->dHout[0], (size_t)m->NtokP * H * 4}, {m->dHout[1], (size_t)m->NtokP * H * 4}, {m->G, (size_t)m->n_params * 4},
+                       {m->dcc[0], (size_t)m->S * H * 4}, {m->dcc[1], (size_t)m->S * H * 4}}, st));
+  LAUNCHED(m);
   for (size_t hi = 0; hi < m->heads.size(); hi++) {
     Head& h = m->heads[hi];
-    if (!h.active) {                          // not fed in this call: its parameters get a zero gradient
-      for (size_t k = 0; k < h.pW.size(); k++) {
-        const Param &pw = m->params[h.pW[k]], &pb = m->params[h.pB[k]];
-        CK(zero_async(m->G + pw.off, (size_t)pw.rows * pw.cols * 4, st));
-        CK(zero_async(m->G + pb.off, (size_t)pb.rows * pb.cols * 4, st));
-      }
-      continue;
-    }
+    if (!h.active) continue;                  // not fed in this call: its parameters keep the zero gradient
     if (!h.has_labels) return fail("backward needs labels for head %zu", hi);
     int B = h.c.batch_size, L = h.c.n_hidden;
-    {   // ONE zero fill of the head's whole gradient range (split-K weight gradients and bias column sums accumulate into it)
-      const int64_t g0 = m->params[h.pW[0]].off, g1 = hi + 1 < m->heads.size() ? m->params[m->heads[hi + 1].pW[0]].off : m->n_params;
-      CK(zero_async(m->G + g0, (size_t)(g1 - g0) * 4, st));
-    }
     // Layer by layer from the softmax down: the chain dz_k -> dz_{k-1} = (dz_k W_k^T) * act' stays on the main stream; the weight
     // and bias gradients of layer k only need dz_k, so they run on the aux stream concurrently with the rest of the chain
     // (joined before the weight-gradient phase of the LSTM / the update).
@@ -1343,7 +1378,7 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
       k_softmax_bwd<<<nb, SMB_THREADS, (size_t)(SMB_ROWS * C + Kl * (C + 1)) * 4, st>>>(h.act[L - 1], h.dlogits, m->P + pw.off, B, Kl, C, e,
                                                                                          h.dzb[L - 1], h.smb_part);
       LAUNCHED(m);
-      k_softmax_bwd_reduce<<<(Kl * C + C + 127) / 128, 128, 0, st>>>(h.smb_part, nb, Kl * C, C, m->G + pw.off, m->G + pb.off);
+      k_softmax_bwd_reduce<<<(Kl * C + C + 31) / 32, dim3(32, 16), 0, st>>>(h.smb_part, nb, Kl * C, C, m->G + pw.off, m->G + pb.off);
       LAUNCHED(m);
     }
     const float* dz = h.dzb[L - 1];    // gradient w.r.t. the pre-activation of layer k+1
@@ -1385,6 +1420,7 @@ static int join_heads_aux(icl_model* m) {
   return 0;
 }
 
+#ifdef ICL_EXPERIMENTS
 // K3 (opt-in): every BPTT step of both directions in one cooperative launch (lstm_persistent.cuh)
 static int rec_backward_persistent(icl_model* m) {
   const int H = m->H, S = m->S;
@@ -1404,6 +1440,8 @@ static int rec_backward_persistent(icl_model* m) {
   m->launches++;
   return 0;
 }
+
+#endif
 
 // K3 (default in tensor-core mode): one fused launch per step for both directions -- dh_rec = dZ_{k+1} W_hh^T with the
 // contraction split over a thread-block cluster, reduced through distributed shared memory, cell backward in the epilogue
@@ -1439,9 +1477,8 @@ static int rec_backward_fused(icl_model* m) {
 // K3 (default in tensor-core mode, H <= 336): the whole backward recurrence in ONE launch, a cluster of 4 CTAs per
 // (direction, 128-row tile) walking all of the tile's time steps with cluster barriers only (lstm_bptt.cuh)
 static int rec_backward_cluster(icl_model* m) {
-  const int H = m->H, S = m->S;
-  cudaStream_t st = m->stream;
-  for (int d = 0; d < 2; d++) CK(zero_async(m->dcc[d], (size_t)S * H * 4, st));
+  const int H = m->H;
+  cudaStream_t st = m->stream;                  // (the dc carry was cleared with the other backward buffers, heads_backward)
   BpttClusterArgs a;
   for (int d = 0; d < 2; d++) { a.Z[d] = m->Z[d]; a.Cc[d] = m->Cc[d]; a.dHout[d] = m->dHout[d]; a.dcc[d] = m->dcc[d]; }
   a.off = m->d_off; a.nact = m->d_nact; a.H = H; a.Tmax = m->Tmax; a.round_ops = m->round_ops;
@@ -1604,8 +1641,11 @@ static int lstm_backward(icl_model* m) {
   else if (m->bp_on && m->bp_cluster && m->Tmax <= RP_MAXT) CKI(rec_backward_cluster(m));
   else if (m->bp_on) CKI(rec_backward_fused(m));
   else {
+#ifdef ICL_EXPERIMENTS
     if (m->rp_U != 0 && m->rp_on && m->rp_bwd_on && m->Tmax <= RP_MAXT) CKI(rec_backward_persistent(m));
-    else CKI(rec_backward_steps(m));
+    else
+#endif
+      CKI(rec_backward_steps(m));
     // pad rows of dZ must be exactly zero for the time-batched weight-gradient GEMM (they still hold gates / Zx)
     k_zero_pad_rows<<<dim3(m->Tmax, 2), 256, 0, st>>>(m->Z[0], m->Z[1], mk_layout(m), 4 * H); LAUNCHED(m);
   }
@@ -1621,7 +1661,7 @@ static int lstm_backward(icl_model* m) {
     // [dKernel; dbias] = [Xd | Hprev | 1]^T dZ  (the bias follows the kernel in the flat buffers)
     if (m->params[m->pBias[d]].off != m->params[m->pK[d]].off + (int64_t)(E + H) * 4 * H) return fail("kernel/bias not contiguous");
     GemmArgs gk = mk_gemm(m->XH[d], m->ldx, m->Z[d], 4 * H, dK, 4 * H, E + H + 1, 4 * H, (int)Ntok);
-    CKI(gemm(m, st, true, true, gk, -1, splits));
+    CKI(gemm(m, st, true, true, gk, -1, splits, /*prezeroed=*/true));
     if (d == 0) CK(cudaEventRecord(m->ev_wg0, st));
   }
   PH_END(m, PH_WGRAD);

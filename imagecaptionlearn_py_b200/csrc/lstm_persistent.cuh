@@ -147,6 +147,8 @@ struct RecFwdMaps {       // [direction]; z/cc/hx/hp: boxes {U units, 32 rows} o
   CUtensorMap z[2], cc[2], hx[2], hp[2];
 };
 
+#ifdef ICL_EXPERIMENTS      // the first-generation kernels (k_rec_fwd: TF32 operands, everything through narrow TMA boxes; k_rec_bwd:
+                            // cooperative grid-barrier BPTT): superseded by lstm_fwd16.cuh / lstm_bptt.cuh, kept for A/B builds only
 template <int U>
 constexpr int rec_fwd_smem(int nkb) { return nkb * 4 * U * 128 + RP_ASTAGES * 16384 + 7 * RP_ROWS * U * 4 + 512 + 1024; }
 
@@ -577,5 +579,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) k_rec_bwd(const __grid_constant
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
   }
 }
+
+#endif  // ICL_EXPERIMENTS
 
 }  // namespace icl

@@ -352,15 +352,16 @@ def test_multitask_shared_encoder_matches_oracle(mode, H):
 
 
 def test_backward_recurrence_variants_agree(monkeypatch):
-    """The BPTT recurrence has four implementations: k_bptt_cluster (default: one launch, a 4-CTA cluster per row tile walks
-    every step), the fused per-step kernel k_bptt_step (ICL_BPTT_MODE=step; cluster split-K over 1, 2 or 4 CTAs reduced
-    through distributed shared memory), the per-step cell + split-K GEMM pair (ICL_BPTT_FUSED=0) and the opt-in cooperative
-    k_rec_bwd (ICL_PERSISTENT_BWD=1).  Same batch, same masks: same gradients up to fp32 summation
+    """The BPTT recurrence has three implementations in the product build: k_bptt_cluster (default: one launch, a 2 / 4 / 8-CTA
+    cluster per row tile walks every step), the fused per-step kernel k_bptt_step (the fallback for H > 336; ICL_BPTT_MODE=step;
+    cluster split-K over 1, 2 or 4 CTAs reduced through distributed shared memory) and the per-step cell + split-K GEMM pair of the
+    fp32 validation mode (ICL_BPTT_FUSED=0).  (k_rec_bwd and k_bptt_nsplit are -DICL_EXPERIMENTS builds only.)  Same batch, same
+    masks: same gradients up to fp32 summation
     order (which can move a dZ element across a TF32 rounding boundary, 2^-11 relative, before the next step: 5e-4)."""
     from imagecaptionlearn_py_b200 import _cabi
     p = tiny_problem(seed=27, dropout=True, **CASES[5])
     grads = {}
-    variants = {"steps": dict(ICL_BPTT_FUSED="0", ICL_PERSISTENT_BWD="0"), "coop": dict(ICL_BPTT_FUSED="0", ICL_PERSISTENT_BWD="1"),
+    variants = {"steps": dict(ICL_BPTT_FUSED="0"),
                 "fused4": dict(ICL_BPTT_FUSED="1", ICL_BPTT_MODE="step", ICL_BPTT_CS="4"),
                 "fused2": dict(ICL_BPTT_FUSED="1", ICL_BPTT_MODE="step", ICL_BPTT_CS="2"),
                 "fused1": dict(ICL_BPTT_FUSED="1", ICL_BPTT_MODE="step", ICL_BPTT_CS="1"),
