@@ -379,6 +379,7 @@ def measure(name, steps, warmup, ctx, clocks=None, e2e_variants=False):
             _cabi.check(L.icl_apply_update(sess.handle))
         else:
             _cabi.check(L.icl_run_resident(sess.handle, _cabi.OP_TRAIN, KEEP_IN, KEEP, seed))
+        _cabi.check(L.icl_join_side_work(sess.handle))      # the step's side-stream work (fp16 repack of the updated LSTM weights) is timed with it
 
     for i in range(warmup):
         resident_step(i)
@@ -411,7 +412,26 @@ def measure(name, steps, warmup, ctx, clocks=None, e2e_variants=False):
     stop.set()          # the clocks are sampled during the device-timed region only
     total_ms = sum(a.elapsed_time(b_) for a, b_ in ev)
     n1 = C.c_int64()
-    L.icl_kernel_launches(sess.handle, C.byref(n1))
+    L.icl_kernel_launches(sess.handle, C.byref(n1))       # kernels launched inside the device-timed region
+    # the same steps back to back (no flush, one event pair): what a training loop sees; the step's working set (~2 GB of activations at
+    # card2048) is many times the 126 MB L2 by itself
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(steps):
+        seed = 5000 + i
+        if dist:
+            _cabi.check(L.icl_run_resident(sess.handle, _cabi.OP_GRADS, KEEP_IN, KEEP, seed))
+            sess.allreduce_grads()
+            _cabi.check(L.icl_apply_update(sess.handle))
+        else:
+            _cabi.check(L.icl_run_resident(sess.handle, _cabi.OP_TRAIN, KEEP_IN, KEEP, seed))
+    _cabi.check(L.icl_join_side_work(sess.handle))
+    e1.record()
+    torch.cuda.synchronize()
+    b2b_ms = e0.elapsed_time(e1) / steps
 
     def max_over_ranks(x):
         if not dist:
@@ -421,7 +441,8 @@ def measure(name, steps, warmup, ctx, clocks=None, e2e_variants=False):
         return float(t.item())
     ms_per_step = max_over_ranks(total_ms) / steps
     out = dict(wl=wl, n_seqs=n_seqs, n_tok=n_tok, t_max=t_max, n_examples=n_examples, ms_per_step=ms_per_step, ph_ms=phases / steps,
-               launches=n1.value - n0.value, wall_ms=1e3 * wall / steps, value=world * n_seqs / (ms_per_step * 1e-3))
+               launches=n1.value - n0.value, wall_ms=1e3 * wall / steps, value=world * n_seqs / (ms_per_step * 1e-3),
+               b2b_ms=max_over_ranks(b2b_ms))
 
     # ---- end-to-end through the reference-facing API with host buffers: a rotation of N_ROT distinct host batches (a real
     # training loop never re-feeds a cache-warm buffer), as many timed steps as the device-timed leg
@@ -632,7 +653,8 @@ def main():
                                 parallelism="dp%d" % world, l2="flushed between timed steps (256 MiB memset, untimed)",
                                 tokens_per_sec=world * main_r["n_tok"] / (ms_per_step * 1e-3),
                                 bilstm_tflops=step_flops / (ms_per_step * 1e-3) / 1e12,
-                                wall_ms_per_step_incl_flush=main_r["wall_ms"]),
+                                wall_ms_per_step_incl_flush=main_r["wall_ms"],
+                                back_to_back_ms_per_step=main_r["b2b_ms"]),
                     phases_ms=body["phases_ms"], roofline=roof, roofline_by_phase=by_phase,
                     e2e=main_r["e2e"], e2e_variants=main_r.get("e2e_variants"),
                     gpu_launches=main_r["launches"], clocks=clocks_summary(clk))

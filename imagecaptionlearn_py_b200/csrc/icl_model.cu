@@ -172,6 +172,8 @@ struct icl_model {
     __half* Hp16[2] = {}; __half* Wp16[2] = {};
     RecFwd16Maps maps;
   } rf20, rf16;
+  RfVar* rf_last = nullptr;      // the slicing the last forward pass used: repacked eagerly after the update
+  cudaEvent_t ev_packs = nullptr; bool packs_pending = false;
   // fused BPTT step kernel (lstm_bptt.cuh): default backward recurrence in tensor-core mode
   bool bp_on = false, bp_cluster = true;     // bp_cluster: k_bptt_cluster (whole recurrence in one launch) when H <= 336
   int bp_cs = 4;
@@ -673,7 +675,7 @@ extern "C" void icl_destroy(icl_model* m) {
   if (m->aux) cudaStreamDestroy(m->aux);
   if (m->aux2) cudaStreamDestroy(m->aux2);
   if (m->aux3) cudaStreamDestroy(m->aux3);
-  for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_join2, m->ev_t0, m->ev_t1, m->ev_heads, m->ev_wg0}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_join2, m->ev_t0, m->ev_t1, m->ev_heads, m->ev_wg0, m->ev_packs}) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : m->ev_dz) if (e) cudaEventDestroy(e);
   for (int i = 0; i < PH_N; i++) for (int j = 0; j < 2; j++) if (m->ev_ph[i][j]) cudaEventDestroy(m->ev_ph[i][j]);
   delete m;
@@ -825,6 +827,7 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   CKD(cudaEventCreateWithFlags(&m->ev_join2, cudaEventDisableTiming));
   CKD(cudaEventCreateWithFlags(&m->ev_heads, cudaEventDisableTiming));
   CKD(cudaEventCreateWithFlags(&m->ev_wg0, cudaEventDisableTiming));
+  CKD(cudaEventCreateWithFlags(&m->ev_packs, cudaEventDisableTiming));
   for (auto& e : m->ev_dz) CKD(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CKD(cudaEventCreate(&m->ev_t0)); CKD(cudaEventCreate(&m->ev_t1));
   for (int i = 0; i < PH_N; i++) for (int j = 0; j < 2; j++) CKD(cudaEventCreate(&m->ev_ph[i][j]));
@@ -939,6 +942,13 @@ extern "C" int icl_wait_head_grads(icl_model* m, void* cuda_stream) {
 // The LSTM's gradient floats are [0, first_head_float): the forward direction's kernel + bias first, then the backward direction's
 // from *first_bw_float on.  The weight-gradient GEMM of the forward direction runs first; icl_wait_fw_lstm_grads makes the given
 // stream wait for it, so a collective on floats [0, first_bw_float) overlaps the backward direction's GEMM.
+// Work the library has queued on its side streams behind the last call (today: the fp16 repack of the LSTM weights after an update,
+// which normally overlaps the next step's input preparation) is joined into the main stream: a caller that brackets ONE step with
+// events calls this before the closing event so that the step's time includes all of its work.
+extern "C" int icl_join_side_work(icl_model* m) {
+  if (m->packs_pending) { CK(cudaStreamWaitEvent(m->stream, m->ev_packs, 0)); m->packs_pending = false; }
+  return 0;
+}
 extern "C" int icl_grad_split_lstm(icl_model* m, int64_t* first_bw_float) {
   *first_bw_float = m->params[m->pK[1]].off;
   return 0;
@@ -1181,20 +1191,43 @@ static RecArgs rec_args(icl_model* m, int training) {
 
 #endif
 
+static void pack_whh16(icl_model* m, icl_model::RfVar& v, cudaStream_t st) {
+  const int E = m->E, H = m->H;
+  const float* W0 = m->P + m->params[m->pK[0]].off + (size_t)E * 4 * H;
+  const float* W1 = m->P + m->params[m->pK[1]].off + (size_t)E * 4 * H;
+  k_pack_whh_fwd16<<<dim3((4 * H + 31) / 32, (H + 31) / 32, 2), dim3(32, 8), 0, st>>>(W0, W1, v.Wp16[0], v.Wp16[1], H, v.U, v.UP, v.nsl, v.KP);
+  m->launches++;
+  v.dirty = false;
+}
+static void pack_wih16(icl_model* m, cudaStream_t st) {
+  const int E = m->E, H = m->H;
+  k_pack_wih16<<<dim3((4 * H + 31) / 32, m->k1_Kp / 32, 2), dim3(32, 8), 0, st>>>(m->P + m->params[m->pK[0]].off, m->P + m->params[m->pK[1]].off,
+                                                                                 m->Wih16[0], m->Wih16[1], E, 4 * H, m->k1_Kp);
+  m->launches++;
+  m->wih_dirty = false;
+}
+// the fp16 operand copies of the LSTM weights follow every update: packed on the aux stream right behind the Adam kernel, so they
+// overlap the host work between two steps and the next step's input preparation instead of standing in front of K1 / K2
+static int repack_after_update(icl_model* m) {
+  if (!m->rf_on || !m->rf_last || !m->k1_f16) return 0;
+  CK(cudaEventRecord(m->ev_fork, m->stream));
+  CK(cudaStreamWaitEvent(m->aux, m->ev_fork, 0));
+  pack_wih16(m, m->aux);
+  pack_whh16(m, *m->rf_last, m->aux);
+  CK(cudaEventRecord(m->ev_packs, m->aux));
+  m->packs_pending = true;
+  return 0;
+}
+
 static int rec_forward_fp16(icl_model* m, int training) {
   cudaStream_t st = m->stream;
   icl_model::RfVar* vp = rf_pick(m);
   if (!vp) return fail("k_rec_fwd16: no slicing fits this batch");
   icl_model::RfVar& v = *vp;
-  const int E = m->E, H = m->H, U = v.U;
+  const int H = m->H, U = v.U;
   if (m->wp_dirty) { m->rf20.dirty = m->rf16.dirty = true; m->wp_dirty = false; }
-  if (v.dirty) {
-    const float* W0 = m->P + m->params[m->pK[0]].off + (size_t)E * 4 * H;
-    const float* W1 = m->P + m->params[m->pK[1]].off + (size_t)E * 4 * H;
-    k_pack_whh_fwd16<<<dim3((4 * H + 31) / 32, (H + 31) / 32, 2), dim3(32, 8), 0, st>>>(W0, W1, v.Wp16[0], v.Wp16[1], H, U, v.UP, v.nsl, v.KP);
-    LAUNCHED(m);
-    v.dirty = false;
-  }
+  if (v.dirty) pack_whh16(m, v, st);
+  m->rf_last = vp;
   CK(zero_async(m->rp_flags, (size_t)2 * m->rp_max_tiles * 4, st));
   RecFwd16Args a;
   a.off = m->d_off; a.nact = m->d_nact; a.Tmax = m->Tmax; a.H = H; a.nsl = v.nsl;
@@ -1258,12 +1291,8 @@ static int lstm_forward(icl_model* m, float keep_in, uint64_t seed, int training
   PH_END(m, PH_PREP);
   // K1: time-batched input projection  Z = Xd * W_ih + b   (W_ih = kernel rows [0,E)), both directions
   PH_BEGIN(m, PH_PROJ);
-  if (m->k1_f16 && m->wih_dirty) {
-    k_pack_wih16<<<dim3((4 * H + 31) / 32, m->k1_Kp / 32, 2), dim3(32, 8), 0, st>>>(m->P + m->params[m->pK[0]].off, m->P + m->params[m->pK[1]].off,
-                                                                                   m->Wih16[0], m->Wih16[1], E, 4 * H, m->k1_Kp);
-    LAUNCHED(m);
-    m->wih_dirty = false;
-  }
+  if (m->packs_pending) { CK(cudaStreamWaitEvent(st, m->ev_packs, 0)); m->packs_pending = false; }     // the eager repack of the last update
+  if (m->k1_f16 && m->wih_dirty) pack_wih16(m, st);
   for (int d = 0; d < 2; d++) {
     const float* K = wbase(m) + m->params[m->pK[d]].off;
     GemmArgs g = mk_gemm(m->xd[d], m->ldx, K, 4 * H, m->Z[d], 4 * H, (int)NP, 4 * H, m->k1_f16 ? m->k1_Kp : E);
@@ -1735,10 +1764,13 @@ static int apply_update(icl_model* m, double extra_sumsq) {
     LAUNCHED(m);
   }
   m->wih_dirty = true;
-  if (!getenv("ICL_DEBUG_STALE_WP")) m->wp_dirty = true;
-  m->wb_dirty = true;   // the packed recurrent weights of the persistent forward kernel follow
-                                                             // the update (the env knob exists so that a test can prove it catches staleness)
+  if (!getenv("ICL_DEBUG_STALE_WP")) m->wp_dirty = true;     // the packed recurrent weights of the persistent forward kernel follow the
+  m->wb_dirty = true;                                        // update (the env knob exists so that a test can prove it catches staleness)
   PH_END(m, PH_UPDATE);
+  if (!getenv("ICL_DEBUG_STALE_WP")) {
+    m->rf20.dirty = m->rf16.dirty = true; m->wp_dirty = false;
+    CKI(repack_after_update(m));
+  }
   return 0;
 }
 

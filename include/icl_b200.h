@@ -151,6 +151,9 @@ int icl_wait_head_grads(icl_model* m, void* cuda_stream);
 /* LSTM slice of the gradient: floats [0, first_bw_float) belong to the forward direction, whose weight-gradient GEMM finishes first;
    icl_wait_fw_lstm_grads makes the given stream wait for it (its collective then overlaps the backward direction's GEMM). */
 int icl_grad_split_lstm(icl_model* m, int64_t* first_bw_float);
+/* Joins work queued on the library's side streams behind the last call (the fp16 repack of the LSTM weights after an update; it
+   normally overlaps the next step's input preparation) into the main stream, so that events around ONE step time all of its work. */
+int icl_join_side_work(icl_model* m);
 int icl_wait_fw_lstm_grads(icl_model* m, void* cuda_stream);
 int icl_apply_update(icl_model* m);
 /* Adam state selection: one (m, v, beta-power) set per tf.train.AdamOptimizer instance -- the `alternate` multitask scheme has
