@@ -174,6 +174,7 @@ struct icl_model {
   } rf20, rf16;
   RfVar* rf_last = nullptr;      // the slicing the last forward pass used: repacked eagerly after the update
   cudaEvent_t ev_packs = nullptr; bool packs_pending = false;
+  cudaEvent_t ev_side = nullptr, ev_loss = nullptr; bool loss_pending = false;   // loss / accuracy sums run beside the backward pass
   // fused BPTT step kernel (lstm_bptt.cuh): default backward recurrence in tensor-core mode
   bool bp_on = false, bp_cluster = true;     // bp_cluster: k_bptt_cluster (whole recurrence in one launch) when H <= 336
   int bp_cs = 4;
@@ -675,7 +676,7 @@ extern "C" void icl_destroy(icl_model* m) {
   if (m->aux) cudaStreamDestroy(m->aux);
   if (m->aux2) cudaStreamDestroy(m->aux2);
   if (m->aux3) cudaStreamDestroy(m->aux3);
-  for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_join2, m->ev_t0, m->ev_t1, m->ev_heads, m->ev_wg0, m->ev_packs}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_join2, m->ev_t0, m->ev_t1, m->ev_heads, m->ev_wg0, m->ev_packs, m->ev_side, m->ev_loss}) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : m->ev_dz) if (e) cudaEventDestroy(e);
   for (int i = 0; i < PH_N; i++) for (int j = 0; j < 2; j++) if (m->ev_ph[i][j]) cudaEventDestroy(m->ev_ph[i][j]);
   delete m;
@@ -828,6 +829,8 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   CKD(cudaEventCreateWithFlags(&m->ev_heads, cudaEventDisableTiming));
   CKD(cudaEventCreateWithFlags(&m->ev_wg0, cudaEventDisableTiming));
   CKD(cudaEventCreateWithFlags(&m->ev_packs, cudaEventDisableTiming));
+  CKD(cudaEventCreateWithFlags(&m->ev_side, cudaEventDisableTiming));
+  CKD(cudaEventCreateWithFlags(&m->ev_loss, cudaEventDisableTiming));
   for (auto& e : m->ev_dz) CKD(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CKD(cudaEventCreate(&m->ev_t0)); CKD(cudaEventCreate(&m->ev_t1));
   for (int i = 0; i < PH_N; i++) for (int j = 0; j < 2; j++) CKD(cudaEventCreate(&m->ev_ph[i][j]));
@@ -1280,14 +1283,18 @@ static int lstm_forward(icl_model* m, float keep_in, uint64_t seed, int training
   cudaStream_t st = m->stream;
   if (Ntok == 0) return 0;
   PH_BEGIN(m, PH_PREP);
+  // the pad rows of XH and the zero state in front of step 0 are cleared on the aux stream beside k_prep_x (disjoint rows)
+  CK(cudaEventRecord(m->ev_side, st));
+  CK(cudaStreamWaitEvent(m->aux, m->ev_side, 0));
+  k_zero_pad_rows<<<dim3(m->Tmax, 2), 256, 0, m->aux>>>(m->XH[0], m->XH[1], mk_layout(m), m->ldx); LAUNCHED(m);
+  k_zero_2d<<<dim3(74, 2), 256, 0, m->aux>>>(m->Hp[0], m->Hp[1], m->ldx, H, m->off[1]); LAUNCHED(m);   // h_prev of step 0 (A rows of dW_hh)
+  CK(cudaEventRecord(m->ev_join, m->aux));
   k_prep_x<<<(unsigned)((Ntok * 32 + 255) / 256), 256, 0, st>>>(m->xraw, m->d_tokseq, m->d_tokstart, mk_layout(m), (int)Ntok, E, m->T_cap,
                                                                m->cfg.data_norm, keep_in, seed, m->seq_gid0, m->round_ops, m->xd[0], m->xd[1], m->ldx, E + H,
                                                                m->use_rows ? m->d_tokrow : nullptr, m->tok_table, m->k1_f16 ? m->X16[0] : nullptr,
                                                                m->k1_f16 ? m->X16[1] : nullptr, m->k1_Kp, m->x_half && !m->use_rows);
   LAUNCHED(m);
-  k_zero_pad_rows<<<dim3(m->Tmax, 2), 256, 0, st>>>(m->XH[0], m->XH[1], mk_layout(m), m->ldx); LAUNCHED(m);
-  // h_prev of step 0 is the zero state: step 0's block of Hp stays zero (these are A rows of dW_hh)
-  k_zero_2d<<<dim3(74, 2), 256, 0, st>>>(m->Hp[0], m->Hp[1], m->ldx, H, m->off[1]); LAUNCHED(m);
+  CK(cudaStreamWaitEvent(st, m->ev_join, 0));
   PH_END(m, PH_PREP);
   // K1: time-batched input projection  Z = Xd * W_ih + b   (W_ih = kernel rows [0,E)), both directions
   PH_BEGIN(m, PH_PROJ);
@@ -1362,8 +1369,12 @@ static int heads_forward(icl_model* m, float keep, uint64_t seed) {
                                                       h.has_labels ? h.labels : nullptr, B, scale, h.loss_w, h.proba, h.pred, h.row_loss,
                                                       h.row_correct, h.dlogits);
     LAUNCHED(m);
-    if (h.has_labels) {
-      k_reduce_sum2<<<2, 256, 0, st>>>(h.row_loss, h.row_correct, B, h.scalars, (float)B); LAUNCHED(m);   // loss sum, accuracy mean
+    if (h.has_labels) {      // loss sum, accuracy mean: nothing on the device waits for them -- beside the backward pass, joined at the end of the call
+      CK(cudaEventRecord(m->ev_side, st));
+      CK(cudaStreamWaitEvent(m->aux2, m->ev_side, 0));
+      k_reduce_sum2<<<2, 256, 0, m->aux2>>>(h.row_loss, h.row_correct, B, h.scalars, (float)B); LAUNCHED(m);
+      CK(cudaEventRecord(m->ev_loss, m->aux2));
+      m->loss_pending = true;
     }
   }
   PH_END(m, PH_HEADS_FWD);
@@ -1407,8 +1418,12 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
       k_softmax_bwd<<<nb, SMB_THREADS, (size_t)(SMB_ROWS * C + Kl * (C + 1)) * 4, st>>>(h.act[L - 1], h.dlogits, m->P + pw.off, B, Kl, C, e,
                                                                                          h.dzb[L - 1], h.smb_part);
       LAUNCHED(m);
-      k_softmax_bwd_reduce<<<(Kl * C + C + 31) / 32, dim3(32, 16), 0, st>>>(h.smb_part, nb, Kl * C, C, m->G + pw.off, m->G + pb.off);
+      // its partial sums only feed the softmax layer's own weight / bias gradient: reduced on the aux stream like the other layers' dW
+      CK(cudaEventRecord(m->ev_side, st));
+      CK(cudaStreamWaitEvent(m->aux2, m->ev_side, 0));
+      k_softmax_bwd_reduce<<<(Kl * C + C + 31) / 32, dim3(32, 16), 0, m->aux2>>>(h.smb_part, nb, Kl * C, C, m->G + pw.off, m->G + pb.off);
       LAUNCHED(m);
+      m->heads_aux_pending = true;
     }
     const float* dz = h.dzb[L - 1];    // gradient w.r.t. the pre-activation of layer k+1
     for (int k = L - 1; k >= 0; k--) {
@@ -1791,6 +1806,7 @@ extern "C" int icl_run_resident(icl_model* m, int op, float keep_in, float keep,
     CKI(join_heads_aux(m));
   }
   if (op == ICL_OP_TRAIN) CKI(icl_apply_update(m));
+  if (m->loss_pending) { CK(cudaStreamWaitEvent(m->stream, m->ev_loss, 0)); m->loss_pending = false; }
   CK(cudaEventRecord(m->ev_t1, m->stream));
   CK(cudaEventRecord(I.ev_done, m->stream));                   // this set's device buffers may be overwritten after this point
   I.done_pending = true;
