@@ -392,6 +392,9 @@ static cudaError_t zero_multi_async(std::initializer_list<std::pair<void*, size_
   k_zero_multi<<<dim3(blocks, n), 256, 0, st>>>(r);
   return cudaGetLastError();
 }
+__global__ void k_fill_u16(uint16_t* __restrict__ p, size_t n, uint16_t v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
 static cudaError_t zero_async(void* p, size_t bytes, cudaStream_t st) {
   if (bytes == 0) return cudaSuccess;
   const size_t words = bytes / 4;
@@ -948,6 +951,19 @@ extern "C" int icl_wait_head_grads(icl_model* m, void* cuda_stream) {
 // Work the library has queued on its side streams behind the last call (today: the fp16 repack of the LSTM weights after an update,
 // which normally overlaps the next step's input preparation) is joined into the main stream: a caller that brackets ONE step with
 // events calls this before the closing event so that the step's time includes all of its work.
+// Test hook: fills the fp16 h_{k-1} operand rows of the forward recurrence (every slicing) with 65504.0 on the main stream.  A run
+// publishes every row before another CTA reads it, so the poison must never reach a result; a read of an unpublished row would.
+// (A large finite value rather than NaN: the K-padding columns are multiplied by zero weight rows.)
+extern "C" int icl_debug_poison_recurrence(icl_model* m) {
+  for (auto* v : {&m->rf20, &m->rf16})
+    for (int d = 0; d < 2; d++)
+      if (v->on && v->Hp16[d]) {
+        const size_t n = (size_t)m->rows_cap * v->KP;
+        k_fill_u16<<<1184, 256, 0, m->stream>>>(reinterpret_cast<uint16_t*>(v->Hp16[d]), n, (uint16_t)0x7BFF);
+        CK(cudaGetLastError());
+      }
+  return 0;
+}
 extern "C" int icl_join_side_work(icl_model* m) {
   if (m->packs_pending) { CK(cudaStreamWaitEvent(m->stream, m->ev_packs, 0)); m->packs_pending = false; }
   return 0;

@@ -154,6 +154,8 @@ int icl_grad_split_lstm(icl_model* m, int64_t* first_bw_float);
 /* Joins work queued on the library's side streams behind the last call (the fp16 repack of the LSTM weights after an update; it
    normally overlaps the next step's input preparation) into the main stream, so that events around ONE step time all of its work. */
 int icl_join_side_work(icl_model* m);
+/* Test hook: poisons the fp16 operand rows of the forward recurrence (65504.0); a correct run never reads a row before it is published. */
+int icl_debug_poison_recurrence(icl_model* m);
 int icl_wait_fw_lstm_grads(icl_model* m, void* cuda_stream);
 int icl_apply_update(icl_model* m);
 /* Adam state selection: one (m, v, beta-power) set per tf.train.AdamOptimizer instance -- the `alternate` multitask scheme has

@@ -153,7 +153,12 @@ def run_config(name, dropout):
         if masks is not None:          # the device keeps the exact h (output dropout is applied where the spans are gathered); the oracle's
             dev = dev * masks[key] / keep          # outputs are as emitted by the DropoutWrapper (core.py:309-312)
         rec[key] = relerr(dev, f[key])
-        assert rec[key] < TOL_FWD, (key, rec[key])
+        if rec[key] >= TOL_FWD:          # say WHERE: sequences (by length rank), time steps and units of the offending elements
+            bad = np.argwhere(np.abs(dev - f[key]) > TOL_FWD * np.max(np.abs(f[key])))
+            order = np.argsort(-lens, kind="stable"); rank = np.empty(len(lens), int); rank[order] = np.arange(len(lens))
+            where = dict(n=len(bad), seq_rank_tiles=sorted(set((rank[bad[:, 0]] // 128).tolist()))[:16], t=sorted(set(bad[:, 1].tolist()))[:16],
+                         units4=sorted(set((bad[:, 2] // 4 * 4).tolist()))[:24], lens=sorted(set(lens[bad[:, 0]].tolist()))[:16])
+            raise AssertionError((name, key, rec[key], where))
     bad = {}
     for k, ref in g.items():
         e = grad_errors(sess.get_tensor(k, 1), ref)
@@ -199,4 +204,41 @@ def test_forward_is_bit_reproducible_over_50_runs():
         else:
             assert np.array_equal(r["proba"], first[0]), "run %d differs" % i
             assert float(r["loss"]) == first[1]
+    sess.close()
+
+
+@pytest.mark.parametrize("name", ["multitask512", "card2048"])
+def test_recurrence_never_reads_unpublished_rows(name):
+    """k_rec_fwd16 hands h_{k-1} from CTA to CTA through global memory: a tile's fp16 rows are TMA-stored by every slice, then a
+    counter is bumped, and the consumers' TMA loads follow the counter.  Round 2 found a consumer reading rows BEFORE the store was
+    visible (the counter moved without a proxy fence behind the bulk store) -- invisible to a session that repeats a batch, because
+    the stale contents are the identical values of the previous run.  Here the rows are poisoned (65504.0) before every run: any
+    read of an unpublished row changes the result.  H = 200 (the whole tile fits the ring: loads follow the counter at once) and H = 300."""
+    import bench
+    from imagecaptionlearn_py_b200 import _cabi, core
+    wl = bench.WORKLOADS[name]
+    bts = bench.make_batches(wl, 20171201)
+    bench.build_graph(wl)
+    sess = core.Session(max_seq_len=bench.T_PAD)
+    sess.ensure()
+    L = _cabi.lib()
+    S = sum(len(bt["seq_lengths"]) for bt in bts)
+    first = None
+    for run in range(12):
+        _cabi.check(L.icl_debug_poison_recurrence(sess.handle))
+        sess.base_seed, sess.run_counter = 9, 0
+        res = sess.run(_cabi.OP_GRADS, [dict(bt) for bt in bts], bench.KEEP_IN, bench.KEEP, True)
+        outs = []
+        for d in range(2):
+            out = np.empty((S, sess.max_seq_len, wl["H"]), np.float32)
+            _cabi.check(L.icl_get_lstm_outputs(sess.handle, d, _cabi.np_ptr(out)))
+            outs.append(out)
+        assert all(np.isfinite(o).all() and np.max(np.abs(o)) <= 1.0 for o in outs), "run %d: poisoned rows reached the outputs" % run
+        if first is None:
+            first = (outs, [r["proba"].copy() for r in res])
+        else:
+            for d in range(2):
+                assert np.array_equal(outs[d], first[0][d]), "run %d direction %d differs" % (run, d)
+            for r, p0 in zip(res, first[1]):
+                assert np.array_equal(r["proba"], p0)
     sess.close()
