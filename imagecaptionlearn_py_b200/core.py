@@ -552,10 +552,10 @@ class Session(object):
             _cabi.check(L.icl_grad_split_lstm(self.handle, C.byref(bw)))
             self._split, self._bw = int(split.value), int(bw.value)
         main = torch.cuda.current_stream()
-        # measured (card2048, profiles/r2_allreduce_overlap.md): 8 GPUs 1.453 -> 1.428 ms per step, 2 GPUs 1.403 -> 1.422 (three launches
-        # instead of one cost more than a 9 MB all-reduce between two GPUs): on by default from 4 ranks up
+        # measured (card2048, profiles/r2_allreduce_overlap.md): 8 GPUs 1.453 -> 1.428 ms per step, but 4 GPUs 1.428 -> 1.450 and 2 GPUs
+        # 1.403 -> 1.422 (three launches + cross-stream waits cost more than a 9 MB all-reduce between few GPUs): on by default at 8 ranks
         ov = os.environ.get("ICL_AR_OVERLAP")
-        overlap = (ov != "0" if ov is not None else td.get_world_size() >= 4) and self._split < g.numel()
+        overlap = (ov != "0" if ov is not None else td.get_world_size() >= 8) and self._split < g.numel()
         grp = self._overlap_group() if overlap else None
         if grp is None:
             td.all_reduce(g, op=td.ReduceOp.SUM)

@@ -37,3 +37,22 @@ def test_build_batch_accepts_the_reference_dict_and_rejects_wrong_shapes():
     sess2 = _session(p, B=p["B"] - 1)                                   # more sequences than the graph was built for
     with pytest.raises(ValueError):
         sess2.build_batch([dict(p["batch"])], True, [])
+
+
+def test_shim_exposes_the_tensorflow_names_the_reference_scripts_touch():
+    """`import tensorflow as tf` -> this module: every tf.* symbol icl_core_lstm.py uses (:89-111,155,393) must
+    exist with the reference's call shapes.  (tests/test_ref_script.py runs the script bodies themselves on a GPU.)"""
+    tf = core
+    core.reset_default_graph()
+    with tf.variable_scope("bidirectional_lstm"):
+        core.setup_bidirectional_lstm(4, False, n_embedding_width=8)
+    core.setup_core_architecture("nonvis", "first_last_mention", 6, 8, 1, False, "relu", 2, 4)
+    loss = tf.get_collection("loss")[0]
+    core.add_train_op(loss, 1e-3, 1e-8, 5.0)
+    assert tf.get_collection("train_op")[0].kind == "train_op" and tf.get_collection("accuracy")[0].kind == "accuracy"
+    assert tf.global_variables_initializer().kind == "init"
+    assert isinstance(tf.train.Saver(max_to_keep=100), core.Saver)
+    core.dump_tf_vars()
+    sess = tf.Session()                       # no arguments, like tf.Session(); the device model is created on first use
+    assert sess.handle is None and sess.max_seq_len > 0
+    core.reset_default_graph()
