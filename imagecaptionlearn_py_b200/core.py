@@ -532,17 +532,60 @@ class Session(object):
                 self._ar_group = None
         return self._ar_group
 
+    def _nvls_setup(self):
+        """Puts the flat gradient buffer into symmetric memory (torch.distributed._symmetric_memory: the same allocation on every rank,
+        mapped into one NVSwitch multicast object) and hands it to the library (icl_adopt_grad_buffer).  Returns (tensor, handle) or
+        None; every rank takes the same decision (a MIN all-reduce of the outcome), so a rank that cannot do it never leaves the
+        others waiting in a collective."""
+        import torch
+        import torch.distributed as td
+        ok, t, hdl = 1, None, None
+        try:
+            if os.environ.get("ICL_AR_NVLS", "1") == "0":
+                raise RuntimeError("disabled")
+            import torch.distributed._symmetric_memory as symm_mem
+            p, n = C.c_void_p(), C.c_int64()
+            _cabi.check(_cabi.lib().icl_grad_buffer(self.handle, C.byref(p), C.byref(n)))
+            t = symm_mem.empty((n.value + 3) // 4 * 4, dtype=torch.float32, device=torch.device("cuda", self.device))
+        except Exception:
+            ok = 0
+        flag = torch.tensor([ok], device="cuda:%d" % self.device, dtype=torch.int32)
+        td.all_reduce(flag, op=td.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            return None
+        try:
+            hdl = symm_mem.rendezvous(t, td.group.WORLD)
+            ok = 1 if int(getattr(hdl, "multicast_ptr", 0) or 0) != 0 else 0
+        except Exception:
+            ok = 0
+        flag.fill_(ok)
+        td.all_reduce(flag, op=td.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            return None
+        _cabi.check(_cabi.lib().icl_adopt_grad_buffer(self.handle, C.c_void_p(t.data_ptr()), t.numel()))
+        self._grad_view = None
+        return (t, hdl)
+
     def allreduce_grads(self):
-        """SUM all-reduce of the flat gradient buffer of the step just enqueued (the loss is a SUM over examples, core.py:267), in
-        three buckets released as the backward pass produces them:
-          heads' slice      -- complete before the BPTT starts: reduced on a side stream while the BPTT and the weight-gradient GEMMs run;
-          LSTM fw slice     -- complete after the forward direction's weight-gradient GEMM: reduced while the backward direction's runs;
-          LSTM bw slice     -- the only exposed collective, on the main stream.
-        The two overlapped buckets go through a CTA-capped communicator (`_overlap_group`).  ICL_AR_OVERLAP=0: one all-reduce after
-        the backward pass."""
+        """SUM all-reduce of the flat gradient buffer of the step just enqueued (the loss is a SUM over examples, core.py:267).
+
+        Default on an NVSwitch box: the buffer lives in symmetric / multicast memory and `icl_nvls_allreduce` sums it IN the switch --
+        rank r reads slice r of all ranks with multimem.ld_reduce and broadcasts the sum with multimem.st (our kernel, no NCCL, no
+        staging), between two cross-rank barriers of the symmetric-memory handle.  Fallbacks: NCCL in three buckets overlapped with
+        the backward pass at 8 ranks (`_overlap_group`), else one NCCL all-reduce after the backward pass (ICL_AR_NVLS=0 /
+        ICL_AR_OVERLAP=0|1 force)."""
         import torch
         import torch.distributed as td
         L = _cabi.lib()
+        if getattr(self, "_nvls", False) is False or getattr(self, "_nvls_handle", None) is not self.handle:
+            self._nvls = self._nvls_setup() if td.get_backend() == "nccl" else None
+            self._nvls_handle = self.handle
+        if self._nvls is not None:
+            t, hdl = self._nvls
+            hdl.barrier(channel=0)                      # every rank's gradients are complete
+            _cabi.check(L.icl_nvls_allreduce(self.handle, C.c_void_p(int(hdl.multicast_ptr)), td.get_rank(), td.get_world_size()))
+            hdl.barrier(channel=1)                      # every slice has been written to every rank
+            return
         g = self.grad_tensor()
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device)

@@ -140,6 +140,7 @@ struct icl_model {
   bool resident = false;
   cudaStream_t stream = nullptr, aux = nullptr, aux2 = nullptr, aux3 = nullptr;      // aux2: the heads' weight gradients
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  bool G_external = false;             // the gradient buffer belongs to the caller (symmetric memory, icl_adopt_grad_buffer)
   cudaEvent_t ev_heads = nullptr;      // recorded when the heads' parameter gradients are complete (before the BPTT)
   cudaEvent_t ev_wg0 = nullptr;        // recorded when the forward direction's LSTM weight gradient is complete (before the backward direction's)
   cudaEvent_t ev_dz[ICL_MAX_LAYERS + 2] = {};   // heads' backward: "dz of this layer is ready" (main stream -> aux stream)
@@ -651,7 +652,7 @@ extern "C" void icl_destroy(icl_model* m) {
   if (!m) return;
   cudaDeviceSynchronize();
   auto F = [](void* p) { if (p) cudaFree(p); };
-  F(m->P); F(m->G); F(m->Pr); F(m->tok_table); F(m->box_table);
+  F(m->P); if (!m->G_external) F(m->G); F(m->Pr); F(m->tok_table); F(m->box_table);
   if (m->slots.empty()) { F(m->M); F(m->V); }
   else {                       // m->M / m->V alias the live slot
     m->slots[m->cur_slot].M = m->M; m->slots[m->cur_slot].V = m->V;
@@ -933,6 +934,41 @@ extern "C" int icl_set_tensor(icl_model* m, int kind, const char* name, const fl
 extern "C" int icl_get_step(icl_model* m, int64_t* t) { *t = m->step; return 0; }
 extern "C" int icl_set_step(icl_model* m, int64_t t) { m->step = t; return 0; }
 extern "C" int icl_grad_buffer(icl_model* m, void** p, int64_t* n) { *p = m->G; *n = m->n_params; return 0; }
+// Data parallel over NVSwitch: the caller hands the library a gradient buffer it allocated in SYMMETRIC memory (same size on every
+// rank, mapped into a multicast object: torch.distributed._symmetric_memory) -- every kernel then writes its gradients there -- and
+// icl_nvls_allreduce sums it over the ranks IN the switch: rank r reads slice r of all ranks' buffers with ONE multimem.ld_reduce per
+// 16 bytes and writes the sum back to slice r of all of them with one multimem.st.  No NCCL kernel, no staging; the caller brackets
+// the call with cross-rank barriers (all gradients complete before / all slices written after).
+extern "C" int icl_adopt_grad_buffer(icl_model* m, void* buf, int64_t n_floats) {
+  if (n_floats < m->n_params) return fail("icl_adopt_grad_buffer: %lld floats < %lld parameters", (long long)n_floats, (long long)m->n_params);
+  if (((uintptr_t)buf & 15) != 0) return fail("icl_adopt_grad_buffer: the buffer must be 16-byte aligned");
+  CK(cudaStreamSynchronize(m->stream));
+  if (m->G && !m->G_external) CK(cudaFree(m->G));
+  m->G = reinterpret_cast<float*>(buf);
+  m->G_external = true;
+  CK(cudaMemsetAsync(m->G, 0, (size_t)m->n_params * 4, m->stream));
+  return 0;
+}
+__global__ void k_nvls_allreduce(float* __restrict__ mc, long n4, int rank, int world) {
+  // slice of this rank in float4 units; every element of the buffer is read-reduced and written by exactly one rank
+  const long per = (n4 + world - 1) / world, lo = rank * per, hi = lo + per < n4 ? lo + per : n4;
+  for (long i = lo + (long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long)gridDim.x * blockDim.x) {
+    float4 v;
+    float* a = mc + i * 4;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  }
+}
+extern "C" int icl_nvls_allreduce(icl_model* m, void* multicast_ptr, int32_t rank, int32_t world) {
+  if (!m->G_external) return fail("icl_nvls_allreduce: no symmetric gradient buffer adopted");
+  if (world < 1 || rank < 0 || rank >= world) return fail("icl_nvls_allreduce: rank %d of %d", rank, world);
+  const long n4 = (m->n_params + 3) / 4;             // the symmetric buffer is allocated in whole float4s
+  const long per = (n4 + world - 1) / world;
+  const int blocks = (int)std::max<long>(1, std::min<long>(296, (per + 255) / 256));
+  k_nvls_allreduce<<<blocks, 256, 0, m->stream>>>(reinterpret_cast<float*>(multicast_ptr), n4, rank, world);
+  m->launches++;
+  return cudaGetLastError() == cudaSuccess ? 0 : fail("k_nvls_allreduce launch failed");
+}
 // Overlapping the gradient all-reduce with the backward pass: the flat gradient buffer is [LSTM | heads]; the heads' part is
 // final once the heads' backward has run, long before the BPTT and the weight-gradient GEMMs finish.  `first_head_float` = where
 // the heads' gradients start; icl_wait_head_grads makes `cuda_stream` wait for them (cudaStreamWaitEvent), so a collective

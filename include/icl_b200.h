@@ -154,6 +154,11 @@ int icl_grad_split_lstm(icl_model* m, int64_t* first_bw_float);
 /* Joins work queued on the library's side streams behind the last call (the fp16 repack of the LSTM weights after an update; it
    normally overlaps the next step's input preparation) into the main stream, so that events around ONE step time all of its work. */
 int icl_join_side_work(icl_model* m);
+/* Data parallel over NVSwitch (no counterpart in the reference, which has no multi-GPU path): the library writes its gradients into a
+   buffer the caller allocated in symmetric / multicast-mapped memory, and icl_nvls_allreduce sums that buffer over the ranks inside the
+   switch (multimem.ld_reduce + multimem.st, each rank one slice).  The caller provides the cross-rank barriers around it. */
+int icl_adopt_grad_buffer(icl_model* m, void* symmetric_buffer, int64_t n_floats);
+int icl_nvls_allreduce(icl_model* m, void* multicast_ptr, int32_t rank, int32_t world);
 /* Test hook: poisons the fp16 operand rows of the forward recurrence (65504.0); a correct run never reads a row before it is published. */
 int icl_debug_poison_recurrence(icl_model* m);
 int icl_wait_fw_lstm_grads(icl_model* m, void* cuda_stream);
