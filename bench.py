@@ -354,7 +354,7 @@ def measure(name, steps, warmup, ctx, clocks=None, e2e_variants=False):
     from imagecaptionlearn_py_b200 import data as nn_data
     wl = WORKLOADS[name]
     dist, rank, world, local = ctx.dist, ctx.rank, ctx.world, ctx.local
-    seed0 = 20171201 + 1000 * rank
+    seed0 = 20171201 + 1000 * (0 if os.environ.get("ICL_BENCH_SAME_BATCH") else rank)     # (every rank the same batch: isolates rank imbalance)
     bts = make_batches(wl, seed0)
     train_op = build_graph(wl)
     sess = core.Session(max_seq_len=T_PAD, device=local, dist=bool(dist), gemm_mode=ctx.gemm_mode)
