@@ -91,6 +91,11 @@ struct Head {
   float loss_w = 1.0f;               // d joint_loss / d loss of this head (icl_set_loss_weights)
   HeadIn in[2];
   float* h_out = nullptr; long long* h_pred = nullptr;   // pinned staging of the results
+  // multi-head models (icl_multitask_lstm.py): the heads only share the encoder, so every head runs its forward / backward chain on
+  // its OWN stream pair (hs: the dz chain, ha: its weight gradients), forked from and joined to the model's stream -- five heads of
+  // latency-bound kernels side by side instead of one after another.  Single-head models use the model's stream / aux2.
+  cudaStream_t hs = nullptr, ha = nullptr;
+  cudaEvent_t ev_done = nullptr, ev_adone = nullptr;
 };
 
 enum { PH_PREP = 0, PH_PROJ, PH_REC_FWD, PH_HEADS_FWD, PH_HEADS_BWD, PH_REC_BWD, PH_WGRAD, PH_UPDATE, PH_N };
@@ -176,6 +181,8 @@ struct icl_model {
   RfVar* rf_last = nullptr;      // the slicing the last forward pass used: repacked eagerly after the update
   cudaEvent_t ev_packs = nullptr; bool packs_pending = false;
   cudaEvent_t ev_side = nullptr, ev_loss = nullptr; bool loss_pending = false;   // loss / accuracy sums run beside the backward pass
+  cudaEvent_t ev_hfork = nullptr;      // multi-head models: the point of the model's stream every head stream starts from
+  bool head_streams = true;            // ICL_HEAD_STREAMS=0: the heads of a multi-head model one after another on the model's stream (A/B)
   // fused BPTT step kernel (lstm_bptt.cuh): default backward recurrence in tensor-core mode
   bool bp_on = false, bp_cluster = true;     // bp_cluster: k_bptt_cluster (whole recurrence in one launch) when H <= 336
   int bp_cs = 4;
@@ -676,11 +683,15 @@ extern "C" void icl_destroy(icl_model* m) {
     F(h.proba); F(h.dlogits); F(h.smb_part); F(h.row_loss); F(h.row_correct); F(h.scalars); F(h.pred);
     if (h.h_out) cudaFreeHost(h.h_out);
     if (h.h_pred) cudaFreeHost(h.h_pred);
+    if (h.hs) cudaStreamDestroy(h.hs);
+    if (h.ha) cudaStreamDestroy(h.ha);
+    if (h.ev_done) cudaEventDestroy(h.ev_done);
+    if (h.ev_adone) cudaEventDestroy(h.ev_adone);
   }
   if (m->aux) cudaStreamDestroy(m->aux);
   if (m->aux2) cudaStreamDestroy(m->aux2);
   if (m->aux3) cudaStreamDestroy(m->aux3);
-  for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_join2, m->ev_t0, m->ev_t1, m->ev_heads, m->ev_wg0, m->ev_packs, m->ev_side, m->ev_loss}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_join2, m->ev_t0, m->ev_t1, m->ev_heads, m->ev_wg0, m->ev_packs, m->ev_side, m->ev_loss, m->ev_hfork}) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : m->ev_dz) if (e) cudaEventDestroy(e);
   for (int i = 0; i < PH_N; i++) for (int j = 0; j < 2; j++) if (m->ev_ph[i][j]) cudaEventDestroy(m->ev_ph[i][j]);
   delete m;
@@ -808,6 +819,7 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   CKD(cudaMallocHost((void**)&m->h_stats, (size_t)2 * ICL_MAX_HEADS * 2 * 4));
   CKD(cudaStreamCreateWithFlags(&m->copy, cudaStreamNonBlocking));
   CKD(dmalloc(&m->d_partial, 1024)); CKD(dmalloc(&m->d_gnorm, 4));
+  if (const char* e = getenv("ICL_HEAD_STREAMS")) m->head_streams = atoi(e) != 0;
   for (auto& h : m->heads) {
     int B = h.c.batch_size, C = h.c.n_classes;
     int maxw = 0;
@@ -822,6 +834,10 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
     CKD(dmalloc(&h.row_loss, B)); CKD(dmalloc(&h.row_correct, B)); CKD(dmalloc(&h.scalars, 4)); CKD(dmalloc(&h.pred, B));
     CKD(cudaMallocHost((void**)&h.h_out, ((size_t)B * C + 4) * 4));
     CKD(cudaMallocHost((void**)&h.h_pred, (size_t)B * 8));
+    if (m->heads.size() > 1 && m->head_streams) {
+      CKD(cudaStreamCreateWithFlags(&h.hs, cudaStreamNonBlocking)); CKD(cudaStreamCreateWithFlags(&h.ha, cudaStreamNonBlocking));
+      CKD(cudaEventCreateWithFlags(&h.ev_done, cudaEventDisableTiming)); CKD(cudaEventCreateWithFlags(&h.ev_adone, cudaEventDisableTiming));
+    }
   }
   use_input_set(m, 0);
   CKD(cudaStreamCreateWithFlags(&m->aux, cudaStreamNonBlocking));
@@ -835,6 +851,7 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   CKD(cudaEventCreateWithFlags(&m->ev_packs, cudaEventDisableTiming));
   CKD(cudaEventCreateWithFlags(&m->ev_side, cudaEventDisableTiming));
   CKD(cudaEventCreateWithFlags(&m->ev_loss, cudaEventDisableTiming));
+  CKD(cudaEventCreateWithFlags(&m->ev_hfork, cudaEventDisableTiming));
   for (auto& e : m->ev_dz) CKD(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CKD(cudaEventCreate(&m->ev_t0)); CKD(cudaEventCreate(&m->ev_t1));
   for (int i = 0; i < PH_N; i++) for (int j = 0; j < 2; j++) CKD(cudaEventCreate(&m->ev_ph[i][j]));
@@ -1408,12 +1425,16 @@ static int lstm_forward(icl_model* m, float keep_in, uint64_t seed, int training
 static Drop mk_drop(uint64_t seed, uint32_t stream, float keep, int64_t gid0) { Drop d; d.seed = seed; d.stream = stream; d.keep = keep; d.row_gid0 = gid0; return d; }
 
 static int heads_forward(icl_model* m, float keep, uint64_t seed) {
-  cudaStream_t st = m->stream;
+  const cudaStream_t st0 = m->stream;
   int H = m->H;
   PH_BEGIN(m, PH_HEADS_FWD);
+  const bool fork = m->heads.size() > 1 && m->heads[0].hs != nullptr;
+  if (fork) CK(cudaEventRecord(m->ev_hfork, st0));
   for (size_t hi = 0; hi < m->heads.size(); hi++) {
     Head& h = m->heads[hi];
     if (!h.active) continue;
+    const cudaStream_t st = fork ? h.hs : st0;
+    if (fork) CK(cudaStreamWaitEvent(st, m->ev_hfork, 0));
     int B = h.c.batch_size, C = h.c.n_classes, L = h.c.n_hidden;
     k_gather_concat<<<dim3(B, h.slots.n_slots), 96, 0, st>>>(h.slots, m->Hx[0], m->Hx[1], mk_layout(m), H, m->T_cap, h.ldbi, mk_drop(seed, 0, keep, m->seq_gid0),
                                       m->round_ops, h.bi);
@@ -1439,6 +1460,7 @@ static int heads_forward(icl_model* m, float keep, uint64_t seed) {
       CK(cudaEventRecord(m->ev_loss, m->aux2));
       m->loss_pending = true;
     }
+    if (fork) { CK(cudaEventRecord(h.ev_done, st)); CK(cudaStreamWaitEvent(st0, h.ev_done, 0)); }
   }
   PH_END(m, PH_HEADS_FWD);
   return 0;
@@ -1453,19 +1475,25 @@ static int colsum(icl_model* m, cudaStream_t st, const float* X, long rows, int 
 }
 
 static int heads_backward(icl_model* m, float keep, uint64_t seed) {
-  cudaStream_t st = m->stream;
+  const cudaStream_t st0 = m->stream;
   int H = m->H;
   PH_BEGIN(m, PH_HEADS_BWD);
+  const bool fork = m->heads.size() > 1 && m->heads[0].hs != nullptr;
+  for (size_t hi = 0; hi < m->heads.size(); hi++)
+    if (m->heads[hi].active && !m->heads[hi].has_labels) return fail("backward needs labels for head %zu", hi);
   // ONE launch clears everything the backward pass accumulates into: dHout of both directions (span scatter), the WHOLE flat
   // gradient buffer (split-K weight gradients and bias column sums of every head and of the LSTM add into it; heads that are not
   // fed keep a zero gradient) and the dc carry of the BPTT
   CK(zero_multi_async({{m->dHout[0], (size_t)m->NtokP * H * 4}, {m->dHout[1], (size_t)m->NtokP * H * 4}, {m->G, (size_t)m->n_params * 4},
-                       {m->dcc[0], (size_t)m->S * H * 4}, {m->dcc[1], (size_t)m->S * H * 4}}, st));
+                       {m->dcc[0], (size_t)m->S * H * 4}, {m->dcc[1], (size_t)m->S * H * 4}}, st0));
   LAUNCHED(m);
+  if (fork) CK(cudaEventRecord(m->ev_hfork, st0));
   for (size_t hi = 0; hi < m->heads.size(); hi++) {
     Head& h = m->heads[hi];
     if (!h.active) continue;                  // not fed in this call: its parameters keep the zero gradient
-    if (!h.has_labels) return fail("backward needs labels for head %zu", hi);
+    // st: this head's dz chain; sa: its weight / bias gradients (span scatters of concurrent heads meet in dHout as float atomics)
+    const cudaStream_t st = fork ? h.hs : st0, sa = fork ? h.ha : m->aux2;
+    if (fork) CK(cudaStreamWaitEvent(st, m->ev_hfork, 0));
     int B = h.c.batch_size, L = h.c.n_hidden;
     // Layer by layer from the softmax down: the chain dz_k -> dz_{k-1} = (dz_k W_k^T) * act' stays on the main stream; the weight
     // and bias gradients of layer k only need dz_k, so they run on the aux stream concurrently with the rest of the chain
@@ -1483,8 +1511,8 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
       LAUNCHED(m);
       // its partial sums only feed the softmax layer's own weight / bias gradient: reduced on the aux stream like the other layers' dW
       CK(cudaEventRecord(m->ev_side, st));
-      CK(cudaStreamWaitEvent(m->aux2, m->ev_side, 0));
-      k_softmax_bwd_reduce<<<(Kl * C + C + 31) / 32, dim3(32, 16), 0, m->aux2>>>(h.smb_part, nb, Kl * C, C, m->G + pw.off, m->G + pb.off);
+      CK(cudaStreamWaitEvent(sa, m->ev_side, 0));
+      k_softmax_bwd_reduce<<<(Kl * C + C + 31) / 32, dim3(32, 16), 0, sa>>>(h.smb_part, nb, Kl * C, C, m->G + pw.off, m->G + pb.off);
       LAUNCHED(m);
       m->heads_aux_pending = true;
     }
@@ -1494,11 +1522,11 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
       int din = h.dims[k], dout = h.dims[k + 1];
       const Param& pw = m->params[h.pW[k]];
       CK(cudaEventRecord(m->ev_dz[k], st));
-      CK(cudaStreamWaitEvent(m->aux2, m->ev_dz[k], 0));
+      CK(cudaStreamWaitEvent(sa, m->ev_dz[k], 0));
       // dW = in^T * dz   (contraction over the batch: both operands MN-major)
       GemmArgs gw = mk_gemm(in, k == 0 ? h.ldbi : din, dz, dout, m->G + pw.off, dout, din, dout, B);
-      CKI(gemm(m, m->aux2, true, true, gw, -1, 0, true));
-      CKI(colsum(m, m->aux2, dz, B, dout, dout, m->G + m->params[h.pB[k]].off));
+      CKI(gemm(m, sa, true, true, gw, -1, 0, true));
+      CKI(colsum(m, sa, dz, B, dout, dout, m->G + m->params[h.pB[k]].off));
       m->heads_aux_pending = true;
       // d(in) = dz * W^T  (W [din,dout] row-major is K-major as the B operand)
       if (k > 0) {
@@ -1516,9 +1544,13 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
         LAUNCHED(m);
       }
     }
+    if (fork) {      // chain -> the model's stream; weight gradients -> aux2, where ev_heads marks "every head gradient complete"
+      CK(cudaEventRecord(h.ev_done, st)); CK(cudaStreamWaitEvent(st0, h.ev_done, 0));
+      CK(cudaEventRecord(h.ev_adone, sa)); CK(cudaStreamWaitEvent(m->aux2, h.ev_adone, 0));
+    }
   }
   PH_END(m, PH_HEADS_BWD);
-  CK(cudaEventRecord(m->ev_heads, m->heads_aux_pending ? m->aux2 : st));   // the head gradients can be all-reduced while the BPTT runs
+  CK(cudaEventRecord(m->ev_heads, m->heads_aux_pending ? m->aux2 : st0));   // the head gradients can be all-reduced while the BPTT runs
   return 0;
 }
 // the heads' weight gradients (aux stream) must be complete before anything reads the gradient buffer on the main stream
