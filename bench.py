@@ -370,6 +370,20 @@ def measure(name, steps, warmup, ctx, clocks=None, e2e_variants=False):
     _cabi.check(L.icl_batch_stats(sess.handle, C.byref(ns), C.byref(nt), C.byref(tm)))
     n_seqs, n_tok, t_max = ns.value, nt.value, tm.value
     n_examples = sum(h["B"] for h in wl["heads"])
+    # affinity heads: how layer 1 of the resident batch runs (factorised over the batch's distinct mentions / boxes)
+    factor = {}
+    for hi, h in enumerate(wl["heads"]):
+        if h["task"] == "affinity":
+            f_, nm_, nb_ = C.c_int32(), C.c_int32(), C.c_int32()
+            _cabi.check(L.icl_head_factor_stats(sess.handle, hi, C.byref(f_), C.byref(nm_), C.byref(nb_), None))
+            d0m, w1 = 4 * wl["H"] + h["F"], h["start"]
+            factor[hi] = dict(formulation="factorised: z1 = U[mention] + V[box] + b1, one GEMM row per distinct mention / box" if f_.value
+                              else "concatenated [mention | box] rows", pairs=h["B"], distinct_mentions=nm_.value if f_.value else h["B"],
+                              distinct_boxes=nb_.value if f_.value else h["B"],
+                              layer1_fwd_flops_concatenated=2 * h["B"] * (d0m + BOX_W) * w1,
+                              layer1_fwd_flops_executed=2 * ((nm_.value * d0m + nb_.value * BOX_W) if f_.value else h["B"] * (d0m + BOX_W)) * w1,
+                              note="training batches are reference-shaped (one caption copy per pair, nn_utils/data.py:397-403): the "
+                                   "mentions do not repeat, the 4096 box columns collapse to the distinct boxes")
 
     def resident_step(i):
         seed = 1000 + i
@@ -442,7 +456,7 @@ def measure(name, steps, warmup, ctx, clocks=None, e2e_variants=False):
     ms_per_step = max_over_ranks(total_ms) / steps
     out = dict(wl=wl, n_seqs=n_seqs, n_tok=n_tok, t_max=t_max, n_examples=n_examples, ms_per_step=ms_per_step, ph_ms=phases / steps,
                launches=n1.value - n0.value, wall_ms=1e3 * wall / steps, value=world * n_seqs / (ms_per_step * 1e-3),
-               b2b_ms=max_over_ranks(b2b_ms))
+               b2b_ms=max_over_ranks(b2b_ms), factor=factor)
 
     # ---- end-to-end through the reference-facing API with host buffers: a rotation of N_ROT distinct host batches (a real
     # training loop never re-feeds a cache-warm buffer), as many timed steps as the device-timed leg
@@ -512,6 +526,8 @@ def summarise(name, r, pk, world, traffic=None):
              roofline=dict(kernel=roof["kernel"], phase=roof["phase"], bound=roof["bound"], frac=roof["frac"], achieved=roof["achieved"],
                            peak=roof["peak"], unit=roof["unit"]),
              gpu_launches_per_step=r["launches"] / max(1, r.get("steps", 1)))
+    if r.get("factor"):
+        d["affinity_layer1"] = {wl["heads"][hi]["scope"] or "affinity": v for hi, v in r["factor"].items()}
     if wl["heads"][0]["task"] == "affinity" and len(wl["heads"]) == 1:
         d["unit_pairs"] = "mention-box pairs/s = examples_per_sec"
     return d, roof, by_phase

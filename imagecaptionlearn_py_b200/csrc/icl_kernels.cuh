@@ -403,6 +403,8 @@ struct SlotTable {
   const int* idx[16];  // kind 0: [B,3] int32 on device
   const float* dense[16];  // kind 1: [B,width], or (rowidx set) a resident table [n_rows,width]
   const int* rowidx[16];   // kind 1, optional: [B] row of example b in the resident table (icl_set_box_table)
+  const int* rowmap;       // optional: output row b is built from example rowmap[b] (index rows, dense rows without rowidx) -- the
+                           // distinct mentions of an affinity batch (layer-1 factorisation) are gathered once each
 };
 
 // one block per (example, slot) -- every slot's index chain (index row -> length / rank / step offset -> state row) resolves
@@ -410,12 +412,12 @@ struct SlotTable {
 // batch_input is only ever a GEMM operand (layer-1 forward, layer-1 weight gradient): stored TF32-rounded.
 __global__ void k_gather_concat(SlotTable st, const float* __restrict__ h_fw, const float* __restrict__ h_bw, StepLayout L,
                                 int H, int Tcap, int D0, Drop drop, int round_ops, float* __restrict__ out) {
-  int b = blockIdx.x;
-  float* o = out + (long)b * D0;
+  const int bo = blockIdx.x, b = st.rowmap ? st.rowmap[bo] : bo;
+  float* o = out + (long)bo * D0;
   {
     const int sl = blockIdx.y;
     if (st.kind[sl] == 1) {
-      const float* src = st.dense[sl] + (long)(st.rowidx[sl] ? st.rowidx[sl][b] : b) * st.width[sl];
+      const float* src = st.dense[sl] + (long)(st.rowidx[sl] ? st.rowidx[sl][bo] : b) * st.width[sl];
       if ((st.width[sl] & 3) == 0 && (st.col[sl] & 3) == 0 && (D0 & 3) == 0) {
         for (int e = threadIdx.x * 4; e < st.width[sl]; e += blockDim.x * 4) {
           float4 v = *reinterpret_cast<const float4*>(src + e);
@@ -450,8 +452,8 @@ __global__ void k_gather_concat(SlotTable st, const float* __restrict__ h_fw, co
 // backward: scatter-add d(batch_input) into dH_fw/bw (pre-dropout gradient, dropout scaling applied here)
 __global__ void k_scatter_spans(SlotTable st, const float* __restrict__ dbi, StepLayout L, int H, int Tcap, int D0, Drop drop,
                                 float* __restrict__ dh_fw, float* __restrict__ dh_bw) {
-  int b = blockIdx.x;
-  const float* g = dbi + (long)b * D0;
+  const int bo = blockIdx.x, b = st.rowmap ? st.rowmap[bo] : bo;
+  const float* g = dbi + (long)bo * D0;
   {                                                  // one block per (example, slot), like k_gather_concat
     const int sl = blockIdx.y;
     if (st.kind[sl] == 1) return;
@@ -472,6 +474,39 @@ __global__ void k_scatter_spans(SlotTable st, const float* __restrict__ dbi, Ste
       if (v[0] != 0.0f || v[1] != 0.0f || v[2] != 0.0f || v[3] != 0.0f)
         atomicAdd(reinterpret_cast<float4*>(dst + u), make_float4(v[0], v[1], v[2], v[3]));     // one 16-byte red (sm_90+)
     }
+  }
+}
+
+// ----------------------------------------------------------------------------- affinity layer 1, factorised
+// batch_input of a mention-box pair is [mention encoding | m_feats | box row (| b_feats)] (core.py:421-433), so
+//   z1[p] = [enc, m_feats](mention of p) . W1[0:Dm]  +  [box (, b_feats)](box of p) . W1[Dm:D0]  +  b1  =  U[m_of[p]] + V[b_of[p]] + b1
+// with U computed once per DISTINCT mention and V once per distinct box of the batch (a batch of 512 pairs of ~2 images holds ~30
+// mentions and ~40 boxes).  This kernel is the layer's epilogue: the pair's two rows, bias, activation, dropout -- bit for bit
+// the epilogue of the concatenated GEMM (same mask stream / element numbering).  One block per pair.
+__global__ void k_pair_combine(const float* __restrict__ U, const float* __restrict__ V, const int* __restrict__ m_of,
+                               const int* __restrict__ b_of, int N, Epilogue e, float* __restrict__ out) {
+  const int p = blockIdx.x;
+  const float* u = U + (long)m_of[p] * N;
+  const float* v = V + (long)b_of[p] * N;
+  float* o = out + (long)p * N;
+  if ((N & 3) == 0) {
+    for (int n = threadIdx.x * 4; n < N; n += blockDim.x * 4) {
+      const float4 a = *reinterpret_cast<const float4*>(u + n), c = *reinterpret_cast<const float4*>(v + n);
+      *reinterpret_cast<float4*>(o + n) = epilogue_apply4(e, make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w), p, n, N);
+    }
+  } else {
+    for (int n = threadIdx.x; n < N; n += blockDim.x) o[n] = epilogue_apply(e, u[n] + v[n], p, n, N);
+  }
+}
+// backward of the row fan-out: dU[g] = sum of dz1[p] over the pairs p of group g, in list order (CSR lists built by the host in
+// pair order: no atomics, bit-reproducible); stored TF32-rounded when it only feeds tensor-core contractions.  One block per group.
+__global__ void k_segment_sum(const float* __restrict__ dz, int N, const int* __restrict__ start, const int* __restrict__ members,
+                              int round_ops, float* __restrict__ out) {
+  const int g = blockIdx.x, p0 = start[g], p1 = start[g + 1];
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float acc = 0.0f;
+    for (int i = p0; i < p1; i++) acc += dz[(long)members[i] * N + n];
+    out[(long)g * N + n] = maybe_round(acc, round_ops);
   }
 }
 

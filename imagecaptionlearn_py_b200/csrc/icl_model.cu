@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <unordered_map>
 #include <numeric>
 #include <atomic>
 #include <condition_variable>
@@ -58,6 +59,8 @@ struct Param { std::string name; int rows, cols; int64_t off; };
 // concurrently running compute stream by ~80 us each -- measured 1.3 ms per step).
 struct HeadIn {                                             // byte offsets into the set's blob
   size_t idx[ICL_N_INDEX] = {}, feats = 0, box = 0, bfeats = 0, labels = 0, boxrow = 0;
+  // affinity layer-1 factorisation: group of every pair, representative pair of every group, CSR member lists (int32 each)
+  size_t m_of = 0, b_of = 0, rep_m = 0, rep_boxrow = 0, m_start = 0, m_mem = 0, b_start = 0, b_mem = 0;
 };
 struct InSet {
   char *d_blob = nullptr, *h_blob = nullptr;
@@ -96,6 +99,21 @@ struct Head {
   // latency-bound kernels side by side instead of one after another.  Single-head models use the model's stream / aux2.
   cudaStream_t hs = nullptr, ha = nullptr;
   cudaEvent_t ev_done = nullptr, ev_adone = nullptr;
+  // Affinity layer 1, factorised (the concat it replaces: core.py:421-433,439): batch_input of a pair is
+  // [mention columns (Dm) | box columns (Db)], so z1 = U[mention of the pair] + V[box of the pair] + b1 with
+  // U = Xm W1[0:Dm] over the batch's DISTINCT mentions and V = Xb W1[Dm:D0] over its distinct boxes (k_pair_combine).
+  bool fact_ok = false;              // an affinity head with a box block (and ICL_AFF_FACTOR != 0)
+  bool fact = false;                 // the uploaded batch runs factorised (its groups are few enough, or ICL_AFF_FACTOR=2)
+  bool box_compact = false;          // fact, host box rows: only the distinct rows were packed (row g of the box / b_feats blocks = group g)
+  int Dm = 0, Db = 0, ldm = 0, ldb = 0, Mu = 0, Nu = 0;
+  int64_t fact_batches = 0, fact_mu = 0, fact_nu = 0;     // statistics (icl_head_factor_stats)
+  SlotTable slots_m, slots_b;        // the mention / box halves of `slots` (rows = groups)
+  std::vector<int> slotm_src, slotb_src;
+  float *Xm = nullptr, *Xb = nullptr, *U = nullptr, *V = nullptr, *dU = nullptr, *dV = nullptr, *dXm = nullptr;
+  int *d_m_of = nullptr, *d_b_of = nullptr, *d_rep_m = nullptr, *d_rep_boxrow = nullptr, *d_m_start = nullptr, *d_m_mem = nullptr,
+      *d_b_start = nullptr, *d_b_mem = nullptr, *d_boxrow = nullptr;
+  cudaStream_t sb = nullptr;         // the box half of the forward pass: needs no LSTM state, runs beside the recurrence
+  cudaEvent_t ev_bfork = nullptr, ev_box = nullptr, ev_du = nullptr;
 };
 
 enum { PH_PREP = 0, PH_PROJ, PH_REC_FWD, PH_HEADS_FWD, PH_HEADS_BWD, PH_REC_BWD, PH_WGRAD, PH_UPDATE, PH_N };
@@ -182,6 +200,8 @@ struct icl_model {
   cudaEvent_t ev_packs = nullptr; bool packs_pending = false;
   cudaEvent_t ev_side = nullptr, ev_loss = nullptr; bool loss_pending = false;   // loss / accuracy sums run beside the backward pass
   cudaEvent_t ev_hfork = nullptr;      // multi-head models: the point of the model's stream every head stream starts from
+  float last_keep = 1.0f; uint64_t last_seed = 0;      // of the last icl_run_resident (icl_get_batch_input of a factorised head)
+  bool pdl = true;                     // ICL_PDL=0: the heads' GEMM chains without programmatic dependent launches (A/B)
   bool head_streams = true;            // ICL_HEAD_STREAMS=0: the heads of a multi-head model one after another on the model's stream (A/B)
   // fused BPTT step kernel (lstm_bptt.cuh): default backward recurrence in tensor-core mode
   bool bp_on = false, bp_cluster = true;     // bp_cluster: k_bptt_cluster (whole recurrence in one launch) when H <= 336
@@ -329,6 +349,48 @@ struct HostPool {
   }
 };
 static HostPool& host_pool() { static HostPool* p = new HostPool(); return *p; }   // leaked on purpose (no exit-time join)
+
+
+// ----------------------------------------------------------------------------- affinity layer-1 factorisation: host side
+static int aff_mode() { const char* e = getenv("ICL_AFF_FACTOR"); return e ? atoi(e) : 1; }   // 0 off, 1 when it pays, 2 always
+static uint64_t mix64(uint64_t h, uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); return h * 0xff51afd7ed558ccdull; }
+static uint64_t hash_bytes(const void* p, size_t n, uint64_t h = 0x243f6a8885a308d3ull) {
+  const unsigned char* c = (const unsigned char*)p;
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8) { uint64_t v; memcpy(&v, c + i, 8); h = mix64(h, v); }
+  if (i < n) { uint64_t v = 0; memcpy(&v, c + i, n - i); h = mix64(h, v); }
+  return h;
+}
+// 32 eight-byte samples spread over a long row: picks the candidate group, the full comparison decides
+static uint64_t hash_sampled(const void* p, size_t n, uint64_t h = 0x13198a2e03707344ull) {
+  if (n <= 512) return hash_bytes(p, n, h);
+  const unsigned char* c = (const unsigned char*)p;
+  const size_t stride = (n - 8) / 31;
+  for (int i = 0; i < 32; i++) { uint64_t v; memcpy(&v, c + (size_t)i * stride, 8); h = mix64(h, v); }
+  return h;
+}
+// groups of equal rows in order of first appearance: of[r] = group of row r, rep[g] = first row of group g.  `same` is the exact test.
+template <typename Same>
+static void group_rows(int B, const std::vector<uint64_t>& key, Same same, int* of, std::vector<int>& rep) {
+  std::unordered_map<uint64_t, std::vector<int>> cand;
+  cand.reserve((size_t)B * 2);
+  rep.clear();
+  for (int r = 0; r < B; r++) {
+    std::vector<int>& c = cand[key[r]];
+    int g = -1;
+    for (int q : c) if (same(r, rep[q])) { g = q; break; }
+    if (g < 0) { g = (int)rep.size(); rep.push_back(r); c.push_back(g); }
+    of[r] = g;
+  }
+}
+static void csr_lists(int B, int G, const int* of, int* start, int* mem) {
+  for (int g = 0; g <= G; g++) start[g] = 0;
+  for (int r = 0; r < B; r++) start[of[r] + 1]++;
+  for (int g = 0; g < G; g++) start[g + 1] += start[g];
+  std::vector<int> fill(start, start + G);
+  for (int r = 0; r < B; r++) mem[fill[of[r]]++] = r;           // pair order inside a group: the order the segment sums add in
+}
+static size_t dtype_size(int dt) { return dt == ICL_F64 ? 8 : 4; }
 
 static void slot_plan(const icl_head_config& c, std::vector<int>& kinds /*index id or -1..-3*/) {
   // nn_utils/core.py:377-433.  -1 feats, -2 box, -3 bfeats
@@ -588,7 +650,28 @@ static void use_input_set(icl_model* m, int s) {
       if (id >= 0) h.slots.idx[i] = h.idx[id];
       else h.slots.dense[i] = id == -1 ? h.feats : id == -2 ? h.box : h.bfeats;
     }
+    h.d_boxrow = I.dev<int>(hin.boxrow);
+    if (h.fact_ok) {
+      h.d_m_of = I.dev<int>(hin.m_of); h.d_b_of = I.dev<int>(hin.b_of); h.d_rep_m = I.dev<int>(hin.rep_m);
+      h.d_rep_boxrow = I.dev<int>(hin.rep_boxrow); h.d_m_start = I.dev<int>(hin.m_start); h.d_m_mem = I.dev<int>(hin.m_mem);
+      h.d_b_start = I.dev<int>(hin.b_start); h.d_b_mem = I.dev<int>(hin.b_mem);
+    }
   }
+}
+// the mention / box halves of a factorised head's slot table for the resident batch (after icl_upload has settled the box source)
+static void fact_slots(Head& h, const float* box_table) {
+  for (size_t j = 0; j < h.slotm_src.size(); j++) {
+    const int i = h.slotm_src[j];
+    h.slots_m.idx[j] = h.slots.idx[i]; h.slots_m.dense[j] = h.slots.dense[i]; h.slots_m.rowidx[j] = nullptr;
+  }
+  h.slots_m.rowmap = h.Mu == h.c.batch_size ? nullptr : h.d_rep_m;     // row g = the group's first pair: its index rows, its m_feats row
+  for (size_t j = 0; j < h.slotb_src.size(); j++) {
+    const int i = h.slotb_src[j];
+    const bool table = h.slot_index_id[i] == -2 && !h.box_compact;
+    h.slots_b.dense[j] = table ? box_table : h.slots.dense[i];           // compact blocks: row g = group g
+    h.slots_b.rowidx[j] = table ? h.d_rep_boxrow : nullptr;
+  }
+  h.slots_b.rowmap = nullptr;
 }
 
 static int bptt_init(icl_model* m) {
@@ -683,6 +766,9 @@ extern "C" void icl_destroy(icl_model* m) {
     F(h.proba); F(h.dlogits); F(h.smb_part); F(h.row_loss); F(h.row_correct); F(h.scalars); F(h.pred);
     if (h.h_out) cudaFreeHost(h.h_out);
     if (h.h_pred) cudaFreeHost(h.h_pred);
+    F(h.Xm); F(h.Xb); F(h.U); F(h.V); F(h.dU); F(h.dV); F(h.dXm);
+    if (h.sb) cudaStreamDestroy(h.sb);
+    for (cudaEvent_t e : {h.ev_bfork, h.ev_box, h.ev_du}) if (e) cudaEventDestroy(e);
     if (h.hs) cudaStreamDestroy(h.hs);
     if (h.ha) cudaStreamDestroy(h.ha);
     if (h.ev_done) cudaEventDestroy(h.ev_done);
@@ -748,6 +834,27 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
     h.slot_index_id = plan;
     h.D0 = col;
     h.ldbi = (h.D0 + 3) / 4 * 4; h.lddbi = (std::max(h.D0g, 1) + 3) / 4 * 4;
+    {   // mention / box halves of the column plan
+      int aff_mode = 1;
+      if (const char* e = getenv("ICL_AFF_FACTOR")) aff_mode = atoi(e);
+      h.fact_ok = aff_mode != 0 && h.c.task == ICL_TASK_AFFINITY && h.c.box_width > 0;
+      memset(&h.slots_m, 0, sizeof(h.slots_m)); memset(&h.slots_b, 0, sizeof(h.slots_b));
+      if (h.fact_ok) {
+        for (size_t i = 0; i < plan.size(); i++) {
+          const bool boxside = plan[i] == -2 || plan[i] == -3;
+          SlotTable& t = boxside ? h.slots_b : h.slots_m;
+          if (boxside && h.slots_b.n_slots == 0) h.Dm = h.slots.col[i];
+          const int j = t.n_slots++;
+          t.kind[j] = h.slots.kind[i]; t.width[j] = h.slots.width[i]; t.col[j] = h.slots.col[i] - (boxside ? h.Dm : 0);
+          (boxside ? h.slotb_src : h.slotm_src).push_back((int)i);
+        }
+        h.Db = h.D0 - h.Dm;
+        h.ldm = (h.Dm + 3) / 4 * 4; h.ldb = (h.Db + 3) / 4 * 4;
+        // box columns must be the tail of the plan (they are: core.py:421-433) and the W1 row split 16-byte aligned
+        if (h.Dm <= 0 || h.Db <= 0 || ((int64_t)h.Dm * h.c.widths[0]) % 4 != 0) h.fact_ok = false;
+        for (size_t i = 0; i + 1 < plan.size(); i++) if ((plan[i] == -2 || plan[i] == -3) && plan[i + 1] >= -1) h.fact_ok = false;
+      }
+    }
     h.dims.push_back(h.D0);
     for (int k = 0; k < h.c.n_hidden; k++) h.dims.push_back(h.c.widths[k]);
     h.dims.push_back(h.c.n_classes);
@@ -807,6 +914,10 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
       hin.feats = take(B * h.c.n_feats * 4); hin.box = take(B * h.c.box_width * 4); hin.bfeats = take(B * h.c.n_box_feats * 4);
       hin.labels = take(B * h.c.n_classes * 4);
       hin.boxrow = take(B * 4);
+      if (h.fact_ok) {
+        hin.m_of = take(B * 4); hin.b_of = take(B * 4); hin.rep_m = take(B * 4); hin.rep_boxrow = take(B * 4);
+        hin.m_start = take((B + 1) * 4); hin.m_mem = take(B * 4); hin.b_start = take((B + 1) * 4); hin.b_mem = take(B * 4);
+      }
     }
     I.o_tokrow = take((size_t)m->Ntok_cap * 4);
     I.o_tokseq = take((size_t)m->Ntok_cap * 4);              // last: only its used prefix is copied
@@ -820,6 +931,7 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   CKD(cudaStreamCreateWithFlags(&m->copy, cudaStreamNonBlocking));
   CKD(dmalloc(&m->d_partial, 1024)); CKD(dmalloc(&m->d_gnorm, 4));
   if (const char* e = getenv("ICL_HEAD_STREAMS")) m->head_streams = atoi(e) != 0;
+  if (const char* e = getenv("ICL_PDL")) m->pdl = atoi(e) != 0;
   for (auto& h : m->heads) {
     int B = h.c.batch_size, C = h.c.n_classes;
     int maxw = 0;
@@ -834,6 +946,16 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
     CKD(dmalloc(&h.row_loss, B)); CKD(dmalloc(&h.row_correct, B)); CKD(dmalloc(&h.scalars, 4)); CKD(dmalloc(&h.pred, B));
     CKD(cudaMallocHost((void**)&h.h_out, ((size_t)B * C + 4) * 4));
     CKD(cudaMallocHost((void**)&h.h_pred, (size_t)B * 8));
+    if (h.fact_ok) {
+      const size_t w1 = (size_t)h.dims[1];
+      CKD(dmalloc(&h.Xm, (size_t)B * h.ldm)); CKD(cudaMemset(h.Xm, 0, (size_t)B * h.ldm * 4));
+      CKD(dmalloc(&h.Xb, (size_t)B * h.ldb)); CKD(cudaMemset(h.Xb, 0, (size_t)B * h.ldb * 4));
+      CKD(dmalloc(&h.U, B * w1)); CKD(dmalloc(&h.V, B * w1)); CKD(dmalloc(&h.dU, B * w1)); CKD(dmalloc(&h.dV, B * w1));
+      CKD(dmalloc(&h.dXm, (size_t)B * h.lddbi)); CKD(cudaMemset(h.dXm, 0, (size_t)B * h.lddbi * 4));
+      CKD(cudaStreamCreateWithFlags(&h.sb, cudaStreamNonBlocking));
+      CKD(cudaEventCreateWithFlags(&h.ev_bfork, cudaEventDisableTiming)); CKD(cudaEventCreateWithFlags(&h.ev_box, cudaEventDisableTiming));
+      CKD(cudaEventCreateWithFlags(&h.ev_du, cudaEventDisableTiming));
+    }
     if (m->heads.size() > 1 && m->head_streams) {
       CKD(cudaStreamCreateWithFlags(&h.hs, cudaStreamNonBlocking)); CKD(cudaStreamCreateWithFlags(&h.ha, cudaStreamNonBlocking));
       CKD(cudaEventCreateWithFlags(&h.ev_done, cudaEventDisableTiming)); CKD(cudaEventCreateWithFlags(&h.ev_adone, cudaEventDisableTiming));
@@ -1170,6 +1292,7 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
       s0 = s1;
     }
   }
+  std::vector<std::pair<size_t, size_t>> holes;          // byte ranges of the meta region nothing on the device will read
   for (int hi = 0; hi < b->n_heads; hi++) {
     Head& h = m->heads[hi];
     HeadIn& hin = h.in[set];
@@ -1199,7 +1322,8 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
       return 0;
     };
     CKI(up(hb.feats, hb.feats_dtype, hin.feats, (size_t)B * h.c.n_feats, "m_feats/ij_feats"));
-    if (hb.box_rows && h.c.box_width > 0) {                 // rows of the resident box table instead of [B, 4096] floats
+    const bool box_table_rows = hb.box_rows && h.c.box_width > 0;
+    if (box_table_rows) {                 // rows of the resident box table instead of [B, 4096] floats
       if (!m->box_table) return fail("icl_upload: head %d gives box_rows but no box table was set (icl_set_box_table)", hi);
       int* br = I.host<int>(hin.boxrow);
       for (int r = 0; r < B; r++) {
@@ -1209,14 +1333,88 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
       }
       for (int sl = 0; sl < h.slots.n_slots; sl++)
         if (h.slot_index_id[sl] == -2) { h.slots.dense[sl] = m->box_table; h.slots.rowidx[sl] = I.dev<int>(hin.boxrow); }
-    } else
-    CKI(up(hb.box, hb.box_dtype, hin.box, (size_t)B * h.c.box_width, "box_embeddings"));
-    CKI(up(hb.bfeats, hb.bfeats_dtype, hin.bfeats, (size_t)B * h.c.n_box_feats, "b_feats"));
+    } else if (h.c.box_width > 0 && !hb.box) return fail("icl_upload: head %d is missing box_embeddings", hi);
+    if (h.c.n_box_feats > 0 && !hb.bfeats) return fail("icl_upload: head %d is missing b_feats", hi);
+    // Affinity layer-1 factorisation: the distinct mentions (index rows + m_feats row) and distinct boxes (table row, or the
+    // bytes of the host row, + b_feats row) of the batch; a hash picks the candidates, an exact comparison decides
+    h.fact = false; h.box_compact = false;
+    const int fmode = h.fact_ok ? aff_mode() : 0;
+    if (fmode != 0) {
+      int *m_of = I.host<int>(hin.m_of), *b_of = I.host<int>(hin.b_of);
+      std::vector<uint64_t> key(B);
+      std::vector<int> rep_m, rep_b;
+      const size_t fsz = (size_t)h.c.n_feats * dtype_size(hb.feats_dtype), xsz = (size_t)h.c.box_width * dtype_size(hb.box_dtype),
+                   bsz = (size_t)h.c.n_box_feats * dtype_size(hb.bfeats_dtype);
+      const char *fsrc = (const char*)hb.feats, *xsrc = (const char*)hb.box, *bsrc = (const char*)hb.bfeats;
+      std::vector<const int*> ixs;
+      for (int i : h.slotm_src) if (h.slot_index_id[i] >= 0) ixs.push_back(I.host<int>(hin.idx[h.slot_index_id[i]]));
+      for (int r = 0; r < B; r++) {
+        uint64_t k = 0x452821e638d01377ull;
+        for (const int* ix : ixs) k = hash_bytes(ix + r * 3, 12, k);      // the m_feats rows are compared, not hashed
+        key[r] = k;
+      }
+      group_rows(B, key, [&](int a, int c) {
+        for (const int* ix : ixs) if (memcmp(ix + a * 3, ix + c * 3, 12) != 0) return false;
+        return fsz == 0 || memcmp(fsrc + a * fsz, fsrc + c * fsz, fsz) == 0;
+      }, m_of, rep_m);
+      const int per = 32;
+      host_pool().run((B + per - 1) / per, [&](int it) {
+        for (int r = it * per; r < std::min(B, (it + 1) * per); r++) {
+          uint64_t k = box_table_rows ? mix64(0x3c6ef372fe94f82bull, (uint64_t)hb.box_rows[r]) : hash_sampled(xsrc + r * xsz, xsz);
+          if (bsz) k = hash_bytes(bsrc + r * bsz, bsz, k);
+          key[r] = k;
+        }
+      });
+      group_rows(B, key, [&](int a, int c) {
+        if (box_table_rows ? hb.box_rows[a] != hb.box_rows[c] : memcmp(xsrc + a * xsz, xsrc + c * xsz, xsz) != 0) return false;
+        return bsz == 0 || memcmp(bsrc + a * bsz, bsrc + c * bsz, bsz) == 0;
+      }, b_of, rep_b);
+      h.Mu = (int)rep_m.size(); h.Nu = (int)rep_b.size();
+      // reference-shaped TRAINING batches carry one copy of the caption per pair (nn_utils/data.py:397-403: every copy draws its own
+      // dropout masks), so their mentions do not repeat and only the box half (4096 of the 5552 columns) collapses; prediction
+      // batches built with load_batch(dedup=True) share captions and collapse on both sides
+      h.fact = fmode >= 2 || h.Nu * 2 <= B;
+      if (h.fact) {
+        h.box_compact = !box_table_rows;
+        memcpy(I.host<int>(hin.rep_m), rep_m.data(), (size_t)h.Mu * 4);
+        int* rbr = I.host<int>(hin.rep_boxrow);
+        for (int g = 0; g < h.Nu; g++) rbr[g] = box_table_rows ? hb.box_rows[rep_b[g]] : rep_b[g];
+        csr_lists(B, h.Mu, m_of, I.host<int>(hin.m_start), I.host<int>(hin.m_mem));
+        csr_lists(B, h.Nu, b_of, I.host<int>(hin.b_start), I.host<int>(hin.b_mem));
+        // only the distinct box / b_feats rows are packed: row g of the block = group g
+        host_pool().run(h.Nu, [&](int g) {
+          if (!box_table_rows) to_f32(I.host<float>(hin.box) + (size_t)g * h.c.box_width, xsrc + rep_b[g] * xsz, hb.box_dtype, h.c.box_width);
+          if (bsz) to_f32(I.host<float>(hin.bfeats) + (size_t)g * h.c.n_box_feats, bsrc + rep_b[g] * bsz, hb.bfeats_dtype, h.c.n_box_feats);
+          if (g_pack_nt) _mm_sfence();
+        });
+        fact_slots(h, m->box_table);
+        h.fact_batches++; h.fact_mu += h.Mu; h.fact_nu += h.Nu;
+        // the unused tails of the two blocks need not cross PCIe
+        if (!box_table_rows) holes.push_back({hin.box + (size_t)h.Nu * h.c.box_width * 4, hin.box + (size_t)B * h.c.box_width * 4});
+        if (bsz) holes.push_back({hin.bfeats + (size_t)h.Nu * h.c.n_box_feats * 4, hin.bfeats + (size_t)B * h.c.n_box_feats * 4});
+      }
+    }
+    if (!h.fact) {
+      if (!box_table_rows) CKI(up(hb.box, hb.box_dtype, hin.box, (size_t)B * h.c.box_width, "box_embeddings"));
+      CKI(up(hb.bfeats, hb.bfeats_dtype, hin.bfeats, (size_t)B * h.c.n_box_feats, "b_feats"));
+    }
     h.has_labels = hb.labels != nullptr;
     if (h.has_labels) CKI(up(hb.labels, hb.labels_dtype, hin.labels, (size_t)B * C, "labels"));
   }
   // everything but the sentence rows: ONE copy of the meta region (the token->sequence map is last: only its used prefix)
-  H2D(I.d_blob + I.meta_off, I.h_blob + I.meta_off, I.o_tokseq - I.meta_off + (size_t)ntok * 4, st);
+  // (a factorised affinity head packs only its distinct box rows: the copy skips the rest of that block when it is worth a second call)
+  {
+    size_t pos = I.meta_off;
+    const size_t end = I.o_tokseq + (size_t)ntok * 4;
+    std::sort(holes.begin(), holes.end());
+    for (const auto& hole : holes) {
+      const size_t h0 = (hole.first + 255) & ~(size_t)255, h1 = hole.second & ~(size_t)255;
+      if (h1 <= h0 || h1 - h0 < (512u << 10) || h0 < pos) continue;
+      H2D(I.d_blob + pos, I.h_blob + pos, h0 - pos, st);
+      pos = h1;
+    }
+    H2D(I.d_blob + pos, I.h_blob + pos, end - pos, st);
+  }
   CK(cudaEventRecord(I.ev_copied, st));
   I.copied_pending = true;
   m->S = S; m->Tmax = tmax; m->Ntok = ntok; m->NtokP = m->off[tmax];
@@ -1357,6 +1555,7 @@ static int rec_forward_persistent(icl_model* m, int training) {
 #endif
 }
 
+static int heads_prefetch(icl_model* m);
 static int lstm_forward(icl_model* m, float keep_in, uint64_t seed, int training) {
   int E = m->E, H = m->H;
   long Ntok = m->Ntok, NP = m->NtokP;
@@ -1390,6 +1589,7 @@ static int lstm_forward(icl_model* m, float keep_in, uint64_t seed, int training
     } else CKI(gemm(m, st, false, true, g));
   }
   PH_END(m, PH_PROJ);
+  CKI(heads_prefetch(m));      // box halves of factorised affinity heads: beside the recurrence (which leaves SMs idle), not beside K1
   // K2: the recurrence
   PH_BEGIN(m, PH_REC_FWD);
   if (rec_usable(m)) {
@@ -1424,6 +1624,27 @@ static int lstm_forward(icl_model* m, float keep_in, uint64_t seed, int training
 
 static Drop mk_drop(uint64_t seed, uint32_t stream, float keep, int64_t gid0) { Drop d; d.seed = seed; d.stream = stream; d.keep = keep; d.row_gid0 = gid0; return d; }
 
+// The box half of a factorised affinity head's layer 1 (V = Xb W1[Dm:D0], one row per distinct box) needs no LSTM state: it is
+// issued at the start of the step on the head's box stream and runs beside the recurrence; k_pair_combine waits for it.
+// No split-K here (the forward pass stays free of float atomics: bit-reproducible predictions).
+static int heads_prefetch(icl_model* m) {
+  for (size_t hi = 0; hi < m->heads.size(); hi++) {
+    Head& h = m->heads[hi];
+    if (!h.active || !h.fact) continue;
+    const int w1 = h.dims[1];
+    CK(cudaEventRecord(h.ev_bfork, m->stream));
+    CK(cudaStreamWaitEvent(h.sb, h.ev_bfork, 0));
+    k_gather_concat<<<dim3(h.Nu, h.slots_b.n_slots), 96, 0, h.sb>>>(h.slots_b, m->Hx[0], m->Hx[1], mk_layout(m), m->H, m->T_cap, h.ldb,
+                                                                     mk_drop(0, 0, 1.0f, 0), m->round_ops, h.Xb);
+    LAUNCHED(m);
+    const Param& pw = m->params[h.pW[0]];
+    GemmArgs g = mk_gemm(h.Xb, h.ldb, wbase(m) + pw.off + (int64_t)h.Dm * w1, w1, h.V, w1, h.Nu, w1, h.Db);
+    CKI(gemm(m, h.sb, false, true, g));
+    CK(cudaEventRecord(h.ev_box, h.sb));
+  }
+  return 0;
+}
+
 static int heads_forward(icl_model* m, float keep, uint64_t seed) {
   const cudaStream_t st0 = m->stream;
   int H = m->H;
@@ -1436,16 +1657,34 @@ static int heads_forward(icl_model* m, float keep, uint64_t seed) {
     const cudaStream_t st = fork ? h.hs : st0;
     if (fork) CK(cudaStreamWaitEvent(st, m->ev_hfork, 0));
     int B = h.c.batch_size, C = h.c.n_classes, L = h.c.n_hidden;
-    k_gather_concat<<<dim3(B, h.slots.n_slots), 96, 0, st>>>(h.slots, m->Hx[0], m->Hx[1], mk_layout(m), H, m->T_cap, h.ldbi, mk_drop(seed, 0, keep, m->seq_gid0),
-                                      m->round_ops, h.bi);
-    LAUNCHED(m);
     const float* in = h.bi;
-    for (int k = 0; k < L; k++) {
+    int k0 = 0;
+    if (h.fact) {          // layer 1 = U[mention] + V[box] + b1, activation, dropout (see Head::fact)
+      const int w1 = h.dims[1];
+      k_gather_concat<<<dim3(h.Mu, h.slots_m.n_slots), 96, 0, st>>>(h.slots_m, m->Hx[0], m->Hx[1], mk_layout(m), H, m->T_cap, h.ldm,
+                                                                    mk_drop(seed, 0, keep, m->seq_gid0), m->round_ops, h.Xm);
+      LAUNCHED(m);
+      GemmArgs gu = mk_gemm(h.Xm, h.ldm, wbase(m) + m->params[h.pW[0]].off, w1, h.U, w1, h.Mu, w1, h.Dm);
+      CKI(gemm(m, st, false, true, gu));
+      CK(cudaStreamWaitEvent(st, h.ev_box, 0));
+      Epilogue e; memset(&e, 0, sizeof(e));
+      e.mode = EPI_BIAS_ACT_DROP; e.bias = m->P + m->params[h.pB[0]].off; e.act = h.c.activation;
+      e.drop = mk_drop(seed, STREAM_HEAD + (uint32_t)hi * 8 + 0, keep, m->ex_gid0);
+      k_pair_combine<<<B, 128, 0, st>>>(h.U, h.V, h.d_m_of, h.d_b_of, w1, e, h.act[0]);
+      LAUNCHED(m);
+      in = h.act[0];
+      k0 = 1;
+    } else {
+      k_gather_concat<<<dim3(B, h.slots.n_slots), 96, 0, st>>>(h.slots, m->Hx[0], m->Hx[1], mk_layout(m), H, m->T_cap, h.ldbi,
+                                                               mk_drop(seed, 0, keep, m->seq_gid0), m->round_ops, h.bi);
+      LAUNCHED(m);
+    }
+    for (int k = k0; k < L; k++) {
       const Param& pw = m->params[h.pW[k]];
       GemmArgs g = mk_gemm(in, k == 0 ? h.ldbi : h.dims[k], wbase(m) + pw.off, h.dims[k + 1], h.act[k], h.dims[k + 1], B, h.dims[k + 1], h.dims[k]);
       g.epi.mode = EPI_BIAS_ACT_DROP; g.epi.bias = m->P + m->params[h.pB[k]].off; g.epi.act = h.c.activation;
       g.epi.drop = mk_drop(seed, STREAM_HEAD + (uint32_t)hi * 8 + k, keep, m->ex_gid0);
-      CKI(gemm(m, st, false, true, g));
+      CKI(gemm(m, st, false, true, g, -1, 1, false, m->pdl));      // programmatic dependent launch: the prologue overlaps the previous layer's tail
       in = h.act[k];
     }
     float scale = h.c.weighted_classes ? 1.0f / B : 1.0f;   // "weighted" as executed == mean CE (core.py:244-267)
@@ -1523,6 +1762,33 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
       const Param& pw = m->params[h.pW[k]];
       CK(cudaEventRecord(m->ev_dz[k], st));
       CK(cudaStreamWaitEvent(sa, m->ev_dz[k], 0));
+      if (k == 0 && h.fact) {
+        // factorised layer 1 in reverse: dU[g] / dV[g] = sums of dz1 over the pairs of a mention / a box (ordered, no atomics), then
+        //   dW1[0:Dm] = Xm^T dU,  dW1[Dm:D0] = Xb^T dV  (contractions over a few dozen groups instead of the batch),
+        //   d(mention columns) = dU W1[0:D0g]^T -> span scatter, once per distinct mention
+        CKI(colsum(m, sa, dz, B, dout, dout, m->G + m->params[h.pB[0]].off));
+        const float* dU = dz;                      // no mention repeats (Mu == B): the groups are the pairs
+        if (h.Mu != B) {
+          k_segment_sum<<<h.Mu, 128, 0, st>>>(dz, dout, h.d_m_start, h.d_m_mem, m->round_ops, h.dU); LAUNCHED(m);
+          CK(cudaEventRecord(h.ev_du, st));
+          CK(cudaStreamWaitEvent(sa, h.ev_du, 0));
+          dU = h.dU;
+        }
+        GemmArgs gm = mk_gemm(h.Xm, h.ldm, dU, dout, m->G + pw.off, dout, h.Dm, dout, h.Mu);
+        CKI(gemm(m, sa, true, true, gm, -1, 0, true));
+        k_segment_sum<<<h.Nu, 128, 0, sa>>>(dz, dout, h.d_b_start, h.d_b_mem, m->round_ops, h.dV); LAUNCHED(m);
+        GemmArgs gb = mk_gemm(h.Xb, h.ldb, h.dV, dout, m->G + pw.off + (int64_t)h.Dm * dout, dout, h.Db, dout, h.Nu);
+        CKI(gemm(m, sa, true, true, gb, -1, 0, true));
+        m->heads_aux_pending = true;
+        if (h.D0g > 0) {
+          GemmArgs gx = mk_gemm(dU, dout, wbase(m) + pw.off, dout, h.dXm, h.lddbi, h.Mu, h.D0g, dout);
+          CKI(gemm(m, st, false, false, gx));
+          k_scatter_spans<<<dim3(h.Mu, h.slots_m.n_slots), 96, 0, st>>>(h.slots_m, h.dXm, mk_layout(m), H, m->T_cap, h.lddbi,
+                                                                        mk_drop(seed, 0, keep, m->seq_gid0), m->dHout[0], m->dHout[1]);
+          LAUNCHED(m);
+        }
+        continue;
+      }
       // dW = in^T * dz   (contraction over the batch: both operands MN-major)
       GemmArgs gw = mk_gemm(in, k == 0 ? h.ldbi : din, dz, dout, m->G + pw.off, dout, din, dout, B);
       CKI(gemm(m, sa, true, true, gw, -1, 0, true));
@@ -1534,11 +1800,11 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
         gx.epi.mode = EPI_DACT; gx.epi.act = h.c.activation; gx.epi.aux = h.act[k - 1]; gx.epi.ldaux = din;
         gx.epi.drop = mk_drop(seed, STREAM_HEAD + (uint32_t)hi * 8 + (k - 1), keep, m->ex_gid0);
         gx.epi.round_out = m->round_ops;
-        CKI(gemm(m, st, false, false, gx));
+        CKI(gemm(m, st, false, false, gx, -1, 1, false, m->pdl));
         dz = h.dzb[k - 1];
       } else if (h.D0g > 0) {
         GemmArgs gx = mk_gemm(dz, dout, wbase(m) + pw.off, dout, h.dbi, h.lddbi, B, h.D0g, dout);
-        CKI(gemm(m, st, false, false, gx));
+        CKI(gemm(m, st, false, false, gx, -1, 1, false, m->pdl));
         k_scatter_spans<<<dim3(B, h.slots.n_slots), 96, 0, st>>>(h.slots, h.dbi, mk_layout(m), H, m->T_cap, h.lddbi, mk_drop(seed, 0, keep, m->seq_gid0),
                                           m->dHout[0], m->dHout[1]);
         LAUNCHED(m);
@@ -1893,6 +2159,7 @@ extern "C" int icl_run_resident(icl_model* m, int op, float keep_in, float keep,
   CK(cudaEventRecord(I.ev_s0, m->stream));
   CK(cudaEventRecord(m->ev_t0, m->stream));
   CKI(refresh_rounded_params(m));
+  m->last_keep = keep; m->last_seed = seed;
   CKI(lstm_forward(m, keep_in, seed, op >= ICL_OP_GRADS));
   CKI(heads_forward(m, keep, seed));
   if (op >= ICL_OP_GRADS) {
@@ -2001,9 +2268,30 @@ extern "C" int icl_get_lstm_outputs(icl_model* m, int dir, float* host) {
   return 0;
 }
 extern "C" int icl_get_batch_input(icl_model* m, int head, float* host) {
+  if (head < 0 || head >= (int)m->heads.size()) return fail("head out of range");
   Head& h = m->heads[head];
   CK(cudaStreamSynchronize(m->stream));
+  if (h.fact) {      // a factorised affinity head never builds the concatenated rows: build them here, for the caller (tests)
+    SlotTable t = h.slots;
+    for (int i = 0; i < t.n_slots; i++)
+      if ((h.slot_index_id[i] == -2 && h.box_compact) || h.slot_index_id[i] == -3) t.rowidx[i] = h.d_b_of;     // compact blocks: row = group
+    k_gather_concat<<<dim3(h.c.batch_size, t.n_slots), 96, 0, m->stream>>>(t, m->Hx[0], m->Hx[1], mk_layout(m), m->H, m->T_cap, h.ldbi,
+                                                                           mk_drop(m->last_seed, 0, m->last_keep, m->seq_gid0), m->round_ops, h.bi);
+    LAUNCHED(m);
+    CK(cudaStreamSynchronize(m->stream));
+  }
   CK(cudaMemcpy2D(host, (size_t)h.D0 * 4, h.bi, (size_t)h.ldbi * 4, (size_t)h.D0 * 4, h.c.batch_size, cudaMemcpyDeviceToHost));
+  return 0;
+}
+// Affinity layer-1 factorisation of head `head`: whether the resident batch runs factorised, its distinct mentions / boxes, and the
+// totals over all uploads so far (batches that ran factorised, their distinct mentions and boxes).
+extern "C" int icl_head_factor_stats(icl_model* m, int head, int32_t* factorised, int32_t* n_mentions, int32_t* n_boxes, int64_t* totals) {
+  if (head < 0 || head >= (int)m->heads.size()) return fail("head out of range");
+  const Head& h = m->heads[head];
+  if (factorised) *factorised = h.fact ? 1 : 0;
+  if (n_mentions) *n_mentions = h.fact ? h.Mu : 0;
+  if (n_boxes) *n_boxes = h.fact ? h.Nu : 0;
+  if (totals) { totals[0] = h.fact_batches; totals[1] = h.fact_mu; totals[2] = h.fact_nu; }
   return 0;
 }
 extern "C" int icl_get_activation(icl_model* m, int head, int layer, float* host) {

@@ -178,6 +178,10 @@ int icl_sync(icl_model* m);
 /* test / profiling hooks */
 int icl_get_lstm_outputs(icl_model* m, int dir, float* host_STH);        /* pre-dropout outputs, padded [S,T,H] */
 int icl_get_batch_input(icl_model* m, int head, float* host_BD);         /* concat input of head [B,D0] */
+/* Affinity layer 1 runs factorised when a batch repeats mentions and boxes (z1 = U[mention] + V[box] + b1; the concat it
+   replaces: nn_utils/core.py:421-433,439): factorised / distinct mentions / distinct boxes of the resident batch, totals[3] over all
+   uploads = {batches factorised, their distinct mentions, their distinct boxes}.  ICL_AFF_FACTOR=0 disables, =2 forces it. */
+int icl_head_factor_stats(icl_model* m, int head, int32_t* factorised, int32_t* n_mentions, int32_t* n_boxes, int64_t* totals);
 int icl_get_activation(icl_model* m, int head, int layer, float* host_BW);  /* hidden layer output (post-dropout) [B,w] */
 int icl_rec_trace(icl_model* m, int cta, long long* host);               /* bring-up trace of one persistent-kernel CTA */
 int icl_debug_mask(icl_model* m, uint64_t seed, uint32_t stream, int64_t first_idx, int64_t n, float keep, float* host);
