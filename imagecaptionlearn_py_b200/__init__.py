@@ -1,3 +1,12 @@
 """B200-native (sm_100a) BiLSTM caption encoder + mention-span heads: drop-in for the neural hot path of
 cmcervantes/ImageCaptionLearn_py (`nn_utils/core.py` + `nn_utils/data.py:load_batch`)."""
 __version__ = "0.1.0"
+
+import os as _os
+
+# The step runs on a dozen CUDA streams (the heads of a multi-head model each have a chain and a weight-gradient stream, the box half of
+# a factorised affinity layer, the side streams of the recurrences, the copy stream).  The driver maps streams onto
+# CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8) and streams that share a queue serialise: measured on the five-head
+# multitask config 1.47 -> 1.39 ms per step with 32 queues.  Read by the driver when the CUDA context is created, so it has to be in
+# the environment before the first CUDA call of the process: import this package first (the drop-in scripts do).
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")

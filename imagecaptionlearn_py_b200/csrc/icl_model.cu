@@ -201,6 +201,7 @@ struct icl_model {
   cudaEvent_t ev_side = nullptr, ev_loss = nullptr; bool loss_pending = false;   // loss / accuracy sums run beside the backward pass
   cudaEvent_t ev_hfork = nullptr;      // multi-head models: the point of the model's stream every head stream starts from
   float last_keep = 1.0f; uint64_t last_seed = 0;      // of the last icl_run_resident (icl_get_batch_input of a factorised head)
+  cudaEvent_t ev_zfork = nullptr, ev_zero = nullptr; bool zero_pending = false; int zero_early = 1;   // ICL_ZERO_EARLY=0: A/B
   bool pdl = true;                     // ICL_PDL=0: the heads' GEMM chains without programmatic dependent launches (A/B)
   bool head_streams = true;            // ICL_HEAD_STREAMS=0: the heads of a multi-head model one after another on the model's stream (A/B)
   // fused BPTT step kernel (lstm_bptt.cuh): default backward recurrence in tensor-core mode
@@ -777,7 +778,7 @@ extern "C" void icl_destroy(icl_model* m) {
   if (m->aux) cudaStreamDestroy(m->aux);
   if (m->aux2) cudaStreamDestroy(m->aux2);
   if (m->aux3) cudaStreamDestroy(m->aux3);
-  for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_join2, m->ev_t0, m->ev_t1, m->ev_heads, m->ev_wg0, m->ev_packs, m->ev_side, m->ev_loss, m->ev_hfork}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_join2, m->ev_t0, m->ev_t1, m->ev_heads, m->ev_wg0, m->ev_packs, m->ev_side, m->ev_loss, m->ev_hfork, m->ev_zfork, m->ev_zero}) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : m->ev_dz) if (e) cudaEventDestroy(e);
   for (int i = 0; i < PH_N; i++) for (int j = 0; j < 2; j++) if (m->ev_ph[i][j]) cudaEventDestroy(m->ev_ph[i][j]);
   delete m;
@@ -932,6 +933,7 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   CKD(dmalloc(&m->d_partial, 1024)); CKD(dmalloc(&m->d_gnorm, 4));
   if (const char* e = getenv("ICL_HEAD_STREAMS")) m->head_streams = atoi(e) != 0;
   if (const char* e = getenv("ICL_PDL")) m->pdl = atoi(e) != 0;
+  if (const char* e = getenv("ICL_ZERO_EARLY")) m->zero_early = atoi(e);
   for (auto& h : m->heads) {
     int B = h.c.batch_size, C = h.c.n_classes;
     int maxw = 0;
@@ -974,6 +976,8 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   CKD(cudaEventCreateWithFlags(&m->ev_side, cudaEventDisableTiming));
   CKD(cudaEventCreateWithFlags(&m->ev_loss, cudaEventDisableTiming));
   CKD(cudaEventCreateWithFlags(&m->ev_hfork, cudaEventDisableTiming));
+  CKD(cudaEventCreateWithFlags(&m->ev_zfork, cudaEventDisableTiming));
+  CKD(cudaEventCreateWithFlags(&m->ev_zero, cudaEventDisableTiming));
   for (auto& e : m->ev_dz) CKD(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CKD(cudaEventCreate(&m->ev_t0)); CKD(cudaEventCreate(&m->ev_t1));
   for (int i = 0; i < PH_N; i++) for (int j = 0; j < 2; j++) CKD(cudaEventCreate(&m->ev_ph[i][j]));
@@ -1556,6 +1560,7 @@ static int rec_forward_persistent(icl_model* m, int training) {
 }
 
 static int heads_prefetch(icl_model* m);
+static int zero_backward_early(icl_model* m);
 static int lstm_forward(icl_model* m, float keep_in, uint64_t seed, int training) {
   int E = m->E, H = m->H;
   long Ntok = m->Ntok, NP = m->NtokP;
@@ -1590,6 +1595,7 @@ static int lstm_forward(icl_model* m, float keep_in, uint64_t seed, int training
   }
   PH_END(m, PH_PROJ);
   CKI(heads_prefetch(m));      // box halves of factorised affinity heads: beside the recurrence (which leaves SMs idle), not beside K1
+  if (training && m->zero_early == 1) CKI(zero_backward_early(m));
   // K2: the recurrence
   PH_BEGIN(m, PH_REC_FWD);
   if (rec_usable(m)) {
@@ -1713,6 +1719,23 @@ static int colsum(icl_model* m, cudaStream_t st, const float* X, long rows, int 
   return 0;
 }
 
+static int zero_backward_buffers(icl_model* m, cudaStream_t st) {
+  const int H = m->H;
+  CK(zero_multi_async({{m->dHout[0], (size_t)m->NtokP * H * 4}, {m->dHout[1], (size_t)m->NtokP * H * 4}, {m->G, (size_t)m->n_params * 4},
+                       {m->dcc[0], (size_t)m->S * H * 4}, {m->dcc[1], (size_t)m->S * H * 4}}, st));
+  LAUNCHED(m);
+  return 0;
+}
+// Nothing touches the backward pass's accumulators before heads_backward: a training step clears them on a side stream while the
+// forward pass runs (ICL_ZERO_EARLY: 1 = beside the recurrence, 2 = beside the heads' forward chain, 0 = in front of heads_backward)
+static int zero_backward_early(icl_model* m) {
+  CK(cudaEventRecord(m->ev_zfork, m->stream));
+  CK(cudaStreamWaitEvent(m->aux3, m->ev_zfork, 0));
+  CKI(zero_backward_buffers(m, m->aux3));
+  CK(cudaEventRecord(m->ev_zero, m->aux3));
+  m->zero_pending = true;
+  return 0;
+}
 static int heads_backward(icl_model* m, float keep, uint64_t seed) {
   const cudaStream_t st0 = m->stream;
   int H = m->H;
@@ -1723,9 +1746,9 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
   // ONE launch clears everything the backward pass accumulates into: dHout of both directions (span scatter), the WHOLE flat
   // gradient buffer (split-K weight gradients and bias column sums of every head and of the LSTM add into it; heads that are not
   // fed keep a zero gradient) and the dc carry of the BPTT
-  CK(zero_multi_async({{m->dHout[0], (size_t)m->NtokP * H * 4}, {m->dHout[1], (size_t)m->NtokP * H * 4}, {m->G, (size_t)m->n_params * 4},
-                       {m->dcc[0], (size_t)m->S * H * 4}, {m->dcc[1], (size_t)m->S * H * 4}}, st0));
-  LAUNCHED(m);
+  // -- issued at the START of a training step on a side stream (zero_backward_buffers): 70 MB of fills beside the forward pass
+  if (m->zero_pending) { CK(cudaStreamWaitEvent(st0, m->ev_zero, 0)); m->zero_pending = false; }
+  else CKI(zero_backward_buffers(m, st0));
   if (fork) CK(cudaEventRecord(m->ev_hfork, st0));
   for (size_t hi = 0; hi < m->heads.size(); hi++) {
     Head& h = m->heads[hi];
@@ -2161,6 +2184,7 @@ extern "C" int icl_run_resident(icl_model* m, int op, float keep_in, float keep,
   CKI(refresh_rounded_params(m));
   m->last_keep = keep; m->last_seed = seed;
   CKI(lstm_forward(m, keep_in, seed, op >= ICL_OP_GRADS));
+  if (op >= ICL_OP_GRADS && m->zero_early == 2) CKI(zero_backward_early(m));
   CKI(heads_forward(m, keep, seed));
   if (op >= ICL_OP_GRADS) {
     CKI(heads_backward(m, keep, seed));

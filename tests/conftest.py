@@ -3,6 +3,7 @@ import sys
 
 import pytest
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")      # see imagecaptionlearn_py_b200/__init__.py
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
