@@ -169,7 +169,7 @@ struct icl_model {
   cudaEvent_t ev_dz[ICL_MAX_LAYERS + 2] = {};   // heads' backward: "dz of this layer is ready" (main stream -> aux stream)
   bool heads_aux_pending = false;      // the aux stream holds weight-gradient work the main stream has not joined yet
   cudaEvent_t ev_ph[PH_N][2] = {};
-  bool ph_used[PH_N] = {};
+  bool ph_used[PH_N] = {}, ph_on = false;      // per-phase timers: off unless asked for (icl_set_phase_timing / ICL_PHASE_EVENTS=1)
   // persistent recurrent kernels
   int rp_U = 0, rp_nsl = 0, rp_nkb = 0, rp_max_tiles = 0;   // rp_U == 0: not available for this H (per-step path)
   bool rp_on = true, wp_dirty = true;
@@ -217,7 +217,7 @@ struct icl_model {
 #endif
   int n_sms = 148;
   int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
-  float last_ms = 0.f;
+  float last_ms = 0.f; bool t_recorded = false;
   TmaCache tma;
 };
 
@@ -933,6 +933,7 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   CKD(dmalloc(&m->d_partial, 1024)); CKD(dmalloc(&m->d_gnorm, 4));
   if (const char* e = getenv("ICL_HEAD_STREAMS")) m->head_streams = atoi(e) != 0;
   if (const char* e = getenv("ICL_PDL")) m->pdl = atoi(e) != 0;
+  if (const char* e = getenv("ICL_PHASE_EVENTS")) m->ph_on = atoi(e) != 0;
   if (const char* e = getenv("ICL_ZERO_EARLY")) m->zero_early = atoi(e);
   for (auto& h : m->heads) {
     int B = h.c.batch_size, C = h.c.n_classes;
@@ -1174,6 +1175,7 @@ extern "C" int icl_batch_stats(icl_model* m, int64_t* n_seqs, int64_t* n_tokens,
   *n_seqs = m->S; *n_tokens = m->Ntok; *t_max = m->Tmax; return 0;
 }
 // device time of each phase of the last icl_run_resident (ms; 0 where the phase did not run).  Synchronises the stream.
+extern "C" int icl_set_phase_timing(icl_model* m, int on) { m->ph_on = on != 0; return 0; }
 extern "C" int icl_phase_ms(icl_model* m, float* ms) {
   CK(cudaStreamSynchronize(m->stream));
   for (int i = 0; i < PH_N; i++) {
@@ -1252,7 +1254,7 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
   if (!by_rows && b->sent_dtype != ICL_F32 && b->sent_dtype != ICL_F64) return fail("icl_upload: sentences must be float32/float64");
   // pack + convert on several host threads, in chunks, so the H2D copy of chunk i overlaps the packing of chunk i+1
   cudaStream_t st = m->copy;
-  CK(cudaEventRecord(I.ev_c0, st));
+  if (m->ph_on) CK(cudaEventRecord(I.ev_c0, st));
   m->use_rows = by_rows;
   // half-width wire (see cvt_f32_h16_stream): only where the device would round these rows to 10 mantissa bits next anyway (product
   // mode with the fp16 projection operands) and no l2-normalisation sits in between (its sum of squares keeps the fp32 inputs)
@@ -1429,8 +1431,11 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
 
 // ----------------------------------------------------------------------------- forward / backward on resident data
 #define LAUNCHED(m) do { (m)->launches++; CK(cudaGetLastError()); } while (0)
-#define PH_BEGIN(m, ph) do { CK(cudaEventRecord((m)->ev_ph[ph][0], (m)->stream)); } while (0)
-#define PH_END(m, ph) do { CK(cudaEventRecord((m)->ev_ph[ph][1], (m)->stream)); (m)->ph_used[ph] = true; } while (0)
+// per-phase CUDA-event timers (icl_phase_ms): sixteen timing-event records per step.  A timing event is a serialisation point of
+// the stream -- measured: card2048 1.295 -> 1.245 ms per step, nonvis512 0.845 -> 0.802 without them -- so they are only recorded
+// when a caller asks for phase times (icl_set_phase_timing; bench.py takes them in a separate pass from the headline number)
+#define PH_BEGIN(m, ph) do { if ((m)->ph_on) CK(cudaEventRecord((m)->ev_ph[ph][0], (m)->stream)); } while (0)
+#define PH_END(m, ph) do { if ((m)->ph_on) { CK(cudaEventRecord((m)->ev_ph[ph][1], (m)->stream)); (m)->ph_used[ph] = true; } } while (0)
 
 static StepLayout mk_layout(icl_model* m) { StepLayout L; L.off = m->d_off; L.nact = m->d_nact; L.rank = m->d_rank; L.lens = m->d_lens; return L; }
 static const float* wbase(icl_model* m) { return m->round_ops ? m->Pr : m->P; }   // GEMM-operand view of the parameters
@@ -2179,8 +2184,11 @@ extern "C" int icl_run_resident(icl_model* m, int op, float keep_in, float keep,
   for (int i = 0; i < PH_N; i++) m->ph_used[i] = false;
   InSet& I = m->in[m->cur];
   CK(cudaStreamWaitEvent(m->stream, I.ev_copied, 0));          // the batch's H2D copies (copy stream) have landed
-  CK(cudaEventRecord(I.ev_s0, m->stream));
-  CK(cudaEventRecord(m->ev_t0, m->stream));
+  if (m->ph_on) {                                              // timing events (icl_last_step_ms, icl_debug_timeline): see PH_BEGIN
+    CK(cudaEventRecord(I.ev_s0, m->stream));
+    CK(cudaEventRecord(m->ev_t0, m->stream));
+  }
+  m->t_recorded = m->ph_on;
   CKI(refresh_rounded_params(m));
   m->last_keep = keep; m->last_seed = seed;
   CKI(lstm_forward(m, keep_in, seed, op >= ICL_OP_GRADS));
@@ -2193,7 +2201,7 @@ extern "C" int icl_run_resident(icl_model* m, int op, float keep_in, float keep,
   }
   if (op == ICL_OP_TRAIN) CKI(icl_apply_update(m));
   if (m->loss_pending) { CK(cudaStreamWaitEvent(m->stream, m->ev_loss, 0)); m->loss_pending = false; }
-  CK(cudaEventRecord(m->ev_t1, m->stream));
+  if (m->ph_on) CK(cudaEventRecord(m->ev_t1, m->stream));
   CK(cudaEventRecord(I.ev_done, m->stream));                   // this set's device buffers may be overwritten after this point
   I.done_pending = true;
   return 0;
@@ -2254,7 +2262,7 @@ extern "C" int icl_fetch(icl_model* m, icl_head_out* out) {
     m->d2h_bytes += (int64_t)B * C * 4 + 8 + (int64_t)B * 8;
   }
   CK(cudaStreamSynchronize(st));
-  cudaEventElapsedTime(&m->last_ms, m->ev_t0, m->ev_t1);
+  if (m->t_recorded) cudaEventElapsedTime(&m->last_ms, m->ev_t0, m->ev_t1); else m->last_ms = NAN;
   for (size_t hi = 0; hi < m->heads.size() && out; hi++) {
     Head& h = m->heads[hi];
     int B = h.c.batch_size, C = h.c.n_classes;

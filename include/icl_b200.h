@@ -188,8 +188,9 @@ int icl_debug_mask(icl_model* m, uint64_t seed, uint32_t stream, int64_t first_i
 int icl_gemm(icl_model* m, int mode, int a_mn_major, int b_mn_major, int M, int N, int K,
              const float* A, const float* B, float* C, int splits);     /* C[M,N] = A*B on the device (validation) */
 int icl_kernel_launches(icl_model* m, int64_t* n);                       /* launches since create */
-int icl_last_step_ms(icl_model* m, float* ms);                           /* device time of last run_resident */
+int icl_last_step_ms(icl_model* m, float* ms);                           /* device time of last run_resident (NaN unless icl_set_phase_timing is on) */
 #define ICL_N_PHASES 8   /* prep, input-projection GEMM, recurrence fwd, heads fwd, heads bwd, BPTT, weight grads, clip+Adam */
+int icl_set_phase_timing(icl_model* m, int on);                          /* record the per-phase timing events (off by default: they serialise the stream, ~50 us per step) */
 int icl_phase_ms(icl_model* m, float* ms /*[ICL_N_PHASES]*/);            /* per-phase device time of the last run_resident */
 int icl_copy_bytes(icl_model* m, int64_t* h2d, int64_t* d2h);            /* bytes copied by the last upload / fetch */
 /* the host conversion icl_upload applies to sentence rows (run_op's float64 -> float32 feed conversion, core.py:558-561), exposed

@@ -22,7 +22,7 @@ def main():
     ctx.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for name in names or list(bench.BY_CONFIG):
         r = bench.measure(name, steps, 5, ctx)
-        print(json.dumps(dict(workload=name, ms_per_step=round(r["ms_per_step"], 4), b2b_ms=round(r["b2b_ms"], 4),
+        print(json.dumps(dict(workload=name, ms_per_step=round(r["ms_per_step"], 4), b2b_ms=round(r["b2b_ms"], 4), with_phase_timers_ms=round(r["ph_step_ms"], 4),
                               e2e_ms=round(r["e2e"]["ms_per_step"], 4), launches_per_step=r["launches"] / steps,
                               phases_ms={n: round(float(v), 4) for n, v in zip(_cabi.PHASES, r["ph_ms"])})), flush=True)
 

@@ -1,4 +1,6 @@
 """Bring-up: host timeline of the pipelined train step (upload / enqueue / poll) and raw pinned H2D bandwidth."""
+import os
+os.environ.setdefault('ICL_PHASE_EVENTS', '1')      # these tools read icl_phase_ms
 import ctypes as C, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

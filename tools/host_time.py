@@ -1,4 +1,6 @@
 """Bring-up: host issue time vs device time of one resident train step; e2e breakdown (upload / run / fetch)."""
+import os
+os.environ.setdefault('ICL_PHASE_EVENTS', '1')
 import ctypes as C, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,4 +1,6 @@
 """rec_fwd phase time of card2048 in predict mode (no gate / c stores) vs training mode, per K2 slicing."""
+import os
+os.environ.setdefault('ICL_PHASE_EVENTS', '1')      # these tools read icl_phase_ms
 import ctypes as C, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,4 +1,6 @@
 """Bring-up: per-step timeline of one CTA of k_bptt_nsplit (ICL_BPTT_NSPLIT=0: k_bptt_cluster) on the card2048 bench batch (clock64 events of cell warp 0)."""
+import os
+os.environ.setdefault('ICL_PHASE_EVENTS', '1')      # these tools read icl_phase_ms
 import ctypes as C, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

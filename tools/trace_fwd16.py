@@ -1,4 +1,6 @@
 """Bring-up: per-(step, tile) timeline of one CTA of k_rec_fwd16 on the card2048 bench batch (clock64 events of its four roles)."""
+import os
+os.environ.setdefault('ICL_PHASE_EVENTS', '1')      # these tools read icl_phase_ms
 import ctypes as C, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,4 +1,6 @@
 """Bring-up: run the card2048 bench batch once with the persistent-kernel trace on and print a per-(step,tile) timeline."""
+import os
+os.environ.setdefault('ICL_PHASE_EVENTS', '1')      # these tools read icl_phase_ms
 import ctypes as C, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
