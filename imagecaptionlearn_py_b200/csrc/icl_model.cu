@@ -11,6 +11,7 @@
 #include "lstm_fwd16.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -294,9 +295,13 @@ static void to_f32(float* dst, const void* src, int dtype, size_t n) {
 }
 
 // Host worker pool for the batch marshalling (pack / convert sentences into pinned memory).  Threads are created once
-// per process: spawning them per call costs more than the 30 MB copy they parallelise.  FOUR threads by default
-// (ICL_HOST_THREADS): packing overlaps the previous step's kernels, and with 16 threads saturating host DRAM the GPU's
-// command fetches over PCIe slowed so much that a 1.77 ms step stretched to 3.0 ms (2 threads: 1.85, 4: 2.0, 8: 2.1-2.4).
+// per process: spawning them per call costs more than the 30 MB copy they parallelise.  How many of them pack is MEASURED, not
+// assumed: the pool holds up to 12 threads (the host cores split between the ranks of the box, one left to the thread that drives
+// the GPU) and the first large uploads of a process time the packing with 4 / 6 / 8 / 12 of them active and keep the fastest
+// (ICL_HOST_THREADS fixes the number instead).  Why not simply "all": packing overlaps the previous step's kernels, and threads that
+// saturate host DRAM slow the GPU's own command fetches over PCIe (round 1: 16 threads stretched a 1.77 ms step to 3.0 ms; round 2,
+// 16-core single-GPU box, fp16 wire + non-temporal stores: e2e 1.97 / 1.47 / 1.29 / 1.29 / 1.29 / 1.45 ms per step with
+// 2 / 4 / 6 / 8 / 12 / 16 threads), and on an 8-GPU box eight ranks share one memory system.
 struct HostPool {
   std::vector<std::thread> th;
   std::mutex mu;
@@ -304,15 +309,44 @@ struct HostPool {
   std::function<void(int)> job;
   int n_items = 0, busy = 0;
   std::atomic<int> next{0};
+  std::atomic<int> active{1};        // threads that take items, the caller included
   uint64_t gen = 0;
   bool stop = false;
+  // tuner: candidate thread counts, best time seen for each, uploads measured so far
+  std::vector<int> cand; std::vector<double> best; int trials = 0; bool tuned = false;
+  static constexpr int TRIALS_PER = 4, WARM = 2;
   HostPool() {
     unsigned share = std::thread::hardware_concurrency();            // one process per GPU: split the host cores between the ranks
     if (const char* e = getenv("LOCAL_WORLD_SIZE")) share /= (unsigned)std::max(1, atoi(e));
     if (share > 2) share -= 1;                                       // leave a core per rank to the thread that drives the GPU
-    int n = (int)std::max(1u, std::min(4u, share)) - 1;
-    if (const char* e = getenv("ICL_HOST_THREADS")) n = std::max(0, atoi(e) - 1);
-    for (int i = 0; i < n; i++) th.emplace_back([this] { worker(); });
+    int cap = (int)std::max(1u, std::min(12u, share));
+    if (const char* e = getenv("ICL_HOST_THREADS")) { cap = std::max(1, atoi(e)); tuned = true; }
+    active = tuned ? cap : std::min(cap, 4);
+    if (!tuned) {
+      for (int c : {4, 6, 8, 12}) if (c <= cap) cand.push_back(c);
+      if (cand.size() < 2) tuned = true;
+      best.assign(cand.size(), 1e30);
+    }
+    for (int i = 1; i < cap; i++) th.emplace_back([this, i] { worker(i); });
+  }
+  // one large packing pass took `ms` with the current number of active threads: next candidate, or settle on the fastest
+  void report(double ms) {
+    if (tuned) return;
+    const int t = trials++ - WARM;
+    if (t < 0) return;
+    const size_t c = (size_t)t / TRIALS_PER;
+    if (c < cand.size()) best[c] = std::min(best[c], ms);
+    const size_t nc = (size_t)(t + 1) / TRIALS_PER;
+    if (nc < cand.size()) { active = cand[nc]; return; }
+    size_t arg = 0;
+    for (size_t i = 1; i < cand.size(); i++) if (best[i] < 0.97 * best[arg]) arg = i;      // more threads only for a clear gain
+    active = cand[arg];
+    tuned = true;
+    if (getenv("ICL_HOST_THREADS_VERBOSE")) {
+      fprintf(stderr, "icl_b200: host packing threads:");
+      for (size_t i = 0; i < cand.size(); i++) fprintf(stderr, " %d -> %.3f ms", cand[i], best[i]);
+      fprintf(stderr, "; using %d\n", active.load());
+    }
   }
   ~HostPool() {
     { std::lock_guard<std::mutex> l(mu); stop = true; }
@@ -320,7 +354,7 @@ struct HostPool {
     for (auto& t : th) t.join();
   }
   void drain() { for (int i; (i = next.fetch_add(1)) < n_items;) job(i); }
-  void worker() {
+  void worker(int id) {
     uint64_t seen = 0;
     for (;;) {
       {
@@ -328,6 +362,7 @@ struct HostPool {
         cv.wait(l, [&] { return stop || gen != seen; });
         if (stop) return;
         seen = gen;
+        if (id >= active.load()) continue;          // not among the threads that pack (see report())
         busy++;
       }
       drain();
@@ -391,7 +426,7 @@ static void csr_lists(int B, int G, const int* of, int* start, int* mem) {
   std::vector<int> fill(start, start + G);
   for (int r = 0; r < B; r++) mem[fill[of[r]]++] = r;           // pair order inside a group: the order the segment sums add in
 }
-static size_t dtype_size(int dt) { return dt == ICL_F64 ? 8 : 4; }
+static size_t dtype_size(int dt) { return (dt == ICL_F64 || dt == ICL_I64) ? 8 : 4; }
 
 static void slot_plan(const icl_head_config& c, std::vector<int>& kinds /*index id or -1..-3*/) {
   // nn_utils/core.py:377-433.  -1 feats, -2 box, -3 bfeats
@@ -1271,6 +1306,7 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
       }
   } else {
     const int n_chunks = ntok * (long)E * 4 > (4 << 20) ? 8 : 1;
+    const auto t_pack0 = std::chrono::steady_clock::now();
     int s0 = 0;
     for (int c = 0; c < n_chunks; c++) {
       const long tok_end = ntok * (c + 1) / n_chunks;
@@ -1297,6 +1333,8 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
       }
       s0 = s1;
     }
+    if (n_chunks > 1)       // a large packing pass: one sample for the pool's thread-count tuner
+      host_pool().report(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_pack0).count());
   }
   std::vector<std::pair<size_t, size_t>> holes;          // byte ranges of the meta region nothing on the device will read
   for (int hi = 0; hi < b->n_heads; hi++) {
@@ -1323,8 +1361,14 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
     auto up = [&](const void* src, int dt, size_t off, size_t n, const char* what) -> int {
       if (n == 0) return 0;
       if (!src) return fail("icl_upload: head %d is missing %s", hi, what);
-      to_f32(I.host<float>(off), src, dt, n);
-      if (g_pack_nt) _mm_sfence();
+      float* dst = I.host<float>(off);
+      if (n < (64u << 10)) { to_f32(dst, src, dt, n); if (g_pack_nt) _mm_sfence(); return 0; }
+      const size_t per = 16u << 10, esz_ = dtype_size(dt);          // large blocks (m_feats of 2048 examples: 4 MB of float64): on the pool
+      host_pool().run((int)((n + per - 1) / per), [&](int it) {
+        const size_t a = (size_t)it * per, c = std::min(n, a + per);
+        to_f32(dst + a, (const char*)src + a * esz_, dt, c - a);
+        if (g_pack_nt) _mm_sfence();
+      });
       return 0;
     };
     CKI(up(hb.feats, hb.feats_dtype, hin.feats, (size_t)B * h.c.n_feats, "m_feats/ij_feats"));
@@ -1371,10 +1415,21 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
           key[r] = k;
         }
       });
-      group_rows(B, key, [&](int a, int c) {
+      auto same_box = [&](int a, int c) {
         if (box_table_rows ? hb.box_rows[a] != hb.box_rows[c] : memcmp(xsrc + a * xsz, xsrc + c * xsz, xsz) != 0) return false;
         return bsz == 0 || memcmp(bsrc + a * bsz, bsrc + c * bsz, bsz) == 0;
-      }, b_of, rep_b);
+      };
+      // host rows: group by the sampled hash alone, then compare every row with its group's first row IN PARALLEL (8 MB of memcmp
+      // per 512 pairs); only if two different rows shared a hash (never seen) is the grouping redone with the exact test inside
+      group_rows(B, key, [&](int a, int c) { return box_table_rows ? same_box(a, c) : true; }, b_of, rep_b);
+      if (!box_table_rows) {
+        std::atomic<int> mismatch{0};
+        host_pool().run((B + 15) / 16, [&](int it) {
+          for (int r = it * 16; r < std::min(B, (it + 1) * 16); r++)
+            if (rep_b[b_of[r]] != r && !same_box(r, rep_b[b_of[r]])) mismatch++;
+        });
+        if (mismatch.load()) group_rows(B, key, same_box, b_of, rep_b);
+      }
       h.Mu = (int)rep_m.size(); h.Nu = (int)rep_b.size();
       // reference-shaped TRAINING batches carry one copy of the caption per pair (nn_utils/data.py:397-403: every copy draws its own
       // dropout masks), so their mentions do not repeat and only the box half (4096 of the 5552 columns) collapses; prediction
