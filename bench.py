@@ -654,7 +654,7 @@ def main():
         traffic = None
         try:       # DRAM bytes of the dominant kernel from the committed `ncu --set full` capture of this workload (profiles/)
             if args.workload == "card2048":
-                for fn in ("r2_ncu_full_summary.json", "r2a_ncu_recurrences.json", "r1h_ncu_full_summary.json"):
+                for fn in ("r2f_ncu_recurrences.json", "r2_ncu_full_summary.json", "r2a_ncu_recurrences.json", "r1h_ncu_full_summary.json"):
                     path = os.path.join(ROOT, "profiles", fn)
                     if os.path.exists(path):
                         ents = json.load(open(path))

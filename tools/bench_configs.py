@@ -13,8 +13,8 @@ def main():
     import torch
     import bench
     from imagecaptionlearn_py_b200 import _cabi
-    names = [a for a in sys.argv[1:] if not a.startswith("--")]
     steps = int(sys.argv[sys.argv.index("--steps") + 1]) if "--steps" in sys.argv else 20
+    names = [a for i, a in enumerate(sys.argv[1:], 1) if not a.startswith("--") and sys.argv[i - 1] != "--steps"]
     ctx = bench.Ctx()
     ctx.rank, ctx.world, ctx.local, ctx.dist = 0, 1, 0, None
     torch.cuda.set_device(0)
