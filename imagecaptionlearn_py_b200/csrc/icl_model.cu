@@ -202,7 +202,7 @@ struct icl_model {
   cudaEvent_t ev_side = nullptr, ev_loss = nullptr; bool loss_pending = false;   // loss / accuracy sums run beside the backward pass
   cudaEvent_t ev_hfork = nullptr;      // multi-head models: the point of the model's stream every head stream starts from
   float last_keep = 1.0f; uint64_t last_seed = 0;      // of the last icl_run_resident (icl_get_batch_input of a factorised head)
-  cudaEvent_t ev_zfork = nullptr, ev_zero = nullptr; bool zero_pending = false; int zero_early = 1;   // ICL_ZERO_EARLY=0: A/B
+  cudaEvent_t ev_zfork = nullptr, ev_zero = nullptr; bool zero_pending = false, dh_clean = false; int zero_early = 1, zero_blocks = 0; cudaEvent_t ev_dhzero = nullptr;   // ICL_ZERO_EARLY=0: A/B
   bool pdl = true;                     // ICL_PDL=0: the heads' GEMM chains without programmatic dependent launches (A/B)
   bool head_streams = true;            // ICL_HEAD_STREAMS=0: the heads of a multi-head model one after another on the model's stream (A/B)
   // fused BPTT step kernel (lstm_bptt.cuh): default backward recurrence in tensor-core mode
@@ -484,18 +484,21 @@ __global__ void k_zero_multi(const ZeroRanges r) {
   if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
     uint4* p4 = reinterpret_cast<uint4*>(p);
     const size_t n4 = n_words >> 2;
-    for (size_t i = i0; i < n4; i += stride) p4[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (size_t i = i0; i < n4; i += stride) __stcs(p4 + i, make_uint4(0u, 0u, 0u, 0u));      // streaming: the zeros are read once, much later
     for (size_t i = (n4 << 2) + i0; i < n_words; i += stride) p[i] = 0u;
   } else {
     for (size_t i = i0; i < n_words; i += stride) p[i] = 0u;
   }
 }
-static cudaError_t zero_multi_async(std::initializer_list<std::pair<void*, size_t>> ranges, cudaStream_t st) {
+// max_blocks > 0: a deliberately NARROW launch (that many CTAs in all) for fills that run beside a latency-bound persistent kernel:
+// they then live on the SMs that kernel leaves idle instead of taking issue slots and L2 from it
+static cudaError_t zero_multi_async(std::initializer_list<std::pair<void*, size_t>> ranges, cudaStream_t st, int max_blocks = 0) {
   ZeroRanges r; int n = 0; size_t mx = 0;
   for (auto& pr : ranges) if (pr.second) { r.p[n] = reinterpret_cast<uint32_t*>(pr.first); r.n[n] = pr.second / 4; mx = std::max(mx, r.n[n]); n++; }
   if (n == 0) return cudaSuccess;
-  const unsigned blocks = (unsigned)std::min<size_t>(296, (mx / 4 + 255) / 256 + 1);
-  k_zero_multi<<<dim3(blocks, n), 256, 0, st>>>(r);
+  unsigned blocks = (unsigned)std::min<size_t>(296, (mx / 4 + 255) / 256 + 1);
+  if (max_blocks > 0) blocks = std::max(1u, std::min(blocks, (unsigned)max_blocks / (unsigned)n));
+  k_zero_multi<<<dim3(blocks, n), max_blocks > 0 ? 512 : 256, 0, st>>>(r);
   return cudaGetLastError();
 }
 __global__ void k_fill_u16(uint16_t* __restrict__ p, size_t n, uint16_t v) {
@@ -813,7 +816,7 @@ extern "C" void icl_destroy(icl_model* m) {
   if (m->aux) cudaStreamDestroy(m->aux);
   if (m->aux2) cudaStreamDestroy(m->aux2);
   if (m->aux3) cudaStreamDestroy(m->aux3);
-  for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_join2, m->ev_t0, m->ev_t1, m->ev_heads, m->ev_wg0, m->ev_packs, m->ev_side, m->ev_loss, m->ev_hfork, m->ev_zfork, m->ev_zero}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_join2, m->ev_t0, m->ev_t1, m->ev_heads, m->ev_wg0, m->ev_packs, m->ev_side, m->ev_loss, m->ev_hfork, m->ev_zfork, m->ev_zero, m->ev_dhzero}) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : m->ev_dz) if (e) cudaEventDestroy(e);
   for (int i = 0; i < PH_N; i++) for (int j = 0; j < 2; j++) if (m->ev_ph[i][j]) cudaEventDestroy(m->ev_ph[i][j]);
   delete m;
@@ -970,6 +973,7 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   if (const char* e = getenv("ICL_PDL")) m->pdl = atoi(e) != 0;
   if (const char* e = getenv("ICL_PHASE_EVENTS")) m->ph_on = atoi(e) != 0;
   if (const char* e = getenv("ICL_ZERO_EARLY")) m->zero_early = atoi(e);
+  if (const char* e = getenv("ICL_ZERO_BLOCKS")) m->zero_blocks = atoi(e);
   for (auto& h : m->heads) {
     int B = h.c.batch_size, C = h.c.n_classes;
     int maxw = 0;
@@ -1014,6 +1018,7 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   CKD(cudaEventCreateWithFlags(&m->ev_hfork, cudaEventDisableTiming));
   CKD(cudaEventCreateWithFlags(&m->ev_zfork, cudaEventDisableTiming));
   CKD(cudaEventCreateWithFlags(&m->ev_zero, cudaEventDisableTiming));
+  CKD(cudaEventCreateWithFlags(&m->ev_dhzero, cudaEventDisableTiming));
   for (auto& e : m->ev_dz) CKD(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CKD(cudaEventCreate(&m->ev_t0)); CKD(cudaEventCreate(&m->ev_t1));
   for (int i = 0; i < PH_N; i++) for (int j = 0; j < 2; j++) CKD(cudaEventCreate(&m->ev_ph[i][j]));
@@ -1655,7 +1660,7 @@ static int lstm_forward(icl_model* m, float keep_in, uint64_t seed, int training
   }
   PH_END(m, PH_PROJ);
   CKI(heads_prefetch(m));      // box halves of factorised affinity heads: beside the recurrence (which leaves SMs idle), not beside K1
-  if (training && m->zero_early == 1) CKI(zero_backward_early(m));
+  if (training && (m->zero_early == 1 || m->zero_early == 3)) CKI(zero_backward_early(m));
   // K2: the recurrence
   PH_BEGIN(m, PH_REC_FWD);
   if (rec_usable(m)) {
@@ -1779,10 +1784,15 @@ static int colsum(icl_model* m, cudaStream_t st, const float* X, long rows, int 
   return 0;
 }
 
-static int zero_backward_buffers(icl_model* m, cudaStream_t st) {
+// which: 1 = the flat gradient buffer, 2 = dHout of both directions + the dc carry, 3 = both
+static int zero_backward_buffers(icl_model* m, cudaStream_t st, int max_blocks = 0, int which = 3) {
   const int H = m->H;
-  CK(zero_multi_async({{m->dHout[0], (size_t)m->NtokP * H * 4}, {m->dHout[1], (size_t)m->NtokP * H * 4}, {m->G, (size_t)m->n_params * 4},
-                       {m->dcc[0], (size_t)m->S * H * 4}, {m->dcc[1], (size_t)m->S * H * 4}}, st));
+  const size_t dh = (which & 2) ? (size_t)m->NtokP * H * 4 : 0, dc = (which & 2) ? (size_t)m->S * H * 4 : 0, g = (which & 1) ? (size_t)m->n_params * 4 : 0;
+  if (dh + dc + g == 0) return 0;
+  // narrow side-stream fills (max_blocks < 0 = sized here): a 512-thread CTA clears ~14 GB/s; enough of them to be done in ~100 us,
+  // i.e. inside the kernel they run beside (measured: 20 CTAs for the 100 MB of the multitask config took longer than its weight-gradient GEMMs)
+  if (max_blocks < 0) max_blocks = (int)std::min<size_t>(296, std::max<size_t>(20, (2 * dh + 2 * dc + g) / (1400u << 10)));
+  CK(zero_multi_async({{m->dHout[0], dh}, {m->dHout[1], dh}, {m->G, g}, {m->dcc[0], dc}, {m->dcc[1], dc}}, st, max_blocks));
   LAUNCHED(m);
   return 0;
 }
@@ -1791,7 +1801,7 @@ static int zero_backward_buffers(icl_model* m, cudaStream_t st) {
 static int zero_backward_early(icl_model* m) {
   CK(cudaEventRecord(m->ev_zfork, m->stream));
   CK(cudaStreamWaitEvent(m->aux3, m->ev_zfork, 0));
-  CKI(zero_backward_buffers(m, m->aux3));
+  CKI(zero_backward_buffers(m, m->aux3, m->zero_blocks, m->dh_clean ? 1 : 3));
   CK(cudaEventRecord(m->ev_zero, m->aux3));
   m->zero_pending = true;
   return 0;
@@ -1808,7 +1818,8 @@ static int heads_backward(icl_model* m, float keep, uint64_t seed) {
   // fed keep a zero gradient) and the dc carry of the BPTT
   // -- issued at the START of a training step on a side stream (zero_backward_buffers): 70 MB of fills beside the forward pass
   if (m->zero_pending) { CK(cudaStreamWaitEvent(st0, m->ev_zero, 0)); m->zero_pending = false; }
-  else CKI(zero_backward_buffers(m, st0));
+  else CKI(zero_backward_buffers(m, st0, 0, m->dh_clean ? 1 : 3));
+  m->dh_clean = false;        // the span scatters below write dHout; lstm_backward clears it again behind the recurrence
   if (fork) CK(cudaEventRecord(m->ev_hfork, st0));
   for (size_t hi = 0; hi < m->heads.size(); hi++) {
     Head& h = m->heads[hi];
@@ -2138,6 +2149,17 @@ static int lstm_backward(icl_model* m) {
     k_zero_pad_rows<<<dim3(m->Tmax, 2), 256, 0, st>>>(m->Z[0], m->Z[1], mk_layout(m), 4 * H); LAUNCHED(m);
   }
   PH_END(m, PH_REC_BWD);
+  if (m->zero_early == 3) {
+    // ICL_ZERO_EARLY=3 (measured, not the default): dHout and the dc carry are dead once the recurrence has run, so they can be
+    // cleared HERE, beside the tensor-bound weight-gradient GEMMs, for the next step (all rows are zero between steps; whatever
+    // fails before this point leaves dh_clean false and the next backward pass clears them itself), leaving only the flat gradient
+    // buffer to clear beside the next step's recurrence.  card2048 1.240 -> 1.235 ms, but multitask512 (100 MB of fills beside two
+    // short GEMMs) 1.34 -> 1.37-1.40 ms, whatever the width of the fill (20 / 40 / auto / 1480 CTAs).
+    CK(cudaEventRecord(m->ev_zfork, st));
+    CK(cudaStreamWaitEvent(m->aux3, m->ev_zfork, 0));
+    CKI(zero_backward_buffers(m, m->aux3, m->zero_blocks, 2));
+    CK(cudaEventRecord(m->ev_dhzero, m->aux3));
+  }
   // time-batched weight gradients: ONE split-K GEMM per direction (contraction over all tokens)
   CKI(join_heads_aux(m));
   PH_BEGIN(m, PH_WGRAD);
@@ -2152,6 +2174,7 @@ static int lstm_backward(icl_model* m) {
     CKI(gemm(m, st, true, true, gk, -1, splits, /*prezeroed=*/true));
     if (d == 0) CK(cudaEventRecord(m->ev_wg0, st));
   }
+  if (m->zero_early == 3) { CK(cudaStreamWaitEvent(st, m->ev_dhzero, 0)); m->dh_clean = true; }      // the fills are joined behind the weight gradients
   PH_END(m, PH_WGRAD);
   return 0;
 }
