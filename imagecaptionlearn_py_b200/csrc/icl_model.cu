@@ -1987,22 +1987,31 @@ static int rec_backward_cluster(icl_model* m) {
   // are ordered by chain length (the longest sequences come first), so: the first n8 tiles get 8-CTA clusters, the last n2 tiles
   // (a handful of steps each) 2-CTA clusters, the rest 4 -- the split that minimises the longest chain time under the SM budget.
   // Three concurrent launches (clusters are independent of each other).
-  const int tiles = (m->n_active[0] + 127) / 128;
-  auto chain = [&](int t) { int k = 0; while (k < m->Tmax && m->n_active[k] > t * 128) k++; return k; };   // steps of tile t
-  int n8 = 0, n2 = 0;
+  // Rows per tile: 128, or 64 when that still fits 8-CTA clusters for every chain (batches of <= 512 sequences: 2 x 8 x 8 = 128
+  // CTAs): twice as many independent chains, each with half the park / pull / cell work per step (ICL_BPTT_TM forces one)
+  int best_tm = 128, n8 = 0, n2 = 0;
   {
-    const double t8 = 12.0, t4 = 20.0, t2 = 35.0;
     double best = 1e30;
     int best_ctas = 1 << 30;
     const int budget = m->n_sms - 8;                 // a few SMs of slack: exactly 148 CTAs measured 0.41 ms, 140 CTAs 0.36 ms
-    for (int a8 = 0; a8 <= tiles; a8++)
-      for (int a2 = 0; a8 + a2 <= tiles; a2++) {
-        const int a4 = tiles - a8 - a2, ctas = 2 * (8 * a8 + 4 * a4 + 2 * a2);
-        if (ctas > budget && !(a8 == 0 && a2 == tiles)) continue;
-        const double cost = std::max({a8 ? chain(0) * t8 : 0.0, a4 ? chain(a8) * t4 : 0.0, a2 ? chain(a8 + a4) * t2 : 0.0});
-        if (cost < best - 1e-9 || (cost < best + 1e-9 && ctas < best_ctas)) { best = cost; best_ctas = ctas; n8 = a8; n2 = a2; }
-      }
+    const int force_tm = getenv("ICL_BPTT_TM") ? atoi(getenv("ICL_BPTT_TM")) : 0;
+    for (int tm : {128, 64}) {
+      if (force_tm && tm != force_tm) continue;
+      const int tiles = (m->n_active[0] + 127) / 128 * (128 / tm);
+      auto chain = [&](int t) { int k = 0; while (k < m->Tmax && (m->n_active[k] + 127) / 128 * 128 > t * tm) k++; return k; };   // steps of tile t
+      // measured per-step times of a (tile rows, cluster size) pair, us (tm = 64: half the pull / cell work of a step)
+      const double t8 = tm == 128 ? 12.0 : 8.7, t4 = tm == 128 ? 20.0 : 14.0, t2 = tm == 128 ? 35.0 : 26.0;
+      for (int a8 = 0; a8 <= tiles; a8++)
+        for (int a2 = 0; a8 + a2 <= tiles; a2++) {
+          const int a4 = tiles - a8 - a2, ctas = 2 * (8 * a8 + 4 * a4 + 2 * a2);
+          if (ctas > budget && !(a8 == 0 && a2 == tiles && tm == 128)) continue;
+          const double cost = std::max({a8 ? chain(0) * t8 : 0.0, a4 ? chain(a8) * t4 : 0.0, a2 ? chain(a8 + a4) * t2 : 0.0});
+          if (cost < best - 1e-9 || (cost < best + 1e-9 && ctas < best_ctas)) { best = cost; best_ctas = ctas; n8 = a8; n2 = a2; best_tm = tm; }
+        }
+    }
   }
+  const int tm = best_tm, tiles = (m->n_active[0] + 127) / 128 * (128 / tm);
+  a.tm = tm;
   if (const char* e = getenv("ICL_BPTT_CLUSTER_CS")) { n2 = 0; n8 = atoi(e) == 8 ? tiles : atoi(e) == 4 ? 0 : n8; }
   if (const char* e = getenv("ICL_BPTT_N8")) { n8 = std::max(0, std::min(tiles, atoi(e))); n2 = std::min(n2, tiles - n8); }
   if (const char* e = getenv("ICL_BPTT_N2")) n2 = std::max(0, std::min(tiles - n8, atoi(e)));

@@ -275,6 +275,7 @@ struct BpttClusterArgs {
   const int* off; const int* nact;       // [Tmax+1] step offsets / running rows
   int H, Tmax, round_ops;
   int tile0;                            // first row tile of this launch (the launch covers tiles [tile0, tile0 + gridDim.y / 2))
+  int tm;                               // rows per tile: 128 or 64
   long long* trace; int trace_cta;      // optional bring-up trace (see Tracer): CTA index = y * gridDim.x + x
 };
 
@@ -292,11 +293,14 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bptt_cluster(const __grid_con
   const int H = g.H, Tmax = g.Tmax, HQ = H >> 2;
   const int rank = (int)cluster_ctarank();
   // grid.y = 2 * tiles with the direction in the low bit: the long chains (low tiles) of BOTH directions are scheduled first
-  const int m0 = (g.tile0 + (blockIdx.y >> 1)) * 128, d = blockIdx.y & 1;
+  // g.tm = rows of a tile: 128, or 64 for small batches (twice as many independent chains, half the park / pull / cell work per
+  // step; the A box still carries 128 rows and the upper 64 accumulator rows are ignored -- the tensor pipe is idle anyway)
+  const int TM = g.tm;
+  const int m0 = (g.tile0 + (blockIdx.y >> 1)) * TM, d = blockIdx.y & 1;
   const int total_kb = (4 * H + 31) / 32, kb_per = (total_kb + BC_CS - 1) / BC_CS;
   const int kb0 = rank * kb_per, num_kb = max(0, min(kb_per, total_kb - kb0));
   const int nacc = (H + BP_BN - 1) / BP_BN;                                   // accumulators in use (<= BC_NACC)
-  constexpr int ROWS_OWN = 128 / BC_CS;
+  const int ROWS_OWN = TM / BC_CS;
 
   for (int i = threadIdx.x; i <= Tmax; i += blockDim.x) { s_off[i] = g.off[i]; s_n[i] = g.nact[i]; }
   if (threadIdx.x == 0) {
@@ -332,7 +336,9 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bptt_cluster(const __grid_con
   }
   // first step in which this tile has running rows (n_k grows as k decreases)
   int k_first = -1;
-  for (int k = Tmax - 1; k >= 0; k--) if (m0 < s_n[k]) { k_first = k; break; }
+  // (step blocks are padded to 128 rows and the pad rows of dZ must be written as zeros: with 64-row tiles the upper half of a
+  // block's last 128 rows may hold no running row at all and still has to be visited)
+  for (int k = Tmax - 1; k >= 0; k--) if (m0 < ((s_n[k] + 127) & ~127)) { k_first = k; break; }
 
   // L2 prefetch of the cell-backward operands of step k for my rows.  The rows of a CTA are contiguous in the step-major layout, so
   // each operand is ONE region: four bulk prefetches per step (two halves of the gate rows, dH, c) from four lanes of warp 2.  (One
@@ -406,7 +412,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bptt_cluster(const __grid_con
         const uint32_t dst = base + (uint32_t)((q * 32 + lane) * BC_PARK_LD) * 4;
         if (num_kb > 0) { mbar_wait(tmem_full, nfull & 1); tc_fence_after(); }
         tr.ev(1, k, 0);
-        for (int ac = 0; ac < nacc; ac++) {
+        for (int ac = 0; ac < nacc && q * 32 < TM; ac++) {           // rows >= TM of the accumulator belong to nobody
 #pragma unroll 1
           for (int c = half * 32; c < BP_BN; c += 64) {
             uint32_t r[32];
