@@ -162,8 +162,8 @@ struct icl_model {
   int64_t seq_gid0 = 0, ex_gid0 = 0;
   std::vector<int> n_active, off;
   bool resident = false;
-  cudaStream_t stream = nullptr, aux = nullptr, aux2 = nullptr, aux3 = nullptr;      // aux2: the heads' weight gradients
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaStream_t stream = nullptr, aux = nullptr, aux2 = nullptr, aux3 = nullptr, aux4 = nullptr;      // aux2: the heads' weight gradients
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_join3 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   bool G_external = false;             // the gradient buffer belongs to the caller (symmetric memory, icl_adopt_grad_buffer)
   cudaEvent_t ev_heads = nullptr;      // recorded when the heads' parameter gradients are complete (before the BPTT)
   cudaEvent_t ev_wg0 = nullptr;        // recorded when the forward direction's LSTM weight gradient is complete (before the backward direction's)
@@ -816,7 +816,8 @@ extern "C" void icl_destroy(icl_model* m) {
   if (m->aux) cudaStreamDestroy(m->aux);
   if (m->aux2) cudaStreamDestroy(m->aux2);
   if (m->aux3) cudaStreamDestroy(m->aux3);
-  for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_join2, m->ev_t0, m->ev_t1, m->ev_heads, m->ev_wg0, m->ev_packs, m->ev_side, m->ev_loss, m->ev_hfork, m->ev_zfork, m->ev_zero, m->ev_dhzero}) if (e) cudaEventDestroy(e);
+  if (m->aux4) cudaStreamDestroy(m->aux4);
+  for (cudaEvent_t e : {m->ev_fork, m->ev_join, m->ev_join2, m->ev_join3, m->ev_t0, m->ev_t1, m->ev_heads, m->ev_wg0, m->ev_packs, m->ev_side, m->ev_loss, m->ev_hfork, m->ev_zfork, m->ev_zero, m->ev_dhzero}) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : m->ev_dz) if (e) cudaEventDestroy(e);
   for (int i = 0; i < PH_N; i++) for (int j = 0; j < 2; j++) if (m->ev_ph[i][j]) cudaEventDestroy(m->ev_ph[i][j]);
   delete m;
@@ -1007,9 +1008,11 @@ extern "C" int icl_create(const icl_config* cfg, icl_model** out) {
   CKD(cudaStreamCreateWithFlags(&m->aux, cudaStreamNonBlocking));
   CKD(cudaStreamCreateWithFlags(&m->aux2, cudaStreamNonBlocking));
   CKD(cudaStreamCreateWithFlags(&m->aux3, cudaStreamNonBlocking));
+  CKD(cudaStreamCreateWithFlags(&m->aux4, cudaStreamNonBlocking));
   CKD(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
   CKD(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
   CKD(cudaEventCreateWithFlags(&m->ev_join2, cudaEventDisableTiming));
+  CKD(cudaEventCreateWithFlags(&m->ev_join3, cudaEventDisableTiming));
   CKD(cudaEventCreateWithFlags(&m->ev_heads, cudaEventDisableTiming));
   CKD(cudaEventCreateWithFlags(&m->ev_wg0, cudaEventDisableTiming));
   CKD(cudaEventCreateWithFlags(&m->ev_packs, cudaEventDisableTiming));
@@ -1987,39 +1990,43 @@ static int rec_backward_cluster(icl_model* m) {
   // are ordered by chain length (the longest sequences come first), so: the first n8 tiles get 8-CTA clusters, the last n2 tiles
   // (a handful of steps each) 2-CTA clusters, the rest 4 -- the split that minimises the longest chain time under the SM budget.
   // Three concurrent launches (clusters are independent of each other).
-  // Rows per tile: 128, or 64 when that still fits 8-CTA clusters for every chain (batches of <= 512 sequences: 2 x 8 x 8 = 128
-  // CTAs): twice as many independent chains, each with half the park / pull / cell work per step (ICL_BPTT_TM forces one)
-  int best_tm = 128, n8 = 0, n2 = 0;
+  // Tile shapes.  The first s 128-row blocks (the longest chains) may be cut into 64-row tiles on 8-CTA clusters: twice the
+  // independent chains, half the park / pull / cell work per step (12 -> 9 us), for 16 CTAs per block and direction instead of 8.
+  // Batches of <= 512 sequences cut everything (2 x 8 x 8 = 128 CTAs); larger batches have no CTAs to spare.  The search below minimises the longest chain time over (s, n8, n4, n2) under the SM budget.
+  const int blocks = (m->n_active[0] + 127) / 128;
+  auto chain = [&](int row) { int k = 0; while (k < m->Tmax && (m->n_active[k] + 127) / 128 * 128 > row) k++; return k; };   // steps of the tile starting at `row`
+  int ns = 0, n8 = 0, n2 = 0;
   {
+    const double t64 = 8.7, t8 = 12.0, t4 = 20.0, t2 = 35.0;       // measured us per step
     double best = 1e30;
     int best_ctas = 1 << 30;
     const int budget = m->n_sms - 8;                 // a few SMs of slack: exactly 148 CTAs measured 0.41 ms, 140 CTAs 0.36 ms
-    const int force_tm = getenv("ICL_BPTT_TM") ? atoi(getenv("ICL_BPTT_TM")) : 0;
-    for (int tm : {128, 64}) {
-      if (force_tm && tm != force_tm) continue;
-      const int tiles = (m->n_active[0] + 127) / 128 * (128 / tm);
-      auto chain = [&](int t) { int k = 0; while (k < m->Tmax && (m->n_active[k] + 127) / 128 * 128 > t * tm) k++; return k; };   // steps of tile t
-      // measured per-step times of a (tile rows, cluster size) pair, us (tm = 64: half the pull / cell work of a step)
-      const double t8 = tm == 128 ? 12.0 : 8.7, t4 = tm == 128 ? 20.0 : 14.0, t2 = tm == 128 ? 35.0 : 26.0;
-      for (int a8 = 0; a8 <= tiles; a8++)
-        for (int a2 = 0; a8 + a2 <= tiles; a2++) {
-          const int a4 = tiles - a8 - a2, ctas = 2 * (8 * a8 + 4 * a4 + 2 * a2);
-          if (ctas > budget && !(a8 == 0 && a2 == tiles && tm == 128)) continue;
-          const double cost = std::max({a8 ? chain(0) * t8 : 0.0, a4 ? chain(a8) * t4 : 0.0, a2 ? chain(a8 + a4) * t2 : 0.0});
-          if (cost < best - 1e-9 || (cost < best + 1e-9 && ctas < best_ctas)) { best = cost; best_ctas = ctas; n8 = a8; n2 = a2; best_tm = tm; }
+    const int force_tm = getenv("ICL_BPTT_TM") ? atoi(getenv("ICL_BPTT_TM")) : 0;      // 128: never cut, 64: cut every block
+    const bool mixed = getenv("ICL_BPTT_MIXED") && atoi(getenv("ICL_BPTT_MIXED")) != 0;
+    for (int s = 0; s <= blocks; s++) {
+      if ((force_tm == 128 && s != 0) || (force_tm == 64 && s != blocks)) continue;
+      // all or nothing unless asked for (ICL_BPTT_MIXED=1): the model prefers cutting only the first block of a 1024-sequence batch
+      // (rel_cross512: 204 vs 240 us), measured it is slower (rec_bwd 0.214 -> 0.259 ms with 136 instead of 104 CTAs)
+      if (s != 0 && s != blocks && !mixed) continue;
+      const int rest = blocks - s;
+      for (int a8 = 0; a8 <= rest; a8++)
+        for (int a2 = 0; a8 + a2 <= rest; a2++) {
+          const int a4 = rest - a8 - a2, ctas = 2 * (16 * s + 8 * a8 + 4 * a4 + 2 * a2);
+          if (ctas > budget && !(s == 0 && a8 == 0 && a2 == rest)) continue;
+          const double cost = std::max({s ? chain(0) * t64 : 0.0, a8 ? chain(128 * s) * t8 : 0.0, a4 ? chain(128 * (s + a8)) * t4 : 0.0,
+                                        a2 ? chain(128 * (s + a8 + a4)) * t2 : 0.0});
+          if (cost < best - 1e-9 || (cost < best + 1e-9 && ctas < best_ctas)) { best = cost; best_ctas = ctas; ns = s; n8 = a8; n2 = a2; }
         }
     }
   }
-  const int tm = best_tm, tiles = (m->n_active[0] + 127) / 128 * (128 / tm);
-  a.tm = tm;
-  if (const char* e = getenv("ICL_BPTT_CLUSTER_CS")) { n2 = 0; n8 = atoi(e) == 8 ? tiles : atoi(e) == 4 ? 0 : n8; }
-  if (const char* e = getenv("ICL_BPTT_N8")) { n8 = std::max(0, std::min(tiles, atoi(e))); n2 = std::min(n2, tiles - n8); }
-  if (const char* e = getenv("ICL_BPTT_N2")) n2 = std::max(0, std::min(tiles - n8, atoi(e)));
-  const int n4 = tiles - n8 - n2;
-  static const int trace_cs = getenv("ICL_TRACE_CS") ? atoi(getenv("ICL_TRACE_CS")) : 8;     // bring-up trace: one of the three launches
-  auto launch = [&](int cs, int tile0, int ntiles, cudaStream_t s) -> int {
-    a.tile0 = tile0;
-    a.trace = cs == trace_cs ? m->rp_trace : nullptr;
+  if (const char* e = getenv("ICL_BPTT_CLUSTER_CS")) { ns = 0; n2 = 0; n8 = atoi(e) == 8 ? blocks : atoi(e) == 4 ? 0 : n8; }
+  if (const char* e = getenv("ICL_BPTT_N8")) { n8 = std::max(0, std::min(blocks - ns, atoi(e))); n2 = std::min(n2, blocks - ns - n8); }
+  if (const char* e = getenv("ICL_BPTT_N2")) n2 = std::max(0, std::min(blocks - ns - n8, atoi(e)));
+  const int n4 = blocks - ns - n8 - n2;
+  static const int trace_cs = getenv("ICL_TRACE_CS") ? atoi(getenv("ICL_TRACE_CS")) : 8;     // bring-up trace: one of the launches
+  auto launch = [&](int cs, int tm, int row0, int ntiles, cudaStream_t s) -> int {
+    a.row0 = row0; a.tm = tm;
+    a.trace = (cs == trace_cs && tm == 128) ? m->rp_trace : nullptr;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(cs, (unsigned)(2 * ntiles), 1);
     cfg.blockDim = dim3(BC_THREADS); cfg.dynamicSmemBytes = BC_SMEM; cfg.stream = s;
@@ -2034,20 +2041,20 @@ static int rec_backward_cluster(icl_model* m) {
     return 0;
   };
   // the group with the longest chains stays on the main stream; the others fork to the side streams and join
-  struct Grp { int cs, t0, n; } grp[3] = {{8, 0, n8}, {4, n8, n4}, {2, n8 + n4, n2}};
-  cudaStream_t side[2] = {m->aux, m->aux3};
-  cudaEvent_t join[2] = {m->ev_join, m->ev_join2};
+  struct Grp { int cs, tm, row0, n; } grp[4] = {{8, 64, 0, 2 * ns}, {8, 128, 128 * ns, n8}, {4, 128, 128 * (ns + n8), n4}, {2, 128, 128 * (ns + n8 + n4), n2}};
+  cudaStream_t side[3] = {m->aux, m->aux3, m->aux4};
+  cudaEvent_t join[3] = {m->ev_join, m->ev_join2, m->ev_join3};
   int used = 0, first = -1;
-  for (int i = 0; i < 3; i++) if (grp[i].n > 0 && first < 0) first = i;
+  for (int i = 0; i < 4; i++) if (grp[i].n > 0 && first < 0) first = i;
   CK(cudaEventRecord(m->ev_fork, st));
-  for (int i = 0; i < 3; i++) {
+  for (int i = 0; i < 4; i++) {
     if (grp[i].n == 0 || i == first) continue;
     CK(cudaStreamWaitEvent(side[used], m->ev_fork, 0));
-    CKI(launch(grp[i].cs, grp[i].t0, grp[i].n, side[used]));
+    CKI(launch(grp[i].cs, grp[i].tm, grp[i].row0, grp[i].n, side[used]));
     CK(cudaEventRecord(join[used], side[used]));
     used++;
   }
-  CKI(launch(grp[first].cs, grp[first].t0, grp[first].n, st));
+  CKI(launch(grp[first].cs, grp[first].tm, grp[first].row0, grp[first].n, st));
   for (int i = 0; i < used; i++) CK(cudaStreamWaitEvent(st, join[i], 0));
   return 0;
 }

@@ -274,7 +274,7 @@ struct BpttClusterArgs {
   float* Z[2]; const float* Cc[2]; const float* dHout[2]; float* dcc[2];
   const int* off; const int* nact;       // [Tmax+1] step offsets / running rows
   int H, Tmax, round_ops;
-  int tile0;                            // first row tile of this launch (the launch covers tiles [tile0, tile0 + gridDim.y / 2))
+  int row0;                             // first row of this launch (it covers gridDim.y / 2 tiles of tm rows from there)
   int tm;                               // rows per tile: 128 or 64
   long long* trace; int trace_cta;      // optional bring-up trace (see Tracer): CTA index = y * gridDim.x + x
 };
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(BC_THREADS, 1) k_bptt_cluster(const __grid_con
   // g.tm = rows of a tile: 128, or 64 for small batches (twice as many independent chains, half the park / pull / cell work per
   // step; the A box still carries 128 rows and the upper 64 accumulator rows are ignored -- the tensor pipe is idle anyway)
   const int TM = g.tm;
-  const int m0 = (g.tile0 + (blockIdx.y >> 1)) * TM, d = blockIdx.y & 1;
+  const int m0 = g.row0 + (blockIdx.y >> 1) * TM, d = blockIdx.y & 1;
   const int total_kb = (4 * H + 31) / 32, kb_per = (total_kb + BC_CS - 1) / BC_CS;
   const int kb0 = rank * kb_per, num_kb = max(0, min(kb_per, total_kb - kb0));
   const int nacc = (H + BP_BN - 1) / BP_BN;                                   // accumulators in use (<= BC_NACC)
