@@ -1792,9 +1792,11 @@ static int zero_backward_buffers(icl_model* m, cudaStream_t st, int max_blocks =
   const int H = m->H;
   const size_t dh = (which & 2) ? (size_t)m->NtokP * H * 4 : 0, dc = (which & 2) ? (size_t)m->S * H * 4 : 0, g = (which & 1) ? (size_t)m->n_params * 4 : 0;
   if (dh + dc + g == 0) return 0;
-  // narrow side-stream fills (max_blocks < 0 = sized here): a 512-thread CTA clears ~14 GB/s; enough of them to be done in ~100 us,
-  // i.e. inside the kernel they run beside (measured: 20 CTAs for the 100 MB of the multitask config took longer than its weight-gradient GEMMs)
-  if (max_blocks < 0) max_blocks = (int)std::min<size_t>(296, std::max<size_t>(20, (2 * dh + 2 * dc + g) / (1400u << 10)));
+  // narrow side-stream fills (max_blocks < 0 = sized here): a 512-thread CTA clears ~14 GB/s; 20 CTAs (the SMs a persistent recurrence
+  // leaves idle) or as many as clear the lot in ~200 us, i.e. inside the recurrence they run beside.  Measured beside K2 against the
+  // full-width launch (the default, ICL_ZERO_BLOCKS=0): nonvis512 -1.2 %, card2048 -0.4 %, but rel_cross512 +4.5 %, multitask512 +2.7 %
+  // (their larger fills outlast the recurrence when narrow): not the default.
+  if (max_blocks < 0) max_blocks = (int)std::min<size_t>(296, std::max<size_t>(20, (2 * dh + 2 * dc + g) / (3u << 20)));
   CK(zero_multi_async({{m->dHout[0], dh}, {m->dHout[1], dh}, {m->G, g}, {m->dcc[0], dc}, {m->dcc[1], dc}}, st, max_blocks));
   LAUNCHED(m);
   return 0;
