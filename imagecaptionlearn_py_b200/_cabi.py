@@ -66,7 +66,7 @@ SYMBOLS = ["icl_last_error", "icl_version", "icl_create", "icl_destroy", "icl_se
            "icl_sync", "icl_get_lstm_outputs", "icl_get_batch_input", "icl_get_activation", "icl_rec_trace", "icl_debug_mask", "icl_gemm",
            "icl_kernel_launches", "icl_last_step_ms", "icl_phase_ms", "icl_copy_bytes", "icl_batch_stats", "icl_train_async",
            "icl_poll_stats", "icl_set_optimizer_slot", "icl_optimizer_slots",
-           "icl_set_loss_weights", "icl_apply_update_ex", "icl_set_token_table", "icl_set_box_table", "icl_grad_split", "icl_wait_head_grads", "icl_grad_split_lstm", "icl_wait_fw_lstm_grads", "icl_join_side_work", "icl_debug_poison_recurrence", "icl_adopt_grad_buffer", "icl_nvls_allreduce", "icl_crc32c", "icl_pack_rows", "icl_head_factor_stats", "icl_set_phase_timing"]
+           "icl_set_loss_weights", "icl_apply_update_ex", "icl_set_token_table", "icl_set_box_table", "icl_grad_split", "icl_wait_head_grads", "icl_grad_split_lstm", "icl_wait_fw_lstm_grads", "icl_join_side_work", "icl_debug_poison_recurrence", "icl_adopt_grad_buffer", "icl_nvls_allreduce", "icl_crc32c", "icl_pack_rows", "icl_head_factor_stats", "icl_set_phase_timing", "icl_group_rows"]
 N_PHASES = 8
 PHASES = ("prep", "proj_gemm", "rec_fwd", "heads_fwd", "heads_bwd", "rec_bwd", "wgrad", "update")
 
@@ -130,6 +130,7 @@ def lib():
                                C.c_void_p, C.c_int]
         L.icl_phase_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.icl_set_phase_timing.argtypes = [C.c_void_p, C.c_int]
+        L.icl_group_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(C.c_int32)]
         L.icl_copy_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.icl_batch_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
         L.icl_kernel_launches.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]

@@ -428,6 +428,47 @@ static void csr_lists(int B, int G, const int* of, int* start, int* mem) {
 }
 static size_t dtype_size(int dt) { return (dt == ICL_F64 || dt == ICL_I64) ? 8 : 4; }
 
+// Distinct boxes of a batch: row r is (box-table row number | the xsz bytes of its host box row) + the bsz bytes of its b_feats row.
+// Table rows are compared as they are grouped.  Host rows (16 KB each) are grouped by a SAMPLED hash alone, then every row is
+// compared in full with its group's first row on the worker pool (8 MB of memcmp per 512 pairs, in parallel); only if two different
+// rows shared a hash is the grouping redone with the exact comparison inside (tests/test_cabi_cpu.py builds such rows).
+static void group_box_rows(int B, const char* xsrc, size_t xsz, const int32_t* table_rows, const char* bsrc, size_t bsz, int* b_of,
+                           std::vector<int>& rep_b) {
+  std::vector<uint64_t> key(B);
+  const int per = 32;
+  host_pool().run((B + per - 1) / per, [&](int it) {
+    for (int r = it * per; r < std::min(B, (it + 1) * per); r++) {
+      uint64_t k = table_rows ? mix64(0x3c6ef372fe94f82bull, (uint64_t)table_rows[r]) : hash_sampled(xsrc + r * xsz, xsz);
+      if (bsz) k = hash_bytes(bsrc + r * bsz, bsz, k);
+      key[r] = k;
+    }
+  });
+  auto same_box = [&](int a, int c) {
+    if (table_rows ? table_rows[a] != table_rows[c] : memcmp(xsrc + a * xsz, xsrc + c * xsz, xsz) != 0) return false;
+    return bsz == 0 || memcmp(bsrc + a * bsz, bsrc + c * bsz, bsz) == 0;
+  };
+  group_rows(B, key, [&](int a, int c) { return table_rows ? same_box(a, c) : true; }, b_of, rep_b);
+  if (!table_rows) {
+    std::atomic<int> mismatch{0};
+    host_pool().run((B + 15) / 16, [&](int it) {
+      for (int r = it * 16; r < std::min(B, (it + 1) * 16); r++)
+        if (rep_b[b_of[r]] != r && !same_box(r, rep_b[b_of[r]])) mismatch++;
+    });
+    if (mismatch.load()) group_rows(B, key, same_box, b_of, rep_b);
+  }
+}
+// Host-only test hook (no device needed): the grouping icl_upload applies to the box rows of an affinity batch.
+// group_of[r] = group of row r in order of first appearance; returns the number of groups through n_groups.
+extern "C" int icl_group_rows(const void* rows, int64_t n_rows, int64_t row_bytes, int32_t* group_of, int32_t* n_groups) {
+  if (!rows || !group_of || !n_groups || n_rows < 0 || row_bytes <= 0) return fail("icl_group_rows: bad argument");
+  std::vector<int> rep;
+  std::vector<int> of((size_t)n_rows);
+  group_box_rows((int)n_rows, (const char*)rows, (size_t)row_bytes, nullptr, nullptr, 0, of.data(), rep);
+  for (int64_t r = 0; r < n_rows; r++) group_of[r] = of[r];
+  *n_groups = (int32_t)rep.size();
+  return 0;
+}
+
 static void slot_plan(const icl_head_config& c, std::vector<int>& kinds /*index id or -1..-3*/) {
   // nn_utils/core.py:377-433.  -1 feats, -2 box, -3 bfeats
   kinds = {ICL_FIRST_I_BW, ICL_LAST_I_FW};
@@ -1415,29 +1456,7 @@ extern "C" int icl_upload(icl_model* m, const icl_batch* b) {
         for (const int* ix : ixs) if (memcmp(ix + a * 3, ix + c * 3, 12) != 0) return false;
         return fsz == 0 || memcmp(fsrc + a * fsz, fsrc + c * fsz, fsz) == 0;
       }, m_of, rep_m);
-      const int per = 32;
-      host_pool().run((B + per - 1) / per, [&](int it) {
-        for (int r = it * per; r < std::min(B, (it + 1) * per); r++) {
-          uint64_t k = box_table_rows ? mix64(0x3c6ef372fe94f82bull, (uint64_t)hb.box_rows[r]) : hash_sampled(xsrc + r * xsz, xsz);
-          if (bsz) k = hash_bytes(bsrc + r * bsz, bsz, k);
-          key[r] = k;
-        }
-      });
-      auto same_box = [&](int a, int c) {
-        if (box_table_rows ? hb.box_rows[a] != hb.box_rows[c] : memcmp(xsrc + a * xsz, xsrc + c * xsz, xsz) != 0) return false;
-        return bsz == 0 || memcmp(bsrc + a * bsz, bsrc + c * bsz, bsz) == 0;
-      };
-      // host rows: group by the sampled hash alone, then compare every row with its group's first row IN PARALLEL (8 MB of memcmp
-      // per 512 pairs); only if two different rows shared a hash (never seen) is the grouping redone with the exact test inside
-      group_rows(B, key, [&](int a, int c) { return box_table_rows ? same_box(a, c) : true; }, b_of, rep_b);
-      if (!box_table_rows) {
-        std::atomic<int> mismatch{0};
-        host_pool().run((B + 15) / 16, [&](int it) {
-          for (int r = it * 16; r < std::min(B, (it + 1) * 16); r++)
-            if (rep_b[b_of[r]] != r && !same_box(r, rep_b[b_of[r]])) mismatch++;
-        });
-        if (mismatch.load()) group_rows(B, key, same_box, b_of, rep_b);
-      }
+      group_box_rows(B, box_table_rows ? nullptr : xsrc, xsz, box_table_rows ? hb.box_rows : nullptr, bsrc, bsz, b_of, rep_b);
       h.Mu = (int)rep_m.size(); h.Nu = (int)rep_b.size();
       // reference-shaped TRAINING batches carry one copy of the caption per pair (nn_utils/data.py:397-403: every copy draws its own
       // dropout masks), so their mentions do not repeat and only the box half (4096 of the 5552 columns) collapses; prediction

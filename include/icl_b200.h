@@ -182,6 +182,8 @@ int icl_get_batch_input(icl_model* m, int head, float* host_BD);         /* conc
    replaces: nn_utils/core.py:421-433,439): factorised / distinct mentions / distinct boxes of the resident batch, totals[3] over all
    uploads = {batches factorised, their distinct mentions, their distinct boxes}.  ICL_AFF_FACTOR=0 disables, =2 forces it. */
 int icl_head_factor_stats(icl_model* m, int head, int32_t* factorised, int32_t* n_mentions, int32_t* n_boxes, int64_t* totals);
+/* host-only (testable without a GPU): groups of byte-identical rows in order of first appearance, as icl_upload finds the distinct box rows */
+int icl_group_rows(const void* rows, int64_t n_rows, int64_t row_bytes, int32_t* group_of, int32_t* n_groups);
 int icl_get_activation(icl_model* m, int head, int layer, float* host_BW);  /* hidden layer output (post-dropout) [B,w] */
 int icl_rec_trace(icl_model* m, int cta, long long* host);               /* bring-up trace of one persistent-kernel CTA */
 int icl_debug_mask(icl_model* m, uint64_t seed, uint32_t stream, int64_t first_idx, int64_t n, float keep, float* host);

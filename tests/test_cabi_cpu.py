@@ -108,3 +108,43 @@ def test_host_row_packing_is_bit_exact(built, src_dtype):
                 assert np.array_equal(h16[off:off + n], want), (start, n, off)
                 assert np.all(h16[:off] == 0x7777) and np.all(h16[off + n:] == 0x7777)
     assert L.icl_pack_rows(None, 0, 4, None, 0) != 0
+
+
+@pytest.mark.parametrize("width", [4096, 64, 33])
+def test_distinct_box_rows_are_found_by_exact_comparison(built, width):
+    """icl_upload finds the distinct box rows of an affinity batch (the factorised layer 1 runs once per distinct box)
+    through icl_group_rows' routine: a SAMPLED hash picks a row's candidate group, a full comparison decides.  Rows that differ only
+    where the hash does not look (32 eight-byte samples of a 16 KB row) must land in different groups; identical rows in the same
+    one; groups are numbered in order of first appearance.  Host code only: no GPU."""
+    import ctypes as C
+    from imagecaptionlearn_py_b200 import _cabi
+    L = _cabi.lib()
+    rng = np.random.default_rng(width)
+    n_distinct, B = 23, 300
+    base = np.maximum(rng.standard_normal((n_distinct, width)) - 0.7, 0).astype(np.float32)       # fc7-like: ~3/4 zeros
+    pick = rng.integers(0, n_distinct, B)
+    rows = base[pick].copy()
+    # adversarial twins: copies of an earlier row changed in ONE float that no hash sample covers (bytes 8..11 of a long row)
+    twins = [40, 41, 150]
+    for t in twins:
+        rows[t] = rows[3]
+        rows[t, 2] += 1.0 + t
+    rows[299] = rows[40]                                                                          # and a true duplicate of a twin
+    want, seen = np.empty(B, np.int32), []
+    for r in range(B):
+        for g, q in enumerate(seen):
+            if np.array_equal(rows[q].view(np.uint32), rows[r].view(np.uint32)):
+                want[r] = g
+                break
+        else:
+            want[r] = len(seen)
+            seen.append(r)
+    got, n = np.full(B, -1, np.int32), C.c_int32(-1)
+    assert L.icl_group_rows(rows.ctypes.data_as(C.c_void_p), B, width * 4, got.ctypes.data_as(C.c_void_p), C.byref(n)) == 0
+    assert n.value == len(seen) and np.array_equal(got, want)
+    assert len({got[t] for t in twins} | {got[3]}) == 4 and got[299] == got[40]
+    # -0.0 and 0.0 are different bytes: separate groups (an extra group, never a wrong merge)
+    z = np.zeros((2, width), np.float32)
+    z[1, 0] = -0.0
+    assert L.icl_group_rows(z.ctypes.data_as(C.c_void_p), 2, width * 4, got.ctypes.data_as(C.c_void_p), C.byref(n)) == 0 and n.value == 2
+    assert L.icl_group_rows(None, 2, 8, got.ctypes.data_as(C.c_void_p), C.byref(n)) != 0
