@@ -1653,7 +1653,7 @@ static int lstm_forward(icl_model* m, float keep_in, uint64_t seed, int training
   int E = m->E, H = m->H;
   long Ntok = m->Ntok, NP = m->NtokP;
   cudaStream_t st = m->stream;
-  if (Ntok == 0) return 0;
+  if (Ntok == 0) return heads_prefetch(m);      // a batch of empty sequences: no recurrence, but the heads still run (on zero rows)
   PH_BEGIN(m, PH_PREP);
   // the pad rows of XH and the zero state in front of step 0 are cleared on the aux stream beside k_prep_x (disjoint rows)
   CK(cudaEventRecord(m->ev_side, st));
