@@ -156,3 +156,35 @@ def test_dedup_batches_address_the_same_tokens():
         for k in a:
             if k not in nn_data.INDEX_NAMES and k not in ("sentences", "seq_lengths"):
                 assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("task", ["nonvis", "card", "rel_intra", "rel_cross", "affinity"])
+@pytest.mark.parametrize("packed", [False, "rows"])
+def test_per_corpus_tables_give_what_per_batch_stacking_gives(monkeypatch, task, packed):
+    """load_batch gathers a batch's labels / mention indices / mention features / caption offsets from per-corpus matrices built
+    once per data_dict; without them (dicts too large for the tables: _TABLE_BYTES_MAX) it stacks the batch's rows out of the
+    dicts as the first version did.  Same arrays bit for bit, same KeyError for an unknown id, and a data_dict whose dicts are
+    replaced gets new tables."""
+    corpus = synth.make_corpus(5, seed=3, E=8, with_boxes=(task == "affinity"), box_width=16)
+    dd = synth.make_data_dict(corpus, task, F=6)
+    ids = synth.example_ids(dd, task)[:37]
+    C = {"nonvis": 2, "card": 12, "rel_intra": 4, "rel_cross": 4, "affinity": 2}[task]
+    import copy
+    dd2 = copy.deepcopy(dd)
+    fast = D.load_batch(ids, dd, task, C, packed=packed)
+    assert dd["_mention_table"][1] is not None and dd["_label_table"][1] is not None
+    monkeypatch.setattr(D, "_TABLE_BYTES_MAX", 0)
+    slow = D.load_batch(ids, dd2, task, C, packed=packed)
+    assert dd2["_mention_table"][1] is None and dd2["_label_table"][1] is None
+    assert set(fast) == set(slow)
+    for k, v in slow.items():
+        assert fast[k].dtype == v.dtype and np.array_equal(fast[k], v), k
+    monkeypatch.undo()
+    for d in (dd, dd2):
+        with pytest.raises(KeyError):
+            D.load_batch(ids[:3] + ["no such mention|no such box" if task == "affinity" else "no such id"], d, task, C, packed=packed)
+    # replaced dicts -> rebuilt tables (same object, different contents would be a caller bug the reference has no answer to either)
+    key = "ij_feats" if "rel" in task else "m_feats"
+    dd["mention_features"] = {m: np.asarray(v) + 1.0 for m, v in dd["mention_features"].items()}
+    again = D.load_batch(ids, dd, task, C, packed=packed)
+    assert np.array_equal(again[key], fast[key] + 1.0)
